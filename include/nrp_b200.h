@@ -1,0 +1,132 @@
+/*
+ * nrp_b200.h -- C ABI of the B200-native Finder-mode repeat-graph builder.
+ *
+ * This library replaces the graph-building internals of ayaanhossain/nrpcalc's Finder mode:
+ *
+ *   reference nrpcalc/base/hgraph.py:23-94    get_repeat_dict      (k-mer -> part-id table)      -> nrp_build
+ *   reference nrpcalc/base/hgraph.py:117-135  get_repeat_cliques   (distinct id tuples)           -> nrp_result_groups / nrp_result_last_single
+ *   reference nrpcalc/base/hgraph.py:157-200  build_homology_graph (part-pair conflict edges)     -> nrp_result_edges
+ *   reference nrpcalc/base/utils.py:37-50     stream_kmers / get_revcomp / stream_min_kmers       -> device code of nrp_build
+ *   reference nrpcalc/base/kmerSetDB.py:177-207  __contains__ / multicheck (background membership) -> nrp_bg_set + nrp_build
+ *
+ * The reference has no FFI; the seam a maintainer would bind is the Python function
+ * hgraph.get_homology_graph (hgraph.py:202-249).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain C types only; every call returns 0 on success or a negative NRP_E_* code, and
+ *     nrp_last_error() returns a thread-local, library-owned message for the last failure;
+ *   - parts are passed in the reference's PROCESSING ORDER (descending last occurrence of the unique,
+ *     upper-cased strings, hgraph.py:11-21 and 218-223) as one ASCII buffer + int64 offsets[n_parts+1];
+ *     a part is identified on the device by its index in that order;
+ *   - k = Lmax + 1 (reference nrpcalc/nrpcalc.py:385), 1 <= k <= 32; characters must be A/C/G/T in
+ *     either case (2-bit alphabet A=0 C=1 G=2 T=3, most significant base first, so that integer
+ *     order equals the reference's string order); anything else must be rejected by the caller;
+ *   - only windows of parts with length >= k are formed here; the host layer submits the parts shorter
+ *     than k (whole-string keys, utils.py:37-40) as separate builds with k = their length;
+ *   - inputs are borrowed for the duration of the call; results stay owned by the context until the
+ *     next nrp_build/nrp_ctx_destroy and are copied into caller-allocated buffers by the getters;
+ *   - one context per device and per host thread; calls on one context must not overlap.
+ */
+#ifndef NRP_B200_H
+#define NRP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRP_OK              0
+#define NRP_E_ARG          -1   /* invalid argument */
+#define NRP_E_CUDA         -2   /* CUDA runtime error */
+#define NRP_E_OOM          -3   /* device allocation failed */
+#define NRP_E_UNSUPPORTED  -4   /* k > 32, more than 2^32-2 records, ... */
+#define NRP_E_STATE        -5   /* getter called without a finished build */
+#define NRP_E_EDGES        -6   /* part-pair expansion exceeds the configured limit */
+
+/* per-part exclusion bits (reference hgraph.py:50-79) */
+#define NRP_FLAG_REPEAT      1  /* two windows share a canonical k-mer (direct or inverted internal repeat) */
+#define NRP_FLAG_PALINDROME  2  /* a window equals its own reverse complement */
+#define NRP_FLAG_BACKGROUND  4  /* a canonical K-window is a background key */
+
+/* indices into nrp_result_counts() */
+#define NRP_C_RECORDS        0  /* (window, part) records of surviving parts that were grouped */
+#define NRP_C_EXCLUDED       1  /* parts with a non-zero flag */
+#define NRP_C_GROUPS         2  /* canonical keys with >= 2 members */
+#define NRP_C_MEMBERS        3  /* total members of those groups */
+#define NRP_C_EDGES          4  /* unique part-pair edges (-1 when edges were not requested) */
+#define NRP_C_PAIRS          5  /* member pairs expanded before dedupe */
+#define NRP_C_CANDIDATES     6  /* records that survived the in-bucket duplicate filter */
+#define NRP_C_RUNS           7  /* pipeline executions (2 when internal repeats forced a second run) */
+#define NRP_C_BUCKETS        8  /* leaf buckets of the radix partition */
+#define NRP_C_OVERSIZED      9  /* leaf buckets larger than the shared-memory filter capacity */
+#define NRP_C_WINDOWS_MAX   10  /* windows of all parts before exclusion */
+#define NRP_C_KEY_BYTES     11  /* 4 or 8 */
+#define NRP_N_COUNTS        16
+
+/* indices into nrp_result_timings() (milliseconds, CUDA events on the context's stream) */
+#define NRP_T_TOTAL          0  /* device-resident inputs -> device-resident results (T_build) */
+#define NRP_T_H2D            1
+#define NRP_T_FLAGS          2
+#define NRP_T_HISTOGRAM      3
+#define NRP_T_SPLIT1         4
+#define NRP_T_SPLIT2         5
+#define NRP_T_FILTER         6
+#define NRP_T_SORT           7
+#define NRP_T_GROUP          8
+#define NRP_T_EDGES          9
+#define NRP_T_ORDER         10  /* first-window ranks + last single window */
+#define NRP_N_TIMINGS       16
+
+typedef struct nrp_ctx nrp_ctx;
+
+int         nrp_version(void);
+const char* nrp_last_error(void);
+
+/* Bind a context to a CUDA device (creates a stream; device buffers grow on demand and are reused). */
+int nrp_ctx_create(int device, nrp_ctx** out);
+int nrp_ctx_destroy(nrp_ctx* ctx);
+int nrp_ctx_device(nrp_ctx* ctx);
+
+/* Tuning knobs used by the tests to force rarely taken paths: name in
+ * {"filter_cap", "leaf_target", "max_level_bits", "max_pairs"}; value <= 0 restores the default. */
+int nrp_ctx_set_option(nrp_ctx* ctx, const char* name, int64_t value);
+
+/* Background (replaces the kmerSetDB membership test, kmerSetDB.py:177-207): n canonical K-mers in the
+ * 2-bit encoding, host memory, any order, duplicates allowed.  A part is excluded iff K <= len(part) and any
+ * canonical K-window of it is in the set (hgraph.py:72-79).  n = 0 or nrp_bg_clear() disables the filter. */
+int nrp_bg_set(nrp_ctx* ctx, const uint64_t* canon_kmers, int64_t n, int K);
+int nrp_bg_clear(nrp_ctx* ctx);
+
+/* Stage one batch of parts on the device (H2D copy unless ascii_on_device != 0; offsets and part_id are
+ * always host arrays).
+ *   ascii, offsets   concatenated parts and their n_parts+1 byte offsets, offsets[0] == 0
+ *   part_id          id of each part (first index in the caller's list); may be NULL when edges are never requested */
+int nrp_load_parts(nrp_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, const uint32_t* part_id, int64_t n_parts,
+                   int ascii_on_device);
+
+/* Build the repeat structure of the staged parts.
+ *   internal_repeats 0: exclude parts with internal direct/inverted repeats or palindromic windows
+ *   want_edges       != 0: also expand groups into unique (id_u < id_v) edges, sorted lexicographically
+ * Synchronous: returns when the results are resident on the device.  May be called repeatedly. */
+int nrp_build(nrp_ctx* ctx, int k, int internal_repeats, int want_edges);
+
+int nrp_result_counts(nrp_ctx* ctx, int64_t out[NRP_N_COUNTS]);
+int nrp_result_timings(nrp_ctx* ctx, double out[NRP_N_TIMINGS]);
+/* flags[n_parts]: NRP_FLAG_* bits per part */
+int nrp_result_flags(nrp_ctx* ctx, uint8_t* flags);
+/* groups with >= 2 members as CSR: indptr[n_groups+1], members[n_members] = part indices in (part, window)
+ * order with multiplicity; first_window[g] = smallest window index of members[indptr[g]] whose canonical
+ * k-mer is the group's key, i.e. the group's rank is (members[indptr[g]], first_window[g]);
+ * keys[g] = the canonical k-mer (may be NULL). */
+int nrp_result_groups(nrp_ctx* ctx, int64_t* indptr, uint32_t* members, uint32_t* first_window, uint64_t* keys);
+/* last_single[n_parts]: largest window index whose canonical k-mer no other record shares, -1 if none
+ * (and -1 for excluded parts) */
+int nrp_result_last_single(nrp_ctx* ctx, int32_t* last_single);
+/* u[n_edges] < v[n_edges], unique, sorted by (u, v) */
+int nrp_result_edges(nrp_ctx* ctx, uint32_t* u, uint32_t* v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRP_B200_H */

@@ -1,0 +1,177 @@
+"""ctypes binding of libnrpb200.so (C ABI declared in include/nrp_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing or no GPU is visible the calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libnrpb200.so')
+
+N_COUNTS = 16
+N_TIMINGS = 16
+COUNT_NAMES = ('records', 'excluded', 'groups', 'members', 'edges', 'pairs', 'candidates', 'runs', 'buckets',
+               'oversized', 'windows_max', 'key_bytes')
+TIMING_NAMES = ('total', 'h2d', 'flags', 'histogram', 'split1', 'split2', 'filter', 'sort', 'group', 'edges', 'order')
+
+FLAG_REPEAT, FLAG_PALINDROME, FLAG_BACKGROUND = 1, 2, 4
+
+E_ARG, E_CUDA, E_OOM, E_UNSUPPORTED, E_STATE, E_EDGES = -1, -2, -3, -4, -5, -6
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__('libnrpb200 error {}: {}'.format(code, message))
+        self.code = code
+
+
+def _declare(lib):
+    c_ctx = ctypes.c_void_p
+    i64, i32 = ctypes.c_int64, ctypes.c_int
+    ptr = ctypes.c_void_p
+    lib.nrp_version.restype = i32
+    lib.nrp_last_error.restype = ctypes.c_char_p
+    sigs = {
+        'nrp_ctx_create': (i32, ctypes.POINTER(c_ctx)),
+        'nrp_ctx_destroy': (c_ctx,),
+        'nrp_ctx_device': (c_ctx,),
+        'nrp_ctx_set_option': (c_ctx, ctypes.c_char_p, i64),
+        'nrp_bg_set': (c_ctx, ptr, i64, i32),
+        'nrp_bg_clear': (c_ctx,),
+        'nrp_load_parts': (c_ctx, ptr, ptr, ptr, i64, i32),
+        'nrp_build': (c_ctx, i32, i32, i32),
+        'nrp_result_counts': (c_ctx, ptr),
+        'nrp_result_timings': (c_ctx, ptr),
+        'nrp_result_flags': (c_ctx, ptr),
+        'nrp_result_groups': (c_ctx, ptr, ptr, ptr, ptr),
+        'nrp_result_last_single': (c_ctx, ptr),
+        'nrp_result_edges': (c_ctx, ptr, ptr),
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = list(argtypes)
+        fn.restype = i32
+    return lib
+
+
+def load_library():
+    """Load libnrpb200.so (built in-tree by `make -C nrpcalc_b200/csrc` or __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(E_STATE, 'CUDA library not built: {} is missing (run __graft_entry__.build())'.format(LIB_PATH))
+        _lib = _declare(ctypes.CDLL(LIB_PATH))
+    return _lib
+
+
+def _check(lib, code):
+    if code != 0:
+        raise NativeError(code, lib.nrp_last_error().decode('utf-8', 'replace'))
+
+
+def _p(array):
+    return None if array is None else ctypes.c_void_p(array.ctypes.data)
+
+
+class BuildResult(object):
+    """Host copies of one nrp_build() result."""
+
+    def __init__(self, counts, timings, flags, indptr, members, first_window, keys, last_single, edges):
+        self.counts = counts
+        self.timings = timings
+        self.flags = flags
+        self.indptr = indptr
+        self.members = members
+        self.first_window = first_window
+        self.keys = keys
+        self.last_single = last_single
+        self.edges = edges
+
+
+class Context(object):
+    """One libnrpb200 context = one CUDA device, one stream, reusable device buffers."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        handle = ctypes.c_void_p()
+        _check(self._lib, self._lib.nrp_ctx_create(int(device), ctypes.byref(handle)))
+        self._h = handle
+        self.device = int(device)
+        self.n_parts = 0
+        self._keep = None
+
+    def close(self):
+        if self._h is not None:
+            self._lib.nrp_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name, value):
+        _check(self._lib, self._lib.nrp_ctx_set_option(self._h, name.encode(), int(value)))
+
+    def set_background(self, canon_kmers, K):
+        if canon_kmers is None or len(canon_kmers) == 0:
+            _check(self._lib, self._lib.nrp_bg_clear(self._h))
+            return
+        keys = np.ascontiguousarray(canon_kmers, dtype=np.uint64)
+        _check(self._lib, self._lib.nrp_bg_set(self._h, _p(keys), keys.size, int(K)))
+
+    def load_parts(self, ascii_buf, offsets, part_id=None, device_ptr=None):
+        """ascii_buf: uint8 array (host) or None with device_ptr = address of the bytes in device memory."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n_parts = offsets.size - 1
+        if part_id is not None:
+            part_id = np.ascontiguousarray(part_id, dtype=np.uint32)
+            assert part_id.size == n_parts
+        if device_ptr is not None:
+            src, on_device = ctypes.c_void_p(int(device_ptr)), 1
+        else:
+            ascii_buf = np.ascontiguousarray(ascii_buf, dtype=np.uint8)
+            assert ascii_buf.size >= int(offsets[-1])
+            src, on_device = _p(ascii_buf), 0
+        _check(self._lib, self._lib.nrp_load_parts(self._h, src, _p(offsets), _p(part_id), n_parts, on_device))
+        self.n_parts = n_parts
+
+    def build(self, k, internal_repeats, want_edges=True):
+        _check(self._lib, self._lib.nrp_build(self._h, int(k), 1 if internal_repeats else 0, 1 if want_edges else 0))
+
+    def counts(self):
+        out = np.zeros(N_COUNTS, dtype=np.int64)
+        _check(self._lib, self._lib.nrp_result_counts(self._h, _p(out)))
+        return dict(zip(COUNT_NAMES, out.tolist()))
+
+    def timings(self):
+        out = np.zeros(N_TIMINGS, dtype=np.float64)
+        _check(self._lib, self._lib.nrp_result_timings(self._h, _p(out)))
+        return dict(zip(TIMING_NAMES, out.tolist()))
+
+    def fetch(self, want_keys=True):
+        """Copy the whole result of the last build to the host."""
+        counts = self.counts()
+        n = self.n_parts
+        flags = np.zeros(n, dtype=np.uint8)
+        _check(self._lib, self._lib.nrp_result_flags(self._h, _p(flags)))
+        ng, nm = counts['groups'], counts['members']
+        indptr = np.zeros(ng + 1, dtype=np.int64)
+        members = np.zeros(nm, dtype=np.uint32)
+        first_window = np.zeros(ng, dtype=np.uint32)
+        keys = np.zeros(ng, dtype=np.uint64) if want_keys else None
+        _check(self._lib, self._lib.nrp_result_groups(self._h, _p(indptr), _p(members), _p(first_window), _p(keys)))
+        last_single = np.zeros(n, dtype=np.int32)
+        _check(self._lib, self._lib.nrp_result_last_single(self._h, _p(last_single)))
+        edges = None
+        if counts['edges'] >= 0:
+            u = np.zeros(counts['edges'], dtype=np.uint32)
+            v = np.zeros(counts['edges'], dtype=np.uint32)
+            _check(self._lib, self._lib.nrp_result_edges(self._h, _p(u), _p(v)))
+            edges = (u, v)
+        return BuildResult(counts, self.timings(), flags, indptr, members, first_window, keys, last_single, edges)

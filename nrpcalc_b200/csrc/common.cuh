@@ -1,0 +1,175 @@
+// Shared device helpers: 2-bit encoding, canonical k-mers, hashing, byte-tile staging of the part buffer.
+//
+// Replaces reference nrpcalc/base/utils.py:10,37-50 (stream_kmers, get_comp, get_revcomp, stream_min_kmers).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace nrp {
+
+constexpr uint8_t kFlagRepeat = 1, kFlagPalindrome = 2, kFlagBackground = 4;
+
+// ---------------------------------------------------------------------------------------------------
+// hashing: one multiplicative (Fibonacci) hash per key; consecutive bit fields of the product, from the top,
+// select the level-1 bucket, the level-2 bucket and the slot of the in-bucket table.
+__host__ __device__ __forceinline__ uint64_t key_hash(uint64_t key) {
+  key ^= key >> 31;
+  return key * 0x9E3779B97F4A7C15ull;
+}
+// independent hash for choosing the owner GPU of a key (sharded path)
+__host__ __device__ __forceinline__ uint32_t owner_hash(uint64_t key) {
+  key ^= key >> 33; key *= 0xff51afd7ed558ccdull; key ^= key >> 33; key *= 0xc4ceb9fe1a85ec53ull; key ^= key >> 33;
+  return (uint32_t)(key >> 32);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 2-bit alphabet, MSB-first.  ASCII -> code: (c>>1)&3 gives A0 C1 T2 G3 for both cases; t ^ (t>>1) swaps the
+// last two so that A<C<G<T numerically as in the reference's string comparison, and complement is x^3.
+__device__ __forceinline__ uint32_t pack4(uint32_t x) {   // 4 ASCII bytes (first char = lowest byte) -> 8 bits
+  uint32_t t = (x >> 1) & 0x03030303u;
+  uint32_t c = t ^ ((t >> 1) & 0x01010101u);
+  return ((c << 6) | (c >> 4) | (c >> 14) | (c >> 24)) & 0xffu;
+}
+__device__ __forceinline__ uint32_t pack16(uint4 v) {     // 16 ASCII bytes -> 32 bits, first char in the top bits
+  return (pack4(v.x) << 24) | (pack4(v.y) << 16) | (pack4(v.z) << 8) | pack4(v.w);
+}
+
+// reverse complement of a right-aligned 2k-bit value: complement all bits, reverse the 64 bits (BREV), swap
+// the two bits inside each base, shift the k bases that moved to the top back down.
+__device__ __forceinline__ uint64_t revcomp2(uint64_t fwd, int k) {
+  uint64_t b = __brevll(~fwd);
+  b = ((b >> 1) & 0x5555555555555555ull) | ((b & 0x5555555555555555ull) << 1);
+  return b >> (64 - 2 * k);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The part buffer as the kernels see it.  The device copy of `ascii` is padded with >= 64 zero bytes.
+struct Parts {
+  const uint8_t* ascii;
+  const int64_t* off;          // n_parts + 1
+  const uint32_t* tile_first;  // per byte tile: index of the part containing its first byte (n_tiles + 1 entries)
+  int64_t n_parts;
+  int64_t total_len;
+  int uniform_len;             // > 0: every part has exactly this length (fast path, no offsets lookup)
+};
+
+constexpr int kTileBytes = 4096;      // window start positions handled by one CTA
+constexpr int kTileThreads = 512;
+constexpr int kTileItems = kTileBytes / kTileThreads;
+constexpr int kPackedWords = kTileBytes / 16 + 3;   // tile + 32-base halo, rounded up
+constexpr int kSliceCap = 1024;                     // offsets cached per tile (parts overlapping the tile)
+
+struct TileStage {
+  uint32_t packed[kPackedWords + 1];
+  int64_t slice[kSliceCap + 2];
+  int64_t first_part;
+  int n_slice;                 // number of parts cached in `slice` (0 = uniform or overflow -> global search)
+};
+
+// Stage one byte tile: 2-bit pack the bytes [g_lo, g_lo + 4096 + 48) and cache the offsets of its parts.
+__device__ __forceinline__ void tile_load(const Parts& P, int64_t tile, TileStage& s) {
+  const int64_t g_lo = tile * kTileBytes;
+  for (int i = threadIdx.x; i < kPackedWords; i += blockDim.x) {
+    int64_t g = g_lo + 16 * (int64_t)i;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (g < P.total_len + 48) v = *reinterpret_cast<const uint4*>(P.ascii + g);   // buffer is padded and 16B aligned
+    s.packed[i] = pack16(v);
+  }
+  if (P.uniform_len == 0) {
+    int64_t p_lo = P.tile_first[tile];
+    int64_t p_hi = P.tile_first[tile + 1];            // first part of the next tile: covers every part of this one
+    int64_t cnt = p_hi - p_lo + 1;
+    if (cnt > kSliceCap) cnt = 0;
+    if (threadIdx.x == 0) { s.first_part = p_lo; s.n_slice = (int)cnt; }
+    for (int i = threadIdx.x; i <= cnt && cnt > 0; i += blockDim.x) s.slice[i] = P.off[p_lo + i];
+  } else if (threadIdx.x == 0) {
+    s.first_part = g_lo / P.uniform_len;
+    s.n_slice = 0;
+  }
+}
+
+// Part containing byte g and the end offset of that part.  Requires g < total_len.
+__device__ __forceinline__ void tile_locate(const Parts& P, const TileStage& s, int64_t g, int64_t& part, int64_t& end) {
+  if (P.uniform_len > 0) {
+    int64_t p0 = s.first_part;
+    uint32_t rel = (uint32_t)(g - p0 * P.uniform_len);
+    part = p0 + rel / (uint32_t)P.uniform_len;
+    end = (part + 1) * P.uniform_len;
+    return;
+  }
+  if (s.n_slice > 0) {
+    int lo = 0, hi = s.n_slice;                // find last i in [0, n_slice] with slice[i] <= g
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (s.slice[mid] <= g) lo = mid; else hi = mid;
+    }
+    part = s.first_part + lo;
+    end = s.slice[lo + 1];
+    return;
+  }
+  int64_t lo = s.first_part, hi = P.n_parts;   // overflow path: search the global offsets
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (P.off[mid] <= g) lo = mid; else hi = mid;
+  }
+  part = lo;
+  end = P.off[lo + 1];
+}
+
+// Forward value of the k-window that starts `c` bases into the staged tile (right-aligned 2k bits).
+__device__ __forceinline__ uint64_t tile_window(const TileStage& s, int c, int k) {
+  int w = c >> 4;
+  int sh = (c & 15) * 2;
+  uint32_t x0 = s.packed[w], x1 = s.packed[w + 1], x2 = s.packed[w + 2];
+  uint32_t hi = __funnelshift_l(x1, x0, sh);
+  uint32_t lo = __funnelshift_l(x2, x1, sh);
+  uint64_t v = ((uint64_t)hi << 32) | lo;
+  return v >> (64 - 2 * k);
+}
+
+// Canonical k-mer starting at byte g of part-relative validity: returns false when no window starts at g.
+struct Window {
+  uint64_t canon;
+  uint32_t part;
+  bool palindrome;
+};
+__device__ __forceinline__ bool tile_canonical(const Parts& P, const TileStage& s, int64_t tile, int idx, int k, Window& w) {
+  int64_t g = tile * kTileBytes + idx;
+  if (g >= P.total_len) return false;
+  int64_t part, end;
+  tile_locate(P, s, g, part, end);
+  if (g + k > end) return false;
+  uint64_t fwd = tile_window(s, idx, k);
+  uint64_t rc = revcomp2(fwd, k);
+  w.canon = fwd < rc ? fwd : rc;
+  w.palindrome = fwd == rc;
+  w.part = (uint32_t)part;
+  return true;
+}
+
+// first part of every byte tile (variable-length parts only): one thread per tile
+__global__ void k_tile_first_part(const int64_t* off, int64_t n_parts, int64_t total_len, int64_t n_tiles, uint32_t* tile_first) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t > n_tiles) return;
+  if (t == n_tiles) { tile_first[t] = (uint32_t)(n_parts > 0 ? n_parts - 1 : 0); return; }
+  int64_t g = t * kTileBytes;
+  int64_t lo = 0, hi = n_parts;              // last p with off[p] <= g
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (off[mid] <= g) lo = mid; else hi = mid;
+  }
+  tile_first[t] = (uint32_t)lo;
+}
+
+__device__ __forceinline__ uint32_t atomic_cas(uint32_t* a, uint32_t cmp, uint32_t v) { return atomicCAS(a, cmp, v); }
+__device__ __forceinline__ uint64_t atomic_cas(uint64_t* a, uint64_t cmp, uint64_t v) {
+  return (uint64_t)atomicCAS(reinterpret_cast<unsigned long long*>(a), (unsigned long long)cmp, (unsigned long long)v);
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+}  // namespace nrp

@@ -1,0 +1,322 @@
+// The bulk path: canonical k-mer extraction fused with a hash-radix partition into shared-memory sized
+// buckets, and the in-bucket duplicate filter.
+//
+// Replaces the construction of repeat_dict in reference nrpcalc/base/hgraph.py:82-89.  The reference needs
+// the table only to learn which canonical k-mers occur in more than one (window, part) record; every key
+// that occurs once contributes nothing but the singleton tuple (id,).  So instead of sorting all M records
+// we (1) scatter them by the top bits of a multiplicative hash into buckets of a few thousand records
+// (two levels of <= 8 bits, ranks taken with shared-memory atomics -- order inside a bucket is irrelevant),
+// (2) load every bucket into shared memory once, insert its keys into an open-addressing table and keep
+// only the records whose key was seen twice.  What survives is sorted and grouped by the small sort.
+//
+// HBM traffic per record (key K_b bytes + 4-byte part index): ASCII twice, one write by split1, one read and
+// one write by split2, one read by the filter  ->  2*L/W + 4*(K_b+4) bytes, against
+// L/W + (2*ceil(2k/8)+4)*(K_b+4) + K_b for the LSD formulation in SURVEY.md 8d.
+#pragma once
+#include "common.cuh"
+
+namespace nrp {
+
+constexpr int kSplitThreads = kTileThreads;     // 512
+constexpr int kSplitItems = 8;
+constexpr int kSplitTile = kSplitThreads * kSplitItems;   // 4096 records staged per CTA
+constexpr int kMaxLevelBits = 8;
+
+template <typename KeyT>
+struct alignas(16) SplitSmem {
+  KeyT keys[kSplitTile];
+  uint32_t vals[kSplitTile];
+  uint32_t cnt[1 << kMaxLevelBits];
+  uint32_t base[1 << kMaxLevelBits];
+  uint32_t gbase[1 << kMaxLevelBits];
+  uint32_t warp_sums[40];
+  uint32_t total;
+};
+
+// digit of a key at one partition level
+struct HashField {            // a bit field of key_hash: leaf-bucket levels
+  int shift; uint32_t mask;
+  __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return (uint32_t)(key_hash(key) >> shift) & mask; }
+};
+struct OwnerDigit {           // owner GPU of a key (sharded path)
+  uint32_t n_owners;
+  __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return owner_hash(key) % n_owners; }
+};
+
+// Steps shared by both split kernels once every thread holds its records, digits and in-bucket ranks:
+// scan the bucket counts, claim global space for each non-empty bucket with one atomic per (tile, bucket),
+// reorder the tile through shared memory and write each bucket's run contiguously.
+template <typename KeyT, typename DigitFn>
+__device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&key)[kSplitItems], const uint32_t (&val)[kSplitItems],
+                                              const uint32_t (&dr)[kSplitItems], int nb, DigitFn digit_of,
+                                              uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // exclusive scan of cnt[0..nb) by the first nb threads (nb <= 256 <= blockDim)
+  uint32_t c = (int)threadIdx.x < nb ? s.cnt[threadIdx.x] : 0u;
+  uint32_t inc = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31 && wid < 8) s.warp_sums[wid] = inc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { uint32_t t = s.warp_sums[w]; s.warp_sums[w] = run; run += t; }
+    s.total = run;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nb) {
+    s.base[threadIdx.x] = s.warp_sums[wid] + inc - c;
+    if (c) s.gbase[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < kSplitItems; ++e) {
+    if (dr[e] != 0xffffffffu) {
+      uint32_t pos = s.base[dr[e] >> 16] + (dr[e] & 0xffffu);
+      s.keys[pos] = key[e];
+      s.vals[pos] = val[e];
+    }
+  }
+  __syncthreads();
+  const uint32_t total = s.total;
+  for (uint32_t i = threadIdx.x; i < total; i += kSplitThreads) {
+    KeyT kx = s.keys[i];
+    uint32_t d = digit_of((uint64_t)kx);
+    uint32_t dst = s.gbase[d] + (i - s.base[d]);
+    out_keys[dst] = kx;
+    out_vals[dst] = s.vals[i];
+  }
+}
+
+// ---- histogram of leaf buckets straight from the part buffer ------------------------------------------
+// hist has 2^bits entries (bits <= 15): leaf bucket = top `bits` bits of key_hash(canonical k-mer).
+// Persistent CTAs accumulate in shared memory and flush once.
+__global__ void __launch_bounds__(kTileThreads) k_hist_from_ascii(Parts P, const uint8_t* flags, int k, int bits, int64_t n_tiles,
+                                                                 uint32_t* hist) {
+  extern __shared__ uint32_t s_hist[];
+  __shared__ TileStage stage;
+  const int nb = 1 << bits;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) s_hist[i] = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    __syncthreads();
+    tile_load(P, tile, stage);
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < kTileItems; ++e) {
+      Window w;
+      if (tile_canonical(P, stage, tile, threadIdx.x + e * kTileThreads, k, w) && !(flags && flags[w.part]))
+        atomicAdd(&s_hist[key_hash(w.canon) >> (64 - bits)], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    uint32_t v = s_hist[i];
+    if (v) atomicAdd(&hist[i], v);
+  }
+}
+
+// same histogram from records already in HBM (sharded path: after the all-to-all)
+template <typename KeyT>
+__global__ void __launch_bounds__(512) k_hist_from_records(const KeyT* keys, int64_t n, int bits, uint32_t* hist) {
+  extern __shared__ uint32_t s_hist[];
+  const int nb = 1 << bits;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&s_hist[key_hash((uint64_t)keys[i]) >> (64 - bits)], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    uint32_t v = s_hist[i];
+    if (v) atomicAdd(&hist[i], v);
+  }
+}
+
+// ---- level 1: extraction fused with the first split ------------------------------------------------------
+// digit = top r1 bits of the hash (or, with by_owner, owner_hash % n_owners for the sharded path).
+// cursor[d] must hold the start offset of bucket d and is advanced atomically.
+template <typename KeyT>
+__global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, const uint8_t* flags, int k, int r1, int n_owners,
+                                                                  uint32_t part_base, uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SplitSmem<KeyT>& s = *reinterpret_cast<SplitSmem<KeyT>*>(smem_raw);
+  TileStage& stage = *reinterpret_cast<TileStage*>(smem_raw + sizeof(SplitSmem<KeyT>));
+  const int64_t tile = blockIdx.x;
+  const int nb = n_owners > 0 ? n_owners : (1 << r1);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s.cnt[i] = 0;
+  tile_load(P, tile, stage);
+  __syncthreads();
+  KeyT key[kSplitItems];
+  uint32_t val[kSplitItems], dr[kSplitItems];
+#pragma unroll
+  for (int e = 0; e < kSplitItems; ++e) {
+    Window w;
+    dr[e] = 0xffffffffu;
+    key[e] = 0; val[e] = 0;
+    if (tile_canonical(P, stage, tile, threadIdx.x + e * kTileThreads, k, w) && !(flags && flags[w.part])) {
+      uint32_t d = n_owners > 0 ? owner_hash(w.canon) % (uint32_t)n_owners : (uint32_t)(key_hash(w.canon) >> (64 - r1));
+      uint32_t rank = atomicAdd(&s.cnt[d], 1u);
+      key[e] = (KeyT)w.canon;
+      val[e] = part_base + w.part;
+      dr[e] = (d << 16) | rank;
+    }
+  }
+  __syncthreads();
+  if (n_owners > 0)
+    split_scatter<KeyT>(s, key, val, dr, nb, OwnerDigit{(uint32_t)n_owners}, cursor, out_keys, out_vals);
+  else
+    split_scatter<KeyT>(s, key, val, dr, nb, HashField{64 - r1, (1u << r1) - 1u}, cursor, out_keys, out_vals);
+}
+
+// ---- level 2 (or level 1 when the records are already in HBM): segmented split of records ---------------
+// Segment b = level-1 bucket b = records [seg_off[b], seg_off[b+1]); its tiles are numbered from tile_prefix[b].
+// Leaf bucket id = top (r1 + r2) bits of the hash; cursor has 2^(r1+r2) entries.
+template <typename KeyT>
+__global__ void __launch_bounds__(kSplitThreads) k_split_from_records(const KeyT* in_keys, const uint32_t* in_vals,
+                                                                     const uint32_t* seg_off, const uint32_t* tile_prefix, int r1, int r2,
+                                                                     uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SplitSmem<KeyT>& s = *reinterpret_cast<SplitSmem<KeyT>*>(smem_raw);
+  __shared__ uint32_t s_prefix[(1 << kMaxLevelBits) + 1];
+  const int n_seg = 1 << r1;
+  for (int i = threadIdx.x; i <= n_seg; i += blockDim.x) s_prefix[i] = tile_prefix[i];
+  __syncthreads();
+  const uint32_t n_tiles = s_prefix[n_seg];
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int lo = 0, hi = n_seg;                       // last segment with tile_prefix <= tile
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (s_prefix[mid] <= tile) lo = mid; else hi = mid;
+    }
+    const uint32_t seg = (uint32_t)lo;
+    const uint32_t start = seg_off[seg] + (tile - s_prefix[seg]) * kSplitTile;
+    const uint32_t end = min(start + (uint32_t)kSplitTile, seg_off[seg + 1]);
+    for (int i = threadIdx.x; i < (1 << r2); i += blockDim.x) s.cnt[i] = 0;
+    __syncthreads();
+    KeyT key[kSplitItems];
+    uint32_t val[kSplitItems], dr[kSplitItems];
+    const uint32_t mask = (1u << r2) - 1u;
+#pragma unroll
+    for (int e = 0; e < kSplitItems; ++e) {
+      uint32_t idx = start + threadIdx.x + e * kSplitThreads;
+      dr[e] = 0xffffffffu; key[e] = 0; val[e] = 0;
+      if (idx < end) {
+        key[e] = in_keys[idx];
+        val[e] = in_vals[idx];
+        uint32_t d = (uint32_t)(key_hash((uint64_t)key[e]) >> (64 - r1 - r2)) & mask;
+        dr[e] = (d << 16) | atomicAdd(&s.cnt[d], 1u);
+      }
+    }
+    __syncthreads();
+    split_scatter<KeyT>(s, key, val, dr, 1 << r2, HashField{64 - r1 - r2, mask}, cursor + ((size_t)seg << r2), out_keys, out_vals);
+    __syncthreads();
+  }
+}
+
+// tiles per segment -> tile_prefix (n_seg + 1 entries), n_seg <= 256: one CTA
+__global__ void k_segment_tiles(const uint32_t* leaf_off, int r1, int r2, uint32_t* seg_off, uint32_t* tile_prefix) {
+  __shared__ uint32_t tiles[256];
+  const int n_seg = 1 << r1;
+  if ((int)threadIdx.x < n_seg) {
+    uint32_t a = leaf_off[(size_t)threadIdx.x << r2], b = leaf_off[(size_t)(threadIdx.x + 1) << r2];
+    seg_off[threadIdx.x] = a;
+    tiles[threadIdx.x] = (b - a + kSplitTile - 1) / kSplitTile;
+    if ((int)threadIdx.x == n_seg - 1) seg_off[n_seg] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int i = 0; i < n_seg; ++i) { tile_prefix[i] = run; run += tiles[i]; }
+    tile_prefix[n_seg] = run;
+  }
+}
+
+// ---- in-bucket duplicate filter -------------------------------------------------------------------------
+// One CTA per leaf bucket (work-stealing).  Keys go into an open-addressing table in shared memory; a key met
+// again marks its slot.  Records whose slot is marked -- i.e. whose canonical k-mer occurs at least twice --
+// are appended to the candidate list.  Buckets larger than `cap` records are appended whole (the small sort
+// then sees a superset, which is still correct).  EMPTY = all ones is never a canonical k-mer: the reverse
+// complement of T..T is A..A = 0.
+template <typename KeyT, int T, int E>
+__global__ void __launch_bounds__(T) k_filter(const KeyT* keys, const uint32_t* vals, const uint32_t* leaf_off, uint32_t n_leaf,
+                                              int leaf_bits, uint32_t cap, uint32_t* work, KeyT* cand_keys, uint32_t* cand_vals,
+                                              unsigned long long* n_cand, uint32_t* n_oversized) {
+  extern __shared__ unsigned char smem_raw[];
+  KeyT* table = reinterpret_cast<KeyT*>(smem_raw);
+  unsigned char* marked = smem_raw + sizeof(KeyT) * (size_t)(2 * T * E);
+  __shared__ uint32_t s_leaf;
+  const KeyT kEmpty = ~KeyT(0);
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_leaf = atomicAdd(work, 1u);
+    __syncthreads();
+    const uint32_t leaf = s_leaf;
+    if (leaf >= n_leaf) break;
+    const uint32_t lo = leaf_off[leaf];
+    const uint32_t n = leaf_off[leaf + 1] - lo;
+    if (n < 2) continue;
+    if (n > cap) {
+      if (threadIdx.x == 0) atomicAdd(n_oversized, 1u);
+      for (uint32_t i = threadIdx.x; i < n + 31u - ((n - 1u) & 31u) ; i += T) {   // whole warps iterate together
+        bool ok = i < n;
+        uint32_t m = __ballot_sync(0xffffffffu, ok);
+        unsigned long long basepos = 0;
+        if (lane == 0) basepos = atomicAdd(n_cand, (unsigned long long)__popc(m));
+        basepos = __shfl_sync(0xffffffffu, basepos, 0);
+        if (ok) {
+          unsigned long long dst = basepos + __popc(m & lanemask_lt());
+          cand_keys[dst] = keys[lo + i];
+          cand_vals[dst] = vals[lo + i];
+        }
+      }
+      continue;
+    }
+    uint32_t slots = 64;
+    while (slots < 2u * n) slots <<= 1;
+    const uint32_t smask = slots - 1u;
+    int log_slots = 31 - __clz(slots);
+    for (uint32_t i = threadIdx.x; i < slots; i += T) { table[i] = kEmpty; marked[i] = 0; }
+    __syncthreads();
+    KeyT key[E];
+    uint32_t val[E], slot[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      uint32_t i = threadIdx.x + e * T;
+      slot[e] = 0xffffffffu;
+      if (i < n) {
+        key[e] = keys[lo + i];
+        val[e] = vals[lo + i];
+        uint32_t h = (uint32_t)(key_hash((uint64_t)key[e]) >> (64 - leaf_bits - log_slots)) & smask;
+        for (;;) {
+          KeyT old = atomic_cas(&table[h], kEmpty, key[e]);
+          if (old == kEmpty) break;
+          if (old == key[e]) { marked[h] = 1; break; }
+          h = (h + 1u) & smask;
+        }
+        slot[e] = h;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      bool dup = slot[e] != 0xffffffffu && marked[slot[e]];
+      uint32_t m = __ballot_sync(0xffffffffu, dup);
+      if (m) {
+        unsigned long long basepos = 0;
+        if (lane == 0) basepos = atomicAdd(n_cand, (unsigned long long)__popc(m));
+        basepos = __shfl_sync(0xffffffffu, basepos, 0);
+        if (dup) {
+          unsigned long long dst = basepos + __popc(m & lanemask_lt());
+          cand_keys[dst] = key[e];
+          cand_vals[dst] = val[e];
+        }
+      }
+    }
+  }
+}
+
+}  // namespace nrp

@@ -1,0 +1,238 @@
+// Kernels around the bulk path: per-part exclusion flags, background table, grouping of the sorted candidate
+// records, group ranks / last single windows for the order-exact host replay, and part-pair edge expansion.
+#pragma once
+#include "common.cuh"
+
+namespace nrp {
+
+// ---- background hash set (replaces the kmerSetDB lookups of reference kmerSetDB.py:119-127,177-207) ------
+// Open addressing, linear probing, EMPTY = all ones (never canonical).  Sized >= 2n and a power of two.
+template <typename KeyT>
+__global__ void k_bg_insert(const uint64_t* keys, int64_t n, KeyT* table, int log_slots) {
+  const KeyT kEmpty = ~KeyT(0);
+  const uint64_t mask = (1ull << log_slots) - 1ull;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    KeyT key = (KeyT)keys[i];
+    uint64_t h = key_hash((uint64_t)key) >> (64 - log_slots);
+    for (;;) {
+      KeyT old = atomic_cas(&table[h], kEmpty, key);
+      if (old == kEmpty || old == key) break;
+      h = (h + 1) & mask;
+    }
+  }
+}
+
+template <typename KeyT>
+__device__ __forceinline__ bool bg_contains(const KeyT* table, int log_slots, uint64_t key64) {
+  const KeyT kEmpty = ~KeyT(0);
+  const KeyT key = (KeyT)key64;
+  const uint64_t mask = (1ull << log_slots) - 1ull;
+  uint64_t h = key_hash(key64) >> (64 - log_slots);
+  for (;;) {
+    KeyT cur = __ldg(&table[h]);
+    if (cur == key) return true;
+    if (cur == kEmpty) return false;
+    h = (h + 1) & mask;
+  }
+}
+
+// ---- per-part exclusion flags that do not need grouping (reference hgraph.py:59-79) ----------------------
+// mode 0: palindromic k-windows (a window equal to its reverse complement, even k only)
+// mode 1: background hit of a canonical K-window (window length = the background's K)
+template <typename BgKeyT>
+__global__ void __launch_bounds__(kTileThreads) k_flag_windows(Parts P, int klen, int mode, const BgKeyT* bg_table, int bg_log_slots,
+                                                              uint8_t* flags) {
+  __shared__ TileStage stage;
+  const int64_t tile = blockIdx.x;
+  tile_load(P, tile, stage);
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < kTileItems; ++e) {
+    Window w;
+    if (!tile_canonical(P, stage, tile, threadIdx.x + e * kTileThreads, klen, w)) continue;
+    if (mode == 0) {
+      if (w.palindrome) flags[w.part] |= kFlagPalindrome;          // benign race: all writers OR the same bit
+    } else {
+      if (!(flags[w.part] & kFlagBackground) && bg_contains<BgKeyT>(bg_table, bg_log_slots, w.canon)) flags[w.part] |= kFlagBackground;
+    }
+  }
+}
+
+// ---- grouping of the sorted candidate records -------------------------------------------------------------
+// records sorted by (key, part).  head[i] = 1 where a new key starts.  Two equal adjacent records (same key,
+// same part) mean that the part has an internal repeat (reference hgraph.py:53-69).
+template <typename KeyT>
+__global__ void k_group_heads(const KeyT* keys, const uint32_t* vals, int64_t n, uint32_t part_base, int64_t n_parts,
+                              uint32_t* head, uint8_t* flags, unsigned long long* n_repeat_records) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool is_head = i == 0 || keys[i] != keys[i - 1];
+  head[i] = is_head ? 1u : 0u;
+  if (!is_head && vals[i] == vals[i - 1]) {
+    int64_t local = (int64_t)vals[i] - (int64_t)part_base;
+    if (flags && local >= 0 && local < n_parts) flags[local] |= kFlagRepeat;
+    atomicAdd(n_repeat_records, 1ull);
+  }
+}
+
+// group_start[g] for every key run (g = exclusive scan of head), plus the sentinel group_start[n_groups] = n
+__global__ void k_group_starts(const uint32_t* head, const uint32_t* head_scan, int64_t n, uint32_t* group_start) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) { group_start[head_scan[n]] = (uint32_t)n; return; }
+  if (head[i]) group_start[head_scan[i]] = (uint32_t)i;
+}
+
+// per key run: is it a real group (>= 2 members), its member count and its pair count
+__global__ void k_group_sizes(const uint32_t* group_start, int64_t n_runs, uint32_t* valid, uint32_t* members, unsigned long long* pairs) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_runs) return;
+  uint32_t sz = group_start[g + 1] - group_start[g];
+  bool ok = sz >= 2;
+  valid[g] = ok ? 1u : 0u;
+  members[g] = ok ? sz : 0u;
+  pairs[g] = ok ? (unsigned long long)sz * (sz - 1) / 2 : 0ull;
+}
+
+// compact the real groups: keys, CSR indptr (64-bit), pair offsets, and the members
+template <typename KeyT>
+__global__ void k_group_emit(const KeyT* keys, const uint32_t* group_start, const uint32_t* valid, const uint32_t* valid_scan,
+                             const unsigned long long* member_scan, const unsigned long long* pair_scan, int64_t n_runs,
+                             uint64_t* out_keys, int64_t* out_indptr, unsigned long long* out_pair_off) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > n_runs) return;
+  if (g == n_runs) {
+    uint32_t ng = valid_scan[n_runs];
+    out_indptr[ng] = (int64_t)member_scan[n_runs];
+    out_pair_off[ng] = pair_scan[n_runs];
+    return;
+  }
+  if (!valid[g]) return;
+  uint32_t o = valid_scan[g];
+  out_keys[o] = (uint64_t)keys[group_start[g]];
+  out_indptr[o] = (int64_t)member_scan[g];
+  out_pair_off[o] = pair_scan[g];
+}
+
+__global__ void k_group_members(const uint32_t* vals, const uint32_t* head_scan, const uint32_t* head, const uint32_t* group_start,
+                                const uint32_t* valid, const unsigned long long* member_scan, int64_t n, uint32_t* out_members) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t g = head_scan[i] + head[i] - 1u;           // run index of record i (inclusive scan - 1)
+  if (!valid[g]) return;
+  out_members[member_scan[g] + (i - group_start[g])] = vals[i];
+}
+
+// ---- order information for the host replay ----------------------------------------------------
+// canonical k-mer of window j of a part, straight from the ASCII buffer (only used on the few shared keys)
+__device__ __forceinline__ uint64_t window_from_ascii(const uint8_t* seq, int k) {
+  uint64_t fwd = 0;
+  for (int t = 0; t < k; ++t) {
+    uint32_t c = seq[t];
+    uint32_t x = (c >> 1) & 3u;
+    fwd = (fwd << 2) | (x ^ (x >> 1));
+  }
+  return fwd;
+}
+
+// first window of part `first_part[g]` whose canonical k-mer equals the group's key: the rank of the group
+// (reference: position of the key's first insertion into repeat_dict, hgraph.py:82-89)
+__global__ void k_group_first_window(const uint8_t* ascii, const int64_t* off, const uint64_t* group_keys, const uint32_t* first_part,
+                                     uint32_t part_base, int64_t n_parts, int64_t n_groups, int k, uint32_t* first_window) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  int64_t p = (int64_t)first_part[g] - (int64_t)part_base;
+  if (p < 0 || p >= n_parts) return;                  // first member lives on another rank
+  const uint8_t* seq = ascii + off[p];
+  const int64_t len = off[p + 1] - off[p];
+  const uint64_t key = group_keys[g];
+  const uint64_t mask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+  uint64_t fwd = window_from_ascii(seq, k);
+  uint32_t found = 0xffffffffu;
+  for (int64_t j = 0; j + k <= len; ++j) {
+    if (j > 0) {
+      uint32_t c = seq[j + k - 1];
+      uint32_t x = (c >> 1) & 3u;
+      fwd = ((fwd << 2) | (x ^ (x >> 1))) & mask;
+    }
+    uint64_t rc = revcomp2(fwd, k);
+    if ((fwd < rc ? fwd : rc) == key) { found = (uint32_t)j; break; }
+  }
+  first_window[g] = found;
+}
+
+// last window of each surviving part whose canonical k-mer is not a shared key: the rank of the part's
+// singleton tuple (id,) in the reference's popitem order
+__global__ void k_last_single(const uint8_t* ascii, const int64_t* off, const uint8_t* flags, int64_t n_parts, int k,
+                              const uint64_t* shared_keys, int64_t n_shared, int32_t* last_single) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_parts) return;
+  const int64_t len = off[p + 1] - off[p];
+  int32_t result = -1;
+  if (len >= k && !(flags && flags[p])) {
+    const uint8_t* seq = ascii + off[p];
+    for (int64_t j = len - k; j >= 0; --j) {
+      uint64_t fwd = window_from_ascii(seq + j, k);
+      uint64_t rc = revcomp2(fwd, k);
+      uint64_t canon = fwd < rc ? fwd : rc;
+      int64_t lo = 0, hi = n_shared;                 // binary search in the sorted shared keys
+      bool shared = false;
+      while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        uint64_t v = shared_keys[mid];
+        if (v == canon) { shared = true; break; }
+        if (v < canon) lo = mid + 1; else hi = mid;
+      }
+      if (!shared) { result = (int32_t)j; break; }
+    }
+  }
+  last_single[p] = result;
+}
+
+// ---- part-pair edges (reference hgraph.py:157-200, order-free) ---------------------------------------------------
+// one thread per member a of a group: pairs (a, b > a).  code = (min id << 32) | max id; pairs of one part with
+// itself (a k-mer occurring twice in a part, internal_repeats=True) get the all-ones code and sort last.
+__global__ void k_edge_pairs(const int64_t* indptr, const uint32_t* members, const unsigned long long* pair_off, int64_t n_groups,
+                             int64_t n_members, const uint32_t* part_id, uint32_t part_base, uint64_t* codes) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_members) return;
+  int64_t lo = 0, hi = n_groups;                      // last group with indptr <= t
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (indptr[mid] <= t) lo = mid; else hi = mid;
+  }
+  const int64_t g = lo;
+  const int64_t s = indptr[g + 1] - indptr[g];
+  const int64_t a = t - indptr[g];
+  const uint32_t ida = part_id[members[t] - part_base];
+  unsigned long long dst = pair_off[g] + (unsigned long long)(a * s - a * (a + 1) / 2);
+  for (int64_t b = a + 1; b < s; ++b) {
+    uint32_t idb = part_id[members[indptr[g] + b] - part_base];
+    uint64_t code = ida == idb ? ~0ull : (ida < idb ? ((uint64_t)ida << 32) | idb : ((uint64_t)idb << 32) | ida);
+    codes[dst + (unsigned long long)(b - a - 1)] = code;
+  }
+}
+
+__global__ void k_edge_heads(const uint64_t* codes, int64_t n, uint32_t* head) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t c = codes[i];
+  head[i] = (c != ~0ull && (i == 0 || c != codes[i - 1])) ? 1u : 0u;
+}
+
+__global__ void k_edge_compact(const uint64_t* codes, const uint32_t* head, const uint32_t* head_scan, int64_t n, uint32_t* u, uint32_t* v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !head[i]) return;
+  uint32_t o = head_scan[i];
+  u[o] = (uint32_t)(codes[i] >> 32);
+  v[o] = (uint32_t)codes[i];
+}
+
+__global__ void k_count_flagged(const uint8_t* flags, int64_t n, unsigned long long* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool f = i < n && flags[i] != 0;
+  uint32_t m = __ballot_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
+
+}  // namespace nrp

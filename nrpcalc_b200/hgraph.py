@@ -1,0 +1,283 @@
+"""Repeat ("homology") graph construction -- the accelerated hot path and its drop-in boundary.
+
+Boundary: get_homology_graph(seq_list, background, homology, internal_repeats, seq_file, verbose) has the
+signature, side effects and result of reference nrpcalc/base/hgraph.py:202-249 -- it consumes seq_list,
+writes the 'id,SEQ' side file in processing order and returns an nx.Graph whose node order and adjacency
+order equal the reference's (the unchanged vertex-cover step observes both).
+
+What runs where
+  host    uniquify + marshalling (this file)                          <- hgraph.py:11-21, 218-223
+  GPU     k-mer extraction, reverse complement, canonical min, background membership, grouping of equal
+          k-mers, internal-repeat exclusion, first-insertion ranks   <- hgraph.py:23-94, utils.py:37-50,
+          (libnrpb200.so through nrpcalc_b200._native)                    kmerSetDB.py:177-207
+  host    replay of the distinct id tuples through the clique tail    <- hgraph.py:96-200
+
+The tail cannot move to the GPU without changing results: the order in which cliques reach the graph is the
+iteration order of CPython sets of tuples (hgraph.py:131-155).  It is reproduced by feeding real sets the
+same values in the same order.  Only tuples that differ from all earlier ones change a set, so the device
+returns every shared k-mer group with its rank and, per part, the rank of its last unshared window
+(SURVEY.md 8b); that is O(parts + shared k-mers) host work instead of O(windows).
+
+There is no CPU fallback: without the CUDA library or a GPU the call raises.
+"""
+import sys
+from collections import defaultdict, deque
+from time import time
+
+import networkx as nx
+import numpy as np
+
+from . import _native
+from . import encoding
+
+_contexts = {}
+
+
+def _context(device=None):
+    if device is None:
+        import os
+        device = int(os.environ.get('NRPCALC_B200_DEVICE', os.environ.get('LOCAL_RANK', '0')))
+    if device not in _contexts:
+        _contexts[device] = _native.Context(device)
+    return _contexts[device]
+
+
+def uniquify_seq_list(seq_list):
+    """Unique upper-cased parts in PROCESSING order: [(id, SEQ)], id = first index, ordered by descending last
+    occurrence (hgraph.py:11-21 followed by the reversal at 218-223).  Empties seq_list like the reference."""
+    first_index = {}
+    for idx in range(len(seq_list) - 1, -1, -1):
+        first_index[seq_list[idx].upper()] = idx
+    del seq_list[:]
+    return [(idx, seq) for seq, idx in first_index.items()]
+
+
+class RepeatStructure(object):
+    """Everything the replay needs, accumulated over the length classes of one job."""
+
+    def __init__(self, n_parts):
+        self.flags = np.zeros(n_parts, dtype=np.uint8)
+        self.rank = []          # int64 arrays: p * 2^32 + window
+        self.start = []         # per entry: offset into members
+        self.size = []
+        self.members = []       # global processing ranks p
+        self.n_members = 0
+        self.records = 0
+        self.timings = defaultdict(float)
+        self.counts = defaultdict(int)
+
+    def add_entries(self, rank, indptr, members):
+        self.rank.append(rank)
+        self.start.append(indptr[:-1] + self.n_members)
+        self.size.append(np.diff(indptr))
+        self.members.append(members)
+        self.n_members += members.size
+
+
+def _device_build(ctx, structure, ascii_buf, offsets, global_p, ids, k, internal_repeats, want_edges=False):
+    """One libnrpb200 build over parts that all have length >= k; global_p maps local index -> processing rank."""
+    ctx.load_parts(ascii_buf, offsets, ids if want_edges else None)
+    ctx.build(k, internal_repeats, want_edges=want_edges)
+    res = ctx.fetch(want_keys=False)
+    structure.flags[global_p] |= res.flags
+    structure.records += res.counts['records']
+    for name, value in res.timings.items():
+        structure.timings[name] += value
+    for name in ('groups', 'members', 'candidates', 'oversized', 'windows_max'):
+        structure.counts[name] += res.counts[name]
+    structure.counts['runs'] = max(structure.counts['runs'], res.counts['runs'])
+    # shared k-mer groups: rank = (p of first member, first window); members -> processing ranks
+    if res.counts['groups']:
+        first = global_p[res.members[res.indptr[:-1]]].astype(np.int64)
+        structure.add_entries((first << 32) | res.first_window.astype(np.int64), res.indptr, global_p[res.members])
+    # singleton tuples: one per part that owns at least one window nobody shares
+    own = np.nonzero(res.last_single >= 0)[0]
+    if own.size:
+        p = global_p[own].astype(np.int64)
+        structure.add_entries((p << 32) | res.last_single[own].astype(np.int64), np.arange(own.size + 1, dtype=np.int64),
+                              global_p[own])
+    return res
+
+
+def repeat_structure(parts, background, homology, internal_repeats, ctx=None, want_edges=False):
+    """Run the device path over the processing-ordered [(id, SEQ)] list.  Returns (RepeatStructure, ids)."""
+    ctx = ctx or _context()
+    n = len(parts)
+    ids = np.fromiter((pid for pid, _ in parts), dtype=np.uint32, count=n)
+    seqs = [seq for _, seq in parts]
+    ascii_buf, offsets = encoding.join_parts(seqs)
+    if not encoding.all_acgt(ascii_buf):
+        raise ValueError('nrpcalc_b200 supports parts over A, C, G, T only (see DESIGN.md, documented deviation)')
+    lengths = np.diff(offsets)
+    structure = RepeatStructure(n)
+
+    if background is not None:
+        if background.K <= (int(lengths.max()) if n else 0) and not background.ALIVE:
+            raise RuntimeError('kmerSetDB was closed or dropped')      # surfaces from multicheck, kmerSetDB.py:97-102
+        keys, _ = background.device_keys()
+        if background.K > 32:
+            if keys.size or len(background):
+                raise ValueError('backgrounds with Lmax > 31 are not supported by the device path')
+            ctx.set_background(None, 0)
+        else:
+            ctx.set_background(keys, background.K)
+    else:
+        ctx.set_background(None, 0)
+
+    if homology > 32 and n and int(lengths.max()) > 32:
+        raise ValueError('Lmax > 31 needs keys wider than 64 bits, which the device path does not support')
+
+    # parts with len >= k: ordinary k-windows.  Shorter parts are keyed by their whole string (utils.py:37-40):
+    # one build per distinct length l < k with k' = l (a string of length l can only equal another of length l).
+    all_p = np.arange(n, dtype=np.int64)
+    long_mask = lengths >= homology
+    try:
+        if long_mask.all():
+            _device_build(ctx, structure, ascii_buf, offsets, all_p, ids, homology, internal_repeats, want_edges)
+        else:
+            classes = [(homology, np.nonzero(long_mask)[0])]
+            for short_len in np.unique(lengths[~long_mask]).tolist():
+                classes.append((int(short_len), np.nonzero(lengths == short_len)[0]))
+            for k_class, idx in classes:
+                if idx.size == 0:
+                    continue
+                if k_class == 0:
+                    # the empty part: its only window '' equals its own reverse complement (hgraph.py:60-63)
+                    if internal_repeats:
+                        structure.add_entries(idx.astype(np.int64) << 32, np.arange(idx.size + 1, dtype=np.int64), idx)
+                    else:
+                        structure.flags[idx] |= _native.FLAG_PALINDROME
+                    continue
+                if k_class > 32:
+                    raise ValueError('parts longer than 32 nt that are shorter than Lmax+1 are not supported')
+                sub_off = np.zeros(idx.size + 1, dtype=np.int64)
+                np.cumsum(lengths[idx], out=sub_off[1:])
+                pieces = [ascii_buf[offsets[i]:offsets[i + 1]] for i in idx.tolist()]
+                sub_ascii = np.concatenate(pieces) if pieces else np.zeros(0, dtype=np.uint8)
+                _device_build(ctx, structure, sub_ascii, sub_off, idx, ids[idx], k_class, internal_repeats, False)
+    finally:
+        ctx.set_background(None, 0)
+    return structure, ids
+
+
+def ordered_tuples(structure, ids):
+    """Distinct-tuple candidates in the order the reference meets them: keys leave repeat_dict by popitem(),
+    i.e. by DESCENDING first-insertion rank (hgraph.py:132-135)."""
+    if not structure.rank:
+        return
+    rank = np.concatenate(structure.rank)
+    start = np.concatenate(structure.start)
+    size = np.concatenate(structure.size)
+    members = ids[np.concatenate(structure.members)].tolist()
+    order = np.argsort(-rank, kind='stable')
+    start = start[order].tolist()
+    size = size[order].tolist()
+    for s, z in zip(start, size):
+        if z == 1:
+            yield (members[s],)
+        else:
+            yield tuple(members[s:s + z])
+
+
+def _maximal_cliques(clique_sets):
+    """Keep cliques that are not contained in another one (hgraph.py:96-115), same set operations in the same order."""
+    member_of = defaultdict(set)
+    for pos, clique in enumerate(clique_sets):
+        for node in clique:
+            member_of[node].add(pos)
+    keep = set()
+    for pos, clique in enumerate(clique_sets):
+        common = set()
+        for node in clique:
+            if len(common) == 0:
+                common |= member_of[node]
+            else:
+                common &= member_of[node]
+        if len(common) == 1:
+            keep.add(pos)
+        else:
+            keep.update(common - set([pos]))
+    return [clique_sets[pos] for pos in keep]
+
+
+def replay_cliques(tuples):
+    """hgraph.py:130-155 on the compressed stream.  Re-adding a tuple that is already present never changes a
+    CPython set, so adding only the (superset of) first occurrences leaves every set exactly as in the reference."""
+    distinct = set()
+    for members in tuples:
+        distinct.add(members)
+    as_sets = []
+    while distinct:
+        as_sets.append(set(distinct.pop()))
+    as_sets = _maximal_cliques(as_sets)
+    final = set()
+    while as_sets:
+        final.add(tuple(as_sets.pop()))
+    while final:
+        yield deque(final.pop())
+
+
+def build_homology_graph(cliques, verbose):
+    """Insert cliques into the graph (hgraph.py:157-200): node and adjacency insertion order are part of the result."""
+    graph = nx.Graph()
+    if verbose:
+        print()
+        clear_length = 0
+    count = 0
+    for clique in cliques:
+        if len(clique) == 1:
+            graph.add_node(clique.popleft())
+        else:
+            pending = set(clique)
+            while clique:
+                u = clique.popleft()
+                pending.remove(u)
+                graph.add_node(u)
+                for v in pending - set(graph[u]):
+                    graph.add_edge(u, v)
+        count += 1
+        if verbose:
+            printed = ' [Cliques inserted] = {}\r'.format(count)
+            sys.stdout.write(' ' * clear_length + '\r')
+            sys.stdout.write(printed)
+            clear_length = len(printed)
+            sys.stdout.flush()
+    if verbose:
+        print()
+    return graph
+
+
+last_build_info = {}
+
+
+def get_homology_graph(seq_list, background, homology, internal_repeats, seq_file, verbose):
+    t0 = time()
+    num_seqs = len(seq_list)
+    parts = uniquify_seq_list(seq_list)
+    unq_seqs = len(parts)
+    if verbose:
+        print('Extracted {} unique sequences out of {} sequences in {:2.4} seconds'.format(unq_seqs, num_seqs, time() - t0))
+
+    t0 = time()
+    with open(seq_file, 'w') as outfile:
+        outfile.write(''.join('{},{}\n'.format(pid, seq) for pid, seq in parts))
+    if verbose:
+        print('\nWritten {} unique sequences out to {} in {:2.4} seconds'.format(unq_seqs, seq_file, time() - t0))
+
+    t0 = time()
+    structure, ids = repeat_structure(parts, background, homology, internal_repeats)
+    t_device = time() - t0
+    if verbose:
+        print(' [Sequence processing remaining] = 0  (GPU: {} k-mers in {:.3f} ms on device)'.format(
+            structure.records, structure.timings['total']))
+    graph = build_homology_graph(replay_cliques(ordered_tuples(structure, ids)), verbose)
+    last_build_info.clear()
+    last_build_info.update({'records': structure.records, 'device_ms': structure.timings['total'], 'call_s': t_device,
+                            'timings': dict(structure.timings), 'counts': dict(structure.counts),
+                            'replay_s': time() - t0 - t_device})
+    if verbose:
+        print('\nBuilt homology graph in {:2.4} seconds. [Edges = {}] [Nodes = {}]'.format(
+            time() - t0, graph.number_of_edges(), graph.number_of_nodes()))
+        print(' [Intital Nodes = {}] - [Repetitive Nodes = {}] = [Final Nodes = {}]'.format(
+            unq_seqs, unq_seqs - graph.number_of_nodes(), graph.number_of_nodes()))
+    return graph

@@ -1,0 +1,69 @@
+"""Independent-set recovery around a vertex-cover routine -- host step, behaviour identical to the
+reference (nrpcalc/base/recovery.py:32-96).
+
+The cover routines destroy the graph they are given, so the full graph is dumped once as an adjacency list
+and reloaded after every round (recovery.py:26-30,55,78).  The reload changes adjacency order (file order
+instead of insertion order), which later rounds observe; the dump/reload is therefore part of result parity
+and is kept as is.
+"""
+import sys
+from time import time
+
+import networkx as nx
+
+from . import vercov
+
+
+def get_recovered_non_homologs(homology_graph, graph_file, vercov_func=None, verbose=True):
+    independent = set()
+    candidates = set(homology_graph.nodes())
+    if verbose:
+        print('\n [+] Initial independent set = {}, computing vertex cover on remaining {} nodes.'.format(
+            len(independent), 0, len(candidates)))
+    if not homology_graph.number_of_nodes():
+        if verbose:
+            print(' [X] Graph is empty, further independent set expansion not possible, terminating.')
+        return independent
+
+    # unknown names fall through to 'nrp2' exactly like recovery.py:18-24
+    routine, routine_name = vercov.ROUTINES.get(vercov_func, vercov.ROUTINES['nrp2'])
+    if verbose:
+        print(' [+] Vertex Cover Function: {}'.format(routine_name))
+        sys.stdout.write(' [+] Dumping graph into: {}'.format(graph_file))
+    t0 = time()
+    nx.write_adjlist(homology_graph, graph_file)
+    if verbose:
+        sys.stdout.write(' in {} seconds\n'.format(time() - t0))
+
+    iteration = -1
+    while True:
+        iteration += 1
+        if verbose:
+            print('\n----------------------')
+            print('Now running iteration: {}'.format(iteration))
+            print('----------------------')
+        t0 = time()
+        if iteration > 0:
+            homology_graph = nx.Graph(homology_graph.subgraph(candidates))
+        cover = routine(homology_graph, verbose)
+        if verbose:
+            print('\n [+] Computed vertex cover of size: {} (in {:.4} seconds)'.format(len(cover), time() - t0))
+            print(' [+] Loading graph from: {}'.format(graph_file))
+        homology_graph = nx.read_adjlist(graph_file, nodetype=int)
+
+        fresh = candidates - cover
+        independent |= fresh
+        candidates = cover
+        before = len(candidates)
+        for node in fresh:
+            candidates.difference_update(homology_graph[node])
+        after = len(candidates)
+        if verbose:
+            print(' [+] Current independent set size:  {}'.format(len(independent)))
+            print(' [+] Potential nodes for expansion: {} (projected independent set size: {})'.format(
+                len(candidates), len(independent) + len(candidates)))
+        if len(candidates) == 0 or before == after:
+            if verbose:
+                print(' [X] Cannot expand independent set, terminating.')
+            break
+    return independent

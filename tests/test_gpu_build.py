@@ -1,0 +1,113 @@
+"""GPU parity of the raw C ABI (libnrpb200.so) against the numpy oracle on seeded inputs."""
+import numpy as np
+import pytest
+
+import cases
+from oracle import np_oracle, ref_port
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    from nrpcalc_b200 import _native
+    context = _native.Context(0)
+    yield context
+    context.close()
+
+
+def _long_parts(parts, k):
+    """(processing-ordered [(id, SEQ)]) restricted to parts with len >= k, as the C ABI expects."""
+    uniq = ref_port.uniquify(list(parts))
+    return [(pid, seq) for pid, seq in uniq if len(seq) >= k]
+
+
+def _run(ctx, uniq, k, internal, bg_keys=None, bg_K=None):
+    seqs = [s for _, s in uniq]
+    ids = np.array([pid for pid, _ in uniq], dtype=np.uint32)
+    offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in seqs], out=offsets[1:])
+    ascii_buf = np.frombuffer(''.join(seqs).encode(), dtype=np.uint8)
+    ctx.set_background(bg_keys, bg_K)
+    ctx.load_parts(ascii_buf, offsets, ids)
+    ctx.build(k, internal, want_edges=True)
+    return ctx.fetch()
+
+
+def _compare(res, uniq, k, internal, bg_keys=None, bg_K=None):
+    want = np_oracle.spec(uniq, k, internal, bg_keys, bg_K)
+    ids = want['ids']
+    assert (res.flags != 0).tolist() == (want['flags'] != 0).tolist()
+    # the reason bits are a subset: a part already excluded for one reason is not examined for the others
+    assert ((res.flags & ~want['flags']) == 0).all()
+    assert res.counts['records'] == want['n_records']
+    got_groups = sorted((int(res.members[res.indptr[g]]), int(res.first_window[g]),
+                         tuple(int(ids[m]) for m in res.members[res.indptr[g]:res.indptr[g + 1]]))
+                        for g in range(res.counts['groups']))
+    assert got_groups == sorted(want['groups'])
+    assert res.last_single.tolist() == want['last_single'].tolist()
+    got_edges = list(zip(res.edges[0].tolist(), res.edges[1].tolist()))
+    assert got_edges == sorted(want['edges'])
+    assert res.counts['excluded'] == int((want['flags'] != 0).sum())
+
+
+@pytest.mark.parametrize('seed', range(3))
+@pytest.mark.parametrize('k', [6, 13, 16, 17, 25, 32])
+@pytest.mark.parametrize('internal', [False, True])
+def test_planted_parts(ctx, seed, k, internal):
+    uniq = _long_parts(cases.planted_parts(400, seed), k)
+    _compare(_run(ctx, uniq, k, internal), uniq, k, internal)
+
+
+@pytest.mark.parametrize('seed', range(2))
+@pytest.mark.parametrize('k,K', [(16, 16), (16, 12), (13, 20), (17, 17), (20, 32)])
+def test_background(ctx, seed, k, K):
+    parts = cases.planted_parts(400, 20 + seed)
+    bg_keys = np_oracle.canonical_key_set(cases.background_seqs_for(parts, seed), K)
+    uniq = _long_parts(parts, k)
+    _compare(_run(ctx, uniq, k, False, bg_keys, K), uniq, k, False, bg_keys, K)
+    ctx.set_background(None, 0)
+
+
+@pytest.mark.parametrize('internal', [False, True])
+def test_palindromes(ctx, internal):
+    uniq = _long_parts(cases.palindrome_parts(0, n_parts=200), 6)
+    _compare(_run(ctx, uniq, 6, internal), uniq, 6, internal)
+
+
+@pytest.mark.parametrize('n,length,k', [(10000, 100, 13), (20000, 100, 17), (3000, 200, 16)])
+def test_random_uniform(ctx, n, length, k):
+    """BASELINE shapes (config 1 in full; configs 2 and 3 scaled down to what the oracle does in seconds)."""
+    uniq = ref_port.uniquify(cases.random_parts(n, length, 1))
+    res = _run(ctx, uniq, k, False)
+    _compare(res, uniq, k, False)
+
+
+def test_variable_length(ctx):
+    uniq = _long_parts(cases.buffer_to_list(*cases.random_varlen_buffer(5000, 50, 300, 5)), 25)
+    _compare(_run(ctx, uniq, 25, False), uniq, 25, False)
+    uniq = _long_parts(cases.buffer_to_list(*cases.random_varlen_buffer(5000, 20, 90, 6)), 11)
+    _compare(_run(ctx, uniq, 11, False), uniq, 11, False)
+
+
+def test_forced_paths(ctx):
+    """Tiny filter capacity -> every leaf bucket takes the oversized path; one level bit -> deep buckets."""
+    uniq = _long_parts(cases.planted_parts(600, 77), 13)
+    try:
+        ctx.set_option('filter_cap', 16)
+        _compare(_run(ctx, uniq, 13, False), uniq, 13, False)
+        ctx.set_option('filter_cap', 0)
+        ctx.set_option('leaf_target', 40)
+        _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
+        ctx.set_option('max_level_bits', 2)
+        _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
+    finally:
+        ctx.set_option('filter_cap', 0)
+        ctx.set_option('leaf_target', 0)
+        ctx.set_option('max_level_bits', 0)
+
+
+def test_empty_and_tiny(ctx):
+    for parts in ([], ['ACGTACGTACGTA'], ['ACGTACGTACGTA', 'ACGTACGTACGTA'.lower(), 'TTTTTTTTTTTTTTTT']):
+        uniq = _long_parts(parts, 13)
+        _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
