@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Finder graph-build benchmark (BASELINE.json metric: k-mers/s, parts/s, % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2]
+
+A step = one build of the repeat structure of one batch of synthetic random-DNA parts (BASELINE config 2 by
+default: 1M x 100 bp, Lmax=16, internal_repeats=False).
+
+  value     k-mers/s with the parts resident in HBM, from the library's CUDA events around the pipeline
+            (device-resident inputs -> device-resident flags/groups/ranks/edges), summed over the K steps
+  e2e       the same through the C ABI with HOST buffers: nrp_load_parts (H2D) + nrp_build + all result getters
+            (D2H), wall clock around the calls
+  roofline  the dominant kernel's algorithmic bytes / its CUDA-event duration against the measured HBM copy peak
+  cpu_baseline  oracle/nrp_oracle.c (hash-table restatement of the reference's algorithm) on the host cores
+
+--impl reference times the literal pure-Python port of the reference (oracle/ref_port.py; the reference itself is
+pure Python and is not present on the GPU box) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+CONFIGS = {
+    # name: (n_parts, length or (lo, hi), Lmax, internal_repeats, background genome bp, seed)
+    'c1': dict(n=10_000, length=100, Lmax=12, internal_repeats=False, genome=0, seed=1,
+               label='Finder mode: 10k synthetic 100-bp parts, Lmax=12, no background'),
+    'c2': dict(n=1_000_000, length=100, Lmax=16, internal_repeats=False, genome=0, seed=2,
+               label='Finder mode: 1M synthetic 100-bp parts, Lmax=16, internal_repeats=False, on 1 B200'),
+    'c3': dict(n=1_000_000, length=200, Lmax=15, internal_repeats=False, genome=5_000_000, seed=3,
+               label='Finder mode: 1M 200-bp parts with a 5-Mbp synthetic background genome k-mer set, Lmax=15'),
+    'c4': dict(n=10_000_000, length=100, Lmax=20, internal_repeats=False, genome=0, seed=4,
+               label='Finder mode: 10M synthetic 100-bp parts, Lmax=20, hash-sharded across 2/4/8 B200'),
+}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for row in self.rows:
+            try:
+                sm.append(float(row[0])); mx.append(float(row[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, cell in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), row[3:7]):
+                if cell.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def make_workload(cfg, n_parts=None):
+    import cases
+    n = cfg['n'] if n_parts is None else n_parts
+    if isinstance(cfg['length'], tuple):
+        return cases.random_varlen_buffer(n, cfg['length'][0], cfg['length'][1], cfg['seed'])
+    return cases.random_dna_buffer(n, cfg['length'], cfg['seed'])
+
+
+def background_keys(cfg):
+    if not cfg['genome']:
+        return None, 0
+    import cases
+    from nrpcalc_b200 import encoding
+    genome = cases.random_genome(cfg['genome'], cfg['seed'] * 11)
+    buf, off = encoding.join_parts([genome])
+    K = cfg['Lmax'] + 1
+    return np.unique(encoding.canonical_kmers(buf, off, K)), K
+
+
+def algorithmic_bytes(total_len, m, key_bytes):
+    rec = key_bytes + 4
+    return {'histogram': total_len, 'split1': total_len + m * rec, 'split2': 2 * m * rec, 'filter': m * rec,
+            'flags': total_len}
+
+
+def run_reference_arm(args, cfg):
+    """Literal pure-Python port of the reference's graph-build path on a bounded sample (1 core, like the reference)."""
+    from oracle import ref_port
+    import cases
+    k = cfg['Lmax'] + 1
+    sample_parts = max(1000, min(cfg['n'], args.reference_parts))
+    buf, off = make_workload(cfg, sample_parts)
+    parts = cases.buffer_to_list(buf, off)
+    bg = None
+    if cfg['genome']:
+        bg = ref_port.SetBackground(k)
+        bg.multiadd([cases.random_genome(min(cfg['genome'], 200_000), cfg['seed'] * 11)])
+    m = int(np.maximum(np.diff(off) - k + 1, 0).sum())
+    times = []
+    for step in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        graph, _ = ref_port.homology_graph(list(parts), bg, k, cfg['internal_repeats'])
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = m / (ms * 1e-3)
+    sample = '{} of {} parts ({} k-mers) per step, get_homology_graph equivalent incl. clique tail'.format(sample_parts, cfg['n'], m)
+    line = {'impl': 'reference', 'metric': 'finder_graph_build_kmers_per_s', 'value': value, 'unit': 'k-mers/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'u64' if k > 16 else 'u32', 'data': 'synthetic',
+            'config': {'workload': cfg['label'], 'n_parts': cfg['n'], 'Lmax': cfg['Lmax']},
+            'parts_per_s': sample_parts / (ms * 1e-3),
+            'cpu_baseline': {'value': value, 'unit': 'k-mers/s', 'cores': 1, 'kind': 'port', 'sample': sample,
+                             'port': 'oracle/ref_port.py: literal pure-Python restatement; the reference (pure Python, single-threaded) is not on the GPU box'},
+            'e2e': {'value': value, 'unit': 'k-mers/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def cpu_baseline(cfg, buf, off, k):
+    """oracle/nrp_oracle.c on a bounded sample of the workload, all host cores."""
+    from oracle import c_oracle
+    cores = os.cpu_count() or 1
+    n_sample = min(cfg['n'], 400_000)
+    sub_off = off[:n_sample + 1]
+    sub_buf = buf[:int(sub_off[-1])]
+    t0 = time.perf_counter()
+    res = c_oracle.build_table(sub_buf, sub_off, k, cfg['internal_repeats'], None, 0, n_threads=cores, want_groups=True)
+    dt = time.perf_counter() - t0
+    return {'value': res['n_records'] / dt, 'unit': 'k-mers/s', 'cores': cores, 'kind': 'port',
+            'sample': 'first {} of {} parts ({} k-mers), oracle/nrp_oracle.c hash-table port, {:.1f} s'.format(
+                n_sample, cfg['n'], res['n_records'], dt)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default=None)
+    ap.add_argument('--reference-parts', type=int, default=20_000)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-edges', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else max(args.warmup, 0)
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    cfg_name = args.config or ('c2' if args.gpus == 1 else 'c4')
+    cfg = CONFIGS[cfg_name]
+
+    if args.impl == 'reference':
+        if rank == 0:
+            run_reference_arm(args, cfg)
+        return
+
+    if args.gpus > 1 or world > 1:
+        import bench_sharded
+        bench_sharded.main(args, cfg, rank, world, local_rank)
+        return
+
+    import torch
+    from nrpcalc_b200 import _native
+
+    k = cfg['Lmax'] + 1
+    buf, off = make_workload(cfg)
+    ids = np.arange(cfg['n'], dtype=np.uint32)[::-1].copy()      # processing order of a duplicate-free list: ids N-1..0
+    bg_keys, bg_K = background_keys(cfg)
+    want_edges = not args.no_edges
+
+    torch.cuda.set_device(local_rank)
+    ctx = _native.Context(local_rank)
+    ctx.set_background(bg_keys, bg_K)
+    # pinned host staging for the e2e leg; device-resident copy for the kernel-only leg
+    host_ascii = torch.from_numpy(buf.copy()).pin_memory()
+    dev_ascii = host_ascii.cuda(non_blocking=False)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')     # > 126 MB L2
+
+    # ---- device-resident leg
+    ctx.load_parts(None, off, ids, device_ptr=dev_ascii.data_ptr())
+    for _ in range(args.warmup):
+        ctx.build(k, cfg['internal_repeats'], want_edges)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    stage_ms = {}
+    total_ms = 0.0
+    launches = 0
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        ctx.build(k, cfg['internal_repeats'], want_edges)
+        t = ctx.timings()
+        total_ms += t['total']
+        for name, v in t.items():
+            stage_ms[name] = stage_ms.get(name, 0.0) + v
+        launches += ctx.counts()['launches']
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    counts = ctx.counts()
+    m = counts['records']
+    ms_per_step = total_ms / args.steps
+    value = m / (ms_per_step * 1e-3)
+
+    # ---- end-to-end leg: host buffers in, host results out
+    e2e_times = []
+    h2d = d2h = 0
+    for step in range(2 + args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.load_parts(host_ascii.numpy(), off, ids)
+        ctx.build(k, cfg['internal_repeats'], want_edges)
+        res = ctx.fetch(want_keys=True)
+        dt = time.perf_counter() - t0
+        if step >= 2:
+            e2e_times.append(dt)
+        h2d = buf.nbytes + off.nbytes + ids.nbytes
+        d2h = (res.flags.nbytes + res.indptr.nbytes + res.members.nbytes + res.first_window.nbytes + res.keys.nbytes +
+               res.last_single.nbytes + (res.edges[0].nbytes + res.edges[1].nbytes if res.edges else 0) + 16 * 8 * 2)
+    clocks = sampler.stop()
+    e2e_value = m / (sum(e2e_times) / len(e2e_times))
+
+    # ---- roofline of the dominant kernel
+    peak, peak_src = measured_peak_gbs()
+    algo = algorithmic_bytes(int(off[-1]), m, counts['key_bytes'])
+    stage_avg = {name: stage_ms.get(name, 0.0) / args.steps for name in algo}
+    dominant = max(stage_avg, key=lambda name: stage_avg[name])
+    kernel_of = {'histogram': 'k_hist_from_ascii', 'split1': 'k_split_from_ascii', 'split2': 'k_split_from_records', 'filter': 'k_filter',
+                 'flags': 'k_flag_windows'}
+    achieved = algo[dominant] / (stage_avg[dominant] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get(cfg_name, {}).get(kernel_of[dominant])
+    pipeline_bytes = sum(algo[name] for name in ('histogram', 'split1', 'split2', 'filter')) + (algo['flags'] if stage_avg['flags'] > 0 else 0)
+    roofline = {'bound': 'hbm', 'kernel': kernel_of[dominant], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': algo[dominant],
+                'kernel_ms': stage_avg[dominant],
+                'per_stage': {name: {'ms': stage_avg[name], 'GB/s': (algo[name] / (stage_avg[name] * 1e-3) / 1e9) if stage_avg[name] > 0 else None}
+                              for name in algo},
+                'pipeline': {'bytes_per_kmer': pipeline_bytes / max(m, 1), 'GB/s': pipeline_bytes / (ms_per_step * 1e-3) / 1e9,
+                             'frac': pipeline_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                             'survey_formula_bytes_per_kmer': (int(off[-1]) / max(m, 1)) + (counts['key_bytes'] + 4) * (2 * -(-2 * k // 8) + 3) + counts['key_bytes'],
+                             }}
+    roofline['pipeline']['survey_formula_frac'] = roofline['pipeline']['survey_formula_bytes_per_kmer'] * m / (ms_per_step * 1e-3) / 1e9 / peak
+
+    line = {'metric': 'finder_graph_build_kmers_per_s', 'value': value, 'unit': 'k-mers/s', 'n_gpus': 1, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'u64' if counts['key_bytes'] == 8 else 'u32', 'data': 'synthetic',
+            'config': {'workload': cfg['label'], 'n_parts': cfg['n'], 'part_len': cfg['length'], 'Lmax': cfg['Lmax'], 'k': k,
+                       'internal_repeats': cfg['internal_repeats'], 'background_kmers': 0 if bg_keys is None else int(bg_keys.size),
+                       'kmers': m, 'edges': want_edges, 'l2': 'explicit 256 MiB flush between steps; per-step working set {:.2f} GB'.format(
+                           2 * m * (counts['key_bytes'] + 4) / 1e9)},
+            'parts_per_s': cfg['n'] / (ms_per_step * 1e-3),
+            'e2e': {'value': e2e_value, 'unit': 'k-mers/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                    'ms_per_step': 1e3 * sum(e2e_times) / len(e2e_times), 'path': 'C ABI: nrp_load_parts(host) + nrp_build + result getters'},
+            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
+            'stage_ms': {name: v / args.steps for name, v in stage_ms.items()},
+            'result': {name: counts[name] for name in ('records', 'excluded', 'groups', 'members', 'edges', 'candidates', 'runs', 'buckets', 'oversized')},
+            'wall_s_timed_region': wall}
+    if not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline(cfg, buf, off, k)
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    main()

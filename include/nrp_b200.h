@@ -62,6 +62,7 @@ extern "C" {
 #define NRP_C_OVERSIZED      9  /* leaf buckets larger than the shared-memory filter capacity */
 #define NRP_C_WINDOWS_MAX   10  /* windows of all parts before exclusion */
 #define NRP_C_KEY_BYTES     11  /* 4 or 8 */
+#define NRP_C_LAUNCHES      12  /* kernels launched by the build */
 #define NRP_N_COUNTS        16
 
 /* indices into nrp_result_timings() (milliseconds, CUDA events on the context's stream) */

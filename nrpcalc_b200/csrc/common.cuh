@@ -9,6 +9,10 @@ namespace nrp {
 
 constexpr uint8_t kFlagRepeat = 1, kFlagPalindrome = 2, kFlagBackground = 4;
 
+// number of kernels launched by this thread (reported through NRP_C_LAUNCHES)
+inline int64_t& launch_counter() { static thread_local int64_t n = 0; return n; }
+#define NRP_LAUNCH(kernel_call) do { ++::nrp::launch_counter(); kernel_call; } while (0)
+
 // ---------------------------------------------------------------------------------------------------
 // hashing: one multiplicative (Fibonacci) hash per key; consecutive bit fields of the product, from the top,
 // select the level-1 bucket, the level-2 bucket and the slot of the in-bucket table.

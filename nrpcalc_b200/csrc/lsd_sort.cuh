@@ -117,9 +117,9 @@ void lsd_sort(KeyT* keys, uint32_t* vals, KeyT* alt_keys, uint32_t* alt_vals, in
     uint32_t* offsets = scratch + n_counts + 1;
     uint32_t* scan_scratch = offsets + n_counts + 2;
     for (int p = 0; p < plan.n_passes; ++p) {
-      k_lsd_count<KeyT, HAS_VAL><<<(unsigned)n_tiles, kLsThreads, 0, stream>>>(ck, cv, n, plan.pass[p], counts, n_tiles);
+      NRP_LAUNCH((k_lsd_count<KeyT, HAS_VAL><<<(unsigned)n_tiles, kLsThreads, 0, stream>>>(ck, cv, n, plan.pass[p], counts, n_tiles)));
       exclusive_scan<uint32_t, uint32_t>(counts, offsets, n_counts, scan_scratch, stream);
-      k_lsd_scatter<KeyT, HAS_VAL><<<(unsigned)n_tiles, kLsThreads, 0, stream>>>(ck, cv, n, plan.pass[p], offsets, n_tiles, ak, av);
+      NRP_LAUNCH((k_lsd_scatter<KeyT, HAS_VAL><<<(unsigned)n_tiles, kLsThreads, 0, stream>>>(ck, cv, n, plan.pass[p], offsets, n_tiles, ak, av)));
       KeyT* tk = ck; ck = ak; ak = tk;
       uint32_t* tv = cv; cv = av; av = tv;
     }

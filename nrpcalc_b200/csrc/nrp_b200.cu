@@ -199,7 +199,8 @@ int configure_kernels(nrp_ctx* c) {
 // cand in (ck, cv) with alternates (ak, av); n_cand records.
 template <typename KeyT>
 int group_candidates(nrp_ctx* c, KeyT* ck, uint32_t* cv, KeyT* ak, uint32_t* av, int64_t n_cand, int key_bits, int val_bits,
-                     int64_t n_parts_for_flags, bool mark_repeats, StageTimer& tm, KeyT** sorted_keys, uint32_t** sorted_vals) {
+                     int64_t n_parts_for_flags, bool mark_repeats, StageTimer& tm, KeyT** sorted_keys, uint32_t** sorted_vals,
+                     int64_t* n_grouped, int64_t* n_repeat_records) {
   cudaStream_t st = c->stream;
   tm.begin(NRP_T_SORT);
   TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n_cand)));
@@ -216,12 +217,36 @@ int group_candidates(nrp_ctx* c, KeyT* ck, uint32_t* cv, KeyT* ak, uint32_t* av,
   TRY(c->pair_cnt.ensure(8 * n1)); TRY(c->pair_scan.ensure(8 * n1));
   TRY(c->scan_scratch.ensure(8 * (size_t)scan_scratch_elems((int64_t)n1 + 1)));
   unsigned long long* cnt = c->counters.as<unsigned long long>();
-  if (n_cand > 0) {
-    k_group_heads<KeyT><<<grid_for(n_cand, 256), 256, 0, st>>>(sk, sv, n_cand, c->part_base, n_parts_for_flags, c->head.as<uint32_t>(),
-                                                               mark_repeats ? c->flags.as<uint8_t>() : nullptr, cnt + CNT_REPEAT);
-    exclusive_scan<uint32_t, uint32_t>(c->head.as<uint32_t>(), c->head_scan.as<uint32_t>(), n_cand, c->scan_scratch.as<uint32_t>(), st);
-    k_group_starts<<<grid_for(n_cand + 1, 256), 256, 0, st>>>(c->head.as<uint32_t>(), c->head_scan.as<uint32_t>(), n_cand,
-                                                              c->group_start.as<uint32_t>());
+  int64_t n = n_cand;
+  *n_repeat_records = 0;
+  if (n > 0) {
+    NRP_LAUNCH((k_group_heads<KeyT><<<grid_for(n, 256), 256, 0, st>>>(sk, sv, n, c->part_base, n_parts_for_flags, c->head.as<uint32_t>(),
+                                                                  mark_repeats ? c->flags.as<uint8_t>() : nullptr, cnt + CNT_REPEAT)));
+    CU(cudaMemcpyAsync(c->h_counters + 18, cnt + CNT_REPEAT, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_repeat_records = (int64_t)c->h_counters[18];
+    if (mark_repeats && *n_repeat_records > 0) {
+      // drop every record of the flagged parts, keep the (key, part) order, and find the key runs again
+      KeyT* ok = sk == ck ? ak : ck;
+      uint32_t* ov = sv == cv ? av : cv;
+      NRP_LAUNCH((k_keep_unflagged<<<grid_for(n, 256), 256, 0, st>>>(sv, n, c->flags.as<uint8_t>() - c->part_base, c->valid.as<uint32_t>())));
+      exclusive_scan<uint32_t, uint32_t>(c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), n, c->scan_scratch.as<uint32_t>(), st);
+      NRP_LAUNCH((k_compact_records<KeyT><<<grid_for(n, 256), 256, 0, st>>>(sk, sv, c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), n, ok, ov)));
+      CU(cudaMemcpyAsync(c->h_counters + 19, c->valid_scan.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      n = (int64_t)(uint32_t)c->h_counters[19];
+      sk = ok; sv = ov;
+      *sorted_keys = sk; *sorted_vals = sv;
+      if (n > 0)
+        NRP_LAUNCH((k_group_heads<KeyT><<<grid_for(n, 256), 256, 0, st>>>(sk, sv, n, c->part_base, n_parts_for_flags, c->head.as<uint32_t>(),
+                                                                      nullptr, cnt + CNT_WORK)));
+    }
+  }
+  *n_grouped = n;
+  if (n > 0) {
+    exclusive_scan<uint32_t, uint32_t>(c->head.as<uint32_t>(), c->head_scan.as<uint32_t>(), n, c->scan_scratch.as<uint32_t>(), st);
+    NRP_LAUNCH((k_group_starts<<<grid_for(n + 1, 256), 256, 0, st>>>(c->head.as<uint32_t>(), c->head_scan.as<uint32_t>(), n,
+                                                                 c->group_start.as<uint32_t>())));
   }
   CU(cudaGetLastError());
   return NRP_OK;
@@ -307,8 +332,8 @@ int nrp_bg_set(nrp_ctx* c, const uint64_t* canon_kmers, int64_t n, int K) {
   CU(cudaMemcpyAsync(staging.ptr, canon_kmers, sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemsetAsync(c->bg_table.ptr, 0xff, table_bytes, c->stream));
   const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, c->n_sms * 8);
-  if (key_bytes == 4) k_bg_insert<uint32_t><<<grid, 256, 0, c->stream>>>(staging.as<uint64_t>(), n, c->bg_table.as<uint32_t>(), log_slots);
-  else k_bg_insert<uint64_t><<<grid, 256, 0, c->stream>>>(staging.as<uint64_t>(), n, c->bg_table.as<uint64_t>(), log_slots);
+  if (key_bytes == 4) NRP_LAUNCH((k_bg_insert<uint32_t><<<grid, 256, 0, c->stream>>>(staging.as<uint64_t>(), n, c->bg_table.as<uint32_t>(), log_slots)));
+  else NRP_LAUNCH((k_bg_insert<uint64_t><<<grid, 256, 0, c->stream>>>(staging.as<uint64_t>(), n, c->bg_table.as<uint64_t>(), log_slots)));
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
   staging.release();
@@ -348,8 +373,8 @@ int nrp_load_parts(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, con
   }
   TRY(c->tile_first.ensure(sizeof(uint32_t) * (size_t)(c->n_tiles + 2)));
   if (uniform == 0 && n_parts > 0)
-    k_tile_first_part<<<grid_for(c->n_tiles + 1, 256), 256, 0, c->stream>>>(c->off.as<int64_t>(), n_parts, total, c->n_tiles,
-                                                                            c->tile_first.as<uint32_t>());
+    NRP_LAUNCH((k_tile_first_part<<<grid_for(c->n_tiles + 1, 256), 256, 0, c->stream>>>(c->off.as<int64_t>(), n_parts, total, c->n_tiles,
+                                                                            c->tile_first.as<uint32_t>())));
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
   c->part_base = 0;
@@ -374,6 +399,7 @@ int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   if (m_max >= 0xffffe000ll) return fail(NRP_E_UNSUPPORTED, "%lld records exceed the 32-bit record index of one device", (long long)m_max);
 
   memset(c->counts, 0, sizeof(c->counts));
+  launch_counter() = 0;
   memset(c->timings, 0, sizeof(c->timings));
   c->counts[NRP_C_WINDOWS_MAX] = m_max;
   c->counts[NRP_C_KEY_BYTES] = sizeof(KeyT);
@@ -397,14 +423,14 @@ int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   CU(cudaMemsetAsync(c->flags.ptr, 0, (size_t)n_parts + 16, st));
   if (c->n_tiles > 0 && m_max >= 0) {
     if (!internal_repeats && (k % 2) == 0)
-      k_flag_windows<uint32_t><<<(unsigned)c->n_tiles, kTileThreads, 0, st>>>(P, k, 0, nullptr, 0, c->flags.as<uint8_t>());
+      NRP_LAUNCH((k_flag_windows<uint32_t><<<(unsigned)c->n_tiles, kTileThreads, 0, st>>>(P, k, 0, nullptr, 0, c->flags.as<uint8_t>())));
     if (c->bg_n > 0) {
       if (c->bg_key_bytes == 4)
-        k_flag_windows<uint32_t><<<(unsigned)c->n_tiles, kTileThreads, 0, st>>>(P, c->bg_K, 1, c->bg_table.as<uint32_t>(), c->bg_log_slots,
-                                                                              c->flags.as<uint8_t>());
+        NRP_LAUNCH((k_flag_windows<uint32_t><<<(unsigned)c->n_tiles, kTileThreads, 0, st>>>(P, c->bg_K, 1, c->bg_table.as<uint32_t>(), c->bg_log_slots,
+                                                                              c->flags.as<uint8_t>())));
       else
-        k_flag_windows<uint64_t><<<(unsigned)c->n_tiles, kTileThreads, 0, st>>>(P, c->bg_K, 1, c->bg_table.as<uint64_t>(), c->bg_log_slots,
-                                                                              c->flags.as<uint8_t>());
+        NRP_LAUNCH((k_flag_windows<uint64_t><<<(unsigned)c->n_tiles, kTileThreads, 0, st>>>(P, c->bg_K, 1, c->bg_table.as<uint64_t>(), c->bg_log_slots,
+                                                                              c->flags.as<uint8_t>())));
     }
   }
   CU(cudaGetLastError());
@@ -419,39 +445,39 @@ int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
 
   int64_t n_groups = 0, n_members = 0, n_pairs = 0, n_cand = 0, n_records = 0;
   KeyT* sk = nullptr; uint32_t* sv = nullptr;
-  for (int run = 0; run < 2; ++run) {
-    c->counts[NRP_C_RUNS] = run + 1;
+  {
+    c->counts[NRP_C_RUNS] = 1;
     tm.begin(NRP_T_HISTOGRAM);
     CU(cudaMemsetAsync(c->hist.ptr, 0, 4 * ((size_t)n_leaf + 2), st));
     CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * CNT_N, st));
     if (m_max > 0) {
       const unsigned hist_grid = (unsigned)std::min<int64_t>(c->n_tiles, (int64_t)c->n_sms * (bits >= 15 ? 1 : 2));
-      k_hist_from_ascii<<<hist_grid, kTileThreads, 4u << bits, st>>>(P, c->flags.as<uint8_t>(), k, bits, c->n_tiles, c->hist.as<uint32_t>());
+      NRP_LAUNCH((k_hist_from_ascii<<<hist_grid, kTileThreads, 4u << bits, st>>>(P, c->flags.as<uint8_t>(), k, bits, c->n_tiles, c->hist.as<uint32_t>())));
     }
     exclusive_scan<uint32_t, uint32_t>(c->hist.as<uint32_t>(), c->leaf_off.as<uint32_t>(), n_leaf, c->scan_scratch.as<uint32_t>(), st);
-    k_init_cursors<<<grid_for(n_leaf, 256), 256, 0, st>>>(c->leaf_off.as<uint32_t>(), r1, r2, c->cursor1.as<uint32_t>(), c->cursor2.as<uint32_t>());
+    NRP_LAUNCH((k_init_cursors<<<grid_for(n_leaf, 256), 256, 0, st>>>(c->leaf_off.as<uint32_t>(), r1, r2, c->cursor1.as<uint32_t>(), c->cursor2.as<uint32_t>())));
 
     tm.begin(NRP_T_SPLIT1);
     KeyT* leaf_keys = c->keysA.as<KeyT>(); uint32_t* leaf_vals = c->valsA.as<uint32_t>();
     KeyT* free_keys = c->keysB.as<KeyT>(); uint32_t* free_vals = c->valsB.as<uint32_t>();
     if (m_max > 0)
-      k_split_from_ascii<KeyT><<<(unsigned)c->n_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-          P, c->flags.as<uint8_t>(), k, r1, 0, c->part_base, r2 > 0 ? c->cursor1.as<uint32_t>() : c->cursor2.as<uint32_t>(), leaf_keys, leaf_vals);
+      NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->n_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+          P, c->flags.as<uint8_t>(), k, r1, 0, c->part_base, r2 > 0 ? c->cursor1.as<uint32_t>() : c->cursor2.as<uint32_t>(), leaf_keys, leaf_vals)));
     if (r2 > 0 && m_max > 0) {
       tm.begin(NRP_T_SPLIT2);
-      k_segment_tiles<<<1, 256, 0, st>>>(c->leaf_off.as<uint32_t>(), r1, r2, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>());
+      NRP_LAUNCH((k_segment_tiles<<<1, 256, 0, st>>>(c->leaf_off.as<uint32_t>(), r1, r2, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>())));
       const unsigned grid2 = (unsigned)std::min<int64_t>(m_max / kSplitTile + (1 << r1), (int64_t)c->n_sms * 4);
-      k_split_from_records<KeyT><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
-          leaf_keys, leaf_vals, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>(), r1, r2, c->cursor2.as<uint32_t>(), free_keys, free_vals);
+      NRP_LAUNCH((k_split_from_records<KeyT><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
+          leaf_keys, leaf_vals, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>(), r1, r2, c->cursor2.as<uint32_t>(), free_keys, free_vals)));
       std::swap(leaf_keys, free_keys); std::swap(leaf_vals, free_vals);
     }
     tm.begin(NRP_T_FILTER);
     if (m_max > 0) {
       const size_t fsm = (sizeof(KeyT) + 1) * 2 * (size_t)kFilterCap;
       const unsigned fgrid = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * (sizeof(KeyT) == 4 ? 2 : 1));
-      k_filter<KeyT, kFilterThreads, kFilterItems><<<fgrid, kFilterThreads, fsm, st>>>(
+      NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItems><<<fgrid, kFilterThreads, fsm, st>>>(
           leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, (uint32_t)c->opt_filter_cap,
-          reinterpret_cast<uint32_t*>(cnt + CNT_WORK), free_keys, free_vals, cnt + CNT_CAND, reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED));
+          reinterpret_cast<uint32_t*>(cnt + CNT_WORK), free_keys, free_vals, cnt + CNT_CAND, reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED))));
     }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_counters, cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, st));
@@ -462,18 +488,24 @@ int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
     c->counts[NRP_C_OVERSIZED] = (int64_t)(uint32_t)c->h_counters[CNT_OVERSIZED];
 
     // candidates live in (free_keys, free_vals); the leaf buffers are free again
-    TRY((group_candidates<KeyT>(c, free_keys, free_vals, leaf_keys, leaf_vals, n_cand, 2 * k, part_bits, n_parts, !internal_repeats, tm, &sk, &sv)));
-    int64_t n_runs_bound = n_cand;       // key runs <= candidates; the exact number stays on the device
-    if (n_cand > 0) {
-      // run count is head_scan[n_cand]; size kernels are launched over the bound and guard on it
-      CU(cudaMemcpyAsync(c->h_counters + 17, c->head_scan.as<uint32_t>() + n_cand, 4, cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(c->h_counters + 18, cnt + CNT_REPEAT, 8, cudaMemcpyDeviceToHost, st));
+    int64_t n_grp = 0, n_repeat = 0;
+    TRY((group_candidates<KeyT>(c, free_keys, free_vals, leaf_keys, leaf_vals, n_cand, 2 * k, part_bits, n_parts, !internal_repeats, tm,
+                                &sk, &sv, &n_grp, &n_repeat)));
+    if (!internal_repeats && n_repeat > 0) {
+      // windows of the parts just flagged were counted as records: take them out again
+      CU(cudaMemsetAsync(cnt + CNT_WORK, 0, 8, st));
+      NRP_LAUNCH((k_flagged_windows<<<grid_for(n_parts, 256), 256, 0, st>>>(c->off.as<int64_t>(), c->flags.as<uint8_t>(), n_parts, k, cnt + CNT_WORK)));
+      CU(cudaMemcpyAsync(c->h_counters + 27, cnt + CNT_WORK, 8, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      n_records -= (int64_t)c->h_counters[27];
+    }
+    int64_t n_runs_bound = 0;
+    if (n_grp > 0) {
+      CU(cudaMemcpyAsync(c->h_counters + 17, c->head_scan.as<uint32_t>() + n_grp, 4, cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
       n_runs_bound = (int64_t)(uint32_t)c->h_counters[17];
-      const int64_t n_repeat = (int64_t)c->h_counters[18];
-      if (!internal_repeats && n_repeat > 0 && run == 0) continue;   // flagged parts must vanish: run again
-      k_group_sizes<<<grid_for(n_runs_bound, 256), 256, 0, st>>>(c->group_start.as<uint32_t>(), n_runs_bound, c->valid.as<uint32_t>(),
-                                                                c->mem_cnt.as<uint32_t>(), c->pair_cnt.as<unsigned long long>());
+      NRP_LAUNCH((k_group_sizes<<<grid_for(n_runs_bound, 256), 256, 0, st>>>(c->group_start.as<uint32_t>(), n_runs_bound, c->valid.as<uint32_t>(),
+                                                                c->mem_cnt.as<uint32_t>(), c->pair_cnt.as<unsigned long long>())));
       exclusive_scan<uint32_t, uint32_t>(c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), n_runs_bound, c->scan_scratch.as<uint32_t>(), st);
       exclusive_scan<uint32_t, unsigned long long>(c->mem_cnt.as<uint32_t>(), c->mem_scan.as<unsigned long long>(), n_runs_bound,
                                                    c->scan_scratch.as<unsigned long long>(), st);
@@ -488,13 +520,13 @@ int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
       n_pairs = (int64_t)c->h_counters[22];
       TRY(c->g_keys.ensure(8 * (size_t)(n_groups + 1))); TRY(c->g_indptr.ensure(8 * (size_t)(n_groups + 2)));
       TRY(c->g_pair_off.ensure(8 * (size_t)(n_groups + 2))); TRY(c->g_members.ensure(4 * (size_t)(n_members + 1)));
-      k_group_emit<KeyT><<<grid_for(n_runs_bound + 1, 256), 256, 0, st>>>(
+      NRP_LAUNCH((k_group_emit<KeyT><<<grid_for(n_runs_bound + 1, 256), 256, 0, st>>>(
           sk, c->group_start.as<uint32_t>(), c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), c->mem_scan.as<unsigned long long>(),
           c->pair_scan.as<unsigned long long>(), n_runs_bound, c->g_keys.as<uint64_t>(), c->g_indptr.as<int64_t>(),
-          c->g_pair_off.as<unsigned long long>());
-      k_group_members<<<grid_for(n_cand, 256), 256, 0, st>>>(sv, c->head_scan.as<uint32_t>(), c->head.as<uint32_t>(), c->group_start.as<uint32_t>(),
-                                                             c->valid.as<uint32_t>(), c->mem_scan.as<unsigned long long>(), n_cand,
-                                                             c->g_members.as<uint32_t>());
+          c->g_pair_off.as<unsigned long long>())));
+      NRP_LAUNCH((k_group_members<<<grid_for(n_grp, 256), 256, 0, st>>>(sv, c->head_scan.as<uint32_t>(), c->head.as<uint32_t>(), c->group_start.as<uint32_t>(),
+                                                             c->valid.as<uint32_t>(), c->mem_scan.as<unsigned long long>(), n_grp,
+                                                             c->g_members.as<uint32_t>())));
       CU(cudaGetLastError());
     } else {
       n_groups = n_members = n_pairs = 0;
@@ -502,7 +534,6 @@ int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
       CU(cudaMemsetAsync(c->g_indptr.ptr, 0, 16, st));
       CU(cudaMemsetAsync(c->g_pair_off.ptr, 0, 16, st));
     }
-    break;
   }
   c->counts[NRP_C_RECORDS] = n_records;
   c->counts[NRP_C_CANDIDATES] = n_cand;
@@ -514,15 +545,15 @@ int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   tm.begin(NRP_T_ORDER);
   TRY(c->g_first_part.ensure(4 * (size_t)(n_groups + 1))); TRY(c->g_first_window.ensure(4 * (size_t)(n_groups + 1)));
   if (n_groups > 0) {
-    k_gather_first_part<<<grid_for(n_groups, 256), 256, 0, st>>>(c->g_indptr.as<int64_t>(), c->g_members.as<uint32_t>(), n_groups,
-                                                                 c->g_first_part.as<uint32_t>());
-    k_group_first_window<<<grid_for(n_groups, 128), 128, 0, st>>>(c->ascii.as<uint8_t>(), c->off.as<int64_t>(), c->g_keys.as<uint64_t>(),
+    NRP_LAUNCH((k_gather_first_part<<<grid_for(n_groups, 256), 256, 0, st>>>(c->g_indptr.as<int64_t>(), c->g_members.as<uint32_t>(), n_groups,
+                                                                 c->g_first_part.as<uint32_t>())));
+    NRP_LAUNCH((k_group_first_window<<<grid_for(n_groups, 128), 128, 0, st>>>(c->ascii.as<uint8_t>(), c->off.as<int64_t>(), c->g_keys.as<uint64_t>(),
                                                                   c->g_first_part.as<uint32_t>(), c->part_base, n_parts, n_groups, k,
-                                                                  c->g_first_window.as<uint32_t>());
+                                                                  c->g_first_window.as<uint32_t>())));
   }
   if (n_parts > 0)
-    k_last_single<<<grid_for(n_parts, 128), 128, 0, st>>>(c->ascii.as<uint8_t>(), c->off.as<int64_t>(), c->flags.as<uint8_t>(), n_parts, k,
-                                                          c->g_keys.as<uint64_t>(), n_groups, c->last_single.as<int32_t>());
+    NRP_LAUNCH((k_last_single<<<grid_for(n_parts, 128), 128, 0, st>>>(c->ascii.as<uint8_t>(), c->off.as<int64_t>(), c->flags.as<uint8_t>(), n_parts, k,
+                                                          c->g_keys.as<uint64_t>(), n_groups, c->last_single.as<int32_t>())));
   CU(cudaGetLastError());
 
   // ---- edges
@@ -536,34 +567,35 @@ int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
       TRY(c->e_head.ensure(4 * (size_t)(n_pairs + 2))); TRY(c->e_head_scan.ensure(4 * (size_t)(n_pairs + 2)));
       TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n_pairs)));
       TRY(c->scan_scratch.ensure(8 * (size_t)scan_scratch_elems(n_pairs + 2)));
-      k_edge_pairs<<<grid_for(n_members, 128), 128, 0, st>>>(c->g_indptr.as<int64_t>(), c->g_members.as<uint32_t>(),
+      NRP_LAUNCH((k_edge_pairs<<<grid_for(n_members, 128), 128, 0, st>>>(c->g_indptr.as<int64_t>(), c->g_members.as<uint32_t>(),
                                                              c->g_pair_off.as<unsigned long long>(), n_groups, n_members,
-                                                             c->part_id.as<uint32_t>(), c->part_base, c->e_codesA.as<uint64_t>());
+                                                             c->part_id.as<uint32_t>(), c->part_base, c->e_codesA.as<uint64_t>())));
       LsdPlan plan; plan.n_passes = 0;
       lsd_plan_add(plan, 0, 0, 64);
       uint64_t* sorted_codes;
       lsd_sort<uint64_t, false>(c->e_codesA.as<uint64_t>(), nullptr, c->e_codesB.as<uint64_t>(), nullptr, n_pairs, plan,
                                 c->lsd_scratch.as<uint32_t>(), st, &sorted_codes, nullptr);
-      k_edge_heads<<<grid_for(n_pairs, 256), 256, 0, st>>>(sorted_codes, n_pairs, c->e_head.as<uint32_t>());
+      NRP_LAUNCH((k_edge_heads<<<grid_for(n_pairs, 256), 256, 0, st>>>(sorted_codes, n_pairs, c->e_head.as<uint32_t>())));
       exclusive_scan<uint32_t, uint32_t>(c->e_head.as<uint32_t>(), c->e_head_scan.as<uint32_t>(), n_pairs, c->scan_scratch.as<uint32_t>(), st);
       CU(cudaMemcpyAsync(c->h_counters + 24, c->e_head_scan.as<uint32_t>() + n_pairs, 4, cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
       n_edges = (int64_t)(uint32_t)c->h_counters[24];
       TRY(c->e_u.ensure(4 * (size_t)(n_edges + 1))); TRY(c->e_v.ensure(4 * (size_t)(n_edges + 1)));
-      k_edge_compact<<<grid_for(n_pairs, 256), 256, 0, st>>>(sorted_codes, c->e_head.as<uint32_t>(), c->e_head_scan.as<uint32_t>(), n_pairs,
-                                                             c->e_u.as<uint32_t>(), c->e_v.as<uint32_t>());
+      NRP_LAUNCH((k_edge_compact<<<grid_for(n_pairs, 256), 256, 0, st>>>(sorted_codes, c->e_head.as<uint32_t>(), c->e_head_scan.as<uint32_t>(), n_pairs,
+                                                             c->e_u.as<uint32_t>(), c->e_v.as<uint32_t>())));
       CU(cudaGetLastError());
     }
     c->counts[NRP_C_EDGES] = n_edges;
   }
   tm.begin(NRP_T_GROUP);
   CU(cudaMemsetAsync(cnt + CNT_FLAGGED, 0, 8, st));
-  if (n_parts > 0) k_count_flagged<<<grid_for(n_parts, 256), 256, 0, st>>>(c->flags.as<uint8_t>(), n_parts, cnt + CNT_FLAGGED);
+  if (n_parts > 0) NRP_LAUNCH((k_count_flagged<<<grid_for(n_parts, 256), 256, 0, st>>>(c->flags.as<uint8_t>(), n_parts, cnt + CNT_FLAGGED)));
   CU(cudaMemcpyAsync(c->h_counters + 26, cnt + CNT_FLAGGED, 8, cudaMemcpyDeviceToHost, st));
   tm.finish(c->timings);
   CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
   c->counts[NRP_C_EXCLUDED] = (int64_t)c->h_counters[26];
+  c->counts[NRP_C_LAUNCHES] = launch_counter();
   double total = 0;
   for (int i = NRP_T_FLAGS; i < NRP_N_TIMINGS; ++i) total += c->timings[i];
   c->timings[NRP_T_TOTAL] = total;

@@ -87,14 +87,14 @@ void exclusive_scan(const Tin* in, Tout* out, int64_t n_in, Tout* scratch, cudaS
   const int64_t n_out = n_in + 1;
   const int64_t tiles = (n_out + kScanTile - 1) / kScanTile;
   if (tiles == 1) {
-    k_scan_tiles<Tin, Tout><<<1, kScanThreads, 0, stream>>>(in, out, nullptr, n_in, n_out);
+    NRP_LAUNCH((k_scan_tiles<Tin, Tout><<<1, kScanThreads, 0, stream>>>(in, out, nullptr, n_in, n_out)));
     return;
   }
   Tout* sums = scratch;                 // [0, tiles): per-tile totals
   Tout* offsets = scratch + tiles + 1;  // [tiles+1, 2*tiles+2): their exclusive scan (+ grand total)
-  k_scan_tiles<Tin, Tout><<<(unsigned)tiles, kScanThreads, 0, stream>>>(in, out, sums, n_in, n_out);
+  NRP_LAUNCH((k_scan_tiles<Tin, Tout><<<(unsigned)tiles, kScanThreads, 0, stream>>>(in, out, sums, n_in, n_out)));
   exclusive_scan<Tout, Tout>(sums, offsets, tiles, scratch + 2 * (tiles + 1), stream);
-  k_scan_add<Tout><<<(unsigned)tiles, kScanThreads, 0, stream>>>(out, offsets, n_out);
+  NRP_LAUNCH((k_scan_add<Tout><<<(unsigned)tiles, kScanThreads, 0, stream>>>(out, offsets, n_out)));
 }
 
 }  // namespace nrp

@@ -75,6 +75,32 @@ __global__ void k_group_heads(const KeyT* keys, const uint32_t* vals, int64_t n,
   }
 }
 
+// records of parts flagged for an internal repeat must vanish from every group (the reference drops such a part
+// before it touches the table, hgraph.py:50-69): keep[i] = 1 unless the record's part carries the repeat flag.
+// flags_global is indexed by the record value itself (global part index).
+__global__ void k_keep_unflagged(const uint32_t* vals, int64_t n, const uint8_t* flags_by_val, uint32_t* keep) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keep[i] = (flags_by_val[vals[i]] & kFlagRepeat) ? 0u : 1u;
+}
+
+template <typename KeyT>
+__global__ void k_compact_records(const KeyT* keys, const uint32_t* vals, const uint32_t* keep, const uint32_t* keep_scan, int64_t n,
+                                  KeyT* out_keys, uint32_t* out_vals) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !keep[i]) return;
+  uint32_t o = keep_scan[i];
+  out_keys[o] = keys[i];
+  out_vals[o] = vals[i];
+}
+
+// windows of the parts that carry the repeat flag (they were counted as records before the flag was known)
+__global__ void k_flagged_windows(const int64_t* off, const uint8_t* flags, int64_t n_parts, int k, unsigned long long* out) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_parts || !(flags[p] & kFlagRepeat)) return;
+  int64_t w = off[p + 1] - off[p] - k + 1;
+  if (w > 0) atomicAdd(out, (unsigned long long)w);
+}
+
 // group_start[g] for every key run (g = exclusive scan of head), plus the sentinel group_start[n_groups] = n
 __global__ void k_group_starts(const uint32_t* head, const uint32_t* head_scan, int64_t n, uint32_t* group_start) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

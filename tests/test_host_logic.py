@@ -1,0 +1,122 @@
+"""CPU tests of the host layer: stream ordering + clique replay + recovery/vertex cover + finder wrapper,
+with the device call replaced by the numpy oracle (tests/fake_device.py).  Expected values are the golden
+fixtures produced by the unmodified reference."""
+import json
+import os
+import random
+
+import networkx as nx
+import pytest
+
+import fake_device
+import nrpcalc_b200
+from conftest import GOLDEN_CASES
+from nrpcalc_b200 import hgraph, recovery, vercov
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(autouse=True)
+def oracle_device(monkeypatch, scratch_cwd):
+    monkeypatch.setattr(hgraph, 'repeat_structure', fake_device.oracle_repeat_structure)
+
+
+def _background(case):
+    if case['bg_seqs'] is None:
+        return None
+    bg = nrpcalc_b200.background(path='./bg_store/', Lmax=case['bg_Lmax'], verbose=False)
+    bg.multiadd(case['bg_seqs'])
+    assert len(bg) == case['bg_len']
+    return bg
+
+
+@pytest.mark.parametrize('case', GOLDEN_CASES, ids=[c['name'] for c in GOLDEN_CASES])
+def test_graph_order_matches_reference(case):
+    bg = _background(case)
+    graph = hgraph.get_homology_graph(list(case['parts']), bg, case['Lmax'] + 1, case['internal_repeats'], './seq.txt', False)
+    assert list(graph.nodes()) == case['graph_nodes']
+    assert [list(graph[n]) for n in graph.nodes()] == case['graph_adj']
+    lines = open('./seq.txt').read().splitlines()
+    assert lines == ['{},{}'.format(i, case['parts'][i].upper()) for i in case['seq_file_ids']]
+    if bg is not None:
+        bg.drop()
+
+
+@pytest.mark.parametrize('case', GOLDEN_CASES, ids=[c['name'] for c in GOLDEN_CASES])
+def test_finder_toolbox_matches_reference(case):
+    bg = _background(case)
+    for vc, by_seed in case['toolbox'].items():
+        for seed, expected_ids in by_seed.items():
+            random.seed(int(seed))
+            parts = list(case['parts'])
+            found = nrpcalc_b200.finder(seq_list=parts, Lmax=case['Lmax'], internal_repeats=case['internal_repeats'],
+                                        background=bg, vercov=vc, output_file=None, verbose=False)
+            assert parts == case['parts']                       # caller's list untouched
+            assert list(found.keys()) == expected_ids, (vc, seed)
+            assert all(found[i] == case['parts'][i].upper() for i in expected_ids)
+    if bg is not None:
+        bg.drop()
+
+
+def test_verbose_run_gives_same_toolbox(capsys):
+    case = next(c for c in GOLDEN_CASES if c['name'] == 'planted_s0_L15_ir0')
+    random.seed(7)
+    found = nrpcalc_b200.finder(case['parts'], case['Lmax'], vercov='nrp2', verbose=True)
+    assert list(found) == case['toolbox']['nrp2']['7']
+    out = capsys.readouterr().out
+    assert '[Non-Repetitive Parts Calculator - Finder Mode]' in out and 'Non-Repetitive Toolbox Size' in out
+
+
+def test_fasta_output(tmp_path):
+    case = next(c for c in GOLDEN_CASES if c['name'] == 'docstring_finder_example')
+    bg = _background(case)
+    out = str(tmp_path / 'toolbox.fa')
+    found = nrpcalc_b200.finder(case['parts'], 15, background=bg, output_file=out, verbose=False)
+    assert found == {1: 'GCAGATAGGGGGTAGTA', 0: 'AGAGCTATGACTGACGT'}          # reference docstring, nrpcalc.py:376
+    assert list(found) == [1, 0]
+    assert open(out).read() == '>index 1\nGCAGATAGGGGGTAGTA\n>index 0\nAGAGCTATGACTGACGT\n'
+    bg.drop()
+
+
+def test_argument_errors():
+    with pytest.raises(RuntimeError, match='Invalid Constraints, or Background'):
+        nrpcalc_b200.finder(['ACGT', 5], 12, verbose=False)
+    with pytest.raises(RuntimeError):
+        nrpcalc_b200.finder(['ACGTACGTACGTACGT'], 4, verbose=False)
+    with pytest.raises(RuntimeError):
+        nrpcalc_b200.finder(['ACGTACGTACGTACGT'], 12, vercov='best', verbose=False)
+    with pytest.raises(RuntimeError):
+        nrpcalc_b200.finder(['ACGTACGTACGTACGT'], 12, background='not a background', verbose=False)
+    with pytest.raises(RuntimeError):
+        nrpcalc_b200.finder(['ACGTACGTACGTACGT'], 12, internal_repeats='yes', verbose=False)
+    assert nrpcalc_b200.finder([], 12, verbose=False) == {}
+
+
+def test_closed_background_raises_like_reference():
+    bg = nrpcalc_b200.background(path='./closed_bg/', Lmax=12, verbose=False)
+    bg.add('ACGTTGCATGCATGCAAAGT')
+    bg.close()
+    with pytest.raises(RuntimeError, match='closed or dropped'):
+        nrpcalc_b200.finder(['ACGTTGCATGCATGCAAAGTCC'], 12, background=bg, verbose=False)
+
+
+def test_vertex_cover_routines_cover_every_edge():
+    rnd = random.Random(5)
+    graph = nx.gnm_random_graph(120, 260, seed=3)
+    for name in ('nrp2', 'nrpG', '2apx'):
+        random.seed(11)
+        routine, _ = vercov.ROUTINES[name]
+        cover = routine(nx.Graph(graph), False)
+        assert all(u in cover or v in cover for u, v in graph.edges())
+    del rnd
+
+
+def test_recovery_returns_maximal_independent_set():
+    graph = nx.gnm_random_graph(150, 300, seed=9)
+    for name in ('nrp2', 'nrpG', '2apx'):
+        random.seed(3)
+        chosen = recovery.get_recovered_non_homologs(nx.Graph(graph), './graph.txt', name, False)
+        assert all(not (u in chosen and v in chosen) for u, v in graph.edges())
+        for node in graph.nodes():
+            if node not in chosen:
+                assert any(nb in chosen for nb in graph[node])       # cannot be extended

@@ -127,3 +127,29 @@ def test_ref_port_against_live_reference(seed, scratch_cwd):
             mine, _ = ref_port.homology_graph(list(parts), None, k, internal)
             assert list(theirs.nodes()) == list(mine.nodes())
             assert [list(theirs[n]) for n in theirs.nodes()] == [list(mine[n]) for n in mine.nodes()]
+
+
+@pytest.mark.parametrize('seed', range(3))
+@pytest.mark.parametrize('k', [6, 13, 17, 32])
+@pytest.mark.parametrize('threads', [1, 3])
+def test_c_oracle_equals_np_oracle(seed, k, threads):
+    """oracle/nrp_oracle.c (hash table in insertion order, like the reference's dict) against the numpy spec."""
+    from oracle import c_oracle
+    parts = cases.planted_parts(250, 300 + seed)
+    bg_keys = np_oracle.canonical_key_set(cases.background_seqs_for(parts, seed), 14) if seed else None
+    for internal in (False, True):
+        uniq = [(pid, seq) for pid, seq in ref_port.uniquify(list(parts)) if len(seq) >= k]
+        want = np_oracle.spec(uniq, k, internal, bg_keys, 14)
+        seqs = [seq for _, seq in uniq]
+        offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum([len(s) for s in seqs], out=offsets[1:])
+        buf = np.frombuffer(''.join(seqs).encode(), dtype=np.uint8)
+        got = c_oracle.build_table(buf, offsets, k, internal, bg_keys, 14, n_threads=threads)
+        assert got['flags'].tolist() == want['flags'].tolist()
+        assert got['n_records'] == want['n_records']
+        assert got['last_single'].tolist() == want['last_single'].tolist()
+        ids = want['ids']
+        groups = sorted((int(got['rank_p'][g]), int(got['rank_j'][g]),
+                         tuple(int(ids[m]) for m in got['members'][got['indptr'][g]:got['indptr'][g + 1]]))
+                        for g in range(got['n_groups']))
+        assert groups == sorted(want['groups'])
