@@ -151,6 +151,42 @@ __device__ __forceinline__ bool tile_canonical(const Parts& P, const TileStage& 
   return true;
 }
 
+// Blocked iteration: thread t owns the kTileItems consecutive window start positions 8t..8t+7 of the tile.
+// The forward value and its reverse complement ROLL from one window to the next (one shift-or each) and the
+// part lookup is done once per thread; parts are advanced when a position passes the current part's end.
+// f(e, canon, part, is_palindrome) is called for every position that starts a valid window, e ascending.
+template <typename F>
+__device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileStage& s, int64_t tile, int k, F f) {
+  const int c0 = threadIdx.x * kTileItems;
+  int64_t g = tile * kTileBytes + c0;
+  if (g >= P.total_len) return;
+  int64_t part, end;
+  tile_locate(P, s, g, part, end);
+  const int w = c0 >> 4, sh = (c0 & 15) * 2;                  // sh is 0 or 16
+  const uint32_t x0 = s.packed[w], x1 = s.packed[w + 1], x2 = s.packed[w + 2];
+  uint64_t v = ((uint64_t)__funnelshift_l(x1, x0, sh) << 32) | __funnelshift_l(x2, x1, sh);   // bases c0 .. c0+31
+  const uint32_t next16 = (x2 >> (16 - sh)) & 0xffffu;       // bases c0+32 .. c0+39
+  const int down = 64 - 2 * k, top = 2 * k - 2;
+  uint64_t fwd = v >> down;
+  uint64_t rc = revcomp2(fwd, k);
+#pragma unroll
+  for (int e = 0; e < kTileItems; ++e) {
+    if (e > 0) {
+      v = (v << 2) | ((next16 >> (16 - 2 * e)) & 3u);
+      fwd = v >> down;
+      rc = (rc >> 2) | ((uint64_t)(3u - ((uint32_t)fwd & 3u)) << top);
+      ++g;
+      if (g >= P.total_len) break;
+      while (g >= end) {                                      // next part (skipping empty ones)
+        ++part;
+        if (P.uniform_len > 0) end += P.uniform_len;
+        else end = s.n_slice > 0 ? s.slice[part - s.first_part + 1] : P.off[part + 1];
+      }
+    }
+    if (g + k <= end) f(e, fwd < rc ? fwd : rc, (uint32_t)part, fwd == rc);
+  }
+}
+
 // first part of every byte tile (variable-length parts only): one thread per tile
 __global__ void k_tile_first_part(const int64_t* off, int64_t n_parts, int64_t total_len, int64_t n_tiles, uint32_t* tile_first) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;

@@ -105,12 +105,9 @@ __global__ void __launch_bounds__(kTileThreads) k_hist_from_ascii(Parts P, const
     __syncthreads();
     tile_load(P, tile, stage);
     __syncthreads();
-#pragma unroll
-    for (int e = 0; e < kTileItems; ++e) {
-      Window w;
-      if (tile_canonical(P, stage, tile, threadIdx.x + e * kTileThreads, k, w) && !(flags && flags[w.part]))
-        atomicAdd(&s_hist[key_hash(w.canon) >> (64 - bits)], 1u);
-    }
+    tile_windows_blocked(P, stage, tile, k, [&](int, uint64_t canon, uint32_t part, bool) {
+      if (!(flags && flags[part])) atomicAdd(&s_hist[key_hash(canon) >> (64 - bits)], 1u);
+    });
   }
   __syncthreads();
   for (int i = threadIdx.x; i < nb; i += blockDim.x) {
@@ -152,18 +149,15 @@ __global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, cons
   KeyT key[kSplitItems];
   uint32_t val[kSplitItems], dr[kSplitItems];
 #pragma unroll
-  for (int e = 0; e < kSplitItems; ++e) {
-    Window w;
-    dr[e] = 0xffffffffu;
-    key[e] = 0; val[e] = 0;
-    if (tile_canonical(P, stage, tile, threadIdx.x + e * kTileThreads, k, w) && !(flags && flags[w.part])) {
-      uint32_t d = n_owners > 0 ? owner_hash(w.canon) % (uint32_t)n_owners : (uint32_t)(key_hash(w.canon) >> (64 - r1));
-      uint32_t rank = atomicAdd(&s.cnt[d], 1u);
-      key[e] = (KeyT)w.canon;
-      val[e] = part_base + w.part;
-      dr[e] = (d << 16) | rank;
-    }
-  }
+  for (int e = 0; e < kSplitItems; ++e) { dr[e] = 0xffffffffu; key[e] = 0; val[e] = 0; }
+  tile_windows_blocked(P, stage, tile, k, [&](int e, uint64_t canon, uint32_t part, bool) {
+    if (flags && flags[part]) return;
+    uint32_t d = n_owners > 0 ? owner_hash(canon) % (uint32_t)n_owners : (uint32_t)(key_hash(canon) >> (64 - r1));
+    uint32_t rank = atomicAdd(&s.cnt[d], 1u);
+#pragma unroll
+    for (int q = 0; q < kSplitItems; ++q)
+      if (q == e) { key[q] = (KeyT)canon; val[q] = part_base + part; dr[q] = (d << 16) | rank; }
+  });
   __syncthreads();
   if (n_owners > 0)
     split_scatter<KeyT>(s, key, val, dr, nb, OwnerDigit{(uint32_t)n_owners}, cursor, out_keys, out_vals);
@@ -175,7 +169,7 @@ __global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, cons
 // Segment b = level-1 bucket b = records [seg_off[b], seg_off[b+1]); its tiles are numbered from tile_prefix[b].
 // Leaf bucket id = top (r1 + r2) bits of the hash; cursor has 2^(r1+r2) entries.
 template <typename KeyT>
-__global__ void __launch_bounds__(kSplitThreads) k_split_from_records(const KeyT* in_keys, const uint32_t* in_vals,
+__global__ void __launch_bounds__(kSplitThreads) k_split_from_records(const KeyT* __restrict__ in_keys, const uint32_t* __restrict__ in_vals,
                                                                      const uint32_t* seg_off, const uint32_t* tile_prefix, int r1, int r2,
                                                                      uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -200,12 +194,17 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_from_records(const KeyT
     uint32_t val[kSplitItems], dr[kSplitItems];
     const uint32_t mask = (1u << r2) - 1u;
 #pragma unroll
+    for (int e = 0; e < kSplitItems; ++e) {                  // all loads first: 16 independent requests per thread
+      uint32_t idx = start + threadIdx.x + e * kSplitThreads;
+      bool ok = idx < end;
+      key[e] = ok ? __ldg(in_keys + idx) : KeyT(0);
+      val[e] = ok ? __ldg(in_vals + idx) : 0u;
+    }
+#pragma unroll
     for (int e = 0; e < kSplitItems; ++e) {
       uint32_t idx = start + threadIdx.x + e * kSplitThreads;
-      dr[e] = 0xffffffffu; key[e] = 0; val[e] = 0;
+      dr[e] = 0xffffffffu;
       if (idx < end) {
-        key[e] = in_keys[idx];
-        val[e] = in_vals[idx];
         uint32_t d = (uint32_t)(key_hash((uint64_t)key[e]) >> (64 - r1 - r2)) & mask;
         dr[e] = (d << 16) | atomicAdd(&s.cnt[d], 1u);
       }

@@ -46,16 +46,13 @@ __global__ void __launch_bounds__(kTileThreads) k_flag_windows(Parts P, int klen
   const int64_t tile = blockIdx.x;
   tile_load(P, tile, stage);
   __syncthreads();
-#pragma unroll
-  for (int e = 0; e < kTileItems; ++e) {
-    Window w;
-    if (!tile_canonical(P, stage, tile, threadIdx.x + e * kTileThreads, klen, w)) continue;
+  tile_windows_blocked(P, stage, tile, klen, [&](int, uint64_t canon, uint32_t part, bool palindrome) {
     if (mode == 0) {
-      if (w.palindrome) flags[w.part] |= kFlagPalindrome;          // benign race: all writers OR the same bit
+      if (palindrome) flags[part] |= kFlagPalindrome;             // benign race: all writers OR the same bit
     } else {
-      if (!(flags[w.part] & kFlagBackground) && bg_contains<BgKeyT>(bg_table, bg_log_slots, w.canon)) flags[w.part] |= kFlagBackground;
+      if (!(flags[part] & kFlagBackground) && bg_contains<BgKeyT>(bg_table, bg_log_slots, canon)) flags[part] |= kFlagBackground;
     }
-  }
+  });
 }
 
 // ---- grouping of the sorted candidate records -------------------------------------------------------------
