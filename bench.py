@@ -187,7 +187,7 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    cfg_name = args.config or ('c2' if args.gpus == 1 else 'c4')
+    cfg_name = args.config or 'c2'
     cfg = CONFIGS[cfg_name]
 
     if args.impl == 'reference':

@@ -127,6 +127,36 @@ int nrp_result_last_single(nrp_ctx* ctx, int32_t* last_single);
 /* u[n_edges] < v[n_edges], unique, sorted by (u, v) */
 int nrp_result_edges(nrp_ctx* ctx, uint32_t* u, uint32_t* v);
 
+/* ---- sharded path: one process per GPU, k-mer space hash-partitioned across n_owners ranks ---------------------
+ * Every rank stages ALL parts with nrp_load_parts (record values are then global part indices and any rank can
+ * read any part), extracts the records of its own contiguous shard of parts, and owns the k-mers with
+ * owner_hash(k-mer) % n_owners == rank.  Between the calls the host layer moves data with torch.distributed:
+ *
+ *   nrp_shard_extract      flags + records of parts [part_lo, part_hi), partitioned by owner; counts per owner
+ *   (all-to-all of the counts and of the records: NCCL over NVLink)
+ *   nrp_shard_group        partition + filter + sort of the records this rank owns; marks internal repeats in flags
+ *   (all-reduce MAX of the per-part flags, nrp_flags_export / nrp_flags_import)
+ *   nrp_shard_finish       drops records of flagged parts, builds this rank's groups (+ first windows, + local edges)
+ *   (all-gather of the shared k-mers)
+ *   nrp_shard_last_single  last unshared window of the parts of this rank's shard
+ */
+/* run all work of the context on a caller-owned CUDA stream (cudaStream_t), e.g. torch's current stream; NULL
+ * restores a private stream */
+int nrp_ctx_set_stream(nrp_ctx* ctx, void* cuda_stream);
+int nrp_shard_extract(nrp_ctx* ctx, int64_t part_lo, int64_t part_hi, int k, int internal_repeats, int n_owners,
+                      int64_t* owner_counts /* n_owners, host */);
+/* device pointers of the owner-partitioned records (owner o's run starts at the prefix sum of owner_counts) */
+int nrp_shard_send_buffers(nrp_ctx* ctx, void** keys, void** vals, int* key_bytes);
+/* keys_dev/vals_dev: n_records received records in device memory, borrowed until the call returns */
+int nrp_shard_group(nrp_ctx* ctx, const void* keys_dev, const uint32_t* vals_dev, int64_t n_records, int k, int internal_repeats);
+/* copy the n_parts per-part flag bytes to / from caller-owned device memory (for the all-reduce) */
+int nrp_flags_export(nrp_ctx* ctx, uint8_t* dst_dev);
+int nrp_flags_import(nrp_ctx* ctx, const uint8_t* src_dev);
+int nrp_shard_finish(nrp_ctx* ctx, int k, int internal_repeats, int want_edges);
+/* shared_keys_sorted: ascending canonical k-mers of ALL ranks' groups (host memory); afterwards
+ * nrp_result_last_single holds valid entries for the parts of this rank's shard */
+int nrp_shard_last_single(nrp_ctx* ctx, const uint64_t* shared_keys_sorted, int64_t n_shared, int k);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,14 @@ def _declare(lib):
         'nrp_result_groups': (c_ctx, ptr, ptr, ptr, ptr),
         'nrp_result_last_single': (c_ctx, ptr),
         'nrp_result_edges': (c_ctx, ptr, ptr),
+        'nrp_ctx_set_stream': (c_ctx, ptr),
+        'nrp_shard_extract': (c_ctx, i64, i64, i32, i32, i32, ptr),
+        'nrp_shard_send_buffers': (c_ctx, ctypes.POINTER(ptr), ctypes.POINTER(ptr), ctypes.POINTER(i32)),
+        'nrp_shard_group': (c_ctx, ptr, ptr, i64, i32, i32),
+        'nrp_flags_export': (c_ctx, ptr),
+        'nrp_flags_import': (c_ctx, ptr),
+        'nrp_shard_finish': (c_ctx, i32, i32, i32),
+        'nrp_shard_last_single': (c_ctx, ptr, i64, i32),
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -143,6 +151,38 @@ class Context(object):
 
     def build(self, k, internal_repeats, want_edges=True):
         _check(self._lib, self._lib.nrp_build(self._h, int(k), 1 if internal_repeats else 0, 1 if want_edges else 0))
+
+    # ---- sharded path (device pointers are plain ints, e.g. torch.Tensor.data_ptr()) --------------------
+    def set_stream(self, cuda_stream):
+        _check(self._lib, self._lib.nrp_ctx_set_stream(self._h, ctypes.c_void_p(int(cuda_stream) if cuda_stream else None)))
+
+    def shard_extract(self, part_lo, part_hi, k, internal_repeats, n_owners):
+        counts = np.zeros(n_owners, dtype=np.int64)
+        _check(self._lib, self._lib.nrp_shard_extract(self._h, int(part_lo), int(part_hi), int(k), 1 if internal_repeats else 0,
+                                                      int(n_owners), _p(counts)))
+        return counts
+
+    def shard_send_buffers(self):
+        keys, vals, kb = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int()
+        _check(self._lib, self._lib.nrp_shard_send_buffers(self._h, ctypes.byref(keys), ctypes.byref(vals), ctypes.byref(kb)))
+        return keys.value or 0, vals.value or 0, kb.value
+
+    def shard_group(self, keys_ptr, vals_ptr, n_records, k, internal_repeats):
+        _check(self._lib, self._lib.nrp_shard_group(self._h, ctypes.c_void_p(int(keys_ptr) or None), ctypes.c_void_p(int(vals_ptr) or None),
+                                                    int(n_records), int(k), 1 if internal_repeats else 0))
+
+    def flags_export(self, dst_ptr):
+        _check(self._lib, self._lib.nrp_flags_export(self._h, ctypes.c_void_p(int(dst_ptr))))
+
+    def flags_import(self, src_ptr):
+        _check(self._lib, self._lib.nrp_flags_import(self._h, ctypes.c_void_p(int(src_ptr))))
+
+    def shard_finish(self, k, internal_repeats, want_edges):
+        _check(self._lib, self._lib.nrp_shard_finish(self._h, int(k), 1 if internal_repeats else 0, 1 if want_edges else 0))
+
+    def shard_last_single(self, shared_keys_sorted, k):
+        keys = np.ascontiguousarray(shared_keys_sorted, dtype=np.uint64)
+        _check(self._lib, self._lib.nrp_shard_last_single(self._h, _p(keys) if keys.size else None, keys.size, int(k)))
 
     def counts(self):
         out = np.zeros(N_COUNTS, dtype=np.int64)

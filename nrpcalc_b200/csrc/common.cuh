@@ -55,6 +55,8 @@ struct Parts {
   int64_t n_parts;
   int64_t total_len;
   int uniform_len;             // > 0: every part has exactly this length (fast path, no offsets lookup)
+  int64_t part_lo, part_hi;    // only windows of parts in [part_lo, part_hi) are produced (this rank's shard)
+  int64_t tile_lo;             // first byte tile of the shard (kernels add it to blockIdx.x)
 };
 
 constexpr int kTileBytes = 4096;      // window start positions handled by one CTA
@@ -183,7 +185,7 @@ __device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileS
         else end = s.n_slice > 0 ? s.slice[part - s.first_part + 1] : P.off[part + 1];
       }
     }
-    if (g + k <= end) f(e, fwd < rc ? fwd : rc, (uint32_t)part, fwd == rc);
+    if (g + k <= end && part >= P.part_lo && part < P.part_hi) f(e, fwd < rc ? fwd : rc, (uint32_t)part, fwd == rc);
   }
 }
 

@@ -106,6 +106,7 @@ struct nrp_ctx {
   int uniform_len = 0;
   bool have_parts = false, have_ids = false;
   uint32_t part_base = 0;
+  int64_t max_id = 0;
 
   // pipeline buffers
   DevBuf flags, hist, leaf_off, cursor1, cursor2, seg_off, tile_prefix, counters, scan_scratch, lsd_scratch;
@@ -114,6 +115,17 @@ struct nrp_ctx {
   DevBuf g_keys, g_indptr, g_pair_off, g_members, g_first_part, g_first_window, last_single;
   DevBuf e_codesA, e_codesB, e_head, e_head_scan, e_u, e_v;
   unsigned long long* h_counters = nullptr;   // pinned
+
+  // shard window (whole batch unless nrp_shard_extract narrowed it)
+  int64_t shard_lo = 0, shard_hi = 0, shard_tile_lo = 0, shard_tiles = 0, shard_m_max = 0;
+  int n_owners = 0;
+  bool external_stream = false;
+
+  // candidate records between the stages (type-erased: uint32_t* or uint64_t* keys)
+  void* cand_keys = nullptr; uint32_t* cand_vals = nullptr;     // candidates / sorted candidates
+  void* spare_keys = nullptr; uint32_t* spare_vals = nullptr;   // scratch of the same size
+  int64_t n_cand = 0, n_sorted = 0, n_records = 0, n_repeat_records = 0;
+  int64_t n_groups = 0, n_members = 0, n_pairs = 0;
 
   // result of the last build
   bool have_result = false;
@@ -132,6 +144,9 @@ Parts parts_view(const nrp_ctx* c) {
   P.n_parts = c->n_parts;
   P.total_len = c->total_len;
   P.uniform_len = c->uniform_len;
+  P.part_lo = c->shard_lo;
+  P.part_hi = c->shard_hi;
+  P.tile_lo = c->shard_tile_lo;
   return P;
 }
 
@@ -195,63 +210,6 @@ int configure_kernels(nrp_ctx* c) {
   return NRP_OK;
 }
 
-// Sort the candidate records and turn key runs into groups.  On return the counters (host) hold the sizes.
-// cand in (ck, cv) with alternates (ak, av); n_cand records.
-template <typename KeyT>
-int group_candidates(nrp_ctx* c, KeyT* ck, uint32_t* cv, KeyT* ak, uint32_t* av, int64_t n_cand, int key_bits, int val_bits,
-                     int64_t n_parts_for_flags, bool mark_repeats, StageTimer& tm, KeyT** sorted_keys, uint32_t** sorted_vals,
-                     int64_t* n_grouped, int64_t* n_repeat_records) {
-  cudaStream_t st = c->stream;
-  tm.begin(NRP_T_SORT);
-  TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n_cand)));
-  LsdPlan plan = lsd_plan(key_bits, val_bits);
-  KeyT* sk; uint32_t* sv;
-  lsd_sort<KeyT, true>(ck, cv, ak, av, n_cand, plan, c->lsd_scratch.as<uint32_t>(), st, &sk, &sv);
-  *sorted_keys = sk; *sorted_vals = sv;
-
-  tm.begin(NRP_T_GROUP);
-  const size_t n1 = (size_t)n_cand + 2;
-  TRY(c->head.ensure(4 * n1)); TRY(c->head_scan.ensure(4 * n1)); TRY(c->group_start.ensure(4 * n1));
-  TRY(c->valid.ensure(4 * n1)); TRY(c->valid_scan.ensure(4 * n1));
-  TRY(c->mem_cnt.ensure(4 * n1)); TRY(c->mem_scan.ensure(8 * n1));
-  TRY(c->pair_cnt.ensure(8 * n1)); TRY(c->pair_scan.ensure(8 * n1));
-  TRY(c->scan_scratch.ensure(8 * (size_t)scan_scratch_elems((int64_t)n1 + 1)));
-  unsigned long long* cnt = c->counters.as<unsigned long long>();
-  int64_t n = n_cand;
-  *n_repeat_records = 0;
-  if (n > 0) {
-    NRP_LAUNCH((k_group_heads<KeyT><<<grid_for(n, 256), 256, 0, st>>>(sk, sv, n, c->part_base, n_parts_for_flags, c->head.as<uint32_t>(),
-                                                                  mark_repeats ? c->flags.as<uint8_t>() : nullptr, cnt + CNT_REPEAT)));
-    CU(cudaMemcpyAsync(c->h_counters + 18, cnt + CNT_REPEAT, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    *n_repeat_records = (int64_t)c->h_counters[18];
-    if (mark_repeats && *n_repeat_records > 0) {
-      // drop every record of the flagged parts, keep the (key, part) order, and find the key runs again
-      KeyT* ok = sk == ck ? ak : ck;
-      uint32_t* ov = sv == cv ? av : cv;
-      NRP_LAUNCH((k_keep_unflagged<<<grid_for(n, 256), 256, 0, st>>>(sv, n, c->flags.as<uint8_t>() - c->part_base, c->valid.as<uint32_t>())));
-      exclusive_scan<uint32_t, uint32_t>(c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), n, c->scan_scratch.as<uint32_t>(), st);
-      NRP_LAUNCH((k_compact_records<KeyT><<<grid_for(n, 256), 256, 0, st>>>(sk, sv, c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), n, ok, ov)));
-      CU(cudaMemcpyAsync(c->h_counters + 19, c->valid_scan.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-      n = (int64_t)(uint32_t)c->h_counters[19];
-      sk = ok; sv = ov;
-      *sorted_keys = sk; *sorted_vals = sv;
-      if (n > 0)
-        NRP_LAUNCH((k_group_heads<KeyT><<<grid_for(n, 256), 256, 0, st>>>(sk, sv, n, c->part_base, n_parts_for_flags, c->head.as<uint32_t>(),
-                                                                      nullptr, cnt + CNT_WORK)));
-    }
-  }
-  *n_grouped = n;
-  if (n > 0) {
-    exclusive_scan<uint32_t, uint32_t>(c->head.as<uint32_t>(), c->head_scan.as<uint32_t>(), n, c->scan_scratch.as<uint32_t>(), st);
-    NRP_LAUNCH((k_group_starts<<<grid_for(n + 1, 256), 256, 0, st>>>(c->head.as<uint32_t>(), c->head_scan.as<uint32_t>(), n,
-                                                                 c->group_start.as<uint32_t>())));
-  }
-  CU(cudaGetLastError());
-  return NRP_OK;
-}
-
 }  // namespace
 
 // =====================================================================================================
@@ -292,7 +250,7 @@ int nrp_ctx_destroy(nrp_ctx* c) {
   for (DevBuf* b : all) b->release();
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   if (c->h_counters) cudaFreeHost(c->h_counters);
-  cudaStreamDestroy(c->stream);
+  if (!c->external_stream) cudaStreamDestroy(c->stream);
   delete c;
   return NRP_OK;
 }
@@ -367,6 +325,8 @@ int nrp_load_parts(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, con
     CU(cudaMemcpyAsync(c->ascii.ptr, ascii, (size_t)total, ascii_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(c->off.ptr, offsets, sizeof(int64_t) * (size_t)(n_parts + 1), cudaMemcpyHostToDevice, c->stream));
   c->have_ids = part_id != nullptr;
+  c->max_id = 0;
+  if (part_id) for (int64_t i = 0; i < n_parts; ++i) if (part_id[i] > c->max_id) c->max_id = part_id[i];
   if (part_id && n_parts > 0) {
     TRY(c->part_id.ensure(sizeof(uint32_t) * (size_t)n_parts));
     CU(cudaMemcpyAsync(c->part_id.ptr, part_id, sizeof(uint32_t) * (size_t)n_parts, cudaMemcpyHostToDevice, c->stream));
@@ -378,6 +338,8 @@ int nrp_load_parts(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, con
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
   c->part_base = 0;
+  c->shard_lo = 0; c->shard_hi = n_parts; c->shard_tile_lo = 0; c->shard_tiles = c->n_tiles;
+  c->n_owners = 0;
   c->have_parts = true;
   return NRP_OK;
 }
@@ -386,219 +348,426 @@ int nrp_load_parts(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, con
 
 namespace {
 
-template <typename KeyT>
-int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
-  TRY(configure_kernels<KeyT>(c));
-  cudaStream_t st = c->stream;
-  const int64_t n_parts = c->n_parts;
-  const Parts P = parts_view(c);
+int64_t windows_in_range(const nrp_ctx* c, int64_t lo, int64_t hi, int k) {
+  if (c->uniform_len > 0) return c->uniform_len >= k ? (hi - lo) * (int64_t)(c->uniform_len - k + 1) : 0;
+  int64_t m = 0;
+  for (int64_t i = lo; i < hi; ++i) { int64_t w = c->h_off[i + 1] - c->h_off[i] - k + 1; if (w > 0) m += w; }
+  return m;
+}
 
-  int64_t m_max = 0;
-  if (c->uniform_len > 0) m_max = c->uniform_len >= k ? n_parts * (int64_t)(c->uniform_len - k + 1) : 0;
-  else for (int64_t i = 0; i < n_parts; ++i) { int64_t w = c->h_off[i + 1] - c->h_off[i] - k + 1; if (w > 0) m_max += w; }
-  if (m_max >= 0xffffe000ll) return fail(NRP_E_UNSUPPORTED, "%lld records exceed the 32-bit record index of one device", (long long)m_max);
-
-  memset(c->counts, 0, sizeof(c->counts));
-  launch_counter() = 0;
-  memset(c->timings, 0, sizeof(c->timings));
-  c->counts[NRP_C_WINDOWS_MAX] = m_max;
-  c->counts[NRP_C_KEY_BYTES] = sizeof(KeyT);
-  c->counts[NRP_C_EDGES] = want_edges ? 0 : -1;
-  c->k = k; c->key_bytes = sizeof(KeyT);
-
-  TRY(c->flags.ensure((size_t)n_parts + 16));
-  TRY(c->last_single.ensure(sizeof(int32_t) * (size_t)(n_parts + 1)));
-  const size_t rec = (size_t)m_max + 16;
-  TRY(c->keysA.ensure(sizeof(KeyT) * rec)); TRY(c->valsA.ensure(4 * rec));
-  TRY(c->keysB.ensure(sizeof(KeyT) * rec)); TRY(c->valsB.ensure(4 * rec));
+int ensure_record_buffers(nrp_ctx* c, int64_t n_records, size_t key_bytes) {
+  const size_t rec = (size_t)n_records + 16;
+  TRY(c->keysA.ensure(key_bytes * rec)); TRY(c->valsA.ensure(4 * rec));
+  TRY(c->keysB.ensure(key_bytes * rec)); TRY(c->valsB.ensure(4 * rec));
   const size_t leaf_max = (size_t)1 << kMaxLeafBits;
   TRY(c->hist.ensure(4 * (leaf_max + 2))); TRY(c->leaf_off.ensure(4 * (leaf_max + 2)));
-  TRY(c->cursor1.ensure(4 * 256)); TRY(c->cursor2.ensure(4 * (leaf_max + 2)));
+  TRY(c->cursor1.ensure(4 * 260)); TRY(c->cursor2.ensure(4 * (leaf_max + 2)));
   TRY(c->seg_off.ensure(4 * 260)); TRY(c->tile_prefix.ensure(4 * 260));
   TRY(c->scan_scratch.ensure(8 * (size_t)scan_scratch_elems((int64_t)leaf_max + 2)));
-  unsigned long long* cnt = c->counters.as<unsigned long long>();
+  return NRP_OK;
+}
 
-  StageTimer tm(c);
+// ---- stage: exclusion flags that need no grouping (palindromes, background) over the shard's tiles
+int stage_flags(nrp_ctx* c, int k, int internal_repeats, StageTimer& tm) {
+  cudaStream_t st = c->stream;
   tm.begin(NRP_T_FLAGS);
-  CU(cudaMemsetAsync(c->flags.ptr, 0, (size_t)n_parts + 16, st));
-  if (c->n_tiles > 0 && m_max >= 0) {
+  const Parts P = parts_view(c);
+  TRY(c->flags.ensure((size_t)c->n_parts + 16));
+  TRY(c->last_single.ensure(sizeof(int32_t) * (size_t)(c->n_parts + 1)));
+  CU(cudaMemsetAsync(c->flags.ptr, 0, (size_t)c->n_parts + 16, st));
+  if (c->shard_tiles > 0) {
     if (!internal_repeats && (k % 2) == 0)
-      NRP_LAUNCH((k_flag_windows<uint32_t><<<(unsigned)c->n_tiles, kTileThreads, 0, st>>>(P, k, 0, nullptr, 0, c->flags.as<uint8_t>())));
+      NRP_LAUNCH((k_flag_windows<uint32_t><<<(unsigned)c->shard_tiles, kTileThreads, 0, st>>>(P, k, 0, nullptr, 0, c->flags.as<uint8_t>())));
     if (c->bg_n > 0) {
       if (c->bg_key_bytes == 4)
-        NRP_LAUNCH((k_flag_windows<uint32_t><<<(unsigned)c->n_tiles, kTileThreads, 0, st>>>(P, c->bg_K, 1, c->bg_table.as<uint32_t>(), c->bg_log_slots,
-                                                                              c->flags.as<uint8_t>())));
+        NRP_LAUNCH((k_flag_windows<uint32_t><<<(unsigned)c->shard_tiles, kTileThreads, 0, st>>>(P, c->bg_K, 1, c->bg_table.as<uint32_t>(),
+                                                                                              c->bg_log_slots, c->flags.as<uint8_t>())));
       else
-        NRP_LAUNCH((k_flag_windows<uint64_t><<<(unsigned)c->n_tiles, kTileThreads, 0, st>>>(P, c->bg_K, 1, c->bg_table.as<uint64_t>(), c->bg_log_slots,
-                                                                              c->flags.as<uint8_t>())));
+        NRP_LAUNCH((k_flag_windows<uint64_t><<<(unsigned)c->shard_tiles, kTileThreads, 0, st>>>(P, c->bg_K, 1, c->bg_table.as<uint64_t>(),
+                                                                                              c->bg_log_slots, c->flags.as<uint8_t>())));
     }
   }
   CU(cudaGetLastError());
+  return NRP_OK;
+}
 
+// ---- stage: records -> leaf buckets -> candidates (records whose key repeats inside its leaf bucket).
+// Source is either the staged part buffer (extraction fused into the first split) or records already in HBM.
+template <typename KeyT>
+int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, int64_t n_in, StageTimer& tm) {
+  cudaStream_t st = c->stream;
+  const bool from_ascii = in_keys == nullptr;
+  const int64_t m_max = from_ascii ? c->shard_m_max : n_in;
+  const Parts P = parts_view(c);
+  unsigned long long* cnt = c->counters.as<unsigned long long>();
   const int bits = choose_leaf_bits(c, m_max);
   const int r1 = std::min<int>(bits, (int)c->opt_max_level_bits);
   const int r2 = bits - r1;
   const uint32_t n_leaf = 1u << bits;
   c->counts[NRP_C_BUCKETS] = n_leaf;
-  int part_bits = 1;
-  while (((int64_t)1 << part_bits) < n_parts) ++part_bits;
+  TRY(ensure_record_buffers(c, m_max, sizeof(KeyT)));
 
-  int64_t n_groups = 0, n_members = 0, n_pairs = 0, n_cand = 0, n_records = 0;
-  KeyT* sk = nullptr; uint32_t* sv = nullptr;
-  {
-    c->counts[NRP_C_RUNS] = 1;
-    tm.begin(NRP_T_HISTOGRAM);
-    CU(cudaMemsetAsync(c->hist.ptr, 0, 4 * ((size_t)n_leaf + 2), st));
-    CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * CNT_N, st));
-    if (m_max > 0) {
-      const unsigned hist_grid = (unsigned)std::min<int64_t>(c->n_tiles, (int64_t)c->n_sms * (bits >= 15 ? 1 : 2));
-      NRP_LAUNCH((k_hist_from_ascii<<<hist_grid, kTileThreads, 4u << bits, st>>>(P, c->flags.as<uint8_t>(), k, bits, c->n_tiles, c->hist.as<uint32_t>())));
-    }
-    exclusive_scan<uint32_t, uint32_t>(c->hist.as<uint32_t>(), c->leaf_off.as<uint32_t>(), n_leaf, c->scan_scratch.as<uint32_t>(), st);
-    NRP_LAUNCH((k_init_cursors<<<grid_for(n_leaf, 256), 256, 0, st>>>(c->leaf_off.as<uint32_t>(), r1, r2, c->cursor1.as<uint32_t>(), c->cursor2.as<uint32_t>())));
-
-    tm.begin(NRP_T_SPLIT1);
-    KeyT* leaf_keys = c->keysA.as<KeyT>(); uint32_t* leaf_vals = c->valsA.as<uint32_t>();
-    KeyT* free_keys = c->keysB.as<KeyT>(); uint32_t* free_vals = c->valsB.as<uint32_t>();
-    if (m_max > 0)
-      NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->n_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-          P, c->flags.as<uint8_t>(), k, r1, 0, c->part_base, r2 > 0 ? c->cursor1.as<uint32_t>() : c->cursor2.as<uint32_t>(), leaf_keys, leaf_vals)));
-    if (r2 > 0 && m_max > 0) {
-      tm.begin(NRP_T_SPLIT2);
-      NRP_LAUNCH((k_segment_tiles<<<1, 256, 0, st>>>(c->leaf_off.as<uint32_t>(), r1, r2, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>())));
-      const unsigned grid2 = (unsigned)std::min<int64_t>(m_max / kSplitTile + (1 << r1), (int64_t)c->n_sms * 4);
-      NRP_LAUNCH((k_split_from_records<KeyT><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
-          leaf_keys, leaf_vals, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>(), r1, r2, c->cursor2.as<uint32_t>(), free_keys, free_vals)));
-      std::swap(leaf_keys, free_keys); std::swap(leaf_vals, free_vals);
-    }
-    tm.begin(NRP_T_FILTER);
-    if (m_max > 0) {
-      const size_t fsm = (sizeof(KeyT) + 1) * 2 * (size_t)kFilterCap;
-      const unsigned fgrid = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * (sizeof(KeyT) == 4 ? 2 : 1));
-      NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItems><<<fgrid, kFilterThreads, fsm, st>>>(
-          leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, (uint32_t)c->opt_filter_cap,
-          reinterpret_cast<uint32_t*>(cnt + CNT_WORK), free_keys, free_vals, cnt + CNT_CAND, reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED))));
-    }
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(c->h_counters, cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(c->h_counters + 16, c->leaf_off.as<uint32_t>() + n_leaf, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    n_cand = (int64_t)c->h_counters[CNT_CAND];
-    n_records = (int64_t)(uint32_t)c->h_counters[16];
-    c->counts[NRP_C_OVERSIZED] = (int64_t)(uint32_t)c->h_counters[CNT_OVERSIZED];
-
-    // candidates live in (free_keys, free_vals); the leaf buffers are free again
-    int64_t n_grp = 0, n_repeat = 0;
-    TRY((group_candidates<KeyT>(c, free_keys, free_vals, leaf_keys, leaf_vals, n_cand, 2 * k, part_bits, n_parts, !internal_repeats, tm,
-                                &sk, &sv, &n_grp, &n_repeat)));
-    if (!internal_repeats && n_repeat > 0) {
-      // windows of the parts just flagged were counted as records: take them out again
-      CU(cudaMemsetAsync(cnt + CNT_WORK, 0, 8, st));
-      NRP_LAUNCH((k_flagged_windows<<<grid_for(n_parts, 256), 256, 0, st>>>(c->off.as<int64_t>(), c->flags.as<uint8_t>(), n_parts, k, cnt + CNT_WORK)));
-      CU(cudaMemcpyAsync(c->h_counters + 27, cnt + CNT_WORK, 8, cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-      n_records -= (int64_t)c->h_counters[27];
-    }
-    int64_t n_runs_bound = 0;
-    if (n_grp > 0) {
-      CU(cudaMemcpyAsync(c->h_counters + 17, c->head_scan.as<uint32_t>() + n_grp, 4, cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-      n_runs_bound = (int64_t)(uint32_t)c->h_counters[17];
-      NRP_LAUNCH((k_group_sizes<<<grid_for(n_runs_bound, 256), 256, 0, st>>>(c->group_start.as<uint32_t>(), n_runs_bound, c->valid.as<uint32_t>(),
-                                                                c->mem_cnt.as<uint32_t>(), c->pair_cnt.as<unsigned long long>())));
-      exclusive_scan<uint32_t, uint32_t>(c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), n_runs_bound, c->scan_scratch.as<uint32_t>(), st);
-      exclusive_scan<uint32_t, unsigned long long>(c->mem_cnt.as<uint32_t>(), c->mem_scan.as<unsigned long long>(), n_runs_bound,
-                                                   c->scan_scratch.as<unsigned long long>(), st);
-      exclusive_scan<unsigned long long, unsigned long long>(c->pair_cnt.as<unsigned long long>(), c->pair_scan.as<unsigned long long>(),
-                                                             n_runs_bound, c->scan_scratch.as<unsigned long long>(), st);
-      CU(cudaMemcpyAsync(c->h_counters + 20, c->valid_scan.as<uint32_t>() + n_runs_bound, 4, cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(c->h_counters + 21, c->mem_scan.as<unsigned long long>() + n_runs_bound, 8, cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(c->h_counters + 22, c->pair_scan.as<unsigned long long>() + n_runs_bound, 8, cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-      n_groups = (int64_t)(uint32_t)c->h_counters[20];
-      n_members = (int64_t)c->h_counters[21];
-      n_pairs = (int64_t)c->h_counters[22];
-      TRY(c->g_keys.ensure(8 * (size_t)(n_groups + 1))); TRY(c->g_indptr.ensure(8 * (size_t)(n_groups + 2)));
-      TRY(c->g_pair_off.ensure(8 * (size_t)(n_groups + 2))); TRY(c->g_members.ensure(4 * (size_t)(n_members + 1)));
-      NRP_LAUNCH((k_group_emit<KeyT><<<grid_for(n_runs_bound + 1, 256), 256, 0, st>>>(
-          sk, c->group_start.as<uint32_t>(), c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), c->mem_scan.as<unsigned long long>(),
-          c->pair_scan.as<unsigned long long>(), n_runs_bound, c->g_keys.as<uint64_t>(), c->g_indptr.as<int64_t>(),
-          c->g_pair_off.as<unsigned long long>())));
-      NRP_LAUNCH((k_group_members<<<grid_for(n_grp, 256), 256, 0, st>>>(sv, c->head_scan.as<uint32_t>(), c->head.as<uint32_t>(), c->group_start.as<uint32_t>(),
-                                                             c->valid.as<uint32_t>(), c->mem_scan.as<unsigned long long>(), n_grp,
-                                                             c->g_members.as<uint32_t>())));
-      CU(cudaGetLastError());
+  tm.begin(NRP_T_HISTOGRAM);
+  CU(cudaMemsetAsync(c->hist.ptr, 0, 4 * ((size_t)n_leaf + 2), st));
+  CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * CNT_N, st));
+  if (m_max > 0) {
+    if (from_ascii) {
+      const unsigned grid = (unsigned)std::min<int64_t>(c->shard_tiles, (int64_t)c->n_sms * (bits >= 15 ? 1 : 2));
+      NRP_LAUNCH((k_hist_from_ascii<<<grid, kTileThreads, 4u << bits, st>>>(P, c->flags.as<uint8_t>(), k, bits, 0, c->shard_tiles, c->hist.as<uint32_t>())));
     } else {
-      n_groups = n_members = n_pairs = 0;
-      TRY(c->g_keys.ensure(8)); TRY(c->g_indptr.ensure(16)); TRY(c->g_pair_off.ensure(16)); TRY(c->g_members.ensure(4));
-      CU(cudaMemsetAsync(c->g_indptr.ptr, 0, 16, st));
-      CU(cudaMemsetAsync(c->g_pair_off.ptr, 0, 16, st));
+      const unsigned grid = (unsigned)std::min<int64_t>((n_in + 511) / 512, (int64_t)c->n_sms * (bits >= 15 ? 1 : 2));
+      NRP_LAUNCH((k_hist_from_records<KeyT><<<grid, 512, 4u << bits, st>>>(in_keys, n_in, bits, c->hist.as<uint32_t>())));
     }
   }
-  c->counts[NRP_C_RECORDS] = n_records;
-  c->counts[NRP_C_CANDIDATES] = n_cand;
-  c->counts[NRP_C_GROUPS] = n_groups;
-  c->counts[NRP_C_MEMBERS] = n_members;
-  c->counts[NRP_C_PAIRS] = n_pairs;
+  exclusive_scan<uint32_t, uint32_t>(c->hist.as<uint32_t>(), c->leaf_off.as<uint32_t>(), n_leaf, c->scan_scratch.as<uint32_t>(), st);
+  NRP_LAUNCH((k_init_cursors<<<grid_for(n_leaf, 256), 256, 0, st>>>(c->leaf_off.as<uint32_t>(), r1, r2, c->cursor1.as<uint32_t>(), c->cursor2.as<uint32_t>())));
 
-  // ---- order information for the host replay
-  tm.begin(NRP_T_ORDER);
-  TRY(c->g_first_part.ensure(4 * (size_t)(n_groups + 1))); TRY(c->g_first_window.ensure(4 * (size_t)(n_groups + 1)));
-  if (n_groups > 0) {
-    NRP_LAUNCH((k_gather_first_part<<<grid_for(n_groups, 256), 256, 0, st>>>(c->g_indptr.as<int64_t>(), c->g_members.as<uint32_t>(), n_groups,
-                                                                 c->g_first_part.as<uint32_t>())));
-    NRP_LAUNCH((k_group_first_window<<<grid_for(n_groups, 128), 128, 0, st>>>(c->ascii.as<uint8_t>(), c->off.as<int64_t>(), c->g_keys.as<uint64_t>(),
-                                                                  c->g_first_part.as<uint32_t>(), c->part_base, n_parts, n_groups, k,
-                                                                  c->g_first_window.as<uint32_t>())));
+  tm.begin(NRP_T_SPLIT1);
+  KeyT* leaf_keys = c->keysA.as<KeyT>(); uint32_t* leaf_vals = c->valsA.as<uint32_t>();
+  KeyT* free_keys = c->keysB.as<KeyT>(); uint32_t* free_vals = c->valsB.as<uint32_t>();
+  uint32_t* level1_cursor = r2 > 0 ? c->cursor1.as<uint32_t>() : c->cursor2.as<uint32_t>();
+  if (m_max > 0) {
+    if (from_ascii) {
+      NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+          P, c->flags.as<uint8_t>(), k, r1, 0, c->part_base, level1_cursor, leaf_keys, leaf_vals)));
+    } else {
+      // one segment holding all records; level-1 digit = top r1 bits
+      const uint32_t seg[2] = {0u, (uint32_t)n_in};
+      const uint32_t tiles[2] = {0u, (uint32_t)((n_in + kSplitTile - 1) / kSplitTile)};
+      CU(cudaMemcpyAsync(c->seg_off.ptr, seg, sizeof(seg), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(c->tile_prefix.ptr, tiles, sizeof(tiles), cudaMemcpyHostToDevice, st));
+      CU(cudaStreamSynchronize(st));       // the two host arrays live on this stack frame
+      const unsigned grid = (unsigned)std::min<int64_t>(tiles[1], (int64_t)c->n_sms * 4);
+      NRP_LAUNCH((k_split_from_records<KeyT><<<grid, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
+          in_keys, in_vals, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>(), 0, r1, level1_cursor, leaf_keys, leaf_vals)));
+    }
   }
-  if (n_parts > 0)
-    NRP_LAUNCH((k_last_single<<<grid_for(n_parts, 128), 128, 0, st>>>(c->ascii.as<uint8_t>(), c->off.as<int64_t>(), c->flags.as<uint8_t>(), n_parts, k,
-                                                          c->g_keys.as<uint64_t>(), n_groups, c->last_single.as<int32_t>())));
+  if (r2 > 0 && m_max > 0) {
+    tm.begin(NRP_T_SPLIT2);
+    NRP_LAUNCH((k_segment_tiles<<<1, 256, 0, st>>>(c->leaf_off.as<uint32_t>(), r1, r2, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>())));
+    const unsigned grid2 = (unsigned)std::min<int64_t>(m_max / kSplitTile + (1 << r1), (int64_t)c->n_sms * 4);
+    NRP_LAUNCH((k_split_from_records<KeyT><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
+        leaf_keys, leaf_vals, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>(), r1, r2, c->cursor2.as<uint32_t>(), free_keys, free_vals)));
+    std::swap(leaf_keys, free_keys); std::swap(leaf_vals, free_vals);
+  }
+  tm.begin(NRP_T_FILTER);
+  if (m_max > 0) {
+    const size_t fsm = (sizeof(KeyT) + 1) * 2 * (size_t)kFilterCap;
+    const unsigned fgrid = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * (sizeof(KeyT) == 4 ? 2 : 1));
+    NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItems><<<fgrid, kFilterThreads, fsm, st>>>(
+        leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, (uint32_t)c->opt_filter_cap,
+        reinterpret_cast<uint32_t*>(cnt + CNT_WORK), free_keys, free_vals, cnt + CNT_CAND, reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED))));
+  }
   CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(c->h_counters, cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(c->h_counters + 16, c->leaf_off.as<uint32_t>() + n_leaf, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  c->n_cand = (int64_t)c->h_counters[CNT_CAND];
+  c->n_records = (int64_t)(uint32_t)c->h_counters[16];
+  c->counts[NRP_C_OVERSIZED] = (int64_t)(uint32_t)c->h_counters[CNT_OVERSIZED];
+  c->counts[NRP_C_CANDIDATES] = c->n_cand;
+  c->cand_keys = free_keys; c->cand_vals = free_vals;         // candidates; the leaf buffers are free again
+  c->spare_keys = leaf_keys; c->spare_vals = leaf_vals;
+  return NRP_OK;
+}
 
-  // ---- edges
-  if (want_edges) {
-    tm.begin(NRP_T_EDGES);
-    if (!c->have_ids) return fail(NRP_E_ARG, "want_edges needs part ids");
-    if (n_pairs > c->opt_max_pairs) return fail(NRP_E_EDGES, "%lld member pairs exceed the limit of %lld", (long long)n_pairs, (long long)c->opt_max_pairs);
-    int64_t n_edges = 0;
-    if (n_pairs > 0) {
-      TRY(c->e_codesA.ensure(8 * (size_t)(n_pairs + 1))); TRY(c->e_codesB.ensure(8 * (size_t)(n_pairs + 1)));
-      TRY(c->e_head.ensure(4 * (size_t)(n_pairs + 2))); TRY(c->e_head_scan.ensure(4 * (size_t)(n_pairs + 2)));
-      TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n_pairs)));
-      TRY(c->scan_scratch.ensure(8 * (size_t)scan_scratch_elems(n_pairs + 2)));
-      NRP_LAUNCH((k_edge_pairs<<<grid_for(n_members, 128), 128, 0, st>>>(c->g_indptr.as<int64_t>(), c->g_members.as<uint32_t>(),
-                                                             c->g_pair_off.as<unsigned long long>(), n_groups, n_members,
-                                                             c->part_id.as<uint32_t>(), c->part_base, c->e_codesA.as<uint64_t>())));
-      LsdPlan plan; plan.n_passes = 0;
-      lsd_plan_add(plan, 0, 0, 64);
-      uint64_t* sorted_codes;
-      lsd_sort<uint64_t, false>(c->e_codesA.as<uint64_t>(), nullptr, c->e_codesB.as<uint64_t>(), nullptr, n_pairs, plan,
-                                c->lsd_scratch.as<uint32_t>(), st, &sorted_codes, nullptr);
-      NRP_LAUNCH((k_edge_heads<<<grid_for(n_pairs, 256), 256, 0, st>>>(sorted_codes, n_pairs, c->e_head.as<uint32_t>())));
-      exclusive_scan<uint32_t, uint32_t>(c->e_head.as<uint32_t>(), c->e_head_scan.as<uint32_t>(), n_pairs, c->scan_scratch.as<uint32_t>(), st);
-      CU(cudaMemcpyAsync(c->h_counters + 24, c->e_head_scan.as<uint32_t>() + n_pairs, 4, cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-      n_edges = (int64_t)(uint32_t)c->h_counters[24];
-      TRY(c->e_u.ensure(4 * (size_t)(n_edges + 1))); TRY(c->e_v.ensure(4 * (size_t)(n_edges + 1)));
-      NRP_LAUNCH((k_edge_compact<<<grid_for(n_pairs, 256), 256, 0, st>>>(sorted_codes, c->e_head.as<uint32_t>(), c->e_head_scan.as<uint32_t>(), n_pairs,
-                                                             c->e_u.as<uint32_t>(), c->e_v.as<uint32_t>())));
-      CU(cudaGetLastError());
-    }
-    c->counts[NRP_C_EDGES] = n_edges;
-  }
+int ensure_group_buffers(nrp_ctx* c, int64_t n) {
+  const size_t n1 = (size_t)n + 2;
+  TRY(c->head.ensure(4 * n1)); TRY(c->head_scan.ensure(4 * n1)); TRY(c->group_start.ensure(4 * n1));
+  TRY(c->valid.ensure(4 * n1)); TRY(c->valid_scan.ensure(4 * n1));
+  TRY(c->mem_cnt.ensure(4 * n1)); TRY(c->mem_scan.ensure(8 * n1));
+  TRY(c->pair_cnt.ensure(8 * n1)); TRY(c->pair_scan.ensure(8 * n1));
+  TRY(c->scan_scratch.ensure(8 * (size_t)scan_scratch_elems((int64_t)n1 + 1)));
+  return NRP_OK;
+}
+
+// ---- stage: sort the candidates by (k-mer, part), mark key-run heads, detect internal repeats
+// (two equal adjacent records).  With mark_repeats the parts get NRP_FLAG_REPEAT in flags[value].
+template <typename KeyT>
+int stage_sort_mark(nrp_ctx* c, int k, int64_t n_parts_total, bool mark_repeats, StageTimer& tm) {
+  cudaStream_t st = c->stream;
+  tm.begin(NRP_T_SORT);
+  const int64_t n = c->n_cand;
+  int part_bits = 1;
+  while (((int64_t)1 << part_bits) < n_parts_total) ++part_bits;
+  TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n)));
+  LsdPlan plan = lsd_plan(2 * k, part_bits);
+  KeyT* sk; uint32_t* sv;
+  lsd_sort<KeyT, true>((KeyT*)c->cand_keys, c->cand_vals, (KeyT*)c->spare_keys, c->spare_vals, n, plan, c->lsd_scratch.as<uint32_t>(), st, &sk, &sv);
+  if (sk != (KeyT*)c->cand_keys) { std::swap(c->cand_keys, c->spare_keys); std::swap(c->cand_vals, c->spare_vals); }
   tm.begin(NRP_T_GROUP);
-  CU(cudaMemsetAsync(cnt + CNT_FLAGGED, 0, 8, st));
-  if (n_parts > 0) NRP_LAUNCH((k_count_flagged<<<grid_for(n_parts, 256), 256, 0, st>>>(c->flags.as<uint8_t>(), n_parts, cnt + CNT_FLAGGED)));
-  CU(cudaMemcpyAsync(c->h_counters + 26, cnt + CNT_FLAGGED, 8, cudaMemcpyDeviceToHost, st));
+  TRY(ensure_group_buffers(c, n));
+  unsigned long long* cnt = c->counters.as<unsigned long long>();
+  c->n_sorted = n;
+  c->n_repeat_records = 0;
+  if (n > 0) {
+    NRP_LAUNCH((k_group_heads<KeyT><<<grid_for(n, 256), 256, 0, st>>>((KeyT*)c->cand_keys, c->cand_vals, n, c->head.as<uint32_t>(),
+                                                                  mark_repeats ? c->flags.as<uint8_t>() : nullptr, cnt + CNT_REPEAT)));
+    CU(cudaMemcpyAsync(c->h_counters + 18, cnt + CNT_REPEAT, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    c->n_repeat_records = (int64_t)c->h_counters[18];
+  }
+  CU(cudaGetLastError());
+  return NRP_OK;
+}
+
+// ---- stage: drop every record of a part that carries the repeat flag (keeps the order), mark heads again
+template <typename KeyT>
+int stage_compact(nrp_ctx* c, StageTimer& tm) {
+  cudaStream_t st = c->stream;
+  tm.begin(NRP_T_GROUP);
+  const int64_t n = c->n_sorted;
+  if (n == 0) return NRP_OK;
+  unsigned long long* cnt = c->counters.as<unsigned long long>();
+  NRP_LAUNCH((k_keep_unflagged<<<grid_for(n, 256), 256, 0, st>>>(c->cand_vals, n, c->flags.as<uint8_t>(), c->valid.as<uint32_t>())));
+  exclusive_scan<uint32_t, uint32_t>(c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), n, c->scan_scratch.as<uint32_t>(), st);
+  NRP_LAUNCH((k_compact_records<KeyT><<<grid_for(n, 256), 256, 0, st>>>((KeyT*)c->cand_keys, c->cand_vals, c->valid.as<uint32_t>(),
+                                                                    c->valid_scan.as<uint32_t>(), n, (KeyT*)c->spare_keys, c->spare_vals)));
+  CU(cudaMemcpyAsync(c->h_counters + 19, c->valid_scan.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  c->n_sorted = (int64_t)(uint32_t)c->h_counters[19];
+  std::swap(c->cand_keys, c->spare_keys); std::swap(c->cand_vals, c->spare_vals);
+  if (c->n_sorted > 0)
+    NRP_LAUNCH((k_group_heads<KeyT><<<grid_for(c->n_sorted, 256), 256, 0, st>>>((KeyT*)c->cand_keys, c->cand_vals, c->n_sorted,
+                                                                           c->head.as<uint32_t>(), nullptr, cnt + CNT_WORK)));
+  CU(cudaGetLastError());
+  return NRP_OK;
+}
+
+// ---- stage: key runs with >= 2 records -> groups CSR (keys, indptr, members, pair offsets)
+template <typename KeyT>
+int stage_groups(nrp_ctx* c, StageTimer& tm) {
+  cudaStream_t st = c->stream;
+  tm.begin(NRP_T_GROUP);
+  const int64_t n = c->n_sorted;
+  c->n_groups = c->n_members = c->n_pairs = 0;
+  if (n > 0) {
+    exclusive_scan<uint32_t, uint32_t>(c->head.as<uint32_t>(), c->head_scan.as<uint32_t>(), n, c->scan_scratch.as<uint32_t>(), st);
+    NRP_LAUNCH((k_group_starts<<<grid_for(n + 1, 256), 256, 0, st>>>(c->head.as<uint32_t>(), c->head_scan.as<uint32_t>(), n,
+                                                                 c->group_start.as<uint32_t>())));
+    CU(cudaMemcpyAsync(c->h_counters + 17, c->head_scan.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int64_t n_runs = (int64_t)(uint32_t)c->h_counters[17];
+    NRP_LAUNCH((k_group_sizes<<<grid_for(n_runs, 256), 256, 0, st>>>(c->group_start.as<uint32_t>(), n_runs, c->valid.as<uint32_t>(),
+                                                                 c->mem_cnt.as<uint32_t>(), c->pair_cnt.as<unsigned long long>())));
+    exclusive_scan<uint32_t, uint32_t>(c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), n_runs, c->scan_scratch.as<uint32_t>(), st);
+    exclusive_scan<uint32_t, unsigned long long>(c->mem_cnt.as<uint32_t>(), c->mem_scan.as<unsigned long long>(), n_runs,
+                                                 c->scan_scratch.as<unsigned long long>(), st);
+    exclusive_scan<unsigned long long, unsigned long long>(c->pair_cnt.as<unsigned long long>(), c->pair_scan.as<unsigned long long>(),
+                                                           n_runs, c->scan_scratch.as<unsigned long long>(), st);
+    CU(cudaMemcpyAsync(c->h_counters + 20, c->valid_scan.as<uint32_t>() + n_runs, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_counters + 21, c->mem_scan.as<unsigned long long>() + n_runs, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_counters + 22, c->pair_scan.as<unsigned long long>() + n_runs, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    c->n_groups = (int64_t)(uint32_t)c->h_counters[20];
+    c->n_members = (int64_t)c->h_counters[21];
+    c->n_pairs = (int64_t)c->h_counters[22];
+    TRY(c->g_keys.ensure(8 * (size_t)(c->n_groups + 1))); TRY(c->g_indptr.ensure(8 * (size_t)(c->n_groups + 2)));
+    TRY(c->g_pair_off.ensure(8 * (size_t)(c->n_groups + 2))); TRY(c->g_members.ensure(4 * (size_t)(c->n_members + 1)));
+    NRP_LAUNCH((k_group_emit<KeyT><<<grid_for(n_runs + 1, 256), 256, 0, st>>>(
+        (KeyT*)c->cand_keys, c->group_start.as<uint32_t>(), c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(),
+        c->mem_scan.as<unsigned long long>(), c->pair_scan.as<unsigned long long>(), n_runs, c->g_keys.as<uint64_t>(),
+        c->g_indptr.as<int64_t>(), c->g_pair_off.as<unsigned long long>())));
+    NRP_LAUNCH((k_group_members<<<grid_for(n, 256), 256, 0, st>>>(c->cand_vals, c->head_scan.as<uint32_t>(), c->head.as<uint32_t>(),
+                                                              c->group_start.as<uint32_t>(), c->valid.as<uint32_t>(),
+                                                              c->mem_scan.as<unsigned long long>(), n, c->g_members.as<uint32_t>())));
+    CU(cudaGetLastError());
+  } else {
+    TRY(c->g_keys.ensure(8)); TRY(c->g_indptr.ensure(16)); TRY(c->g_pair_off.ensure(16)); TRY(c->g_members.ensure(4));
+    CU(cudaMemsetAsync(c->g_indptr.ptr, 0, 16, st));
+    CU(cudaMemsetAsync(c->g_pair_off.ptr, 0, 16, st));
+  }
+  c->counts[NRP_C_GROUPS] = c->n_groups;
+  c->counts[NRP_C_MEMBERS] = c->n_members;
+  c->counts[NRP_C_PAIRS] = c->n_pairs;
+  return NRP_OK;
+}
+
+// ---- stage: rank of every group = first window of its first member that carries the group's key
+int stage_first_window(nrp_ctx* c, int k, StageTimer& tm) {
+  cudaStream_t st = c->stream;
+  tm.begin(NRP_T_ORDER);
+  TRY(c->g_first_part.ensure(4 * (size_t)(c->n_groups + 1))); TRY(c->g_first_window.ensure(4 * (size_t)(c->n_groups + 1)));
+  if (c->n_groups > 0) {
+    NRP_LAUNCH((k_gather_first_part<<<grid_for(c->n_groups, 256), 256, 0, st>>>(c->g_indptr.as<int64_t>(), c->g_members.as<uint32_t>(),
+                                                                            c->n_groups, c->g_first_part.as<uint32_t>())));
+    NRP_LAUNCH((k_group_first_window<<<grid_for(c->n_groups, 128), 128, 0, st>>>(c->ascii.as<uint8_t>(), c->off.as<int64_t>(),
+                                                                             c->g_keys.as<uint64_t>(), c->g_first_part.as<uint32_t>(),
+                                                                             c->n_parts, c->n_groups, k, c->g_first_window.as<uint32_t>())));
+  }
+  CU(cudaGetLastError());
+  return NRP_OK;
+}
+
+// ---- stage: last unshared window of the parts in [lo, hi) given the sorted shared keys
+int stage_last_single(nrp_ctx* c, int k, const uint64_t* shared_keys, int64_t n_shared, int64_t lo, int64_t hi, StageTimer& tm) {
+  cudaStream_t st = c->stream;
+  tm.begin(NRP_T_ORDER);
+  if (c->n_parts > 0) CU(cudaMemsetAsync(c->last_single.ptr, 0xff, sizeof(int32_t) * (size_t)c->n_parts, st));
+  if (hi > lo)
+    NRP_LAUNCH((k_last_single<<<grid_for(hi - lo, 128), 128, 0, st>>>(c->ascii.as<uint8_t>(), c->off.as<int64_t>(), c->flags.as<uint8_t>(), lo, hi,
+                                                                  k, shared_keys, n_shared, c->last_single.as<int32_t>())));
+  CU(cudaGetLastError());
+  return NRP_OK;
+}
+
+// ---- stage: unique part-pair edges of this context's groups
+int stage_edges(nrp_ctx* c, StageTimer& tm) {
+  cudaStream_t st = c->stream;
+  tm.begin(NRP_T_EDGES);
+  if (!c->have_ids) return fail(NRP_E_ARG, "want_edges needs part ids");
+  if (c->n_pairs > c->opt_max_pairs)
+    return fail(NRP_E_EDGES, "%lld member pairs exceed the limit of %lld", (long long)c->n_pairs, (long long)c->opt_max_pairs);
+  int64_t n_edges = 0;
+  const int64_t n_pairs = c->n_pairs;
+  if (n_pairs > 0) {
+    TRY(c->e_codesA.ensure(8 * (size_t)(n_pairs + 1))); TRY(c->e_codesB.ensure(8 * (size_t)(n_pairs + 1)));
+    TRY(c->e_head.ensure(4 * (size_t)(n_pairs + 2))); TRY(c->e_head_scan.ensure(4 * (size_t)(n_pairs + 2)));
+    TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n_pairs)));
+    TRY(c->scan_scratch.ensure(8 * (size_t)scan_scratch_elems(n_pairs + 2)));
+    NRP_LAUNCH((k_edge_pairs<<<grid_for(c->n_members, 128), 128, 0, st>>>(c->g_indptr.as<int64_t>(), c->g_members.as<uint32_t>(),
+                                                                      c->g_pair_off.as<unsigned long long>(), c->n_groups, c->n_members,
+                                                                      c->part_id.as<uint32_t>(), c->e_codesA.as<uint64_t>())));
+    // ids are < 2^id_bits; the all-ones code of self pairs sorts last because 2^id_bits - 1 is never an id
+    int id_bits = 1;
+    while (id_bits < 32 && ((int64_t)1 << id_bits) <= c->max_id) ++id_bits;
+    LsdPlan plan; plan.n_passes = 0;
+    lsd_plan_add(plan, 0, 0, id_bits);
+    lsd_plan_add(plan, 0, 32, 32 + id_bits);
+    uint64_t* sorted_codes;
+    lsd_sort<uint64_t, false>(c->e_codesA.as<uint64_t>(), nullptr, c->e_codesB.as<uint64_t>(), nullptr, n_pairs, plan,
+                              c->lsd_scratch.as<uint32_t>(), st, &sorted_codes, nullptr);
+    NRP_LAUNCH((k_edge_heads<<<grid_for(n_pairs, 256), 256, 0, st>>>(sorted_codes, n_pairs, c->e_head.as<uint32_t>())));
+    exclusive_scan<uint32_t, uint32_t>(c->e_head.as<uint32_t>(), c->e_head_scan.as<uint32_t>(), n_pairs, c->scan_scratch.as<uint32_t>(), st);
+    CU(cudaMemcpyAsync(c->h_counters + 24, c->e_head_scan.as<uint32_t>() + n_pairs, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    n_edges = (int64_t)(uint32_t)c->h_counters[24];
+    TRY(c->e_u.ensure(4 * (size_t)(n_edges + 1))); TRY(c->e_v.ensure(4 * (size_t)(n_edges + 1)));
+    NRP_LAUNCH((k_edge_compact<<<grid_for(n_pairs, 256), 256, 0, st>>>(sorted_codes, c->e_head.as<uint32_t>(), c->e_head_scan.as<uint32_t>(),
+                                                                   n_pairs, c->e_u.as<uint32_t>(), c->e_v.as<uint32_t>())));
+    CU(cudaGetLastError());
+  }
+  c->counts[NRP_C_EDGES] = n_edges;
+  return NRP_OK;
+}
+
+int finish_counts(nrp_ctx* c, StageTimer& tm) {
+  cudaStream_t st = c->stream;
+  unsigned long long* cnt = c->counters.as<unsigned long long>();
+  tm.begin(NRP_T_GROUP);
+  CU(cudaMemsetAsync(cnt + CNT_FLAGGED, 0, 16, st));
+  if (c->n_parts > 0) {
+    NRP_LAUNCH((k_count_flagged<<<grid_for(c->n_parts, 256), 256, 0, st>>>(c->flags.as<uint8_t>(), c->n_parts, cnt + CNT_FLAGGED)));
+    // windows of the parts flagged for internal repeats were counted as records before the flag was known
+    NRP_LAUNCH((k_flagged_windows<<<grid_for(c->shard_hi - c->shard_lo, 256), 256, 0, st>>>(c->off.as<int64_t>(), c->flags.as<uint8_t>(),
+                                                                                        c->shard_lo, c->shard_hi, c->k, cnt + CNT_WORK)));
+  }
+  CU(cudaMemcpyAsync(c->h_counters + 26, cnt + CNT_FLAGGED, 16, cudaMemcpyDeviceToHost, st));
   tm.finish(c->timings);
   CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
   c->counts[NRP_C_EXCLUDED] = (int64_t)c->h_counters[26];
+  c->counts[NRP_C_RECORDS] = c->n_records - (int64_t)c->h_counters[27];
   c->counts[NRP_C_LAUNCHES] = launch_counter();
   double total = 0;
   for (int i = NRP_T_FLAGS; i < NRP_N_TIMINGS; ++i) total += c->timings[i];
   c->timings[NRP_T_TOTAL] = total;
+  return NRP_OK;
+}
+
+void begin_job(nrp_ctx* c, int k, size_t key_bytes, int want_edges) {
+  memset(c->counts, 0, sizeof(c->counts));
+  memset(c->timings, 0, sizeof(c->timings));
+  launch_counter() = 0;
+  c->counts[NRP_C_KEY_BYTES] = (int64_t)key_bytes;
+  c->counts[NRP_C_EDGES] = want_edges ? 0 : -1;
+  c->counts[NRP_C_RUNS] = 1;
+  c->k = k; c->key_bytes = (int)key_bytes;
+  c->have_result = false;
+}
+
+template <typename KeyT>
+int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
+  TRY(configure_kernels<KeyT>(c));
+  c->shard_lo = 0; c->shard_hi = c->n_parts; c->shard_tile_lo = 0; c->shard_tiles = c->n_tiles; c->n_owners = 0;
+  c->shard_m_max = windows_in_range(c, 0, c->n_parts, k);
+  if (c->shard_m_max >= 0xffffe000ll)
+    return fail(NRP_E_UNSUPPORTED, "%lld records exceed the 32-bit record index of one device", (long long)c->shard_m_max);
+  begin_job(c, k, sizeof(KeyT), want_edges);
+  c->counts[NRP_C_WINDOWS_MAX] = c->shard_m_max;
+  StageTimer tm(c);
+  TRY(stage_flags(c, k, internal_repeats, tm));
+  TRY((stage_bulk<KeyT>(c, k, nullptr, nullptr, 0, tm)));
+  TRY((stage_sort_mark<KeyT>(c, k, c->n_parts, !internal_repeats, tm)));
+  if (!internal_repeats && c->n_repeat_records > 0) TRY((stage_compact<KeyT>(c, tm)));
+  TRY((stage_groups<KeyT>(c, tm)));
+  TRY(stage_first_window(c, k, tm));
+  TRY(stage_last_single(c, k, c->g_keys.as<uint64_t>(), c->n_groups, 0, c->n_parts, tm));
+  if (want_edges) TRY(stage_edges(c, tm));
+  TRY(finish_counts(c, tm));
+  c->have_result = true;
+  return NRP_OK;
+}
+
+// ---- sharded path -------------------------------------------------------------------------------------
+template <typename KeyT>
+int shard_extract_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int internal_repeats, int n_owners, int64_t* owner_counts) {
+  TRY(configure_kernels<KeyT>(c));
+  cudaStream_t st = c->stream;
+  c->shard_lo = lo; c->shard_hi = hi; c->n_owners = n_owners;
+  const int64_t byte_lo = c->h_off[lo], byte_hi = c->h_off[hi];
+  c->shard_tile_lo = byte_lo / kTileBytes;
+  c->shard_tiles = hi > lo && byte_hi > byte_lo ? (byte_hi + kTileBytes - 1) / kTileBytes - c->shard_tile_lo : 0;
+  c->shard_m_max = windows_in_range(c, lo, hi, k);
+  if (c->shard_m_max >= 0xffffe000ll) return fail(NRP_E_UNSUPPORTED, "shard too large for 32-bit record indices");
+  begin_job(c, k, sizeof(KeyT), 0);
+  c->counts[NRP_C_WINDOWS_MAX] = c->shard_m_max;
+  StageTimer tm(c);
+  TRY(stage_flags(c, k, internal_repeats, tm));
+  TRY(ensure_record_buffers(c, c->shard_m_max, sizeof(KeyT)));
+  const Parts P = parts_view(c);
+  tm.begin(NRP_T_HISTOGRAM);
+  CU(cudaMemsetAsync(c->hist.ptr, 0, 4 * 260, st));
+  if (c->shard_m_max > 0) {
+    const unsigned grid = (unsigned)std::min<int64_t>(c->shard_tiles, (int64_t)c->n_sms * 2);
+    NRP_LAUNCH((k_hist_from_ascii<<<grid, kTileThreads, 4u * 256, st>>>(P, c->flags.as<uint8_t>(), k, 8, n_owners, c->shard_tiles, c->hist.as<uint32_t>())));
+  }
+  exclusive_scan<uint32_t, uint32_t>(c->hist.as<uint32_t>(), c->cursor1.as<uint32_t>(), n_owners, c->scan_scratch.as<uint32_t>(), st);
+  CU(cudaMemcpyAsync(c->h_counters + 32, c->hist.ptr, 4 * (size_t)n_owners, cudaMemcpyDeviceToHost, st));
+  tm.begin(NRP_T_SPLIT1);
+  if (c->shard_m_max > 0)
+    NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+        P, c->flags.as<uint8_t>(), k, 8, n_owners, 0u, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>())));
+  CU(cudaGetLastError());
+  tm.finish(c->timings);
+  CU(cudaStreamSynchronize(st));
+  const uint32_t* h = reinterpret_cast<const uint32_t*>(c->h_counters + 32);
+  int64_t total = 0;
+  for (int i = 0; i < n_owners; ++i) { owner_counts[i] = h[i]; total += h[i]; }
+  c->n_records = total;
+  return NRP_OK;
+}
+
+template <typename KeyT>
+int shard_group_impl(nrp_ctx* c, const void* keys, const uint32_t* vals, int64_t n, int k, int internal_repeats) {
+  TRY(configure_kernels<KeyT>(c));
+  if (n >= 0xffffe000ll) return fail(NRP_E_UNSUPPORTED, "too many records for 32-bit record indices");
+  // the received buffers are borrowed: they are consumed by the first split only
+  StageTimer tm(c);
+  TRY((stage_bulk<KeyT>(c, k, (const KeyT*)keys, vals, n, tm)));
+  TRY((stage_sort_mark<KeyT>(c, k, c->n_parts, !internal_repeats, tm)));
+  tm.finish(c->timings);
+  return NRP_OK;
+}
+
+template <typename KeyT>
+int shard_finish_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
+  StageTimer tm(c);
+  if (!internal_repeats) TRY((stage_compact<KeyT>(c, tm)));     // flags may come from other ranks: always filter
+  TRY((stage_groups<KeyT>(c, tm)));
+  TRY(stage_first_window(c, k, tm));
+  if (want_edges) { c->counts[NRP_C_EDGES] = 0; TRY(stage_edges(c, tm)); }
+  tm.finish(c->timings);
   c->have_result = true;
   return NRP_OK;
 }
@@ -614,6 +783,78 @@ int nrp_build(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   CU(cudaSetDevice(c->device));
   c->have_result = false;
   return k <= 16 ? build_impl<uint32_t>(c, k, internal_repeats, want_edges) : build_impl<uint64_t>(c, k, internal_repeats, want_edges);
+}
+
+int nrp_ctx_set_stream(nrp_ctx* c, void* cuda_stream) {
+  if (!c) return fail(NRP_E_ARG, "null context");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  if (!c->external_stream) cudaStreamDestroy(c->stream);
+  if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->external_stream = true; }
+  else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->external_stream = false; }
+  return NRP_OK;
+}
+
+int nrp_shard_extract(nrp_ctx* c, int64_t part_lo, int64_t part_hi, int k, int internal_repeats, int n_owners, int64_t* owner_counts) {
+  if (!c || !owner_counts) return fail(NRP_E_ARG, "null argument");
+  if (!c->have_parts) return fail(NRP_E_STATE, "nrp_load_parts has not been called");
+  if (k < 1 || k > 32) return fail(NRP_E_UNSUPPORTED, "k=%d outside [1, 32]", k);
+  if (part_lo < 0 || part_hi < part_lo || part_hi > c->n_parts) return fail(NRP_E_ARG, "bad shard range");
+  if (n_owners < 1 || n_owners > 256) return fail(NRP_E_ARG, "n_owners must be in [1, 256]");
+  CU(cudaSetDevice(c->device));
+  return k <= 16 ? shard_extract_impl<uint32_t>(c, part_lo, part_hi, k, internal_repeats, n_owners, owner_counts)
+                 : shard_extract_impl<uint64_t>(c, part_lo, part_hi, k, internal_repeats, n_owners, owner_counts);
+}
+
+int nrp_shard_send_buffers(nrp_ctx* c, void** keys, void** vals, int* key_bytes) {
+  if (!c || !keys || !vals || !key_bytes) return fail(NRP_E_ARG, "null argument");
+  *keys = c->keysA.ptr; *vals = c->valsA.ptr; *key_bytes = c->key_bytes;
+  return NRP_OK;
+}
+
+int nrp_shard_group(nrp_ctx* c, const void* keys_dev, const uint32_t* vals_dev, int64_t n_records, int k, int internal_repeats) {
+  if (!c) return fail(NRP_E_ARG, "null context");
+  if (!c->have_parts) return fail(NRP_E_STATE, "nrp_load_parts has not been called");
+  if (n_records < 0 || (n_records > 0 && (!keys_dev || !vals_dev))) return fail(NRP_E_ARG, "bad record buffers");
+  CU(cudaSetDevice(c->device));
+  return k <= 16 ? shard_group_impl<uint32_t>(c, keys_dev, vals_dev, n_records, k, internal_repeats)
+                 : shard_group_impl<uint64_t>(c, keys_dev, vals_dev, n_records, k, internal_repeats);
+}
+
+int nrp_flags_export(nrp_ctx* c, uint8_t* dst_dev) {
+  if (!c || !dst_dev) return fail(NRP_E_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (c->n_parts > 0) CU(cudaMemcpyAsync(dst_dev, c->flags.ptr, (size_t)c->n_parts, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return NRP_OK;
+}
+
+int nrp_flags_import(nrp_ctx* c, const uint8_t* src_dev) {
+  if (!c || !src_dev) return fail(NRP_E_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (c->n_parts > 0) CU(cudaMemcpyAsync(c->flags.ptr, src_dev, (size_t)c->n_parts, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return NRP_OK;
+}
+
+int nrp_shard_finish(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
+  if (!c) return fail(NRP_E_ARG, "null context");
+  CU(cudaSetDevice(c->device));
+  return k <= 16 ? shard_finish_impl<uint32_t>(c, k, internal_repeats, want_edges) : shard_finish_impl<uint64_t>(c, k, internal_repeats, want_edges);
+}
+
+int nrp_shard_last_single(nrp_ctx* c, const uint64_t* shared_keys_sorted, int64_t n_shared, int k) {
+  if (!c) return fail(NRP_E_ARG, "null context");
+  if (n_shared < 0 || (n_shared > 0 && !shared_keys_sorted)) return fail(NRP_E_ARG, "bad key array");
+  CU(cudaSetDevice(c->device));
+  DevBuf& buf = c->e_codesA;       // free at this point of the sharded flow
+  TRY(buf.ensure(8 * (size_t)(n_shared + 1)));
+  if (n_shared > 0) CU(cudaMemcpyAsync(buf.ptr, shared_keys_sorted, 8 * (size_t)n_shared, cudaMemcpyHostToDevice, c->stream));
+  StageTimer tm(c);
+  TRY(stage_last_single(c, k, buf.as<uint64_t>(), n_shared, c->shard_lo, c->shard_hi, tm));
+  tm.finish(c->timings);
+  CU(cudaStreamSynchronize(c->stream));
+  return NRP_OK;
 }
 
 int nrp_result_counts(nrp_ctx* c, int64_t out[NRP_N_COUNTS]) {

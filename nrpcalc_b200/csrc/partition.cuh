@@ -95,18 +95,20 @@ __device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&k
 // ---- histogram of leaf buckets straight from the part buffer ------------------------------------------
 // hist has 2^bits entries (bits <= 15): leaf bucket = top `bits` bits of key_hash(canonical k-mer).
 // Persistent CTAs accumulate in shared memory and flush once.
-__global__ void __launch_bounds__(kTileThreads) k_hist_from_ascii(Parts P, const uint8_t* flags, int k, int bits, int64_t n_tiles,
-                                                                 uint32_t* hist) {
+__global__ void __launch_bounds__(kTileThreads) k_hist_from_ascii(Parts P, const uint8_t* flags, int k, int bits, int n_owners,
+                                                                 int64_t n_tiles, uint32_t* hist) {
   extern __shared__ uint32_t s_hist[];
   __shared__ TileStage stage;
-  const int nb = 1 << bits;
+  const int nb = n_owners > 0 ? n_owners : (1 << bits);
   for (int i = threadIdx.x; i < nb; i += blockDim.x) s_hist[i] = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  for (int64_t tile = P.tile_lo + blockIdx.x; tile < P.tile_lo + n_tiles; tile += gridDim.x) {
     __syncthreads();
     tile_load(P, tile, stage);
     __syncthreads();
     tile_windows_blocked(P, stage, tile, k, [&](int, uint64_t canon, uint32_t part, bool) {
-      if (!(flags && flags[part])) atomicAdd(&s_hist[key_hash(canon) >> (64 - bits)], 1u);
+      if (flags && flags[part]) return;
+      uint32_t bin = n_owners > 0 ? owner_hash(canon) % (uint32_t)n_owners : (uint32_t)(key_hash(canon) >> (64 - bits));
+      atomicAdd(&s_hist[bin], 1u);
     });
   }
   __syncthreads();
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, cons
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SplitSmem<KeyT>& s = *reinterpret_cast<SplitSmem<KeyT>*>(smem_raw);
   TileStage& stage = *reinterpret_cast<TileStage*>(smem_raw + sizeof(SplitSmem<KeyT>));
-  const int64_t tile = blockIdx.x;
+  const int64_t tile = P.tile_lo + blockIdx.x;
   const int nb = n_owners > 0 ? n_owners : (1 << r1);
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s.cnt[i] = 0;
   tile_load(P, tile, stage);

@@ -43,7 +43,7 @@ template <typename BgKeyT>
 __global__ void __launch_bounds__(kTileThreads) k_flag_windows(Parts P, int klen, int mode, const BgKeyT* bg_table, int bg_log_slots,
                                                               uint8_t* flags) {
   __shared__ TileStage stage;
-  const int64_t tile = blockIdx.x;
+  const int64_t tile = P.tile_lo + blockIdx.x;
   tile_load(P, tile, stage);
   __syncthreads();
   tile_windows_blocked(P, stage, tile, klen, [&](int, uint64_t canon, uint32_t part, bool palindrome) {
@@ -59,15 +59,14 @@ __global__ void __launch_bounds__(kTileThreads) k_flag_windows(Parts P, int klen
 // records sorted by (key, part).  head[i] = 1 where a new key starts.  Two equal adjacent records (same key,
 // same part) mean that the part has an internal repeat (reference hgraph.py:53-69).
 template <typename KeyT>
-__global__ void k_group_heads(const KeyT* keys, const uint32_t* vals, int64_t n, uint32_t part_base, int64_t n_parts,
-                              uint32_t* head, uint8_t* flags, unsigned long long* n_repeat_records) {
+__global__ void k_group_heads(const KeyT* keys, const uint32_t* vals, int64_t n, uint32_t* head, uint8_t* flags,
+                              unsigned long long* n_repeat_records) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   bool is_head = i == 0 || keys[i] != keys[i - 1];
   head[i] = is_head ? 1u : 0u;
   if (!is_head && vals[i] == vals[i - 1]) {
-    int64_t local = (int64_t)vals[i] - (int64_t)part_base;
-    if (flags && local >= 0 && local < n_parts) flags[local] |= kFlagRepeat;
+    if (flags) flags[vals[i]] |= kFlagRepeat;
     atomicAdd(n_repeat_records, 1ull);
   }
 }
@@ -91,9 +90,9 @@ __global__ void k_compact_records(const KeyT* keys, const uint32_t* vals, const 
 }
 
 // windows of the parts that carry the repeat flag (they were counted as records before the flag was known)
-__global__ void k_flagged_windows(const int64_t* off, const uint8_t* flags, int64_t n_parts, int k, unsigned long long* out) {
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_parts || !(flags[p] & kFlagRepeat)) return;
+__global__ void k_flagged_windows(const int64_t* off, const uint8_t* flags, int64_t lo, int64_t hi, int k, unsigned long long* out) {
+  int64_t p = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= hi || !(flags[p] & kFlagRepeat)) return;
   int64_t w = off[p + 1] - off[p] - k + 1;
   if (w > 0) atomicAdd(out, (unsigned long long)w);
 }
@@ -161,11 +160,11 @@ __device__ __forceinline__ uint64_t window_from_ascii(const uint8_t* seq, int k)
 // first window of part `first_part[g]` whose canonical k-mer equals the group's key: the rank of the group
 // (reference: position of the key's first insertion into repeat_dict, hgraph.py:82-89)
 __global__ void k_group_first_window(const uint8_t* ascii, const int64_t* off, const uint64_t* group_keys, const uint32_t* first_part,
-                                     uint32_t part_base, int64_t n_parts, int64_t n_groups, int k, uint32_t* first_window) {
+                                     int64_t n_parts, int64_t n_groups, int k, uint32_t* first_window) {
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_groups) return;
-  int64_t p = (int64_t)first_part[g] - (int64_t)part_base;
-  if (p < 0 || p >= n_parts) return;                  // first member lives on another rank
+  int64_t p = (int64_t)first_part[g];
+  if (p >= n_parts) return;
   const uint8_t* seq = ascii + off[p];
   const int64_t len = off[p + 1] - off[p];
   const uint64_t key = group_keys[g];
@@ -186,10 +185,10 @@ __global__ void k_group_first_window(const uint8_t* ascii, const int64_t* off, c
 
 // last window of each surviving part whose canonical k-mer is not a shared key: the rank of the part's
 // singleton tuple (id,) in the reference's popitem order
-__global__ void k_last_single(const uint8_t* ascii, const int64_t* off, const uint8_t* flags, int64_t n_parts, int k,
+__global__ void k_last_single(const uint8_t* ascii, const int64_t* off, const uint8_t* flags, int64_t lo, int64_t hi, int k,
                               const uint64_t* shared_keys, int64_t n_shared, int32_t* last_single) {
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_parts) return;
+  int64_t p = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= hi) return;
   const int64_t len = off[p + 1] - off[p];
   int32_t result = -1;
   if (len >= k && !(flags && flags[p])) {
@@ -216,7 +215,7 @@ __global__ void k_last_single(const uint8_t* ascii, const int64_t* off, const ui
 // one thread per member a of a group: pairs (a, b > a).  code = (min id << 32) | max id; pairs of one part with
 // itself (a k-mer occurring twice in a part, internal_repeats=True) get the all-ones code and sort last.
 __global__ void k_edge_pairs(const int64_t* indptr, const uint32_t* members, const unsigned long long* pair_off, int64_t n_groups,
-                             int64_t n_members, const uint32_t* part_id, uint32_t part_base, uint64_t* codes) {
+                             int64_t n_members, const uint32_t* part_id, uint64_t* codes) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_members) return;
   int64_t lo = 0, hi = n_groups;                      // last group with indptr <= t
@@ -227,10 +226,10 @@ __global__ void k_edge_pairs(const int64_t* indptr, const uint32_t* members, con
   const int64_t g = lo;
   const int64_t s = indptr[g + 1] - indptr[g];
   const int64_t a = t - indptr[g];
-  const uint32_t ida = part_id[members[t] - part_base];
+  const uint32_t ida = part_id[members[t]];
   unsigned long long dst = pair_off[g] + (unsigned long long)(a * s - a * (a + 1) / 2);
   for (int64_t b = a + 1; b < s; ++b) {
-    uint32_t idb = part_id[members[indptr[g] + b] - part_base];
+    uint32_t idb = part_id[members[indptr[g] + b]];
     uint64_t code = ida == idb ? ~0ull : (ida < idb ? ((uint64_t)ida << 32) | idb : ((uint64_t)idb << 32) | ida);
     codes[dst + (unsigned long long)(b - a - 1)] = code;
   }

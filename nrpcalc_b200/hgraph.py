@@ -65,6 +65,7 @@ class RepeatStructure(object):
         self.records = 0
         self.timings = defaultdict(float)
         self.counts = defaultdict(int)
+        self.edges = None       # (u, v) id arrays of the last build that asked for edges
 
     def add_entries(self, rank, indptr, members):
         self.rank.append(rank)
@@ -74,29 +75,53 @@ class RepeatStructure(object):
         self.n_members += members.size
 
 
-def _device_build(ctx, structure, ascii_buf, offsets, global_p, ids, k, internal_repeats, want_edges=False):
-    """One libnrpb200 build over parts that all have length >= k; global_p maps local index -> processing rank."""
-    ctx.load_parts(ascii_buf, offsets, ids if want_edges else None)
-    ctx.build(k, internal_repeats, want_edges=want_edges)
-    res = ctx.fetch(want_keys=False)
-    structure.flags[global_p] |= res.flags
-    structure.records += res.counts['records']
-    for name, value in res.timings.items():
-        structure.timings[name] += value
-    for name in ('groups', 'members', 'candidates', 'oversized', 'windows_max'):
-        structure.counts[name] += res.counts[name]
-    structure.counts['runs'] = max(structure.counts['runs'], res.counts['runs'])
+def _world_size():
+    try:
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    except ImportError:
+        return 1
+
+
+def _device_build(ctx, structure, ascii_buf, offsets, global_p, ids, k, internal_repeats, want_edges=False, allow_sharding=False):
+    """One build over parts that all have length >= k; global_p maps local index -> processing rank.
+    With an initialised torch.distributed group of more than one rank the build is hash-sharded across the ranks
+    (nrpcalc_b200.sharded); every rank receives the same result."""
+    if allow_sharding and _world_size() > 1:
+        from . import sharded
+        ops = sharded.NativeOps(ctx)
+        ops.load(ascii_buf, offsets, ids if want_edges else None)
+        out = sharded.build_sharded(ops, offsets, k, internal_repeats, want_edges=want_edges)
+        flags, indptr, members = out['flags'], out['indptr'], out['members']
+        first_window, last_single = out['first_window'], out['last_single']
+        structure.records += out['stats']['records']
+        structure.counts['groups'] += indptr.size - 1
+        structure.counts['members'] += members.size
+        structure.counts['runs'] = max(structure.counts['runs'], 1)
+        structure.edges = out['edges']
+    else:
+        ctx.load_parts(ascii_buf, offsets, ids if want_edges else None)
+        ctx.build(k, internal_repeats, want_edges=want_edges)
+        res = ctx.fetch(want_keys=False)
+        flags, indptr, members, first_window, last_single = res.flags, res.indptr, res.members, res.first_window, res.last_single
+        structure.records += res.counts['records']
+        for name, value in res.timings.items():
+            structure.timings[name] += value
+        for name in ('groups', 'members', 'candidates', 'oversized', 'windows_max'):
+            structure.counts[name] += res.counts[name]
+        structure.counts['runs'] = max(structure.counts['runs'], res.counts['runs'])
+        structure.edges = res.edges
+    structure.flags[global_p] |= flags
     # shared k-mer groups: rank = (p of first member, first window); members -> processing ranks
-    if res.counts['groups']:
-        first = global_p[res.members[res.indptr[:-1]]].astype(np.int64)
-        structure.add_entries((first << 32) | res.first_window.astype(np.int64), res.indptr, global_p[res.members])
+    if indptr.size > 1:
+        first = global_p[members[indptr[:-1]]].astype(np.int64)
+        structure.add_entries((first << 32) | first_window.astype(np.int64), indptr, global_p[members])
     # singleton tuples: one per part that owns at least one window nobody shares
-    own = np.nonzero(res.last_single >= 0)[0]
+    own = np.nonzero(last_single >= 0)[0]
     if own.size:
         p = global_p[own].astype(np.int64)
-        structure.add_entries((p << 32) | res.last_single[own].astype(np.int64), np.arange(own.size + 1, dtype=np.int64),
+        structure.add_entries((p << 32) | last_single[own].astype(np.int64), np.arange(own.size + 1, dtype=np.int64),
                               global_p[own])
-    return res
 
 
 def repeat_structure(parts, background, homology, internal_repeats, ctx=None, want_edges=False):
@@ -133,7 +158,7 @@ def repeat_structure(parts, background, homology, internal_repeats, ctx=None, wa
     long_mask = lengths >= homology
     try:
         if long_mask.all():
-            _device_build(ctx, structure, ascii_buf, offsets, all_p, ids, homology, internal_repeats, want_edges)
+            _device_build(ctx, structure, ascii_buf, offsets, all_p, ids, homology, internal_repeats, want_edges, allow_sharding=True)
         else:
             classes = [(homology, np.nonzero(long_mask)[0])]
             for short_len in np.unique(lengths[~long_mask]).tolist():
@@ -154,7 +179,8 @@ def repeat_structure(parts, background, homology, internal_repeats, ctx=None, wa
                 np.cumsum(lengths[idx], out=sub_off[1:])
                 pieces = [ascii_buf[offsets[i]:offsets[i + 1]] for i in idx.tolist()]
                 sub_ascii = np.concatenate(pieces) if pieces else np.zeros(0, dtype=np.uint8)
-                _device_build(ctx, structure, sub_ascii, sub_off, idx, ids[idx], k_class, internal_repeats, False)
+                _device_build(ctx, structure, sub_ascii, sub_off, idx, ids[idx], k_class, internal_repeats, False,
+                              allow_sharding=k_class == homology)
     finally:
         ctx.set_background(None, 0)
     return structure, ids

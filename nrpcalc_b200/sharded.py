@@ -1,0 +1,214 @@
+"""Hash-sharded repeat-graph construction across the GPUs of one node: one process per GPU, torch.distributed for
+the plumbing (NCCL over NVLink / NVSwitch; gloo in the CPU tests).
+
+The reference has no distributed mode; this is the multi-GPU form of the hot path that replaces
+nrpcalc/base/hgraph.py:23-94:
+
+  * parts are block-sharded: rank r extracts the k-mers of a contiguous range of parts (balanced by windows);
+  * the k-mer space is hash-partitioned: owner(kmer) = owner_hash(kmer) % world, so all records of one k-mer meet
+    on one rank -- ONE all-to-all of (k-mer, part) records;
+  * a part's internal repeat is detected by whichever rank owns the repeated k-mer, but every rank must drop that
+    part: ONE all-reduce (MAX) of the per-part flag bytes;
+  * groups, their ranks, last single windows and edges are small and are gathered to every rank, so that each
+    rank ends with the same RepeatStructure as the single-GPU path and runs the same host replay.
+
+Every rank stages ALL parts on its device (record values are global part indices; first-window ranks can be
+computed by the owner of a group without another exchange).
+
+`ops` is the per-rank device back end: NativeOps drives libnrpb200.so; the CPU tests plug in a numpy model of the
+same five calls to exercise the sharding / exchange / merge logic under gloo.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(lengths, k, world):
+    """Contiguous part ranges, one per rank, balanced by the number of k-windows."""
+    windows = np.maximum(np.asarray(lengths, dtype=np.int64) - k + 1, 0)
+    total = int(windows.sum())
+    csum = np.concatenate(([0], np.cumsum(windows)))
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(csum, total * r / world, side='left')))
+    cuts.append(len(lengths))
+    cuts = np.maximum.accumulate(np.minimum(cuts, len(lengths)))
+    return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]
+
+
+class _DeviceArray(object):
+    """Zero-copy view of library-owned device memory for torch.as_tensor."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {'shape': (int(n),), 'typestr': typestr, 'data': (int(ptr), False), 'version': 2}
+
+
+class NativeOps(object):
+    """The five device calls of the sharded path on one GPU (include/nrp_b200.h, 'sharded path')."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.device = torch.device('cuda', ctx.device)
+        self.stage_ms = {}
+
+    def _account(self):
+        for name, value in self.ctx.timings().items():
+            self.stage_ms[name] = value           # cumulative inside the library for the current job
+
+    def load(self, ascii_buf, offsets, ids, device_ptr=None):
+        self.ctx.load_parts(ascii_buf, offsets, ids, device_ptr=device_ptr)
+        self.n_parts = len(offsets) - 1
+
+    def extract(self, lo, hi, k, internal_repeats, world):
+        counts = self.ctx.shard_extract(lo, hi, k, internal_repeats, world)
+        keys_ptr, vals_ptr, key_bytes = self.ctx.shard_send_buffers()
+        n = int(counts.sum())
+        self.key_dtype = torch.int64 if key_bytes == 8 else torch.int32
+        if n == 0:
+            return (torch.empty(0, dtype=self.key_dtype, device=self.device), torch.empty(0, dtype=torch.int32, device=self.device), counts)
+        keys = torch.as_tensor(_DeviceArray(keys_ptr, n, '<i8' if key_bytes == 8 else '<i4'), device=self.device)
+        vals = torch.as_tensor(_DeviceArray(vals_ptr, n, '<i4'), device=self.device)
+        return keys, vals, counts
+
+    def group(self, keys, vals, k, internal_repeats):
+        torch.cuda.current_stream(self.device).synchronize()
+        self.ctx.shard_group(keys.data_ptr() if keys.numel() else 0, vals.data_ptr() if vals.numel() else 0, keys.numel(), k, internal_repeats)
+
+    def flags(self):
+        out = torch.empty(max(self.n_parts, 1), dtype=torch.uint8, device=self.device)
+        self.ctx.flags_export(out.data_ptr())
+        return out[:self.n_parts]
+
+    def set_flags(self, flags):
+        torch.cuda.current_stream(self.device).synchronize()
+        if self.n_parts:
+            self.ctx.flags_import(flags.data_ptr())
+
+    def finish(self, k, internal_repeats, want_edges):
+        self.ctx.shard_finish(k, internal_repeats, want_edges)
+        counts = self.ctx.counts()
+        res = self.ctx.fetch(want_keys=True)
+        return {'indptr': res.indptr, 'members': res.members, 'first_window': res.first_window, 'keys': res.keys,
+                'edges': res.edges, 'candidates': counts['candidates'], 'oversized': counts['oversized']}
+
+    def last_single(self, shared_keys_sorted, k):
+        self.ctx.shard_last_single(shared_keys_sorted, k)
+        out = np.zeros(self.n_parts, dtype=np.int32)
+        _native_check_last_single(self.ctx, out)
+        return out
+
+
+def _native_check_last_single(ctx, out):
+    from . import _native
+    _native._check(ctx._lib, ctx._lib.nrp_result_last_single(ctx._h, _native._p(out)))
+
+
+def _all_to_all_records(keys, vals, send_counts, group):
+    """One all-to-all of the owner-partitioned records.  Returns (recv_keys, recv_vals, recv_counts)."""
+    world = dist.get_world_size(group)
+    device = keys.device
+    send = torch.as_tensor(np.asarray(send_counts, dtype=np.int64), device=device)
+    recv = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_to_all_single(recv, send, group=group)
+    recv_counts = recv.cpu().numpy()
+    n_recv = int(recv_counts.sum())
+    recv_keys = torch.empty(n_recv, dtype=keys.dtype, device=device)
+    recv_vals = torch.empty(n_recv, dtype=vals.dtype, device=device)
+    in_splits = [int(x) for x in send_counts]
+    out_splits = [int(x) for x in recv_counts]
+    dist.all_to_all_single(recv_keys, keys, out_splits, in_splits, group=group)
+    dist.all_to_all_single(recv_vals, vals, out_splits, in_splits, group=group)
+    return recv_keys, recv_vals, recv_counts
+
+
+class _Phases(object):
+    """Wall-clock per phase (device work is synchronised at every phase boundary by the calls themselves)."""
+
+    def __init__(self, sink, device):
+        import time
+        self.sink, self.device, self.clock = sink, device, time.perf_counter
+        self.t = self.clock()
+
+    def mark(self, name):
+        if self.sink is None:
+            return
+        if self.device.type == 'cuda':
+            torch.cuda.synchronize(self.device)
+        now = self.clock()
+        self.sink[name] = self.sink.get(name, 0.0) + (now - self.t) * 1e3
+        self.t = now
+
+
+def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=None, phase_ms=None):
+    """Run the sharded build over the parts already staged in `ops`.  Every rank returns the same dict:
+    flags[n], indptr, members (global part indices), first_window, keys, last_single[n], edges (u, v) or None,
+    plus per-rank statistics under 'stats'."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    offsets = np.asarray(offsets, dtype=np.int64)
+    n = offsets.size - 1
+    bounds = shard_bounds(np.diff(offsets), k, world)
+    lo, hi = bounds[rank]
+
+    phases = _Phases(phase_ms, ops.device)
+    keys, vals, send_counts = ops.extract(lo, hi, k, internal_repeats, world)
+    phases.mark('extract')
+    recv_keys, recv_vals, recv_counts = _all_to_all_records(keys, vals, send_counts, group)
+    phases.mark('all_to_all')
+    ops.group(recv_keys, recv_vals, k, internal_repeats)
+    phases.mark('group')
+    flags_all = _or_reduce_flags(ops, ops.flags(), group)
+    ops.set_flags(flags_all)
+    phases.mark('flag_reduce')
+    local = ops.finish(k, internal_repeats, want_edges)
+    phases.mark('finish')
+
+    gathered = [None] * world
+    dist.all_gather_object(gathered, {'indptr': local['indptr'], 'members': local['members'], 'first_window': local['first_window'],
+                                      'keys': local['keys'], 'edges': local['edges'], 'sent': int(np.sum(send_counts)),
+                                      'received': int(np.sum(recv_counts)), 'candidates': local['candidates'],
+                                      'oversized': local['oversized']}, group=group)
+    shared_keys = np.sort(np.concatenate([g['keys'] for g in gathered])) if gathered else np.zeros(0, np.uint64)
+    mine = ops.last_single(shared_keys, k)
+    pieces = [None] * world
+    dist.all_gather_object(pieces, mine[lo:hi], group=group)
+    last_single = np.concatenate(pieces) if n else np.zeros(0, dtype=np.int32)
+    phases.mark('gather_order')
+
+    indptr = [np.zeros(1, dtype=np.int64)]
+    base = 0
+    for g in gathered:
+        indptr.append(g['indptr'][1:] + base)
+        base += int(g['indptr'][-1])
+    flags_host = flags_all.cpu().numpy() if n else np.zeros(0, dtype=np.uint8)
+    windows = np.maximum(np.diff(offsets) - k + 1, 0)
+    # records of parts flagged for an internal repeat were exchanged before the flag was known (single path: same)
+    n_records = int(sum(g['received'] for g in gathered)) - int(windows[(flags_host & 1) != 0].sum())
+    result = {
+        'flags': flags_host,
+        'indptr': np.concatenate(indptr),
+        'members': np.concatenate([g['members'] for g in gathered]),
+        'first_window': np.concatenate([g['first_window'] for g in gathered]),
+        'keys': np.concatenate([g['keys'] for g in gathered]),
+        'last_single': last_single,
+        'edges': None,
+        'stats': {'bounds': bounds, 'sent': [g['sent'] for g in gathered], 'received': [g['received'] for g in gathered],
+                  'candidates': [g['candidates'] for g in gathered], 'oversized': [g['oversized'] for g in gathered],
+                  'records': n_records},
+    }
+    if want_edges:
+        codes = [(g['edges'][0].astype(np.uint64) << np.uint64(32)) | g['edges'][1].astype(np.uint64) for g in gathered if g['edges'] is not None]
+        codes = np.unique(np.concatenate(codes)) if codes else np.zeros(0, dtype=np.uint64)   # a pair can come from several owners
+        result['edges'] = ((codes >> np.uint64(32)).astype(np.uint32), (codes & np.uint64(0xffffffff)).astype(np.uint32))
+    phases.mark('merge')
+    return result
+
+
+def _or_reduce_flags(ops, flags_dev, group):
+    """Bitwise OR across ranks.  MAX is not OR for multi-bit bytes (2 | 1 = 3 but max = 2), so reduce each flag bit
+    as its own 0/1 byte plane."""
+    if flags_dev.numel() == 0:
+        return flags_dev
+    planes = torch.stack([(flags_dev >> b) & 1 for b in range(3)])
+    dist.all_reduce(planes, op=dist.ReduceOp.MAX, group=group)
+    return (planes[0] | (planes[1] << 1) | (planes[2] << 2)).contiguous()

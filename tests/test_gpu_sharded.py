@@ -1,0 +1,82 @@
+"""Multi-GPU parity: the hash-sharded build (one process per GPU, NCCL all-to-all) must give exactly the
+single-GPU result.  Spawns world_size processes itself; needs >= 2 visible GPUs (gpurun --gpus 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_parts, k, internal, out_dir):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [os.path.dirname(here), here]
+    import torch
+    import torch.distributed as dist
+    import cases
+    from nrpcalc_b200 import _native, sharded
+    from oracle import ref_port
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        parts = cases.planted_parts(n_parts, 1234) + cases.random_parts(n_parts, 100, 9)
+        uniq = [(pid, seq) for pid, seq in ref_port.uniquify(list(parts)) if len(seq) >= k]
+        seqs = [s for _, s in uniq]
+        ids = np.array([pid for pid, _ in uniq], dtype=np.uint32)
+        offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum([len(s) for s in seqs], out=offsets[1:])
+        buf = np.frombuffer(''.join(seqs).encode(), dtype=np.uint8)
+        ctx = _native.Context(rank)
+        ops = sharded.NativeOps(ctx)
+        ops.load(buf, offsets, ids)
+        res = sharded.build_sharded(ops, offsets, k, internal, want_edges=True)
+        np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), flags=res['flags'], indptr=res['indptr'], members=res['members'],
+                 first_window=res['first_window'], last_single=res['last_single'], eu=res['edges'][0], ev=res['edges'][1],
+                 records=res['stats']['records'])
+        if rank == 0:       # single-GPU result of the same input on the same device
+            ctx.load_parts(buf, offsets, ids)
+            ctx.build(k, internal, True)
+            one = ctx.fetch()
+            np.savez(os.path.join(out_dir, 'single.npz'), flags=one.flags, indptr=one.indptr, members=one.members,
+                     first_window=one.first_window, last_single=one.last_single, eu=one.edges[0], ev=one.edges[1],
+                     records=one.counts['records'])
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def _groups(res):
+    return sorted((int(res['first_window'][g]), tuple(res['members'][res['indptr'][g]:res['indptr'][g + 1]].tolist()))
+                  for g in range(len(res['indptr']) - 1))
+
+
+@pytest.mark.parametrize('k,internal', [(13, False), (17, False), (16, True)])
+def test_sharded_equals_single_gpu(tmp_path, k, internal):
+    world = min(_n_gpus(), 4)
+    if world < 2:
+        pytest.skip('needs at least 2 GPUs')
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(world, _free_port(), 3000, k, internal, str(tmp_path)), nprocs=world, join=True)
+    single = np.load(str(tmp_path / 'single.npz'))
+    for rank in range(world):
+        res = np.load(str(tmp_path / ('rank%d.npz' % rank)))
+        assert ((res['flags'] != 0) == (single['flags'] != 0)).all()
+        assert int(res['records']) == int(single['records'])
+        assert _groups(res) == _groups(single)
+        assert res['last_single'].tolist() == single['last_single'].tolist()
+        assert res['eu'].tolist() == single['eu'].tolist() and res['ev'].tolist() == single['ev'].tolist()
