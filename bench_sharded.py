@@ -28,8 +28,9 @@ def main(args, cfg, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     ops.load(None, off, ids, device_ptr=dev_ascii.data_ptr())
 
-    def step(phase_ms=None):
-        return sharded.build_sharded(ops, off, k, cfg['internal_repeats'], want_edges=want_edges, phase_ms=phase_ms)
+    def step(phase_ms=None, gather_host=False):
+        return sharded.build_sharded(ops, off, k, cfg['internal_repeats'], want_edges=want_edges, phase_ms=phase_ms,
+                                     gather_host=gather_host)
 
     for _ in range(args.warmup):
         res = step()
@@ -63,7 +64,7 @@ def main(args, cfg, rank, world, local_rank):
         dist.barrier()
         t0 = time.perf_counter()
         ops.load(host_ascii.numpy(), off, ids)
-        res = step()
+        res = step(gather_host=True)
         dt = torch.tensor([(time.perf_counter() - t0) * 1e3], device='cuda')
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e.append(float(dt.item()))
@@ -83,7 +84,7 @@ def main(args, cfg, rank, world, local_rank):
                 'vs_baseline': None, 'dtype': 'u64' if key_bytes == 8 else 'u32', 'data': 'synthetic',
                 'config': {'workload': cfg['label'] + (' -- x{} parts (one config-2 batch per GPU)'.format(world) if weak else ''), 'n_parts': n_parts, 'part_len': cfg['length'], 'Lmax': cfg['Lmax'], 'k': k,
                            'kmers': m, 'edges': want_edges, 'sharding': 'parts block-sharded, k-mers hash-partitioned, 1 all-to-all',
-                           'l2': 'explicit 256 MiB flush between steps', 'timing': 'wall clock between barrier+synchronize, max over ranks'},
+                           'l2': 'explicit 256 MiB flush between steps', 'timing': 'wall clock between barrier+synchronize around the device phase (results resident on the devices), max over ranks'},
                 'parts_per_s': n_parts / (ms_per_step * 1e-3),
                 'e2e': {'value': m / (np.mean(e2e) * 1e-3), 'unit': 'k-mers/s', 'h2d_bytes_per_step': int(world * (buf.nbytes + off.nbytes + ids.nbytes)),
                         'd2h_bytes_per_step': int(world * (res['flags'].nbytes + res['members'].nbytes + res['indptr'].nbytes + res['last_single'].nbytes)),

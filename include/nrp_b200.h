@@ -153,9 +153,21 @@ int nrp_shard_group(nrp_ctx* ctx, const void* keys_dev, const uint32_t* vals_dev
 int nrp_flags_export(nrp_ctx* ctx, uint8_t* dst_dev);
 int nrp_flags_import(nrp_ctx* ctx, const uint8_t* src_dev);
 int nrp_shard_finish(nrp_ctx* ctx, int k, int internal_repeats, int want_edges);
-/* shared_keys_sorted: ascending canonical k-mers of ALL ranks' groups (host memory); afterwards
- * nrp_result_last_single holds valid entries for the parts of this rank's shard */
-int nrp_shard_last_single(nrp_ctx* ctx, const uint64_t* shared_keys_sorted, int64_t n_shared, int k);
+/* shared_keys: canonical k-mers of ALL ranks' groups, any order (host memory, or device memory when keys_on_device != 0);
+ * afterwards nrp_result_last_single holds valid entries for the parts of this rank's shard */
+int nrp_shard_last_single(nrp_ctx* ctx, const uint64_t* shared_keys, int64_t n_shared, int k, int keys_on_device);
+/* replace this context's edge list by the sorted, distinct union of n gathered (u < v) edges in device memory */
+int nrp_edges_merge(nrp_ctx* ctx, const uint32_t* u_dev, const uint32_t* v_dev, int64_t n);
+/* device pointer + element count of a result array, for zero-copy use by the host layer's collectives */
+#define NRP_D_GROUP_KEYS   0   /* uint64 */
+#define NRP_D_EDGE_U       1   /* uint32 */
+#define NRP_D_EDGE_V       2   /* uint32 */
+#define NRP_D_FLAGS        3   /* uint8  */
+#define NRP_D_LAST_SINGLE  4   /* int32  */
+#define NRP_D_INDPTR       5   /* int64  */
+#define NRP_D_MEMBERS      6   /* uint32 */
+#define NRP_D_FIRST_WINDOW 7   /* uint32 */
+int nrp_result_device(nrp_ctx* ctx, int what, void** ptr, int64_t* count);
 
 #ifdef __cplusplus
 }

@@ -57,7 +57,9 @@ def _declare(lib):
         'nrp_flags_export': (c_ctx, ptr),
         'nrp_flags_import': (c_ctx, ptr),
         'nrp_shard_finish': (c_ctx, i32, i32, i32),
-        'nrp_shard_last_single': (c_ctx, ptr, i64, i32),
+        'nrp_shard_last_single': (c_ctx, ptr, i64, i32, i32),
+        'nrp_edges_merge': (c_ctx, ptr, ptr, i64),
+        'nrp_result_device': (c_ctx, i32, ctypes.POINTER(ptr), ctypes.POINTER(i64)),
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -180,9 +182,21 @@ class Context(object):
     def shard_finish(self, k, internal_repeats, want_edges):
         _check(self._lib, self._lib.nrp_shard_finish(self._h, int(k), 1 if internal_repeats else 0, 1 if want_edges else 0))
 
-    def shard_last_single(self, shared_keys_sorted, k):
-        keys = np.ascontiguousarray(shared_keys_sorted, dtype=np.uint64)
-        _check(self._lib, self._lib.nrp_shard_last_single(self._h, _p(keys) if keys.size else None, keys.size, int(k)))
+    def shard_last_single(self, shared_keys, k, device_ptr=None, n=0):
+        """shared keys as a host uint64 array, or (device_ptr, n) for keys already in device memory"""
+        if device_ptr is not None:
+            _check(self._lib, self._lib.nrp_shard_last_single(self._h, ctypes.c_void_p(int(device_ptr) or None), int(n), int(k), 1))
+            return
+        keys = np.ascontiguousarray(shared_keys, dtype=np.uint64)
+        _check(self._lib, self._lib.nrp_shard_last_single(self._h, _p(keys) if keys.size else None, keys.size, int(k), 0))
+
+    def edges_merge(self, u_ptr, v_ptr, n):
+        _check(self._lib, self._lib.nrp_edges_merge(self._h, ctypes.c_void_p(int(u_ptr) or None), ctypes.c_void_p(int(v_ptr) or None), int(n)))
+
+    def result_device(self, what):
+        ptr, count = ctypes.c_void_p(), ctypes.c_int64()
+        _check(self._lib, self._lib.nrp_result_device(self._h, int(what), ctypes.byref(ptr), ctypes.byref(count)))
+        return ptr.value or 0, count.value
 
     def counts(self):
         out = np.zeros(N_COUNTS, dtype=np.int64)

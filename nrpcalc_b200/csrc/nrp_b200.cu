@@ -113,7 +113,7 @@ struct nrp_ctx {
   DevBuf keysA, valsA, keysB, valsB;
   DevBuf head, head_scan, group_start, valid, valid_scan, mem_cnt, mem_scan, pair_cnt, pair_scan;
   DevBuf g_keys, g_indptr, g_pair_off, g_members, g_first_part, g_first_window, last_single;
-  DevBuf e_codesA, e_codesB, e_head, e_head_scan, e_u, e_v;
+  DevBuf e_codesA, e_codesB, e_head, e_head_scan, e_u, e_v, shared_keysA, shared_keysB;
   unsigned long long* h_counters = nullptr;   // pinned
 
   // shard window (whole batch unless nrp_shard_extract narrowed it)
@@ -246,7 +246,7 @@ int nrp_ctx_destroy(nrp_ctx* c) {
                    &c->keysB, &c->valsB, &c->head, &c->head_scan, &c->group_start, &c->valid, &c->valid_scan, &c->mem_cnt,
                    &c->mem_scan, &c->pair_cnt, &c->pair_scan, &c->g_keys, &c->g_indptr, &c->g_pair_off, &c->g_members,
                    &c->g_first_part, &c->g_first_window, &c->last_single, &c->e_codesA, &c->e_codesB, &c->e_head, &c->e_head_scan,
-                   &c->e_u, &c->e_v};
+                   &c->e_u, &c->e_v, &c->shared_keysA, &c->shared_keysB};
   for (DevBuf* b : all) b->release();
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -611,6 +611,33 @@ int stage_last_single(nrp_ctx* c, int k, const uint64_t* shared_keys, int64_t n_
   return NRP_OK;
 }
 
+// sort the n codes in e_codesA (alternate e_codesB) and compact the distinct valid ones into e_u / e_v
+int unique_edge_codes(nrp_ctx* c, int64_t n, int64_t* n_edges) {
+  cudaStream_t st = c->stream;
+  TRY(c->e_head.ensure(4 * (size_t)(n + 2))); TRY(c->e_head_scan.ensure(4 * (size_t)(n + 2)));
+  TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n)));
+  TRY(c->scan_scratch.ensure(8 * (size_t)scan_scratch_elems(n + 2)));
+  // ids are < 2^id_bits; the all-ones code of self pairs sorts last because 2^id_bits - 1 is never an id
+  int id_bits = 1;
+  while (id_bits < 32 && ((int64_t)1 << id_bits) <= c->max_id) ++id_bits;
+  LsdPlan plan; plan.n_passes = 0;
+  lsd_plan_add(plan, 0, 0, id_bits);
+  lsd_plan_add(plan, 0, 32, 32 + id_bits);
+  uint64_t* sorted_codes;
+  lsd_sort<uint64_t, false>(c->e_codesA.as<uint64_t>(), nullptr, c->e_codesB.as<uint64_t>(), nullptr, n, plan,
+                            c->lsd_scratch.as<uint32_t>(), st, &sorted_codes, nullptr);
+  NRP_LAUNCH((k_edge_heads<<<grid_for(n, 256), 256, 0, st>>>(sorted_codes, n, c->e_head.as<uint32_t>())));
+  exclusive_scan<uint32_t, uint32_t>(c->e_head.as<uint32_t>(), c->e_head_scan.as<uint32_t>(), n, c->scan_scratch.as<uint32_t>(), st);
+  CU(cudaMemcpyAsync(c->h_counters + 24, c->e_head_scan.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  *n_edges = (int64_t)(uint32_t)c->h_counters[24];
+  TRY(c->e_u.ensure(4 * (size_t)(*n_edges + 1))); TRY(c->e_v.ensure(4 * (size_t)(*n_edges + 1)));
+  NRP_LAUNCH((k_edge_compact<<<grid_for(n, 256), 256, 0, st>>>(sorted_codes, c->e_head.as<uint32_t>(), c->e_head_scan.as<uint32_t>(), n,
+                                                           c->e_u.as<uint32_t>(), c->e_v.as<uint32_t>())));
+  CU(cudaGetLastError());
+  return NRP_OK;
+}
+
 // ---- stage: unique part-pair edges of this context's groups
 int stage_edges(nrp_ctx* c, StageTimer& tm) {
   cudaStream_t st = c->stream;
@@ -622,30 +649,10 @@ int stage_edges(nrp_ctx* c, StageTimer& tm) {
   const int64_t n_pairs = c->n_pairs;
   if (n_pairs > 0) {
     TRY(c->e_codesA.ensure(8 * (size_t)(n_pairs + 1))); TRY(c->e_codesB.ensure(8 * (size_t)(n_pairs + 1)));
-    TRY(c->e_head.ensure(4 * (size_t)(n_pairs + 2))); TRY(c->e_head_scan.ensure(4 * (size_t)(n_pairs + 2)));
-    TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n_pairs)));
-    TRY(c->scan_scratch.ensure(8 * (size_t)scan_scratch_elems(n_pairs + 2)));
     NRP_LAUNCH((k_edge_pairs<<<grid_for(c->n_members, 128), 128, 0, st>>>(c->g_indptr.as<int64_t>(), c->g_members.as<uint32_t>(),
                                                                       c->g_pair_off.as<unsigned long long>(), c->n_groups, c->n_members,
                                                                       c->part_id.as<uint32_t>(), c->e_codesA.as<uint64_t>())));
-    // ids are < 2^id_bits; the all-ones code of self pairs sorts last because 2^id_bits - 1 is never an id
-    int id_bits = 1;
-    while (id_bits < 32 && ((int64_t)1 << id_bits) <= c->max_id) ++id_bits;
-    LsdPlan plan; plan.n_passes = 0;
-    lsd_plan_add(plan, 0, 0, id_bits);
-    lsd_plan_add(plan, 0, 32, 32 + id_bits);
-    uint64_t* sorted_codes;
-    lsd_sort<uint64_t, false>(c->e_codesA.as<uint64_t>(), nullptr, c->e_codesB.as<uint64_t>(), nullptr, n_pairs, plan,
-                              c->lsd_scratch.as<uint32_t>(), st, &sorted_codes, nullptr);
-    NRP_LAUNCH((k_edge_heads<<<grid_for(n_pairs, 256), 256, 0, st>>>(sorted_codes, n_pairs, c->e_head.as<uint32_t>())));
-    exclusive_scan<uint32_t, uint32_t>(c->e_head.as<uint32_t>(), c->e_head_scan.as<uint32_t>(), n_pairs, c->scan_scratch.as<uint32_t>(), st);
-    CU(cudaMemcpyAsync(c->h_counters + 24, c->e_head_scan.as<uint32_t>() + n_pairs, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    n_edges = (int64_t)(uint32_t)c->h_counters[24];
-    TRY(c->e_u.ensure(4 * (size_t)(n_edges + 1))); TRY(c->e_v.ensure(4 * (size_t)(n_edges + 1)));
-    NRP_LAUNCH((k_edge_compact<<<grid_for(n_pairs, 256), 256, 0, st>>>(sorted_codes, c->e_head.as<uint32_t>(), c->e_head_scan.as<uint32_t>(),
-                                                                   n_pairs, c->e_u.as<uint32_t>(), c->e_v.as<uint32_t>())));
-    CU(cudaGetLastError());
+    TRY(unique_edge_codes(c, n_pairs, &n_edges));
   }
   c->counts[NRP_C_EDGES] = n_edges;
   return NRP_OK;
@@ -843,17 +850,56 @@ int nrp_shard_finish(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   return k <= 16 ? shard_finish_impl<uint32_t>(c, k, internal_repeats, want_edges) : shard_finish_impl<uint64_t>(c, k, internal_repeats, want_edges);
 }
 
-int nrp_shard_last_single(nrp_ctx* c, const uint64_t* shared_keys_sorted, int64_t n_shared, int k) {
+int nrp_shard_last_single(nrp_ctx* c, const uint64_t* shared_keys, int64_t n_shared, int k, int keys_on_device) {
   if (!c) return fail(NRP_E_ARG, "null context");
-  if (n_shared < 0 || (n_shared > 0 && !shared_keys_sorted)) return fail(NRP_E_ARG, "bad key array");
+  if (n_shared < 0 || (n_shared > 0 && !shared_keys)) return fail(NRP_E_ARG, "bad key array");
   CU(cudaSetDevice(c->device));
-  DevBuf& buf = c->e_codesA;       // free at this point of the sharded flow
-  TRY(buf.ensure(8 * (size_t)(n_shared + 1)));
-  if (n_shared > 0) CU(cudaMemcpyAsync(buf.ptr, shared_keys_sorted, 8 * (size_t)n_shared, cudaMemcpyHostToDevice, c->stream));
+  TRY(c->shared_keysA.ensure(8 * (size_t)(n_shared + 1))); TRY(c->shared_keysB.ensure(8 * (size_t)(n_shared + 1)));
+  TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n_shared)));
+  if (n_shared > 0)
+    CU(cudaMemcpyAsync(c->shared_keysA.ptr, shared_keys, 8 * (size_t)n_shared, keys_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
   StageTimer tm(c);
-  TRY(stage_last_single(c, k, buf.as<uint64_t>(), n_shared, c->shard_lo, c->shard_hi, tm));
+  tm.begin(NRP_T_ORDER);
+  LsdPlan plan; plan.n_passes = 0;
+  lsd_plan_add(plan, 0, 0, 2 * k);
+  uint64_t* sorted;
+  lsd_sort<uint64_t, false>(c->shared_keysA.as<uint64_t>(), nullptr, c->shared_keysB.as<uint64_t>(), nullptr, n_shared, plan,
+                            c->lsd_scratch.as<uint32_t>(), c->stream, &sorted, nullptr);
+  TRY(stage_last_single(c, k, sorted, n_shared, c->shard_lo, c->shard_hi, tm));
   tm.finish(c->timings);
   CU(cudaStreamSynchronize(c->stream));
+  return NRP_OK;
+}
+
+int nrp_edges_merge(nrp_ctx* c, const uint32_t* u_dev, const uint32_t* v_dev, int64_t n) {
+  if (!c) return fail(NRP_E_ARG, "null context");
+  if (n < 0 || (n > 0 && (!u_dev || !v_dev))) return fail(NRP_E_ARG, "bad edge arrays");
+  CU(cudaSetDevice(c->device));
+  int64_t n_edges = 0;
+  if (n > 0) {
+    TRY(c->e_codesA.ensure(8 * (size_t)(n + 1))); TRY(c->e_codesB.ensure(8 * (size_t)(n + 1)));
+    NRP_LAUNCH((k_edge_codes<<<grid_for(n, 256), 256, 0, c->stream>>>(u_dev, v_dev, n, c->e_codesA.as<uint64_t>())));
+    TRY(unique_edge_codes(c, n, &n_edges));
+  }
+  c->counts[NRP_C_EDGES] = n_edges;
+  CU(cudaStreamSynchronize(c->stream));
+  return NRP_OK;
+}
+
+int nrp_result_device(nrp_ctx* c, int what, void** ptr, int64_t* count) {
+  if (!c || !ptr || !count) return fail(NRP_E_ARG, "null argument");
+  if (!c->have_result) return fail(NRP_E_STATE, "no finished build");
+  switch (what) {
+    case NRP_D_GROUP_KEYS: *ptr = c->g_keys.ptr; *count = c->counts[NRP_C_GROUPS]; break;
+    case NRP_D_EDGE_U: *ptr = c->e_u.ptr; *count = c->counts[NRP_C_EDGES] < 0 ? 0 : c->counts[NRP_C_EDGES]; break;
+    case NRP_D_EDGE_V: *ptr = c->e_v.ptr; *count = c->counts[NRP_C_EDGES] < 0 ? 0 : c->counts[NRP_C_EDGES]; break;
+    case NRP_D_FLAGS: *ptr = c->flags.ptr; *count = c->n_parts; break;
+    case NRP_D_LAST_SINGLE: *ptr = c->last_single.ptr; *count = c->n_parts; break;
+    case NRP_D_INDPTR: *ptr = c->g_indptr.ptr; *count = c->counts[NRP_C_GROUPS] + 1; break;
+    case NRP_D_MEMBERS: *ptr = c->g_members.ptr; *count = c->counts[NRP_C_MEMBERS]; break;
+    case NRP_D_FIRST_WINDOW: *ptr = c->g_first_window.ptr; *count = c->counts[NRP_C_GROUPS]; break;
+    default: return fail(NRP_E_ARG, "unknown result selector %d", what);
+  }
   return NRP_OK;
 }
 

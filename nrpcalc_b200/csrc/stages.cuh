@@ -235,6 +235,11 @@ __global__ void k_edge_pairs(const int64_t* indptr, const uint32_t* members, con
   }
 }
 
+__global__ void k_edge_codes(const uint32_t* u, const uint32_t* v, int64_t n, uint64_t* codes) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) codes[i] = ((uint64_t)u[i] << 32) | v[i];
+}
+
 __global__ void k_edge_heads(const uint64_t* codes, int64_t n, uint32_t* head) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

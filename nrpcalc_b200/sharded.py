@@ -84,23 +84,52 @@ class NativeOps(object):
         if self.n_parts:
             self.ctx.flags_import(flags.data_ptr())
 
+    def _view(self, what, dtype, typestr):
+        ptr, n = self.ctx.result_device(what)
+        if n == 0:
+            return torch.empty(0, dtype=dtype, device=self.device)
+        return torch.as_tensor(_DeviceArray(ptr, n, typestr), device=self.device)
+
     def finish(self, k, internal_repeats, want_edges):
+        """Groups of this rank stay on the device; returns zero-copy views of (group keys, edge u, edge v)."""
         self.ctx.shard_finish(k, internal_repeats, want_edges)
+        keys = self._view(0, torch.int64, '<i8')
+        if want_edges:
+            return keys, self._view(1, torch.int32, '<i4'), self._view(2, torch.int32, '<i4')
+        return keys, None, None
+
+    def last_single(self, all_keys, k):
+        torch.cuda.current_stream(self.device).synchronize()
+        self.ctx.shard_last_single(None, k, device_ptr=all_keys.data_ptr() if all_keys.numel() else 0, n=all_keys.numel())
+
+    def merge_edges(self, u, v):
+        torch.cuda.current_stream(self.device).synchronize()
+        self.ctx.edges_merge(u.data_ptr() if u.numel() else 0, v.data_ptr() if v.numel() else 0, u.numel())
+
+    def fetch_host(self, want_edges):
+        """Host copies of this rank's groups, the flags, this shard's last single windows and the merged edges."""
         counts = self.ctx.counts()
         res = self.ctx.fetch(want_keys=True)
         return {'indptr': res.indptr, 'members': res.members, 'first_window': res.first_window, 'keys': res.keys,
-                'edges': res.edges, 'candidates': counts['candidates'], 'oversized': counts['oversized']}
-
-    def last_single(self, shared_keys_sorted, k):
-        self.ctx.shard_last_single(shared_keys_sorted, k)
-        out = np.zeros(self.n_parts, dtype=np.int32)
-        _native_check_last_single(self.ctx, out)
-        return out
+                'last_single': res.last_single, 'flags': res.flags, 'edges': res.edges if want_edges else None,
+                'candidates': counts['candidates'], 'oversized': counts['oversized']}
 
 
-def _native_check_last_single(ctx, out):
-    from . import _native
-    _native._check(ctx._lib, ctx._lib.nrp_result_last_single(ctx._h, _native._p(out)))
+def _all_gather_var(tensor, group):
+    """all-gather of 1-D tensors of different lengths (pads to the longest, NCCL needs equal sizes)."""
+    world = dist.get_world_size(group)
+    n = torch.tensor([tensor.numel()], dtype=torch.int64, device=tensor.device)
+    sizes = torch.empty(world, dtype=torch.int64, device=tensor.device)
+    dist.all_gather_into_tensor(sizes, n, group=group)
+    sizes = sizes.cpu().tolist()
+    longest = max(sizes) if sizes else 0
+    if longest == 0:
+        return tensor.new_empty(0)
+    padded = tensor.new_zeros(longest)
+    padded[:tensor.numel()] = tensor
+    out = tensor.new_empty(world * longest)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * longest:r * longest + sizes[r]] for r in range(world)])
 
 
 def _all_to_all_records(keys, vals, send_counts, group):
@@ -139,10 +168,17 @@ class _Phases(object):
         self.t = now
 
 
-def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=None, phase_ms=None):
-    """Run the sharded build over the parts already staged in `ops`.  Every rank returns the same dict:
-    flags[n], indptr, members (global part indices), first_window, keys, last_single[n], edges (u, v) or None,
-    plus per-rank statistics under 'stats'."""
+def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=None, phase_ms=None, gather_host=True):
+    """Run the sharded build over the parts already staged in `ops`.
+
+    Device phase (what the graph-build metric times): extract -> all-to-all -> group -> flag OR-reduce -> finish
+    (this rank's groups + first windows) -> all-gather of the shared k-mers -> last single windows of the shard ->
+    all-gather + dedupe of the edges.  Afterwards flags and edges are complete on every device, groups and last
+    single windows are distributed.
+
+    Host phase (gather_host=True): every rank collects all groups and last single windows and returns the same
+    dict: flags[n], indptr, members (global part indices), first_window, keys, last_single[n], edges (u, v) or
+    None, plus statistics under 'stats'.  With gather_host=False only 'stats' is returned."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     offsets = np.asarray(offsets, dtype=np.int64)
@@ -160,47 +196,52 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
     flags_all = _or_reduce_flags(ops, ops.flags(), group)
     ops.set_flags(flags_all)
     phases.mark('flag_reduce')
-    local = ops.finish(k, internal_repeats, want_edges)
+    group_keys, edge_u, edge_v = ops.finish(k, internal_repeats, want_edges)
     phases.mark('finish')
+    ops.last_single(_all_gather_var(group_keys, group), k)
+    phases.mark('last_single')
+    if want_edges:
+        ops.merge_edges(_all_gather_var(edge_u, group), _all_gather_var(edge_v, group))   # a pair can come from several owners
+    phases.mark('edges')
 
+    stats = {'bounds': bounds, 'sent_here': int(np.sum(send_counts)), 'received_here': int(np.sum(recv_counts))}
+    totals = torch.tensor([stats['sent_here'], stats['received_here']], dtype=torch.int64, device=ops.device)
+    per_rank = torch.empty(2 * world, dtype=torch.int64, device=ops.device)
+    dist.all_gather_into_tensor(per_rank, totals, group=group)
+    per_rank = per_rank.cpu().numpy().reshape(world, 2)
+    stats['sent'] = per_rank[:, 0].tolist()
+    stats['received'] = per_rank[:, 1].tolist()
+    flags_host = flags_all.cpu().numpy() if n else np.zeros(0, dtype=np.uint8)
+    windows = np.maximum(np.diff(offsets) - k + 1, 0)
+    # records of parts flagged for an internal repeat were exchanged before the flag was known (single path: same)
+    stats['records'] = int(per_rank[:, 1].sum()) - int(windows[(flags_host & 1) != 0].sum())
+    phases.mark('stats')
+    if not gather_host:
+        return {'stats': stats, 'flags': flags_host}
+
+    local = ops.fetch_host(want_edges)
     gathered = [None] * world
     dist.all_gather_object(gathered, {'indptr': local['indptr'], 'members': local['members'], 'first_window': local['first_window'],
-                                      'keys': local['keys'], 'edges': local['edges'], 'sent': int(np.sum(send_counts)),
-                                      'received': int(np.sum(recv_counts)), 'candidates': local['candidates'],
-                                      'oversized': local['oversized']}, group=group)
-    shared_keys = np.sort(np.concatenate([g['keys'] for g in gathered])) if gathered else np.zeros(0, np.uint64)
-    mine = ops.last_single(shared_keys, k)
-    pieces = [None] * world
-    dist.all_gather_object(pieces, mine[lo:hi], group=group)
-    last_single = np.concatenate(pieces) if n else np.zeros(0, dtype=np.int32)
-    phases.mark('gather_order')
-
+                                      'keys': local['keys'], 'last_single': local['last_single'][lo:hi],
+                                      'candidates': local['candidates'], 'oversized': local['oversized']}, group=group)
     indptr = [np.zeros(1, dtype=np.int64)]
     base = 0
     for g in gathered:
         indptr.append(g['indptr'][1:] + base)
         base += int(g['indptr'][-1])
-    flags_host = flags_all.cpu().numpy() if n else np.zeros(0, dtype=np.uint8)
-    windows = np.maximum(np.diff(offsets) - k + 1, 0)
-    # records of parts flagged for an internal repeat were exchanged before the flag was known (single path: same)
-    n_records = int(sum(g['received'] for g in gathered)) - int(windows[(flags_host & 1) != 0].sum())
+    stats['candidates'] = [g['candidates'] for g in gathered]
+    stats['oversized'] = [g['oversized'] for g in gathered]
     result = {
         'flags': flags_host,
         'indptr': np.concatenate(indptr),
         'members': np.concatenate([g['members'] for g in gathered]),
         'first_window': np.concatenate([g['first_window'] for g in gathered]),
         'keys': np.concatenate([g['keys'] for g in gathered]),
-        'last_single': last_single,
-        'edges': None,
-        'stats': {'bounds': bounds, 'sent': [g['sent'] for g in gathered], 'received': [g['received'] for g in gathered],
-                  'candidates': [g['candidates'] for g in gathered], 'oversized': [g['oversized'] for g in gathered],
-                  'records': n_records},
+        'last_single': np.concatenate([g['last_single'] for g in gathered]) if n else np.zeros(0, dtype=np.int32),
+        'edges': local['edges'],
+        'stats': stats,
     }
-    if want_edges:
-        codes = [(g['edges'][0].astype(np.uint64) << np.uint64(32)) | g['edges'][1].astype(np.uint64) for g in gathered if g['edges'] is not None]
-        codes = np.unique(np.concatenate(codes)) if codes else np.zeros(0, dtype=np.uint64)   # a pair can come from several owners
-        result['edges'] = ((codes >> np.uint64(32)).astype(np.uint32), (codes & np.uint64(0xffffffff)).astype(np.uint32))
-    phases.mark('merge')
+    phases.mark('host_gather')
     return result
 
 

@@ -79,20 +79,32 @@ class OracleOps(object):
             p = int(vals[s])
             _, _, canon, _ = np_oracle.canonical_records(self.codes[self.offsets[p]:self.offsets[p + 1]], np.array([0, self.offsets[p + 1] - self.offsets[p]]), k)
             first_window[g] = int(np.nonzero(canon == np.uint64(key))[0][0])
-        edges = None
+        self.local = {'indptr': indptr, 'members': members, 'first_window': first_window, 'keys': gkeys.astype(np.uint64),
+                      'candidates': int(m), 'oversized': 0}
+        eu = ev = None
         if want_edges:
             pairs = set()
             for g in range(gkeys.size):
                 uniq = sorted(set(int(self.ids[x]) for x in members[indptr[g]:indptr[g + 1]]))
                 pairs.update((a, b) for i, a in enumerate(uniq) for b in uniq[i + 1:])
             pairs = sorted(pairs)
-            edges = (np.array([a for a, _ in pairs], dtype=np.uint32), np.array([b for _, b in pairs], dtype=np.uint32))
-        return {'indptr': indptr, 'members': members, 'first_window': first_window, 'keys': gkeys.astype(np.uint64), 'edges': edges,
-                'candidates': int(m), 'oversized': 0}
+            eu = torch.tensor([a for a, _ in pairs], dtype=torch.int32)
+            ev = torch.tensor([b for _, b in pairs], dtype=torch.int32)
+        return torch.from_numpy(gkeys.astype(np.uint64).view(np.int64).copy()), eu, ev
 
-    def last_single(self, shared_keys_sorted, k):
+    def last_single(self, all_keys, k):
+        shared = np.sort(all_keys.numpy().view(np.uint64))
         out = np.full(self.n_parts, -1, dtype=np.int32)
         part, j, canon, _ = np_oracle.canonical_records(self.codes, self.offsets, k)
-        ok = (part >= self.lo) & (part < self.hi) & (self.flag_bytes[part] == 0) & ~np.isin(canon, shared_keys_sorted)
+        ok = (part >= self.lo) & (part < self.hi) & (self.flag_bytes[part] == 0) & ~np.isin(canon, shared)
         np.maximum.at(out, part[ok], j[ok].astype(np.int32))
+        self.last = out
+
+    def merge_edges(self, u, v):
+        codes = np.unique((u.numpy().astype(np.uint64) << np.uint64(32)) | v.numpy().astype(np.uint32).astype(np.uint64))
+        self.edges = ((codes >> np.uint64(32)).astype(np.uint32), (codes & np.uint64(0xffffffff)).astype(np.uint32))
+
+    def fetch_host(self, want_edges):
+        out = dict(self.local)
+        out.update({'last_single': self.last, 'flags': self.flag_bytes, 'edges': self.edges if want_edges else None})
         return out
