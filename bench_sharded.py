@@ -12,6 +12,9 @@ def main(args, cfg, rank, world, local_rank):
     import bench
     from nrpcalc_b200 import _native, sharded
 
+    # NCCL may print its version banner to stdout; rank 0 must print exactly one JSON line there
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     k = cfg['Lmax'] + 1
@@ -53,7 +56,6 @@ def main(args, cfg, rank, world, local_rank):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)          # slowest rank
         total_ms += float(dt.item())
     clocks = sampler.stop() if rank == 0 else None
-    m = res['stats']['records']
     ms_per_step = total_ms / args.steps
 
     # end to end: host buffers in (every rank stages all parts), merged host results out
@@ -68,6 +70,7 @@ def main(args, cfg, rank, world, local_rank):
         dt = torch.tensor([(time.perf_counter() - t0) * 1e3], device='cuda')
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e.append(float(dt.item()))
+    m = res['stats']['records']
     stage = ctx.timings()
     all_phases = [None] * world
     dist.all_gather_object(all_phases, {name: v / args.steps for name, v in phase_ms.items()})
@@ -102,6 +105,8 @@ def main(args, cfg, rank, world, local_rank):
                 'stage_ms_rank0_last_job': stage,
                 'result': {'records': m, 'groups': int(res['indptr'].size - 1), 'edges': int(res['edges'][0].size) if res['edges'] else -1,
                            'excluded': int((res['flags'] != 0).sum()), 'sent': sent, 'received': res['stats']['received']}}
-        print(json.dumps(line))
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     ctx.close()
     dist.destroy_process_group()

