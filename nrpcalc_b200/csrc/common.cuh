@@ -154,16 +154,16 @@ __device__ __forceinline__ bool tile_canonical(const Parts& P, const TileStage& 
 }
 
 // Blocked iteration: thread t owns the kTileItems consecutive window start positions 8t..8t+7 of the tile.
-// The forward value and its reverse complement ROLL from one window to the next (one shift-or each) and the
-// part lookup is done once per thread; parts are advanced when a position passes the current part's end.
-// f(e, canon, part, is_palindrome) is called for every position that starts a valid window, e ascending.
-template <typename F>
-__device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileStage& s, int64_t tile, int k, F f) {
+// The forward value and its reverse complement ROLL from one window to the next (one shift-or each).  Part
+// bookkeeping is 32-bit and tile relative: for uniform-length parts a (quotient, remainder) pair is advanced
+// per position, for variable-length parts the cached offsets slice is walked.  A part is skipped when it is outside
+// the shard [part_lo, part_hi) or -- with SKIP_FLAGGED -- when its flag byte is non-zero; both tests are made
+// once per part, not per window.  f(e, canon, part, is_palindrome) is called for every valid window, e ascending.
+template <bool SKIP_FLAGGED, typename F>
+__device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileStage& s, int64_t tile, int k, const uint8_t* flags, F f) {
   const int c0 = threadIdx.x * kTileItems;
-  int64_t g = tile * kTileBytes + c0;
-  if (g >= P.total_len) return;
-  int64_t part, end;
-  tile_locate(P, s, g, part, end);
+  const int64_t g_lo = tile * kTileBytes;
+  if (g_lo + c0 >= P.total_len) return;
   const int w = c0 >> 4, sh = (c0 & 15) * 2;                  // sh is 0 or 16
   const uint32_t x0 = s.packed[w], x1 = s.packed[w + 1], x2 = s.packed[w + 2];
   uint64_t v = ((uint64_t)__funnelshift_l(x1, x0, sh) << 32) | __funnelshift_l(x2, x1, sh);   // bases c0 .. c0+31
@@ -171,21 +171,56 @@ __device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileS
   const int down = 64 - 2 * k, top = 2 * k - 2;
   uint64_t fwd = v >> down;
   uint64_t rc = revcomp2(fwd, k);
+  auto part_usable = [&](int64_t part) -> bool {
+    if (part < P.part_lo || part >= P.part_hi) return false;
+    return SKIP_FLAGGED ? flags[part] == 0 : true;
+  };
+  if (P.uniform_len > 0) {
+    const uint32_t L = (uint32_t)P.uniform_len;
+    const int64_t p0 = s.first_part;
+    const uint32_t rel = (uint32_t)(g_lo - p0 * (int64_t)L) + (uint32_t)c0;
+    uint32_t q = rel / L;
+    uint32_t r = rel - q * L;                                 // offset of the position inside its part
+    int64_t part = p0 + q;
+    bool ok = part_usable(part);
+#pragma unroll
+    for (int e = 0; e < kTileItems; ++e) {
+      if (e > 0) {
+        v = (v << 2) | ((next16 >> (16 - 2 * e)) & 3u);
+        fwd = v >> down;
+        rc = (rc >> 2) | ((uint64_t)(3u - ((uint32_t)fwd & 3u)) << top);
+        if (++r == L) { r = 0; ++part; ok = part_usable(part); }
+      }
+      if (ok && r + (uint32_t)k <= L) f(e, fwd < rc ? fwd : rc, (uint32_t)part, fwd == rc);
+    }
+    return;
+  }
+  // variable-length parts: walk the offsets (tile-relative, clamped to int32)
+  const int64_t remaining = P.total_len - g_lo;
+  const int limit = remaining > kTileBytes ? kTileBytes : (int)remaining;      // positions >= limit hold no data
+  int64_t part, end64;
+  tile_locate(P, s, g_lo + c0, part, end64);
+  auto rel_end = [&](int64_t e64) -> int { int64_t d = e64 - g_lo; return d > (1 << 30) ? (1 << 30) : (int)d; };
+  int end = rel_end(end64);
+  bool ok = part_usable(part);
+  int c = c0;
 #pragma unroll
   for (int e = 0; e < kTileItems; ++e) {
     if (e > 0) {
       v = (v << 2) | ((next16 >> (16 - 2 * e)) & 3u);
       fwd = v >> down;
       rc = (rc >> 2) | ((uint64_t)(3u - ((uint32_t)fwd & 3u)) << top);
-      ++g;
-      if (g >= P.total_len) break;
-      while (g >= end) {                                      // next part (skipping empty ones)
-        ++part;
-        if (P.uniform_len > 0) end += P.uniform_len;
-        else end = s.n_slice > 0 ? s.slice[part - s.first_part + 1] : P.off[part + 1];
+      ++c;
+      if (c >= limit) break;
+      if (c >= end) {
+        do {                                                   // next non-empty part
+          ++part;
+          end = rel_end(s.n_slice > 0 ? s.slice[part - s.first_part + 1] : P.off[part + 1]);
+        } while (c >= end);
+        ok = part_usable(part);
       }
     }
-    if (g + k <= end && part >= P.part_lo && part < P.part_hi) f(e, fwd < rc ? fwd : rc, (uint32_t)part, fwd == rc);
+    if (ok && c + k <= end) f(e, fwd < rc ? fwd : rc, (uint32_t)part, fwd == rc);
   }
 }
 

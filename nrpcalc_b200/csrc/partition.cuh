@@ -105,8 +105,7 @@ __global__ void __launch_bounds__(kTileThreads) k_hist_from_ascii(Parts P, const
     __syncthreads();
     tile_load(P, tile, stage);
     __syncthreads();
-    tile_windows_blocked(P, stage, tile, k, [&](int, uint64_t canon, uint32_t part, bool) {
-      if (flags && flags[part]) return;
+    tile_windows_blocked<true>(P, stage, tile, k, flags, [&](int, uint64_t canon, uint32_t, bool) {
       uint32_t bin = n_owners > 0 ? owner_hash(canon) % (uint32_t)n_owners : (uint32_t)(key_hash(canon) >> (64 - bits));
       atomicAdd(&s_hist[bin], 1u);
     });
@@ -152,8 +151,7 @@ __global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, cons
   uint32_t val[kSplitItems], dr[kSplitItems];
 #pragma unroll
   for (int e = 0; e < kSplitItems; ++e) { dr[e] = 0xffffffffu; key[e] = 0; val[e] = 0; }
-  tile_windows_blocked(P, stage, tile, k, [&](int e, uint64_t canon, uint32_t part, bool) {
-    if (flags && flags[part]) return;
+  tile_windows_blocked<true>(P, stage, tile, k, flags, [&](int e, uint64_t canon, uint32_t part, bool) {
     uint32_t d = n_owners > 0 ? owner_hash(canon) % (uint32_t)n_owners : (uint32_t)(key_hash(canon) >> (64 - r1));
     uint32_t rank = atomicAdd(&s.cnt[d], 1u);
 #pragma unroll

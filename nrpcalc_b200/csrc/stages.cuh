@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kTileThreads) k_flag_windows(Parts P, int klen
   const int64_t tile = P.tile_lo + blockIdx.x;
   tile_load(P, tile, stage);
   __syncthreads();
-  tile_windows_blocked(P, stage, tile, klen, [&](int, uint64_t canon, uint32_t part, bool palindrome) {
+  tile_windows_blocked<false>(P, stage, tile, klen, flags, [&](int, uint64_t canon, uint32_t part, bool palindrome) {
     if (mode == 0) {
       if (palindrome) flags[part] |= kFlagPalindrome;             // benign race: all writers OR the same bit
     } else {
