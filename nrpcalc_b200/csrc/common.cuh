@@ -73,9 +73,10 @@ struct TileStage {
 };
 
 // Stage one byte tile: 2-bit pack the bytes [g_lo, g_lo + 4096 + 48) and cache the offsets of its parts.
-__device__ __forceinline__ void tile_load(const Parts& P, int64_t tile, TileStage& s) {
+// `tid` is the thread's index inside the group of kTileThreads threads that works on this tile.
+__device__ __forceinline__ void tile_load(const Parts& P, int64_t tile, TileStage& s, int tid) {
   const int64_t g_lo = tile * kTileBytes;
-  for (int i = threadIdx.x; i < kPackedWords; i += blockDim.x) {
+  for (int i = tid; i < kPackedWords; i += kTileThreads) {
     int64_t g = g_lo + 16 * (int64_t)i;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (g < P.total_len + 48) v = *reinterpret_cast<const uint4*>(P.ascii + g);   // buffer is padded and 16B aligned
@@ -86,9 +87,9 @@ __device__ __forceinline__ void tile_load(const Parts& P, int64_t tile, TileStag
     int64_t p_hi = P.tile_first[tile + 1];            // first part of the next tile: covers every part of this one
     int64_t cnt = p_hi - p_lo + 1;
     if (cnt > kSliceCap) cnt = 0;
-    if (threadIdx.x == 0) { s.first_part = p_lo; s.n_slice = (int)cnt; }
-    for (int i = threadIdx.x; i <= cnt && cnt > 0; i += blockDim.x) s.slice[i] = P.off[p_lo + i];
-  } else if (threadIdx.x == 0) {
+    if (tid == 0) { s.first_part = p_lo; s.n_slice = (int)cnt; }
+    for (int i = tid; i <= cnt && cnt > 0; i += kTileThreads) s.slice[i] = P.off[p_lo + i];
+  } else if (tid == 0) {
     s.first_part = g_lo / P.uniform_len;
     s.n_slice = 0;
   }
@@ -160,8 +161,8 @@ __device__ __forceinline__ bool tile_canonical(const Parts& P, const TileStage& 
 // the shard [part_lo, part_hi) or -- with SKIP_FLAGGED -- when its flag byte is non-zero; both tests are made
 // once per part, not per window.  f(e, canon, part, is_palindrome) is called for every valid window, e ascending.
 template <bool SKIP_FLAGGED, typename F>
-__device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileStage& s, int64_t tile, int k, const uint8_t* flags, F f) {
-  const int c0 = threadIdx.x * kTileItems;
+__device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileStage& s, int64_t tile, int k, const uint8_t* flags, int tid, F f) {
+  const int c0 = tid * kTileItems;
   const int64_t g_lo = tile * kTileBytes;
   if (g_lo + c0 >= P.total_len) return;
   const int w = c0 >> 4, sh = (c0 & 15) * 2;                  // sh is 0 or 16

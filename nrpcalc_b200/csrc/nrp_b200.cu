@@ -78,7 +78,15 @@ enum { CNT_CAND = 0, CNT_REPEAT = 1, CNT_FLAGGED = 2, CNT_WORK = 3, CNT_OVERSIZE
 
 constexpr int kFilterThreads = 1024;
 constexpr int kFilterItems = 8;
-constexpr int kFilterCap = kFilterThreads * kFilterItems;   // 8192 records per leaf bucket in shared memory
+constexpr int kFilterCap = kFilterThreads * kFilterItems;   // 8192 records per leaf bucket in shared memory (1 CTA/SM for 64-bit keys)
+constexpr int kFilterItemsSmall = 4;
+constexpr int kFilterCapSmall = 4096;   // half-size table: two 1024-thread CTAs per SM
+constexpr bool kFilterStaged = false;   // cp.async staging of the next leaf measured slower than direct loads (profiles/README.md)
+
+template <typename KeyT> constexpr size_t filter_smem_large() { return (sizeof(KeyT) + 1) * 2 * (size_t)kFilterCap; }
+template <typename KeyT> constexpr size_t filter_smem_small() {
+  return (sizeof(KeyT) + 1) * 2 * (size_t)(kFilterThreads * kFilterItemsSmall) + (kFilterStaged ? (sizeof(KeyT) + 4) * (size_t)kFilterCapSmall : 0);
+}
 constexpr int kMaxLeafBits = 15;                            // 2^15 u32 counters = 128 KB of shared memory
 
 }  // namespace
@@ -92,7 +100,7 @@ struct nrp_ctx {
 
   // options
   int64_t opt_filter_cap = kFilterCap;
-  int64_t opt_leaf_target = 5500;
+  int64_t opt_leaf_target = 2750;
   int64_t opt_max_level_bits = kMaxLevelBits;
   int64_t opt_max_pairs = (int64_t)1 << 31;
 
@@ -202,9 +210,12 @@ int configure_kernels(nrp_ctx* c) {
   const int split_smem = (int)(sizeof(SplitSmem<KeyT>) + sizeof(TileStage));
   CU(cudaFuncSetAttribute(k_split_from_ascii<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, split_smem));
   CU(cudaFuncSetAttribute(k_split_from_records<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<KeyT>)));
-  const int filter_smem = (int)((sizeof(KeyT) + 1) * 2 * kFilterCap);
-  CU(cudaFuncSetAttribute((k_filter<KeyT, kFilterThreads, kFilterItems>), cudaFuncAttributeMaxDynamicSharedMemorySize, filter_smem));
-  CU(cudaFuncSetAttribute(k_hist_from_ascii, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << kMaxLeafBits));
+  CU(cudaFuncSetAttribute((k_filter<KeyT, kFilterThreads, kFilterItems, kFilterCap, false>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)filter_smem_large<KeyT>()));
+  CU(cudaFuncSetAttribute((k_filter<KeyT, kFilterThreads, kFilterItemsSmall, kFilterCapSmall, kFilterStaged>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)filter_smem_small<KeyT>()));
+  CU(cudaFuncSetAttribute(k_hist_from_ascii<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << kMaxLeafBits));
+  CU(cudaFuncSetAttribute(k_hist_from_ascii<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << kMaxLeafBits));
   CU(cudaFuncSetAttribute(k_hist_from_records<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << kMaxLeafBits));
   done = true;
   return NRP_OK;
@@ -261,7 +272,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   if (!c || !name) return fail(NRP_E_ARG, "null argument");
   std::string n(name);
   if (n == "filter_cap") c->opt_filter_cap = (value <= 0 || value > kFilterCap) ? kFilterCap : value;
-  else if (n == "leaf_target") c->opt_leaf_target = value <= 0 ? 5500 : value;
+  else if (n == "leaf_target") c->opt_leaf_target = value <= 0 ? 2750 : value;
   else if (n == "max_level_bits") c->opt_max_level_bits = (value <= 0 || value > kMaxLevelBits) ? kMaxLevelBits : value;
   else if (n == "max_pairs") c->opt_max_pairs = value <= 0 ? ((int64_t)1 << 31) : value;
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
@@ -412,8 +423,13 @@ int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, 
   CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * CNT_N, st));
   if (m_max > 0) {
     if (from_ascii) {
-      const unsigned grid = (unsigned)std::min<int64_t>(c->shard_tiles, (int64_t)c->n_sms * (bits >= 15 ? 1 : 2));
-      NRP_LAUNCH((k_hist_from_ascii<<<grid, kTileThreads, 4u << bits, st>>>(P, c->flags.as<uint8_t>(), k, bits, 0, c->shard_tiles, c->hist.as<uint32_t>())));
+      if (bits >= 15) {
+        const unsigned grid = (unsigned)std::min<int64_t>((c->shard_tiles + 1) / 2, (int64_t)c->n_sms);
+        NRP_LAUNCH((k_hist_from_ascii<2><<<grid, 2 * kTileThreads, 4u << bits, st>>>(P, c->flags.as<uint8_t>(), k, bits, 0, c->shard_tiles, c->hist.as<uint32_t>())));
+      } else {
+        const unsigned grid = (unsigned)std::min<int64_t>(c->shard_tiles, (int64_t)c->n_sms * (bits >= 14 ? 2 : 3));
+        NRP_LAUNCH((k_hist_from_ascii<1><<<grid, kTileThreads, 4u << bits, st>>>(P, c->flags.as<uint8_t>(), k, bits, 0, c->shard_tiles, c->hist.as<uint32_t>())));
+      }
     } else {
       const unsigned grid = (unsigned)std::min<int64_t>((n_in + 511) / 512, (int64_t)c->n_sms * (bits >= 15 ? 1 : 2));
       NRP_LAUNCH((k_hist_from_records<KeyT><<<grid, 512, 4u << bits, st>>>(in_keys, n_in, bits, c->hist.as<uint32_t>())));
@@ -452,11 +468,20 @@ int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, 
   }
   tm.begin(NRP_T_FILTER);
   if (m_max > 0) {
-    const size_t fsm = (sizeof(KeyT) + 1) * 2 * (size_t)kFilterCap;
-    const unsigned fgrid = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * (sizeof(KeyT) == 4 ? 2 : 1));
-    NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItems><<<fgrid, kFilterThreads, fsm, st>>>(
-        leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, (uint32_t)c->opt_filter_cap,
-        reinterpret_cast<uint32_t*>(cnt + CNT_WORK), free_keys, free_vals, cnt + CNT_CAND, reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED))));
+    // leaves that average <= 2750 records use the half-size table (two CTAs per SM); larger ones the full table
+    const bool small = (m_max >> bits) <= 2750;
+    const size_t fsm = small ? filter_smem_small<KeyT>() : filter_smem_large<KeyT>();
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (224 * 1024) / (fsm + 1024)));
+    const unsigned fgrid = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * per_sm);
+    const uint32_t cap = (uint32_t)std::min<int64_t>(c->opt_filter_cap, small ? kFilterCapSmall : kFilterCap);
+    if (small)
+      NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItemsSmall, kFilterCapSmall, kFilterStaged><<<fgrid, kFilterThreads, fsm, st>>>(
+          leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, free_keys, free_vals, cnt + CNT_CAND,
+          reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED))));
+    else
+      NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItems, kFilterCap, false><<<fgrid, kFilterThreads, fsm, st>>>(
+          leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, free_keys, free_vals, cnt + CNT_CAND,
+          reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED))));
   }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->h_counters, cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, st));
@@ -737,7 +762,7 @@ int shard_extract_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int internal_r
   CU(cudaMemsetAsync(c->hist.ptr, 0, 4 * 260, st));
   if (c->shard_m_max > 0) {
     const unsigned grid = (unsigned)std::min<int64_t>(c->shard_tiles, (int64_t)c->n_sms * 2);
-    NRP_LAUNCH((k_hist_from_ascii<<<grid, kTileThreads, 4u * 256, st>>>(P, c->flags.as<uint8_t>(), k, 8, n_owners, c->shard_tiles, c->hist.as<uint32_t>())));
+    NRP_LAUNCH((k_hist_from_ascii<1><<<grid, kTileThreads, 4u * 256, st>>>(P, c->flags.as<uint8_t>(), k, 8, n_owners, c->shard_tiles, c->hist.as<uint32_t>())));
   }
   exclusive_scan<uint32_t, uint32_t>(c->hist.as<uint32_t>(), c->cursor1.as<uint32_t>(), n_owners, c->scan_scratch.as<uint32_t>(), st);
   CU(cudaMemcpyAsync(c->h_counters + 32, c->hist.ptr, 4 * (size_t)n_owners, cudaMemcpyDeviceToHost, st));

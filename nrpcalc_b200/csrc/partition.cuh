@@ -95,20 +95,29 @@ __device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&k
 // ---- histogram of leaf buckets straight from the part buffer ------------------------------------------
 // hist has 2^bits entries (bits <= 15): leaf bucket = top `bits` bits of key_hash(canonical k-mer).
 // Persistent CTAs accumulate in shared memory and flush once.
-__global__ void __launch_bounds__(kTileThreads) k_hist_from_ascii(Parts P, const uint8_t* flags, int k, int bits, int n_owners,
-                                                                 int64_t n_tiles, uint32_t* hist) {
+// HALVES groups of kTileThreads threads work on different tiles and share the histogram (HALVES = 2 keeps 32 warps
+// on an SM when the 128 KB histogram of 2^15 buckets allows only one CTA).
+template <int HALVES>
+__global__ void __launch_bounds__(kTileThreads * HALVES) k_hist_from_ascii(Parts P, const uint8_t* flags, int k, int bits, int n_owners,
+                                                                          int64_t n_tiles, uint32_t* hist) {
   extern __shared__ uint32_t s_hist[];
-  __shared__ TileStage stage;
+  __shared__ TileStage stages[HALVES];
+  const int half = threadIdx.x / kTileThreads, tid = threadIdx.x % kTileThreads;
+  TileStage& stage = stages[half];
   const int nb = n_owners > 0 ? n_owners : (1 << bits);
   for (int i = threadIdx.x; i < nb; i += blockDim.x) s_hist[i] = 0;
-  for (int64_t tile = P.tile_lo + blockIdx.x; tile < P.tile_lo + n_tiles; tile += gridDim.x) {
+  const int64_t rounds = (n_tiles + (int64_t)gridDim.x * HALVES - 1) / ((int64_t)gridDim.x * HALVES);
+  for (int64_t r = 0; r < rounds; ++r) {
+    const int64_t t = (r * gridDim.x + blockIdx.x) * HALVES + half;
+    const int64_t tile = P.tile_lo + t;
     __syncthreads();
-    tile_load(P, tile, stage);
+    if (t < n_tiles) tile_load(P, tile, stage, tid);
     __syncthreads();
-    tile_windows_blocked<true>(P, stage, tile, k, flags, [&](int, uint64_t canon, uint32_t, bool) {
-      uint32_t bin = n_owners > 0 ? owner_hash(canon) % (uint32_t)n_owners : (uint32_t)(key_hash(canon) >> (64 - bits));
-      atomicAdd(&s_hist[bin], 1u);
-    });
+    if (t < n_tiles)
+      tile_windows_blocked<true>(P, stage, tile, k, flags, tid, [&](int, uint64_t canon, uint32_t, bool) {
+        uint32_t bin = n_owners > 0 ? owner_hash(canon) % (uint32_t)n_owners : (uint32_t)(key_hash(canon) >> (64 - bits));
+        atomicAdd(&s_hist[bin], 1u);
+      });
   }
   __syncthreads();
   for (int i = threadIdx.x; i < nb; i += blockDim.x) {
@@ -145,13 +154,13 @@ __global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, cons
   const int64_t tile = P.tile_lo + blockIdx.x;
   const int nb = n_owners > 0 ? n_owners : (1 << r1);
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s.cnt[i] = 0;
-  tile_load(P, tile, stage);
+  tile_load(P, tile, stage, threadIdx.x);
   __syncthreads();
   KeyT key[kSplitItems];
   uint32_t val[kSplitItems], dr[kSplitItems];
 #pragma unroll
   for (int e = 0; e < kSplitItems; ++e) { dr[e] = 0xffffffffu; key[e] = 0; val[e] = 0; }
-  tile_windows_blocked<true>(P, stage, tile, k, flags, [&](int e, uint64_t canon, uint32_t part, bool) {
+  tile_windows_blocked<true>(P, stage, tile, k, flags, threadIdx.x, [&](int e, uint64_t canon, uint32_t part, bool) {
     uint32_t d = n_owners > 0 ? owner_hash(canon) % (uint32_t)n_owners : (uint32_t)(key_hash(canon) >> (64 - r1));
     uint32_t rank = atomicAdd(&s.cnt[d], 1u);
 #pragma unroll
@@ -239,24 +248,71 @@ __global__ void k_segment_tiles(const uint32_t* leaf_off, int r1, int r2, uint32
 // are appended to the candidate list.  Buckets larger than `cap` records are appended whole (the small sort
 // then sees a superset, which is still correct).  EMPTY = all ones is never a canonical k-mer: the reverse
 // complement of T..T is A..A = 0.
-template <typename KeyT, int T, int E>
-__global__ void __launch_bounds__(T) k_filter(const KeyT* keys, const uint32_t* vals, const uint32_t* leaf_off, uint32_t n_leaf,
-                                              int leaf_bits, uint32_t cap, uint32_t* work, KeyT* cand_keys, uint32_t* cand_vals,
+__device__ __forceinline__ void cp_async_u32(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_u64(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_key(uint32_t* d, const uint32_t* s) { cp_async_u32(d, s); }
+__device__ __forceinline__ void cp_async_key(uint64_t* d, const uint64_t* s) { cp_async_u64(d, s); }
+
+// STAGED: the records of the NEXT leaf are copied global -> shared with cp.async (LDGSTS) while the current leaf is
+// processed out of registers, which takes the DRAM latency of a leaf off the critical path without costing
+// registers (two 1024-thread CTAs per SM need <= 32 registers per thread).  CAP = records a leaf may hold to be
+// filtered in shared memory (table of 2*T*E slots, staging of CAP records).
+template <typename KeyT, int T, int E, int CAP, bool STAGED>
+__global__ void __launch_bounds__(T, (E <= 4) ? 2 : 1) k_filter(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* leaf_off,
+                                              uint32_t n_leaf, int leaf_bits, uint32_t cap, KeyT* cand_keys, uint32_t* cand_vals,
                                               unsigned long long* n_cand, uint32_t* n_oversized) {
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   KeyT* table = reinterpret_cast<KeyT*>(smem_raw);
   unsigned char* marked = smem_raw + sizeof(KeyT) * (size_t)(2 * T * E);
-  __shared__ uint32_t s_leaf;
+  KeyT* st_keys = reinterpret_cast<KeyT*>(marked + 2 * T * E);
+  uint32_t* st_vals = reinterpret_cast<uint32_t*>(st_keys + (STAGED ? CAP : 0));
   const KeyT kEmpty = ~KeyT(0);
   const int lane = threadIdx.x & 31;
-  for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_leaf = atomicAdd(work, 1u);
-    __syncthreads();
-    const uint32_t leaf = s_leaf;
-    if (leaf >= n_leaf) break;
-    const uint32_t lo = leaf_off[leaf];
-    const uint32_t n = leaf_off[leaf + 1] - lo;
+  uint32_t next_lo = 0, next_n = 0;
+  auto stage_next = [&](uint32_t lf) {            // start the asynchronous copy of leaf lf into the staging area
+    next_n = 0;
+    if (lf < n_leaf) { next_lo = leaf_off[lf]; next_n = leaf_off[lf + 1] - next_lo; }
+    if (STAGED && next_n >= 2 && next_n <= cap) {
+      for (uint32_t i = threadIdx.x; i < next_n; i += T) {
+        cp_async_key(st_keys + i, keys + next_lo + i);
+        cp_async_u32(st_vals + i, vals + next_lo + i);
+      }
+    }
+    if (STAGED) asm volatile("cp.async.commit_group;" ::);
+  };
+  stage_next(blockIdx.x);
+  for (uint32_t leaf = blockIdx.x; leaf < n_leaf; leaf += gridDim.x) {
+    const uint32_t lo = next_lo, n = next_n;
+    const bool fits = n >= 2 && n <= cap;
+    KeyT key[E];
+    uint32_t val[E], slot[E];
+    if (STAGED) {
+      asm volatile("cp.async.wait_group 0;" ::);
+      __syncthreads();                              // staging holds this leaf; previous leaf's table readers are done
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        uint32_t i = threadIdx.x + e * T;
+        bool ok = fits && i < n;
+        key[e] = ok ? st_keys[i] : kEmpty;
+        val[e] = ok ? st_vals[i] : 0u;
+      }
+      __syncthreads();                              // everyone copied out: the staging area is free again
+      stage_next(leaf + gridDim.x);
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {                 // issue the loads first; they are in flight while the table is cleared
+        uint32_t i = threadIdx.x + e * T;
+        bool ok = fits && i < n;
+        key[e] = ok ? __ldg(keys + lo + i) : kEmpty;
+        val[e] = ok ? __ldg(vals + lo + i) : 0u;
+      }
+      stage_next(leaf + gridDim.x);
+      __syncthreads();                              // previous leaf's readers are done with the table
+    }
     if (n < 2) continue;
     if (n > cap) {
       if (threadIdx.x == 0) atomicAdd(n_oversized, 1u);
@@ -277,18 +333,13 @@ __global__ void __launch_bounds__(T) k_filter(const KeyT* keys, const uint32_t* 
     uint32_t slots = 64;
     while (slots < 2u * n) slots <<= 1;
     const uint32_t smask = slots - 1u;
-    int log_slots = 31 - __clz(slots);
+    const int log_slots = 31 - __clz(slots);
     for (uint32_t i = threadIdx.x; i < slots; i += T) { table[i] = kEmpty; marked[i] = 0; }
     __syncthreads();
-    KeyT key[E];
-    uint32_t val[E], slot[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      uint32_t i = threadIdx.x + e * T;
       slot[e] = 0xffffffffu;
-      if (i < n) {
-        key[e] = keys[lo + i];
-        val[e] = vals[lo + i];
+      if (key[e] != kEmpty) {
         uint32_t h = (uint32_t)(key_hash((uint64_t)key[e]) >> (64 - leaf_bits - log_slots)) & smask;
         for (;;) {
           KeyT old = atomic_cas(&table[h], kEmpty, key[e]);
@@ -316,6 +367,7 @@ __global__ void __launch_bounds__(T) k_filter(const KeyT* keys, const uint32_t* 
       }
     }
   }
+  if (STAGED) asm volatile("cp.async.wait_group 0;" ::);
 }
 
 }  // namespace nrp

@@ -44,9 +44,9 @@ __global__ void __launch_bounds__(kTileThreads) k_flag_windows(Parts P, int klen
                                                               uint8_t* flags) {
   __shared__ TileStage stage;
   const int64_t tile = P.tile_lo + blockIdx.x;
-  tile_load(P, tile, stage);
+  tile_load(P, tile, stage, threadIdx.x);
   __syncthreads();
-  tile_windows_blocked<false>(P, stage, tile, klen, flags, [&](int, uint64_t canon, uint32_t part, bool palindrome) {
+  tile_windows_blocked<false>(P, stage, tile, klen, flags, threadIdx.x, [&](int, uint64_t canon, uint32_t part, bool palindrome) {
     if (mode == 0) {
       if (palindrome) flags[part] |= kFlagPalindrome;             // benign race: all writers OR the same bit
     } else {
