@@ -74,7 +74,7 @@ struct DevBuf {
   template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
 };
 
-enum { CNT_CAND = 0, CNT_REPEAT = 1, CNT_FLAGGED = 2, CNT_WORK = 3, CNT_OVERSIZED = 4, CNT_N = 8 };
+enum { CNT_CAND = 0, CNT_REPEAT = 1, CNT_FLAGGED = 2, CNT_WORK = 3, CNT_OVERSIZED = 4, CNT_UNSORTED = 5, CNT_N = 8 };
 
 constexpr int kFilterThreads = 1024;
 constexpr int kFilterItems = 8;
@@ -133,6 +133,7 @@ struct nrp_ctx {
   void* cand_keys = nullptr; uint32_t* cand_vals = nullptr;     // candidates / sorted candidates
   void* spare_keys = nullptr; uint32_t* spare_vals = nullptr;   // scratch of the same size
   int64_t n_cand = 0, n_sorted = 0, n_records = 0, n_repeat_records = 0;
+  bool cand_unsorted = false;    // the filter could not order some leaf's candidates: the global sort is needed
   int64_t n_groups = 0, n_members = 0, n_pairs = 0;
 
   // result of the last build
@@ -477,11 +478,11 @@ int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, 
     if (small)
       NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItemsSmall, kFilterCapSmall, kFilterStaged><<<fgrid, kFilterThreads, fsm, st>>>(
           leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, free_keys, free_vals, cnt + CNT_CAND,
-          reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED))));
+          reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED), reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED))));
     else
       NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItems, kFilterCap, false><<<fgrid, kFilterThreads, fsm, st>>>(
           leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, free_keys, free_vals, cnt + CNT_CAND,
-          reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED))));
+          reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED), reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED))));
   }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->h_counters, cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, st));
@@ -491,6 +492,7 @@ int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, 
   c->n_records = (int64_t)(uint32_t)c->h_counters[16];
   c->counts[NRP_C_OVERSIZED] = (int64_t)(uint32_t)c->h_counters[CNT_OVERSIZED];
   c->counts[NRP_C_CANDIDATES] = c->n_cand;
+  c->cand_unsorted = (uint32_t)c->h_counters[CNT_UNSORTED] != 0;
   c->cand_keys = free_keys; c->cand_vals = free_vals;         // candidates; the leaf buffers are free again
   c->spare_keys = leaf_keys; c->spare_vals = leaf_vals;
   return NRP_OK;
@@ -515,11 +517,15 @@ int stage_sort_mark(nrp_ctx* c, int k, int64_t n_parts_total, bool mark_repeats,
   const int64_t n = c->n_cand;
   int part_bits = 1;
   while (((int64_t)1 << part_bits) < n_parts_total) ++part_bits;
-  TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n)));
-  LsdPlan plan = lsd_plan(2 * k, part_bits);
-  KeyT* sk; uint32_t* sv;
-  lsd_sort<KeyT, true>((KeyT*)c->cand_keys, c->cand_vals, (KeyT*)c->spare_keys, c->spare_vals, n, plan, c->lsd_scratch.as<uint32_t>(), st, &sk, &sv);
-  if (sk != (KeyT*)c->cand_keys) { std::swap(c->cand_keys, c->spare_keys); std::swap(c->cand_vals, c->spare_vals); }
+  if (c->cand_unsorted) {
+    // rare: a leaf bucket over the filter capacity or with > kLeafSortCap candidates (heavy duplicate keys)
+    TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n)));
+    LsdPlan plan = lsd_plan(2 * k, part_bits);
+    KeyT* sk; uint32_t* sv;
+    lsd_sort<KeyT, true>((KeyT*)c->cand_keys, c->cand_vals, (KeyT*)c->spare_keys, c->spare_vals, n, plan, c->lsd_scratch.as<uint32_t>(), st, &sk, &sv);
+    if (sk != (KeyT*)c->cand_keys) { std::swap(c->cand_keys, c->spare_keys); std::swap(c->cand_vals, c->spare_vals); }
+    c->counts[NRP_C_RUNS] = 2;      // reported: the fallback sort ran
+  }
   tm.begin(NRP_T_GROUP);
   TRY(ensure_group_buffers(c, n));
   unsigned long long* cnt = c->counters.as<unsigned long long>();
@@ -624,14 +630,23 @@ int stage_first_window(nrp_ctx* c, int k, StageTimer& tm) {
   return NRP_OK;
 }
 
-// ---- stage: last unshared window of the parts in [lo, hi) given the sorted shared keys
+// ---- stage: last unshared window of the parts in [lo, hi); the shared k-mers (device, any order) go into a hash set
 int stage_last_single(nrp_ctx* c, int k, const uint64_t* shared_keys, int64_t n_shared, int64_t lo, int64_t hi, StageTimer& tm) {
   cudaStream_t st = c->stream;
   tm.begin(NRP_T_ORDER);
+  int log_slots = 0;
+  if (n_shared > 0) {
+    log_slots = 6;
+    while (((int64_t)1 << log_slots) < 2 * n_shared) ++log_slots;
+    TRY(c->shared_keysB.ensure((size_t)8 << log_slots));
+    CU(cudaMemsetAsync(c->shared_keysB.ptr, 0xff, (size_t)8 << log_slots, st));
+    const unsigned grid = (unsigned)std::min<int64_t>((n_shared + 255) / 256, c->n_sms * 8);
+    NRP_LAUNCH((k_bg_insert<uint64_t><<<grid, 256, 0, st>>>(shared_keys, n_shared, c->shared_keysB.as<uint64_t>(), log_slots)));
+  }
   if (c->n_parts > 0) CU(cudaMemsetAsync(c->last_single.ptr, 0xff, sizeof(int32_t) * (size_t)c->n_parts, st));
   if (hi > lo)
     NRP_LAUNCH((k_last_single<<<grid_for(hi - lo, 128), 128, 0, st>>>(c->ascii.as<uint8_t>(), c->off.as<int64_t>(), c->flags.as<uint8_t>(), lo, hi,
-                                                                  k, shared_keys, n_shared, c->last_single.as<int32_t>())));
+                                                                  k, c->shared_keysB.as<uint64_t>(), log_slots, c->last_single.as<int32_t>())));
   CU(cudaGetLastError());
   return NRP_OK;
 }
@@ -879,18 +894,11 @@ int nrp_shard_last_single(nrp_ctx* c, const uint64_t* shared_keys, int64_t n_sha
   if (!c) return fail(NRP_E_ARG, "null context");
   if (n_shared < 0 || (n_shared > 0 && !shared_keys)) return fail(NRP_E_ARG, "bad key array");
   CU(cudaSetDevice(c->device));
-  TRY(c->shared_keysA.ensure(8 * (size_t)(n_shared + 1))); TRY(c->shared_keysB.ensure(8 * (size_t)(n_shared + 1)));
-  TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n_shared)));
+  TRY(c->shared_keysA.ensure(8 * (size_t)(n_shared + 1)));
   if (n_shared > 0)
     CU(cudaMemcpyAsync(c->shared_keysA.ptr, shared_keys, 8 * (size_t)n_shared, keys_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
   StageTimer tm(c);
-  tm.begin(NRP_T_ORDER);
-  LsdPlan plan; plan.n_passes = 0;
-  lsd_plan_add(plan, 0, 0, 2 * k);
-  uint64_t* sorted;
-  lsd_sort<uint64_t, false>(c->shared_keysA.as<uint64_t>(), nullptr, c->shared_keysB.as<uint64_t>(), nullptr, n_shared, plan,
-                            c->lsd_scratch.as<uint32_t>(), c->stream, &sorted, nullptr);
-  TRY(stage_last_single(c, k, sorted, n_shared, c->shard_lo, c->shard_hi, tm));
+  TRY(stage_last_single(c, k, c->shared_keysA.as<uint64_t>(), n_shared, c->shard_lo, c->shard_hi, tm));
   tm.finish(c->timings);
   CU(cudaStreamSynchronize(c->stream));
   return NRP_OK;

@@ -21,6 +21,7 @@ constexpr int kSplitThreads = kTileThreads;     // 512
 constexpr int kSplitItems = 8;
 constexpr int kSplitTile = kSplitThreads * kSplitItems;   // 4096 records staged per CTA
 constexpr int kMaxLevelBits = 8;
+constexpr int kLeafSortCap = 1024;              // candidates of one leaf that are ordered inside the filter kernel
 
 template <typename KeyT>
 struct alignas(16) SplitSmem {
@@ -264,7 +265,13 @@ __device__ __forceinline__ void cp_async_key(uint64_t* d, const uint64_t* s) { c
 template <typename KeyT, int T, int E, int CAP, bool STAGED>
 __global__ void __launch_bounds__(T, (E <= 4) ? 2 : 1) k_filter(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* leaf_off,
                                               uint32_t n_leaf, int leaf_bits, uint32_t cap, KeyT* cand_keys, uint32_t* cand_vals,
-                                              unsigned long long* n_cand, uint32_t* n_oversized) {
+                                              unsigned long long* n_cand, uint32_t* n_oversized, uint32_t* unsorted) {
+  // candidates of one leaf are ordered by (key, part) in shared memory before they are written as one contiguous run:
+  // equal keys end up adjacent and in part order WITHOUT a global sort (keys of different leaves differ).
+  __shared__ KeyT c_keys[kLeafSortCap];
+  __shared__ uint32_t c_vals[kLeafSortCap];
+  __shared__ uint32_t s_ccount;
+  __shared__ unsigned long long s_cbase;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KeyT* table = reinterpret_cast<KeyT*>(smem_raw);
   unsigned char* marked = smem_raw + sizeof(KeyT) * (size_t)(2 * T * E);
@@ -315,7 +322,7 @@ __global__ void __launch_bounds__(T, (E <= 4) ? 2 : 1) k_filter(const KeyT* __re
     }
     if (n < 2) continue;
     if (n > cap) {
-      if (threadIdx.x == 0) atomicAdd(n_oversized, 1u);
+      if (threadIdx.x == 0) { atomicAdd(n_oversized, 1u); *unsorted = 1u; }
       for (uint32_t i = threadIdx.x; i < n + 31u - ((n - 1u) & 31u) ; i += T) {   // whole warps iterate together
         bool ok = i < n;
         uint32_t m = __ballot_sync(0xffffffffu, ok);
@@ -335,6 +342,7 @@ __global__ void __launch_bounds__(T, (E <= 4) ? 2 : 1) k_filter(const KeyT* __re
     const uint32_t smask = slots - 1u;
     const int log_slots = 31 - __clz(slots);
     for (uint32_t i = threadIdx.x; i < slots; i += T) { table[i] = kEmpty; marked[i] = 0; }
+    if (threadIdx.x == 0) s_ccount = 0;
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -351,18 +359,50 @@ __global__ void __launch_bounds__(T, (E <= 4) ? 2 : 1) k_filter(const KeyT* __re
       }
     }
     __syncthreads();
+    bool dup[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      bool dup = slot[e] != 0xffffffffu && marked[slot[e]];
-      uint32_t m = __ballot_sync(0xffffffffu, dup);
-      if (m) {
-        unsigned long long basepos = 0;
-        if (lane == 0) basepos = atomicAdd(n_cand, (unsigned long long)__popc(m));
-        basepos = __shfl_sync(0xffffffffu, basepos, 0);
-        if (dup) {
-          unsigned long long dst = basepos + __popc(m & lanemask_lt());
-          cand_keys[dst] = key[e];
-          cand_vals[dst] = val[e];
+      dup[e] = slot[e] != 0xffffffffu && marked[slot[e]];
+      if (dup[e]) {
+        uint32_t pos = atomicAdd(&s_ccount, 1u);
+        if (pos < (uint32_t)kLeafSortCap) { c_keys[pos] = key[e]; c_vals[pos] = val[e]; }
+      }
+    }
+    __syncthreads();
+    const uint32_t c = s_ccount;
+    if (c == 0) continue;
+    if (c <= (uint32_t)kLeafSortCap) {
+      // rank by counting: position of candidate t in (key, part, arrival) order
+      uint32_t rank = 0;
+      KeyT mk = 0; uint32_t mv = 0;
+      if (threadIdx.x < c) {
+        mk = c_keys[threadIdx.x]; mv = c_vals[threadIdx.x];
+        for (uint32_t j = 0; j < c; ++j) {
+          KeyT ok = c_keys[j]; uint32_t ov = c_vals[j];
+          rank += (ok < mk || (ok == mk && (ov < mv || (ov == mv && j < threadIdx.x)))) ? 1u : 0u;
+        }
+      }
+      if (threadIdx.x == 0) s_cbase = atomicAdd(n_cand, (unsigned long long)c);
+      __syncthreads();
+      if (threadIdx.x < c) {
+        cand_keys[s_cbase + rank] = mk;
+        cand_vals[s_cbase + rank] = mv;
+      }
+    } else {
+      // too many candidates for the in-leaf ordering: emit unordered and ask for the global sort
+      if (threadIdx.x == 0) *unsorted = 1u;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        uint32_t m = __ballot_sync(0xffffffffu, dup[e]);
+        if (m) {
+          unsigned long long basepos = 0;
+          if (lane == 0) basepos = atomicAdd(n_cand, (unsigned long long)__popc(m));
+          basepos = __shfl_sync(0xffffffffu, basepos, 0);
+          if (dup[e]) {
+            unsigned long long dst = basepos + __popc(m & lanemask_lt());
+            cand_keys[dst] = key[e];
+            cand_vals[dst] = val[e];
+          }
         }
       }
     }

@@ -186,7 +186,7 @@ __global__ void k_group_first_window(const uint8_t* ascii, const int64_t* off, c
 // last window of each surviving part whose canonical k-mer is not a shared key: the rank of the part's
 // singleton tuple (id,) in the reference's popitem order
 __global__ void k_last_single(const uint8_t* ascii, const int64_t* off, const uint8_t* flags, int64_t lo, int64_t hi, int k,
-                              const uint64_t* shared_keys, int64_t n_shared, int32_t* last_single) {
+                              const uint64_t* shared_table, int log_slots, int32_t* last_single) {
   int64_t p = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= hi) return;
   const int64_t len = off[p + 1] - off[p];
@@ -197,14 +197,7 @@ __global__ void k_last_single(const uint8_t* ascii, const int64_t* off, const ui
       uint64_t fwd = window_from_ascii(seq + j, k);
       uint64_t rc = revcomp2(fwd, k);
       uint64_t canon = fwd < rc ? fwd : rc;
-      int64_t lo = 0, hi = n_shared;                 // binary search in the sorted shared keys
-      bool shared = false;
-      while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        uint64_t v = shared_keys[mid];
-        if (v == canon) { shared = true; break; }
-        if (v < canon) lo = mid + 1; else hi = mid;
-      }
+      const bool shared = log_slots > 0 && bg_contains<uint64_t>(shared_table, log_slots, canon);   // hash set of the shared k-mers
       if (!shared) { result = (int32_t)j; break; }
     }
   }
