@@ -159,7 +159,8 @@ __device__ __forceinline__ bool tile_canonical(const Parts& P, const TileStage& 
 // bookkeeping is 32-bit and tile relative: for uniform-length parts a (quotient, remainder) pair is advanced
 // per position, for variable-length parts the cached offsets slice is walked.  A part is skipped when it is outside
 // the shard [part_lo, part_hi) or -- with SKIP_FLAGGED -- when its flag byte is non-zero; both tests are made
-// once per part, not per window.  f(e, canon, part, is_palindrome) is called for every valid window, e ascending.
+// once per part, not per window.  f(e, canon, part, j, is_palindrome) is called for every valid window (j = index of
+// the window inside its part), e ascending.
 template <bool SKIP_FLAGGED, typename F>
 __device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileStage& s, int64_t tile, int k, const uint8_t* flags, int tid, F f) {
   const int c0 = tid * kTileItems;
@@ -192,7 +193,7 @@ __device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileS
         rc = (rc >> 2) | ((uint64_t)(3u - ((uint32_t)fwd & 3u)) << top);
         if (++r == L) { r = 0; ++part; ok = part_usable(part); }
       }
-      if (ok && r + (uint32_t)k <= L) f(e, fwd < rc ? fwd : rc, (uint32_t)part, fwd == rc);
+      if (ok && r + (uint32_t)k <= L) f(e, fwd < rc ? fwd : rc, (uint32_t)part, r, fwd == rc);
     }
     return;
   }
@@ -203,6 +204,7 @@ __device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileS
   tile_locate(P, s, g_lo + c0, part, end64);
   auto rel_end = [&](int64_t e64) -> int { int64_t d = e64 - g_lo; return d > (1 << 30) ? (1 << 30) : (int)d; };
   int end = rel_end(end64);
+  int start = (int)((s.n_slice > 0 ? s.slice[part - s.first_part] : P.off[part]) - g_lo);   // may be negative
   bool ok = part_usable(part);
   int c = c0;
 #pragma unroll
@@ -216,12 +218,13 @@ __device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileS
       if (c >= end) {
         do {                                                   // next non-empty part
           ++part;
+          start = end;
           end = rel_end(s.n_slice > 0 ? s.slice[part - s.first_part + 1] : P.off[part + 1]);
         } while (c >= end);
         ok = part_usable(part);
       }
     }
-    if (ok && c + k <= end) f(e, fwd < rc ? fwd : rc, (uint32_t)part, fwd == rc);
+    if (ok && c + k <= end) f(e, fwd < rc ? fwd : rc, (uint32_t)part, (uint32_t)(c - start), fwd == rc);
   }
 }
 

@@ -103,6 +103,7 @@ struct nrp_ctx {
   int64_t opt_leaf_target = 2750;
   int64_t opt_max_level_bits = kMaxLevelBits;
   int64_t opt_max_pairs = (int64_t)1 << 31;
+  int64_t opt_no_window_carry = 0;
 
   // background
   DevBuf bg_table; int bg_K = 0; int bg_log_slots = 0; int bg_key_bytes = 0; int64_t bg_n = 0;
@@ -110,7 +111,7 @@ struct nrp_ctx {
   // loaded parts
   DevBuf ascii, off, part_id, tile_first;
   std::vector<int64_t> h_off;
-  int64_t n_parts = 0, total_len = 0, n_tiles = 0;
+  int64_t n_parts = 0, total_len = 0, n_tiles = 0, max_len = 0;
   int uniform_len = 0;
   bool have_parts = false, have_ids = false;
   uint32_t part_base = 0;
@@ -127,6 +128,7 @@ struct nrp_ctx {
   // shard window (whole batch unless nrp_shard_extract narrowed it)
   int64_t shard_lo = 0, shard_hi = 0, shard_tile_lo = 0, shard_tiles = 0, shard_m_max = 0;
   int n_owners = 0;
+  int j_bits = 0;                // > 0: record values are (part << j_bits) | window
   bool external_stream = false;
 
   // candidate records between the stages (type-erased: uint32_t* or uint64_t* keys)
@@ -276,6 +278,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "leaf_target") c->opt_leaf_target = value <= 0 ? 2750 : value;
   else if (n == "max_level_bits") c->opt_max_level_bits = (value <= 0 || value > kMaxLevelBits) ? kMaxLevelBits : value;
   else if (n == "max_pairs") c->opt_max_pairs = value <= 0 ? ((int64_t)1 << 31) : value;
+  else if (n == "no_window_carry") c->opt_no_window_carry = value > 0 ? 1 : 0;
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
   return NRP_OK;
 }
@@ -320,14 +323,16 @@ int nrp_load_parts(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, con
   if (offsets[0] != 0) return fail(NRP_E_ARG, "offsets[0] must be 0");
   const int64_t total = offsets[n_parts];
   int uniform = n_parts > 0 ? (int)std::min<int64_t>(offsets[1] - offsets[0], (int64_t)1 << 30) : 0;
+  int64_t max_len = 0;
   for (int64_t i = 0; i < n_parts; ++i) {
     int64_t len = offsets[i + 1] - offsets[i];
     if (len < 0) return fail(NRP_E_ARG, "offsets must be non-decreasing (part %lld)", (long long)i);
     if (len != uniform) uniform = 0;
+    if (len > max_len) max_len = len;
   }
   if (uniform >= (1 << 30)) uniform = 0;
   c->h_off.assign(offsets, offsets + n_parts + 1);
-  c->n_parts = n_parts; c->total_len = total; c->uniform_len = uniform;
+  c->n_parts = n_parts; c->total_len = total; c->uniform_len = uniform; c->max_len = max_len;
   c->n_tiles = (total + kTileBytes - 1) / kTileBytes;
   const size_t padded = (size_t)c->n_tiles * kTileBytes + 256;
   TRY(c->ascii.ensure(padded));
@@ -446,7 +451,7 @@ int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, 
   if (m_max > 0) {
     if (from_ascii) {
       NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-          P, c->flags.as<uint8_t>(), k, r1, 0, c->part_base, level1_cursor, leaf_keys, leaf_vals)));
+          P, c->flags.as<uint8_t>(), k, r1, 0, c->part_base, c->j_bits, level1_cursor, leaf_keys, leaf_vals)));
     } else {
       // one segment holding all records; level-1 digit = top r1 bits
       const uint32_t seg[2] = {0u, (uint32_t)n_in};
@@ -472,7 +477,7 @@ int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, 
     // leaves that average <= 2750 records use the half-size table (two CTAs per SM); larger ones the full table
     const bool small = (m_max >> bits) <= 2750;
     const size_t fsm = small ? filter_smem_small<KeyT>() : filter_smem_large<KeyT>();
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (224 * 1024) / (fsm + 1024)));
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / (fsm + 18 * 1024)));   // + static smem of the leaf ordering
     const unsigned fgrid = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * per_sm);
     const uint32_t cap = (uint32_t)std::min<int64_t>(c->opt_filter_cap, small ? kFilterCapSmall : kFilterCap);
     if (small)
@@ -520,7 +525,7 @@ int stage_sort_mark(nrp_ctx* c, int k, int64_t n_parts_total, bool mark_repeats,
   if (c->cand_unsorted) {
     // rare: a leaf bucket over the filter capacity or with > kLeafSortCap candidates (heavy duplicate keys)
     TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n)));
-    LsdPlan plan = lsd_plan(2 * k, part_bits);
+    LsdPlan plan = lsd_plan(2 * k, part_bits + c->j_bits);
     KeyT* sk; uint32_t* sv;
     lsd_sort<KeyT, true>((KeyT*)c->cand_keys, c->cand_vals, (KeyT*)c->spare_keys, c->spare_vals, n, plan, c->lsd_scratch.as<uint32_t>(), st, &sk, &sv);
     if (sk != (KeyT*)c->cand_keys) { std::swap(c->cand_keys, c->spare_keys); std::swap(c->cand_vals, c->spare_vals); }
@@ -532,7 +537,7 @@ int stage_sort_mark(nrp_ctx* c, int k, int64_t n_parts_total, bool mark_repeats,
   c->n_sorted = n;
   c->n_repeat_records = 0;
   if (n > 0) {
-    NRP_LAUNCH((k_group_heads<KeyT><<<grid_for(n, 256), 256, 0, st>>>((KeyT*)c->cand_keys, c->cand_vals, n, c->head.as<uint32_t>(),
+    NRP_LAUNCH((k_group_heads<KeyT><<<grid_for(n, 256), 256, 0, st>>>((KeyT*)c->cand_keys, c->cand_vals, n, c->j_bits, c->head.as<uint32_t>(),
                                                                   mark_repeats ? c->flags.as<uint8_t>() : nullptr, cnt + CNT_REPEAT)));
     CU(cudaMemcpyAsync(c->h_counters + 18, cnt + CNT_REPEAT, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -550,7 +555,7 @@ int stage_compact(nrp_ctx* c, StageTimer& tm) {
   const int64_t n = c->n_sorted;
   if (n == 0) return NRP_OK;
   unsigned long long* cnt = c->counters.as<unsigned long long>();
-  NRP_LAUNCH((k_keep_unflagged<<<grid_for(n, 256), 256, 0, st>>>(c->cand_vals, n, c->flags.as<uint8_t>(), c->valid.as<uint32_t>())));
+  NRP_LAUNCH((k_keep_unflagged<<<grid_for(n, 256), 256, 0, st>>>(c->cand_vals, n, c->j_bits, c->flags.as<uint8_t>(), c->valid.as<uint32_t>())));
   exclusive_scan<uint32_t, uint32_t>(c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), n, c->scan_scratch.as<uint32_t>(), st);
   NRP_LAUNCH((k_compact_records<KeyT><<<grid_for(n, 256), 256, 0, st>>>((KeyT*)c->cand_keys, c->cand_vals, c->valid.as<uint32_t>(),
                                                                     c->valid_scan.as<uint32_t>(), n, (KeyT*)c->spare_keys, c->spare_vals)));
@@ -559,7 +564,7 @@ int stage_compact(nrp_ctx* c, StageTimer& tm) {
   c->n_sorted = (int64_t)(uint32_t)c->h_counters[19];
   std::swap(c->cand_keys, c->spare_keys); std::swap(c->cand_vals, c->spare_vals);
   if (c->n_sorted > 0)
-    NRP_LAUNCH((k_group_heads<KeyT><<<grid_for(c->n_sorted, 256), 256, 0, st>>>((KeyT*)c->cand_keys, c->cand_vals, c->n_sorted,
+    NRP_LAUNCH((k_group_heads<KeyT><<<grid_for(c->n_sorted, 256), 256, 0, st>>>((KeyT*)c->cand_keys, c->cand_vals, c->n_sorted, c->j_bits,
                                                                            c->head.as<uint32_t>(), nullptr, cnt + CNT_WORK)));
   CU(cudaGetLastError());
   return NRP_OK;
@@ -595,13 +600,14 @@ int stage_groups(nrp_ctx* c, StageTimer& tm) {
     c->n_pairs = (int64_t)c->h_counters[22];
     TRY(c->g_keys.ensure(8 * (size_t)(c->n_groups + 1))); TRY(c->g_indptr.ensure(8 * (size_t)(c->n_groups + 2)));
     TRY(c->g_pair_off.ensure(8 * (size_t)(c->n_groups + 2))); TRY(c->g_members.ensure(4 * (size_t)(c->n_members + 1)));
+    TRY(c->g_first_window.ensure(4 * (size_t)(c->n_groups + 1)));
     NRP_LAUNCH((k_group_emit<KeyT><<<grid_for(n_runs + 1, 256), 256, 0, st>>>(
-        (KeyT*)c->cand_keys, c->group_start.as<uint32_t>(), c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(),
+        (KeyT*)c->cand_keys, c->cand_vals, c->j_bits, c->group_start.as<uint32_t>(), c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(),
         c->mem_scan.as<unsigned long long>(), c->pair_scan.as<unsigned long long>(), n_runs, c->g_keys.as<uint64_t>(),
-        c->g_indptr.as<int64_t>(), c->g_pair_off.as<unsigned long long>())));
+        c->g_indptr.as<int64_t>(), c->g_pair_off.as<unsigned long long>(), c->g_first_window.as<uint32_t>())));
     NRP_LAUNCH((k_group_members<<<grid_for(n, 256), 256, 0, st>>>(c->cand_vals, c->head_scan.as<uint32_t>(), c->head.as<uint32_t>(),
                                                               c->group_start.as<uint32_t>(), c->valid.as<uint32_t>(),
-                                                              c->mem_scan.as<unsigned long long>(), n, c->g_members.as<uint32_t>())));
+                                                              c->mem_scan.as<unsigned long long>(), n, c->j_bits, c->g_members.as<uint32_t>())));
     CU(cudaGetLastError());
   } else {
     TRY(c->g_keys.ensure(8)); TRY(c->g_indptr.ensure(16)); TRY(c->g_pair_off.ensure(16)); TRY(c->g_members.ensure(4));
@@ -619,7 +625,7 @@ int stage_first_window(nrp_ctx* c, int k, StageTimer& tm) {
   cudaStream_t st = c->stream;
   tm.begin(NRP_T_ORDER);
   TRY(c->g_first_part.ensure(4 * (size_t)(c->n_groups + 1))); TRY(c->g_first_window.ensure(4 * (size_t)(c->n_groups + 1)));
-  if (c->n_groups > 0) {
+  if (c->n_groups > 0 && c->j_bits == 0) {
     NRP_LAUNCH((k_gather_first_part<<<grid_for(c->n_groups, 256), 256, 0, st>>>(c->g_indptr.as<int64_t>(), c->g_members.as<uint32_t>(),
                                                                             c->n_groups, c->g_first_part.as<uint32_t>())));
     NRP_LAUNCH((k_group_first_window<<<grid_for(c->n_groups, 128), 128, 0, st>>>(c->ascii.as<uint8_t>(), c->off.as<int64_t>(),
@@ -731,6 +737,13 @@ void begin_job(nrp_ctx* c, int k, size_t key_bytes, int want_edges) {
   c->counts[NRP_C_RUNS] = 1;
   c->k = k; c->key_bytes = (int)key_bytes;
   c->have_result = false;
+  // carry the window index in the record value when (part, window) fits 32 bits
+  int part_bits = 1, win_bits = 1;
+  while (((int64_t)1 << part_bits) < c->n_parts) ++part_bits;
+  const int64_t max_windows = c->max_len - k + 1;
+  while (((int64_t)1 << win_bits) < max_windows) ++win_bits;
+  c->j_bits = (max_windows >= 1 && part_bits + win_bits <= 32) ? win_bits : 0;
+  if (c->opt_no_window_carry) c->j_bits = 0;
 }
 
 template <typename KeyT>
@@ -784,7 +797,7 @@ int shard_extract_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int internal_r
   tm.begin(NRP_T_SPLIT1);
   if (c->shard_m_max > 0)
     NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, 8, n_owners, 0u, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>())));
+        P, c->flags.as<uint8_t>(), k, 8, n_owners, 0u, c->j_bits, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>())));
   CU(cudaGetLastError());
   tm.finish(c->timings);
   CU(cudaStreamSynchronize(st));

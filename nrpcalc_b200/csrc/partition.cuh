@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kTileThreads * HALVES) k_hist_from_ascii(Parts
     if (t < n_tiles) tile_load(P, tile, stage, tid);
     __syncthreads();
     if (t < n_tiles)
-      tile_windows_blocked<true>(P, stage, tile, k, flags, tid, [&](int, uint64_t canon, uint32_t, bool) {
+      tile_windows_blocked<true>(P, stage, tile, k, flags, tid, [&](int, uint64_t canon, uint32_t, uint32_t, bool) {
         uint32_t bin = n_owners > 0 ? owner_hash(canon) % (uint32_t)n_owners : (uint32_t)(key_hash(canon) >> (64 - bits));
         atomicAdd(&s_hist[bin], 1u);
       });
@@ -146,9 +146,11 @@ __global__ void __launch_bounds__(512) k_hist_from_records(const KeyT* keys, int
 // ---- level 1: extraction fused with the first split ------------------------------------------------------
 // digit = top r1 bits of the hash (or, with by_owner, owner_hash % n_owners for the sharded path).
 // cursor[d] must hold the start offset of bucket d and is advanced atomically.
+// Record value = part index, or (part << j_bits) | window index when both fit 32 bits (j_bits > 0): sorting by value
+// is then sorting by (part, window), and a group's first record carries the group's rank for free.
 template <typename KeyT>
 __global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, const uint8_t* flags, int k, int r1, int n_owners,
-                                                                  uint32_t part_base, uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals) {
+                                                                  uint32_t part_base, int j_bits, uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SplitSmem<KeyT>& s = *reinterpret_cast<SplitSmem<KeyT>*>(smem_raw);
   TileStage& stage = *reinterpret_cast<TileStage*>(smem_raw + sizeof(SplitSmem<KeyT>));
@@ -161,12 +163,12 @@ __global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, cons
   uint32_t val[kSplitItems], dr[kSplitItems];
 #pragma unroll
   for (int e = 0; e < kSplitItems; ++e) { dr[e] = 0xffffffffu; key[e] = 0; val[e] = 0; }
-  tile_windows_blocked<true>(P, stage, tile, k, flags, threadIdx.x, [&](int e, uint64_t canon, uint32_t part, bool) {
+  tile_windows_blocked<true>(P, stage, tile, k, flags, threadIdx.x, [&](int e, uint64_t canon, uint32_t part, uint32_t j, bool) {
     uint32_t d = n_owners > 0 ? owner_hash(canon) % (uint32_t)n_owners : (uint32_t)(key_hash(canon) >> (64 - r1));
     uint32_t rank = atomicAdd(&s.cnt[d], 1u);
 #pragma unroll
     for (int q = 0; q < kSplitItems; ++q)
-      if (q == e) { key[q] = (KeyT)canon; val[q] = part_base + part; dr[q] = (d << 16) | rank; }
+      if (q == e) { key[q] = (KeyT)canon; val[q] = ((part_base + part) << j_bits) | (j_bits ? j : 0u); dr[q] = (d << 16) | rank; }
   });
   __syncthreads();
   if (n_owners > 0)
@@ -270,6 +272,7 @@ __global__ void __launch_bounds__(T, (E <= 4) ? 2 : 1) k_filter(const KeyT* __re
   // equal keys end up adjacent and in part order WITHOUT a global sort (keys of different leaves differ).
   __shared__ KeyT c_keys[kLeafSortCap];
   __shared__ uint32_t c_vals[kLeafSortCap];
+  __shared__ uint32_t c_rank[kLeafSortCap];
   __shared__ uint32_t s_ccount;
   __shared__ unsigned long long s_cbase;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -279,6 +282,7 @@ __global__ void __launch_bounds__(T, (E <= 4) ? 2 : 1) k_filter(const KeyT* __re
   uint32_t* st_vals = reinterpret_cast<uint32_t*>(st_keys + (STAGED ? CAP : 0));
   const KeyT kEmpty = ~KeyT(0);
   const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kLeafSortCap; i += T) c_rank[i] = 0;
   uint32_t next_lo = 0, next_n = 0;
   auto stage_next = [&](uint32_t lf) {            // start the asynchronous copy of leaf lf into the staging area
     next_n = 0;
@@ -372,21 +376,27 @@ __global__ void __launch_bounds__(T, (E <= 4) ? 2 : 1) k_filter(const KeyT* __re
     const uint32_t c = s_ccount;
     if (c == 0) continue;
     if (c <= (uint32_t)kLeafSortCap) {
-      // rank by counting: position of candidate t in (key, part, arrival) order
-      uint32_t rank = 0;
-      KeyT mk = 0; uint32_t mv = 0;
-      if (threadIdx.x < c) {
-        mk = c_keys[threadIdx.x]; mv = c_vals[threadIdx.x];
-        for (uint32_t j = 0; j < c; ++j) {
+      // rank by counting: position of candidate i in (key, part, arrival) order.  T / c threads share one candidate
+      // (each scans a strided part of the list), so the loop stays short when many records of a leaf are shared.
+      const uint32_t share = T / c;                           // >= 1 because c <= kLeafSortCap <= T
+      const uint32_t cand = threadIdx.x % c, seg = threadIdx.x / c;
+      if (seg < share) {
+        const KeyT mk = c_keys[cand];
+        const uint32_t mv = c_vals[cand];
+        uint32_t partial = 0;
+        for (uint32_t j = seg; j < c; j += share) {
           KeyT ok = c_keys[j]; uint32_t ov = c_vals[j];
-          rank += (ok < mk || (ok == mk && (ov < mv || (ov == mv && j < threadIdx.x)))) ? 1u : 0u;
+          partial += (ok < mk || (ok == mk && (ov < mv || (ov == mv && j < cand)))) ? 1u : 0u;
         }
+        if (partial) atomicAdd(&c_rank[cand], partial);
       }
       if (threadIdx.x == 0) s_cbase = atomicAdd(n_cand, (unsigned long long)c);
       __syncthreads();
       if (threadIdx.x < c) {
-        cand_keys[s_cbase + rank] = mk;
-        cand_vals[s_cbase + rank] = mv;
+        const uint32_t rank = c_rank[threadIdx.x];
+        cand_keys[s_cbase + rank] = c_keys[threadIdx.x];
+        cand_vals[s_cbase + rank] = c_vals[threadIdx.x];
+        c_rank[threadIdx.x] = 0;                              // ready for the next leaf (ordered by the loop-top barrier)
       }
     } else {
       // too many candidates for the in-leaf ordering: emit unordered and ask for the global sort

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kTileThreads) k_flag_windows(Parts P, int klen
   const int64_t tile = P.tile_lo + blockIdx.x;
   tile_load(P, tile, stage, threadIdx.x);
   __syncthreads();
-  tile_windows_blocked<false>(P, stage, tile, klen, flags, threadIdx.x, [&](int, uint64_t canon, uint32_t part, bool palindrome) {
+  tile_windows_blocked<false>(P, stage, tile, klen, flags, threadIdx.x, [&](int, uint64_t canon, uint32_t part, uint32_t, bool palindrome) {
     if (mode == 0) {
       if (palindrome) flags[part] |= kFlagPalindrome;             // benign race: all writers OR the same bit
     } else {
@@ -59,14 +59,14 @@ __global__ void __launch_bounds__(kTileThreads) k_flag_windows(Parts P, int klen
 // records sorted by (key, part).  head[i] = 1 where a new key starts.  Two equal adjacent records (same key,
 // same part) mean that the part has an internal repeat (reference hgraph.py:53-69).
 template <typename KeyT>
-__global__ void k_group_heads(const KeyT* keys, const uint32_t* vals, int64_t n, uint32_t* head, uint8_t* flags,
+__global__ void k_group_heads(const KeyT* keys, const uint32_t* vals, int64_t n, int j_bits, uint32_t* head, uint8_t* flags,
                               unsigned long long* n_repeat_records) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   bool is_head = i == 0 || keys[i] != keys[i - 1];
   head[i] = is_head ? 1u : 0u;
-  if (!is_head && vals[i] == vals[i - 1]) {
-    if (flags) flags[vals[i]] |= kFlagRepeat;
+  if (!is_head && (vals[i] >> j_bits) == (vals[i - 1] >> j_bits)) {
+    if (flags) flags[vals[i] >> j_bits] |= kFlagRepeat;
     atomicAdd(n_repeat_records, 1ull);
   }
 }
@@ -74,9 +74,9 @@ __global__ void k_group_heads(const KeyT* keys, const uint32_t* vals, int64_t n,
 // records of parts flagged for an internal repeat must vanish from every group (the reference drops such a part
 // before it touches the table, hgraph.py:50-69): keep[i] = 1 unless the record's part carries the repeat flag.
 // flags_global is indexed by the record value itself (global part index).
-__global__ void k_keep_unflagged(const uint32_t* vals, int64_t n, const uint8_t* flags_by_val, uint32_t* keep) {
+__global__ void k_keep_unflagged(const uint32_t* vals, int64_t n, int j_bits, const uint8_t* flags_by_val, uint32_t* keep) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) keep[i] = (flags_by_val[vals[i]] & kFlagRepeat) ? 0u : 1u;
+  if (i < n) keep[i] = (flags_by_val[vals[i] >> j_bits] & kFlagRepeat) ? 0u : 1u;
 }
 
 template <typename KeyT>
@@ -118,9 +118,10 @@ __global__ void k_group_sizes(const uint32_t* group_start, int64_t n_runs, uint3
 
 // compact the real groups: keys, CSR indptr (64-bit), pair offsets, and the members
 template <typename KeyT>
-__global__ void k_group_emit(const KeyT* keys, const uint32_t* group_start, const uint32_t* valid, const uint32_t* valid_scan,
-                             const unsigned long long* member_scan, const unsigned long long* pair_scan, int64_t n_runs,
-                             uint64_t* out_keys, int64_t* out_indptr, unsigned long long* out_pair_off) {
+__global__ void k_group_emit(const KeyT* keys, const uint32_t* vals, int j_bits, const uint32_t* group_start, const uint32_t* valid,
+                             const uint32_t* valid_scan, const unsigned long long* member_scan, const unsigned long long* pair_scan,
+                             int64_t n_runs, uint64_t* out_keys, int64_t* out_indptr, unsigned long long* out_pair_off,
+                             uint32_t* out_first_window) {
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g > n_runs) return;
   if (g == n_runs) {
@@ -132,17 +133,18 @@ __global__ void k_group_emit(const KeyT* keys, const uint32_t* group_start, cons
   if (!valid[g]) return;
   uint32_t o = valid_scan[g];
   out_keys[o] = (uint64_t)keys[group_start[g]];
+  if (j_bits) out_first_window[o] = vals[group_start[g]] & ((1u << j_bits) - 1u);     // the first record is (first part, first window)
   out_indptr[o] = (int64_t)member_scan[g];
   out_pair_off[o] = pair_scan[g];
 }
 
 __global__ void k_group_members(const uint32_t* vals, const uint32_t* head_scan, const uint32_t* head, const uint32_t* group_start,
-                                const uint32_t* valid, const unsigned long long* member_scan, int64_t n, uint32_t* out_members) {
+                                const uint32_t* valid, const unsigned long long* member_scan, int64_t n, int j_bits, uint32_t* out_members) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t g = head_scan[i] + head[i] - 1u;           // run index of record i (inclusive scan - 1)
   if (!valid[g]) return;
-  out_members[member_scan[g] + (i - group_start[g])] = vals[i];
+  out_members[member_scan[g] + (i - group_start[g])] = vals[i] >> j_bits;
 }
 
 // ---- order information for the host replay ----------------------------------------------------

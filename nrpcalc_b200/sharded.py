@@ -18,9 +18,15 @@ computed by the owner of a group without another exchange).
 `ops` is the per-rank device back end: NativeOps drives libnrpb200.so; the CPU tests plug in a numpy model of the
 same five calls to exercise the sharding / exchange / merge logic under gloo.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+# the record exchange is point-to-point traffic: let NCCL use many channels per peer (NVSwitch gives every pair full bandwidth)
+os.environ.setdefault('NCCL_MIN_P2P_NCHANNELS', '32')
+os.environ.setdefault('NCCL_MAX_P2P_NCHANNELS', '64')
 
 
 def shard_bounds(lengths, k, world):
