@@ -108,7 +108,7 @@ int nrp_load_parts(nrp_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, c
 
 /* Build the repeat structure of the staged parts.
  *   internal_repeats 0: exclude parts with internal direct/inverted repeats or palindromic windows
- *   want_edges       != 0: also expand groups into unique (id_u < id_v) edges, sorted lexicographically
+ *   want_edges       != 0: also expand groups into the distinct (id_u < id_v) edges
  * Synchronous: returns when the results are resident on the device.  May be called repeatedly. */
 int nrp_build(nrp_ctx* ctx, int k, int internal_repeats, int want_edges);
 
@@ -124,7 +124,7 @@ int nrp_result_groups(nrp_ctx* ctx, int64_t* indptr, uint32_t* members, uint32_t
 /* last_single[n_parts]: largest window index whose canonical k-mer no other record shares, -1 if none
  * (and -1 for excluded parts) */
 int nrp_result_last_single(nrp_ctx* ctx, int32_t* last_single);
-/* u[n_edges] < v[n_edges], unique, sorted by (u, v) */
+/* u[n_edges] < v[n_edges], every conflicting id pair exactly once, order unspecified */
 int nrp_result_edges(nrp_ctx* ctx, uint32_t* u, uint32_t* v);
 
 /* ---- sharded path: one process per GPU, k-mer space hash-partitioned across n_owners ranks ---------------------
@@ -156,7 +156,7 @@ int nrp_shard_finish(nrp_ctx* ctx, int k, int internal_repeats, int want_edges);
 /* shared_keys: canonical k-mers of ALL ranks' groups, any order (host memory, or device memory when keys_on_device != 0);
  * afterwards nrp_result_last_single holds valid entries for the parts of this rank's shard */
 int nrp_shard_last_single(nrp_ctx* ctx, const uint64_t* shared_keys, int64_t n_shared, int k, int keys_on_device);
-/* replace this context's edge list by the sorted, distinct union of n gathered (u < v) edges in device memory */
+/* replace this context's edge list by the distinct union of n gathered (u < v) edges in device memory */
 int nrp_edges_merge(nrp_ctx* ctx, const uint32_t* u_dev, const uint32_t* v_dev, int64_t n);
 /* device pointer + element count of a result array, for zero-copy use by the host layer's collectives */
 #define NRP_D_GROUP_KEYS   0   /* uint64 */

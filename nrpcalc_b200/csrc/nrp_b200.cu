@@ -74,7 +74,7 @@ struct DevBuf {
   template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
 };
 
-enum { CNT_CAND = 0, CNT_REPEAT = 1, CNT_FLAGGED = 2, CNT_WORK = 3, CNT_OVERSIZED = 4, CNT_UNSORTED = 5, CNT_N = 8 };
+enum { CNT_CAND = 0, CNT_REPEAT = 1, CNT_FLAGGED = 2, CNT_WORK = 3, CNT_OVERSIZED = 4, CNT_UNSORTED = 5, CNT_N = 8, CNT_EDGES = 8, CNT_TOTAL = 12 };
 
 constexpr int kFilterThreads = 1024;
 constexpr int kFilterItems = 8;
@@ -122,7 +122,7 @@ struct nrp_ctx {
   DevBuf keysA, valsA, keysB, valsB;
   DevBuf head, head_scan, group_start, valid, valid_scan, mem_cnt, mem_scan, pair_cnt, pair_scan;
   DevBuf g_keys, g_indptr, g_pair_off, g_members, g_first_part, g_first_window, last_single;
-  DevBuf e_codesA, e_codesB, e_head, e_head_scan, e_u, e_v, shared_keysA, shared_keysB;
+  DevBuf e_codesA, e_codesB, e_head, e_head_scan, e_u, e_v, e_u_alt, e_v_alt, shared_keysA, shared_keysB;
   unsigned long long* h_counters = nullptr;   // pinned
 
   // shard window (whole batch unless nrp_shard_extract narrowed it)
@@ -245,7 +245,7 @@ int nrp_ctx_create(int device, nrp_ctx** out) {
   c->n_sms = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaHostAlloc(&c->h_counters, sizeof(unsigned long long) * 64, cudaHostAllocDefault));
-  int r = c->counters.ensure(sizeof(unsigned long long) * CNT_N);
+  int r = c->counters.ensure(sizeof(unsigned long long) * CNT_TOTAL);
   if (r != NRP_OK) return r;
   *out = c;
   return NRP_OK;
@@ -260,7 +260,7 @@ int nrp_ctx_destroy(nrp_ctx* c) {
                    &c->keysB, &c->valsB, &c->head, &c->head_scan, &c->group_start, &c->valid, &c->valid_scan, &c->mem_cnt,
                    &c->mem_scan, &c->pair_cnt, &c->pair_scan, &c->g_keys, &c->g_indptr, &c->g_pair_off, &c->g_members,
                    &c->g_first_part, &c->g_first_window, &c->last_single, &c->e_codesA, &c->e_codesB, &c->e_head, &c->e_head_scan,
-                   &c->e_u, &c->e_v, &c->shared_keysA, &c->shared_keysB};
+                   &c->e_u, &c->e_v, &c->e_u_alt, &c->e_v_alt, &c->shared_keysA, &c->shared_keysB};
   for (DevBuf* b : all) b->release();
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -657,50 +657,43 @@ int stage_last_single(nrp_ctx* c, int k, const uint64_t* shared_keys, int64_t n_
   return NRP_OK;
 }
 
-// sort the n codes in e_codesA (alternate e_codesB) and compact the distinct valid ones into e_u / e_v
-int unique_edge_codes(nrp_ctx* c, int64_t n, int64_t* n_edges) {
-  cudaStream_t st = c->stream;
-  TRY(c->e_head.ensure(4 * (size_t)(n + 2))); TRY(c->e_head_scan.ensure(4 * (size_t)(n + 2)));
-  TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n)));
-  TRY(c->scan_scratch.ensure(8 * (size_t)scan_scratch_elems(n + 2)));
-  // ids are < 2^id_bits; the all-ones code of self pairs sorts last because 2^id_bits - 1 is never an id
-  int id_bits = 1;
-  while (id_bits < 32 && ((int64_t)1 << id_bits) <= c->max_id) ++id_bits;
-  LsdPlan plan; plan.n_passes = 0;
-  lsd_plan_add(plan, 0, 0, id_bits);
-  lsd_plan_add(plan, 0, 32, 32 + id_bits);
-  uint64_t* sorted_codes;
-  lsd_sort<uint64_t, false>(c->e_codesA.as<uint64_t>(), nullptr, c->e_codesB.as<uint64_t>(), nullptr, n, plan,
-                            c->lsd_scratch.as<uint32_t>(), st, &sorted_codes, nullptr);
-  NRP_LAUNCH((k_edge_heads<<<grid_for(n, 256), 256, 0, st>>>(sorted_codes, n, c->e_head.as<uint32_t>())));
-  exclusive_scan<uint32_t, uint32_t>(c->e_head.as<uint32_t>(), c->e_head_scan.as<uint32_t>(), n, c->scan_scratch.as<uint32_t>(), st);
-  CU(cudaMemcpyAsync(c->h_counters + 24, c->e_head_scan.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  *n_edges = (int64_t)(uint32_t)c->h_counters[24];
-  TRY(c->e_u.ensure(4 * (size_t)(*n_edges + 1))); TRY(c->e_v.ensure(4 * (size_t)(*n_edges + 1)));
-  NRP_LAUNCH((k_edge_compact<<<grid_for(n, 256), 256, 0, st>>>(sorted_codes, c->e_head.as<uint32_t>(), c->e_head_scan.as<uint32_t>(), n,
-                                                           c->e_u.as<uint32_t>(), c->e_v.as<uint32_t>())));
-  CU(cudaGetLastError());
+// hash set for at most n_codes edge codes in e_codesA, cleared; output lists e_u / e_v sized for n_codes
+int edge_set_prepare(nrp_ctx* c, int64_t n_codes, int* log_slots) {
+  int ls = 6;
+  while (((int64_t)1 << ls) < 2 * n_codes) ++ls;
+  TRY(c->e_codesA.ensure((size_t)8 << ls));
+  TRY(c->e_u.ensure(4 * (size_t)(n_codes + 1))); TRY(c->e_v.ensure(4 * (size_t)(n_codes + 1)));
+  CU(cudaMemsetAsync(c->e_codesA.ptr, 0xff, (size_t)8 << ls, c->stream));
+  CU(cudaMemsetAsync(c->counters.as<unsigned long long>() + CNT_EDGES, 0, 8, c->stream));
+  *log_slots = ls;
   return NRP_OK;
 }
 
-// ---- stage: unique part-pair edges of this context's groups
+int edge_set_count(nrp_ctx* c) {
+  CU(cudaMemcpyAsync(c->h_counters + 24, c->counters.as<unsigned long long>() + CNT_EDGES, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->counts[NRP_C_EDGES] = (int64_t)c->h_counters[24];
+  return NRP_OK;
+}
+
+// ---- stage: distinct part-pair edges of this context's groups (order unspecified)
 int stage_edges(nrp_ctx* c, StageTimer& tm) {
   cudaStream_t st = c->stream;
   tm.begin(NRP_T_EDGES);
   if (!c->have_ids) return fail(NRP_E_ARG, "want_edges needs part ids");
   if (c->n_pairs > c->opt_max_pairs)
     return fail(NRP_E_EDGES, "%lld member pairs exceed the limit of %lld", (long long)c->n_pairs, (long long)c->opt_max_pairs);
-  int64_t n_edges = 0;
-  const int64_t n_pairs = c->n_pairs;
-  if (n_pairs > 0) {
-    TRY(c->e_codesA.ensure(8 * (size_t)(n_pairs + 1))); TRY(c->e_codesB.ensure(8 * (size_t)(n_pairs + 1)));
-    NRP_LAUNCH((k_edge_pairs<<<grid_for(c->n_members, 128), 128, 0, st>>>(c->g_indptr.as<int64_t>(), c->g_members.as<uint32_t>(),
-                                                                      c->g_pair_off.as<unsigned long long>(), c->n_groups, c->n_members,
-                                                                      c->part_id.as<uint32_t>(), c->e_codesA.as<uint64_t>())));
-    TRY(unique_edge_codes(c, n_pairs, &n_edges));
+  c->counts[NRP_C_EDGES] = 0;
+  if (c->n_pairs > 0) {
+    int log_slots = 0;
+    TRY(edge_set_prepare(c, c->n_pairs, &log_slots));
+    NRP_LAUNCH((k_edge_pairs<<<grid_for(c->n_members, 128), 128, 0, st>>>(c->g_indptr.as<int64_t>(), c->g_members.as<uint32_t>(), c->n_groups,
+                                                                      c->n_members, c->part_id.as<uint32_t>(), c->e_codesA.as<uint64_t>(),
+                                                                      log_slots, c->e_u.as<uint32_t>(), c->e_v.as<uint32_t>(),
+                                                                      c->counters.as<unsigned long long>() + CNT_EDGES)));
+    CU(cudaGetLastError());
+    TRY(edge_set_count(c));
   }
-  c->counts[NRP_C_EDGES] = n_edges;
   return NRP_OK;
 }
 
@@ -921,13 +914,22 @@ int nrp_edges_merge(nrp_ctx* c, const uint32_t* u_dev, const uint32_t* v_dev, in
   if (!c) return fail(NRP_E_ARG, "null context");
   if (n < 0 || (n > 0 && (!u_dev || !v_dev))) return fail(NRP_E_ARG, "bad edge arrays");
   CU(cudaSetDevice(c->device));
-  int64_t n_edges = 0;
+  c->counts[NRP_C_EDGES] = 0;
   if (n > 0) {
-    TRY(c->e_codesA.ensure(8 * (size_t)(n + 1))); TRY(c->e_codesB.ensure(8 * (size_t)(n + 1)));
-    NRP_LAUNCH((k_edge_codes<<<grid_for(n, 256), 256, 0, c->stream>>>(u_dev, v_dev, n, c->e_codesA.as<uint64_t>())));
-    TRY(unique_edge_codes(c, n, &n_edges));
+    // the inputs may alias e_u / e_v of this context (zero-copy views): gather into fresh lists
+    DevBuf& new_u = c->e_u_alt; DevBuf& new_v = c->e_v_alt;
+    TRY(new_u.ensure(4 * (size_t)(n + 1))); TRY(new_v.ensure(4 * (size_t)(n + 1)));
+    int log_slots = 6;
+    while (((int64_t)1 << log_slots) < 2 * n) ++log_slots;
+    TRY(c->e_codesA.ensure((size_t)8 << log_slots));
+    CU(cudaMemsetAsync(c->e_codesA.ptr, 0xff, (size_t)8 << log_slots, c->stream));
+    CU(cudaMemsetAsync(c->counters.as<unsigned long long>() + CNT_EDGES, 0, 8, c->stream));
+    NRP_LAUNCH((k_edge_merge<<<grid_for(n, 256), 256, 0, c->stream>>>(u_dev, v_dev, n, c->e_codesA.as<uint64_t>(), log_slots, new_u.as<uint32_t>(),
+                                                                  new_v.as<uint32_t>(), c->counters.as<unsigned long long>() + CNT_EDGES)));
+    CU(cudaGetLastError());
+    TRY(edge_set_count(c));
+    std::swap(c->e_u, c->e_u_alt); std::swap(c->e_v, c->e_v_alt);
   }
-  c->counts[NRP_C_EDGES] = n_edges;
   CU(cudaStreamSynchronize(c->stream));
   return NRP_OK;
 }

@@ -207,10 +207,31 @@ __global__ void k_last_single(const uint8_t* ascii, const int64_t* off, const ui
 }
 
 // ---- part-pair edges (reference hgraph.py:157-200, order-free) ---------------------------------------------------
-// one thread per member a of a group: pairs (a, b > a).  code = (min id << 32) | max id; pairs of one part with
-// itself (a k-mer occurring twice in a part, internal_repeats=True) get the all-ones code and sort last.
-__global__ void k_edge_pairs(const int64_t* indptr, const uint32_t* members, const unsigned long long* pair_off, int64_t n_groups,
-                             int64_t n_members, const uint32_t* part_id, uint64_t* codes) {
+// Distinct (id_u < id_v) pairs through an open-addressing hash set of 64-bit codes (EMPTY = all ones): the thread that
+// wins the slot appends the edge to the output list.  Pairs of a part with itself (a k-mer occurring twice in one
+// part, internal_repeats=True) are skipped.  The output order is unspecified.
+__device__ __forceinline__ void edge_insert(uint32_t ida, uint32_t idb, uint64_t* table, int log_slots, uint32_t* out_u, uint32_t* out_v,
+                                            unsigned long long* n_out) {
+  if (ida == idb) return;
+  const uint32_t lo = ida < idb ? ida : idb, hi = ida < idb ? idb : ida;
+  const uint64_t code = ((uint64_t)lo << 32) | hi;
+  const uint64_t mask = (1ull << log_slots) - 1ull;
+  uint64_t h = key_hash(code) >> (64 - log_slots);
+  for (;;) {
+    uint64_t old = atomic_cas(&table[h], ~0ull, code);
+    if (old == code) return;
+    if (old == ~0ull) {
+      unsigned long long o = atomicAdd(n_out, 1ull);
+      out_u[o] = lo; out_v[o] = hi;
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+}
+
+// one thread per member a of a group: pairs (a, b > a)
+__global__ void k_edge_pairs(const int64_t* indptr, const uint32_t* members, int64_t n_groups, int64_t n_members, const uint32_t* part_id,
+                             uint64_t* table, int log_slots, uint32_t* out_u, uint32_t* out_v, unsigned long long* n_out) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_members) return;
   int64_t lo = 0, hi = n_groups;                      // last group with indptr <= t
@@ -218,36 +239,16 @@ __global__ void k_edge_pairs(const int64_t* indptr, const uint32_t* members, con
     int64_t mid = (lo + hi) >> 1;
     if (indptr[mid] <= t) lo = mid; else hi = mid;
   }
-  const int64_t g = lo;
-  const int64_t s = indptr[g + 1] - indptr[g];
-  const int64_t a = t - indptr[g];
+  const int64_t end = indptr[lo + 1];
   const uint32_t ida = part_id[members[t]];
-  unsigned long long dst = pair_off[g] + (unsigned long long)(a * s - a * (a + 1) / 2);
-  for (int64_t b = a + 1; b < s; ++b) {
-    uint32_t idb = part_id[members[indptr[g] + b]];
-    uint64_t code = ida == idb ? ~0ull : (ida < idb ? ((uint64_t)ida << 32) | idb : ((uint64_t)idb << 32) | ida);
-    codes[dst + (unsigned long long)(b - a - 1)] = code;
-  }
+  for (int64_t b = t + 1; b < end; ++b) edge_insert(ida, part_id[members[b]], table, log_slots, out_u, out_v, n_out);
 }
 
-__global__ void k_edge_codes(const uint32_t* u, const uint32_t* v, int64_t n, uint64_t* codes) {
+// union of edge lists gathered from several ranks
+__global__ void k_edge_merge(const uint32_t* u, const uint32_t* v, int64_t n, uint64_t* table, int log_slots, uint32_t* out_u, uint32_t* out_v,
+                             unsigned long long* n_out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) codes[i] = ((uint64_t)u[i] << 32) | v[i];
-}
-
-__global__ void k_edge_heads(const uint64_t* codes, int64_t n, uint32_t* head) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint64_t c = codes[i];
-  head[i] = (c != ~0ull && (i == 0 || c != codes[i - 1])) ? 1u : 0u;
-}
-
-__global__ void k_edge_compact(const uint64_t* codes, const uint32_t* head, const uint32_t* head_scan, int64_t n, uint32_t* u, uint32_t* v) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !head[i]) return;
-  uint32_t o = head_scan[i];
-  u[o] = (uint32_t)(codes[i] >> 32);
-  v[o] = (uint32_t)codes[i];
+  if (i < n) edge_insert(u[i], v[i], table, log_slots, out_u, out_v, n_out);
 }
 
 __global__ void k_count_flagged(const uint8_t* flags, int64_t n, unsigned long long* out) {

@@ -79,4 +79,4 @@ def test_sharded_equals_single_gpu(tmp_path, k, internal):
         assert int(res['records']) == int(single['records'])
         assert _groups(res) == _groups(single)
         assert res['last_single'].tolist() == single['last_single'].tolist()
-        assert res['eu'].tolist() == single['eu'].tolist() and res['ev'].tolist() == single['ev'].tolist()
+        assert sorted(zip(res['eu'].tolist(), res['ev'].tolist())) == sorted(zip(single['eu'].tolist(), single['ev'].tolist()))
