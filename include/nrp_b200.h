@@ -90,7 +90,7 @@ int nrp_ctx_destroy(nrp_ctx* ctx);
 int nrp_ctx_device(nrp_ctx* ctx);
 
 /* Tuning knobs used by the tests to force rarely taken paths: name in
- * {"filter_cap", "leaf_target", "max_level_bits", "max_pairs"}; value <= 0 restores the default. */
+ * {"filter_cap", "leaf_target", "max_level_bits", "max_pairs", "no_window_carry", "no_bloom"}; value <= 0 restores the default. */
 int nrp_ctx_set_option(nrp_ctx* ctx, const char* name, int64_t value);
 
 /* Background (replaces the kmerSetDB membership test, kmerSetDB.py:177-207): n canonical K-mers in the

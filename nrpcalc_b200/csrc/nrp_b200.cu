@@ -104,6 +104,7 @@ struct nrp_ctx {
   int64_t opt_max_level_bits = kMaxLevelBits;
   int64_t opt_max_pairs = (int64_t)1 << 31;
   int64_t opt_no_window_carry = 0;
+  int64_t opt_no_bloom = 0;
 
   // background
   DevBuf bg_table; int bg_K = 0; int bg_log_slots = 0; int bg_key_bytes = 0; int64_t bg_n = 0;
@@ -213,6 +214,8 @@ int configure_kernels(nrp_ctx* c) {
   const int split_smem = (int)(sizeof(SplitSmem<KeyT>) + sizeof(TileStage));
   CU(cudaFuncSetAttribute(k_split_from_ascii<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, split_smem));
   CU(cudaFuncSetAttribute(k_split_from_records<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<KeyT>)));
+  CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, kFilterItemsSmall>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)filter_bloom_smem<KeyT>()));
   CU(cudaFuncSetAttribute((k_filter<KeyT, kFilterThreads, kFilterItems, kFilterCap, false>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)filter_smem_large<KeyT>()));
   CU(cudaFuncSetAttribute((k_filter<KeyT, kFilterThreads, kFilterItemsSmall, kFilterCapSmall, kFilterStaged>), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -279,6 +282,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "max_level_bits") c->opt_max_level_bits = (value <= 0 || value > kMaxLevelBits) ? kMaxLevelBits : value;
   else if (n == "max_pairs") c->opt_max_pairs = value <= 0 ? ((int64_t)1 << 31) : value;
   else if (n == "no_window_carry") c->opt_no_window_carry = value > 0 ? 1 : 0;
+  else if (n == "no_bloom") c->opt_no_bloom = value > 0 ? 1 : 0;
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
   return NRP_OK;
 }
@@ -480,7 +484,11 @@ int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, 
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / (fsm + 18 * 1024)));   // + static smem of the leaf ordering
     const unsigned fgrid = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * per_sm);
     const uint32_t cap = (uint32_t)std::min<int64_t>(c->opt_filter_cap, small ? kFilterCapSmall : kFilterCap);
-    if (small)
+    if (small && !c->opt_no_bloom)
+      NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, kFilterItemsSmall><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * 2), kFilterThreads, filter_bloom_smem<KeyT>(), st>>>(
+          leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, free_keys, free_vals, cnt + CNT_CAND,
+          reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED), reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED))));
+    else if (small)
       NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItemsSmall, kFilterCapSmall, kFilterStaged><<<fgrid, kFilterThreads, fsm, st>>>(
           leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, free_keys, free_vals, cnt + CNT_CAND,
           reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED), reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED))));

@@ -420,4 +420,168 @@ __global__ void __launch_bounds__(T, (E <= 4) ? 2 : 1) k_filter(const KeyT* __re
   if (STAGED) asm volatile("cp.async.wait_group 0;" ::);
 }
 
+// ---- in-bucket duplicate filter, two stages ---------------------------------------------------------------------
+// ~99 % of the records of a leaf are singletons.  Stage 1 throws most of them out with two 65536-bit maps in shared
+// memory: every record sets its bit in map A, a record that finds its bit already set also sets it in map B; afterwards
+// a record is a SUSPECT iff its bit is set in B (every key that occurs twice makes both of its records suspects; a
+// singleton is a suspect only if another key shares its bit, ~n/65536 of them).  Stage 2 runs the exact open-addressing
+// test on the few suspects only and orders the confirmed ones by (key, part, window) before they are written as one run.
+// Per record this is a hash, one or two shared-memory atomics and a bit test instead of a CAS loop in a table that has to
+// be cleared for every leaf.  Leaves above `cap` records, or with more than kLeafSortCap suspects, are passed on
+// unfiltered / unordered and the host runs the global sort (always correct, only slower).
+constexpr int kBloomWords = 2048;            // 65536 bits per map
+constexpr int kSuspectSlots = 2 * kLeafSortCap;
+template <typename KeyT> constexpr size_t filter_bloom_smem() {
+  return sizeof(KeyT) * (kSuspectSlots + kLeafSortCap) + 4 * (2 * kBloomWords + 2 * kLeafSortCap) + kLeafSortCap + kSuspectSlots;
+}
+
+template <typename KeyT, int T, int E>
+__global__ void __launch_bounds__(T, 2) k_filter_bloom(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* leaf_off,
+                                                      uint32_t n_leaf, int leaf_bits, uint32_t cap, KeyT* cand_keys, uint32_t* cand_vals,
+                                                      unsigned long long* n_cand, uint32_t* n_oversized, uint32_t* unsorted) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KeyT* table = reinterpret_cast<KeyT*>(smem_raw);                                  // kSuspectSlots
+  KeyT* c_keys = table + kSuspectSlots;                                              // kLeafSortCap
+  uint32_t* map_a = reinterpret_cast<uint32_t*>(c_keys + kLeafSortCap);             // kBloomWords
+  uint32_t* map_b = map_a + kBloomWords;                                             // kBloomWords
+  uint32_t* c_vals = map_b + kBloomWords;                                            // kLeafSortCap
+  uint32_t* c_rank = c_vals + kLeafSortCap;                                          // kLeafSortCap
+  unsigned char* c_dup = reinterpret_cast<unsigned char*>(c_rank + kLeafSortCap);   // kLeafSortCap
+  unsigned char* marked = c_dup + kLeafSortCap;                                      // kSuspectSlots
+  __shared__ uint32_t s_c1, s_c2;
+  __shared__ unsigned long long s_cbase;
+  const KeyT kEmpty = ~KeyT(0);
+  const int lane = threadIdx.x & 31;
+  const int bit_shift = 48 - leaf_bits, slot_shift = 37 - leaf_bits;
+  for (int i = threadIdx.x; i < kLeafSortCap; i += T) c_rank[i] = 0;
+  for (uint32_t leaf = blockIdx.x; leaf < n_leaf; leaf += gridDim.x) {
+    const uint32_t lo = leaf_off[leaf];
+    const uint32_t n = leaf_off[leaf + 1] - lo;
+    const bool fits = n >= 2 && n <= cap;
+    KeyT key[E];
+    uint32_t val[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {                   // loads are in flight while the maps are cleared
+      uint32_t i = threadIdx.x + e * T;
+      bool ok = fits && i < n;
+      key[e] = ok ? __ldg(keys + lo + i) : kEmpty;
+      val[e] = ok ? __ldg(vals + lo + i) : 0u;
+    }
+    __syncthreads();                                // previous leaf is completely done with the shared arrays
+    if (n < 2) continue;
+    if (n > cap) {
+      if (threadIdx.x == 0) { atomicAdd(n_oversized, 1u); *unsorted = 1u; }
+      for (uint32_t i = threadIdx.x; i < n + 31u - ((n - 1u) & 31u) ; i += T) {   // whole warps iterate together
+        bool ok = i < n;
+        uint32_t m = __ballot_sync(0xffffffffu, ok);
+        unsigned long long basepos = 0;
+        if (lane == 0) basepos = atomicAdd(n_cand, (unsigned long long)__popc(m));
+        basepos = __shfl_sync(0xffffffffu, basepos, 0);
+        if (ok) {
+          unsigned long long dst = basepos + __popc(m & lanemask_lt());
+          cand_keys[dst] = keys[lo + i];
+          cand_vals[dst] = vals[lo + i];
+        }
+      }
+      continue;
+    }
+    for (int i = threadIdx.x; i < kBloomWords; i += T) { map_a[i] = 0; map_b[i] = 0; }
+    for (int i = threadIdx.x; i < kSuspectSlots; i += T) { table[i] = kEmpty; marked[i] = 0; }
+    if (threadIdx.x == 0) { s_c1 = 0; s_c2 = 0; }
+    __syncthreads();
+    // stage 1a: set bits
+    uint32_t bits[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      bits[e] = (uint32_t)(key_hash((uint64_t)key[e]) >> bit_shift) & 0xffffu;
+      if (key[e] != kEmpty) {
+        const uint32_t w = bits[e] >> 5, m = 1u << (bits[e] & 31u);
+        if (atomicOr(&map_a[w], m) & m) atomicOr(&map_b[w], m);
+      }
+    }
+    __syncthreads();
+    // stage 1b: collect the suspects
+    bool suspect[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      suspect[e] = key[e] != kEmpty && ((map_b[bits[e] >> 5] >> (bits[e] & 31u)) & 1u);
+      if (suspect[e]) {
+        uint32_t pos = atomicAdd(&s_c1, 1u);
+        if (pos < (uint32_t)kLeafSortCap) { c_keys[pos] = key[e]; c_vals[pos] = val[e]; }
+      }
+    }
+    __syncthreads();
+    const uint32_t c1 = s_c1;
+    if (c1 == 0) continue;
+    if (c1 > (uint32_t)kLeafSortCap) {
+      // heavy sharing: hand all suspects (a superset of the shared records) to the global sort
+      if (threadIdx.x == 0) *unsorted = 1u;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        uint32_t m = __ballot_sync(0xffffffffu, suspect[e]);
+        if (m) {
+          unsigned long long basepos = 0;
+          if (lane == 0) basepos = atomicAdd(n_cand, (unsigned long long)__popc(m));
+          basepos = __shfl_sync(0xffffffffu, basepos, 0);
+          if (suspect[e]) {
+            unsigned long long dst = basepos + __popc(m & lanemask_lt());
+            cand_keys[dst] = key[e];
+            cand_vals[dst] = val[e];
+          }
+        }
+      }
+      continue;
+    }
+    // stage 2: exact test on the suspects (thread t owns suspect t)
+    uint32_t slot = 0xffffffffu;
+    KeyT mk = kEmpty;
+    uint32_t mv = 0;
+    if (threadIdx.x < c1) {
+      mk = c_keys[threadIdx.x]; mv = c_vals[threadIdx.x];
+      uint32_t h = (uint32_t)(key_hash((uint64_t)mk) >> slot_shift) & (kSuspectSlots - 1);
+      for (;;) {
+        KeyT old = atomic_cas(&table[h], kEmpty, mk);
+        if (old == kEmpty) break;
+        if (old == mk) { marked[h] = 1; break; }
+        h = (h + 1u) & (kSuspectSlots - 1);
+      }
+      slot = h;
+    }
+    __syncthreads();
+    if (threadIdx.x < c1) {
+      const bool dup = marked[slot] != 0;
+      c_dup[threadIdx.x] = dup ? 1 : 0;
+      if (dup) atomicAdd(&s_c2, 1u);
+    }
+    __syncthreads();
+    const uint32_t c2 = s_c2;
+    if (c2 == 0) continue;
+    {  // order the confirmed records: rank by counting among them, T / c1 threads per suspect
+      const uint32_t share = T / c1;
+      const uint32_t cand = threadIdx.x % c1, seg = threadIdx.x / c1;
+      if (seg < share && c_dup[cand]) {
+        const KeyT ck = c_keys[cand];
+        const uint32_t cv = c_vals[cand];
+        uint32_t partial = 0;
+        for (uint32_t j = seg; j < c1; j += share) {
+          if (!c_dup[j]) continue;
+          KeyT ok = c_keys[j]; uint32_t ov = c_vals[j];
+          partial += (ok < ck || (ok == ck && (ov < cv || (ov == cv && j < cand)))) ? 1u : 0u;
+        }
+        if (partial) atomicAdd(&c_rank[cand], partial);
+      }
+      if (threadIdx.x == 0) s_cbase = atomicAdd(n_cand, (unsigned long long)c2);
+    }
+    __syncthreads();
+    if (threadIdx.x < c1) {
+      if (c_dup[threadIdx.x]) {
+        const uint32_t rank = c_rank[threadIdx.x];
+        cand_keys[s_cbase + rank] = mk;
+        cand_vals[s_cbase + rank] = mv;
+      }
+      c_rank[threadIdx.x] = 0;
+    }
+  }
+}
+
 }  // namespace nrp

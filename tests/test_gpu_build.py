@@ -104,12 +104,16 @@ def test_forced_paths(ctx):
         _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
         ctx.set_option('max_level_bits', 0)
         ctx.set_option('leaf_target', 0)
+        ctx.set_option('no_bloom', 1)                 # exact table on every record instead of the two-stage filter
+        _compare(_run(ctx, uniq, 13, False), uniq, 13, False)
+        ctx.set_option('no_bloom', 0)
         ctx.set_option('no_window_carry', 1)          # ranks from the ASCII scan instead of the record value
         _compare(_run(ctx, uniq, 13, False), uniq, 13, False)
         uniq17 = _long_parts(cases.planted_parts(600, 77), 17)
         _compare(_run(ctx, uniq17, 17, True), uniq17, 17, True)
     finally:
         ctx.set_option('no_window_carry', 0)
+        ctx.set_option('no_bloom', 0)
         ctx.set_option('filter_cap', 0)
         ctx.set_option('leaf_target', 0)
         ctx.set_option('max_level_bits', 0)
