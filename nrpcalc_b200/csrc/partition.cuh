@@ -429,10 +429,34 @@ __global__ void __launch_bounds__(T, (E <= 4) ? 2 : 1) k_filter(const KeyT* __re
 // Per record this is a hash, one or two shared-memory atomics and a bit test instead of a CAS loop in a table that has to
 // be cleared for every leaf.  Leaves above `cap` records, or with more than kLeafSortCap suspects, are passed on
 // unfiltered / unordered and the host runs the global sort (always correct, only slower).
+// --- TMA (cp.async.bulk) + mbarrier helpers: one thread streams a leaf bucket global -> shared, the CTA waits on the barrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (spin > (1u << 26)) __trap();          // never hang the device: a lost copy is a bug, fail loudly
+  }
+}
+
 constexpr int kBloomWords = 2048;            // 65536 bits per map
 constexpr int kSuspectSlots = 2 * kLeafSortCap;
+constexpr int kBloomCap = 4096;              // records of a leaf that fit the staging area
 template <typename KeyT> constexpr size_t filter_bloom_smem() {
-  return sizeof(KeyT) * (kSuspectSlots + kLeafSortCap) + 4 * (2 * kBloomWords + 2 * kLeafSortCap) + kLeafSortCap + kSuspectSlots;
+  return sizeof(KeyT) * (kSuspectSlots + kLeafSortCap) + 4 * (2 * kBloomWords + 2 * kLeafSortCap) + kLeafSortCap + kSuspectSlots +
+         (sizeof(KeyT) + 4) * (kBloomCap + 8) + 64;
 }
 
 template <typename KeyT, int T, int E>
@@ -448,27 +472,82 @@ __global__ void __launch_bounds__(T, 2) k_filter_bloom(const KeyT* __restrict__ 
   uint32_t* c_rank = c_vals + kLeafSortCap;                                          // kLeafSortCap
   unsigned char* c_dup = reinterpret_cast<unsigned char*>(c_rank + kLeafSortCap);   // kLeafSortCap
   unsigned char* marked = c_dup + kLeafSortCap;                                      // kSuspectSlots
+  // staging area of the NEXT leaf, filled by TMA bulk copies (16-byte aligned source windows around the leaf)
+  KeyT* st_keys = reinterpret_cast<KeyT*>((reinterpret_cast<uintptr_t>(marked + kSuspectSlots) + 15) & ~uintptr_t(15));
+  uint32_t* st_vals = reinterpret_cast<uint32_t*>(st_keys + kBloomCap + 8);
+  __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_c1, s_c2;
   __shared__ unsigned long long s_cbase;
   const KeyT kEmpty = ~KeyT(0);
   const int lane = threadIdx.x & 31;
   const int bit_shift = 48 - leaf_bits, slot_shift = 37 - leaf_bits;
   for (int i = threadIdx.x; i < kLeafSortCap; i += T) c_rank[i] = 0;
-  for (uint32_t leaf = blockIdx.x; leaf < n_leaf; leaf += gridDim.x) {
-    const uint32_t lo = leaf_off[leaf];
-    const uint32_t n = leaf_off[leaf + 1] - lo;
-    const bool fits = n >= 2 && n <= cap;
+  constexpr uint32_t kKeysPer16 = 16 / sizeof(KeyT);
+  // thread 0 starts the bulk copies of a leaf: the source windows are widened to 16-byte boundaries
+  auto stage = [&](uint32_t slo, uint32_t sn) {
+    if (sn < 2 || sn > cap || sn > (uint32_t)kBloomCap) return;
+    const uint32_t k0 = slo & ~(kKeysPer16 - 1), k1 = (slo + sn + kKeysPer16 - 1) & ~(kKeysPer16 - 1);
+    const uint32_t v0 = slo & ~3u, v1 = (slo + sn + 3u) & ~3u;
+    const uint32_t kb = (k1 - k0) * (uint32_t)sizeof(KeyT), vb = (v1 - v0) * 4u;
+    mbar_expect_tx(&s_bar, kb + vb);
+    tma_bulk_load(st_keys, keys + k0, kb, &s_bar);
+    tma_bulk_load(st_vals, vals + v0, vb, &s_bar);
+  };
+  // leaf extents are read two leaves ahead so that no global-load latency sits on the per-leaf critical path
+  auto extent = [&](uint32_t lf, uint32_t& elo, uint32_t& en) {
+    elo = 0; en = 0;
+    if (lf < n_leaf) { elo = __ldg(leaf_off + lf); en = __ldg(leaf_off + lf + 1) - elo; }
+  };
+  uint32_t lo, n, lo1, n1, lo2, n2;
+  extent(blockIdx.x, lo, n);
+  extent(blockIdx.x + gridDim.x, lo1, n1);
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) stage(lo, n);
+  uint32_t parity = 0;
+  for (uint32_t leaf = blockIdx.x; leaf < n_leaf; leaf += gridDim.x, lo = lo1, n = n1, lo1 = lo2, n1 = n2) {
+    extent(leaf + 2 * gridDim.x, lo2, n2);
+    const bool fits = n >= 2 && n <= cap && n <= (uint32_t)kBloomCap;
     KeyT key[E];
     uint32_t val[E];
+    if (fits) {                                     // uniform: the copy of this leaf was issued one iteration ago
+      mbar_wait(&s_bar, parity);
+      parity ^= 1u;
+      const uint32_t kshift = lo & (kKeysPer16 - 1), vshift = lo & 3u;
 #pragma unroll
-    for (int e = 0; e < E; ++e) {                   // loads are in flight while the maps are cleared
-      uint32_t i = threadIdx.x + e * T;
-      bool ok = fits && i < n;
-      key[e] = ok ? __ldg(keys + lo + i) : kEmpty;
-      val[e] = ok ? __ldg(vals + lo + i) : 0u;
+      for (int e = 0; e < E; ++e) {
+        uint32_t i = threadIdx.x + e * T;
+        bool ok = i < n;
+        key[e] = ok ? st_keys[i + kshift] : kEmpty;
+        val[e] = ok ? st_vals[i + vshift] : 0u;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) { key[e] = kEmpty; val[e] = 0u; }
     }
-    __syncthreads();                                // previous leaf is completely done with the shared arrays
+    __syncthreads();                                // everyone copied out; the previous leaf is done with the shared arrays
+    if (threadIdx.x == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before the async-proxy overwrite
+      stage(lo1, n1);
+    }
     if (n < 2) continue;
+    if (n > cap || n > (uint32_t)kBloomCap) {
+      if (threadIdx.x == 0) { atomicAdd(n_oversized, 1u); *unsorted = 1u; }
+      for (uint32_t i = threadIdx.x; i < n + 31u - ((n - 1u) & 31u) ; i += T) {   // whole warps iterate together
+        bool ok = i < n;
+        uint32_t m = __ballot_sync(0xffffffffu, ok);
+        unsigned long long basepos = 0;
+        if (lane == 0) basepos = atomicAdd(n_cand, (unsigned long long)__popc(m));
+        basepos = __shfl_sync(0xffffffffu, basepos, 0);
+        if (ok) {
+          unsigned long long dst = basepos + __popc(m & lanemask_lt());
+          cand_keys[dst] = keys[lo + i];
+          cand_vals[dst] = vals[lo + i];
+        }
+      }
+      continue;
+    }
+    for (int i = threadIdx.x; i < kBloomWords; i += T) { map_a[i] = 0; map_b[i] = 0; }    if (n < 2) continue;
     if (n > cap) {
       if (threadIdx.x == 0) { atomicAdd(n_oversized, 1u); *unsorted = 1u; }
       for (uint32_t i = threadIdx.x; i < n + 31u - ((n - 1u) & 31u) ; i += T) {   // whole warps iterate together
@@ -548,23 +627,24 @@ __global__ void __launch_bounds__(T, 2) k_filter_bloom(const KeyT* __restrict__ 
       slot = h;
     }
     __syncthreads();
-    if (threadIdx.x < c1) {
-      const bool dup = marked[slot] != 0;
-      c_dup[threadIdx.x] = dup ? 1 : 0;
-      if (dup) atomicAdd(&s_c2, 1u);
+    // confirmed records are compacted to the front of the suspect list (every owner holds its record in registers)
+    if (threadIdx.x < c1 && marked[slot] != 0) {
+      const uint32_t pos = atomicAdd(&s_c2, 1u);
+      c_keys[pos] = mk;
+      c_vals[pos] = mv;
     }
     __syncthreads();
     const uint32_t c2 = s_c2;
     if (c2 == 0) continue;
-    {  // order the confirmed records: rank by counting among them, T / c1 threads per suspect
-      const uint32_t share = T / c1;
-      const uint32_t cand = threadIdx.x % c1, seg = threadIdx.x / c1;
-      if (seg < share && c_dup[cand]) {
+    {  // order them: rank by counting, a power-of-two group of threads per record
+      int lg = 0;
+      while ((2u << lg) * c2 <= (uint32_t)T) ++lg;           // 2^lg threads per record, 2^lg * c2 <= T
+      const uint32_t cand = threadIdx.x >> lg, seg = threadIdx.x & ((1u << lg) - 1u);
+      if (cand < c2) {
         const KeyT ck = c_keys[cand];
         const uint32_t cv = c_vals[cand];
         uint32_t partial = 0;
-        for (uint32_t j = seg; j < c1; j += share) {
-          if (!c_dup[j]) continue;
+        for (uint32_t j = seg; j < c2; j += (1u << lg)) {
           KeyT ok = c_keys[j]; uint32_t ov = c_vals[j];
           partial += (ok < ck || (ok == ck && (ov < cv || (ov == cv && j < cand)))) ? 1u : 0u;
         }
@@ -573,12 +653,10 @@ __global__ void __launch_bounds__(T, 2) k_filter_bloom(const KeyT* __restrict__ 
       if (threadIdx.x == 0) s_cbase = atomicAdd(n_cand, (unsigned long long)c2);
     }
     __syncthreads();
-    if (threadIdx.x < c1) {
-      if (c_dup[threadIdx.x]) {
-        const uint32_t rank = c_rank[threadIdx.x];
-        cand_keys[s_cbase + rank] = mk;
-        cand_vals[s_cbase + rank] = mv;
-      }
+    if (threadIdx.x < c2) {
+      const uint32_t rank = c_rank[threadIdx.x];
+      cand_keys[s_cbase + rank] = c_keys[threadIdx.x];
+      cand_vals[s_cbase + rank] = c_vals[threadIdx.x];
       c_rank[threadIdx.x] = 0;
     }
   }
