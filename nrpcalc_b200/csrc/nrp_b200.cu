@@ -214,8 +214,10 @@ int configure_kernels(nrp_ctx* c) {
   const int split_smem = (int)(sizeof(SplitSmem<KeyT>) + sizeof(TileStage));
   CU(cudaFuncSetAttribute(k_split_from_ascii<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, split_smem));
   CU(cudaFuncSetAttribute(k_split_from_records<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<KeyT>)));
-  CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, kFilterItemsSmall>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)filter_bloom_smem<KeyT>()));
+  CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, 4, 2048, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)filter_bloom_smem<KeyT, 4096, 2048>()));
+  CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)filter_bloom_smem<KeyT, 8192, 4096>()));
   CU(cudaFuncSetAttribute((k_filter<KeyT, kFilterThreads, kFilterItems, kFilterCap, false>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)filter_smem_large<KeyT>()));
   CU(cudaFuncSetAttribute((k_filter<KeyT, kFilterThreads, kFilterItemsSmall, kFilterCapSmall, kFilterStaged>), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -485,7 +487,13 @@ int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, 
     const unsigned fgrid = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * per_sm);
     const uint32_t cap = (uint32_t)std::min<int64_t>(c->opt_filter_cap, small ? kFilterCapSmall : kFilterCap);
     if (small && !c->opt_no_bloom)
-      NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, kFilterItemsSmall><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * 2), kFilterThreads, filter_bloom_smem<KeyT>(), st>>>(
+      NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 4, 2048, 2><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * 2), kFilterThreads,
+                                                                 filter_bloom_smem<KeyT, 4096, 2048>(), st>>>(
+          leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, free_keys, free_vals, cnt + CNT_CAND,
+          reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED), reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED))));
+    else if (!c->opt_no_bloom)
+      NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms), kFilterThreads,
+                                                                 filter_bloom_smem<KeyT, 8192, 4096>(), st>>>(
           leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, free_keys, free_vals, cnt + CNT_CAND,
           reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED), reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED))));
     else if (small)

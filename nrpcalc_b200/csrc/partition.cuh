@@ -451,18 +451,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-constexpr int kBloomWords = 2048;            // 65536 bits per map
 constexpr int kSuspectSlots = 2 * kLeafSortCap;
-constexpr int kBloomCap = 4096;              // records of a leaf that fit the staging area
-template <typename KeyT> constexpr size_t filter_bloom_smem() {
-  return sizeof(KeyT) * (kSuspectSlots + kLeafSortCap) + 4 * (2 * kBloomWords + 2 * kLeafSortCap) + kLeafSortCap + kSuspectSlots +
-         (sizeof(KeyT) + 4) * (kBloomCap + 8) + 64;
+// capacity of a leaf = T * E records (staging area); WORDS = 32-bit words per bit map (16 bits per record or more)
+template <typename KeyT, int CAP, int WORDS> constexpr size_t filter_bloom_smem() {
+  return sizeof(KeyT) * (kSuspectSlots + kLeafSortCap) + 4 * (2 * WORDS + 2 * kLeafSortCap) + kLeafSortCap + kSuspectSlots +
+         (sizeof(KeyT) + 4) * (CAP + 8) + 64;
 }
 
-template <typename KeyT, int T, int E>
-__global__ void __launch_bounds__(T, 2) k_filter_bloom(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* leaf_off,
+template <typename KeyT, int T, int E, int WORDS, int MINB>
+__global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* leaf_off,
                                                       uint32_t n_leaf, int leaf_bits, uint32_t cap, KeyT* cand_keys, uint32_t* cand_vals,
                                                       unsigned long long* n_cand, uint32_t* n_oversized, uint32_t* unsorted) {
+  constexpr int kBloomWords = WORDS, kBloomCap = T * E;
+  constexpr uint32_t kBitMask = (uint32_t)WORDS * 32u - 1u;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KeyT* table = reinterpret_cast<KeyT*>(smem_raw);                                  // kSuspectSlots
   KeyT* c_keys = table + kSuspectSlots;                                              // kLeafSortCap
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(T, 2) k_filter_bloom(const KeyT* __restrict__ 
   __shared__ unsigned long long s_cbase;
   const KeyT kEmpty = ~KeyT(0);
   const int lane = threadIdx.x & 31;
-  const int bit_shift = 48 - leaf_bits, slot_shift = 37 - leaf_bits;
+  const int bit_shift = 44 - leaf_bits, slot_shift = 33 - leaf_bits;     // 20 hash bits for the maps, the next 11 for the table
   for (int i = threadIdx.x; i < kLeafSortCap; i += T) c_rank[i] = 0;
   constexpr uint32_t kKeysPer16 = 16 / sizeof(KeyT);
   // thread 0 starts the bulk copies of a leaf: the source windows are widened to 16-byte boundaries
@@ -572,7 +573,7 @@ __global__ void __launch_bounds__(T, 2) k_filter_bloom(const KeyT* __restrict__ 
     uint32_t bits[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      bits[e] = (uint32_t)(key_hash((uint64_t)key[e]) >> bit_shift) & 0xffffu;
+      bits[e] = (uint32_t)(key_hash((uint64_t)key[e]) >> bit_shift) & kBitMask;
       if (key[e] != kEmpty) {
         const uint32_t w = bits[e] >> 5, m = 1u << (bits[e] & 31u);
         if (atomicOr(&map_a[w], m) & m) atomicOr(&map_b[w], m);
