@@ -140,6 +140,21 @@ int nrp_result_edges(nrp_ctx* ctx, uint32_t* u, uint32_t* v);
  *   (all-gather of the shared k-mers)
  *   nrp_shard_last_single  last unshared window of the parts of this rank's shard
  */
+/* Fused exchange (preferred when the ranks' GPUs have peer access): instead of an NCCL all-to-all, the extraction kernel
+ * stores every record straight into its owner's receive buffer over NVLink.
+ *   nrp_peer_export          allocate this rank's receive buffers (capacity in records) and return their CUDA IPC handles
+ *   nrp_peer_open            open all ranks' handles (n_peers x 128 bytes: keys handle, values handle); own rank = local memory
+ *   nrp_shard_count          flags + number of records this rank will send to every owner
+ *   (host: all-gather of the counts -> write offsets; barrier)
+ *   nrp_shard_scatter_peers  extraction + scatter into the owners' buffers at write_offsets[owner]
+ *   (host: barrier)
+ *   nrp_shard_group_received = nrp_shard_group on the first n_records of this rank's receive buffers */
+int nrp_peer_export(nrp_ctx* ctx, int64_t capacity_records, int k, unsigned char* handle_keys /*64*/, unsigned char* handle_vals /*64*/);
+int nrp_peer_open(nrp_ctx* ctx, int n_peers, int my_rank, const unsigned char* handles);
+int nrp_shard_count(nrp_ctx* ctx, int64_t part_lo, int64_t part_hi, int k, int internal_repeats, int n_owners, int64_t* owner_counts);
+int nrp_shard_scatter_peers(nrp_ctx* ctx, int k, const int64_t* write_offsets);
+int nrp_shard_group_received(nrp_ctx* ctx, int64_t n_records, int k, int internal_repeats);
+
 /* run all work of the context on a caller-owned CUDA stream (cudaStream_t), e.g. torch's current stream; NULL
  * restores a private stream */
 int nrp_ctx_set_stream(nrp_ctx* ctx, void* cuda_stream);

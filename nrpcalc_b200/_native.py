@@ -59,6 +59,11 @@ def _declare(lib):
         'nrp_shard_finish': (c_ctx, i32, i32, i32),
         'nrp_shard_last_single': (c_ctx, ptr, i64, i32, i32),
         'nrp_edges_merge': (c_ctx, ptr, ptr, i64),
+        'nrp_peer_export': (c_ctx, i64, i32, ptr, ptr),
+        'nrp_peer_open': (c_ctx, i32, i32, ptr),
+        'nrp_shard_count': (c_ctx, i64, i64, i32, i32, i32, ptr),
+        'nrp_shard_scatter_peers': (c_ctx, i32, ptr),
+        'nrp_shard_group_received': (c_ctx, i64, i32, i32),
         'nrp_result_device': (c_ctx, i32, ctypes.POINTER(ptr), ctypes.POINTER(i64)),
     }
     for name, argtypes in sigs.items():
@@ -172,6 +177,29 @@ class Context(object):
     def shard_group(self, keys_ptr, vals_ptr, n_records, k, internal_repeats):
         _check(self._lib, self._lib.nrp_shard_group(self._h, ctypes.c_void_p(int(keys_ptr) or None), ctypes.c_void_p(int(vals_ptr) or None),
                                                     int(n_records), int(k), 1 if internal_repeats else 0))
+
+    def peer_export(self, capacity_records, k):
+        hk = np.zeros(64, dtype=np.uint8)
+        hv = np.zeros(64, dtype=np.uint8)
+        _check(self._lib, self._lib.nrp_peer_export(self._h, int(capacity_records), int(k), _p(hk), _p(hv)))
+        return hk.tobytes() + hv.tobytes()
+
+    def peer_open(self, handles, my_rank):
+        blob = np.frombuffer(b''.join(handles), dtype=np.uint8).copy()
+        _check(self._lib, self._lib.nrp_peer_open(self._h, len(handles), int(my_rank), _p(blob)))
+
+    def shard_count(self, part_lo, part_hi, k, internal_repeats, n_owners):
+        counts = np.zeros(n_owners, dtype=np.int64)
+        _check(self._lib, self._lib.nrp_shard_count(self._h, int(part_lo), int(part_hi), int(k), 1 if internal_repeats else 0,
+                                                    int(n_owners), _p(counts)))
+        return counts
+
+    def shard_scatter_peers(self, k, write_offsets):
+        offs = np.ascontiguousarray(write_offsets, dtype=np.int64)
+        _check(self._lib, self._lib.nrp_shard_scatter_peers(self._h, int(k), _p(offs)))
+
+    def shard_group_received(self, n_records, k, internal_repeats):
+        _check(self._lib, self._lib.nrp_shard_group_received(self._h, int(n_records), int(k), 1 if internal_repeats else 0))
 
     def flags_export(self, dst_ptr):
         _check(self._lib, self._lib.nrp_flags_export(self._h, ctypes.c_void_p(int(dst_ptr))))

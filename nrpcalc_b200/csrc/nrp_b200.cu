@@ -130,6 +130,13 @@ struct nrp_ctx {
   int64_t shard_lo = 0, shard_hi = 0, shard_tile_lo = 0, shard_tiles = 0, shard_m_max = 0;
   int n_owners = 0;
   int j_bits = 0;                // > 0: record values are (part << j_bits) | window
+  // receive buffers of the fused exchange (exported with CUDA IPC) and the peers' buffers opened here
+  DevBuf recv_keys, recv_vals;
+  int64_t recv_capacity = 0;
+  PeerBuffers peers{};
+  int n_peers = 0, my_rank = 0;
+  std::vector<std::vector<unsigned char>> opened_handles;
+  std::vector<void*> opened_ptrs;
   bool external_stream = false;
 
   // candidate records between the stages (type-erased: uint32_t* or uint64_t* keys)
@@ -265,7 +272,8 @@ int nrp_ctx_destroy(nrp_ctx* c) {
                    &c->keysB, &c->valsB, &c->head, &c->head_scan, &c->group_start, &c->valid, &c->valid_scan, &c->mem_cnt,
                    &c->mem_scan, &c->pair_cnt, &c->pair_scan, &c->g_keys, &c->g_indptr, &c->g_pair_off, &c->g_members,
                    &c->g_first_part, &c->g_first_window, &c->last_single, &c->e_codesA, &c->e_codesB, &c->e_head, &c->e_head_scan,
-                   &c->e_u, &c->e_v, &c->e_u_alt, &c->e_v_alt, &c->shared_keysA, &c->shared_keysB};
+                   &c->e_u, &c->e_v, &c->e_u_alt, &c->e_v_alt, &c->shared_keysA, &c->shared_keysB, &c->recv_keys, &c->recv_vals};
+  for (void* p : c->opened_ptrs) cudaIpcCloseMemHandle(p);
   for (DevBuf* b : all) b->release();
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -457,7 +465,7 @@ int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, 
   if (m_max > 0) {
     if (from_ascii) {
       NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-          P, c->flags.as<uint8_t>(), k, r1, 0, c->part_base, c->j_bits, level1_cursor, leaf_keys, leaf_vals)));
+          P, c->flags.as<uint8_t>(), k, r1, 0, c->part_base, c->j_bits, level1_cursor, leaf_keys, leaf_vals, PeerBuffers{}, 0)));
     } else {
       // one segment holding all records; level-1 digit = top r1 bits
       const uint32_t seg[2] = {0u, (uint32_t)n_in};
@@ -806,7 +814,7 @@ int shard_extract_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int internal_r
   tm.begin(NRP_T_SPLIT1);
   if (c->shard_m_max > 0)
     NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, 8, n_owners, 0u, c->j_bits, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>())));
+        P, c->flags.as<uint8_t>(), k, 8, n_owners, 0u, c->j_bits, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>(), PeerBuffers{}, 0)));
   CU(cudaGetLastError());
   tm.finish(c->timings);
   CU(cudaStreamSynchronize(st));
@@ -838,6 +846,60 @@ int shard_finish_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   if (want_edges) { c->counts[NRP_C_EDGES] = 0; TRY(stage_edges(c, tm)); }
   tm.finish(c->timings);
   c->have_result = true;
+  return NRP_OK;
+}
+
+// fused exchange, step 1: flags + owner histogram of the shard (counts go to the host for the offset exchange)
+template <typename KeyT>
+int shard_count_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int internal_repeats, int n_owners, int64_t* owner_counts) {
+  TRY(configure_kernels<KeyT>(c));
+  cudaStream_t st = c->stream;
+  c->shard_lo = lo; c->shard_hi = hi; c->n_owners = n_owners;
+  const int64_t byte_lo = c->h_off[lo], byte_hi = c->h_off[hi];
+  c->shard_tile_lo = byte_lo / kTileBytes;
+  c->shard_tiles = hi > lo && byte_hi > byte_lo ? (byte_hi + kTileBytes - 1) / kTileBytes - c->shard_tile_lo : 0;
+  c->shard_m_max = windows_in_range(c, lo, hi, k);
+  if (c->shard_m_max >= 0xffffe000ll) return fail(NRP_E_UNSUPPORTED, "shard too large for 32-bit record indices");
+  begin_job(c, k, sizeof(KeyT), 0);
+  c->counts[NRP_C_WINDOWS_MAX] = c->shard_m_max;
+  StageTimer tm(c);
+  TRY(stage_flags(c, k, internal_repeats, tm));
+  TRY(c->hist.ensure(4 * (((size_t)1 << kMaxLeafBits) + 2)));
+  TRY(c->scan_scratch.ensure(8 * (size_t)scan_scratch_elems(((int64_t)1 << kMaxLeafBits) + 2)));
+  TRY(c->cursor1.ensure(4 * 260));
+  const Parts P = parts_view(c);
+  tm.begin(NRP_T_HISTOGRAM);
+  CU(cudaMemsetAsync(c->hist.ptr, 0, 4 * 260, st));
+  if (c->shard_m_max > 0) {
+    const unsigned grid = (unsigned)std::min<int64_t>(c->shard_tiles, (int64_t)c->n_sms * 3);
+    NRP_LAUNCH((k_hist_from_ascii<1><<<grid, kTileThreads, 4u * 256, st>>>(P, c->flags.as<uint8_t>(), k, 8, n_owners, c->shard_tiles, c->hist.as<uint32_t>())));
+  }
+  CU(cudaMemcpyAsync(c->h_counters + 32, c->hist.ptr, 4 * (size_t)n_owners, cudaMemcpyDeviceToHost, st));
+  CU(cudaGetLastError());
+  tm.finish(c->timings);
+  CU(cudaStreamSynchronize(st));
+  const uint32_t* h = reinterpret_cast<const uint32_t*>(c->h_counters + 32);
+  for (int i = 0; i < n_owners; ++i) owner_counts[i] = h[i];
+  return NRP_OK;
+}
+
+// fused exchange, step 2: extraction + scatter straight into the owners' receive buffers (peer stores over NVLink).
+// write_offsets[o] = record index in owner o's buffer where this rank's run starts.
+template <typename KeyT>
+int shard_scatter_impl(nrp_ctx* c, int k, const int64_t* write_offsets) {
+  cudaStream_t st = c->stream;
+  const Parts P = parts_view(c);
+  uint32_t h_cursor[kMaxPeers];
+  for (int o = 0; o < c->n_owners; ++o) h_cursor[o] = (uint32_t)write_offsets[o];
+  CU(cudaMemcpyAsync(c->cursor1.ptr, h_cursor, 4 * (size_t)c->n_owners, cudaMemcpyHostToDevice, st));
+  StageTimer tm(c);
+  tm.begin(NRP_T_SPLIT1);
+  if (c->shard_m_max > 0)
+    NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+        P, c->flags.as<uint8_t>(), k, 8, c->n_owners, 0u, c->j_bits, c->cursor1.as<uint32_t>(), nullptr, nullptr, c->peers, 1)));
+  CU(cudaGetLastError());
+  tm.finish(c->timings);
+  CU(cudaStreamSynchronize(st));
   return NRP_OK;
 }
 
@@ -965,6 +1027,74 @@ int nrp_result_device(nrp_ctx* c, int what, void** ptr, int64_t* count) {
     default: return fail(NRP_E_ARG, "unknown result selector %d", what);
   }
   return NRP_OK;
+}
+
+int nrp_peer_export(nrp_ctx* c, int64_t capacity_records, int k, unsigned char* handle_keys, unsigned char* handle_vals) {
+  if (!c || !handle_keys || !handle_vals) return fail(NRP_E_ARG, "null argument");
+  if (capacity_records < 1 || capacity_records >= 0xffffe000ll) return fail(NRP_E_ARG, "bad capacity");
+  CU(cudaSetDevice(c->device));
+  const size_t key_bytes = k <= 16 ? 4 : 8;
+  TRY(c->recv_keys.ensure(key_bytes * (size_t)(capacity_records + 16)));
+  TRY(c->recv_vals.ensure(4 * (size_t)(capacity_records + 16)));
+  c->recv_capacity = capacity_records;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t hk, hv;
+  CU(cudaIpcGetMemHandle(&hk, c->recv_keys.ptr));
+  CU(cudaIpcGetMemHandle(&hv, c->recv_vals.ptr));
+  memcpy(handle_keys, &hk, 64);
+  memcpy(handle_vals, &hv, 64);
+  return NRP_OK;
+}
+
+int nrp_peer_open(nrp_ctx* c, int n_peers, int my_rank, const unsigned char* handles) {
+  if (!c || !handles) return fail(NRP_E_ARG, "null argument");
+  if (n_peers < 1 || n_peers > kMaxPeers || my_rank < 0 || my_rank >= n_peers) return fail(NRP_E_ARG, "bad peer count");
+  CU(cudaSetDevice(c->device));
+  auto open_one = [&](const unsigned char* h, void** out) -> int {
+    for (size_t i = 0; i < c->opened_handles.size(); ++i)
+      if (memcmp(c->opened_handles[i].data(), h, 64) == 0) { *out = c->opened_ptrs[i]; return NRP_OK; }
+    cudaIpcMemHandle_t handle;
+    memcpy(&handle, h, 64);
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, handle, cudaIpcMemLazyEnablePeerAccess));
+    c->opened_handles.emplace_back(h, h + 64);
+    c->opened_ptrs.push_back(ptr);
+    *out = ptr;
+    return NRP_OK;
+  };
+  for (int p = 0; p < n_peers; ++p) {
+    if (p == my_rank) { c->peers.keys[p] = c->recv_keys.ptr; c->peers.vals[p] = c->recv_vals.as<uint32_t>(); continue; }
+    void* pk = nullptr; void* pv = nullptr;
+    TRY(open_one(handles + (size_t)p * 128, &pk));
+    TRY(open_one(handles + (size_t)p * 128 + 64, &pv));
+    c->peers.keys[p] = pk; c->peers.vals[p] = reinterpret_cast<uint32_t*>(pv);
+  }
+  c->n_peers = n_peers; c->my_rank = my_rank;
+  return NRP_OK;
+}
+
+int nrp_shard_count(nrp_ctx* c, int64_t part_lo, int64_t part_hi, int k, int internal_repeats, int n_owners, int64_t* owner_counts) {
+  if (!c || !owner_counts) return fail(NRP_E_ARG, "null argument");
+  if (!c->have_parts) return fail(NRP_E_STATE, "nrp_load_parts has not been called");
+  if (k < 1 || k > 32) return fail(NRP_E_UNSUPPORTED, "k=%d outside [1, 32]", k);
+  if (part_lo < 0 || part_hi < part_lo || part_hi > c->n_parts) return fail(NRP_E_ARG, "bad shard range");
+  if (n_owners < 1 || n_owners > kMaxPeers) return fail(NRP_E_ARG, "n_owners must be in [1, %d]", kMaxPeers);
+  CU(cudaSetDevice(c->device));
+  return k <= 16 ? shard_count_impl<uint32_t>(c, part_lo, part_hi, k, internal_repeats, n_owners, owner_counts)
+                 : shard_count_impl<uint64_t>(c, part_lo, part_hi, k, internal_repeats, n_owners, owner_counts);
+}
+
+int nrp_shard_scatter_peers(nrp_ctx* c, int k, const int64_t* write_offsets) {
+  if (!c || !write_offsets) return fail(NRP_E_ARG, "null argument");
+  if (c->n_peers != c->n_owners || c->n_owners < 1) return fail(NRP_E_STATE, "peers are not open for %d owners", c->n_owners);
+  CU(cudaSetDevice(c->device));
+  return k <= 16 ? shard_scatter_impl<uint32_t>(c, k, write_offsets) : shard_scatter_impl<uint64_t>(c, k, write_offsets);
+}
+
+int nrp_shard_group_received(nrp_ctx* c, int64_t n_records, int k, int internal_repeats) {
+  if (!c) return fail(NRP_E_ARG, "null context");
+  if (n_records < 0 || n_records > c->recv_capacity) return fail(NRP_E_ARG, "record count exceeds the receive capacity");
+  return nrp_shard_group(c, c->recv_keys.ptr, c->recv_vals.as<uint32_t>(), n_records, k, internal_repeats);
 }
 
 int nrp_result_counts(nrp_ctx* c, int64_t out[NRP_N_COUNTS]) {

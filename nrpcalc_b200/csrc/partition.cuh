@@ -34,6 +34,14 @@ struct alignas(16) SplitSmem {
   uint32_t total;
 };
 
+// Destination buffers of the owner-mode scatter when records are stored straight into the owners' receive buffers
+// over NVLink (peer pointers opened with CUDA IPC); entry o = owner o's buffers (the own rank maps to local memory).
+constexpr int kMaxPeers = 16;
+struct PeerBuffers {
+  void* keys[kMaxPeers];
+  uint32_t* vals[kMaxPeers];
+};
+
 // digit of a key at one partition level
 struct HashField {            // a bit field of key_hash: leaf-bucket levels
   int shift; uint32_t mask;
@@ -50,7 +58,7 @@ struct OwnerDigit {           // owner GPU of a key (sharded path)
 template <typename KeyT, typename DigitFn>
 __device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&key)[kSplitItems], const uint32_t (&val)[kSplitItems],
                                               const uint32_t (&dr)[kSplitItems], int nb, DigitFn digit_of,
-                                              uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals) {
+                                              uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals, const PeerBuffers* peers = nullptr) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // exclusive scan of cnt[0..nb) by the first nb threads (nb <= 256 <= blockDim)
   uint32_t c = (int)threadIdx.x < nb ? s.cnt[threadIdx.x] : 0u;
@@ -88,8 +96,13 @@ __device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&k
     KeyT kx = s.keys[i];
     uint32_t d = digit_of((uint64_t)kx);
     uint32_t dst = s.gbase[d] + (i - s.base[d]);
-    out_keys[dst] = kx;
-    out_vals[dst] = s.vals[i];
+    if (peers) {                                   // bucket d lives in owner d's receive buffer (peer store over NVLink)
+      reinterpret_cast<KeyT*>(peers->keys[d])[dst] = kx;
+      peers->vals[d][dst] = s.vals[i];
+    } else {
+      out_keys[dst] = kx;
+      out_vals[dst] = s.vals[i];
+    }
   }
 }
 
@@ -150,7 +163,8 @@ __global__ void __launch_bounds__(512) k_hist_from_records(const KeyT* keys, int
 // is then sorting by (part, window), and a group's first record carries the group's rank for free.
 template <typename KeyT>
 __global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, const uint8_t* flags, int k, int r1, int n_owners,
-                                                                  uint32_t part_base, int j_bits, uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals) {
+                                                                  uint32_t part_base, int j_bits, uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals,
+                                                                  PeerBuffers peers, int use_peers) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SplitSmem<KeyT>& s = *reinterpret_cast<SplitSmem<KeyT>*>(smem_raw);
   TileStage& stage = *reinterpret_cast<TileStage*>(smem_raw + sizeof(SplitSmem<KeyT>));
@@ -172,7 +186,7 @@ __global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, cons
   });
   __syncthreads();
   if (n_owners > 0)
-    split_scatter<KeyT>(s, key, val, dr, nb, OwnerDigit{(uint32_t)n_owners}, cursor, out_keys, out_vals);
+    split_scatter<KeyT>(s, key, val, dr, nb, OwnerDigit{(uint32_t)n_owners}, cursor, out_keys, out_vals, use_peers ? &peers : nullptr);
   else
     split_scatter<KeyT>(s, key, val, dr, nb, HashField{64 - r1, (1u << r1) - 1u}, cursor, out_keys, out_vals);
 }

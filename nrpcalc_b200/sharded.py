@@ -76,6 +76,42 @@ class NativeOps(object):
         vals = torch.as_tensor(_DeviceArray(vals_ptr, n, '<i4'), device=self.device)
         return keys, vals, counts
 
+    # ---- fused exchange: records are stored straight into the owners' receive buffers over NVLink ------------------
+    def peers_available(self):
+        mode = os.environ.get('NRPCALC_B200_EXCHANGE', 'peer')
+        if mode != 'peer' or torch.cuda.device_count() < 2:
+            return False
+        return True
+
+    def exchange_fused(self, lo, hi, k, internal_repeats, windows_total, group, phases):
+        """flags + counts -> all-gather of the counts -> peer-store scatter -> barrier -> group the received records.
+        Returns (sent, received) or None when the receive capacity would overflow (caller falls back to NCCL)."""
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        capacity = int(windows_total / world * 1.15) + 65536
+        key = (capacity, k <= 16, self.n_parts, world)
+        if getattr(self, '_peer_key', None) != key:
+            handle = self.ctx.peer_export(capacity, k)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle, group=group)
+            self.ctx.peer_open(handles, rank)
+            self._peer_key = key
+        counts = self.ctx.shard_count(lo, hi, k, internal_repeats, world)
+        mine = torch.as_tensor(counts, device=self.device)
+        matrix = torch.empty(world * world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(matrix, mine, group=group)      # also orders this build after every rank's previous one
+        matrix = matrix.cpu().numpy().reshape(world, world)          # [sender, owner]
+        phases.mark('counts')
+        received = matrix.sum(axis=0)
+        if int(received.max()) > capacity:
+            return None
+        offsets = matrix[:rank].sum(axis=0)
+        self.ctx.shard_scatter_peers(k, offsets)
+        phases.mark('scatter')
+        dist.barrier(group=group)                                    # every peer's stores have landed
+        phases.mark('barrier')
+        self.ctx.shard_group_received(int(received[rank]), k, internal_repeats)
+        return int(counts.sum()), int(received[rank])
+
     def group(self, keys, vals, k, internal_repeats):
         torch.cuda.current_stream(self.device).synchronize()
         self.ctx.shard_group(keys.data_ptr() if keys.numel() else 0, vals.data_ptr() if vals.numel() else 0, keys.numel(), k, internal_repeats)
@@ -138,7 +174,7 @@ def _all_gather_var(tensor, group):
     return torch.cat([out[r * longest:r * longest + sizes[r]] for r in range(world)])
 
 
-def _all_to_all_records(keys, vals, send_counts, group):
+def _all_to_all_records(keys, vals, send_counts, group, phases=None):
     """One all-to-all of the owner-partitioned records.  Returns (recv_keys, recv_vals, recv_counts)."""
     world = dist.get_world_size(group)
     device = keys.device
@@ -146,13 +182,21 @@ def _all_to_all_records(keys, vals, send_counts, group):
     recv = torch.empty(world, dtype=torch.int64, device=device)
     dist.all_to_all_single(recv, send, group=group)
     recv_counts = recv.cpu().numpy()
+    if phases is not None:
+        phases.mark('a2a_counts')
     n_recv = int(recv_counts.sum())
     recv_keys = torch.empty(n_recv, dtype=keys.dtype, device=device)
     recv_vals = torch.empty(n_recv, dtype=vals.dtype, device=device)
     in_splits = [int(x) for x in send_counts]
     out_splits = [int(x) for x in recv_counts]
+    if phases is not None:
+        phases.mark('a2a_alloc')
     dist.all_to_all_single(recv_keys, keys, out_splits, in_splits, group=group)
+    if phases is not None:
+        phases.mark('a2a_keys')
     dist.all_to_all_single(recv_vals, vals, out_splits, in_splits, group=group)
+    if phases is not None:
+        phases.mark('a2a_vals')
     return recv_keys, recv_vals, recv_counts
 
 
@@ -198,11 +242,16 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
     lo, hi = bounds[rank]
 
     phases = _Phases(phase_ms, ops.device)
-    keys, vals, send_counts = ops.extract(lo, hi, k, internal_repeats, world)
-    phases.mark('extract')
-    recv_keys, recv_vals, recv_counts = _all_to_all_records(keys, vals, send_counts, group)
-    phases.mark('all_to_all')
-    ops.group(recv_keys, recv_vals, k, internal_repeats)
+    moved = None
+    if hasattr(ops, 'exchange_fused') and ops.peers_available():
+        moved = ops.exchange_fused(lo, hi, k, internal_repeats, int(windows.sum()), group, phases)
+    if moved is None:
+        keys, vals, send_counts = ops.extract(lo, hi, k, internal_repeats, world)
+        phases.mark('extract')
+        recv_keys, recv_vals, recv_counts = _all_to_all_records(keys, vals, send_counts, group, phases if phase_ms is not None else None)
+        phases.mark('all_to_all')
+        ops.group(recv_keys, recv_vals, k, internal_repeats)
+        moved = (int(np.sum(send_counts)), int(np.sum(recv_counts)))
     phases.mark('group')
     flags_all = _or_reduce_flags(ops, ops.flags(), group)
     ops.set_flags(flags_all)
@@ -215,7 +264,7 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
         ops.merge_edges(_all_gather_var(edge_u, group), _all_gather_var(edge_v, group))   # a pair can come from several owners
     phases.mark('edges')
 
-    stats = {'bounds': bounds, 'sent_here': int(np.sum(send_counts)), 'received_here': int(np.sum(recv_counts))}
+    stats = {'bounds': bounds, 'sent_here': moved[0], 'received_here': moved[1]}
     if not gather_host:
         return {'stats': stats}
 
