@@ -95,7 +95,9 @@ class NativeOps(object):
             dist.all_gather_object(handles, handle, group=group)
             self.ctx.peer_open(handles, rank)
             self._peer_key = key
+        phases.mark('peer_setup')
         counts = self.ctx.shard_count(lo, hi, k, internal_repeats, world)
+        phases.mark('count_kernel')
         mine = torch.as_tensor(counts, device=self.device)
         matrix = torch.empty(world * world, dtype=torch.int64, device=self.device)
         dist.all_gather_into_tensor(matrix, mine, group=group)      # also orders this build after every rank's previous one
@@ -236,15 +238,15 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
     plan = getattr(ops, '_shard_plan', None)
     if plan is None or plan[0] != (id(offsets), n, k, world):
         windows = np.maximum(np.diff(offsets) - k + 1, 0)
-        plan = ((id(offsets), n, k, world), shard_bounds(np.diff(offsets), k, world), windows)
+        plan = ((id(offsets), n, k, world), shard_bounds(np.diff(offsets), k, world), windows, int(windows.sum()))
         ops._shard_plan = plan                     # host-side plan of a staged batch, reused by repeated builds
-    bounds, windows = plan[1], plan[2]
+    bounds, windows, windows_total = plan[1], plan[2], plan[3]
     lo, hi = bounds[rank]
 
     phases = _Phases(phase_ms, ops.device)
     moved = None
     if hasattr(ops, 'exchange_fused') and ops.peers_available():
-        moved = ops.exchange_fused(lo, hi, k, internal_repeats, int(windows.sum()), group, phases)
+        moved = ops.exchange_fused(lo, hi, k, internal_repeats, windows_total, group, phases)
     if moved is None:
         keys, vals, send_counts = ops.extract(lo, hi, k, internal_repeats, world)
         phases.mark('extract')
