@@ -171,7 +171,8 @@ int nrp_shard_finish(nrp_ctx* ctx, int k, int internal_repeats, int want_edges);
 /* shared_keys: canonical k-mers of ALL ranks' groups, any order (host memory, or device memory when keys_on_device != 0);
  * afterwards nrp_result_last_single holds valid entries for the parts of this rank's shard */
 int nrp_shard_last_single(nrp_ctx* ctx, const uint64_t* shared_keys, int64_t n_shared, int k, int keys_on_device);
-/* replace this context's edge list by the distinct union of n gathered (u < v) edges in device memory */
+/* replace this context's edge list by the distinct union of n gathered (u < v) edges in device memory;
+ * with v_dev == NULL, u_dev points to n 64-bit codes (u << 32) | v */
 int nrp_edges_merge(nrp_ctx* ctx, const uint32_t* u_dev, const uint32_t* v_dev, int64_t n);
 /* device pointer + element count of a result array, for zero-copy use by the host layer's collectives */
 #define NRP_D_GROUP_KEYS   0   /* uint64 */

@@ -990,7 +990,7 @@ int nrp_shard_last_single(nrp_ctx* c, const uint64_t* shared_keys, int64_t n_sha
 
 int nrp_edges_merge(nrp_ctx* c, const uint32_t* u_dev, const uint32_t* v_dev, int64_t n) {
   if (!c) return fail(NRP_E_ARG, "null context");
-  if (n < 0 || (n > 0 && (!u_dev || !v_dev))) return fail(NRP_E_ARG, "bad edge arrays");
+  if (n < 0 || (n > 0 && !u_dev)) return fail(NRP_E_ARG, "bad edge arrays");
   CU(cudaSetDevice(c->device));
   c->counts[NRP_C_EDGES] = 0;
   if (n > 0) {
@@ -1002,8 +1002,13 @@ int nrp_edges_merge(nrp_ctx* c, const uint32_t* u_dev, const uint32_t* v_dev, in
     TRY(c->e_codesA.ensure((size_t)8 << log_slots));
     CU(cudaMemsetAsync(c->e_codesA.ptr, 0xff, (size_t)8 << log_slots, c->stream));
     CU(cudaMemsetAsync(c->counters.as<unsigned long long>() + CNT_EDGES, 0, 8, c->stream));
-    NRP_LAUNCH((k_edge_merge<<<grid_for(n, 256), 256, 0, c->stream>>>(u_dev, v_dev, n, c->e_codesA.as<uint64_t>(), log_slots, new_u.as<uint32_t>(),
-                                                                  new_v.as<uint32_t>(), c->counters.as<unsigned long long>() + CNT_EDGES)));
+    if (v_dev)
+      NRP_LAUNCH((k_edge_merge<<<grid_for(n, 256), 256, 0, c->stream>>>(u_dev, v_dev, n, c->e_codesA.as<uint64_t>(), log_slots, new_u.as<uint32_t>(),
+                                                                    new_v.as<uint32_t>(), c->counters.as<unsigned long long>() + CNT_EDGES)));
+    else      // u_dev holds n 64-bit codes (u << 32) | v
+      NRP_LAUNCH((k_edge_merge_codes<<<grid_for(n, 256), 256, 0, c->stream>>>(reinterpret_cast<const uint64_t*>(u_dev), n, c->e_codesA.as<uint64_t>(),
+                                                                          log_slots, new_u.as<uint32_t>(), new_v.as<uint32_t>(),
+                                                                          c->counters.as<unsigned long long>() + CNT_EDGES)));
     CU(cudaGetLastError());
     TRY(edge_set_count(c));
     std::swap(c->e_u, c->e_u_alt); std::swap(c->e_v, c->e_v_alt);

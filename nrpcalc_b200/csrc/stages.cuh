@@ -244,6 +244,13 @@ __global__ void k_edge_pairs(const int64_t* indptr, const uint32_t* members, int
   for (int64_t b = t + 1; b < end; ++b) edge_insert(ida, part_id[members[b]], table, log_slots, out_u, out_v, n_out);
 }
 
+// union of edge codes ((u << 32) | v) gathered from several ranks
+__global__ void k_edge_merge_codes(const uint64_t* codes, int64_t n, uint64_t* table, int log_slots, uint32_t* out_u, uint32_t* out_v,
+                                   unsigned long long* n_out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) edge_insert((uint32_t)(codes[i] >> 32), (uint32_t)codes[i], table, log_slots, out_u, out_v, n_out);
+}
+
 // union of edge lists gathered from several ranks
 __global__ void k_edge_merge(const uint32_t* u, const uint32_t* v, int64_t n, uint64_t* table, int log_slots, uint32_t* out_u, uint32_t* out_v,
                              unsigned long long* n_out) {

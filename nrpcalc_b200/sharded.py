@@ -146,9 +146,10 @@ class NativeOps(object):
         torch.cuda.current_stream(self.device).synchronize()
         self.ctx.shard_last_single(None, k, device_ptr=all_keys.data_ptr() if all_keys.numel() else 0, n=all_keys.numel())
 
-    def merge_edges(self, u, v):
+    def merge_edges(self, codes):
+        """codes: int64 tensor of (u << 32) | v gathered from all ranks"""
         torch.cuda.current_stream(self.device).synchronize()
-        self.ctx.edges_merge(u.data_ptr() if u.numel() else 0, v.data_ptr() if v.numel() else 0, u.numel())
+        self.ctx.edges_merge(codes.data_ptr() if codes.numel() else 0, 0, codes.numel())
 
     def fetch_host(self, want_edges):
         """Host copies of this rank's groups, the flags, this shard's last single windows and the merged edges."""
@@ -159,21 +160,22 @@ class NativeOps(object):
                 'candidates': counts['candidates'], 'oversized': counts['oversized']}
 
 
-def _all_gather_var(tensor, group):
-    """all-gather of 1-D tensors of different lengths (pads to the longest, NCCL needs equal sizes)."""
+def _all_gather_var(tensor, group, extra=0):
+    """all-gather of 1-D tensors of different lengths (pads to the longest, NCCL needs equal sizes).
+    Returns (concatenation in rank order, [(length, extra) per rank]); `extra` is a small integer shipped along."""
     world = dist.get_world_size(group)
-    n = torch.tensor([tensor.numel()], dtype=torch.int64, device=tensor.device)
-    sizes = torch.empty(world, dtype=torch.int64, device=tensor.device)
+    n = torch.tensor([tensor.numel(), int(extra)], dtype=torch.int64, device=tensor.device)
+    sizes = torch.empty(2 * world, dtype=torch.int64, device=tensor.device)
     dist.all_gather_into_tensor(sizes, n, group=group)
-    sizes = sizes.cpu().tolist()
-    longest = max(sizes) if sizes else 0
+    sizes = sizes.cpu().view(world, 2).tolist()
+    longest = max(s[0] for s in sizes) if sizes else 0
     if longest == 0:
-        return tensor.new_empty(0)
-    padded = tensor.new_zeros(longest)
+        return tensor.new_empty(0), [(0, 0)] * world
+    padded = tensor.new_empty(longest)
     padded[:tensor.numel()] = tensor
     out = tensor.new_empty(world * longest)
     dist.all_gather_into_tensor(out, padded, group=group)
-    return torch.cat([out[r * longest:r * longest + sizes[r]] for r in range(world)])
+    return torch.cat([out[r * longest:r * longest + sizes[r][0]] for r in range(world)]), [(int(a), int(b)) for a, b in sizes]
 
 
 def _all_to_all_records(keys, vals, send_counts, group, phases=None):
@@ -260,10 +262,24 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
     phases.mark('flag_reduce')
     group_keys, edge_u, edge_v = ops.finish(k, internal_repeats, want_edges)
     phases.mark('finish')
-    ops.last_single(_all_gather_var(group_keys, group), k)
+    # one variable-length all-gather carries both small results: the shared k-mers and the edge codes
+    n_keys = group_keys.numel()
+    if want_edges:
+        codes = (edge_u.to(torch.int64) << 32) | (edge_v.to(torch.int64) & 0xffffffff)
+        packed = torch.cat([group_keys, codes])
+    else:
+        packed = group_keys
+    gathered_small, sizes_small = _all_gather_var(packed, group, extra=n_keys)
+    all_keys, all_codes = [], []
+    pos = 0
+    for total, nk in sizes_small:
+        all_keys.append(gathered_small[pos:pos + nk])
+        all_codes.append(gathered_small[pos + nk:pos + total])
+        pos += total
+    ops.last_single(torch.cat(all_keys) if all_keys else group_keys, k)
     phases.mark('last_single')
     if want_edges:
-        ops.merge_edges(_all_gather_var(edge_u, group), _all_gather_var(edge_v, group))   # a pair can come from several owners
+        ops.merge_edges(torch.cat(all_codes))                       # a pair can come from several owners
     phases.mark('edges')
 
     stats = {'bounds': bounds, 'sent_here': moved[0], 'received_here': moved[1]}
@@ -307,10 +323,10 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
 
 
 def _or_reduce_flags(ops, flags_dev, group):
-    """Bitwise OR across ranks.  MAX is not OR for multi-bit bytes (2 | 1 = 3 but max = 2), so reduce each flag bit
-    as its own 0/1 byte plane."""
-    if flags_dev.numel() == 0:
-        return flags_dev
-    planes = torch.stack([(flags_dev >> b) & 1 for b in range(3)])
-    dist.all_reduce(planes, op=dist.ReduceOp.MAX, group=group)
-    return (planes[0] | (planes[1] << 1) | (planes[2] << 2)).contiguous()
+    """Combine the per-part flag bytes of all ranks with ONE all-reduce(MAX).
+    MAX equals OR here: the palindrome / background bits of a part are set only by the rank whose shard holds the
+    part, and such a part sends no records, so no other rank can add the repeat bit (value 1) to it; for every
+    other part the only possible values are 0 and 1."""
+    if flags_dev.numel():
+        dist.all_reduce(flags_dev, op=dist.ReduceOp.MAX, group=group)
+    return flags_dev

@@ -100,8 +100,8 @@ class OracleOps(object):
         np.maximum.at(out, part[ok], j[ok].astype(np.int32))
         self.last = out
 
-    def merge_edges(self, u, v):
-        codes = np.unique((u.numpy().astype(np.uint64) << np.uint64(32)) | v.numpy().astype(np.uint32).astype(np.uint64))
+    def merge_edges(self, codes):
+        codes = np.unique(codes.numpy().view(np.uint64))
         self.edges = ((codes >> np.uint64(32)).astype(np.uint32), (codes & np.uint64(0xffffffff)).astype(np.uint32))
 
     def fetch_host(self, want_edges):
