@@ -57,7 +57,7 @@ extern "C" {
 #define NRP_C_EDGES          4  /* unique part-pair edges (-1 when edges were not requested) */
 #define NRP_C_PAIRS          5  /* member pairs expanded before dedupe */
 #define NRP_C_CANDIDATES     6  /* records that survived the in-bucket duplicate filter */
-#define NRP_C_RUNS           7  /* pipeline executions (2 when internal repeats forced a second run) */
+#define NRP_C_RUNS           7  /* passes over slices of the hash space (1 unless the batch exceeds pass_records) */
 #define NRP_C_BUCKETS        8  /* leaf buckets of the radix partition */
 #define NRP_C_OVERSIZED      9  /* leaf buckets larger than the shared-memory filter capacity */
 #define NRP_C_WINDOWS_MAX   10  /* windows of all parts before exclusion */
@@ -90,7 +90,7 @@ int nrp_ctx_destroy(nrp_ctx* ctx);
 int nrp_ctx_device(nrp_ctx* ctx);
 
 /* Tuning knobs used by the tests to force rarely taken paths: name in
- * {"filter_cap", "leaf_target", "max_level_bits", "max_pairs", "no_window_carry", "no_bloom"}; value <= 0 restores the default. */
+ * {"filter_cap", "leaf_target", "max_level_bits", "max_pairs", "no_window_carry", "no_bloom", "pass_records"}; value <= 0 restores the default. */
 int nrp_ctx_set_option(nrp_ctx* ctx, const char* name, int64_t value);
 
 /* Background (replaces the kmerSetDB membership test, kmerSetDB.py:177-207): n canonical K-mers in the

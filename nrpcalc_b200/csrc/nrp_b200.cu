@@ -70,6 +70,18 @@ struct DevBuf {
     cap = want;
     return NRP_OK;
   }
+  // grow to at least `bytes`, keeping the first `keep` bytes
+  int grow_keep(size_t bytes, size_t keep) {
+    if (bytes <= cap) return NRP_OK;
+    void* fresh = nullptr;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&fresh, want);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(NRP_E_OOM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e)); }
+    if (ptr && keep) cudaMemcpy(fresh, ptr, keep, cudaMemcpyDeviceToDevice);
+    if (ptr) cudaFree(ptr);
+    ptr = fresh; cap = want;
+    return NRP_OK;
+  }
   void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
   template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
 };
@@ -105,6 +117,7 @@ struct nrp_ctx {
   int64_t opt_max_pairs = (int64_t)1 << 31;
   int64_t opt_no_window_carry = 0;
   int64_t opt_no_bloom = 0;
+  int64_t opt_pass_records = 210000000;   // more records than this per device are processed in several hash-slice passes
 
   // background
   DevBuf bg_table; int bg_K = 0; int bg_log_slots = 0; int bg_key_bytes = 0; int64_t bg_n = 0;
@@ -120,7 +133,7 @@ struct nrp_ctx {
 
   // pipeline buffers
   DevBuf flags, hist, leaf_off, cursor1, cursor2, seg_off, tile_prefix, counters, scan_scratch, lsd_scratch;
-  DevBuf keysA, valsA, keysB, valsB;
+  DevBuf keysA, valsA, keysB, valsB, cand_keys_buf, cand_vals_buf;
   DevBuf head, head_scan, group_start, valid, valid_scan, mem_cnt, mem_scan, pair_cnt, pair_scan;
   DevBuf g_keys, g_indptr, g_pair_off, g_members, g_first_part, g_first_window, last_single;
   DevBuf e_codesA, e_codesB, e_head, e_head_scan, e_u, e_v, e_u_alt, e_v_alt, shared_keysA, shared_keysB;
@@ -268,7 +281,7 @@ int nrp_ctx_destroy(nrp_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->bg_table, &c->ascii, &c->off, &c->part_id, &c->tile_first, &c->flags, &c->hist, &c->leaf_off, &c->cursor1,
-                   &c->cursor2, &c->seg_off, &c->tile_prefix, &c->counters, &c->scan_scratch, &c->lsd_scratch, &c->keysA, &c->valsA,
+                   &c->cursor2, &c->seg_off, &c->tile_prefix, &c->counters, &c->scan_scratch, &c->lsd_scratch, &c->keysA, &c->valsA, &c->cand_keys_buf, &c->cand_vals_buf,
                    &c->keysB, &c->valsB, &c->head, &c->head_scan, &c->group_start, &c->valid, &c->valid_scan, &c->mem_cnt,
                    &c->mem_scan, &c->pair_cnt, &c->pair_scan, &c->g_keys, &c->g_indptr, &c->g_pair_off, &c->g_members,
                    &c->g_first_part, &c->g_first_window, &c->last_single, &c->e_codesA, &c->e_codesB, &c->e_head, &c->e_head_scan,
@@ -293,6 +306,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "max_pairs") c->opt_max_pairs = value <= 0 ? ((int64_t)1 << 31) : value;
   else if (n == "no_window_carry") c->opt_no_window_carry = value > 0 ? 1 : 0;
   else if (n == "no_bloom") c->opt_no_bloom = value > 0 ? 1 : 0;
+  else if (n == "pass_records") c->opt_pass_records = value <= 0 ? 210000000 : value;
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
   return NRP_OK;
 }
@@ -431,99 +445,130 @@ int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, 
   const int64_t m_max = from_ascii ? c->shard_m_max : n_in;
   const Parts P = parts_view(c);
   unsigned long long* cnt = c->counters.as<unsigned long long>();
-  const int bits = choose_leaf_bits(c, m_max);
+  // passes over disjoint slices of the hash space (1 unless the batch is too large for two split levels)
+  int pass_bits = 0;
+  while (pass_bits < 6 && (m_max >> pass_bits) > c->opt_pass_records) ++pass_bits;
+  const int n_passes = 1 << pass_bits;
+  const int64_t m_pass = (m_max >> pass_bits) + (pass_bits ? (m_max >> (pass_bits + 3)) + (1 << 20) : 0);   // slack: slices are near-uniform
+  const int bits = choose_leaf_bits(c, m_max >> pass_bits);
   const int r1 = std::min<int>(bits, (int)c->opt_max_level_bits);
   const int r2 = bits - r1;
   const uint32_t n_leaf = 1u << bits;
-  c->counts[NRP_C_BUCKETS] = n_leaf;
-  TRY(ensure_record_buffers(c, m_max, sizeof(KeyT)));
-
-  tm.begin(NRP_T_HISTOGRAM);
-  CU(cudaMemsetAsync(c->hist.ptr, 0, 4 * ((size_t)n_leaf + 2), st));
+  c->counts[NRP_C_BUCKETS] = (int64_t)n_leaf * n_passes;
+  TRY(ensure_record_buffers(c, m_pass, sizeof(KeyT)));
   CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * CNT_N, st));
-  if (m_max > 0) {
-    if (from_ascii) {
-      if (bits >= 15) {
-        const unsigned grid = (unsigned)std::min<int64_t>((c->shard_tiles + 1) / 2, (int64_t)c->n_sms);
-        NRP_LAUNCH((k_hist_from_ascii<2><<<grid, 2 * kTileThreads, 4u << bits, st>>>(P, c->flags.as<uint8_t>(), k, bits, 0, c->shard_tiles, c->hist.as<uint32_t>())));
-      } else {
-        const unsigned grid = (unsigned)std::min<int64_t>(c->shard_tiles, (int64_t)c->n_sms * (bits >= 14 ? 2 : 3));
-        NRP_LAUNCH((k_hist_from_ascii<1><<<grid, kTileThreads, 4u << bits, st>>>(P, c->flags.as<uint8_t>(), k, bits, 0, c->shard_tiles, c->hist.as<uint32_t>())));
-      }
-    } else {
-      const unsigned grid = (unsigned)std::min<int64_t>((n_in + 511) / 512, (int64_t)c->n_sms * (bits >= 15 ? 1 : 2));
-      NRP_LAUNCH((k_hist_from_records<KeyT><<<grid, 512, 4u << bits, st>>>(in_keys, n_in, bits, c->hist.as<uint32_t>())));
-    }
-  }
-  exclusive_scan<uint32_t, uint32_t>(c->hist.as<uint32_t>(), c->leaf_off.as<uint32_t>(), n_leaf, c->scan_scratch.as<uint32_t>(), st);
-  NRP_LAUNCH((k_init_cursors<<<grid_for(n_leaf, 256), 256, 0, st>>>(c->leaf_off.as<uint32_t>(), r1, r2, c->cursor1.as<uint32_t>(), c->cursor2.as<uint32_t>())));
+  c->n_records = 0;
+  KeyT* leaf_keys = nullptr; uint32_t* leaf_vals = nullptr; KeyT* free_keys = nullptr; uint32_t* free_vals = nullptr;
+  int64_t cand_so_far = 0;
 
-  tm.begin(NRP_T_SPLIT1);
-  KeyT* leaf_keys = c->keysA.as<KeyT>(); uint32_t* leaf_vals = c->valsA.as<uint32_t>();
-  KeyT* free_keys = c->keysB.as<KeyT>(); uint32_t* free_vals = c->valsB.as<uint32_t>();
-  uint32_t* level1_cursor = r2 > 0 ? c->cursor1.as<uint32_t>() : c->cursor2.as<uint32_t>();
-  if (m_max > 0) {
-    if (from_ascii) {
-      NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-          P, c->flags.as<uint8_t>(), k, r1, 0, c->part_base, c->j_bits, level1_cursor, leaf_keys, leaf_vals, PeerBuffers{}, 0)));
-    } else {
-      // one segment holding all records; level-1 digit = top r1 bits
-      const uint32_t seg[2] = {0u, (uint32_t)n_in};
-      const uint32_t tiles[2] = {0u, (uint32_t)((n_in + kSplitTile - 1) / kSplitTile)};
-      CU(cudaMemcpyAsync(c->seg_off.ptr, seg, sizeof(seg), cudaMemcpyHostToDevice, st));
-      CU(cudaMemcpyAsync(c->tile_prefix.ptr, tiles, sizeof(tiles), cudaMemcpyHostToDevice, st));
-      CU(cudaStreamSynchronize(st));       // the two host arrays live on this stack frame
-      const unsigned grid = (unsigned)std::min<int64_t>(tiles[1], (int64_t)c->n_sms * 4);
-      NRP_LAUNCH((k_split_from_records<KeyT><<<grid, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
-          in_keys, in_vals, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>(), 0, r1, level1_cursor, leaf_keys, leaf_vals)));
+  for (int pass = 0; pass < n_passes; ++pass) {
+    const PassSel sel{64 - kMaxLeafBits - pass_bits, (uint32_t)n_passes - 1u, (uint32_t)pass};
+    tm.begin(NRP_T_HISTOGRAM);
+    CU(cudaMemsetAsync(c->hist.ptr, 0, 4 * ((size_t)n_leaf + 2), st));
+    if (m_max > 0) {
+      if (from_ascii) {
+        if (bits >= 15) {
+          const unsigned grid = (unsigned)std::min<int64_t>((c->shard_tiles + 1) / 2, (int64_t)c->n_sms);
+          NRP_LAUNCH((k_hist_from_ascii<2><<<grid, 2 * kTileThreads, 4u << bits, st>>>(P, c->flags.as<uint8_t>(), k, bits, 0, c->shard_tiles, sel, c->hist.as<uint32_t>())));
+        } else {
+          const unsigned grid = (unsigned)std::min<int64_t>(c->shard_tiles, (int64_t)c->n_sms * (bits >= 14 ? 2 : 3));
+          NRP_LAUNCH((k_hist_from_ascii<1><<<grid, kTileThreads, 4u << bits, st>>>(P, c->flags.as<uint8_t>(), k, bits, 0, c->shard_tiles, sel, c->hist.as<uint32_t>())));
+        }
+      } else {
+        const unsigned grid = (unsigned)std::min<int64_t>((n_in + 511) / 512, (int64_t)c->n_sms * (bits >= 15 ? 1 : 2));
+        NRP_LAUNCH((k_hist_from_records<KeyT><<<grid, 512, 4u << bits, st>>>(in_keys, n_in, bits, sel, c->hist.as<uint32_t>())));
+      }
     }
+    exclusive_scan<uint32_t, uint32_t>(c->hist.as<uint32_t>(), c->leaf_off.as<uint32_t>(), n_leaf, c->scan_scratch.as<uint32_t>(), st);
+    NRP_LAUNCH((k_init_cursors<<<grid_for(n_leaf, 256), 256, 0, st>>>(c->leaf_off.as<uint32_t>(), r1, r2, c->cursor1.as<uint32_t>(), c->cursor2.as<uint32_t>())));
+    int64_t n_pass = m_max;
+    if (n_passes > 1) {
+      // the slice's exact size decides the buffers; its candidates are appended to a dedicated list
+      CU(cudaMemcpyAsync(c->h_counters + 16, c->leaf_off.as<uint32_t>() + n_leaf, 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      n_pass = (int64_t)(uint32_t)c->h_counters[16];
+      TRY(ensure_record_buffers(c, n_pass, sizeof(KeyT)));
+      TRY(c->cand_keys_buf.grow_keep(sizeof(KeyT) * (size_t)(cand_so_far + n_pass + 16), sizeof(KeyT) * (size_t)cand_so_far));
+      TRY(c->cand_vals_buf.grow_keep(4 * (size_t)(cand_so_far + n_pass + 16), 4 * (size_t)cand_so_far));
+    }
+
+    tm.begin(NRP_T_SPLIT1);
+    leaf_keys = c->keysA.as<KeyT>(); leaf_vals = c->valsA.as<uint32_t>();
+    free_keys = c->keysB.as<KeyT>(); free_vals = c->valsB.as<uint32_t>();
+    uint32_t* level1_cursor = r2 > 0 ? c->cursor1.as<uint32_t>() : c->cursor2.as<uint32_t>();
+    if (m_max > 0) {
+      if (from_ascii) {
+        NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+            P, c->flags.as<uint8_t>(), k, r1, 0, c->part_base, c->j_bits, sel, level1_cursor, leaf_keys, leaf_vals, PeerBuffers{}, 0)));
+      } else {
+        // one segment holding all records; level-1 digit = top r1 bits
+        const uint32_t seg[2] = {0u, (uint32_t)n_in};
+        const uint32_t tiles[2] = {0u, (uint32_t)((n_in + kSplitTile - 1) / kSplitTile)};
+        CU(cudaMemcpyAsync(c->seg_off.ptr, seg, sizeof(seg), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->tile_prefix.ptr, tiles, sizeof(tiles), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));       // the two host arrays live on this stack frame
+        const unsigned grid = (unsigned)std::min<int64_t>(tiles[1], (int64_t)c->n_sms * 4);
+        NRP_LAUNCH((k_split_from_records<KeyT><<<grid, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
+            in_keys, in_vals, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>(), 0, r1, sel, level1_cursor, leaf_keys, leaf_vals)));
+      }
+    }
+    if (r2 > 0 && m_max > 0) {
+      tm.begin(NRP_T_SPLIT2);
+      NRP_LAUNCH((k_segment_tiles<<<1, 256, 0, st>>>(c->leaf_off.as<uint32_t>(), r1, r2, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>())));
+      const unsigned grid2 = (unsigned)std::min<int64_t>(n_pass / kSplitTile + (1 << r1), (int64_t)c->n_sms * 4);
+      NRP_LAUNCH((k_split_from_records<KeyT><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
+          leaf_keys, leaf_vals, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>(), r1, r2, PassSel{0, 0u, 0u}, c->cursor2.as<uint32_t>(),
+          free_keys, free_vals)));
+      std::swap(leaf_keys, free_keys); std::swap(leaf_vals, free_vals);
+    }
+    tm.begin(NRP_T_FILTER);
+    KeyT* out_keys = n_passes > 1 ? c->cand_keys_buf.as<KeyT>() : free_keys;
+    uint32_t* out_vals = n_passes > 1 ? c->cand_vals_buf.as<uint32_t>() : free_vals;
+    if (m_max > 0) {
+      // leaves that average <= 2750 records use the half-size variant (two CTAs per SM); larger ones the full one
+      const bool small = ((m_max >> pass_bits) >> bits) <= 2750;
+      const size_t fsm = small ? filter_smem_small<KeyT>() : filter_smem_large<KeyT>();
+      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / (fsm + 18 * 1024)));   // + static smem of the leaf ordering
+      const unsigned fgrid = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * per_sm);
+      const uint32_t cap = (uint32_t)std::min<int64_t>(c->opt_filter_cap, small ? kFilterCapSmall : kFilterCap);
+      uint32_t* n_over = reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED);
+      uint32_t* unsorted = reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED);
+      if (small && !c->opt_no_bloom)
+        NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 4, 2048, 2><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * 2), kFilterThreads,
+                                                                   filter_bloom_smem<KeyT, 4096, 2048>(), st>>>(
+            leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+      else if (!c->opt_no_bloom)
+        NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms), kFilterThreads,
+                                                                   filter_bloom_smem<KeyT, 8192, 4096>(), st>>>(
+            leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+      else if (small)
+        NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItemsSmall, kFilterCapSmall, kFilterStaged><<<fgrid, kFilterThreads, fsm, st>>>(
+            leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+      else
+        NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItems, kFilterCap, false><<<fgrid, kFilterThreads, fsm, st>>>(
+            leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_counters, cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_counters + 16, c->leaf_off.as<uint32_t>() + n_leaf, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cand_so_far = (int64_t)c->h_counters[CNT_CAND];
+    c->n_records += (int64_t)(uint32_t)c->h_counters[16];
   }
-  if (r2 > 0 && m_max > 0) {
-    tm.begin(NRP_T_SPLIT2);
-    NRP_LAUNCH((k_segment_tiles<<<1, 256, 0, st>>>(c->leaf_off.as<uint32_t>(), r1, r2, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>())));
-    const unsigned grid2 = (unsigned)std::min<int64_t>(m_max / kSplitTile + (1 << r1), (int64_t)c->n_sms * 4);
-    NRP_LAUNCH((k_split_from_records<KeyT><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
-        leaf_keys, leaf_vals, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>(), r1, r2, c->cursor2.as<uint32_t>(), free_keys, free_vals)));
-    std::swap(leaf_keys, free_keys); std::swap(leaf_vals, free_vals);
-  }
-  tm.begin(NRP_T_FILTER);
-  if (m_max > 0) {
-    // leaves that average <= 2750 records use the half-size table (two CTAs per SM); larger ones the full table
-    const bool small = (m_max >> bits) <= 2750;
-    const size_t fsm = small ? filter_smem_small<KeyT>() : filter_smem_large<KeyT>();
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / (fsm + 18 * 1024)));   // + static smem of the leaf ordering
-    const unsigned fgrid = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * per_sm);
-    const uint32_t cap = (uint32_t)std::min<int64_t>(c->opt_filter_cap, small ? kFilterCapSmall : kFilterCap);
-    if (small && !c->opt_no_bloom)
-      NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 4, 2048, 2><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * 2), kFilterThreads,
-                                                                 filter_bloom_smem<KeyT, 4096, 2048>(), st>>>(
-          leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, free_keys, free_vals, cnt + CNT_CAND,
-          reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED), reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED))));
-    else if (!c->opt_no_bloom)
-      NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms), kFilterThreads,
-                                                                 filter_bloom_smem<KeyT, 8192, 4096>(), st>>>(
-          leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, free_keys, free_vals, cnt + CNT_CAND,
-          reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED), reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED))));
-    else if (small)
-      NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItemsSmall, kFilterCapSmall, kFilterStaged><<<fgrid, kFilterThreads, fsm, st>>>(
-          leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, free_keys, free_vals, cnt + CNT_CAND,
-          reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED), reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED))));
-    else
-      NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItems, kFilterCap, false><<<fgrid, kFilterThreads, fsm, st>>>(
-          leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, free_keys, free_vals, cnt + CNT_CAND,
-          reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED), reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED))));
-  }
-  CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(c->h_counters, cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(c->h_counters + 16, c->leaf_off.as<uint32_t>() + n_leaf, 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  c->n_cand = (int64_t)c->h_counters[CNT_CAND];
-  c->n_records = (int64_t)(uint32_t)c->h_counters[16];
+  c->n_cand = cand_so_far;
   c->counts[NRP_C_OVERSIZED] = (int64_t)(uint32_t)c->h_counters[CNT_OVERSIZED];
   c->counts[NRP_C_CANDIDATES] = c->n_cand;
+  c->counts[NRP_C_RUNS] = n_passes;
   c->cand_unsorted = (uint32_t)c->h_counters[CNT_UNSORTED] != 0;
-  c->cand_keys = free_keys; c->cand_vals = free_vals;         // candidates; the leaf buffers are free again
-  c->spare_keys = leaf_keys; c->spare_vals = leaf_vals;
+  if (n_passes > 1) {
+    // candidates of all passes live in the dedicated list; the ping-pong buffers serve as scratch of the same size
+    TRY(c->keysA.ensure(sizeof(KeyT) * (size_t)(c->n_cand + 16))); TRY(c->valsA.ensure(4 * (size_t)(c->n_cand + 16)));
+    c->cand_keys = c->cand_keys_buf.ptr; c->cand_vals = c->cand_vals_buf.as<uint32_t>();
+    c->spare_keys = c->keysA.ptr; c->spare_vals = c->valsA.as<uint32_t>();
+  } else {
+    c->cand_keys = free_keys; c->cand_vals = free_vals;         // candidates; the leaf buffers are free again
+    c->spare_keys = leaf_keys; c->spare_vals = leaf_vals;
+  }
   return NRP_OK;
 }
 
@@ -553,7 +598,6 @@ int stage_sort_mark(nrp_ctx* c, int k, int64_t n_parts_total, bool mark_repeats,
     KeyT* sk; uint32_t* sv;
     lsd_sort<KeyT, true>((KeyT*)c->cand_keys, c->cand_vals, (KeyT*)c->spare_keys, c->spare_vals, n, plan, c->lsd_scratch.as<uint32_t>(), st, &sk, &sv);
     if (sk != (KeyT*)c->cand_keys) { std::swap(c->cand_keys, c->spare_keys); std::swap(c->cand_vals, c->spare_vals); }
-    c->counts[NRP_C_RUNS] = 2;      // reported: the fallback sort ran
   }
   tm.begin(NRP_T_GROUP);
   TRY(ensure_group_buffers(c, n));
@@ -807,14 +851,14 @@ int shard_extract_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int internal_r
   CU(cudaMemsetAsync(c->hist.ptr, 0, 4 * 260, st));
   if (c->shard_m_max > 0) {
     const unsigned grid = (unsigned)std::min<int64_t>(c->shard_tiles, (int64_t)c->n_sms * 2);
-    NRP_LAUNCH((k_hist_from_ascii<1><<<grid, kTileThreads, 4u * 256, st>>>(P, c->flags.as<uint8_t>(), k, 8, n_owners, c->shard_tiles, c->hist.as<uint32_t>())));
+    NRP_LAUNCH((k_hist_from_ascii<1><<<grid, kTileThreads, 4u * 256, st>>>(P, c->flags.as<uint8_t>(), k, 8, n_owners, c->shard_tiles, PassSel{0, 0u, 0u}, c->hist.as<uint32_t>())));
   }
   exclusive_scan<uint32_t, uint32_t>(c->hist.as<uint32_t>(), c->cursor1.as<uint32_t>(), n_owners, c->scan_scratch.as<uint32_t>(), st);
   CU(cudaMemcpyAsync(c->h_counters + 32, c->hist.ptr, 4 * (size_t)n_owners, cudaMemcpyDeviceToHost, st));
   tm.begin(NRP_T_SPLIT1);
   if (c->shard_m_max > 0)
     NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, 8, n_owners, 0u, c->j_bits, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>(), PeerBuffers{}, 0)));
+        P, c->flags.as<uint8_t>(), k, 8, n_owners, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>(), PeerBuffers{}, 0)));
   CU(cudaGetLastError());
   tm.finish(c->timings);
   CU(cudaStreamSynchronize(st));
@@ -872,7 +916,7 @@ int shard_count_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int internal_rep
   CU(cudaMemsetAsync(c->hist.ptr, 0, 4 * 260, st));
   if (c->shard_m_max > 0) {
     const unsigned grid = (unsigned)std::min<int64_t>(c->shard_tiles, (int64_t)c->n_sms * 3);
-    NRP_LAUNCH((k_hist_from_ascii<1><<<grid, kTileThreads, 4u * 256, st>>>(P, c->flags.as<uint8_t>(), k, 8, n_owners, c->shard_tiles, c->hist.as<uint32_t>())));
+    NRP_LAUNCH((k_hist_from_ascii<1><<<grid, kTileThreads, 4u * 256, st>>>(P, c->flags.as<uint8_t>(), k, 8, n_owners, c->shard_tiles, PassSel{0, 0u, 0u}, c->hist.as<uint32_t>())));
   }
   CU(cudaMemcpyAsync(c->h_counters + 32, c->hist.ptr, 4 * (size_t)n_owners, cudaMemcpyDeviceToHost, st));
   CU(cudaGetLastError());
@@ -896,7 +940,7 @@ int shard_scatter_impl(nrp_ctx* c, int k, const int64_t* write_offsets) {
   tm.begin(NRP_T_SPLIT1);
   if (c->shard_m_max > 0)
     NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, 8, c->n_owners, 0u, c->j_bits, c->cursor1.as<uint32_t>(), nullptr, nullptr, c->peers, 1)));
+        P, c->flags.as<uint8_t>(), k, 8, c->n_owners, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr, c->peers, 1)));
   CU(cudaGetLastError());
   tm.finish(c->timings);
   CU(cudaStreamSynchronize(st));

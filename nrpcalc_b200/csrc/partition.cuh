@@ -42,6 +42,13 @@ struct PeerBuffers {
   uint32_t* vals[kMaxPeers];
 };
 
+// Batches too large for two split levels are processed in several passes over disjoint slices of the hash space:
+// a record belongs to pass `id` iff the hash bits selected by (shift, mask) equal id.  mask = 0 accepts everything.
+struct PassSel {
+  int shift; uint32_t mask; uint32_t id;
+  __device__ __forceinline__ bool accept(uint64_t hash) const { return (((uint32_t)(hash >> shift)) & mask) == id; }
+};
+
 // digit of a key at one partition level
 struct HashField {            // a bit field of key_hash: leaf-bucket levels
   int shift; uint32_t mask;
@@ -113,7 +120,7 @@ __device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&k
 // on an SM when the 128 KB histogram of 2^15 buckets allows only one CTA).
 template <int HALVES>
 __global__ void __launch_bounds__(kTileThreads * HALVES) k_hist_from_ascii(Parts P, const uint8_t* flags, int k, int bits, int n_owners,
-                                                                          int64_t n_tiles, uint32_t* hist) {
+                                                                          int64_t n_tiles, PassSel sel, uint32_t* hist) {
   extern __shared__ uint32_t s_hist[];
   __shared__ TileStage stages[HALVES];
   const int half = threadIdx.x / kTileThreads, tid = threadIdx.x % kTileThreads;
@@ -129,7 +136,9 @@ __global__ void __launch_bounds__(kTileThreads * HALVES) k_hist_from_ascii(Parts
     __syncthreads();
     if (t < n_tiles)
       tile_windows_blocked<true>(P, stage, tile, k, flags, tid, [&](int, uint64_t canon, uint32_t, uint32_t, bool) {
-        uint32_t bin = n_owners > 0 ? owner_hash(canon) % (uint32_t)n_owners : (uint32_t)(key_hash(canon) >> (64 - bits));
+        const uint64_t h = key_hash(canon);
+        if (!sel.accept(h)) return;
+        uint32_t bin = n_owners > 0 ? owner_hash(canon) % (uint32_t)n_owners : (uint32_t)(h >> (64 - bits));
         atomicAdd(&s_hist[bin], 1u);
       });
   }
@@ -142,13 +151,15 @@ __global__ void __launch_bounds__(kTileThreads * HALVES) k_hist_from_ascii(Parts
 
 // same histogram from records already in HBM (sharded path: after the all-to-all)
 template <typename KeyT>
-__global__ void __launch_bounds__(512) k_hist_from_records(const KeyT* keys, int64_t n, int bits, uint32_t* hist) {
+__global__ void __launch_bounds__(512) k_hist_from_records(const KeyT* keys, int64_t n, int bits, PassSel sel, uint32_t* hist) {
   extern __shared__ uint32_t s_hist[];
   const int nb = 1 << bits;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    atomicAdd(&s_hist[key_hash((uint64_t)keys[i]) >> (64 - bits)], 1u);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t h = key_hash((uint64_t)keys[i]);
+    if (sel.accept(h)) atomicAdd(&s_hist[h >> (64 - bits)], 1u);
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < nb; i += blockDim.x) {
     uint32_t v = s_hist[i];
@@ -163,8 +174,8 @@ __global__ void __launch_bounds__(512) k_hist_from_records(const KeyT* keys, int
 // is then sorting by (part, window), and a group's first record carries the group's rank for free.
 template <typename KeyT>
 __global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, const uint8_t* flags, int k, int r1, int n_owners,
-                                                                  uint32_t part_base, int j_bits, uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals,
-                                                                  PeerBuffers peers, int use_peers) {
+                                                                  uint32_t part_base, int j_bits, PassSel sel, uint32_t* cursor, KeyT* out_keys,
+                                                                  uint32_t* out_vals, PeerBuffers peers, int use_peers) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SplitSmem<KeyT>& s = *reinterpret_cast<SplitSmem<KeyT>*>(smem_raw);
   TileStage& stage = *reinterpret_cast<TileStage*>(smem_raw + sizeof(SplitSmem<KeyT>));
@@ -178,7 +189,9 @@ __global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, cons
 #pragma unroll
   for (int e = 0; e < kSplitItems; ++e) { dr[e] = 0xffffffffu; key[e] = 0; val[e] = 0; }
   tile_windows_blocked<true>(P, stage, tile, k, flags, threadIdx.x, [&](int e, uint64_t canon, uint32_t part, uint32_t j, bool) {
-    uint32_t d = n_owners > 0 ? owner_hash(canon) % (uint32_t)n_owners : (uint32_t)(key_hash(canon) >> (64 - r1));
+    const uint64_t h = key_hash(canon);
+    if (!sel.accept(h)) return;
+    uint32_t d = n_owners > 0 ? owner_hash(canon) % (uint32_t)n_owners : (uint32_t)(h >> (64 - r1));
     uint32_t rank = atomicAdd(&s.cnt[d], 1u);
 #pragma unroll
     for (int q = 0; q < kSplitItems; ++q)
@@ -197,7 +210,7 @@ __global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, cons
 template <typename KeyT>
 __global__ void __launch_bounds__(kSplitThreads) k_split_from_records(const KeyT* __restrict__ in_keys, const uint32_t* __restrict__ in_vals,
                                                                      const uint32_t* seg_off, const uint32_t* tile_prefix, int r1, int r2,
-                                                                     uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals) {
+                                                                     PassSel sel, uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SplitSmem<KeyT>& s = *reinterpret_cast<SplitSmem<KeyT>*>(smem_raw);
   __shared__ uint32_t s_prefix[(1 << kMaxLevelBits) + 1];
@@ -231,8 +244,11 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_from_records(const KeyT
       uint32_t idx = start + threadIdx.x + e * kSplitThreads;
       dr[e] = 0xffffffffu;
       if (idx < end) {
-        uint32_t d = (uint32_t)(key_hash((uint64_t)key[e]) >> (64 - r1 - r2)) & mask;
-        dr[e] = (d << 16) | atomicAdd(&s.cnt[d], 1u);
+        const uint64_t h = key_hash((uint64_t)key[e]);
+        if (sel.accept(h)) {
+          uint32_t d = (uint32_t)(h >> (64 - r1 - r2)) & mask;
+          dr[e] = (d << 16) | atomicAdd(&s.cnt[d], 1u);
+        }
       }
     }
     __syncthreads();

@@ -104,6 +104,12 @@ def test_forced_paths(ctx):
         _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
         ctx.set_option('max_level_bits', 0)
         ctx.set_option('leaf_target', 0)
+        ctx.set_option('pass_records', 9000)          # several passes over slices of the hash space
+        res = _run(ctx, uniq, 13, False)
+        assert res.counts['runs'] > 1
+        _compare(res, uniq, 13, False)
+        _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
+        ctx.set_option('pass_records', 0)
         ctx.set_option('no_bloom', 1)                 # exact table on every record instead of the two-stage filter
         _compare(_run(ctx, uniq, 13, False), uniq, 13, False)
         ctx.set_option('no_bloom', 0)
@@ -114,6 +120,7 @@ def test_forced_paths(ctx):
     finally:
         ctx.set_option('no_window_carry', 0)
         ctx.set_option('no_bloom', 0)
+        ctx.set_option('pass_records', 0)
         ctx.set_option('filter_cap', 0)
         ctx.set_option('leaf_target', 0)
         ctx.set_option('max_level_bits', 0)
