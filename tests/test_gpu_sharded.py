@@ -80,3 +80,52 @@ def test_sharded_equals_single_gpu(tmp_path, k, internal):
         assert _groups(res) == _groups(single)
         assert res['last_single'].tolist() == single['last_single'].tolist()
         assert sorted(zip(res['eu'].tolist(), res['ev'].tolist())) == sorted(zip(single['eu'].tolist(), single['ev'].tolist()))
+
+
+def _finder_worker(rank, world, port, case_name, out_dir):
+    import json
+    import random
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [os.path.dirname(here), here]
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    os.environ['LOCAL_RANK'] = str(rank)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        import nrpcalc_b200
+        from conftest import GOLDEN_CASES
+        case = next(c for c in GOLDEN_CASES if c['name'] == case_name)
+        os.chdir(out_dir)
+        os.makedirs('rank%d' % rank, exist_ok=True)
+        os.chdir('rank%d' % rank)
+        found = {}
+        for vc in ('nrp2', '2apx'):
+            random.seed(7)
+            res = nrpcalc_b200.finder(list(case['parts']), case['Lmax'], internal_repeats=case['internal_repeats'], vercov=vc, verbose=False)
+            found[vc] = list(res.keys())
+        with open(os.path.join(out_dir, 'finder_rank%d.json' % rank), 'w') as fh:
+            json.dump(found, fh)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('case_name', ['planted_s0_L15_ir0', 'random_2000x100_L12', 'short_parts_ir1'])
+def test_finder_under_torch_distributed_matches_reference(tmp_path, case_name):
+    """nrpcalc_b200.finder() called on every rank of an initialised process group: the build is hash-sharded and every
+    rank returns the reference's toolbox."""
+    import json
+    from conftest import GOLDEN_CASES
+    world = 2
+    if _n_gpus() < world:
+        pytest.skip('needs at least 2 GPUs')
+    import torch.multiprocessing as mp
+    mp.spawn(_finder_worker, args=(world, _free_port(), case_name, str(tmp_path)), nprocs=world, join=True)
+    case = next(c for c in GOLDEN_CASES if c['name'] == case_name)
+    for rank in range(world):
+        found = json.load(open(str(tmp_path / ('finder_rank%d.json' % rank))))
+        for vc in ('nrp2', '2apx'):
+            assert found[vc] == case['toolbox'][vc]['7'], (rank, vc)
