@@ -181,6 +181,7 @@ def main():
     ap.add_argument('--reference-parts', type=int, default=20_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-edges', action='store_true')
+    ap.add_argument('--opt', action='append', default=[], help='library tuning knob name=value (nrp_ctx_set_option), repeatable')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else max(args.warmup, 0)
 
@@ -211,6 +212,9 @@ def main():
 
     torch.cuda.set_device(local_rank)
     ctx = _native.Context(local_rank)
+    for item in args.opt:
+        name, value = item.split('=')
+        ctx.set_option(name, int(value))
     ctx.set_background(bg_keys, bg_K)
     # pinned host staging for the e2e leg; device-resident copy for the kernel-only leg
     host_ascii = torch.from_numpy(buf.copy()).pin_memory()
