@@ -280,7 +280,8 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh).get(cfg_name, {}).get(kernel_of[dominant])
-    pipeline_bytes = sum(algo[name] for name in ('histogram', 'split1', 'split2', 'filter')) + (algo['flags'] if stage_avg['flags'] > 0 else 0)
+    # stages that did not run (no histogram pass on the direct path, no flag pass for odd k without background) move no bytes
+    pipeline_bytes = sum(algo[name] for name in ('histogram', 'split1', 'split2', 'filter', 'flags') if stage_avg[name] > 0)
     roofline = {'bound': 'hbm', 'kernel': kernel_of[dominant], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': algo[dominant],
                 'kernel_ms': stage_avg[dominant],
@@ -304,7 +305,8 @@ def main():
                     'ms_per_step': 1e3 * sum(e2e_times) / len(e2e_times), 'path': 'C ABI: nrp_load_parts(host) + nrp_build + result getters'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
             'stage_ms': {name: v / args.steps for name, v in stage_ms.items()},
-            'result': {name: counts[name] for name in ('records', 'excluded', 'groups', 'members', 'edges', 'candidates', 'runs', 'buckets', 'oversized')},
+            'result': {name: counts[name] for name in ('records', 'excluded', 'groups', 'members', 'edges', 'candidates', 'runs', 'buckets', 'oversized',
+                                                       'direct', 'fallbacks')},
             'wall_s_timed_region': wall}
     if not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline(cfg, buf, off, k)

@@ -63,6 +63,8 @@ extern "C" {
 #define NRP_C_WINDOWS_MAX   10  /* windows of all parts before exclusion */
 #define NRP_C_KEY_BYTES     11  /* 4 or 8 */
 #define NRP_C_LAUNCHES      12  /* kernels launched by the build */
+#define NRP_C_DIRECT        13  /* 1: buckets were placed in fixed regions (no histogram pass); 0: exact histogram path */
+#define NRP_C_FALLBACKS     14  /* a fixed region overflowed and the batch was repeated on the exact path */
 #define NRP_N_COUNTS        16
 
 /* indices into nrp_result_timings() (milliseconds, CUDA events on the context's stream) */
@@ -90,7 +92,8 @@ int nrp_ctx_destroy(nrp_ctx* ctx);
 int nrp_ctx_device(nrp_ctx* ctx);
 
 /* Tuning knobs used by the tests to force rarely taken paths: name in
- * {"filter_cap", "leaf_target", "max_level_bits", "max_pairs", "no_window_carry", "no_bloom", "pass_records"}; value <= 0 restores the default. */
+ * {"filter_cap", "leaf_target", "max_level_bits", "max_pairs", "no_window_carry", "no_bloom", "pass_records", "direct"};
+ * value <= 0 restores the default ("direct": 0 forces the exact histogram path, negative restores the default 1). */
 int nrp_ctx_set_option(nrp_ctx* ctx, const char* name, int64_t value);
 
 /* Background (replaces the kmerSetDB membership test, kmerSetDB.py:177-207): n canonical K-mers in the
@@ -154,6 +157,23 @@ int nrp_peer_open(nrp_ctx* ctx, int n_peers, int my_rank, const unsigned char* h
 int nrp_shard_count(nrp_ctx* ctx, int64_t part_lo, int64_t part_hi, int k, int internal_repeats, int n_owners, int64_t* owner_counts);
 int nrp_shard_scatter_peers(nrp_ctx* ctx, int k, const int64_t* write_offsets);
 int nrp_shard_group_received(nrp_ctx* ctx, int64_t n_records, int k, int internal_repeats);
+
+/* Direct fused exchange (default): no count pass and no count exchange.  Every (level-1 bucket, sender) pair owns a FIXED
+ * region of the owner's receive buffer; the extraction kernel stores each record into region (bucket * n_owners + sender) of
+ * its owner over NVLink and finally delivers the regions' end positions.  The owner then continues with its level-2 split
+ * straight from the received regions.  All ranks must call with the same windows_total (k-windows of ALL parts).
+ *   nrp_peer_export_direct    size + allocate the receive buffers for (windows_total, n_owners); three IPC handles
+ *   nrp_peer_open_direct      open all ranks' handles (n_peers x 192 bytes: keys, values, ends)
+ *   nrp_shard_scatter_direct  flags + extraction + scatter into the owners' regions; *overflow != 0: some region was too
+ *                             small (heavily duplicated input) -- every rank must then fall back to the counted exchange
+ *   (host: all-reduce MAX of the overflow flags = barrier)
+ *   nrp_shard_group_direct    level-2 split + filter + ordering of the records this rank received */
+int nrp_peer_export_direct(nrp_ctx* ctx, int64_t windows_total, int n_owners, int k, unsigned char* handles /*192*/);
+int nrp_peer_open_direct(nrp_ctx* ctx, int n_peers, int my_rank, const unsigned char* handles /* n_peers x 192 */);
+int nrp_shard_scatter_direct(nrp_ctx* ctx, int64_t part_lo, int64_t part_hi, int k, int internal_repeats, int n_owners, int* overflow);
+int nrp_shard_group_direct(nrp_ctx* ctx, int k, int internal_repeats);
+/* out[0] = records this rank sent in the last nrp_shard_scatter_direct, out[1] = records it received and partitioned */
+int nrp_shard_moved(nrp_ctx* ctx, int64_t out[2]);
 
 /* run all work of the context on a caller-owned CUDA stream (cudaStream_t), e.g. torch's current stream; NULL
  * restores a private stream */

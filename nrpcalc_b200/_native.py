@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libnrpb200.so')
 N_COUNTS = 16
 N_TIMINGS = 16
 COUNT_NAMES = ('records', 'excluded', 'groups', 'members', 'edges', 'pairs', 'candidates', 'runs', 'buckets',
-               'oversized', 'windows_max', 'key_bytes', 'launches')
+               'oversized', 'windows_max', 'key_bytes', 'launches', 'direct', 'fallbacks')
 TIMING_NAMES = ('total', 'h2d', 'flags', 'histogram', 'split1', 'split2', 'filter', 'sort', 'group', 'edges', 'order')
 
 FLAG_REPEAT, FLAG_PALINDROME, FLAG_BACKGROUND = 1, 2, 4
@@ -65,6 +65,11 @@ def _declare(lib):
         'nrp_shard_scatter_peers': (c_ctx, i32, ptr),
         'nrp_shard_group_received': (c_ctx, i64, i32, i32),
         'nrp_result_device': (c_ctx, i32, ctypes.POINTER(ptr), ctypes.POINTER(i64)),
+        'nrp_peer_export_direct': (c_ctx, i64, i32, i32, ptr),
+        'nrp_peer_open_direct': (c_ctx, i32, i32, ptr),
+        'nrp_shard_scatter_direct': (c_ctx, i64, i64, i32, i32, i32, ctypes.POINTER(i32)),
+        'nrp_shard_group_direct': (c_ctx, i32, i32),
+        'nrp_shard_moved': (c_ctx, ptr),
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -187,6 +192,29 @@ class Context(object):
     def peer_open(self, handles, my_rank):
         blob = np.frombuffer(b''.join(handles), dtype=np.uint8).copy()
         _check(self._lib, self._lib.nrp_peer_open(self._h, len(handles), int(my_rank), _p(blob)))
+
+    def peer_export_direct(self, windows_total, n_owners, k):
+        handles = np.zeros(192, dtype=np.uint8)
+        _check(self._lib, self._lib.nrp_peer_export_direct(self._h, int(windows_total), int(n_owners), int(k), _p(handles)))
+        return handles.tobytes()
+
+    def peer_open_direct(self, handles, my_rank):
+        blob = np.frombuffer(b''.join(handles), dtype=np.uint8).copy()
+        _check(self._lib, self._lib.nrp_peer_open_direct(self._h, len(handles), int(my_rank), _p(blob)))
+
+    def shard_scatter_direct(self, part_lo, part_hi, k, internal_repeats, n_owners):
+        overflow = ctypes.c_int(0)
+        _check(self._lib, self._lib.nrp_shard_scatter_direct(self._h, int(part_lo), int(part_hi), int(k), 1 if internal_repeats else 0,
+                                                             int(n_owners), ctypes.byref(overflow)))
+        return overflow.value != 0
+
+    def shard_group_direct(self, k, internal_repeats):
+        _check(self._lib, self._lib.nrp_shard_group_direct(self._h, int(k), 1 if internal_repeats else 0))
+
+    def shard_moved(self):
+        out = np.zeros(2, dtype=np.int64)
+        _check(self._lib, self._lib.nrp_shard_moved(self._h, _p(out)))
+        return int(out[0]), int(out[1])
 
     def shard_count(self, part_lo, part_hi, k, internal_repeats, n_owners):
         counts = np.zeros(n_owners, dtype=np.int64)

@@ -26,6 +26,16 @@ __host__ __device__ __forceinline__ uint32_t owner_hash(uint64_t key) {
   return (uint32_t)(key >> 32);
 }
 
+// owner GPU of a key on the direct sharded path: a cheap 32-bit mix (fold, two multiplies), independent of the bit
+// fields of key_hash that select the leaf buckets; the top bits of the product are mapped onto [0, n_owners)
+__host__ __device__ __forceinline__ uint32_t owner_of(uint64_t key, uint32_t n_owners) {
+  uint32_t x = ((uint32_t)(key >> 32) * 0x85EBCA6Bu) ^ (uint32_t)key;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 15;
+  x *= 0x9E3779B1u;
+  return (uint32_t)(((uint64_t)x * n_owners) >> 32);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // 2-bit alphabet, MSB-first.  ASCII -> code: (c>>1)&3 gives A0 C1 T2 G3 for both cases; t ^ (t>>1) swaps the
 // last two so that A<C<G<T numerically as in the reference's string comparison, and complement is x^3.

@@ -86,7 +86,9 @@ struct DevBuf {
   template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
 };
 
-enum { CNT_CAND = 0, CNT_REPEAT = 1, CNT_FLAGGED = 2, CNT_WORK = 3, CNT_OVERSIZED = 4, CNT_UNSORTED = 5, CNT_N = 8, CNT_EDGES = 8, CNT_TOTAL = 12 };
+// CNT_EDGES = 8 and CNT_SCATTER_OVERFLOW = 9 live outside the block [0, CNT_N) that every bulk stage clears
+enum { CNT_SCATTER_OVERFLOW = 9, CNT_SENT = 10 };
+enum { CNT_CAND = 0, CNT_REPEAT = 1, CNT_FLAGGED = 2, CNT_WORK = 3, CNT_OVERSIZED = 4, CNT_UNSORTED = 5, CNT_OVERFLOW = 6, CNT_RECORDS = 7, CNT_N = 8, CNT_EDGES = 8, CNT_TOTAL = 12 };
 
 constexpr int kFilterThreads = 1024;
 constexpr int kFilterItems = 8;
@@ -99,7 +101,8 @@ template <typename KeyT> constexpr size_t filter_smem_large() { return (sizeof(K
 template <typename KeyT> constexpr size_t filter_smem_small() {
   return (sizeof(KeyT) + 1) * 2 * (size_t)(kFilterThreads * kFilterItemsSmall) + (kFilterStaged ? (sizeof(KeyT) + 4) * (size_t)kFilterCapSmall : 0);
 }
-constexpr int kMaxLeafBits = 15;                            // 2^15 u32 counters = 128 KB of shared memory
+constexpr int kMaxLeafBits = 15;                            // exact path: 2^15 u32 counters = 128 KB of shared memory
+constexpr int kMaxDirectBits = 2 * kMaxLevelBits;           // direct path: two levels of <= 9 bits
 
 }  // namespace
 
@@ -117,7 +120,8 @@ struct nrp_ctx {
   int64_t opt_max_pairs = (int64_t)1 << 31;
   int64_t opt_no_window_carry = 0;
   int64_t opt_no_bloom = 0;
-  int64_t opt_pass_records = 210000000;   // more records than this per device are processed in several hash-slice passes
+  int64_t opt_pass_records = 210000000;   // exact path: more records than this per device are processed in several hash-slice passes
+  int64_t opt_direct = 1;                 // fixed-region partition without a histogram pass (falls back to the exact path on overflow)
 
   // background
   DevBuf bg_table; int bg_K = 0; int bg_log_slots = 0; int bg_key_bytes = 0; int64_t bg_n = 0;
@@ -132,7 +136,7 @@ struct nrp_ctx {
   int64_t max_id = 0;
 
   // pipeline buffers
-  DevBuf flags, hist, leaf_off, cursor1, cursor2, seg_off, tile_prefix, counters, scan_scratch, lsd_scratch;
+  DevBuf flags, hist, leaf_off, cursor1, cursor2, seg_off, tile_prefix, tile_desc, region_ends, counters, scan_scratch, lsd_scratch;
   DevBuf keysA, valsA, keysB, valsB, cand_keys_buf, cand_vals_buf;
   DevBuf head, head_scan, group_start, valid, valid_scan, mem_cnt, mem_scan, pair_cnt, pair_scan;
   DevBuf g_keys, g_indptr, g_pair_off, g_members, g_first_part, g_first_window, last_single;
@@ -145,6 +149,13 @@ struct nrp_ctx {
   int j_bits = 0;                // > 0: record values are (part << j_bits) | window
   // receive buffers of the fused exchange (exported with CUDA IPC) and the peers' buffers opened here
   DevBuf recv_keys, recv_vals;
+  // direct fused exchange: fixed regions (level-1 bucket x sender) + the end position of every region
+  DevBuf recv_keys_d, recv_vals_d, recv_ends;
+  PeerBuffers peers_d{};
+  uint32_t* peer_ends[kMaxPeers] = {nullptr};
+  int sh_world = 0, sh_r1 = 0, sh_key_bytes = 0, n_peers_d = 0;
+  uint32_t sh_cap1s = 0;
+  int64_t sh_windows_total = 0, sh_m_owner = 0, sh_sent = 0;
   int64_t recv_capacity = 0;
   PeerBuffers peers{};
   int n_peers = 0, my_rank = 0;
@@ -218,15 +229,6 @@ struct StageTimer {
   }
 };
 
-// number of leaf-bucket bits for m records
-int choose_leaf_bits(const nrp_ctx* c, int64_t m) {
-  int bits = 1;
-  while (bits < kMaxLeafBits && (m >> bits) > c->opt_leaf_target) ++bits;
-  int cap_bits = (int)(2 * c->opt_max_level_bits);
-  if (bits > cap_bits) bits = cap_bits;
-  return bits;
-}
-
 template <typename KeyT>
 int configure_kernels(nrp_ctx* c) {
   bool& done = c->configured[sizeof(KeyT) == 4 ? 0 : 1];
@@ -244,7 +246,7 @@ int configure_kernels(nrp_ctx* c) {
                           (int)filter_smem_small<KeyT>()));
   CU(cudaFuncSetAttribute(k_hist_from_ascii<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << kMaxLeafBits));
   CU(cudaFuncSetAttribute(k_hist_from_ascii<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << kMaxLeafBits));
-  CU(cudaFuncSetAttribute(k_hist_from_records<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << kMaxLeafBits));
+  CU(cudaFuncSetAttribute(k_hist_from_tiles<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 << kMaxLeafBits));
   done = true;
   return NRP_OK;
 }
@@ -281,7 +283,7 @@ int nrp_ctx_destroy(nrp_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->bg_table, &c->ascii, &c->off, &c->part_id, &c->tile_first, &c->flags, &c->hist, &c->leaf_off, &c->cursor1,
-                   &c->cursor2, &c->seg_off, &c->tile_prefix, &c->counters, &c->scan_scratch, &c->lsd_scratch, &c->keysA, &c->valsA, &c->cand_keys_buf, &c->cand_vals_buf,
+                   &c->cursor2, &c->seg_off, &c->tile_prefix, &c->tile_desc, &c->region_ends, &c->recv_ends, &c->recv_keys_d, &c->recv_vals_d, &c->counters, &c->scan_scratch, &c->lsd_scratch, &c->keysA, &c->valsA, &c->cand_keys_buf, &c->cand_vals_buf,
                    &c->keysB, &c->valsB, &c->head, &c->head_scan, &c->group_start, &c->valid, &c->valid_scan, &c->mem_cnt,
                    &c->mem_scan, &c->pair_cnt, &c->pair_scan, &c->g_keys, &c->g_indptr, &c->g_pair_off, &c->g_members,
                    &c->g_first_part, &c->g_first_window, &c->last_single, &c->e_codesA, &c->e_codesB, &c->e_head, &c->e_head_scan,
@@ -307,6 +309,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "no_window_carry") c->opt_no_window_carry = value > 0 ? 1 : 0;
   else if (n == "no_bloom") c->opt_no_bloom = value > 0 ? 1 : 0;
   else if (n == "pass_records") c->opt_pass_records = value <= 0 ? 210000000 : value;
+  else if (n == "direct") c->opt_direct = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
   return NRP_OK;
 }
@@ -400,15 +403,18 @@ int64_t windows_in_range(const nrp_ctx* c, int64_t lo, int64_t hi, int k) {
   return m;
 }
 
-int ensure_record_buffers(nrp_ctx* c, int64_t n_records, size_t key_bytes) {
+int ensure_record_buffers(nrp_ctx* c, int64_t n_records, size_t key_bytes, int64_t n_segments = 0) {
   const size_t rec = (size_t)n_records + 16;
   TRY(c->keysA.ensure(key_bytes * rec)); TRY(c->valsA.ensure(4 * rec));
   TRY(c->keysB.ensure(key_bytes * rec)); TRY(c->valsB.ensure(4 * rec));
-  const size_t leaf_max = (size_t)1 << kMaxLeafBits;
-  TRY(c->hist.ensure(4 * (leaf_max + 2))); TRY(c->leaf_off.ensure(4 * (leaf_max + 2)));
-  TRY(c->cursor1.ensure(4 * 260)); TRY(c->cursor2.ensure(4 * (leaf_max + 2)));
-  TRY(c->seg_off.ensure(4 * 260)); TRY(c->tile_prefix.ensure(4 * 260));
-  TRY(c->scan_scratch.ensure(8 * (size_t)scan_scratch_elems((int64_t)leaf_max + 2)));
+  const size_t leaf_max = (size_t)1 << kMaxDirectBits;
+  TRY(c->hist.ensure(4 * (((size_t)1 << kMaxLeafBits) + 2))); TRY(c->leaf_off.ensure(4 * (((size_t)1 << kMaxLeafBits) + 2)));
+  TRY(c->cursor1.ensure(4 * (size_t)(kLevelBuckets * kMaxPeers + 4))); TRY(c->cursor2.ensure(4 * (leaf_max + 2)));
+  TRY(c->region_ends.ensure(4 * (size_t)(kLevelBuckets * kMaxPeers + 4)));
+  const size_t segs = (size_t)std::max<int64_t>(n_segments, kLevelBuckets * kMaxPeers) + 4;
+  TRY(c->seg_off.ensure(4 * segs)); TRY(c->tile_prefix.ensure(4 * segs));
+  TRY(c->tile_desc.ensure(16 * ((size_t)n_records / kSplitTile + segs + 4)));
+  TRY(c->scan_scratch.ensure(8 * (size_t)scan_scratch_elems(((int64_t)1 << kMaxLeafBits) + 2)));
   return NRP_OK;
 }
 
@@ -437,12 +443,173 @@ int stage_flags(nrp_ctx* c, int k, int internal_repeats, StageTimer& tm) {
 }
 
 // ---- stage: records -> leaf buckets -> candidates (records whose key repeats inside its leaf bucket).
-// Source is either the staged part buffer (extraction fused into the first split) or records already in HBM.
+// Where the records of a bulk stage come from: the staged part buffer (extraction fused into the first split), or a
+// segmented record list in HBM -- a flat array (one segment), or the fixed regions the senders of the direct sharded
+// path filled, which are already partitioned by the first r_done hash bits.
 template <typename KeyT>
-int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, int64_t n_in, StageTimer& tm) {
+struct BulkSource {
+  bool from_parts = true;              // records are extracted from the staged parts
+  const KeyT* keys = nullptr;
+  const uint32_t* vals = nullptr;
+  SegExtents ext{nullptr, 0, nullptr, 0};
+  uint32_t n_seg = 0;                  // segments of the record list
+  uint32_t segs_per_bucket = 1;        // pre-partitioned input: consecutive segments that belong to one level-1 bucket
+  int r_done = 0;                      // pre-partitioned input: hash bits already consumed (0 = none)
+  int64_t m_upper = 0;                 // hard upper bound of the number of records (buffer sizes)
+  int64_t m_plan = 0;                  // expected number of records (level planning); 0 = m_upper
+};
+
+struct LevelPlan { int bits, r1, r2; uint32_t cap1, cap2; };
+
+// region size of the direct path: mean + 12.5 % + 8 sigma (Poisson) + slack, a multiple of 4 records
+inline uint32_t region_cap(double mean, int slack) {
+  const double v = mean + mean / 8.0 + 8.0 * std::sqrt(mean) + slack;
+  return (uint32_t)(((int64_t)v + 4) & ~3ll);
+}
+
+// Leaf bits and their division into two levels for m records.  fixed_r1 >= 0: the first level is given (pre-partitioned).
+LevelPlan plan_levels(const nrp_ctx* c, int64_t m, bool direct, int fixed_r1 = -1) {
+  const int lv = (int)c->opt_max_level_bits;
+  int max_bits = std::min(direct ? kMaxDirectBits : kMaxLeafBits, fixed_r1 >= 0 ? fixed_r1 + lv : 2 * lv);
+  int bits = fixed_r1 >= 0 ? std::max(fixed_r1, 1) : 1;
+  while (bits < max_bits && (m >> bits) > c->opt_leaf_target) ++bits;
+  LevelPlan p;
+  p.bits = bits;
+  if (fixed_r1 >= 0) p.r1 = fixed_r1;
+  else p.r1 = bits <= std::min(lv, 8) ? bits : std::min(lv, (bits + 1) / 2);
+  p.r2 = bits - p.r1;
+  p.cap1 = region_cap((double)m / (double)(1ll << p.r1), 1024);
+  p.cap2 = region_cap((double)m / (double)(1ll << bits), 64);
+  return p;
+}
+
+template <typename KeyT>
+int launch_filter(nrp_ctx* c, const KeyT* leaf_keys, const uint32_t* leaf_vals, LeafExtents leaves, uint32_t n_leaf, int bits, int64_t mean_leaf,
+                  KeyT* out_keys, uint32_t* out_vals) {
   cudaStream_t st = c->stream;
-  const bool from_ascii = in_keys == nullptr;
-  const int64_t m_max = from_ascii ? c->shard_m_max : n_in;
+  unsigned long long* cnt = c->counters.as<unsigned long long>();
+  // leaves that average <= 2750 records use the half-size variant (two CTAs per SM); larger ones the full one
+  const bool small = mean_leaf <= 2750;
+  const size_t fsm = small ? filter_smem_small<KeyT>() : filter_smem_large<KeyT>();
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / (fsm + 18 * 1024)));   // + static smem of the leaf ordering
+  const unsigned fgrid = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * per_sm);
+  const uint32_t cap = (uint32_t)std::min<int64_t>(c->opt_filter_cap, small ? kFilterCapSmall : kFilterCap);
+  uint32_t* n_over = reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED);
+  uint32_t* unsorted = reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED);
+  if (small && !c->opt_no_bloom)
+    NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 4, 2048, 2><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * 2), kFilterThreads,
+                                                               filter_bloom_smem<KeyT, 4096, 2048>(), st>>>(
+        leaf_keys, leaf_vals, leaves, n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+  else if (!c->opt_no_bloom)
+    NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms), kFilterThreads,
+                                                               filter_bloom_smem<KeyT, 8192, 4096>(), st>>>(
+        leaf_keys, leaf_vals, leaves, n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+  else if (small)
+    NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItemsSmall, kFilterCapSmall, kFilterStaged><<<fgrid, kFilterThreads, fsm, st>>>(
+        leaf_keys, leaf_vals, leaves, n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+  else
+    NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItems, kFilterCap, false><<<fgrid, kFilterThreads, fsm, st>>>(
+        leaf_keys, leaf_vals, leaves, n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+  CU(cudaGetLastError());
+  return NRP_OK;
+}
+
+// tile descriptors of a segmented record list; the number of tiles ends up in tile_prefix[n_seg] (device)
+int build_tiles(nrp_ctx* c, SegExtents ext, uint32_t n_seg, uint32_t segs_per_bucket, int r_child, unsigned long long* n_records_dev) {
+  cudaStream_t st = c->stream;
+  NRP_LAUNCH((k_segment_scan<<<1, 1024, 0, st>>>(ext, n_seg, c->tile_prefix.as<uint32_t>(), n_records_dev)));
+  NRP_LAUNCH((k_segment_fill<<<(n_seg + 7) / 8, 256, 0, st>>>(ext, n_seg, c->tile_prefix.as<uint32_t>(), segs_per_bucket, r_child, c->tile_desc.as<uint4>())));
+  CU(cudaGetLastError());
+  return NRP_OK;
+}
+
+// Direct path: fixed regions, no histogram.  *overflowed is set when a region was too small (nothing usable was produced).
+template <typename KeyT>
+int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer& tm, bool* overflowed) {
+  cudaStream_t st = c->stream;
+  const bool from_ascii = src.from_parts;
+  const bool prepart = !from_ascii && src.r_done > 0;
+  const int64_t m_max = from_ascii ? c->shard_m_max : (src.m_plan > 0 ? src.m_plan : src.m_upper);
+  const Parts P = parts_view(c);
+  unsigned long long* cnt = c->counters.as<unsigned long long>();
+  uint32_t* overflow = reinterpret_cast<uint32_t*>(cnt + CNT_OVERFLOW);
+  const LevelPlan lp = plan_levels(c, m_max, true, prepart ? src.r_done : -1);
+  const int bits = lp.bits, r1 = lp.r1, r2 = lp.r2;
+  const uint32_t n_leaf = 1u << bits, n_l1 = 1u << r1;
+  *overflowed = false;
+  const int64_t total1 = (r2 > 0 && !prepart) ? (int64_t)n_l1 * lp.cap1 : 0, total2 = (int64_t)n_leaf * lp.cap2;
+  if (std::max(total1, total2) >= 0xffffe000ll || r2 > (int)c->opt_max_level_bits) { *overflowed = true; return NRP_OK; }   // beyond 32-bit record indices: exact path
+  c->counts[NRP_C_BUCKETS] = (int64_t)n_leaf;
+  TRY(ensure_record_buffers(c, std::max<int64_t>(std::max(total1, total2), m_max), sizeof(KeyT), (int64_t)n_l1 * src.segs_per_bucket));
+  CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * CNT_N, st));
+  c->n_records = 0;
+
+  tm.begin(NRP_T_SPLIT1);
+  // level-1 output: buffer A (regions of cap1, or the leaves themselves when there is one level)
+  KeyT* l1_keys = c->keysA.as<KeyT>(); uint32_t* l1_vals = c->valsA.as<uint32_t>();
+  KeyT* l2_keys = c->keysB.as<KeyT>(); uint32_t* l2_vals = c->valsB.as<uint32_t>();
+  NRP_LAUNCH((k_init_region_cursors<<<grid_for(n_leaf, 256), 256, 0, st>>>(c->cursor2.as<uint32_t>(), n_leaf, lp.cap2)));
+  if (r2 > 0 && !prepart)
+    NRP_LAUNCH((k_init_region_cursors<<<grid_for(n_l1, 256), 256, 0, st>>>(c->cursor1.as<uint32_t>(), n_l1, lp.cap1)));
+  uint32_t* level1_cursor = r2 > 0 ? c->cursor1.as<uint32_t>() : c->cursor2.as<uint32_t>();
+  const RegionLimit lim1{r2 > 0 ? lp.cap1 : lp.cap2, 0u, overflow, nullptr};
+  const RegionLimit lim2{lp.cap2, 0u, overflow, nullptr};
+  if (m_max > 0 && !prepart) {
+    if (from_ascii) {
+      NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+          P, c->flags.as<uint8_t>(), k, r1, 0, 0, c->part_base, c->j_bits, PassSel{0, 0u, 0u}, level1_cursor, l1_keys, l1_vals, lim1, PeerBuffers{}, 0)));
+    } else {
+      TRY(build_tiles(c, src.ext, src.n_seg, 0xffffffffu, 0, nullptr));
+      const unsigned grid = (unsigned)std::min<int64_t>(m_max / kSplitTile + src.n_seg, (int64_t)c->n_sms * 4);
+      NRP_LAUNCH((k_split_from_records<KeyT><<<grid, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
+          src.keys, src.vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + src.n_seg, 0, r1, PassSel{0, 0u, 0u}, level1_cursor,
+          l1_keys, l1_vals, lim1)));
+    }
+  }
+  const KeyT* leaf_keys = l1_keys; const uint32_t* leaf_vals = l1_vals;
+  KeyT* out_keys = l2_keys; uint32_t* out_vals = l2_vals;
+  if (r2 > 0 && m_max > 0) {
+    tm.begin(NRP_T_SPLIT2);
+    const KeyT* in_k = prepart ? src.keys : l1_keys; const uint32_t* in_v = prepart ? src.vals : l1_vals;
+    const SegExtents ext = prepart ? src.ext : SegExtents{nullptr, 0, c->cursor1.as<uint32_t>(), lp.cap1};
+    const uint32_t n_seg = prepart ? src.n_seg : n_l1;
+    TRY(build_tiles(c, ext, n_seg, prepart ? src.segs_per_bucket : 1u, r2, cnt + CNT_RECORDS));
+    const unsigned grid2 = (unsigned)std::min<int64_t>(m_max / kSplitTile + n_seg, (int64_t)c->n_sms * 4);
+    NRP_LAUNCH((k_split_from_records<KeyT><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
+        in_k, in_v, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + n_seg, r1, r2, PassSel{0, 0u, 0u}, c->cursor2.as<uint32_t>(),
+        l2_keys, l2_vals, lim2)));
+    leaf_keys = l2_keys; leaf_vals = l2_vals;
+    out_keys = l1_keys; out_vals = l1_vals;                  // level-1 regions are consumed: candidates go there
+  }
+  tm.begin(NRP_T_FILTER);
+  if (m_max > 0) {
+    if (r2 == 0) NRP_LAUNCH((k_region_total<<<1, 1024, 0, st>>>(c->cursor2.as<uint32_t>(), n_leaf, lp.cap2, cnt + CNT_RECORDS)));
+    TRY((launch_filter<KeyT>(c, leaf_keys, leaf_vals, LeafExtents{nullptr, c->cursor2.as<uint32_t>(), lp.cap2}, n_leaf, bits, m_max >> bits,
+                             out_keys, out_vals)));
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(c->h_counters, cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if ((uint32_t)c->h_counters[CNT_OVERFLOW] != 0) { *overflowed = true; return NRP_OK; }
+  c->n_cand = (int64_t)c->h_counters[CNT_CAND];
+  c->n_records = (int64_t)c->h_counters[CNT_RECORDS];
+  c->counts[NRP_C_OVERSIZED] = (int64_t)(uint32_t)c->h_counters[CNT_OVERSIZED];
+  c->counts[NRP_C_CANDIDATES] = c->n_cand;
+  c->counts[NRP_C_RUNS] = 1;
+  c->counts[NRP_C_DIRECT] = 1;
+  c->cand_unsorted = (uint32_t)c->h_counters[CNT_UNSORTED] != 0;
+  c->cand_keys = out_keys; c->cand_vals = out_vals;
+  c->spare_keys = const_cast<KeyT*>(leaf_keys); c->spare_vals = const_cast<uint32_t*>(leaf_vals);
+  return NRP_OK;
+}
+
+// Exact path: leaf sizes from a histogram pass, tight offsets; several passes over slices of the hash space when the
+// batch is too large for two split levels of a 2^15-entry shared-memory histogram.
+template <typename KeyT>
+int stage_bulk_exact(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer& tm) {
+  cudaStream_t st = c->stream;
+  const bool from_ascii = src.from_parts;
+  const int64_t m_max = from_ascii ? c->shard_m_max : src.m_upper;
   const Parts P = parts_view(c);
   unsigned long long* cnt = c->counters.as<unsigned long long>();
   // passes over disjoint slices of the hash space (1 unless the batch is too large for two split levels)
@@ -450,16 +617,20 @@ int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, 
   while (pass_bits < 6 && (m_max >> pass_bits) > c->opt_pass_records) ++pass_bits;
   const int n_passes = 1 << pass_bits;
   const int64_t m_pass = (m_max >> pass_bits) + (pass_bits ? (m_max >> (pass_bits + 3)) + (1 << 20) : 0);   // slack: slices are near-uniform
-  const int bits = choose_leaf_bits(c, m_max >> pass_bits);
-  const int r1 = std::min<int>(bits, (int)c->opt_max_level_bits);
-  const int r2 = bits - r1;
+  const int64_t m_plan = from_ascii || src.m_plan <= 0 ? m_max : src.m_plan;
+  const LevelPlan lp = plan_levels(c, m_plan >> pass_bits, false);
+  const int bits = lp.bits, r1 = lp.r1, r2 = lp.r2;
   const uint32_t n_leaf = 1u << bits;
   c->counts[NRP_C_BUCKETS] = (int64_t)n_leaf * n_passes;
-  TRY(ensure_record_buffers(c, m_pass, sizeof(KeyT)));
+  c->counts[NRP_C_DIRECT] = 0;
+  TRY(ensure_record_buffers(c, m_pass, sizeof(KeyT), src.n_seg));
   CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * CNT_N, st));
   c->n_records = 0;
   KeyT* leaf_keys = nullptr; uint32_t* leaf_vals = nullptr; KeyT* free_keys = nullptr; uint32_t* free_vals = nullptr;
   int64_t cand_so_far = 0;
+  const RegionLimit no_limit{0u, 0u, nullptr, nullptr};
+  const uint32_t* n_src_tiles = c->tile_prefix.as<uint32_t>() + src.n_seg;
+  const int64_t src_tiles_max = m_max / kSplitTile + src.n_seg;
 
   for (int pass = 0; pass < n_passes; ++pass) {
     const PassSel sel{64 - kMaxLeafBits - pass_bits, (uint32_t)n_passes - 1u, (uint32_t)pass};
@@ -475,8 +646,10 @@ int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, 
           NRP_LAUNCH((k_hist_from_ascii<1><<<grid, kTileThreads, 4u << bits, st>>>(P, c->flags.as<uint8_t>(), k, bits, 0, c->shard_tiles, sel, c->hist.as<uint32_t>())));
         }
       } else {
-        const unsigned grid = (unsigned)std::min<int64_t>((n_in + 511) / 512, (int64_t)c->n_sms * (bits >= 15 ? 1 : 2));
-        NRP_LAUNCH((k_hist_from_records<KeyT><<<grid, 512, 4u << bits, st>>>(in_keys, n_in, bits, sel, c->hist.as<uint32_t>())));
+        // the source's tile list is rebuilt every pass: the level-2 split below reuses the descriptor buffer
+        TRY(build_tiles(c, src.ext, src.n_seg, 0xffffffffu, 0, nullptr));
+        const unsigned grid = (unsigned)std::min<int64_t>(src_tiles_max, (int64_t)c->n_sms * (bits >= 15 ? 1 : 2));
+        NRP_LAUNCH((k_hist_from_tiles<KeyT><<<grid, 512, 4u << bits, st>>>(src.keys, c->tile_desc.as<uint4>(), n_src_tiles, bits, sel, c->hist.as<uint32_t>())));
       }
     }
     exclusive_scan<uint32_t, uint32_t>(c->hist.as<uint32_t>(), c->leaf_off.as<uint32_t>(), n_leaf, c->scan_scratch.as<uint32_t>(), st);
@@ -487,7 +660,7 @@ int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, 
       CU(cudaMemcpyAsync(c->h_counters + 16, c->leaf_off.as<uint32_t>() + n_leaf, 4, cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
       n_pass = (int64_t)(uint32_t)c->h_counters[16];
-      TRY(ensure_record_buffers(c, n_pass, sizeof(KeyT)));
+      TRY(ensure_record_buffers(c, std::max(n_pass, m_pass), sizeof(KeyT), src.n_seg));
       TRY(c->cand_keys_buf.grow_keep(sizeof(KeyT) * (size_t)(cand_so_far + n_pass + 16), sizeof(KeyT) * (size_t)cand_so_far));
       TRY(c->cand_vals_buf.grow_keep(4 * (size_t)(cand_so_far + n_pass + 16), 4 * (size_t)cand_so_far));
     }
@@ -499,55 +672,29 @@ int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, 
     if (m_max > 0) {
       if (from_ascii) {
         NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-            P, c->flags.as<uint8_t>(), k, r1, 0, c->part_base, c->j_bits, sel, level1_cursor, leaf_keys, leaf_vals, PeerBuffers{}, 0)));
+            P, c->flags.as<uint8_t>(), k, r1, 0, 0, c->part_base, c->j_bits, sel, level1_cursor, leaf_keys, leaf_vals, no_limit, PeerBuffers{}, 0)));
       } else {
-        // one segment holding all records; level-1 digit = top r1 bits
-        const uint32_t seg[2] = {0u, (uint32_t)n_in};
-        const uint32_t tiles[2] = {0u, (uint32_t)((n_in + kSplitTile - 1) / kSplitTile)};
-        CU(cudaMemcpyAsync(c->seg_off.ptr, seg, sizeof(seg), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(c->tile_prefix.ptr, tiles, sizeof(tiles), cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));       // the two host arrays live on this stack frame
-        const unsigned grid = (unsigned)std::min<int64_t>(tiles[1], (int64_t)c->n_sms * 4);
+        const unsigned grid = (unsigned)std::min<int64_t>(src_tiles_max, (int64_t)c->n_sms * 4);
         NRP_LAUNCH((k_split_from_records<KeyT><<<grid, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
-            in_keys, in_vals, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>(), 0, r1, sel, level1_cursor, leaf_keys, leaf_vals)));
+            src.keys, src.vals, c->tile_desc.as<uint4>(), n_src_tiles, 0, r1, sel, level1_cursor, leaf_keys, leaf_vals, no_limit)));
       }
     }
     if (r2 > 0 && m_max > 0) {
       tm.begin(NRP_T_SPLIT2);
-      NRP_LAUNCH((k_segment_tiles<<<1, 256, 0, st>>>(c->leaf_off.as<uint32_t>(), r1, r2, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>())));
-      const unsigned grid2 = (unsigned)std::min<int64_t>(n_pass / kSplitTile + (1 << r1), (int64_t)c->n_sms * 4);
+      const uint32_t n_l1 = 1u << r1;
+      TRY(build_tiles(c, SegExtents{c->leaf_off.as<uint32_t>(), r2, nullptr, 0u}, n_l1, 1u, r2, nullptr));
+      const unsigned grid2 = (unsigned)std::min<int64_t>(n_pass / kSplitTile + n_l1, (int64_t)c->n_sms * 4);
       NRP_LAUNCH((k_split_from_records<KeyT><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
-          leaf_keys, leaf_vals, c->seg_off.as<uint32_t>(), c->tile_prefix.as<uint32_t>(), r1, r2, PassSel{0, 0u, 0u}, c->cursor2.as<uint32_t>(),
-          free_keys, free_vals)));
+          leaf_keys, leaf_vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + n_l1, r1, r2, PassSel{0, 0u, 0u}, c->cursor2.as<uint32_t>(),
+          free_keys, free_vals, no_limit)));
       std::swap(leaf_keys, free_keys); std::swap(leaf_vals, free_vals);
     }
     tm.begin(NRP_T_FILTER);
     KeyT* out_keys = n_passes > 1 ? c->cand_keys_buf.as<KeyT>() : free_keys;
     uint32_t* out_vals = n_passes > 1 ? c->cand_vals_buf.as<uint32_t>() : free_vals;
-    if (m_max > 0) {
-      // leaves that average <= 2750 records use the half-size variant (two CTAs per SM); larger ones the full one
-      const bool small = ((m_max >> pass_bits) >> bits) <= 2750;
-      const size_t fsm = small ? filter_smem_small<KeyT>() : filter_smem_large<KeyT>();
-      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / (fsm + 18 * 1024)));   // + static smem of the leaf ordering
-      const unsigned fgrid = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * per_sm);
-      const uint32_t cap = (uint32_t)std::min<int64_t>(c->opt_filter_cap, small ? kFilterCapSmall : kFilterCap);
-      uint32_t* n_over = reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED);
-      uint32_t* unsorted = reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED);
-      if (small && !c->opt_no_bloom)
-        NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 4, 2048, 2><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * 2), kFilterThreads,
-                                                                   filter_bloom_smem<KeyT, 4096, 2048>(), st>>>(
-            leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
-      else if (!c->opt_no_bloom)
-        NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms), kFilterThreads,
-                                                                   filter_bloom_smem<KeyT, 8192, 4096>(), st>>>(
-            leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
-      else if (small)
-        NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItemsSmall, kFilterCapSmall, kFilterStaged><<<fgrid, kFilterThreads, fsm, st>>>(
-            leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
-      else
-        NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItems, kFilterCap, false><<<fgrid, kFilterThreads, fsm, st>>>(
-            leaf_keys, leaf_vals, c->leaf_off.as<uint32_t>(), n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
-    }
+    if (m_max > 0)
+      TRY((launch_filter<KeyT>(c, leaf_keys, leaf_vals, LeafExtents{c->leaf_off.as<uint32_t>(), nullptr, 0u}, n_leaf, bits,
+                               (m_plan >> pass_bits) >> bits, out_keys, out_vals)));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_counters, cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(c->h_counters + 16, c->leaf_off.as<uint32_t>() + n_leaf, 4, cudaMemcpyDeviceToHost, st));
@@ -569,6 +716,30 @@ int stage_bulk(nrp_ctx* c, int k, const KeyT* in_keys, const uint32_t* in_vals, 
     c->cand_keys = free_keys; c->cand_vals = free_vals;         // candidates; the leaf buffers are free again
     c->spare_keys = leaf_keys; c->spare_vals = leaf_vals;
   }
+  return NRP_OK;
+}
+
+template <typename KeyT>
+int stage_bulk(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer& tm) {
+  if (c->opt_direct) {
+    bool overflowed = false;
+    TRY((stage_bulk_direct<KeyT>(c, k, src, tm, &overflowed)));
+    if (!overflowed) return NRP_OK;
+    c->counts[NRP_C_FALLBACKS] += 1;
+  }
+  return stage_bulk_exact<KeyT>(c, k, src, tm);
+}
+
+// a flat record array as a one-segment source (the two offsets live in the context's seg_off buffer)
+template <typename KeyT>
+int flat_source(nrp_ctx* c, const KeyT* keys, const uint32_t* vals, int64_t n, BulkSource<KeyT>* out) {
+  TRY(c->seg_off.ensure(4 * (size_t)(kLevelBuckets * kMaxPeers + 4)));
+  uint32_t* h = reinterpret_cast<uint32_t*>(c->h_counters + 40);     // pinned: no need to wait for the copy
+  h[0] = 0u; h[1] = (uint32_t)n;
+  CU(cudaMemcpyAsync(c->seg_off.ptr, h, 8, cudaMemcpyHostToDevice, c->stream));
+  out->from_parts = false; out->keys = keys; out->vals = vals;
+  out->ext = SegExtents{c->seg_off.as<uint32_t>(), 0, nullptr, 0u};
+  out->n_seg = 1; out->segs_per_bucket = 1; out->r_done = 0; out->m_upper = n;
   return NRP_OK;
 }
 
@@ -818,7 +989,7 @@ int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   c->counts[NRP_C_WINDOWS_MAX] = c->shard_m_max;
   StageTimer tm(c);
   TRY(stage_flags(c, k, internal_repeats, tm));
-  TRY((stage_bulk<KeyT>(c, k, nullptr, nullptr, 0, tm)));
+  TRY((stage_bulk<KeyT>(c, k, BulkSource<KeyT>{}, tm)));
   TRY((stage_sort_mark<KeyT>(c, k, c->n_parts, !internal_repeats, tm)));
   if (!internal_repeats && c->n_repeat_records > 0) TRY((stage_compact<KeyT>(c, tm)));
   TRY((stage_groups<KeyT>(c, tm)));
@@ -858,7 +1029,8 @@ int shard_extract_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int internal_r
   tm.begin(NRP_T_SPLIT1);
   if (c->shard_m_max > 0)
     NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, 8, n_owners, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>(), PeerBuffers{}, 0)));
+        P, c->flags.as<uint8_t>(), k, 8, n_owners, 1, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>(),
+        RegionLimit{0u, 0u, nullptr, nullptr}, PeerBuffers{}, 0)));
   CU(cudaGetLastError());
   tm.finish(c->timings);
   CU(cudaStreamSynchronize(st));
@@ -875,7 +1047,9 @@ int shard_group_impl(nrp_ctx* c, const void* keys, const uint32_t* vals, int64_t
   if (n >= 0xffffe000ll) return fail(NRP_E_UNSUPPORTED, "too many records for 32-bit record indices");
   // the received buffers are borrowed: they are consumed by the first split only
   StageTimer tm(c);
-  TRY((stage_bulk<KeyT>(c, k, (const KeyT*)keys, vals, n, tm)));
+  BulkSource<KeyT> src;
+  TRY((flat_source<KeyT>(c, (const KeyT*)keys, vals, n, &src)));
+  TRY((stage_bulk<KeyT>(c, k, src, tm)));
   TRY((stage_sort_mark<KeyT>(c, k, c->n_parts, !internal_repeats, tm)));
   tm.finish(c->timings);
   return NRP_OK;
@@ -910,7 +1084,7 @@ int shard_count_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int internal_rep
   TRY(stage_flags(c, k, internal_repeats, tm));
   TRY(c->hist.ensure(4 * (((size_t)1 << kMaxLeafBits) + 2)));
   TRY(c->scan_scratch.ensure(8 * (size_t)scan_scratch_elems(((int64_t)1 << kMaxLeafBits) + 2)));
-  TRY(c->cursor1.ensure(4 * 260));
+  TRY(c->cursor1.ensure(4 * (size_t)(kLevelBuckets * kMaxPeers + 4)));
   const Parts P = parts_view(c);
   tm.begin(NRP_T_HISTOGRAM);
   CU(cudaMemsetAsync(c->hist.ptr, 0, 4 * 260, st));
@@ -940,10 +1114,109 @@ int shard_scatter_impl(nrp_ctx* c, int k, const int64_t* write_offsets) {
   tm.begin(NRP_T_SPLIT1);
   if (c->shard_m_max > 0)
     NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, 8, c->n_owners, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr, c->peers, 1)));
+        P, c->flags.as<uint8_t>(), k, 8, c->n_owners, 1, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr,
+        RegionLimit{0u, 0u, nullptr, nullptr}, c->peers, 1)));
   CU(cudaGetLastError());
   tm.finish(c->timings);
   CU(cudaStreamSynchronize(st));
+  return NRP_OK;
+}
+
+// ---- direct fused exchange ----------------------------------------------------------------------------------
+// cursors and region ends of the sender: digit d = (owner << r1) | bucket writes into region (bucket * world + rank) of its owner
+__global__ void k_init_owner_cursors(uint32_t* cursor, uint32_t* ends, uint32_t n_digits, int r1, uint32_t world, uint32_t rank, uint32_t cap) {
+  const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_digits) return;
+  const uint32_t b = d & ((1u << r1) - 1u);
+  const uint32_t region = b * world + rank;
+  cursor[d] = region * cap;
+  ends[d] = (region + 1u) * cap;
+}
+
+// deliver the final cursors to the owners: ends of region (bucket * world + rank) in owner o's table (peer stores)
+struct PeerEnds { uint32_t* ptr[kMaxPeers]; };
+__global__ void k_push_region_ends(const uint32_t* cursor, uint32_t n_digits, int r1, uint32_t world, uint32_t rank, uint32_t cap, PeerEnds dst,
+                                   unsigned long long* n_sent) {
+  const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_digits) return;
+  const uint32_t b = d & ((1u << r1) - 1u), o = d >> r1;
+  const uint32_t region = b * world + rank;
+  uint32_t e = cursor[d];
+  if (e > (region + 1u) * cap) e = (region + 1u) * cap;
+  dst.ptr[o][region] = e;
+  atomicAdd(n_sent, (unsigned long long)(e - region * cap));
+}
+
+// level-1 bits of the direct sharded path: world * 2^r1 digits must fit one split level
+int direct_shard_plan(nrp_ctx* c, int64_t windows_total, int world, int* r1_out, uint32_t* cap1s_out, int64_t* m_owner_out) {
+  const int64_t m_owner = windows_total / world + (windows_total / world) / 32 + 4096;
+  int max_r1 = 0;
+  while ((world << (max_r1 + 1)) <= kLevelBuckets) ++max_r1;
+  LevelPlan p = plan_levels(c, m_owner, true);
+  int r1 = std::min(p.r1, max_r1);
+  if (r1 < 1) r1 = 1;
+  if ((world << r1) > kLevelBuckets) return fail(NRP_E_UNSUPPORTED, "%d owners do not fit one split level", world);
+  *r1_out = r1;
+  *cap1s_out = region_cap((double)windows_total / ((double)world * world * (double)(1 << r1)), 256);
+  *m_owner_out = m_owner;
+  return NRP_OK;
+}
+
+template <typename KeyT>
+int shard_scatter_direct_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int internal_repeats, int n_owners, int* overflow_out) {
+  TRY(configure_kernels<KeyT>(c));
+  cudaStream_t st = c->stream;
+  c->shard_lo = lo; c->shard_hi = hi; c->n_owners = n_owners;
+  const int64_t byte_lo = c->h_off[lo], byte_hi = c->h_off[hi];
+  c->shard_tile_lo = byte_lo / kTileBytes;
+  c->shard_tiles = hi > lo && byte_hi > byte_lo ? (byte_hi + kTileBytes - 1) / kTileBytes - c->shard_tile_lo : 0;
+  c->shard_m_max = windows_in_range(c, lo, hi, k);
+  begin_job(c, k, sizeof(KeyT), 0);
+  c->counts[NRP_C_WINDOWS_MAX] = c->shard_m_max;
+  StageTimer tm(c);
+  TRY(stage_flags(c, k, internal_repeats, tm));
+  TRY(c->cursor1.ensure(4 * (size_t)(kLevelBuckets * kMaxPeers + 4)));
+  TRY(c->region_ends.ensure(4 * (size_t)(kLevelBuckets * kMaxPeers + 4)));
+  const Parts P = parts_view(c);
+  unsigned long long* cnt = c->counters.as<unsigned long long>();
+  tm.begin(NRP_T_SPLIT1);
+  const uint32_t nd = (uint32_t)n_owners << c->sh_r1;
+  CU(cudaMemsetAsync(cnt + CNT_SCATTER_OVERFLOW, 0, 16, st));
+  NRP_LAUNCH((k_init_owner_cursors<<<grid_for(nd, 256), 256, 0, st>>>(c->cursor1.as<uint32_t>(), c->region_ends.as<uint32_t>(), nd, c->sh_r1,
+                                                                    (uint32_t)n_owners, (uint32_t)c->my_rank, c->sh_cap1s)));
+  if (c->shard_m_max > 0)
+    NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+        P, c->flags.as<uint8_t>(), k, c->sh_r1, n_owners, 2, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr,
+        RegionLimit{c->sh_cap1s, 0u, reinterpret_cast<uint32_t*>(cnt + CNT_SCATTER_OVERFLOW), c->region_ends.as<uint32_t>()}, c->peers_d, 1)));
+  PeerEnds pe;
+  for (int o = 0; o < kMaxPeers; ++o) pe.ptr[o] = c->peer_ends[o];
+  NRP_LAUNCH((k_push_region_ends<<<grid_for(nd, 256), 256, 0, st>>>(c->cursor1.as<uint32_t>(), nd, c->sh_r1, (uint32_t)n_owners, (uint32_t)c->my_rank, c->sh_cap1s, pe,
+                                                                  cnt + CNT_SENT)));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(c->h_counters + 44, cnt + CNT_SCATTER_OVERFLOW, 16, cudaMemcpyDeviceToHost, st));
+  tm.finish(c->timings);
+  CU(cudaStreamSynchronize(st));
+  *overflow_out = (uint32_t)c->h_counters[44] != 0 ? 1 : 0;
+  c->sh_sent = (int64_t)c->h_counters[45];
+  return NRP_OK;
+}
+
+template <typename KeyT>
+int shard_group_direct_impl(nrp_ctx* c, int k, int internal_repeats) {
+  TRY(configure_kernels<KeyT>(c));
+  StageTimer tm(c);
+  BulkSource<KeyT> src;
+  src.from_parts = false;
+  src.keys = c->recv_keys_d.as<KeyT>(); src.vals = c->recv_vals_d.as<uint32_t>();
+  src.n_seg = (uint32_t)c->sh_world << c->sh_r1;
+  src.ext = SegExtents{nullptr, 0, c->recv_ends.as<uint32_t>(), c->sh_cap1s};
+  src.segs_per_bucket = (uint32_t)c->sh_world;
+  src.r_done = c->sh_r1;
+  src.m_upper = (int64_t)src.n_seg * c->sh_cap1s;
+  src.m_plan = c->sh_m_owner;
+  TRY((stage_bulk<KeyT>(c, k, src, tm)));
+  TRY((stage_sort_mark<KeyT>(c, k, c->n_parts, !internal_repeats, tm)));
+  tm.finish(c->timings);
   return NRP_OK;
 }
 
@@ -1144,6 +1417,88 @@ int nrp_shard_group_received(nrp_ctx* c, int64_t n_records, int k, int internal_
   if (!c) return fail(NRP_E_ARG, "null context");
   if (n_records < 0 || n_records > c->recv_capacity) return fail(NRP_E_ARG, "record count exceeds the receive capacity");
   return nrp_shard_group(c, c->recv_keys.ptr, c->recv_vals.as<uint32_t>(), n_records, k, internal_repeats);
+}
+
+int nrp_peer_export_direct(nrp_ctx* c, int64_t windows_total, int n_owners, int k, unsigned char* handles) {
+  if (!c || !handles) return fail(NRP_E_ARG, "null argument");
+  if (n_owners < 1 || n_owners > kMaxPeers || windows_total < 0) return fail(NRP_E_ARG, "bad arguments");
+  if (k < 1 || k > 32) return fail(NRP_E_UNSUPPORTED, "k=%d outside [1, 32]", k);
+  CU(cudaSetDevice(c->device));
+  int r1 = 0; uint32_t cap1s = 0; int64_t m_owner = 0;
+  TRY(direct_shard_plan(c, windows_total, n_owners, &r1, &cap1s, &m_owner));
+  const int64_t n_regions = (int64_t)n_owners << r1;
+  const int64_t capacity = n_regions * cap1s;
+  if (capacity >= 0xffffe000ll) return fail(NRP_E_UNSUPPORTED, "receive regions exceed 32-bit record indices");
+  const size_t key_bytes = k <= 16 ? 4 : 8;
+  TRY(c->recv_keys_d.ensure(key_bytes * (size_t)(capacity + 16)));
+  TRY(c->recv_vals_d.ensure(4 * (size_t)(capacity + 16)));
+  TRY(c->recv_ends.ensure(4 * (size_t)(kLevelBuckets * kMaxPeers + 4)));
+  c->sh_world = n_owners; c->sh_r1 = r1; c->sh_cap1s = cap1s; c->sh_key_bytes = (int)key_bytes;
+  c->sh_windows_total = windows_total; c->sh_m_owner = m_owner;
+  cudaIpcMemHandle_t h[3];
+  CU(cudaIpcGetMemHandle(&h[0], c->recv_keys_d.ptr));
+  CU(cudaIpcGetMemHandle(&h[1], c->recv_vals_d.ptr));
+  CU(cudaIpcGetMemHandle(&h[2], c->recv_ends.ptr));
+  for (int i = 0; i < 3; ++i) memcpy(handles + 64 * i, &h[i], 64);
+  return NRP_OK;
+}
+
+int nrp_peer_open_direct(nrp_ctx* c, int n_peers, int my_rank, const unsigned char* handles) {
+  if (!c || !handles) return fail(NRP_E_ARG, "null argument");
+  if (n_peers < 1 || n_peers > kMaxPeers || my_rank < 0 || my_rank >= n_peers) return fail(NRP_E_ARG, "bad peer count");
+  if (n_peers != c->sh_world) return fail(NRP_E_STATE, "nrp_peer_export_direct was called for %d owners", c->sh_world);
+  CU(cudaSetDevice(c->device));
+  auto open_one = [&](const unsigned char* h, void** out) -> int {
+    for (size_t i = 0; i < c->opened_handles.size(); ++i)
+      if (memcmp(c->opened_handles[i].data(), h, 64) == 0) { *out = c->opened_ptrs[i]; return NRP_OK; }
+    cudaIpcMemHandle_t handle;
+    memcpy(&handle, h, 64);
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, handle, cudaIpcMemLazyEnablePeerAccess));
+    c->opened_handles.emplace_back(h, h + 64);
+    c->opened_ptrs.push_back(ptr);
+    *out = ptr;
+    return NRP_OK;
+  };
+  for (int p = 0; p < n_peers; ++p) {
+    if (p == my_rank) {
+      c->peers_d.keys[p] = c->recv_keys_d.ptr; c->peers_d.vals[p] = c->recv_vals_d.as<uint32_t>(); c->peer_ends[p] = c->recv_ends.as<uint32_t>();
+      continue;
+    }
+    void* pk = nullptr; void* pv = nullptr; void* pe = nullptr;
+    TRY(open_one(handles + (size_t)p * 192, &pk));
+    TRY(open_one(handles + (size_t)p * 192 + 64, &pv));
+    TRY(open_one(handles + (size_t)p * 192 + 128, &pe));
+    c->peers_d.keys[p] = pk; c->peers_d.vals[p] = reinterpret_cast<uint32_t*>(pv); c->peer_ends[p] = reinterpret_cast<uint32_t*>(pe);
+  }
+  c->n_peers_d = n_peers; c->my_rank = my_rank;
+  return NRP_OK;
+}
+
+int nrp_shard_scatter_direct(nrp_ctx* c, int64_t part_lo, int64_t part_hi, int k, int internal_repeats, int n_owners, int* overflow) {
+  if (!c || !overflow) return fail(NRP_E_ARG, "null argument");
+  if (!c->have_parts) return fail(NRP_E_STATE, "nrp_load_parts has not been called");
+  if (k < 1 || k > 32) return fail(NRP_E_UNSUPPORTED, "k=%d outside [1, 32]", k);
+  if (part_lo < 0 || part_hi < part_lo || part_hi > c->n_parts) return fail(NRP_E_ARG, "bad shard range");
+  if (c->n_peers_d != n_owners || c->sh_world != n_owners) return fail(NRP_E_STATE, "direct peers are not open for %d owners", n_owners);
+  if (c->sh_key_bytes != (k <= 16 ? 4 : 8)) return fail(NRP_E_STATE, "receive buffers were exported for another key width");
+  CU(cudaSetDevice(c->device));
+  return k <= 16 ? shard_scatter_direct_impl<uint32_t>(c, part_lo, part_hi, k, internal_repeats, n_owners, overflow)
+                 : shard_scatter_direct_impl<uint64_t>(c, part_lo, part_hi, k, internal_repeats, n_owners, overflow);
+}
+
+int nrp_shard_group_direct(nrp_ctx* c, int k, int internal_repeats) {
+  if (!c) return fail(NRP_E_ARG, "null context");
+  if (!c->have_parts) return fail(NRP_E_STATE, "nrp_load_parts has not been called");
+  if (c->n_peers_d < 1) return fail(NRP_E_STATE, "direct peers are not open");
+  CU(cudaSetDevice(c->device));
+  return k <= 16 ? shard_group_direct_impl<uint32_t>(c, k, internal_repeats) : shard_group_direct_impl<uint64_t>(c, k, internal_repeats);
+}
+
+int nrp_shard_moved(nrp_ctx* c, int64_t out[2]) {
+  if (!c || !out) return fail(NRP_E_ARG, "null argument");
+  out[0] = c->sh_sent; out[1] = c->n_records;
+  return NRP_OK;
 }
 
 int nrp_result_counts(nrp_ctx* c, int64_t out[NRP_N_COUNTS]) {

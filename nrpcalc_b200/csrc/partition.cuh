@@ -5,12 +5,18 @@
 // the table only to learn which canonical k-mers occur in more than one (window, part) record; every key
 // that occurs once contributes nothing but the singleton tuple (id,).  So instead of sorting all M records
 // we (1) scatter them by the top bits of a multiplicative hash into buckets of a few thousand records
-// (two levels of <= 8 bits, ranks taken with shared-memory atomics -- order inside a bucket is irrelevant),
-// (2) load every bucket into shared memory once, insert its keys into an open-addressing table and keep
-// only the records whose key was seen twice.  What survives is sorted and grouped by the small sort.
+// (two levels of <= 9 bits, ranks taken with shared-memory atomics -- order inside a bucket is irrelevant),
+// (2) load every bucket into shared memory once and keep only the records whose key was seen twice.
+// What survives is ordered inside the filter (or by the small fallback sort) and grouped.
 //
-// HBM traffic per record (key K_b bytes + 4-byte part index): ASCII twice, one write by split1, one read and
-// one write by split2, one read by the filter  ->  2*L/W + 4*(K_b+4) bytes, against
+// Two ways to place the buckets:
+//   direct (default)  every bucket owns a FIXED region of mean + 12.5 % + 8 sigma records; no histogram pass.  The hash
+//                     spreads random k-mers evenly, so a region overflows only on heavily duplicated input; the overflow
+//                     is detected (nothing is written past a region) and the batch is repeated on the exact path.
+//   exact             leaf sizes from a histogram pass over the parts (k_hist_from_ascii), tight offsets.
+//
+// HBM traffic per record on the direct path (key K_b bytes + 4-byte value): ASCII once, one write by split1, one read
+// and one write by split2, one read by the filter  ->  L/W + 4*(K_b+4) bytes, against
 // L/W + (2*ceil(2k/8)+4)*(K_b+4) + K_b for the LSD formulation in SURVEY.md 8d.
 #pragma once
 #include "common.cuh"
@@ -20,16 +26,18 @@ namespace nrp {
 constexpr int kSplitThreads = kTileThreads;     // 512
 constexpr int kSplitItems = 8;
 constexpr int kSplitTile = kSplitThreads * kSplitItems;   // 4096 records staged per CTA
-constexpr int kMaxLevelBits = 8;
+constexpr int kMaxLevelBits = 9;
+constexpr int kLevelBuckets = 1 << kMaxLevelBits;
 constexpr int kLeafSortCap = 1024;              // candidates of one leaf that are ordered inside the filter kernel
+static_assert(kLevelBuckets <= kSplitThreads, "one thread per bucket in split_scatter");
 
 template <typename KeyT>
 struct alignas(16) SplitSmem {
   KeyT keys[kSplitTile];
   uint32_t vals[kSplitTile];
-  uint32_t cnt[1 << kMaxLevelBits];
-  uint32_t base[1 << kMaxLevelBits];
-  uint32_t gbase[1 << kMaxLevelBits];
+  uint32_t cnt[kLevelBuckets];
+  uint32_t base[kLevelBuckets];
+  uint32_t gbase[kLevelBuckets];
   uint32_t warp_sums[40];
   uint32_t total;
 };
@@ -54,20 +62,42 @@ struct HashField {            // a bit field of key_hash: leaf-bucket levels
   int shift; uint32_t mask;
   __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return (uint32_t)(key_hash(key) >> shift) & mask; }
 };
-struct OwnerDigit {           // owner GPU of a key (sharded path)
+struct OwnerDigit {           // owner GPU of a key (sharded path, exact exchange)
   uint32_t n_owners;
   __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return owner_hash(key) % n_owners; }
 };
+struct OwnerBucketDigit {     // direct sharded path: (owner, top r1 bits of the hash) = owner * 2^r1 + level-1 bucket
+  uint32_t n_owners; int r1;
+  __device__ __forceinline__ uint32_t operator()(uint64_t key) const {
+    return (owner_of(key, n_owners) << r1) | (r1 ? (uint32_t)(key_hash(key) >> (64 - r1)) : 0u);
+  }
+};
+
+// Direct mode (no histogram pass): bucket i of a level owns the FIXED region [i * cap, (i + 1) * cap) of the output buffer
+// and cursor[i] starts at i * cap.  A claim that would cross the region's end sets *overflow and writes nothing; the
+// host then repeats the batch on the exact (histogram) path.  cap == 0: exact offsets, nothing to check.
+// With peers (direct sharded path) cursor[d] indexes the OWNER's buffer and the region of digit d = (owner, bucket) is
+// region_of_digit = (bucket * n_senders + my_rank): the limit is passed as explicit per-digit ends.
+struct RegionLimit {
+  uint32_t cap;          // records per region, 0 = unchecked
+  uint32_t first;        // index of the region that cursor[0] belongs to
+  uint32_t* overflow;
+  const uint32_t* ends;  // optional: explicit end of digit d's region (overrides first/cap arithmetic)
+};
+constexpr uint32_t kNoSpace = 0xffffffffu;
 
 // Steps shared by both split kernels once every thread holds its records, digits and in-bucket ranks:
 // scan the bucket counts, claim global space for each non-empty bucket with one atomic per (tile, bucket),
 // reorder the tile through shared memory and write each bucket's run contiguously.
+// peer_shift >= 0: the buffers of digit d are those of owner d >> peer_shift (peer stores over NVLink).
 template <typename KeyT, typename DigitFn>
 __device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&key)[kSplitItems], const uint32_t (&val)[kSplitItems],
                                               const uint32_t (&dr)[kSplitItems], int nb, DigitFn digit_of,
-                                              uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals, const PeerBuffers* peers = nullptr) {
+                                              uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals, RegionLimit lim,
+                                              const PeerBuffers* peers = nullptr, int peer_shift = 0) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  // exclusive scan of cnt[0..nb) by the first nb threads (nb <= 256 <= blockDim)
+  constexpr int kWarps = kSplitThreads / 32;
+  // exclusive scan of cnt[0..nb) by the first nb threads (nb <= kLevelBuckets <= blockDim)
   uint32_t c = (int)threadIdx.x < nb ? s.cnt[threadIdx.x] : 0u;
   uint32_t inc = c;
 #pragma unroll
@@ -75,18 +105,30 @@ __device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&k
     uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
     if (lane >= d) inc += o;
   }
-  if (lane == 31 && wid < 8) s.warp_sums[wid] = inc;
+  if (lane == 31) s.warp_sums[wid] = inc;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t run = 0;
+  if (threadIdx.x < 32) {
+    uint32_t t = lane < kWarps ? s.warp_sums[lane] : 0u;
+    uint32_t tin = t;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { uint32_t t = s.warp_sums[w]; s.warp_sums[w] = run; run += t; }
-    s.total = run;
+    for (int d = 1; d < kWarps; d <<= 1) {
+      uint32_t o = __shfl_up_sync(0xffffffffu, tin, d);
+      if (lane >= d) tin += o;
+    }
+    if (lane < kWarps) s.warp_sums[lane] = tin - t;
+    if (lane == kWarps - 1) s.total = tin;
   }
   __syncthreads();
   if ((int)threadIdx.x < nb) {
     s.base[threadIdx.x] = s.warp_sums[wid] + inc - c;
-    if (c) s.gbase[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], c);
+    if (c) {
+      uint32_t g = atomicAdd(&cursor[threadIdx.x], c);
+      if (lim.cap) {
+        const uint64_t end = lim.ends ? (uint64_t)lim.ends[threadIdx.x] : (uint64_t)(lim.first + threadIdx.x + 1u) * lim.cap;
+        if ((uint64_t)g + c > end) { g = kNoSpace; *lim.overflow = 1u; }
+      }
+      s.gbase[threadIdx.x] = g;
+    }
   }
   __syncthreads();
 #pragma unroll
@@ -102,10 +144,13 @@ __device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&k
   for (uint32_t i = threadIdx.x; i < total; i += kSplitThreads) {
     KeyT kx = s.keys[i];
     uint32_t d = digit_of((uint64_t)kx);
-    uint32_t dst = s.gbase[d] + (i - s.base[d]);
-    if (peers) {                                   // bucket d lives in owner d's receive buffer (peer store over NVLink)
-      reinterpret_cast<KeyT*>(peers->keys[d])[dst] = kx;
-      peers->vals[d][dst] = s.vals[i];
+    const uint32_t gb = s.gbase[d];
+    if (gb == kNoSpace) continue;
+    uint32_t dst = gb + (i - s.base[d]);
+    if (peers) {                                   // digit d lives in its owner's receive buffer (peer store over NVLink)
+      const uint32_t o = d >> peer_shift;
+      reinterpret_cast<KeyT*>(peers->keys[o])[dst] = kx;
+      peers->vals[o][dst] = s.vals[i];
     } else {
       out_keys[dst] = kx;
       out_vals[dst] = s.vals[i];
@@ -113,7 +158,7 @@ __device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&k
   }
 }
 
-// ---- histogram of leaf buckets straight from the part buffer ------------------------------------------
+// ---- histogram of leaf buckets straight from the part buffer (exact path) ---------------------------------
 // hist has 2^bits entries (bits <= 15): leaf bucket = top `bits` bits of key_hash(canonical k-mer).
 // Persistent CTAs accumulate in shared memory and flush once.
 // HALVES groups of kTileThreads threads work on different tiles and share the histogram (HALVES = 2 keeps 32 warps
@@ -149,16 +194,21 @@ __global__ void __launch_bounds__(kTileThreads * HALVES) k_hist_from_ascii(Parts
   }
 }
 
-// same histogram from records already in HBM (sharded path: after the all-to-all)
+// same histogram over a segmented record list given by tile descriptors {first record, end, -, -}
 template <typename KeyT>
-__global__ void __launch_bounds__(512) k_hist_from_records(const KeyT* keys, int64_t n, int bits, PassSel sel, uint32_t* hist) {
+__global__ void __launch_bounds__(512) k_hist_from_tiles(const KeyT* keys, const uint4* tile_desc, const uint32_t* n_tiles_ptr, int bits,
+                                                        PassSel sel, uint32_t* hist) {
   extern __shared__ uint32_t s_hist[];
   const int nb = 1 << bits;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint64_t h = key_hash((uint64_t)keys[i]);
-    if (sel.accept(h)) atomicAdd(&s_hist[h >> (64 - bits)], 1u);
+  const uint32_t n_tiles = *n_tiles_ptr;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint4 d4 = __ldg(tile_desc + tile);
+    for (uint32_t i = d4.x + threadIdx.x; i < d4.y; i += blockDim.x) {
+      const uint64_t h = key_hash((uint64_t)keys[i]);
+      if (sel.accept(h)) atomicAdd(&s_hist[h >> (64 - bits)], 1u);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < nb; i += blockDim.x) {
@@ -167,21 +217,49 @@ __global__ void __launch_bounds__(512) k_hist_from_records(const KeyT* keys, int
   }
 }
 
+// cursors of the direct path: cursor[i] = i * cap (region starts)
+__global__ void k_init_region_cursors(uint32_t* cursor, uint32_t n, uint32_t cap) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cursor[i] = i * cap;
+}
+
+// records held by n fixed regions: sum of min(cursor[i], (i+1)*cap) - i*cap  (one CTA)
+__global__ void __launch_bounds__(1024) k_region_total(const uint32_t* cursor, uint32_t n, uint32_t cap, unsigned long long* out) {
+  __shared__ unsigned long long warp_sums[32];
+  unsigned long long sum = 0;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t lo = i * cap;
+    uint32_t e = cursor[i];
+    if (e > lo + cap) e = lo + cap;
+    sum += e - lo;
+  }
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_sums[w];
+    *out = t;
+  }
+}
+
 // ---- level 1: extraction fused with the first split ------------------------------------------------------
-// digit = top r1 bits of the hash (or, with by_owner, owner_hash % n_owners for the sharded path).
+// mode 0  digit = top r1 bits of the hash
+// mode 1  digit = owner_hash % n_owners (sharded path, exact exchange); with use_peers the runs go to the owners' buffers
+// mode 2  digit = (owner_of, top r1 bits) (direct sharded path): stored into the owner's region of this (bucket, sender)
 // cursor[d] must hold the start offset of bucket d and is advanced atomically.
 // Record value = part index, or (part << j_bits) | window index when both fit 32 bits (j_bits > 0): sorting by value
 // is then sorting by (part, window), and a group's first record carries the group's rank for free.
 template <typename KeyT>
-__global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, const uint8_t* flags, int k, int r1, int n_owners,
+__global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, const uint8_t* flags, int k, int r1, int n_owners, int mode,
                                                                   uint32_t part_base, int j_bits, PassSel sel, uint32_t* cursor, KeyT* out_keys,
-                                                                  uint32_t* out_vals, PeerBuffers peers, int use_peers) {
+                                                                  uint32_t* out_vals, RegionLimit lim, PeerBuffers peers, int use_peers) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SplitSmem<KeyT>& s = *reinterpret_cast<SplitSmem<KeyT>*>(smem_raw);
   TileStage& stage = *reinterpret_cast<TileStage*>(smem_raw + sizeof(SplitSmem<KeyT>));
   const int64_t tile = P.tile_lo + blockIdx.x;
-  const int nb = n_owners > 0 ? n_owners : (1 << r1);
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s.cnt[i] = 0;
+  const int nb = mode == 0 ? (1 << r1) : mode == 1 ? n_owners : (n_owners << r1);
+  for (int i = threadIdx.x; i < kLevelBuckets; i += blockDim.x) s.cnt[i] = 0;
   tile_load(P, tile, stage, threadIdx.x);
   __syncthreads();
   KeyT key[kSplitItems];
@@ -191,42 +269,42 @@ __global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, cons
   tile_windows_blocked<true>(P, stage, tile, k, flags, threadIdx.x, [&](int e, uint64_t canon, uint32_t part, uint32_t j, bool) {
     const uint64_t h = key_hash(canon);
     if (!sel.accept(h)) return;
-    uint32_t d = n_owners > 0 ? owner_hash(canon) % (uint32_t)n_owners : (uint32_t)(h >> (64 - r1));
+    uint32_t d;
+    if (mode == 0) d = (uint32_t)(h >> (64 - r1));
+    else if (mode == 1) d = owner_hash(canon) % (uint32_t)n_owners;
+    else d = (owner_of(canon, (uint32_t)n_owners) << r1) | (r1 ? (uint32_t)(h >> (64 - r1)) : 0u);
     uint32_t rank = atomicAdd(&s.cnt[d], 1u);
 #pragma unroll
     for (int q = 0; q < kSplitItems; ++q)
       if (q == e) { key[q] = (KeyT)canon; val[q] = ((part_base + part) << j_bits) | (j_bits ? j : 0u); dr[q] = (d << 16) | rank; }
   });
   __syncthreads();
-  if (n_owners > 0)
-    split_scatter<KeyT>(s, key, val, dr, nb, OwnerDigit{(uint32_t)n_owners}, cursor, out_keys, out_vals, use_peers ? &peers : nullptr);
+  if (mode == 0)
+    split_scatter<KeyT>(s, key, val, dr, nb, HashField{64 - r1, (1u << r1) - 1u}, cursor, out_keys, out_vals, lim);
+  else if (mode == 1)
+    split_scatter<KeyT>(s, key, val, dr, nb, OwnerDigit{(uint32_t)n_owners}, cursor, out_keys, out_vals, lim, use_peers ? &peers : nullptr, 0);
   else
-    split_scatter<KeyT>(s, key, val, dr, nb, HashField{64 - r1, (1u << r1) - 1u}, cursor, out_keys, out_vals);
+    split_scatter<KeyT>(s, key, val, dr, nb, OwnerBucketDigit{(uint32_t)n_owners, r1}, cursor, out_keys, out_vals, lim, &peers, r1);
 }
 
 // ---- level 2 (or level 1 when the records are already in HBM): segmented split of records ---------------
-// Segment b = level-1 bucket b = records [seg_off[b], seg_off[b+1]); its tiles are numbered from tile_prefix[b].
-// Leaf bucket id = top (r1 + r2) bits of the hash; cursor has 2^(r1+r2) entries.
+// The input is a list of segments (level-1 buckets, or the per-sender parts of them on the sharded path); every
+// segment is cut into tiles of kSplitTile records and each tile has a descriptor {first record, end, index of the
+// first child cursor}.  Persistent CTAs walk the tile list; the next tile's descriptor is fetched one tile ahead.
+// Child bucket = hash bits [64 - r_done - r2, 64 - r_done).
 template <typename KeyT>
 __global__ void __launch_bounds__(kSplitThreads) k_split_from_records(const KeyT* __restrict__ in_keys, const uint32_t* __restrict__ in_vals,
-                                                                     const uint32_t* seg_off, const uint32_t* tile_prefix, int r1, int r2,
-                                                                     PassSel sel, uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals) {
+                                                                     const uint4* __restrict__ tile_desc, const uint32_t* n_tiles_ptr,
+                                                                     int r_done, int r2, PassSel sel, uint32_t* cursor, KeyT* out_keys,
+                                                                     uint32_t* out_vals, RegionLimit lim) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SplitSmem<KeyT>& s = *reinterpret_cast<SplitSmem<KeyT>*>(smem_raw);
-  __shared__ uint32_t s_prefix[(1 << kMaxLevelBits) + 1];
-  const int n_seg = 1 << r1;
-  for (int i = threadIdx.x; i <= n_seg; i += blockDim.x) s_prefix[i] = tile_prefix[i];
-  __syncthreads();
-  const uint32_t n_tiles = s_prefix[n_seg];
+  const uint32_t n_tiles = *n_tiles_ptr;
+  uint4 next = blockIdx.x < n_tiles ? __ldg(tile_desc + blockIdx.x) : make_uint4(0, 0, 0, 0);
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    int lo = 0, hi = n_seg;                       // last segment with tile_prefix <= tile
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (s_prefix[mid] <= tile) lo = mid; else hi = mid;
-    }
-    const uint32_t seg = (uint32_t)lo;
-    const uint32_t start = seg_off[seg] + (tile - s_prefix[seg]) * kSplitTile;
-    const uint32_t end = min(start + (uint32_t)kSplitTile, seg_off[seg + 1]);
+    const uint4 d4 = next;
+    if (tile + gridDim.x < n_tiles) next = __ldg(tile_desc + tile + gridDim.x);
+    const uint32_t start = d4.x, end = d4.y, child0 = d4.z;
     for (int i = threadIdx.x; i < (1 << r2); i += blockDim.x) s.cnt[i] = 0;
     __syncthreads();
     KeyT key[kSplitItems];
@@ -246,34 +324,125 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_from_records(const KeyT
       if (idx < end) {
         const uint64_t h = key_hash((uint64_t)key[e]);
         if (sel.accept(h)) {
-          uint32_t d = (uint32_t)(h >> (64 - r1 - r2)) & mask;
+          uint32_t d = (uint32_t)(h >> (64 - r_done - r2)) & mask;
           dr[e] = (d << 16) | atomicAdd(&s.cnt[d], 1u);
         }
       }
     }
     __syncthreads();
-    split_scatter<KeyT>(s, key, val, dr, 1 << r2, HashField{64 - r1 - r2, mask}, cursor + ((size_t)seg << r2), out_keys, out_vals);
+    RegionLimit tile_lim = lim;
+    tile_lim.first = child0;
+    split_scatter<KeyT>(s, key, val, dr, 1 << r2, HashField{64 - r_done - r2, mask}, cursor + child0, out_keys, out_vals, tile_lim);
     __syncthreads();
   }
 }
 
-// tiles per segment -> tile_prefix (n_seg + 1 entries), n_seg <= 256: one CTA
-__global__ void k_segment_tiles(const uint32_t* leaf_off, int r1, int r2, uint32_t* seg_off, uint32_t* tile_prefix) {
-  __shared__ uint32_t tiles[256];
-  const int n_seg = 1 << r1;
-  if ((int)threadIdx.x < n_seg) {
-    uint32_t a = leaf_off[(size_t)threadIdx.x << r2], b = leaf_off[(size_t)(threadIdx.x + 1) << r2];
-    seg_off[threadIdx.x] = a;
-    tiles[threadIdx.x] = (b - a + kSplitTile - 1) / kSplitTile;
-    if ((int)threadIdx.x == n_seg - 1) seg_off[n_seg] = b;
+// Extents of the segments a segmented split reads.
+//   exact   segment g = records [leaf_off[g << shift], leaf_off[(g + 1) << shift])
+//   direct  segment g = records [g * cap, min(ends[g], (g + 1) * cap))   (ends = final cursors of the previous level, or
+//           the end positions the senders delivered on the sharded path)
+struct SegExtents {
+  const uint32_t* leaf_off; int shift;
+  const uint32_t* ends; uint32_t cap;
+  __device__ __forceinline__ void get(uint32_t g, uint32_t& a, uint32_t& b) const {
+    if (cap) {
+      a = g * cap;
+      b = ends[g];
+      if (b > a + cap) b = a + cap;
+      if (b < a) b = a;
+    } else {
+      a = leaf_off[(size_t)g << shift];
+      b = leaf_off[(size_t)(g + 1) << shift];
+    }
+  }
+};
+
+// tiles per segment -> tile_prefix (n_seg + 1 entries) and the total number of records in *n_records.  One CTA.
+__global__ void __launch_bounds__(1024) k_segment_scan(SegExtents ext, uint32_t n_seg, uint32_t* tile_prefix, unsigned long long* n_records) {
+  __shared__ uint32_t warp_sums[33];
+  __shared__ unsigned long long rec_sums[32];
+  const uint32_t per = (n_seg + blockDim.x - 1) / blockDim.x;
+  const uint32_t g0 = threadIdx.x * per, g1 = min(g0 + per, n_seg);
+  uint32_t tiles = 0;
+  unsigned long long recs = 0;
+  for (uint32_t g = g0; g < g1; ++g) {
+    uint32_t a, b;
+    ext.get(g, a, b);
+    tiles += (b - a + kSplitTile - 1) / kSplitTile;
+    recs += b - a;
+  }
+  // block exclusive scan of `tiles`
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = tiles;
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  for (int d = 16; d > 0; d >>= 1) recs += __shfl_down_sync(0xffffffffu, recs, d);
+  if (lane == 31) warp_sums[wid] = inc;
+  if (lane == 0) rec_sums[wid] = recs;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = warp_sums[lane], winc = w;
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += o;
+    }
+    warp_sums[lane] = winc - w;
+    if (lane == 31) warp_sums[32] = winc;
   }
   __syncthreads();
+  uint32_t run = warp_sums[wid] + inc - tiles;
+  for (uint32_t g = g0; g < g1; ++g) {
+    uint32_t a, b;
+    ext.get(g, a, b);
+    tile_prefix[g] = run;
+    run += (b - a + kSplitTile - 1) / kSplitTile;
+  }
   if (threadIdx.x == 0) {
-    uint32_t run = 0;
-    for (int i = 0; i < n_seg; ++i) { tile_prefix[i] = run; run += tiles[i]; }
-    tile_prefix[n_seg] = run;
+    tile_prefix[n_seg] = warp_sums[32];
+    if (n_records) {
+      unsigned long long t = 0;
+      for (int w = 0; w < 32; ++w) t += rec_sums[w];
+      *n_records = t;
+    }
   }
 }
+
+// tile descriptors: one warp per segment.  The children of segment g are the cursors (g / segs_per_bucket) << r_child ...
+__global__ void __launch_bounds__(256) k_segment_fill(SegExtents ext, uint32_t n_seg, const uint32_t* tile_prefix, uint32_t segs_per_bucket,
+                                                     int r_child, uint4* tile_desc) {
+  const uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= n_seg) return;
+  uint32_t a, b;
+  ext.get(g, a, b);
+  const uint32_t t0 = tile_prefix[g], nt = tile_prefix[g + 1] - t0;
+  const uint32_t child0 = (g / segs_per_bucket) << r_child;
+  for (uint32_t t = threadIdx.x & 31; t < nt; t += 32) {
+    const uint32_t start = a + t * kSplitTile;
+    tile_desc[t0 + t] = make_uint4(start, min(start + (uint32_t)kSplitTile, b), child0, g);
+  }
+}
+
+// Extents of the leaf buckets the filter reads (same two forms as SegExtents with shift = 0).
+struct LeafExtents {
+  const uint32_t* off;      // exact: n_leaf + 1 offsets
+  const uint32_t* ends;     // direct: final cursor of every leaf region
+  uint32_t cap;             // direct: records per region (0 = exact)
+  __device__ __forceinline__ void get(uint32_t lf, uint32_t n_leaf, uint32_t& lo, uint32_t& n) const {
+    lo = 0; n = 0;
+    if (lf >= n_leaf) return;
+    if (cap) {
+      lo = lf * cap;
+      uint32_t e = __ldg(ends + lf);
+      if (e > lo + cap) e = lo + cap;
+      n = e > lo ? e - lo : 0u;
+    } else {
+      lo = __ldg(off + lf);
+      n = __ldg(off + lf + 1) - lo;
+    }
+  }
+};
 
 // ---- in-bucket duplicate filter -------------------------------------------------------------------------
 // One CTA per leaf bucket (work-stealing).  Keys go into an open-addressing table in shared memory; a key met
@@ -295,7 +464,7 @@ __device__ __forceinline__ void cp_async_key(uint64_t* d, const uint64_t* s) { c
 // registers (two 1024-thread CTAs per SM need <= 32 registers per thread).  CAP = records a leaf may hold to be
 // filtered in shared memory (table of 2*T*E slots, staging of CAP records).
 template <typename KeyT, int T, int E, int CAP, bool STAGED>
-__global__ void __launch_bounds__(T, (E <= 4) ? 2 : 1) k_filter(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* leaf_off,
+__global__ void __launch_bounds__(T, (E <= 4) ? 2 : 1) k_filter(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, LeafExtents leaves,
                                               uint32_t n_leaf, int leaf_bits, uint32_t cap, KeyT* cand_keys, uint32_t* cand_vals,
                                               unsigned long long* n_cand, uint32_t* n_oversized, uint32_t* unsorted) {
   // candidates of one leaf are ordered by (key, part) in shared memory before they are written as one contiguous run:
@@ -315,8 +484,7 @@ __global__ void __launch_bounds__(T, (E <= 4) ? 2 : 1) k_filter(const KeyT* __re
   for (int i = threadIdx.x; i < kLeafSortCap; i += T) c_rank[i] = 0;
   uint32_t next_lo = 0, next_n = 0;
   auto stage_next = [&](uint32_t lf) {            // start the asynchronous copy of leaf lf into the staging area
-    next_n = 0;
-    if (lf < n_leaf) { next_lo = leaf_off[lf]; next_n = leaf_off[lf + 1] - next_lo; }
+    leaves.get(lf, n_leaf, next_lo, next_n);
     if (STAGED && next_n >= 2 && next_n <= cap) {
       for (uint32_t i = threadIdx.x; i < next_n; i += T) {
         cp_async_key(st_keys + i, keys + next_lo + i);
@@ -489,7 +657,7 @@ template <typename KeyT, int CAP, int WORDS> constexpr size_t filter_bloom_smem(
 }
 
 template <typename KeyT, int T, int E, int WORDS, int MINB>
-__global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, const uint32_t* leaf_off,
+__global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, LeafExtents leaves,
                                                       uint32_t n_leaf, int leaf_bits, uint32_t cap, KeyT* cand_keys, uint32_t* cand_vals,
                                                       unsigned long long* n_cand, uint32_t* n_oversized, uint32_t* unsorted) {
   constexpr int kBloomWords = WORDS, kBloomCap = T * E;
@@ -525,10 +693,7 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict
     tma_bulk_load(st_vals, vals + v0, vb, &s_bar);
   };
   // leaf extents are read two leaves ahead so that no global-load latency sits on the per-leaf critical path
-  auto extent = [&](uint32_t lf, uint32_t& elo, uint32_t& en) {
-    elo = 0; en = 0;
-    if (lf < n_leaf) { elo = __ldg(leaf_off + lf); en = __ldg(leaf_off + lf + 1) - elo; }
-  };
+  auto extent = [&](uint32_t lf, uint32_t& elo, uint32_t& en) { leaves.get(lf, n_leaf, elo, en); };
   uint32_t lo, n, lo1, n1, lo2, n2;
   extent(blockIdx.x, lo, n);
   extent(blockIdx.x + gridDim.x, lo1, n1);
@@ -563,23 +728,6 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict
     }
     if (n < 2) continue;
     if (n > cap || n > (uint32_t)kBloomCap) {
-      if (threadIdx.x == 0) { atomicAdd(n_oversized, 1u); *unsorted = 1u; }
-      for (uint32_t i = threadIdx.x; i < n + 31u - ((n - 1u) & 31u) ; i += T) {   // whole warps iterate together
-        bool ok = i < n;
-        uint32_t m = __ballot_sync(0xffffffffu, ok);
-        unsigned long long basepos = 0;
-        if (lane == 0) basepos = atomicAdd(n_cand, (unsigned long long)__popc(m));
-        basepos = __shfl_sync(0xffffffffu, basepos, 0);
-        if (ok) {
-          unsigned long long dst = basepos + __popc(m & lanemask_lt());
-          cand_keys[dst] = keys[lo + i];
-          cand_vals[dst] = vals[lo + i];
-        }
-      }
-      continue;
-    }
-    for (int i = threadIdx.x; i < kBloomWords; i += T) { map_a[i] = 0; map_b[i] = 0; }    if (n < 2) continue;
-    if (n > cap) {
       if (threadIdx.x == 0) { atomicAdd(n_oversized, 1u); *unsorted = 1u; }
       for (uint32_t i = threadIdx.x; i < n + 31u - ((n - 1u) & 31u) ; i += T) {   // whole warps iterate together
         bool ok = i < n;

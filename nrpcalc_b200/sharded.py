@@ -83,6 +83,34 @@ class NativeOps(object):
             return False
         return True
 
+    def exchange_direct(self, lo, hi, k, internal_repeats, windows_total, group, phases):
+        """Direct fused exchange: no count pass.  Every (level-1 bucket, sender) pair owns a fixed region of the owner's
+        receive buffer; scatter -> all-reduce(MAX) of the overflow flags (= barrier) -> the owner's level-2 split, filter and
+        ordering run straight from the received regions.  Returns (sent, received) or None when a region overflowed on some
+        rank (heavily duplicated input): the caller then uses the counted exchange."""
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if os.environ.get('NRPCALC_B200_DIRECT', '1') == '0':
+            return None
+        key = ('direct', int(windows_total), k <= 16, self.n_parts, world)
+        if getattr(self, '_peer_key_direct', None) != key:
+            handle = self.ctx.peer_export_direct(windows_total, world, k)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle, group=group)
+            self.ctx.peer_open_direct(handles, rank)
+            self._peer_key_direct = key
+            self._overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        phases.mark('peer_setup')
+        overflow = self.ctx.shard_scatter_direct(lo, hi, k, internal_repeats, world)
+        phases.mark('scatter')
+        self._overflow.fill_(1 if overflow else 0)
+        dist.all_reduce(self._overflow, op=dist.ReduceOp.MAX, group=group)      # also the barrier: every peer's stores have landed
+        if int(self._overflow.item()) != 0:
+            phases.mark('barrier')
+            return None
+        phases.mark('barrier')
+        self.ctx.shard_group_direct(k, internal_repeats)
+        return self.ctx.shard_moved()
+
     def exchange_fused(self, lo, hi, k, internal_repeats, windows_total, group, phases):
         """flags + counts -> all-gather of the counts -> peer-store scatter -> barrier -> group the received records.
         Returns (sent, received) or None when the receive capacity would overflow (caller falls back to NCCL)."""
@@ -247,7 +275,9 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
 
     phases = _Phases(phase_ms, ops.device)
     moved = None
-    if hasattr(ops, 'exchange_fused') and ops.peers_available():
+    if hasattr(ops, 'exchange_direct') and ops.peers_available():
+        moved = ops.exchange_direct(lo, hi, k, internal_repeats, windows_total, group, phases)
+    if moved is None and hasattr(ops, 'exchange_fused') and ops.peers_available():
         moved = ops.exchange_fused(lo, hi, k, internal_repeats, windows_total, group, phases)
     if moved is None:
         keys, vals, send_counts = ops.extract(lo, hi, k, internal_repeats, world)

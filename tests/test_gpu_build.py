@@ -104,12 +104,14 @@ def test_forced_paths(ctx):
         _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
         ctx.set_option('max_level_bits', 0)
         ctx.set_option('leaf_target', 0)
-        ctx.set_option('pass_records', 9000)          # several passes over slices of the hash space
+        ctx.set_option('pass_records', 9000)          # exact path: several passes over slices of the hash space
+        ctx.set_option('direct', 0)
         res = _run(ctx, uniq, 13, False)
         assert res.counts['runs'] > 1
         _compare(res, uniq, 13, False)
         _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
         ctx.set_option('pass_records', 0)
+        ctx.set_option('direct', -1)
         ctx.set_option('no_bloom', 1)                 # exact table on every record instead of the two-stage filter
         _compare(_run(ctx, uniq, 13, False), uniq, 13, False)
         ctx.set_option('no_bloom', 0)
@@ -118,12 +120,61 @@ def test_forced_paths(ctx):
         uniq17 = _long_parts(cases.planted_parts(600, 77), 17)
         _compare(_run(ctx, uniq17, 17, True), uniq17, 17, True)
     finally:
+        ctx.set_option('direct', -1)
         ctx.set_option('no_window_carry', 0)
         ctx.set_option('no_bloom', 0)
         ctx.set_option('pass_records', 0)
         ctx.set_option('filter_cap', 0)
         ctx.set_option('leaf_target', 0)
         ctx.set_option('max_level_bits', 0)
+
+
+def test_direct_and_exact_paths_agree(ctx):
+    """Default = fixed regions without a histogram pass; direct=0 = exact histogram path.  Both must match the oracle."""
+    for k, internal in ((13, False), (17, True), (25, False)):
+        uniq = _long_parts(cases.planted_parts(1500, 5) + cases.random_parts(3000, 100, 3), k)
+        try:
+            res = _run(ctx, uniq, k, internal)
+            assert res.counts['direct'] == 1 and res.counts['fallbacks'] == 0
+            _compare(res, uniq, k, internal)
+            ctx.set_option('direct', 0)
+            res = _run(ctx, uniq, k, internal)
+            assert res.counts['direct'] == 0
+            _compare(res, uniq, k, internal)
+        finally:
+            ctx.set_option('direct', -1)
+
+
+def test_direct_overflow_falls_back_to_exact(ctx):
+    """A k-mer shared by thousands of parts overflows its fixed region: the batch is repeated on the exact path."""
+    import random
+    rnd = random.Random(3)
+    common = ''.join(rnd.choice('ACGT') for _ in range(14))
+    parts = [common + ''.join(rnd.choice('ACGT') for _ in range(36)) for _ in range(1200)]
+    uniq = _long_parts(parts, 13)
+    try:
+        ctx.set_option('max_pairs', 1 << 40)
+        res = _run(ctx, uniq, 13, True)
+        assert res.counts['fallbacks'] == 1 and res.counts['direct'] == 0
+        want = np_oracle.spec(uniq, 13, True)
+        assert res.counts['records'] == want['n_records']
+        assert res.counts['groups'] == len(want['groups'])
+        assert sorted(zip(res.edges[0].tolist(), res.edges[1].tolist())) == sorted(want['edges'])
+        assert res.last_single.tolist() == want['last_single'].tolist()
+    finally:
+        ctx.set_option('max_pairs', 0)
+
+
+def test_deep_direct_levels(ctx):
+    """Tiny leaf target: two 9-bit levels on the direct path."""
+    uniq = _long_parts(cases.planted_parts(800, 9) + cases.random_parts(4000, 100, 4), 17)
+    try:
+        ctx.set_option('leaf_target', 2)
+        res = _run(ctx, uniq, 17, False)
+        assert res.counts['buckets'] == 1 << 18
+        _compare(res, uniq, 17, False)
+    finally:
+        ctx.set_option('leaf_target', 0)
 
 
 def test_empty_and_tiny(ctx):
