@@ -101,6 +101,7 @@ template <typename KeyT> constexpr size_t filter_smem_large() { return (sizeof(K
 template <typename KeyT> constexpr size_t filter_smem_small() {
   return (sizeof(KeyT) + 1) * 2 * (size_t)(kFilterThreads * kFilterItemsSmall) + (kFilterStaged ? (sizeof(KeyT) + 4) * (size_t)kFilterCapSmall : 0);
 }
+constexpr int64_t kDefaultLeafTarget = 5500;                // records per leaf bucket aimed for (filter capacity 8192)
 constexpr int kMaxLeafBits = 15;                            // exact path: 2^15 u32 counters = 128 KB of shared memory
 constexpr int kMaxDirectBits = 2 * kMaxLevelBits;           // direct path: two levels of <= 9 bits
 
@@ -115,7 +116,7 @@ struct nrp_ctx {
 
   // options
   int64_t opt_filter_cap = kFilterCap;
-  int64_t opt_leaf_target = 2750;
+  int64_t opt_leaf_target = kDefaultLeafTarget;
   int64_t opt_max_level_bits = kMaxLevelBits;
   int64_t opt_max_pairs = (int64_t)1 << 31;
   int64_t opt_no_window_carry = 0;
@@ -303,7 +304,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   if (!c || !name) return fail(NRP_E_ARG, "null argument");
   std::string n(name);
   if (n == "filter_cap") c->opt_filter_cap = (value <= 0 || value > kFilterCap) ? kFilterCap : value;
-  else if (n == "leaf_target") c->opt_leaf_target = value <= 0 ? 2750 : value;
+  else if (n == "leaf_target") c->opt_leaf_target = value <= 0 ? kDefaultLeafTarget : value;
   else if (n == "max_level_bits") c->opt_max_level_bits = (value <= 0 || value > kMaxLevelBits) ? kMaxLevelBits : value;
   else if (n == "max_pairs") c->opt_max_pairs = value <= 0 ? ((int64_t)1 << 31) : value;
   else if (n == "no_window_carry") c->opt_no_window_carry = value > 0 ? 1 : 0;
@@ -454,7 +455,8 @@ struct BulkSource {
   SegExtents ext{nullptr, 0, nullptr, 0};
   uint32_t n_seg = 0;                  // segments of the record list
   uint32_t segs_per_bucket = 1;        // pre-partitioned input: consecutive segments that belong to one level-1 bucket
-  int r_done = 0;                      // pre-partitioned input: hash bits already consumed (0 = none)
+  bool prepartitioned = false;         // the segments are (level-1 bucket, sender) regions: level 1 is done
+  int r_done = 0;                      // pre-partitioned input: hash bits already consumed
   int64_t m_upper = 0;                 // hard upper bound of the number of records (buffer sizes)
   int64_t m_plan = 0;                  // expected number of records (level planning); 0 = m_upper
 };
@@ -471,7 +473,7 @@ inline uint32_t region_cap(double mean, int slack) {
 LevelPlan plan_levels(const nrp_ctx* c, int64_t m, bool direct, int fixed_r1 = -1) {
   const int lv = (int)c->opt_max_level_bits;
   int max_bits = std::min(direct ? kMaxDirectBits : kMaxLeafBits, fixed_r1 >= 0 ? fixed_r1 + lv : 2 * lv);
-  int bits = fixed_r1 >= 0 ? std::max(fixed_r1, 1) : 1;
+  int bits = fixed_r1 >= 0 ? fixed_r1 + 1 : 1;            // a pre-partitioned input always takes one more level (it merges the senders' regions)
   while (bits < max_bits && (m >> bits) > c->opt_leaf_target) ++bits;
   LevelPlan p;
   p.bits = bits;
@@ -528,7 +530,7 @@ template <typename KeyT>
 int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer& tm, bool* overflowed) {
   cudaStream_t st = c->stream;
   const bool from_ascii = src.from_parts;
-  const bool prepart = !from_ascii && src.r_done > 0;
+  const bool prepart = !from_ascii && src.prepartitioned;
   const int64_t m_max = from_ascii ? c->shard_m_max : (src.m_plan > 0 ? src.m_plan : src.m_upper);
   const Parts P = parts_view(c);
   unsigned long long* cnt = c->counters.as<unsigned long long>();
@@ -1152,9 +1154,9 @@ int direct_shard_plan(nrp_ctx* c, int64_t windows_total, int world, int* r1_out,
   const int64_t m_owner = windows_total / world + (windows_total / world) / 32 + 4096;
   int max_r1 = 0;
   while ((world << (max_r1 + 1)) <= kLevelBuckets) ++max_r1;
-  LevelPlan p = plan_levels(c, m_owner, true);
-  int r1 = std::min(p.r1, max_r1);
-  if (r1 < 1) r1 = 1;
+  // as few level-1 bits as the owner's second level allows: the fewer digits, the longer the runs stored over NVLink
+  const LevelPlan p = plan_levels(c, m_owner, true);
+  int r1 = std::min(std::max(p.bits - (int)c->opt_max_level_bits, 0), max_r1);
   if ((world << r1) > kLevelBuckets) return fail(NRP_E_UNSUPPORTED, "%d owners do not fit one split level", world);
   *r1_out = r1;
   *cap1s_out = region_cap((double)windows_total / ((double)world * world * (double)(1 << r1)), 256);
@@ -1211,6 +1213,7 @@ int shard_group_direct_impl(nrp_ctx* c, int k, int internal_repeats) {
   src.n_seg = (uint32_t)c->sh_world << c->sh_r1;
   src.ext = SegExtents{nullptr, 0, c->recv_ends.as<uint32_t>(), c->sh_cap1s};
   src.segs_per_bucket = (uint32_t)c->sh_world;
+  src.prepartitioned = true;
   src.r_done = c->sh_r1;
   src.m_upper = (int64_t)src.n_seg * c->sh_cap1s;
   src.m_plan = c->sh_m_owner;

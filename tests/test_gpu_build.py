@@ -169,7 +169,7 @@ def test_deep_direct_levels(ctx):
     """Tiny leaf target: two 9-bit levels on the direct path."""
     uniq = _long_parts(cases.planted_parts(800, 9) + cases.random_parts(4000, 100, 4), 17)
     try:
-        ctx.set_option('leaf_target', 2)
+        ctx.set_option('leaf_target', 1)
         res = _run(ctx, uniq, 17, False)
         assert res.counts['buckets'] == 1 << 18
         _compare(res, uniq, 17, False)

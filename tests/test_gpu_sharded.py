@@ -20,8 +20,11 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n_parts, k, internal, out_dir):
+def _worker(rank, world, port, n_parts, k, internal, out_dir, mode='direct'):
     import sys
+    # exchange flavour: direct (fixed regions, no count pass), counted (count pass + peer stores), nccl (all-to-all)
+    os.environ['NRPCALC_B200_DIRECT'] = '1' if mode == 'direct' else '0'
+    os.environ['NRPCALC_B200_EXCHANGE'] = 'nccl' if mode == 'nccl' else 'peer'
     here = os.path.dirname(os.path.abspath(__file__))
     sys.path[:0] = [os.path.dirname(here), here]
     import torch
@@ -65,13 +68,14 @@ def _groups(res):
                   for g in range(len(res['indptr']) - 1))
 
 
-@pytest.mark.parametrize('k,internal', [(13, False), (17, False), (16, True)])
-def test_sharded_equals_single_gpu(tmp_path, k, internal):
+@pytest.mark.parametrize('k,internal,mode', [(13, False, 'direct'), (17, False, 'direct'), (16, True, 'direct'), (16, False, 'direct'),
+                                             (13, False, 'counted'), (17, True, 'counted'), (17, False, 'nccl')])
+def test_sharded_equals_single_gpu(tmp_path, k, internal, mode):
     world = min(_n_gpus(), 4)
     if world < 2:
         pytest.skip('needs at least 2 GPUs')
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(world, _free_port(), 3000, k, internal, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), 3000, k, internal, str(tmp_path), mode), nprocs=world, join=True)
     single = np.load(str(tmp_path / 'single.npz'))
     for rank in range(world):
         res = np.load(str(tmp_path / ('rank%d.npz' % rank)))
