@@ -17,7 +17,7 @@ inline int64_t& launch_counter() { static thread_local int64_t n = 0; return n; 
 // hashing: one multiplicative (Fibonacci) hash per key; consecutive bit fields of the product, from the top,
 // select the level-1 bucket, the level-2 bucket and the slot of the in-bucket table.
 __host__ __device__ __forceinline__ uint64_t key_hash(uint64_t key) {
-  key ^= key >> 31;
+  key ^= key >> 32;                         // fold the high word into the low one (one LOP3 on the device)
   return key * 0x9E3779B97F4A7C15ull;
 }
 // independent hash for choosing the owner GPU of a key (sharded path)
@@ -183,9 +183,9 @@ __device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileS
   const int down = 64 - 2 * k, top = 2 * k - 2;
   uint64_t fwd = v >> down;
   uint64_t rc = revcomp2(fwd, k);
-  auto part_usable = [&](int64_t part) -> bool {
-    if (part < P.part_lo || part >= P.part_hi) return false;
-    return SKIP_FLAGGED ? flags[part] == 0 : true;
+  auto part_usable = [&](int64_t part) -> int {
+    if (part < P.part_lo || part >= P.part_hi) return 0;
+    return SKIP_FLAGGED ? (flags[part] == 0 ? 1 : 0) : 1;
   };
   if (P.uniform_len > 0) {
     const uint32_t L = (uint32_t)P.uniform_len;
@@ -194,7 +194,9 @@ __device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileS
     uint32_t q = rel / L;
     uint32_t r = rel - q * L;                                 // offset of the position inside its part
     int64_t part = p0 + q;
-    bool ok = part_usable(part);
+    if (L < (uint32_t)k) return;
+    const uint32_t last = L - (uint32_t)k;                   // last window start inside a part
+    int ok = part_usable(part);
 #pragma unroll
     for (int e = 0; e < kTileItems; ++e) {
       if (e > 0) {
@@ -203,7 +205,7 @@ __device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileS
         rc = (rc >> 2) | ((uint64_t)(3u - ((uint32_t)fwd & 3u)) << top);
         if (++r == L) { r = 0; ++part; ok = part_usable(part); }
       }
-      if (ok && r + (uint32_t)k <= L) f(e, fwd < rc ? fwd : rc, (uint32_t)part, r, fwd == rc);
+      if (ok != 0 && r <= last) f(e, fwd < rc ? fwd : rc, (uint32_t)part, r, fwd == rc);
     }
     return;
   }
@@ -215,7 +217,7 @@ __device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileS
   auto rel_end = [&](int64_t e64) -> int { int64_t d = e64 - g_lo; return d > (1 << 30) ? (1 << 30) : (int)d; };
   int end = rel_end(end64);
   int start = (int)((s.n_slice > 0 ? s.slice[part - s.first_part] : P.off[part]) - g_lo);   // may be negative
-  bool ok = part_usable(part);
+  int ok = part_usable(part);
   int c = c0;
 #pragma unroll
   for (int e = 0; e < kTileItems; ++e) {
@@ -234,7 +236,7 @@ __device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileS
         ok = part_usable(part);
       }
     }
-    if (ok && c + k <= end) f(e, fwd < rc ? fwd : rc, (uint32_t)part, (uint32_t)(c - start), fwd == rc);
+    if (ok != 0 && c + k <= end) f(e, fwd < rc ? fwd : rc, (uint32_t)part, (uint32_t)(c - start), fwd == rc);
   }
 }
 

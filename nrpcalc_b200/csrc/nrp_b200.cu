@@ -235,8 +235,12 @@ int configure_kernels(nrp_ctx* c) {
   bool& done = c->configured[sizeof(KeyT) == 4 ? 0 : 1];
   if (done) return NRP_OK;
   const int split_smem = (int)(sizeof(SplitSmem<KeyT>) + sizeof(TileStage));
-  CU(cudaFuncSetAttribute(k_split_from_ascii<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, split_smem));
-  CU(cudaFuncSetAttribute(k_split_from_records<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<KeyT>)));
+  CU(cudaFuncSetAttribute((k_split_from_ascii<KeyT, 0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, split_smem));
+  CU(cudaFuncSetAttribute((k_split_from_ascii<KeyT, 0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, split_smem));
+  CU(cudaFuncSetAttribute((k_split_from_ascii<KeyT, 1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, split_smem));
+  CU(cudaFuncSetAttribute((k_split_from_ascii<KeyT, 2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, split_smem));
+  CU(cudaFuncSetAttribute((k_split_from_records<KeyT, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<KeyT>)));
+  CU(cudaFuncSetAttribute((k_split_from_records<KeyT, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<KeyT>)));
   CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, 4, 2048, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)filter_bloom_smem<KeyT, 4096, 2048>()));
   CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -558,12 +562,12 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
   const RegionLimit lim2{lp.cap2, 0u, overflow, nullptr};
   if (m_max > 0 && !prepart) {
     if (from_ascii) {
-      NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-          P, c->flags.as<uint8_t>(), k, r1, 0, 0, c->part_base, c->j_bits, PassSel{0, 0u, 0u}, level1_cursor, l1_keys, l1_vals, lim1, PeerBuffers{}, 0)));
+      NRP_LAUNCH((k_split_from_ascii<KeyT, 0, false><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+          P, c->flags.as<uint8_t>(), k, r1, 0, c->part_base, c->j_bits, PassSel{0, 0u, 0u}, level1_cursor, l1_keys, l1_vals, lim1, PeerBuffers{}, 0)));
     } else {
       TRY(build_tiles(c, src.ext, src.n_seg, 0xffffffffu, 0, nullptr));
       const unsigned grid = (unsigned)std::min<int64_t>(m_max / kSplitTile + src.n_seg, (int64_t)c->n_sms * 4);
-      NRP_LAUNCH((k_split_from_records<KeyT><<<grid, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
+      NRP_LAUNCH((k_split_from_records<KeyT, false><<<grid, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
           src.keys, src.vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + src.n_seg, 0, r1, PassSel{0, 0u, 0u}, level1_cursor,
           l1_keys, l1_vals, lim1)));
     }
@@ -577,7 +581,7 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
     const uint32_t n_seg = prepart ? src.n_seg : n_l1;
     TRY(build_tiles(c, ext, n_seg, prepart ? src.segs_per_bucket : 1u, r2, cnt + CNT_RECORDS));
     const unsigned grid2 = (unsigned)std::min<int64_t>(m_max / kSplitTile + n_seg, (int64_t)c->n_sms * 4);
-    NRP_LAUNCH((k_split_from_records<KeyT><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
+    NRP_LAUNCH((k_split_from_records<KeyT, false><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
         in_k, in_v, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + n_seg, r1, r2, PassSel{0, 0u, 0u}, c->cursor2.as<uint32_t>(),
         l2_keys, l2_vals, lim2)));
     leaf_keys = l2_keys; leaf_vals = l2_vals;
@@ -673,11 +677,11 @@ int stage_bulk_exact(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer&
     uint32_t* level1_cursor = r2 > 0 ? c->cursor1.as<uint32_t>() : c->cursor2.as<uint32_t>();
     if (m_max > 0) {
       if (from_ascii) {
-        NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-            P, c->flags.as<uint8_t>(), k, r1, 0, 0, c->part_base, c->j_bits, sel, level1_cursor, leaf_keys, leaf_vals, no_limit, PeerBuffers{}, 0)));
+        NRP_LAUNCH((k_split_from_ascii<KeyT, 0, true><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+            P, c->flags.as<uint8_t>(), k, r1, 0, c->part_base, c->j_bits, sel, level1_cursor, leaf_keys, leaf_vals, no_limit, PeerBuffers{}, 0)));
       } else {
         const unsigned grid = (unsigned)std::min<int64_t>(src_tiles_max, (int64_t)c->n_sms * 4);
-        NRP_LAUNCH((k_split_from_records<KeyT><<<grid, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
+        NRP_LAUNCH((k_split_from_records<KeyT, true><<<grid, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
             src.keys, src.vals, c->tile_desc.as<uint4>(), n_src_tiles, 0, r1, sel, level1_cursor, leaf_keys, leaf_vals, no_limit)));
       }
     }
@@ -686,7 +690,7 @@ int stage_bulk_exact(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer&
       const uint32_t n_l1 = 1u << r1;
       TRY(build_tiles(c, SegExtents{c->leaf_off.as<uint32_t>(), r2, nullptr, 0u}, n_l1, 1u, r2, nullptr));
       const unsigned grid2 = (unsigned)std::min<int64_t>(n_pass / kSplitTile + n_l1, (int64_t)c->n_sms * 4);
-      NRP_LAUNCH((k_split_from_records<KeyT><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
+      NRP_LAUNCH((k_split_from_records<KeyT, false><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
           leaf_keys, leaf_vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + n_l1, r1, r2, PassSel{0, 0u, 0u}, c->cursor2.as<uint32_t>(),
           free_keys, free_vals, no_limit)));
       std::swap(leaf_keys, free_keys); std::swap(leaf_vals, free_vals);
@@ -1030,8 +1034,8 @@ int shard_extract_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int internal_r
   CU(cudaMemcpyAsync(c->h_counters + 32, c->hist.ptr, 4 * (size_t)n_owners, cudaMemcpyDeviceToHost, st));
   tm.begin(NRP_T_SPLIT1);
   if (c->shard_m_max > 0)
-    NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, 8, n_owners, 1, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>(),
+    NRP_LAUNCH((k_split_from_ascii<KeyT, 1, false><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+        P, c->flags.as<uint8_t>(), k, 8, n_owners, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>(),
         RegionLimit{0u, 0u, nullptr, nullptr}, PeerBuffers{}, 0)));
   CU(cudaGetLastError());
   tm.finish(c->timings);
@@ -1115,8 +1119,8 @@ int shard_scatter_impl(nrp_ctx* c, int k, const int64_t* write_offsets) {
   StageTimer tm(c);
   tm.begin(NRP_T_SPLIT1);
   if (c->shard_m_max > 0)
-    NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, 8, c->n_owners, 1, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr,
+    NRP_LAUNCH((k_split_from_ascii<KeyT, 1, false><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+        P, c->flags.as<uint8_t>(), k, 8, c->n_owners, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr,
         RegionLimit{0u, 0u, nullptr, nullptr}, c->peers, 1)));
   CU(cudaGetLastError());
   tm.finish(c->timings);
@@ -1187,8 +1191,8 @@ int shard_scatter_direct_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int int
   NRP_LAUNCH((k_init_owner_cursors<<<grid_for(nd, 256), 256, 0, st>>>(c->cursor1.as<uint32_t>(), c->region_ends.as<uint32_t>(), nd, c->sh_r1,
                                                                     (uint32_t)n_owners, (uint32_t)c->my_rank, c->sh_cap1s)));
   if (c->shard_m_max > 0)
-    NRP_LAUNCH((k_split_from_ascii<KeyT><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, c->sh_r1, n_owners, 2, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr,
+    NRP_LAUNCH((k_split_from_ascii<KeyT, 2, false><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+        P, c->flags.as<uint8_t>(), k, c->sh_r1, n_owners, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr,
         RegionLimit{c->sh_cap1s, 0u, reinterpret_cast<uint32_t*>(cnt + CNT_SCATTER_OVERFLOW), c->region_ends.as<uint32_t>()}, c->peers_d, 1)));
   PeerEnds pe;
   for (int o = 0; o < kMaxPeers; ++o) pe.ptr[o] = c->peer_ends[o];

@@ -35,9 +35,10 @@ template <typename KeyT>
 struct alignas(16) SplitSmem {
   KeyT keys[kSplitTile];
   uint32_t vals[kSplitTile];
+  uint16_t dig[kSplitTile];          // bucket of the record at this position of the reordered tile
   uint32_t cnt[kLevelBuckets];
   uint32_t base[kLevelBuckets];
-  uint32_t gbase[kLevelBuckets];
+  uint32_t delta[kLevelBuckets];     // global position of the bucket's run minus its position in the tile (kNoSpace: region full)
   uint32_t warp_sums[40];
   uint32_t total;
 };
@@ -57,22 +58,6 @@ struct PassSel {
   __device__ __forceinline__ bool accept(uint64_t hash) const { return (((uint32_t)(hash >> shift)) & mask) == id; }
 };
 
-// digit of a key at one partition level
-struct HashField {            // a bit field of key_hash: leaf-bucket levels
-  int shift; uint32_t mask;
-  __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return (uint32_t)(key_hash(key) >> shift) & mask; }
-};
-struct OwnerDigit {           // owner GPU of a key (sharded path, exact exchange)
-  uint32_t n_owners;
-  __device__ __forceinline__ uint32_t operator()(uint64_t key) const { return owner_hash(key) % n_owners; }
-};
-struct OwnerBucketDigit {     // direct sharded path: (owner, top r1 bits of the hash) = owner * 2^r1 + level-1 bucket
-  uint32_t n_owners; int r1;
-  __device__ __forceinline__ uint32_t operator()(uint64_t key) const {
-    return (owner_of(key, n_owners) << r1) | (r1 ? (uint32_t)(key_hash(key) >> (64 - r1)) : 0u);
-  }
-};
-
 // Direct mode (no histogram pass): bucket i of a level owns the FIXED region [i * cap, (i + 1) * cap) of the output buffer
 // and cursor[i] starts at i * cap.  A claim that would cross the region's end sets *overflow and writes nothing; the
 // host then repeats the batch on the exact (histogram) path.  cap == 0: exact offsets, nothing to check.
@@ -89,10 +74,10 @@ constexpr uint32_t kNoSpace = 0xffffffffu;
 // Steps shared by both split kernels once every thread holds its records, digits and in-bucket ranks:
 // scan the bucket counts, claim global space for each non-empty bucket with one atomic per (tile, bucket),
 // reorder the tile through shared memory and write each bucket's run contiguously.
-// peer_shift >= 0: the buffers of digit d are those of owner d >> peer_shift (peer stores over NVLink).
-template <typename KeyT, typename DigitFn>
+// peer_shift >= 0 with peers: the buffers of digit d are those of owner d >> peer_shift (peer stores over NVLink).
+template <typename KeyT>
 __device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&key)[kSplitItems], const uint32_t (&val)[kSplitItems],
-                                              const uint32_t (&dr)[kSplitItems], int nb, DigitFn digit_of,
+                                              const uint32_t (&dr)[kSplitItems], int nb,
                                               uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals, RegionLimit lim,
                                               const PeerBuffers* peers = nullptr, int peer_shift = 0) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -120,39 +105,42 @@ __device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&k
   }
   __syncthreads();
   if ((int)threadIdx.x < nb) {
-    s.base[threadIdx.x] = s.warp_sums[wid] + inc - c;
+    const uint32_t base = s.warp_sums[wid] + inc - c;
+    s.base[threadIdx.x] = base;
     if (c) {
       uint32_t g = atomicAdd(&cursor[threadIdx.x], c);
+      uint32_t dl = g - base + (uint32_t)kSplitTile;     // biased by the tile size: never wraps, never equals kNoSpace
       if (lim.cap) {
         const uint64_t end = lim.ends ? (uint64_t)lim.ends[threadIdx.x] : (uint64_t)(lim.first + threadIdx.x + 1u) * lim.cap;
-        if ((uint64_t)g + c > end) { g = kNoSpace; *lim.overflow = 1u; }
+        if ((uint64_t)g + c > end) { dl = kNoSpace; *lim.overflow = 1u; }
       }
-      s.gbase[threadIdx.x] = g;
+      s.delta[threadIdx.x] = dl;
     }
   }
   __syncthreads();
 #pragma unroll
   for (int e = 0; e < kSplitItems; ++e) {
     if (dr[e] != 0xffffffffu) {
-      uint32_t pos = s.base[dr[e] >> 16] + (dr[e] & 0xffffu);
+      const uint32_t d = dr[e] >> 16;
+      const uint32_t pos = s.base[d] + (dr[e] & 0xffffu);
       s.keys[pos] = key[e];
       s.vals[pos] = val[e];
+      s.dig[pos] = (uint16_t)d;
     }
   }
   __syncthreads();
   const uint32_t total = s.total;
   for (uint32_t i = threadIdx.x; i < total; i += kSplitThreads) {
-    KeyT kx = s.keys[i];
-    uint32_t d = digit_of((uint64_t)kx);
-    const uint32_t gb = s.gbase[d];
-    if (gb == kNoSpace) continue;
-    uint32_t dst = gb + (i - s.base[d]);
+    const uint32_t d = s.dig[i];
+    const uint32_t dl = s.delta[d];
+    if (dl == kNoSpace) continue;
+    const uint32_t dst = i + dl - (uint32_t)kSplitTile;
     if (peers) {                                   // digit d lives in its owner's receive buffer (peer store over NVLink)
       const uint32_t o = d >> peer_shift;
-      reinterpret_cast<KeyT*>(peers->keys[o])[dst] = kx;
+      reinterpret_cast<KeyT*>(peers->keys[o])[dst] = s.keys[i];
       peers->vals[o][dst] = s.vals[i];
     } else {
-      out_keys[dst] = kx;
+      out_keys[dst] = s.keys[i];
       out_vals[dst] = s.vals[i];
     }
   }
@@ -250,41 +238,47 @@ __global__ void __launch_bounds__(1024) k_region_total(const uint32_t* cursor, u
 // cursor[d] must hold the start offset of bucket d and is advanced atomically.
 // Record value = part index, or (part << j_bits) | window index when both fit 32 bits (j_bits > 0): sorting by value
 // is then sorting by (part, window), and a group's first record carries the group's rank for free.
-template <typename KeyT>
-__global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, const uint8_t* flags, int k, int r1, int n_owners, int mode,
+template <typename KeyT, int MODE, bool PASSES>
+__global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, const uint8_t* flags, int k, int r1, int n_owners,
                                                                   uint32_t part_base, int j_bits, PassSel sel, uint32_t* cursor, KeyT* out_keys,
                                                                   uint32_t* out_vals, RegionLimit lim, PeerBuffers peers, int use_peers) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SplitSmem<KeyT>& s = *reinterpret_cast<SplitSmem<KeyT>*>(smem_raw);
   TileStage& stage = *reinterpret_cast<TileStage*>(smem_raw + sizeof(SplitSmem<KeyT>));
   const int64_t tile = P.tile_lo + blockIdx.x;
-  const int nb = mode == 0 ? (1 << r1) : mode == 1 ? n_owners : (n_owners << r1);
-  for (int i = threadIdx.x; i < kLevelBuckets; i += blockDim.x) s.cnt[i] = 0;
+  const int nb = MODE == 0 ? (1 << r1) : MODE == 1 ? n_owners : (n_owners << r1);
+  static_assert(kLevelBuckets == kTileThreads, "one counter per thread");
+  s.cnt[threadIdx.x] = 0;
   tile_load(P, tile, stage, threadIdx.x);
   __syncthreads();
   KeyT key[kSplitItems];
   uint32_t val[kSplitItems], dr[kSplitItems];
 #pragma unroll
   for (int e = 0; e < kSplitItems; ++e) { dr[e] = 0xffffffffu; key[e] = 0; val[e] = 0; }
+  const uint32_t j_mask = j_bits ? 0xffffffffu : 0u;
+  const int top_shift = 64 - r1;
   tile_windows_blocked<true>(P, stage, tile, k, flags, threadIdx.x, [&](int e, uint64_t canon, uint32_t part, uint32_t j, bool) {
-    const uint64_t h = key_hash(canon);
-    if (!sel.accept(h)) return;
     uint32_t d;
-    if (mode == 0) d = (uint32_t)(h >> (64 - r1));
-    else if (mode == 1) d = owner_hash(canon) % (uint32_t)n_owners;
-    else d = (owner_of(canon, (uint32_t)n_owners) << r1) | (r1 ? (uint32_t)(h >> (64 - r1)) : 0u);
-    uint32_t rank = atomicAdd(&s.cnt[d], 1u);
+    if (MODE == 1) {
+      d = owner_hash(canon) % (uint32_t)n_owners;
+      if (PASSES && !sel.accept(key_hash(canon))) return;
+    } else {
+      const uint64_t h = key_hash(canon);
+      if (PASSES && !sel.accept(h)) return;
+      d = MODE == 0 ? (uint32_t)(h >> top_shift) : ((owner_of(canon, (uint32_t)n_owners) << r1) | (r1 ? (uint32_t)(h >> top_shift) : 0u));
+    }
+    const uint32_t rank = atomicAdd(&s.cnt[d], 1u);
 #pragma unroll
     for (int q = 0; q < kSplitItems; ++q)
-      if (q == e) { key[q] = (KeyT)canon; val[q] = ((part_base + part) << j_bits) | (j_bits ? j : 0u); dr[q] = (d << 16) | rank; }
+      if (q == e) { key[q] = (KeyT)canon; val[q] = ((part_base + part) << j_bits) | (j & j_mask); dr[q] = (d << 16) | rank; }
   });
   __syncthreads();
-  if (mode == 0)
-    split_scatter<KeyT>(s, key, val, dr, nb, HashField{64 - r1, (1u << r1) - 1u}, cursor, out_keys, out_vals, lim);
-  else if (mode == 1)
-    split_scatter<KeyT>(s, key, val, dr, nb, OwnerDigit{(uint32_t)n_owners}, cursor, out_keys, out_vals, lim, use_peers ? &peers : nullptr, 0);
+  if (MODE == 0)
+    split_scatter<KeyT>(s, key, val, dr, nb, cursor, out_keys, out_vals, lim);
+  else if (MODE == 1)
+    split_scatter<KeyT>(s, key, val, dr, nb, cursor, out_keys, out_vals, lim, use_peers ? &peers : nullptr, 0);
   else
-    split_scatter<KeyT>(s, key, val, dr, nb, OwnerBucketDigit{(uint32_t)n_owners, r1}, cursor, out_keys, out_vals, lim, &peers, r1);
+    split_scatter<KeyT>(s, key, val, dr, nb, cursor, out_keys, out_vals, lim, &peers, r1);
 }
 
 // ---- level 2 (or level 1 when the records are already in HBM): segmented split of records ---------------
@@ -292,7 +286,7 @@ __global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, cons
 // segment is cut into tiles of kSplitTile records and each tile has a descriptor {first record, end, index of the
 // first child cursor}.  Persistent CTAs walk the tile list; the next tile's descriptor is fetched one tile ahead.
 // Child bucket = hash bits [64 - r_done - r2, 64 - r_done).
-template <typename KeyT>
+template <typename KeyT, bool PASSES>
 __global__ void __launch_bounds__(kSplitThreads) k_split_from_records(const KeyT* __restrict__ in_keys, const uint32_t* __restrict__ in_vals,
                                                                      const uint4* __restrict__ tile_desc, const uint32_t* n_tiles_ptr,
                                                                      int r_done, int r2, PassSel sel, uint32_t* cursor, KeyT* out_keys,
@@ -305,7 +299,7 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_from_records(const KeyT
     const uint4 d4 = next;
     if (tile + gridDim.x < n_tiles) next = __ldg(tile_desc + tile + gridDim.x);
     const uint32_t start = d4.x, end = d4.y, child0 = d4.z;
-    for (int i = threadIdx.x; i < (1 << r2); i += blockDim.x) s.cnt[i] = 0;
+    s.cnt[threadIdx.x] = 0;
     __syncthreads();
     KeyT key[kSplitItems];
     uint32_t val[kSplitItems], dr[kSplitItems];
@@ -323,7 +317,7 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_from_records(const KeyT
       dr[e] = 0xffffffffu;
       if (idx < end) {
         const uint64_t h = key_hash((uint64_t)key[e]);
-        if (sel.accept(h)) {
+        if (!PASSES || sel.accept(h)) {
           uint32_t d = (uint32_t)(h >> (64 - r_done - r2)) & mask;
           dr[e] = (d << 16) | atomicAdd(&s.cnt[d], 1u);
         }
@@ -332,7 +326,7 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_from_records(const KeyT
     __syncthreads();
     RegionLimit tile_lim = lim;
     tile_lim.first = child0;
-    split_scatter<KeyT>(s, key, val, dr, 1 << r2, HashField{64 - r_done - r2, mask}, cursor + child0, out_keys, out_vals, tile_lim);
+    split_scatter<KeyT>(s, key, val, dr, 1 << r2, cursor + child0, out_keys, out_vals, tile_lim);
     __syncthreads();
   }
 }
@@ -650,10 +644,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 constexpr int kSuspectSlots = 2 * kLeafSortCap;
-// capacity of a leaf = T * E records (staging area); WORDS = 32-bit words per bit map (16 bits per record or more)
+// capacity of a leaf = T * E records; WORDS = 32-bit words per bit map (16 bits per record or more).
+// Shared memory: exact table + suspect list + two bit maps + key staging (one leaf) + value staging (two leaves, ping-pong).
 template <typename KeyT, int CAP, int WORDS> constexpr size_t filter_bloom_smem() {
-  return sizeof(KeyT) * (kSuspectSlots + kLeafSortCap) + 4 * (2 * WORDS + 2 * kLeafSortCap) + kLeafSortCap + kSuspectSlots +
-         (sizeof(KeyT) + 4) * (CAP + 8) + 64;
+  return sizeof(KeyT) * (kSuspectSlots + kLeafSortCap) + 4 * (2 * WORDS + 2 * kLeafSortCap) + kSuspectSlots +
+         sizeof(KeyT) * (CAP + 8) + 2 * 4 * (CAP + 8) + 128;
 }
 
 template <typename KeyT, int T, int E, int WORDS, int MINB>
@@ -663,17 +658,19 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict
   constexpr int kBloomWords = WORDS, kBloomCap = T * E;
   constexpr uint32_t kBitMask = (uint32_t)WORDS * 32u - 1u;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // 16-byte aligned blocks first (they are cleared with 128-bit stores)
   KeyT* table = reinterpret_cast<KeyT*>(smem_raw);                                  // kSuspectSlots
-  KeyT* c_keys = table + kSuspectSlots;                                              // kLeafSortCap
-  uint32_t* map_a = reinterpret_cast<uint32_t*>(c_keys + kLeafSortCap);             // kBloomWords
+  uint32_t* map_a = reinterpret_cast<uint32_t*>(table + kSuspectSlots);             // kBloomWords
   uint32_t* map_b = map_a + kBloomWords;                                             // kBloomWords
-  uint32_t* c_vals = map_b + kBloomWords;                                            // kLeafSortCap
+  unsigned char* marked = reinterpret_cast<unsigned char*>(map_b + kBloomWords);    // kSuspectSlots
+  KeyT* c_keys = reinterpret_cast<KeyT*>(marked + kSuspectSlots);                   // kLeafSortCap
+  uint32_t* c_vals = reinterpret_cast<uint32_t*>(c_keys + kLeafSortCap);            // kLeafSortCap
   uint32_t* c_rank = c_vals + kLeafSortCap;                                          // kLeafSortCap
-  unsigned char* c_dup = reinterpret_cast<unsigned char*>(c_rank + kLeafSortCap);   // kLeafSortCap
-  unsigned char* marked = c_dup + kLeafSortCap;                                      // kSuspectSlots
-  // staging area of the NEXT leaf, filled by TMA bulk copies (16-byte aligned source windows around the leaf)
-  KeyT* st_keys = reinterpret_cast<KeyT*>((reinterpret_cast<uintptr_t>(marked + kSuspectSlots) + 15) & ~uintptr_t(15));
-  uint32_t* st_vals = reinterpret_cast<uint32_t*>(st_keys + kBloomCap + 8);
+  // staging, filled by TMA bulk copies (16-byte aligned source windows around the leaf): the keys of the NEXT leaf (they are
+  // copied to registers at the top of a leaf's turn) and the values of this and the next leaf (only suspects read theirs)
+  KeyT* st_keys = reinterpret_cast<KeyT*>((reinterpret_cast<uintptr_t>(c_rank + kLeafSortCap) + 15) & ~uintptr_t(15));
+  uint32_t* st_vals0 = reinterpret_cast<uint32_t*>(st_keys + kBloomCap + 8);
+  uint32_t* st_vals1 = st_vals0 + kBloomCap + 8;
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_c1, s_c2;
   __shared__ unsigned long long s_cbase;
@@ -683,7 +680,7 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict
   for (int i = threadIdx.x; i < kLeafSortCap; i += T) c_rank[i] = 0;
   constexpr uint32_t kKeysPer16 = 16 / sizeof(KeyT);
   // thread 0 starts the bulk copies of a leaf: the source windows are widened to 16-byte boundaries
-  auto stage = [&](uint32_t slo, uint32_t sn) {
+  auto stage = [&](uint32_t slo, uint32_t sn, uint32_t* st_vals) {
     if (sn < 2 || sn > cap || sn > (uint32_t)kBloomCap) return;
     const uint32_t k0 = slo & ~(kKeysPer16 - 1), k1 = (slo + sn + kKeysPer16 - 1) & ~(kKeysPer16 - 1);
     const uint32_t v0 = slo & ~3u, v1 = (slo + sn + 3u) & ~3u;
@@ -699,35 +696,32 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict
   extent(blockIdx.x + gridDim.x, lo1, n1);
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   __syncthreads();
-  if (threadIdx.x == 0) stage(lo, n);
-  uint32_t parity = 0;
-  for (uint32_t leaf = blockIdx.x; leaf < n_leaf; leaf += gridDim.x, lo = lo1, n = n1, lo1 = lo2, n1 = n2) {
+  if (threadIdx.x == 0) stage(lo, n, st_vals0);
+  uint32_t parity = 0, turn = 0;
+  for (uint32_t leaf = blockIdx.x; leaf < n_leaf; leaf += gridDim.x, lo = lo1, n = n1, lo1 = lo2, n1 = n2, turn ^= 1u) {
     extent(leaf + 2 * gridDim.x, lo2, n2);
     const bool fits = n >= 2 && n <= cap && n <= (uint32_t)kBloomCap;
+    const uint32_t* my_vals = (turn ? st_vals1 : st_vals0) + (lo & 3u);          // this leaf's values (valid for the whole turn)
+    // records held by this thread: i = threadIdx.x + e * T < n
+    const int ne = (fits && n > threadIdx.x) ? (int)((n - threadIdx.x + (uint32_t)T - 1u) / (uint32_t)T) : 0;
     KeyT key[E];
-    uint32_t val[E];
     if (fits) {                                     // uniform: the copy of this leaf was issued one iteration ago
       mbar_wait(&s_bar, parity);
       parity ^= 1u;
-      const uint32_t kshift = lo & (kKeysPer16 - 1), vshift = lo & 3u;
+      const KeyT* src = st_keys + (lo & (kKeysPer16 - 1)) + threadIdx.x;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
-        uint32_t i = threadIdx.x + e * T;
-        bool ok = i < n;
-        key[e] = ok ? st_keys[i + kshift] : kEmpty;
-        val[e] = ok ? st_vals[i + vshift] : 0u;
+        if (e >= ne) break;
+        key[e] = src[e * T];
       }
-    } else {
-#pragma unroll
-      for (int e = 0; e < E; ++e) { key[e] = kEmpty; val[e] = 0u; }
     }
     __syncthreads();                                // everyone copied out; the previous leaf is done with the shared arrays
     if (threadIdx.x == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before the async-proxy overwrite
-      stage(lo1, n1);
+      stage(lo1, n1, turn ? st_vals0 : st_vals1);
     }
     if (n < 2) continue;
-    if (n > cap || n > (uint32_t)kBloomCap) {
+    if (!fits) {
       if (threadIdx.x == 0) { atomicAdd(n_oversized, 1u); *unsorted = 1u; }
       for (uint32_t i = threadIdx.x; i < n + 31u - ((n - 1u) & 31u) ; i += T) {   // whole warps iterate together
         bool ok = i < n;
@@ -743,29 +737,51 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict
       }
       continue;
     }
-    for (int i = threadIdx.x; i < kBloomWords; i += T) { map_a[i] = 0; map_b[i] = 0; }
-    for (int i = threadIdx.x; i < kSuspectSlots; i += T) { table[i] = kEmpty; marked[i] = 0; }
+    {  // clear the exact table, both maps and the marks (contiguous, 16-byte aligned) with 128-bit stores
+      constexpr int kClear16 = (int)((sizeof(KeyT) * kSuspectSlots + 8 * kBloomWords + kSuspectSlots) / 16);
+      uint4* z = reinterpret_cast<uint4*>(smem_raw);
+      const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zeros = make_uint4(0u, 0u, 0u, 0u);
+      constexpr int kTable16 = (int)(sizeof(KeyT) * kSuspectSlots / 16);
+#pragma unroll
+      for (int i = threadIdx.x; i < kClear16; i += T) z[i] = i < kTable16 ? ones : zeros;
+    }
     if (threadIdx.x == 0) { s_c1 = 0; s_c2 = 0; }
     __syncthreads();
     // stage 1a: set bits
     uint32_t bits[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
+      if (e >= ne) break;
       bits[e] = (uint32_t)(key_hash((uint64_t)key[e]) >> bit_shift) & kBitMask;
-      if (key[e] != kEmpty) {
-        const uint32_t w = bits[e] >> 5, m = 1u << (bits[e] & 31u);
-        if (atomicOr(&map_a[w], m) & m) atomicOr(&map_b[w], m);
-      }
+      const uint32_t w = bits[e] >> 5, m = 1u << (bits[e] & 31u);
+      if (atomicOr(&map_a[w], m) & m) atomicOr(&map_b[w], m);
     }
     __syncthreads();
-    // stage 1b: collect the suspects
-    bool suspect[E];
+    // stage 1b: collect the suspects -- one shared-memory atomic per warp claims the slots of its suspects
+    uint32_t smask = 0;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      suspect[e] = key[e] != kEmpty && ((map_b[bits[e] >> 5] >> (bits[e] & 31u)) & 1u);
-      if (suspect[e]) {
-        uint32_t pos = atomicAdd(&s_c1, 1u);
-        if (pos < (uint32_t)kLeafSortCap) { c_keys[pos] = key[e]; c_vals[pos] = val[e]; }
+      if (e >= ne) break;
+      smask |= ((map_b[bits[e] >> 5] >> (bits[e] & 31u)) & 1u) << e;
+    }
+    const uint32_t mine = __popc(smask);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    uint32_t wbase = 0;
+    if (lane == 31 && incl) wbase = atomicAdd(&s_c1, incl);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    if (smask) {
+      uint32_t pos = wbase + incl - mine;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if ((smask >> e) & 1u) {
+          if (pos < (uint32_t)kLeafSortCap) { c_keys[pos] = key[e]; c_vals[pos] = my_vals[threadIdx.x + e * T]; }
+          ++pos;
+        }
       }
     }
     __syncthreads();
@@ -776,15 +792,16 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict
       if (threadIdx.x == 0) *unsorted = 1u;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
-        uint32_t m = __ballot_sync(0xffffffffu, suspect[e]);
+        const bool sus = (smask >> e) & 1u;
+        uint32_t m = __ballot_sync(0xffffffffu, sus);
         if (m) {
           unsigned long long basepos = 0;
           if (lane == 0) basepos = atomicAdd(n_cand, (unsigned long long)__popc(m));
           basepos = __shfl_sync(0xffffffffu, basepos, 0);
-          if (suspect[e]) {
+          if (sus) {
             unsigned long long dst = basepos + __popc(m & lanemask_lt());
             cand_keys[dst] = key[e];
-            cand_vals[dst] = val[e];
+            cand_vals[dst] = my_vals[threadIdx.x + e * T];
           }
         }
       }
@@ -815,9 +832,8 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict
     __syncthreads();
     const uint32_t c2 = s_c2;
     if (c2 == 0) continue;
-    {  // order them: rank by counting, a power-of-two group of threads per record
-      int lg = 0;
-      while ((2u << lg) * c2 <= (uint32_t)T) ++lg;           // 2^lg threads per record, 2^lg * c2 <= T
+    {  // order them: rank by counting, a power-of-two group of threads per record (2^lg * c2 <= T)
+      const int lg = 31 - __clz((uint32_t)T / c2);
       const uint32_t cand = threadIdx.x >> lg, seg = threadIdx.x & ((1u << lg) - 1u);
       if (cand < c2) {
         const KeyT ck = c_keys[cand];
