@@ -75,23 +75,42 @@ constexpr int kTileItems = kTileBytes / kTileThreads;
 constexpr int kPackedWords = kTileBytes / 16 + 3;   // tile + 32-base halo, rounded up
 constexpr int kSliceCap = 1024;                     // offsets cached per tile (parts overlapping the tile)
 
+constexpr int kTileFlags = 64;                      // per-part flag bytes cached per tile (uniform parts of >= 70 bases)
+constexpr int kTileFlagMinLen = 70;
 struct TileStage {
   uint32_t packed[kPackedWords + 1];
   int64_t slice[kSliceCap + 2];
   int64_t first_part;
   int n_slice;                 // number of parts cached in `slice` (0 = uniform or overflow -> global search)
+  int n_flag;                  // > 0: part_flag[i] is the flag byte of part first_part + i
+  uint8_t part_flag[kTileFlags];
 };
+
+// What one thread fetches from global memory for a tile; kept in registers so that the loads of the NEXT tile can be in
+// flight while the current tile is written out (tile_fetch / tile_commit), or consumed at once (tile_load).
+struct TileRegs { uint4 v; uint32_t flag; };
 
 // Stage one byte tile: 2-bit pack the bytes [g_lo, g_lo + 4096 + 48) and cache the offsets of its parts.
 // `tid` is the thread's index inside the group of kTileThreads threads that works on this tile.
-__device__ __forceinline__ void tile_load(const Parts& P, int64_t tile, TileStage& s, int tid) {
+static_assert(kPackedWords <= kTileThreads, "one 16-byte word per thread");
+__device__ __forceinline__ void tile_fetch(const Parts& P, int64_t tile, int tid, const uint8_t* flags, TileRegs& r) {
   const int64_t g_lo = tile * kTileBytes;
-  for (int i = tid; i < kPackedWords; i += kTileThreads) {
-    int64_t g = g_lo + 16 * (int64_t)i;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (g < P.total_len + 48) v = *reinterpret_cast<const uint4*>(P.ascii + g);   // buffer is padded and 16B aligned
-    s.packed[i] = pack16(v);
+  const int64_t g = g_lo + 16 * (int64_t)tid;
+  r.v = make_uint4(0, 0, 0, 0);
+  r.flag = 0;
+  if (tid < kPackedWords && g < P.total_len + 48) r.v = __ldg(reinterpret_cast<const uint4*>(P.ascii + g));   // buffer is padded and 16B aligned
+  if (flags != nullptr && P.uniform_len >= kTileFlagMinLen && tid < kTileFlags) {
+    const int64_t p = g_lo / P.uniform_len + tid;
+    if (p < P.n_parts) r.flag = flags[p];
   }
+}
+
+__device__ __forceinline__ void tile_commit(const Parts& P, int64_t tile, TileStage& s, int tid, const uint8_t* flags, const TileRegs& r) {
+  const int64_t g_lo = tile * kTileBytes;
+  if (tid < kPackedWords) s.packed[tid] = pack16(r.v);
+  const bool cached_flags = flags != nullptr && P.uniform_len >= kTileFlagMinLen;
+  if (cached_flags && tid < kTileFlags) s.part_flag[tid] = (uint8_t)r.flag;
+  if (tid == 0) s.n_flag = cached_flags ? kTileFlags : 0;
   if (P.uniform_len == 0) {
     int64_t p_lo = P.tile_first[tile];
     int64_t p_hi = P.tile_first[tile + 1];            // first part of the next tile: covers every part of this one
@@ -103,6 +122,12 @@ __device__ __forceinline__ void tile_load(const Parts& P, int64_t tile, TileStag
     s.first_part = g_lo / P.uniform_len;
     s.n_slice = 0;
   }
+}
+
+__device__ __forceinline__ void tile_load(const Parts& P, int64_t tile, TileStage& s, int tid, const uint8_t* flags = nullptr) {
+  TileRegs r;
+  tile_fetch(P, tile, tid, flags, r);
+  tile_commit(P, tile, s, tid, flags, r);
 }
 
 // Part containing byte g and the end offset of that part.  Requires g < total_len.
@@ -185,7 +210,9 @@ __device__ __forceinline__ void tile_windows_blocked(const Parts& P, const TileS
   uint64_t rc = revcomp2(fwd, k);
   auto part_usable = [&](int64_t part) -> int {
     if (part < P.part_lo || part >= P.part_hi) return 0;
-    return SKIP_FLAGGED ? (flags[part] == 0 ? 1 : 0) : 1;
+    if (!SKIP_FLAGGED) return 1;
+    if (s.n_flag > 0) return s.part_flag[(int)(part - s.first_part)] == 0 ? 1 : 0;    // flag bytes cached with the tile
+    return flags[part] == 0 ? 1 : 0;
   };
   if (P.uniform_len > 0) {
     const uint32_t L = (uint32_t)P.uniform_len;

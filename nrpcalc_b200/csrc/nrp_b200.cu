@@ -101,7 +101,8 @@ template <typename KeyT> constexpr size_t filter_smem_large() { return (sizeof(K
 template <typename KeyT> constexpr size_t filter_smem_small() {
   return (sizeof(KeyT) + 1) * 2 * (size_t)(kFilterThreads * kFilterItemsSmall) + (kFilterStaged ? (sizeof(KeyT) + 4) * (size_t)kFilterCapSmall : 0);
 }
-constexpr int64_t kDefaultLeafTarget = 5500;                // records per leaf bucket aimed for (filter capacity 8192)
+constexpr int64_t kDefaultLeafTarget = 2750;                // records per leaf bucket aimed for (two 512-thread filter CTAs per SM, capacity 4096)
+constexpr int64_t kLargeLeafTarget = 6200;                  // when the bits run out: one 1024-thread filter CTA per SM, capacity 8192
 constexpr int kMaxLeafBits = 15;                            // exact path: 2^15 u32 counters = 128 KB of shared memory
 constexpr int kMaxDirectBits = 2 * kMaxLevelBits;           // direct path: two levels of <= 9 bits
 
@@ -122,6 +123,8 @@ struct nrp_ctx {
   int64_t opt_no_window_carry = 0;
   int64_t opt_no_bloom = 0;
   int64_t opt_pass_records = 210000000;   // exact path: more records than this per device are processed in several hash-slice passes
+  int64_t opt_persistent_split = 0;       // extraction kernel: persistent CTAs with register prefetch (1) or one CTA per byte tile (0)
+  int64_t opt_r1_bias = 0;                // added to the number of level-1 bits (tuning)
   int64_t opt_direct = 1;                 // fixed-region partition without a histogram pass (falls back to the exact path on overflow)
 
   // background
@@ -206,6 +209,11 @@ __global__ void k_gather_first_part(const int64_t* indptr, const uint32_t* membe
 }
 
 inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+// persistent CTAs of the extraction kernel: two per SM (registers and shared memory allow no more)
+inline unsigned split_grid(const nrp_ctx* c) {
+  const int64_t cap = c->opt_persistent_split ? (int64_t)c->n_sms * 2 : (int64_t)0x7fffffff;
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(c->shard_tiles, cap));
+}
 
 struct StageTimer {
   nrp_ctx* c;
@@ -241,10 +249,10 @@ int configure_kernels(nrp_ctx* c) {
   CU(cudaFuncSetAttribute((k_split_from_ascii<KeyT, 2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, split_smem));
   CU(cudaFuncSetAttribute((k_split_from_records<KeyT, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<KeyT>)));
   CU(cudaFuncSetAttribute((k_split_from_records<KeyT, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<KeyT>)));
-  CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, 4, 2048, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)filter_bloom_smem<KeyT, 4096, 2048>()));
-  CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)filter_bloom_smem<KeyT, 8192, 4096>()));
+  CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, 512, 8, 2048, 2, 512>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)filter_bloom_smem<KeyT, 4096, 2048, 512>()));
+  CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1, 1024>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)filter_bloom_smem<KeyT, 8192, 4096, 1024>()));
   CU(cudaFuncSetAttribute((k_filter<KeyT, kFilterThreads, kFilterItems, kFilterCap, false>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)filter_smem_large<KeyT>()));
   CU(cudaFuncSetAttribute((k_filter<KeyT, kFilterThreads, kFilterItemsSmall, kFilterCapSmall, kFilterStaged>), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -314,6 +322,8 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "no_window_carry") c->opt_no_window_carry = value > 0 ? 1 : 0;
   else if (n == "no_bloom") c->opt_no_bloom = value > 0 ? 1 : 0;
   else if (n == "pass_records") c->opt_pass_records = value <= 0 ? 210000000 : value;
+  else if (n == "persistent_split") c->opt_persistent_split = value > 0 ? 1 : 0;
+  else if (n == "r1_bias") c->opt_r1_bias = value;
   else if (n == "direct") c->opt_direct = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
   return NRP_OK;
@@ -479,10 +489,14 @@ LevelPlan plan_levels(const nrp_ctx* c, int64_t m, bool direct, int fixed_r1 = -
   int max_bits = std::min(direct ? kMaxDirectBits : kMaxLeafBits, fixed_r1 >= 0 ? fixed_r1 + lv : 2 * lv);
   int bits = fixed_r1 >= 0 ? fixed_r1 + 1 : 1;            // a pre-partitioned input always takes one more level (it merges the senders' regions)
   while (bits < max_bits && (m >> bits) > c->opt_leaf_target) ++bits;
+  // the small-leaf target is out of reach: take the fewest bits that still fit the large filter variant
+  if (c->opt_leaf_target == kDefaultLeafTarget && (m >> bits) > kDefaultLeafTarget)
+    while (bits > (fixed_r1 >= 0 ? fixed_r1 + 1 : 1) && (m >> (bits - 1)) <= kLargeLeafTarget) --bits;
   LevelPlan p;
   p.bits = bits;
   if (fixed_r1 >= 0) p.r1 = fixed_r1;
-  else p.r1 = bits <= std::min(lv, 8) ? bits : std::min(lv, (bits + 1) / 2);
+  else p.r1 = bits <= std::min(lv, 8) ? bits : std::max(1, std::min(std::min(lv, bits - 1), (bits + 1) / 2 + (int)c->opt_r1_bias));
+  if (fixed_r1 < 0 && bits - p.r1 > lv) p.r1 = bits - lv;
   p.r2 = bits - p.r1;
   p.cap1 = region_cap((double)m / (double)(1ll << p.r1), 1024);
   p.cap2 = region_cap((double)m / (double)(1ll << bits), 64);
@@ -502,13 +516,13 @@ int launch_filter(nrp_ctx* c, const KeyT* leaf_keys, const uint32_t* leaf_vals, 
   const uint32_t cap = (uint32_t)std::min<int64_t>(c->opt_filter_cap, small ? kFilterCapSmall : kFilterCap);
   uint32_t* n_over = reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED);
   uint32_t* unsorted = reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED);
-  if (small && !c->opt_no_bloom)
-    NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 4, 2048, 2><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * 2), kFilterThreads,
-                                                               filter_bloom_smem<KeyT, 4096, 2048>(), st>>>(
+  if (small && !c->opt_no_bloom)      // two 512-thread CTAs per SM, leaves of up to 4096 records
+    NRP_LAUNCH((k_filter_bloom<KeyT, 512, 8, 2048, 2, 512><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * 2), 512,
+                                                               filter_bloom_smem<KeyT, 4096, 2048, 512>(), st>>>(
         leaf_keys, leaf_vals, leaves, n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
-  else if (!c->opt_no_bloom)
-    NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms), kFilterThreads,
-                                                               filter_bloom_smem<KeyT, 8192, 4096>(), st>>>(
+  else if (!c->opt_no_bloom)          // one 1024-thread CTA per SM, leaves of up to 8192 records
+    NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1, 1024><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms), kFilterThreads,
+                                                               filter_bloom_smem<KeyT, 8192, 4096, 1024>(), st>>>(
         leaf_keys, leaf_vals, leaves, n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
   else if (small)
     NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItemsSmall, kFilterCapSmall, kFilterStaged><<<fgrid, kFilterThreads, fsm, st>>>(
@@ -562,8 +576,8 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
   const RegionLimit lim2{lp.cap2, 0u, overflow, nullptr};
   if (m_max > 0 && !prepart) {
     if (from_ascii) {
-      NRP_LAUNCH((k_split_from_ascii<KeyT, 0, false><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-          P, c->flags.as<uint8_t>(), k, r1, 0, c->part_base, c->j_bits, PassSel{0, 0u, 0u}, level1_cursor, l1_keys, l1_vals, lim1, PeerBuffers{}, 0)));
+      NRP_LAUNCH((k_split_from_ascii<KeyT, 0, false><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+          P, c->flags.as<uint8_t>(), k, r1, 0, c->shard_tiles, c->part_base, c->j_bits, PassSel{0, 0u, 0u}, level1_cursor, l1_keys, l1_vals, lim1, PeerBuffers{}, 0)));
     } else {
       TRY(build_tiles(c, src.ext, src.n_seg, 0xffffffffu, 0, nullptr));
       const unsigned grid = (unsigned)std::min<int64_t>(m_max / kSplitTile + src.n_seg, (int64_t)c->n_sms * 4);
@@ -677,8 +691,8 @@ int stage_bulk_exact(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer&
     uint32_t* level1_cursor = r2 > 0 ? c->cursor1.as<uint32_t>() : c->cursor2.as<uint32_t>();
     if (m_max > 0) {
       if (from_ascii) {
-        NRP_LAUNCH((k_split_from_ascii<KeyT, 0, true><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-            P, c->flags.as<uint8_t>(), k, r1, 0, c->part_base, c->j_bits, sel, level1_cursor, leaf_keys, leaf_vals, no_limit, PeerBuffers{}, 0)));
+        NRP_LAUNCH((k_split_from_ascii<KeyT, 0, true><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+            P, c->flags.as<uint8_t>(), k, r1, 0, c->shard_tiles, c->part_base, c->j_bits, sel, level1_cursor, leaf_keys, leaf_vals, no_limit, PeerBuffers{}, 0)));
       } else {
         const unsigned grid = (unsigned)std::min<int64_t>(src_tiles_max, (int64_t)c->n_sms * 4);
         NRP_LAUNCH((k_split_from_records<KeyT, true><<<grid, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
@@ -1034,8 +1048,8 @@ int shard_extract_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int internal_r
   CU(cudaMemcpyAsync(c->h_counters + 32, c->hist.ptr, 4 * (size_t)n_owners, cudaMemcpyDeviceToHost, st));
   tm.begin(NRP_T_SPLIT1);
   if (c->shard_m_max > 0)
-    NRP_LAUNCH((k_split_from_ascii<KeyT, 1, false><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, 8, n_owners, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>(),
+    NRP_LAUNCH((k_split_from_ascii<KeyT, 1, false><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+        P, c->flags.as<uint8_t>(), k, 8, n_owners, c->shard_tiles, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>(),
         RegionLimit{0u, 0u, nullptr, nullptr}, PeerBuffers{}, 0)));
   CU(cudaGetLastError());
   tm.finish(c->timings);
@@ -1119,8 +1133,8 @@ int shard_scatter_impl(nrp_ctx* c, int k, const int64_t* write_offsets) {
   StageTimer tm(c);
   tm.begin(NRP_T_SPLIT1);
   if (c->shard_m_max > 0)
-    NRP_LAUNCH((k_split_from_ascii<KeyT, 1, false><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, 8, c->n_owners, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr,
+    NRP_LAUNCH((k_split_from_ascii<KeyT, 1, false><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+        P, c->flags.as<uint8_t>(), k, 8, c->n_owners, c->shard_tiles, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr,
         RegionLimit{0u, 0u, nullptr, nullptr}, c->peers, 1)));
   CU(cudaGetLastError());
   tm.finish(c->timings);
@@ -1191,8 +1205,8 @@ int shard_scatter_direct_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int int
   NRP_LAUNCH((k_init_owner_cursors<<<grid_for(nd, 256), 256, 0, st>>>(c->cursor1.as<uint32_t>(), c->region_ends.as<uint32_t>(), nd, c->sh_r1,
                                                                     (uint32_t)n_owners, (uint32_t)c->my_rank, c->sh_cap1s)));
   if (c->shard_m_max > 0)
-    NRP_LAUNCH((k_split_from_ascii<KeyT, 2, false><<<(unsigned)c->shard_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, c->sh_r1, n_owners, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr,
+    NRP_LAUNCH((k_split_from_ascii<KeyT, 2, false><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+        P, c->flags.as<uint8_t>(), k, c->sh_r1, n_owners, c->shard_tiles, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr,
         RegionLimit{c->sh_cap1s, 0u, reinterpret_cast<uint32_t*>(cnt + CNT_SCATTER_OVERFLOW), c->region_ends.as<uint32_t>()}, c->peers_d, 1)));
   PeerEnds pe;
   for (int o = 0; o < kMaxPeers; ++o) pe.ptr[o] = c->peer_ends[o];

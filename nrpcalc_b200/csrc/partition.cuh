@@ -76,10 +76,8 @@ constexpr uint32_t kNoSpace = 0xffffffffu;
 // reorder the tile through shared memory and write each bucket's run contiguously.
 // peer_shift >= 0 with peers: the buffers of digit d are those of owner d >> peer_shift (peer stores over NVLink).
 template <typename KeyT>
-__device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&key)[kSplitItems], const uint32_t (&val)[kSplitItems],
-                                              const uint32_t (&dr)[kSplitItems], int nb,
-                                              uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals, RegionLimit lim,
-                                              const PeerBuffers* peers = nullptr, int peer_shift = 0) {
+__device__ __forceinline__ void split_reorder(SplitSmem<KeyT>& s, const KeyT (&key)[kSplitItems], const uint32_t (&val)[kSplitItems],
+                                              const uint32_t (&dr)[kSplitItems], int nb, uint32_t* cursor, RegionLimit lim) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   constexpr int kWarps = kSplitThreads / 32;
   // exclusive scan of cnt[0..nb) by the first nb threads (nb <= kLevelBuckets <= blockDim)
@@ -129,6 +127,12 @@ __device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&k
     }
   }
   __syncthreads();
+}
+
+// second half: every bucket's run of the reordered tile goes to its place in global (or peer) memory
+template <typename KeyT>
+__device__ __forceinline__ void split_flush(SplitSmem<KeyT>& s, KeyT* out_keys, uint32_t* out_vals, const PeerBuffers* peers = nullptr,
+                                            int peer_shift = 0) {
   const uint32_t total = s.total;
   for (uint32_t i = threadIdx.x; i < total; i += kSplitThreads) {
     const uint32_t d = s.dig[i];
@@ -144,6 +148,15 @@ __device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&k
       out_vals[dst] = s.vals[i];
     }
   }
+}
+
+template <typename KeyT>
+__device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&key)[kSplitItems], const uint32_t (&val)[kSplitItems],
+                                              const uint32_t (&dr)[kSplitItems], int nb,
+                                              uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals, RegionLimit lim,
+                                              const PeerBuffers* peers = nullptr, int peer_shift = 0) {
+  split_reorder<KeyT>(s, key, val, dr, nb, cursor, lim);
+  split_flush<KeyT>(s, out_keys, out_vals, peers, peer_shift);
 }
 
 // ---- histogram of leaf buckets straight from the part buffer (exact path) ---------------------------------
@@ -239,46 +252,51 @@ __global__ void __launch_bounds__(1024) k_region_total(const uint32_t* cursor, u
 // Record value = part index, or (part << j_bits) | window index when both fit 32 bits (j_bits > 0): sorting by value
 // is then sorting by (part, window), and a group's first record carries the group's rank for free.
 template <typename KeyT, int MODE, bool PASSES>
-__global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, const uint8_t* flags, int k, int r1, int n_owners,
+__global__ void __launch_bounds__(kTileThreads, 2) k_split_from_ascii(Parts P, const uint8_t* flags, int k, int r1, int n_owners, int64_t n_tiles,
                                                                   uint32_t part_base, int j_bits, PassSel sel, uint32_t* cursor, KeyT* out_keys,
                                                                   uint32_t* out_vals, RegionLimit lim, PeerBuffers peers, int use_peers) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SplitSmem<KeyT>& s = *reinterpret_cast<SplitSmem<KeyT>*>(smem_raw);
   TileStage& stage = *reinterpret_cast<TileStage*>(smem_raw + sizeof(SplitSmem<KeyT>));
-  const int64_t tile = P.tile_lo + blockIdx.x;
   const int nb = MODE == 0 ? (1 << r1) : MODE == 1 ? n_owners : (n_owners << r1);
   static_assert(kLevelBuckets == kTileThreads, "one counter per thread");
-  s.cnt[threadIdx.x] = 0;
-  tile_load(P, tile, stage, threadIdx.x);
-  __syncthreads();
-  KeyT key[kSplitItems];
-  uint32_t val[kSplitItems], dr[kSplitItems];
-#pragma unroll
-  for (int e = 0; e < kSplitItems; ++e) { dr[e] = 0xffffffffu; key[e] = 0; val[e] = 0; }
   const uint32_t j_mask = j_bits ? 0xffffffffu : 0u;
   const int top_shift = 64 - r1;
-  tile_windows_blocked<true>(P, stage, tile, k, flags, threadIdx.x, [&](int e, uint64_t canon, uint32_t part, uint32_t j, bool) {
-    uint32_t d;
-    if (MODE == 1) {
-      d = owner_hash(canon) % (uint32_t)n_owners;
-      if (PASSES && !sel.accept(key_hash(canon))) return;
-    } else {
-      const uint64_t h = key_hash(canon);
-      if (PASSES && !sel.accept(h)) return;
-      d = MODE == 0 ? (uint32_t)(h >> top_shift) : ((owner_of(canon, (uint32_t)n_owners) << r1) | (r1 ? (uint32_t)(h >> top_shift) : 0u));
-    }
-    const uint32_t rank = atomicAdd(&s.cnt[d], 1u);
+  // persistent CTAs: the global loads of the next tile are issued before the current tile is written out
+  TileRegs pre;
+  if ((int64_t)blockIdx.x < n_tiles) tile_fetch(P, P.tile_lo + blockIdx.x, threadIdx.x, flags, pre);
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t tile = P.tile_lo + t;
+    s.cnt[threadIdx.x] = 0;
+    tile_commit(P, tile, stage, threadIdx.x, flags, pre);
+    __syncthreads();
+    KeyT key[kSplitItems];
+    uint32_t val[kSplitItems], dr[kSplitItems];
 #pragma unroll
-    for (int q = 0; q < kSplitItems; ++q)
-      if (q == e) { key[q] = (KeyT)canon; val[q] = ((part_base + part) << j_bits) | (j & j_mask); dr[q] = (d << 16) | rank; }
-  });
-  __syncthreads();
-  if (MODE == 0)
-    split_scatter<KeyT>(s, key, val, dr, nb, cursor, out_keys, out_vals, lim);
-  else if (MODE == 1)
-    split_scatter<KeyT>(s, key, val, dr, nb, cursor, out_keys, out_vals, lim, use_peers ? &peers : nullptr, 0);
-  else
-    split_scatter<KeyT>(s, key, val, dr, nb, cursor, out_keys, out_vals, lim, &peers, r1);
+    for (int e = 0; e < kSplitItems; ++e) { dr[e] = 0xffffffffu; key[e] = 0; val[e] = 0; }
+    tile_windows_blocked<true>(P, stage, tile, k, flags, threadIdx.x, [&](int e, uint64_t canon, uint32_t part, uint32_t j, bool) {
+      uint32_t d;
+      if (MODE == 1) {
+        d = owner_hash(canon) % (uint32_t)n_owners;
+        if (PASSES && !sel.accept(key_hash(canon))) return;
+      } else {
+        const uint64_t h = key_hash(canon);
+        if (PASSES && !sel.accept(h)) return;
+        d = MODE == 0 ? (uint32_t)(h >> top_shift) : ((owner_of(canon, (uint32_t)n_owners) << r1) | (r1 ? (uint32_t)(h >> top_shift) : 0u));
+      }
+      const uint32_t rank = atomicAdd(&s.cnt[d], 1u);
+#pragma unroll
+      for (int q = 0; q < kSplitItems; ++q)
+        if (q == e) { key[q] = (KeyT)canon; val[q] = ((part_base + part) << j_bits) | (j & j_mask); dr[q] = (d << 16) | rank; }
+    });
+    __syncthreads();
+    split_reorder<KeyT>(s, key, val, dr, nb, cursor, lim);
+    if (t + gridDim.x < n_tiles) tile_fetch(P, tile + gridDim.x, threadIdx.x, flags, pre);
+    if (MODE == 0) split_flush<KeyT>(s, out_keys, out_vals);
+    else if (MODE == 1) split_flush<KeyT>(s, out_keys, out_vals, use_peers ? &peers : nullptr, 0);
+    else split_flush<KeyT>(s, out_keys, out_vals, &peers, r1);
+    __syncthreads();
+  }
 }
 
 // ---- level 2 (or level 1 when the records are already in HBM): segmented split of records ---------------
@@ -287,30 +305,33 @@ __global__ void __launch_bounds__(kTileThreads) k_split_from_ascii(Parts P, cons
 // first child cursor}.  Persistent CTAs walk the tile list; the next tile's descriptor is fetched one tile ahead.
 // Child bucket = hash bits [64 - r_done - r2, 64 - r_done).
 template <typename KeyT, bool PASSES>
-__global__ void __launch_bounds__(kSplitThreads) k_split_from_records(const KeyT* __restrict__ in_keys, const uint32_t* __restrict__ in_vals,
+__global__ void __launch_bounds__(kSplitThreads, 2) k_split_from_records(const KeyT* __restrict__ in_keys, const uint32_t* __restrict__ in_vals,
                                                                      const uint4* __restrict__ tile_desc, const uint32_t* n_tiles_ptr,
                                                                      int r_done, int r2, PassSel sel, uint32_t* cursor, KeyT* out_keys,
                                                                      uint32_t* out_vals, RegionLimit lim) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SplitSmem<KeyT>& s = *reinterpret_cast<SplitSmem<KeyT>*>(smem_raw);
   const uint32_t n_tiles = *n_tiles_ptr;
-  uint4 next = blockIdx.x < n_tiles ? __ldg(tile_desc + blockIdx.x) : make_uint4(0, 0, 0, 0);
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint4 d4 = next;
-    if (tile + gridDim.x < n_tiles) next = __ldg(tile_desc + tile + gridDim.x);
-    const uint32_t start = d4.x, end = d4.y, child0 = d4.z;
-    s.cnt[threadIdx.x] = 0;
-    __syncthreads();
-    KeyT key[kSplitItems];
-    uint32_t val[kSplitItems], dr[kSplitItems];
-    const uint32_t mask = (1u << r2) - 1u;
+  const uint32_t mask = (1u << r2) - 1u;
+  KeyT key[kSplitItems];
+  uint32_t val[kSplitItems], dr[kSplitItems];
+  // the loads of a tile are issued while the previous tile is still being written out (its registers are free by then)
+  auto load_tile = [&](const uint4& t4) {
 #pragma unroll
     for (int e = 0; e < kSplitItems; ++e) {                  // all loads first: 16 independent requests per thread
-      uint32_t idx = start + threadIdx.x + e * kSplitThreads;
-      bool ok = idx < end;
+      const uint32_t idx = t4.x + threadIdx.x + e * kSplitThreads;
+      const bool ok = idx < t4.y;
       key[e] = ok ? __ldg(in_keys + idx) : KeyT(0);
       val[e] = ok ? __ldg(in_vals + idx) : 0u;
     }
+  };
+  uint4 d4 = blockIdx.x < n_tiles ? __ldg(tile_desc + blockIdx.x) : make_uint4(0, 0, 0, 0);
+  uint4 next = blockIdx.x + gridDim.x < n_tiles ? __ldg(tile_desc + blockIdx.x + gridDim.x) : make_uint4(0, 0, 0, 0);
+  if (blockIdx.x < n_tiles) load_tile(d4);
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t start = d4.x, end = d4.y, child0 = d4.z;
+    s.cnt[threadIdx.x] = 0;
+    __syncthreads();
 #pragma unroll
     for (int e = 0; e < kSplitItems; ++e) {
       uint32_t idx = start + threadIdx.x + e * kSplitThreads;
@@ -326,7 +347,13 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_from_records(const KeyT
     __syncthreads();
     RegionLimit tile_lim = lim;
     tile_lim.first = child0;
-    split_scatter<KeyT>(s, key, val, dr, 1 << r2, cursor + child0, out_keys, out_vals, tile_lim);
+    split_reorder<KeyT>(s, key, val, dr, 1 << r2, cursor + child0, tile_lim);
+    d4 = next;
+    if (tile + gridDim.x < n_tiles) {
+      load_tile(d4);
+      if (tile + 2 * gridDim.x < n_tiles) next = __ldg(tile_desc + tile + 2 * gridDim.x);
+    }
+    split_flush<KeyT>(s, out_keys, out_vals);
     __syncthreads();
   }
 }
@@ -643,19 +670,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-constexpr int kSuspectSlots = 2 * kLeafSortCap;
 // capacity of a leaf = T * E records; WORDS = 32-bit words per bit map (16 bits per record or more).
 // Shared memory: exact table + suspect list + two bit maps + key staging (one leaf) + value staging (two leaves, ping-pong).
-template <typename KeyT, int CAP, int WORDS> constexpr size_t filter_bloom_smem() {
-  return sizeof(KeyT) * (kSuspectSlots + kLeafSortCap) + 4 * (2 * WORDS + 2 * kLeafSortCap) + kSuspectSlots +
+// SORTCAP = suspects of one leaf that the exact stage and the in-leaf ordering can take (more: the global sort runs).
+template <typename KeyT, int CAP, int WORDS, int SORTCAP> constexpr size_t filter_bloom_smem() {
+  return sizeof(KeyT) * (2 * SORTCAP + SORTCAP) + 4 * (2 * WORDS + 2 * SORTCAP) + 2 * SORTCAP +
          sizeof(KeyT) * (CAP + 8) + 2 * 4 * (CAP + 8) + 128;
 }
 
-template <typename KeyT, int T, int E, int WORDS, int MINB>
+template <typename KeyT, int T, int E, int WORDS, int MINB, int SORTCAP>
 __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, LeafExtents leaves,
                                                       uint32_t n_leaf, int leaf_bits, uint32_t cap, KeyT* cand_keys, uint32_t* cand_vals,
                                                       unsigned long long* n_cand, uint32_t* n_oversized, uint32_t* unsorted) {
   constexpr int kBloomWords = WORDS, kBloomCap = T * E;
+  constexpr int kSuspectSlots = 2 * SORTCAP, kLeafSortCap = SORTCAP;
+  static_assert(SORTCAP <= T, "one thread per suspect");
   constexpr uint32_t kBitMask = (uint32_t)WORDS * 32u - 1u;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // 16-byte aligned blocks first (they are cleared with 128-bit stores)
