@@ -250,17 +250,21 @@ def main():
 
     # ---- end-to-end leg: host buffers in, host results out
     e2e_times = []
+    e2e_parts = []
     h2d = d2h = 0
     for step in range(2 + args.steps):
         flush.fill_(1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ctx.load_parts(host_ascii.numpy(), off, ids)
+        t1 = time.perf_counter()
         ctx.build(k, cfg['internal_repeats'], want_edges)
+        t2 = time.perf_counter()
         res = ctx.fetch(want_keys=True)
         dt = time.perf_counter() - t0
         if step >= 2:
             e2e_times.append(dt)
+            e2e_parts.append((t1 - t0, t2 - t1, t0 + dt - t2))
         h2d = buf.nbytes + off.nbytes + ids.nbytes
         d2h = (res.flags.nbytes + res.indptr.nbytes + res.members.nbytes + res.first_window.nbytes + res.keys.nbytes +
                res.last_single.nbytes + (res.edges[0].nbytes + res.edges[1].nbytes if res.edges else 0) + 16 * 8 * 2)
@@ -302,7 +306,9 @@ def main():
                            2 * m * (counts['key_bytes'] + 4) / 1e9)},
             'parts_per_s': cfg['n'] / (ms_per_step * 1e-3),
             'e2e': {'value': e2e_value, 'unit': 'k-mers/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                    'ms_per_step': 1e3 * sum(e2e_times) / len(e2e_times), 'path': 'C ABI: nrp_load_parts(host) + nrp_build + result getters'},
+                    'ms_per_step': 1e3 * sum(e2e_times) / len(e2e_times),
+                    'ms_load_build_fetch': [1e3 * sum(p[i] for p in e2e_parts) / len(e2e_parts) for i in range(3)],
+                    'path': 'C ABI: nrp_load_parts(host buffers) + nrp_build + nrp_result_host (page-locked result buffers)'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
             'stage_ms': {name: v / args.steps for name, v in stage_ms.items()},
             'result': {name: counts[name] for name in ('records', 'excluded', 'groups', 'members', 'edges', 'candidates', 'runs', 'buckets', 'oversized',

@@ -130,6 +130,22 @@ int nrp_result_last_single(nrp_ctx* ctx, int32_t* last_single);
 /* u[n_edges] < v[n_edges], every conflicting id pair exactly once, order unspecified */
 int nrp_result_edges(nrp_ctx* ctx, uint32_t* u, uint32_t* v);
 
+/* All results of the last build in ONE call: the library copies them into its own page-locked host buffers (full-speed DMA,
+ * one synchronisation) and returns pointers that stay valid until the next nrp_load_parts / nrp_build / nrp_ctx_destroy on this
+ * context.  keys is NULL unless want_keys != 0; edge_u / edge_v are NULL when edges were not requested. */
+typedef struct nrp_host_result {
+  const uint8_t*  flags;         /* n_parts */
+  const int64_t*  indptr;        /* n_groups + 1 */
+  const uint32_t* members;       /* n_members */
+  const uint32_t* first_window;  /* n_groups */
+  const uint64_t* keys;          /* n_groups */
+  const int32_t*  last_single;   /* n_parts */
+  const uint32_t* edge_u;        /* n_edges */
+  const uint32_t* edge_v;        /* n_edges */
+  int64_t n_parts, n_groups, n_members, n_edges;
+} nrp_host_result;
+int nrp_result_host(nrp_ctx* ctx, int want_keys, nrp_host_result* out);
+
 /* ---- sharded path: one process per GPU, k-mer space hash-partitioned across n_owners ranks ---------------------
  * Every rank stages ALL parts with nrp_load_parts (record values are then global part indices and any rank can
  * read any part), extracts the records of its own contiguous shard of parts, and owns the k-mers with

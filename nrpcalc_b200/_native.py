@@ -23,6 +23,21 @@ E_ARG, E_CUDA, E_OOM, E_UNSUPPORTED, E_STATE, E_EDGES = -1, -2, -3, -4, -5, -6
 _lib = None
 
 
+class HostResult(ctypes.Structure):
+    """nrp_host_result (include/nrp_b200.h): pointers into the library's page-locked result buffers."""
+    _fields_ = [('flags', ctypes.c_void_p), ('indptr', ctypes.c_void_p), ('members', ctypes.c_void_p), ('first_window', ctypes.c_void_p),
+                ('keys', ctypes.c_void_p), ('last_single', ctypes.c_void_p), ('edge_u', ctypes.c_void_p), ('edge_v', ctypes.c_void_p),
+                ('n_parts', ctypes.c_int64), ('n_groups', ctypes.c_int64), ('n_members', ctypes.c_int64), ('n_edges', ctypes.c_int64)]
+
+
+def _view(address, count, dtype):
+    """numpy view (no copy) of `count` items of library-owned host memory"""
+    if count == 0 or not address:
+        return np.zeros(0, dtype=dtype)
+    nbytes = int(count) * np.dtype(dtype).itemsize
+    return np.frombuffer((ctypes.c_char * nbytes).from_address(address), dtype=dtype, count=int(count))
+
+
 class NativeError(RuntimeError):
     def __init__(self, code, message):
         super().__init__('libnrpb200 error {}: {}'.format(code, message))
@@ -65,6 +80,7 @@ def _declare(lib):
         'nrp_shard_scatter_peers': (c_ctx, i32, ptr),
         'nrp_shard_group_received': (c_ctx, i64, i32, i32),
         'nrp_result_device': (c_ctx, i32, ctypes.POINTER(ptr), ctypes.POINTER(i64)),
+        'nrp_result_host': (c_ctx, i32, ctypes.POINTER(HostResult)),
         'nrp_peer_export_direct': (c_ctx, i64, i32, i32, ptr),
         'nrp_peer_open_direct': (c_ctx, i32, i32, ptr),
         'nrp_shard_scatter_direct': (c_ctx, i64, i64, i32, i32, i32, ctypes.POINTER(i32)),
@@ -264,24 +280,22 @@ class Context(object):
         _check(self._lib, self._lib.nrp_result_timings(self._h, _p(out)))
         return dict(zip(TIMING_NAMES, out.tolist()))
 
-    def fetch(self, want_keys=True):
-        """Copy the whole result of the last build to the host."""
+    def fetch(self, want_keys=True, copy=False):
+        """The whole result of the last build on the host (one call, one synchronisation: nrp_result_host).
+        The arrays are VIEWS of the library's page-locked result buffers, valid until the next load_parts / build on this
+        context; copy=True returns private copies."""
         counts = self.counts()
-        n = self.n_parts
-        flags = np.zeros(n, dtype=np.uint8)
-        _check(self._lib, self._lib.nrp_result_flags(self._h, _p(flags)))
-        ng, nm = counts['groups'], counts['members']
-        indptr = np.zeros(ng + 1, dtype=np.int64)
-        members = np.zeros(nm, dtype=np.uint32)
-        first_window = np.zeros(ng, dtype=np.uint32)
-        keys = np.zeros(ng, dtype=np.uint64) if want_keys else None
-        _check(self._lib, self._lib.nrp_result_groups(self._h, _p(indptr), _p(members), _p(first_window), _p(keys)))
-        last_single = np.zeros(n, dtype=np.int32)
-        _check(self._lib, self._lib.nrp_result_last_single(self._h, _p(last_single)))
+        hr = HostResult()
+        _check(self._lib, self._lib.nrp_result_host(self._h, 1 if want_keys else 0, ctypes.byref(hr)))
+        n, ng, nm, ne = hr.n_parts, hr.n_groups, hr.n_members, hr.n_edges
+        fix = (lambda a: a.copy()) if copy else (lambda a: a)
+        flags = fix(_view(hr.flags, n, np.uint8))
+        indptr = fix(_view(hr.indptr, ng + 1, np.int64))
+        members = fix(_view(hr.members, nm, np.uint32))
+        first_window = fix(_view(hr.first_window, ng, np.uint32))
+        keys = fix(_view(hr.keys, ng, np.uint64)) if want_keys else None
+        last_single = fix(_view(hr.last_single, n, np.int32))
         edges = None
         if counts['edges'] >= 0:
-            u = np.zeros(counts['edges'], dtype=np.uint32)
-            v = np.zeros(counts['edges'], dtype=np.uint32)
-            _check(self._lib, self._lib.nrp_result_edges(self._h, _p(u), _p(v)))
-            edges = (u, v)
+            edges = (fix(_view(hr.edge_u, ne, np.uint32)), fix(_view(hr.edge_v, ne, np.uint32)))
         return BuildResult(counts, self.timings(), flags, indptr, members, first_window, keys, last_single, edges)

@@ -87,6 +87,24 @@ struct DevBuf {
 };
 
 // CNT_EDGES = 8 and CNT_SCATTER_OVERFLOW = 9 live outside the block [0, CNT_N) that every bulk stage clears
+// page-locked host buffer that grows on demand
+struct HostBuf {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return NRP_OK;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaHostAlloc(&ptr, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(NRP_E_OOM, "cudaHostAlloc(%zu bytes) failed: %s", want, cudaGetErrorString(e)); }
+    cap = want;
+    return NRP_OK;
+  }
+  void release() { if (ptr) cudaFreeHost(ptr); ptr = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
 enum { CNT_SCATTER_OVERFLOW = 9, CNT_SENT = 10 };
 enum { CNT_CAND = 0, CNT_REPEAT = 1, CNT_FLAGGED = 2, CNT_WORK = 3, CNT_OVERSIZED = 4, CNT_UNSORTED = 5, CNT_OVERFLOW = 6, CNT_RECORDS = 7, CNT_N = 8, CNT_EDGES = 8, CNT_TOTAL = 12 };
 
@@ -146,6 +164,7 @@ struct nrp_ctx {
   DevBuf g_keys, g_indptr, g_pair_off, g_members, g_first_part, g_first_window, last_single;
   DevBuf e_codesA, e_codesB, e_head, e_head_scan, e_u, e_v, e_u_alt, e_v_alt, shared_keysA, shared_keysB;
   unsigned long long* h_counters = nullptr;   // pinned
+  HostBuf h_upload, h_results;                // pinned staging: offsets + ids on the way in, all results on the way out
 
   // shard window (whole batch unless nrp_shard_extract narrowed it)
   int64_t shard_lo = 0, shard_hi = 0, shard_tile_lo = 0, shard_tiles = 0, shard_m_max = 0;
@@ -305,6 +324,7 @@ int nrp_ctx_destroy(nrp_ctx* c) {
   for (DevBuf* b : all) b->release();
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   if (c->h_counters) cudaFreeHost(c->h_counters);
+  c->h_upload.release(); c->h_results.release();
   if (!c->external_stream) cudaStreamDestroy(c->stream);
   delete c;
   return NRP_OK;
@@ -368,38 +388,50 @@ int nrp_load_parts(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, con
   c->have_parts = false; c->have_result = false;
   if (offsets[0] != 0) return fail(NRP_E_ARG, "offsets[0] must be 0");
   const int64_t total = offsets[n_parts];
-  int uniform = n_parts > 0 ? (int)std::min<int64_t>(offsets[1] - offsets[0], (int64_t)1 << 30) : 0;
-  int64_t max_len = 0;
-  for (int64_t i = 0; i < n_parts; ++i) {
-    int64_t len = offsets[i + 1] - offsets[i];
-    if (len < 0) return fail(NRP_E_ARG, "offsets must be non-decreasing (part %lld)", (long long)i);
-    if (len != uniform) uniform = 0;
-    if (len > max_len) max_len = len;
-  }
-  if (uniform >= (1 << 30)) uniform = 0;
-  c->h_off.assign(offsets, offsets + n_parts + 1);
-  c->n_parts = n_parts; c->total_len = total; c->uniform_len = uniform; c->max_len = max_len;
-  c->n_tiles = (total + kTileBytes - 1) / kTileBytes;
-  const size_t padded = (size_t)c->n_tiles * kTileBytes + 256;
+  if (total < 0) return fail(NRP_E_ARG, "negative total length");
+  // the big copy goes first: the DMA runs while the host validates the offsets and stages the small arrays
+  const int64_t n_tiles = (total + kTileBytes - 1) / kTileBytes;
+  const size_t padded = (size_t)n_tiles * kTileBytes + 256;
   TRY(c->ascii.ensure(padded));
-  TRY(c->off.ensure(sizeof(int64_t) * (size_t)(n_parts + 1)));
   CU(cudaMemsetAsync(c->ascii.as<uint8_t>() + total, 0, padded - (size_t)total, c->stream));
   if (total > 0)
     CU(cudaMemcpyAsync(c->ascii.ptr, ascii, (size_t)total, ascii_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->off.ptr, offsets, sizeof(int64_t) * (size_t)(n_parts + 1), cudaMemcpyHostToDevice, c->stream));
+  // offsets + ids travel through one page-locked staging buffer (the caller's arrays are usually pageable)
+  const size_t off_bytes = sizeof(int64_t) * (size_t)(n_parts + 1), id_bytes = part_id ? sizeof(uint32_t) * (size_t)n_parts : 0;
+  TRY(c->h_upload.ensure(off_bytes + id_bytes + 16));
+  int64_t* st_off = c->h_upload.as<int64_t>();
+  uint32_t* st_id = reinterpret_cast<uint32_t*>(c->h_upload.as<unsigned char>() + off_bytes);
+  int uniform = n_parts > 0 ? (int)std::min<int64_t>(offsets[1] - offsets[0], (int64_t)1 << 30) : 0;
+  int64_t max_len = 0;
+  st_off[0] = 0;
+  for (int64_t i = 0; i < n_parts; ++i) {
+    const int64_t len = offsets[i + 1] - offsets[i];
+    if (len < 0) { cudaStreamSynchronize(c->stream); return fail(NRP_E_ARG, "offsets must be non-decreasing (part %lld)", (long long)i); }
+    if (len != uniform) uniform = 0;
+    if (len > max_len) max_len = len;
+    st_off[i + 1] = offsets[i + 1];
+  }
+  if (uniform >= (1 << 30)) uniform = 0;
+  TRY(c->off.ensure(off_bytes));
+  CU(cudaMemcpyAsync(c->off.ptr, st_off, off_bytes, cudaMemcpyHostToDevice, c->stream));
+  c->h_off.assign(offsets, offsets + n_parts + 1);
+  c->n_parts = n_parts; c->total_len = total; c->uniform_len = uniform; c->max_len = max_len;
+  c->n_tiles = n_tiles;
   c->have_ids = part_id != nullptr;
   c->max_id = 0;
-  if (part_id) for (int64_t i = 0; i < n_parts; ++i) if (part_id[i] > c->max_id) c->max_id = part_id[i];
   if (part_id && n_parts > 0) {
-    TRY(c->part_id.ensure(sizeof(uint32_t) * (size_t)n_parts));
-    CU(cudaMemcpyAsync(c->part_id.ptr, part_id, sizeof(uint32_t) * (size_t)n_parts, cudaMemcpyHostToDevice, c->stream));
+    uint32_t mx = 0;
+    for (int64_t i = 0; i < n_parts; ++i) { const uint32_t v = part_id[i]; st_id[i] = v; if (v > mx) mx = v; }
+    c->max_id = mx;
+    TRY(c->part_id.ensure(id_bytes));
+    CU(cudaMemcpyAsync(c->part_id.ptr, st_id, id_bytes, cudaMemcpyHostToDevice, c->stream));
   }
   TRY(c->tile_first.ensure(sizeof(uint32_t) * (size_t)(c->n_tiles + 2)));
   if (uniform == 0 && n_parts > 0)
     NRP_LAUNCH((k_tile_first_part<<<grid_for(c->n_tiles + 1, 256), 256, 0, c->stream>>>(c->off.as<int64_t>(), n_parts, total, c->n_tiles,
                                                                             c->tile_first.as<uint32_t>())));
   CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->stream));        // the caller's buffers are borrowed only for the duration of the call
   c->part_base = 0;
   c->shard_lo = 0; c->shard_hi = n_parts; c->shard_tile_lo = 0; c->shard_tiles = c->n_tiles;
   c->n_owners = 0;
@@ -1556,6 +1588,43 @@ int nrp_result_groups(nrp_ctx* c, int64_t* indptr, uint32_t* members, uint32_t* 
   if (first_window && ng > 0) CU(cudaMemcpyAsync(first_window, c->g_first_window.ptr, 4 * (size_t)ng, cudaMemcpyDeviceToHost, c->stream));
   if (keys && ng > 0) CU(cudaMemcpyAsync(keys, c->g_keys.ptr, 8 * (size_t)ng, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  return NRP_OK;
+}
+
+int nrp_result_host(nrp_ctx* c, int want_keys, nrp_host_result* out) {
+  NEED_RESULT();
+  if (!out) return fail(NRP_E_ARG, "null argument");
+  const int64_t n = c->n_parts, ng = c->counts[NRP_C_GROUPS], nm = c->counts[NRP_C_MEMBERS];
+  const int64_t ne = c->counts[NRP_C_EDGES] < 0 ? 0 : c->counts[NRP_C_EDGES];
+  auto up = [](size_t b) { return (b + 63) & ~(size_t)63; };
+  const size_t o_indptr = 0, o_keys = o_indptr + up(8 * (size_t)(ng + 1)), o_members = o_keys + up(8 * (size_t)ng),
+               o_fw = o_members + up(4 * (size_t)nm), o_last = o_fw + up(4 * (size_t)ng), o_eu = o_last + up(4 * (size_t)n),
+               o_ev = o_eu + up(4 * (size_t)ne), o_flags = o_ev + up(4 * (size_t)ne), total = o_flags + up((size_t)n) + 64;
+  TRY(c->h_results.ensure(total));
+  unsigned char* h = c->h_results.as<unsigned char>();
+  cudaStream_t st = c->stream;
+  CU(cudaMemcpyAsync(h + o_indptr, c->g_indptr.ptr, 8 * (size_t)(ng + 1), cudaMemcpyDeviceToHost, st));
+  if (want_keys && ng > 0) CU(cudaMemcpyAsync(h + o_keys, c->g_keys.ptr, 8 * (size_t)ng, cudaMemcpyDeviceToHost, st));
+  if (nm > 0) CU(cudaMemcpyAsync(h + o_members, c->g_members.ptr, 4 * (size_t)nm, cudaMemcpyDeviceToHost, st));
+  if (ng > 0) CU(cudaMemcpyAsync(h + o_fw, c->g_first_window.ptr, 4 * (size_t)ng, cudaMemcpyDeviceToHost, st));
+  if (n > 0) {
+    CU(cudaMemcpyAsync(h + o_last, c->last_single.ptr, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h + o_flags, c->flags.ptr, (size_t)n, cudaMemcpyDeviceToHost, st));
+  }
+  if (ne > 0) {
+    CU(cudaMemcpyAsync(h + o_eu, c->e_u.ptr, 4 * (size_t)ne, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h + o_ev, c->e_v.ptr, 4 * (size_t)ne, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  out->flags = h + o_flags;
+  out->indptr = reinterpret_cast<const int64_t*>(h + o_indptr);
+  out->members = reinterpret_cast<const uint32_t*>(h + o_members);
+  out->first_window = reinterpret_cast<const uint32_t*>(h + o_fw);
+  out->keys = want_keys ? reinterpret_cast<const uint64_t*>(h + o_keys) : nullptr;
+  out->last_single = reinterpret_cast<const int32_t*>(h + o_last);
+  out->edge_u = c->counts[NRP_C_EDGES] < 0 ? nullptr : reinterpret_cast<const uint32_t*>(h + o_eu);
+  out->edge_v = c->counts[NRP_C_EDGES] < 0 ? nullptr : reinterpret_cast<const uint32_t*>(h + o_ev);
+  out->n_parts = n; out->n_groups = ng; out->n_members = nm; out->n_edges = ne;
   return NRP_OK;
 }
 

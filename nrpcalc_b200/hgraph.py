@@ -110,7 +110,7 @@ def _device_build(ctx, structure, ascii_buf, offsets, global_p, ids, k, internal
         for name in ('groups', 'members', 'candidates', 'oversized', 'windows_max'):
             structure.counts[name] += res.counts[name]
         structure.counts['runs'] = max(structure.counts['runs'], res.counts['runs'])
-        structure.edges = res.edges
+        structure.edges = None if res.edges is None else (res.edges[0].copy(), res.edges[1].copy())     # views of library memory
     structure.flags[global_p] |= flags
     # shared k-mer groups: rank = (p of first member, first window); members -> processing ranks
     if indptr.size > 1:

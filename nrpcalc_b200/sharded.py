@@ -184,7 +184,8 @@ class NativeOps(object):
         counts = self.ctx.counts()
         res = self.ctx.fetch(want_keys=True)
         return {'indptr': res.indptr, 'members': res.members, 'first_window': res.first_window, 'keys': res.keys,
-                'last_single': res.last_single, 'flags': res.flags, 'edges': res.edges if want_edges else None,
+                'last_single': res.last_single, 'flags': res.flags,
+                'edges': (res.edges[0].copy(), res.edges[1].copy()) if want_edges and res.edges is not None else None,
                 'candidates': counts['candidates'], 'oversized': counts['oversized']}
 
 
