@@ -105,7 +105,7 @@ struct HostBuf {
   template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
 };
 
-enum { CNT_SCATTER_OVERFLOW = 9, CNT_SENT = 10 };
+enum { CNT_SCATTER_OVERFLOW = 9, CNT_SENT = 10, CNT_NSORTED = 11 };
 enum { CNT_CAND = 0, CNT_REPEAT = 1, CNT_FLAGGED = 2, CNT_WORK = 3, CNT_OVERSIZED = 4, CNT_UNSORTED = 5, CNT_OVERFLOW = 6, CNT_RECORDS = 7, CNT_N = 8, CNT_EDGES = 8, CNT_TOTAL = 12 };
 
 constexpr int kFilterThreads = 1024;
@@ -805,8 +805,8 @@ int ensure_group_buffers(nrp_ctx* c, int64_t n) {
   return NRP_OK;
 }
 
-// ---- stage: sort the candidates by (k-mer, part), mark key-run heads, detect internal repeats
-// (two equal adjacent records).  With mark_repeats the parts get NRP_FLAG_REPEAT in flags[value].
+// ---- stage: order the candidates by (k-mer, part) if the filter could not, mark key-run heads, detect internal repeats
+// (two equal adjacent records).  With mark_repeats the parts get NRP_FLAG_REPEAT in flags[value].  No host round trip.
 template <typename KeyT>
 int stage_sort_mark(nrp_ctx* c, int k, int64_t n_parts_total, bool mark_repeats, StageTimer& tm) {
   cudaStream_t st = c->stream;
@@ -815,7 +815,7 @@ int stage_sort_mark(nrp_ctx* c, int k, int64_t n_parts_total, bool mark_repeats,
   int part_bits = 1;
   while (((int64_t)1 << part_bits) < n_parts_total) ++part_bits;
   if (c->cand_unsorted) {
-    // rare: a leaf bucket over the filter capacity or with > kLeafSortCap candidates (heavy duplicate keys)
+    // rare: a leaf bucket over the filter capacity or with more suspects than the in-leaf ordering takes (heavy duplicate keys)
     TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n)));
     LsdPlan plan = lsd_plan(2 * k, part_bits + c->j_bits);
     KeyT* sk; uint32_t* sv;
@@ -827,88 +827,85 @@ int stage_sort_mark(nrp_ctx* c, int k, int64_t n_parts_total, bool mark_repeats,
   unsigned long long* cnt = c->counters.as<unsigned long long>();
   c->n_sorted = n;
   c->n_repeat_records = 0;
-  if (n > 0) {
+  if (n > 0)
     NRP_LAUNCH((k_group_heads<KeyT><<<grid_for(n, 256), 256, 0, st>>>((KeyT*)c->cand_keys, c->cand_vals, n, c->j_bits, c->head.as<uint32_t>(),
                                                                   mark_repeats ? c->flags.as<uint8_t>() : nullptr, cnt + CNT_REPEAT)));
-    CU(cudaMemcpyAsync(c->h_counters + 18, cnt + CNT_REPEAT, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    c->n_repeat_records = (int64_t)c->h_counters[18];
-  }
   CU(cudaGetLastError());
   return NRP_OK;
 }
 
-// ---- stage: drop every record of a part that carries the repeat flag (keeps the order), mark heads again
+// ---- stage: (optionally) drop every record of a part that carries the repeat flag, then key runs with >= 2 records ->
+// groups CSR (keys, indptr, members, pair offsets).  Everything is enqueued with device-side counts (n_max = number of
+// candidates bounds every grid); the totals are copied to pinned memory and become valid at the caller's next synchronisation
+// (read them with group_counts_ready).
 template <typename KeyT>
-int stage_compact(nrp_ctx* c, StageTimer& tm) {
+int stage_groups(nrp_ctx* c, bool drop_flagged, StageTimer& tm) {
   cudaStream_t st = c->stream;
   tm.begin(NRP_T_GROUP);
-  const int64_t n = c->n_sorted;
-  if (n == 0) return NRP_OK;
-  unsigned long long* cnt = c->counters.as<unsigned long long>();
-  NRP_LAUNCH((k_keep_unflagged<<<grid_for(n, 256), 256, 0, st>>>(c->cand_vals, n, c->j_bits, c->flags.as<uint8_t>(), c->valid.as<uint32_t>())));
-  exclusive_scan<uint32_t, uint32_t>(c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), n, c->scan_scratch.as<uint32_t>(), st);
-  NRP_LAUNCH((k_compact_records<KeyT><<<grid_for(n, 256), 256, 0, st>>>((KeyT*)c->cand_keys, c->cand_vals, c->valid.as<uint32_t>(),
-                                                                    c->valid_scan.as<uint32_t>(), n, (KeyT*)c->spare_keys, c->spare_vals)));
-  CU(cudaMemcpyAsync(c->h_counters + 19, c->valid_scan.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  c->n_sorted = (int64_t)(uint32_t)c->h_counters[19];
-  std::swap(c->cand_keys, c->spare_keys); std::swap(c->cand_vals, c->spare_vals);
-  if (c->n_sorted > 0)
-    NRP_LAUNCH((k_group_heads<KeyT><<<grid_for(c->n_sorted, 256), 256, 0, st>>>((KeyT*)c->cand_keys, c->cand_vals, c->n_sorted, c->j_bits,
-                                                                           c->head.as<uint32_t>(), nullptr, cnt + CNT_WORK)));
-  CU(cudaGetLastError());
-  return NRP_OK;
-}
-
-// ---- stage: key runs with >= 2 records -> groups CSR (keys, indptr, members, pair offsets)
-template <typename KeyT>
-int stage_groups(nrp_ctx* c, StageTimer& tm) {
-  cudaStream_t st = c->stream;
-  tm.begin(NRP_T_GROUP);
-  const int64_t n = c->n_sorted;
+  const int64_t n_max = c->n_cand;
   c->n_groups = c->n_members = c->n_pairs = 0;
-  if (n > 0) {
-    exclusive_scan<uint32_t, uint32_t>(c->head.as<uint32_t>(), c->head_scan.as<uint32_t>(), n, c->scan_scratch.as<uint32_t>(), st);
-    NRP_LAUNCH((k_group_starts<<<grid_for(n + 1, 256), 256, 0, st>>>(c->head.as<uint32_t>(), c->head_scan.as<uint32_t>(), n,
-                                                                 c->group_start.as<uint32_t>())));
-    CU(cudaMemcpyAsync(c->h_counters + 17, c->head_scan.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    const int64_t n_runs = (int64_t)(uint32_t)c->h_counters[17];
-    NRP_LAUNCH((k_group_sizes<<<grid_for(n_runs, 256), 256, 0, st>>>(c->group_start.as<uint32_t>(), n_runs, c->valid.as<uint32_t>(),
-                                                                 c->mem_cnt.as<uint32_t>(), c->pair_cnt.as<unsigned long long>())));
-    exclusive_scan<uint32_t, uint32_t>(c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), n_runs, c->scan_scratch.as<uint32_t>(), st);
-    exclusive_scan<uint32_t, unsigned long long>(c->mem_cnt.as<uint32_t>(), c->mem_scan.as<unsigned long long>(), n_runs,
-                                                 c->scan_scratch.as<unsigned long long>(), st);
-    exclusive_scan<unsigned long long, unsigned long long>(c->pair_cnt.as<unsigned long long>(), c->pair_scan.as<unsigned long long>(),
-                                                           n_runs, c->scan_scratch.as<unsigned long long>(), st);
-    CU(cudaMemcpyAsync(c->h_counters + 20, c->valid_scan.as<uint32_t>() + n_runs, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(c->h_counters + 21, c->mem_scan.as<unsigned long long>() + n_runs, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(c->h_counters + 22, c->pair_scan.as<unsigned long long>() + n_runs, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    c->n_groups = (int64_t)(uint32_t)c->h_counters[20];
-    c->n_members = (int64_t)c->h_counters[21];
-    c->n_pairs = (int64_t)c->h_counters[22];
-    TRY(c->g_keys.ensure(8 * (size_t)(c->n_groups + 1))); TRY(c->g_indptr.ensure(8 * (size_t)(c->n_groups + 2)));
-    TRY(c->g_pair_off.ensure(8 * (size_t)(c->n_groups + 2))); TRY(c->g_members.ensure(4 * (size_t)(c->n_members + 1)));
-    TRY(c->g_first_window.ensure(4 * (size_t)(c->n_groups + 1)));
-    NRP_LAUNCH((k_group_emit<KeyT><<<grid_for(n_runs + 1, 256), 256, 0, st>>>(
-        (KeyT*)c->cand_keys, c->cand_vals, c->j_bits, c->group_start.as<uint32_t>(), c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(),
-        c->mem_scan.as<unsigned long long>(), c->pair_scan.as<unsigned long long>(), n_runs, c->g_keys.as<uint64_t>(),
-        c->g_indptr.as<int64_t>(), c->g_pair_off.as<unsigned long long>(), c->g_first_window.as<uint32_t>())));
-    NRP_LAUNCH((k_group_members<<<grid_for(n, 256), 256, 0, st>>>(c->cand_vals, c->head_scan.as<uint32_t>(), c->head.as<uint32_t>(),
-                                                              c->group_start.as<uint32_t>(), c->valid.as<uint32_t>(),
-                                                              c->mem_scan.as<unsigned long long>(), n, c->j_bits, c->g_members.as<uint32_t>())));
-    CU(cudaGetLastError());
-  } else {
-    TRY(c->g_keys.ensure(8)); TRY(c->g_indptr.ensure(16)); TRY(c->g_pair_off.ensure(16)); TRY(c->g_members.ensure(4));
+  for (int i = 17; i <= 22; ++i) c->h_counters[i] = 0;
+  const size_t ng_max = (size_t)n_max / 2 + 2;
+  TRY(c->g_keys.ensure(8 * ng_max)); TRY(c->g_indptr.ensure(8 * (ng_max + 1)));
+  TRY(c->g_pair_off.ensure(8 * (ng_max + 1))); TRY(c->g_members.ensure(4 * (size_t)(n_max + 1)));
+  TRY(c->g_first_window.ensure(4 * ng_max)); TRY(c->g_first_part.ensure(4 * ng_max));
+  if (n_max == 0) {
     CU(cudaMemsetAsync(c->g_indptr.ptr, 0, 16, st));
     CU(cudaMemsetAsync(c->g_pair_off.ptr, 0, 16, st));
+    return NRP_OK;
   }
+  unsigned long long* cnt = c->counters.as<unsigned long long>();
+  uint32_t* n_sorted_dev = reinterpret_cast<uint32_t*>(cnt + CNT_NSORTED);
+  const unsigned grid = grid_for(n_max + 1, 256);
+  if (drop_flagged) {
+    NRP_LAUNCH((k_keep_unflagged<<<grid, 256, 0, st>>>(c->cand_vals, n_max, c->j_bits, c->flags.as<uint8_t>(), c->valid.as<uint32_t>())));
+    exclusive_scan<uint32_t, uint32_t>(c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), n_max, c->scan_scratch.as<uint32_t>(), st);
+    NRP_LAUNCH((k_compact_records<KeyT><<<grid, 256, 0, st>>>((KeyT*)c->cand_keys, c->cand_vals, c->valid.as<uint32_t>(),
+                                                            c->valid_scan.as<uint32_t>(), n_max, (KeyT*)c->spare_keys, c->spare_vals)));
+    CU(cudaMemcpyAsync(n_sorted_dev, c->valid_scan.as<uint32_t>() + n_max, 4, cudaMemcpyDeviceToDevice, st));
+    std::swap(c->cand_keys, c->spare_keys); std::swap(c->cand_vals, c->spare_vals);
+    NRP_LAUNCH((k_group_heads_n<KeyT><<<grid, 256, 0, st>>>((KeyT*)c->cand_keys, c->cand_vals, n_sorted_dev, n_max, c->head.as<uint32_t>())));
+  } else {
+    uint32_t* h = reinterpret_cast<uint32_t*>(c->h_counters + 46);       // pinned: the copy reads it later, nobody rewrites it before the next job
+    h[0] = (uint32_t)n_max;
+    CU(cudaMemcpyAsync(n_sorted_dev, h, 4, cudaMemcpyHostToDevice, st));
+  }
+  exclusive_scan<uint32_t, uint32_t>(c->head.as<uint32_t>(), c->head_scan.as<uint32_t>(), n_max, c->scan_scratch.as<uint32_t>(), st);
+  const uint32_t* n_runs_dev = c->head_scan.as<uint32_t>() + n_max;
+  NRP_LAUNCH((k_group_starts_n<<<grid, 256, 0, st>>>(c->head.as<uint32_t>(), c->head_scan.as<uint32_t>(), n_sorted_dev, n_max, c->group_start.as<uint32_t>())));
+  NRP_LAUNCH((k_group_sizes_n<<<grid, 256, 0, st>>>(c->group_start.as<uint32_t>(), n_runs_dev, n_max, c->valid.as<uint32_t>(),
+                                                  c->mem_cnt.as<uint32_t>(), c->pair_cnt.as<unsigned long long>())));
+  exclusive_scan<uint32_t, uint32_t>(c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), n_max, c->scan_scratch.as<uint32_t>(), st);
+  exclusive_scan<uint32_t, unsigned long long>(c->mem_cnt.as<uint32_t>(), c->mem_scan.as<unsigned long long>(), n_max,
+                                               c->scan_scratch.as<unsigned long long>(), st);
+  exclusive_scan<unsigned long long, unsigned long long>(c->pair_cnt.as<unsigned long long>(), c->pair_scan.as<unsigned long long>(),
+                                                         n_max, c->scan_scratch.as<unsigned long long>(), st);
+  NRP_LAUNCH((k_group_emit_n<KeyT><<<grid, 256, 0, st>>>(
+      (KeyT*)c->cand_keys, c->cand_vals, c->j_bits, c->group_start.as<uint32_t>(), c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(),
+      c->mem_scan.as<unsigned long long>(), c->pair_scan.as<unsigned long long>(), n_runs_dev, n_max, c->g_keys.as<uint64_t>(),
+      c->g_indptr.as<int64_t>(), c->g_pair_off.as<unsigned long long>(), c->g_first_window.as<uint32_t>())));
+  NRP_LAUNCH((k_group_members_n<<<grid, 256, 0, st>>>(c->cand_vals, c->head_scan.as<uint32_t>(), c->head.as<uint32_t>(),
+                                                    c->group_start.as<uint32_t>(), c->valid.as<uint32_t>(),
+                                                    c->mem_scan.as<unsigned long long>(), n_sorted_dev, c->j_bits, c->g_members.as<uint32_t>())));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(c->h_counters + 18, cnt + CNT_REPEAT, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(c->h_counters + 19, n_sorted_dev, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(c->h_counters + 20, c->valid_scan.as<uint32_t>() + n_max, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(c->h_counters + 21, c->mem_scan.as<unsigned long long>() + n_max, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(c->h_counters + 22, c->pair_scan.as<unsigned long long>() + n_max, 8, cudaMemcpyDeviceToHost, st));
+  return NRP_OK;
+}
+
+// after a synchronisation that follows stage_groups
+void group_counts_ready(nrp_ctx* c) {
+  c->n_repeat_records = (int64_t)c->h_counters[18];
+  c->n_sorted = c->n_cand > 0 ? (int64_t)(uint32_t)c->h_counters[19] : 0;
+  c->n_groups = (int64_t)(uint32_t)c->h_counters[20];
+  c->n_members = (int64_t)c->h_counters[21];
+  c->n_pairs = (int64_t)c->h_counters[22];
   c->counts[NRP_C_GROUPS] = c->n_groups;
   c->counts[NRP_C_MEMBERS] = c->n_members;
   c->counts[NRP_C_PAIRS] = c->n_pairs;
-  return NRP_OK;
 }
 
 // ---- stage: rank of every group = first window of its first member that carries the group's key
@@ -988,23 +985,32 @@ int stage_edges(nrp_ctx* c, StageTimer& tm) {
   return NRP_OK;
 }
 
-int finish_counts(nrp_ctx* c, StageTimer& tm) {
+// flagged parts and the windows of the parts flagged for internal repeats (they were counted as records before the flag was
+// known): enqueued; finish_counts_ready reads the numbers after the next synchronisation
+int finish_counts_enqueue(nrp_ctx* c, StageTimer& tm) {
   cudaStream_t st = c->stream;
   unsigned long long* cnt = c->counters.as<unsigned long long>();
   tm.begin(NRP_T_GROUP);
   CU(cudaMemsetAsync(cnt + CNT_FLAGGED, 0, 16, st));
   if (c->n_parts > 0) {
     NRP_LAUNCH((k_count_flagged<<<grid_for(c->n_parts, 256), 256, 0, st>>>(c->flags.as<uint8_t>(), c->n_parts, cnt + CNT_FLAGGED)));
-    // windows of the parts flagged for internal repeats were counted as records before the flag was known
     NRP_LAUNCH((k_flagged_windows<<<grid_for(c->shard_hi - c->shard_lo, 256), 256, 0, st>>>(c->off.as<int64_t>(), c->flags.as<uint8_t>(),
                                                                                         c->shard_lo, c->shard_hi, c->k, cnt + CNT_WORK)));
   }
   CU(cudaMemcpyAsync(c->h_counters + 26, cnt + CNT_FLAGGED, 16, cudaMemcpyDeviceToHost, st));
-  tm.finish(c->timings);
-  CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
+  return NRP_OK;
+}
+
+void finish_counts_ready(nrp_ctx* c) {
   c->counts[NRP_C_EXCLUDED] = (int64_t)c->h_counters[26];
   c->counts[NRP_C_RECORDS] = c->n_records - (int64_t)c->h_counters[27];
+}
+
+int finish_timing(nrp_ctx* c, StageTimer& tm) {
+  tm.finish(c->timings);
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
   c->counts[NRP_C_LAUNCHES] = launch_counter();
   double total = 0;
   for (int i = NRP_T_FLAGS; i < NRP_N_TIMINGS; ++i) total += c->timings[i];
@@ -1043,12 +1049,15 @@ int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   TRY(stage_flags(c, k, internal_repeats, tm));
   TRY((stage_bulk<KeyT>(c, k, BulkSource<KeyT>{}, tm)));
   TRY((stage_sort_mark<KeyT>(c, k, c->n_parts, !internal_repeats, tm)));
-  if (!internal_repeats && c->n_repeat_records > 0) TRY((stage_compact<KeyT>(c, tm)));
-  TRY((stage_groups<KeyT>(c, tm)));
+  TRY((stage_groups<KeyT>(c, !internal_repeats, tm)));
+  TRY(finish_counts_enqueue(c, tm));
+  CU(cudaStreamSynchronize(c->stream));               // the one host round trip of the grouping: all counts at once
+  group_counts_ready(c);
+  finish_counts_ready(c);
   TRY(stage_first_window(c, k, tm));
   TRY(stage_last_single(c, k, c->g_keys.as<uint64_t>(), c->n_groups, 0, c->n_parts, tm));
   if (want_edges) TRY(stage_edges(c, tm));
-  TRY(finish_counts(c, tm));
+  TRY(finish_timing(c, tm));
   c->have_result = true;
   return NRP_OK;
 }
@@ -1110,8 +1119,9 @@ int shard_group_impl(nrp_ctx* c, const void* keys, const uint32_t* vals, int64_t
 template <typename KeyT>
 int shard_finish_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   StageTimer tm(c);
-  if (!internal_repeats) TRY((stage_compact<KeyT>(c, tm)));     // flags may come from other ranks: always filter
-  TRY((stage_groups<KeyT>(c, tm)));
+  TRY((stage_groups<KeyT>(c, !internal_repeats, tm)));     // flags may come from other ranks: always filter
+  CU(cudaStreamSynchronize(c->stream));
+  group_counts_ready(c);
   TRY(stage_first_window(c, k, tm));
   if (want_edges) { c->counts[NRP_C_EDGES] = 0; TRY(stage_edges(c, tm)); }
   tm.finish(c->timings);
