@@ -65,6 +65,7 @@ extern "C" {
 #define NRP_C_LAUNCHES      12  /* kernels launched by the build */
 #define NRP_C_DIRECT        13  /* 1: buckets were placed in fixed regions (no histogram pass); 0: exact histogram path */
 #define NRP_C_FALLBACKS     14  /* a fixed region overflowed and the batch was repeated on the exact path */
+#define NRP_C_PACKED        15  /* 1: records travelled as single 64-bit words (k-mer << value bits) | value */
 #define NRP_N_COUNTS        16
 
 /* indices into nrp_result_timings() (milliseconds, CUDA events on the context's stream) */
@@ -92,7 +93,7 @@ int nrp_ctx_destroy(nrp_ctx* ctx);
 int nrp_ctx_device(nrp_ctx* ctx);
 
 /* Tuning knobs used by the tests to force rarely taken paths: name in
- * {"filter_cap", "leaf_target", "max_level_bits", "max_pairs", "no_window_carry", "no_bloom", "pass_records", "direct"};
+ * {"filter_cap", "leaf_target", "max_level_bits", "max_pairs", "no_window_carry", "no_bloom", "pass_records", "direct", "packed", "persistent_split", "r1_bias"};
  * value <= 0 restores the default ("direct": 0 forces the exact histogram path, negative restores the default 1). */
 int nrp_ctx_set_option(nrp_ctx* ctx, const char* name, int64_t value);
 

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libnrpb200.so')
 N_COUNTS = 16
 N_TIMINGS = 16
 COUNT_NAMES = ('records', 'excluded', 'groups', 'members', 'edges', 'pairs', 'candidates', 'runs', 'buckets',
-               'oversized', 'windows_max', 'key_bytes', 'launches', 'direct', 'fallbacks')
+               'oversized', 'windows_max', 'key_bytes', 'launches', 'direct', 'fallbacks', 'packed')
 TIMING_NAMES = ('total', 'h2d', 'flags', 'histogram', 'split1', 'split2', 'filter', 'sort', 'group', 'edges', 'order')
 
 FLAG_REPEAT, FLAG_PALINDROME, FLAG_BACKGROUND = 1, 2, 4

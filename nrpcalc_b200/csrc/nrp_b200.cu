@@ -143,6 +143,7 @@ struct nrp_ctx {
   int64_t opt_pass_records = 210000000;   // exact path: more records than this per device are processed in several hash-slice passes
   int64_t opt_persistent_split = 0;       // extraction kernel: persistent CTAs with register prefetch (1) or one CTA per byte tile (0)
   int64_t opt_r1_bias = 0;                // added to the number of level-1 bits (tuning)
+  int64_t opt_packed = 1;                 // one 64-bit word per record on the direct path whenever key and value fit
   int64_t opt_direct = 1;                 // fixed-region partition without a histogram pass (falls back to the exact path on overflow)
 
   // background
@@ -170,6 +171,9 @@ struct nrp_ctx {
   int64_t shard_lo = 0, shard_hi = 0, shard_tile_lo = 0, shard_tiles = 0, shard_m_max = 0;
   int n_owners = 0;
   int j_bits = 0;                // > 0: record values are (part << j_bits) | window
+  int vbits = 32;                // bits of a record value
+  bool packed = false;           // direct path: records are single words (k-mer << vbits) | value
+  DevBuf fb_keys, fb_vals;       // unpacked copy of a packed source for the exact-path fallback
   // receive buffers of the fused exchange (exported with CUDA IPC) and the peers' buffers opened here
   DevBuf recv_keys, recv_vals;
   // direct fused exchange: fixed regions (level-1 bucket x sender) + the end position of every region
@@ -177,6 +181,7 @@ struct nrp_ctx {
   PeerBuffers peers_d{};
   uint32_t* peer_ends[kMaxPeers] = {nullptr};
   int sh_world = 0, sh_r1 = 0, sh_key_bytes = 0, n_peers_d = 0;
+  bool sh_packed = false;
   uint32_t sh_cap1s = 0;
   int64_t sh_windows_total = 0, sh_m_owner = 0, sh_sent = 0;
   int64_t recv_capacity = 0;
@@ -268,10 +273,19 @@ int configure_kernels(nrp_ctx* c) {
   CU(cudaFuncSetAttribute((k_split_from_ascii<KeyT, 2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, split_smem));
   CU(cudaFuncSetAttribute((k_split_from_records<KeyT, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<KeyT>)));
   CU(cudaFuncSetAttribute((k_split_from_records<KeyT, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplitSmem<KeyT>)));
-  CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, 512, 8, 2048, 2, 512>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)filter_bloom_smem<KeyT, 4096, 2048, 512>()));
-  CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1, 1024>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)filter_bloom_smem<KeyT, 8192, 4096, 1024>()));
+  CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, 512, 8, 2048, 2, 512, false>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)filter_bloom_smem<(int)sizeof(KeyT), false, 4096, 2048, 512>()));
+  CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1, 1024, false>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)filter_bloom_smem<(int)sizeof(KeyT), false, 8192, 4096, 1024>()));
+  CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, 512, 8, 2048, 2, 512, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)filter_bloom_smem<8, true, 4096, 2048, 512>()));
+  CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1, 1024, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)filter_bloom_smem<8, true, 8192, 4096, 1024>()));
+  const int packed_smem = (int)(sizeof(SplitSmem<uint64_t, true>) + sizeof(TileStage));
+  CU(cudaFuncSetAttribute((k_split_from_ascii<uint64_t, 0, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, packed_smem));
+  CU(cudaFuncSetAttribute((k_split_from_ascii<uint64_t, 2, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, packed_smem));
+  CU(cudaFuncSetAttribute((k_split_from_records<uint64_t, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)sizeof(SplitSmem<uint64_t, true>)));
   CU(cudaFuncSetAttribute((k_filter<KeyT, kFilterThreads, kFilterItems, kFilterCap, false>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)filter_smem_large<KeyT>()));
   CU(cudaFuncSetAttribute((k_filter<KeyT, kFilterThreads, kFilterItemsSmall, kFilterCapSmall, kFilterStaged>), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -315,7 +329,7 @@ int nrp_ctx_destroy(nrp_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DevBuf* all[] = {&c->bg_table, &c->ascii, &c->off, &c->part_id, &c->tile_first, &c->flags, &c->hist, &c->leaf_off, &c->cursor1,
-                   &c->cursor2, &c->seg_off, &c->tile_prefix, &c->tile_desc, &c->region_ends, &c->recv_ends, &c->recv_keys_d, &c->recv_vals_d, &c->counters, &c->scan_scratch, &c->lsd_scratch, &c->keysA, &c->valsA, &c->cand_keys_buf, &c->cand_vals_buf,
+                   &c->cursor2, &c->seg_off, &c->tile_prefix, &c->tile_desc, &c->region_ends, &c->recv_ends, &c->recv_keys_d, &c->recv_vals_d, &c->fb_keys, &c->fb_vals, &c->counters, &c->scan_scratch, &c->lsd_scratch, &c->keysA, &c->valsA, &c->cand_keys_buf, &c->cand_vals_buf,
                    &c->keysB, &c->valsB, &c->head, &c->head_scan, &c->group_start, &c->valid, &c->valid_scan, &c->mem_cnt,
                    &c->mem_scan, &c->pair_cnt, &c->pair_scan, &c->g_keys, &c->g_indptr, &c->g_pair_off, &c->g_members,
                    &c->g_first_part, &c->g_first_window, &c->last_single, &c->e_codesA, &c->e_codesB, &c->e_head, &c->e_head_scan,
@@ -344,6 +358,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "pass_records") c->opt_pass_records = value <= 0 ? 210000000 : value;
   else if (n == "persistent_split") c->opt_persistent_split = value > 0 ? 1 : 0;
   else if (n == "r1_bias") c->opt_r1_bias = value;
+  else if (n == "packed") c->opt_packed = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "direct") c->opt_direct = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
   return NRP_OK;
@@ -496,7 +511,8 @@ int stage_flags(nrp_ctx* c, int k, int internal_repeats, StageTimer& tm) {
 template <typename KeyT>
 struct BulkSource {
   bool from_parts = true;              // records are extracted from the staged parts
-  const KeyT* keys = nullptr;
+  bool packed = false;                 // the record list holds packed words (direct sharded path), not (key, value) arrays
+  const void* keys = nullptr;
   const uint32_t* vals = nullptr;
   SegExtents ext{nullptr, 0, nullptr, 0};
   uint32_t n_seg = 0;                  // segments of the record list
@@ -536,32 +552,41 @@ LevelPlan plan_levels(const nrp_ctx* c, int64_t m, bool direct, int fixed_r1 = -
 }
 
 template <typename KeyT>
-int launch_filter(nrp_ctx* c, const KeyT* leaf_keys, const uint32_t* leaf_vals, LeafExtents leaves, uint32_t n_leaf, int bits, int64_t mean_leaf,
-                  KeyT* out_keys, uint32_t* out_vals) {
+int launch_filter(nrp_ctx* c, bool packed, const void* leaf_keys, const uint32_t* leaf_vals, LeafExtents leaves, uint32_t n_leaf, int bits,
+                  int64_t mean_leaf, KeyT* out_keys, uint32_t* out_vals) {
   cudaStream_t st = c->stream;
   unsigned long long* cnt = c->counters.as<unsigned long long>();
   // leaves that average <= 2750 records use the half-size variant (two CTAs per SM); larger ones the full one
   const bool small = mean_leaf <= 2750;
-  const size_t fsm = small ? filter_smem_small<KeyT>() : filter_smem_large<KeyT>();
-  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / (fsm + 18 * 1024)));   // + static smem of the leaf ordering
-  const unsigned fgrid = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * per_sm);
   const uint32_t cap = (uint32_t)std::min<int64_t>(c->opt_filter_cap, small ? kFilterCapSmall : kFilterCap);
   uint32_t* n_over = reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED);
   uint32_t* unsorted = reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED);
-  if (small && !c->opt_no_bloom)      // two 512-thread CTAs per SM, leaves of up to 4096 records
-    NRP_LAUNCH((k_filter_bloom<KeyT, 512, 8, 2048, 2, 512><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * 2), 512,
-                                                               filter_bloom_smem<KeyT, 4096, 2048, 512>(), st>>>(
-        leaf_keys, leaf_vals, leaves, n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
-  else if (!c->opt_no_bloom)          // one 1024-thread CTA per SM, leaves of up to 8192 records
-    NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1, 1024><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms), kFilterThreads,
-                                                               filter_bloom_smem<KeyT, 8192, 4096, 1024>(), st>>>(
-        leaf_keys, leaf_vals, leaves, n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
-  else if (small)
-    NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItemsSmall, kFilterCapSmall, kFilterStaged><<<fgrid, kFilterThreads, fsm, st>>>(
-        leaf_keys, leaf_vals, leaves, n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
-  else
-    NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItems, kFilterCap, false><<<fgrid, kFilterThreads, fsm, st>>>(
-        leaf_keys, leaf_vals, leaves, n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+  const unsigned grid_small = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * 2), grid_large = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms);
+  if (!c->opt_no_bloom) {
+    if (small && packed)           // two 512-thread CTAs per SM, leaves of up to 4096 records
+      NRP_LAUNCH((k_filter_bloom<KeyT, 512, 8, 2048, 2, 512, true><<<grid_small, 512, filter_bloom_smem<8, true, 4096, 2048, 512>(), st>>>(
+          leaf_keys, leaf_vals, leaves, n_leaf, bits, c->vbits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+    else if (small)
+      NRP_LAUNCH((k_filter_bloom<KeyT, 512, 8, 2048, 2, 512, false><<<grid_small, 512, filter_bloom_smem<(int)sizeof(KeyT), false, 4096, 2048, 512>(), st>>>(
+          leaf_keys, leaf_vals, leaves, n_leaf, bits, 0, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+    else if (packed)               // one 1024-thread CTA per SM, leaves of up to 8192 records
+      NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1, 1024, true><<<grid_large, kFilterThreads, filter_bloom_smem<8, true, 8192, 4096, 1024>(), st>>>(
+          leaf_keys, leaf_vals, leaves, n_leaf, bits, c->vbits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+    else
+      NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1, 1024, false><<<grid_large, kFilterThreads,
+                                                                                 filter_bloom_smem<(int)sizeof(KeyT), false, 8192, 4096, 1024>(), st>>>(
+          leaf_keys, leaf_vals, leaves, n_leaf, bits, 0, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+  } else {
+    const size_t fsm = small ? filter_smem_small<KeyT>() : filter_smem_large<KeyT>();
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / (fsm + 18 * 1024)));   // + static smem of the leaf ordering
+    const unsigned fgrid = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * per_sm);
+    if (small)
+      NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItemsSmall, kFilterCapSmall, kFilterStaged><<<fgrid, kFilterThreads, fsm, st>>>(
+          (const KeyT*)leaf_keys, leaf_vals, leaves, n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+    else
+      NRP_LAUNCH((k_filter<KeyT, kFilterThreads, kFilterItems, kFilterCap, false><<<fgrid, kFilterThreads, fsm, st>>>(
+          (const KeyT*)leaf_keys, leaf_vals, leaves, n_leaf, bits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+  }
   CU(cudaGetLastError());
   return NRP_OK;
 }
@@ -592,14 +617,16 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
   const int64_t total1 = (r2 > 0 && !prepart) ? (int64_t)n_l1 * lp.cap1 : 0, total2 = (int64_t)n_leaf * lp.cap2;
   if (std::max(total1, total2) >= 0xffffe000ll || r2 > (int)c->opt_max_level_bits) { *overflowed = true; return NRP_OK; }   // beyond 32-bit record indices: exact path
   c->counts[NRP_C_BUCKETS] = (int64_t)n_leaf;
-  TRY(ensure_record_buffers(c, std::max<int64_t>(std::max(total1, total2), m_max), sizeof(KeyT), (int64_t)n_l1 * src.segs_per_bucket));
+  // records as single 64-bit words when key and value fit (a packed source dictates it)
+  const bool packed = from_ascii ? c->packed : src.packed;
+  TRY(ensure_record_buffers(c, std::max<int64_t>(std::max(total1, total2), m_max), packed ? 8 : sizeof(KeyT), (int64_t)n_l1 * src.segs_per_bucket));
   CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * CNT_N, st));
   c->n_records = 0;
 
   tm.begin(NRP_T_SPLIT1);
   // level-1 output: buffer A (regions of cap1, or the leaves themselves when there is one level)
-  KeyT* l1_keys = c->keysA.as<KeyT>(); uint32_t* l1_vals = c->valsA.as<uint32_t>();
-  KeyT* l2_keys = c->keysB.as<KeyT>(); uint32_t* l2_vals = c->valsB.as<uint32_t>();
+  void* l1_keys = c->keysA.ptr; uint32_t* l1_vals = c->valsA.as<uint32_t>();
+  void* l2_keys = c->keysB.ptr; uint32_t* l2_vals = c->valsB.as<uint32_t>();
   NRP_LAUNCH((k_init_region_cursors<<<grid_for(n_leaf, 256), 256, 0, st>>>(c->cursor2.as<uint32_t>(), n_leaf, lp.cap2)));
   if (r2 > 0 && !prepart)
     NRP_LAUNCH((k_init_region_cursors<<<grid_for(n_l1, 256), 256, 0, st>>>(c->cursor1.as<uint32_t>(), n_l1, lp.cap1)));
@@ -608,36 +635,52 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
   const RegionLimit lim2{lp.cap2, 0u, overflow, nullptr};
   if (m_max > 0 && !prepart) {
     if (from_ascii) {
-      NRP_LAUNCH((k_split_from_ascii<KeyT, 0, false><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-          P, c->flags.as<uint8_t>(), k, r1, 0, c->shard_tiles, c->part_base, c->j_bits, PassSel{0, 0u, 0u}, level1_cursor, l1_keys, l1_vals, lim1, PeerBuffers{}, 0)));
+      if (packed)
+        NRP_LAUNCH((k_split_from_ascii<uint64_t, 0, false, true><<<split_grid(c), kTileThreads, sizeof(SplitSmem<uint64_t, true>) + sizeof(TileStage), st>>>(
+            P, c->flags.as<uint8_t>(), k, r1, 0, c->shard_tiles, c->part_base, c->j_bits, c->vbits, PassSel{0, 0u, 0u}, level1_cursor,
+            (uint64_t*)l1_keys, l1_vals, lim1, PeerBuffers{}, 0)));
+      else
+        NRP_LAUNCH((k_split_from_ascii<KeyT, 0, false><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+            P, c->flags.as<uint8_t>(), k, r1, 0, c->shard_tiles, c->part_base, c->j_bits, 0, PassSel{0, 0u, 0u}, level1_cursor,
+            (KeyT*)l1_keys, l1_vals, lim1, PeerBuffers{}, 0)));
     } else {
       TRY(build_tiles(c, src.ext, src.n_seg, 0xffffffffu, 0, nullptr));
       const unsigned grid = (unsigned)std::min<int64_t>(m_max / kSplitTile + src.n_seg, (int64_t)c->n_sms * 4);
-      NRP_LAUNCH((k_split_from_records<KeyT, false><<<grid, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
-          src.keys, src.vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + src.n_seg, 0, r1, PassSel{0, 0u, 0u}, level1_cursor,
-          l1_keys, l1_vals, lim1)));
+      if (packed)
+        NRP_LAUNCH((k_split_from_records<uint64_t, false, true><<<grid, kSplitThreads, sizeof(SplitSmem<uint64_t, true>), st>>>(
+            (const uint64_t*)src.keys, src.vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + src.n_seg, 0, r1, c->vbits,
+            PassSel{0, 0u, 0u}, level1_cursor, (uint64_t*)l1_keys, l1_vals, lim1)));
+      else
+        NRP_LAUNCH((k_split_from_records<KeyT, false><<<grid, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
+            (const KeyT*)src.keys, src.vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + src.n_seg, 0, r1, 0, PassSel{0, 0u, 0u},
+            level1_cursor, (KeyT*)l1_keys, l1_vals, lim1)));
     }
   }
-  const KeyT* leaf_keys = l1_keys; const uint32_t* leaf_vals = l1_vals;
-  KeyT* out_keys = l2_keys; uint32_t* out_vals = l2_vals;
+  const void* leaf_keys = l1_keys; const uint32_t* leaf_vals = l1_vals;
+  void* out_keys = l2_keys; uint32_t* out_vals = l2_vals;
   if (r2 > 0 && m_max > 0) {
     tm.begin(NRP_T_SPLIT2);
-    const KeyT* in_k = prepart ? src.keys : l1_keys; const uint32_t* in_v = prepart ? src.vals : l1_vals;
+    const void* in_k = prepart ? src.keys : l1_keys; const uint32_t* in_v = prepart ? src.vals : l1_vals;
     const SegExtents ext = prepart ? src.ext : SegExtents{nullptr, 0, c->cursor1.as<uint32_t>(), lp.cap1};
     const uint32_t n_seg = prepart ? src.n_seg : n_l1;
     TRY(build_tiles(c, ext, n_seg, prepart ? src.segs_per_bucket : 1u, r2, cnt + CNT_RECORDS));
     const unsigned grid2 = (unsigned)std::min<int64_t>(m_max / kSplitTile + n_seg, (int64_t)c->n_sms * 4);
-    NRP_LAUNCH((k_split_from_records<KeyT, false><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
-        in_k, in_v, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + n_seg, r1, r2, PassSel{0, 0u, 0u}, c->cursor2.as<uint32_t>(),
-        l2_keys, l2_vals, lim2)));
+    if (packed)
+      NRP_LAUNCH((k_split_from_records<uint64_t, false, true><<<grid2, kSplitThreads, sizeof(SplitSmem<uint64_t, true>), st>>>(
+          (const uint64_t*)in_k, in_v, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + n_seg, r1, r2, c->vbits, PassSel{0, 0u, 0u},
+          c->cursor2.as<uint32_t>(), (uint64_t*)l2_keys, l2_vals, lim2)));
+    else
+      NRP_LAUNCH((k_split_from_records<KeyT, false><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
+          (const KeyT*)in_k, in_v, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + n_seg, r1, r2, 0, PassSel{0, 0u, 0u},
+          c->cursor2.as<uint32_t>(), (KeyT*)l2_keys, l2_vals, lim2)));
     leaf_keys = l2_keys; leaf_vals = l2_vals;
     out_keys = l1_keys; out_vals = l1_vals;                  // level-1 regions are consumed: candidates go there
   }
   tm.begin(NRP_T_FILTER);
   if (m_max > 0) {
     if (r2 == 0) NRP_LAUNCH((k_region_total<<<1, 1024, 0, st>>>(c->cursor2.as<uint32_t>(), n_leaf, lp.cap2, cnt + CNT_RECORDS)));
-    TRY((launch_filter<KeyT>(c, leaf_keys, leaf_vals, LeafExtents{nullptr, c->cursor2.as<uint32_t>(), lp.cap2}, n_leaf, bits, m_max >> bits,
-                             out_keys, out_vals)));
+    TRY((launch_filter<KeyT>(c, packed, leaf_keys, leaf_vals, LeafExtents{nullptr, c->cursor2.as<uint32_t>(), lp.cap2}, n_leaf, bits, m_max >> bits,
+                             (KeyT*)out_keys, out_vals)));
   }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->h_counters, cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, st));
@@ -649,9 +692,10 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
   c->counts[NRP_C_CANDIDATES] = c->n_cand;
   c->counts[NRP_C_RUNS] = 1;
   c->counts[NRP_C_DIRECT] = 1;
+  c->counts[NRP_C_PACKED] = packed ? 1 : 0;
   c->cand_unsorted = (uint32_t)c->h_counters[CNT_UNSORTED] != 0;
   c->cand_keys = out_keys; c->cand_vals = out_vals;
-  c->spare_keys = const_cast<KeyT*>(leaf_keys); c->spare_vals = const_cast<uint32_t*>(leaf_vals);
+  c->spare_keys = const_cast<void*>(leaf_keys); c->spare_vals = const_cast<uint32_t*>(leaf_vals);
   return NRP_OK;
 }
 
@@ -675,12 +719,22 @@ int stage_bulk_exact(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer&
   const uint32_t n_leaf = 1u << bits;
   c->counts[NRP_C_BUCKETS] = (int64_t)n_leaf * n_passes;
   c->counts[NRP_C_DIRECT] = 0;
+  c->counts[NRP_C_PACKED] = 0;
   TRY(ensure_record_buffers(c, m_pass, sizeof(KeyT), src.n_seg));
   CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * CNT_N, st));
   c->n_records = 0;
   KeyT* leaf_keys = nullptr; uint32_t* leaf_vals = nullptr; KeyT* free_keys = nullptr; uint32_t* free_vals = nullptr;
   int64_t cand_so_far = 0;
   const RegionLimit no_limit{0u, 0u, nullptr, nullptr};
+  const KeyT* src_keys = (const KeyT*)src.keys; const uint32_t* src_vals = src.vals;
+  if (!from_ascii && src.packed && m_max > 0) {
+    // the source holds packed words (direct sharded path): the exact path works on (key, value) arrays at the same indices
+    TRY(c->fb_keys.ensure(sizeof(KeyT) * (size_t)(src.m_upper + 16))); TRY(c->fb_vals.ensure(4 * (size_t)(src.m_upper + 16)));
+    TRY(build_tiles(c, src.ext, src.n_seg, 0xffffffffu, 0, nullptr));
+    NRP_LAUNCH((k_unpack_tiles<KeyT><<<(unsigned)std::min<int64_t>(m_max / kSplitTile + src.n_seg, (int64_t)c->n_sms * 4), 512, 0, st>>>(
+        (const uint64_t*)src.keys, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + src.n_seg, c->vbits, c->fb_keys.as<KeyT>(), c->fb_vals.as<uint32_t>())));
+    src_keys = c->fb_keys.as<KeyT>(); src_vals = c->fb_vals.as<uint32_t>();
+  }
   const uint32_t* n_src_tiles = c->tile_prefix.as<uint32_t>() + src.n_seg;
   const int64_t src_tiles_max = m_max / kSplitTile + src.n_seg;
 
@@ -701,7 +755,7 @@ int stage_bulk_exact(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer&
         // the source's tile list is rebuilt every pass: the level-2 split below reuses the descriptor buffer
         TRY(build_tiles(c, src.ext, src.n_seg, 0xffffffffu, 0, nullptr));
         const unsigned grid = (unsigned)std::min<int64_t>(src_tiles_max, (int64_t)c->n_sms * (bits >= 15 ? 1 : 2));
-        NRP_LAUNCH((k_hist_from_tiles<KeyT><<<grid, 512, 4u << bits, st>>>(src.keys, c->tile_desc.as<uint4>(), n_src_tiles, bits, sel, c->hist.as<uint32_t>())));
+        NRP_LAUNCH((k_hist_from_tiles<KeyT><<<grid, 512, 4u << bits, st>>>(src_keys, c->tile_desc.as<uint4>(), n_src_tiles, bits, sel, c->hist.as<uint32_t>())));
       }
     }
     exclusive_scan<uint32_t, uint32_t>(c->hist.as<uint32_t>(), c->leaf_off.as<uint32_t>(), n_leaf, c->scan_scratch.as<uint32_t>(), st);
@@ -724,11 +778,11 @@ int stage_bulk_exact(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer&
     if (m_max > 0) {
       if (from_ascii) {
         NRP_LAUNCH((k_split_from_ascii<KeyT, 0, true><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-            P, c->flags.as<uint8_t>(), k, r1, 0, c->shard_tiles, c->part_base, c->j_bits, sel, level1_cursor, leaf_keys, leaf_vals, no_limit, PeerBuffers{}, 0)));
+            P, c->flags.as<uint8_t>(), k, r1, 0, c->shard_tiles, c->part_base, c->j_bits, 0, sel, level1_cursor, leaf_keys, leaf_vals, no_limit, PeerBuffers{}, 0)));
       } else {
         const unsigned grid = (unsigned)std::min<int64_t>(src_tiles_max, (int64_t)c->n_sms * 4);
         NRP_LAUNCH((k_split_from_records<KeyT, true><<<grid, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
-            src.keys, src.vals, c->tile_desc.as<uint4>(), n_src_tiles, 0, r1, sel, level1_cursor, leaf_keys, leaf_vals, no_limit)));
+            src_keys, src_vals, c->tile_desc.as<uint4>(), n_src_tiles, 0, r1, 0, sel, level1_cursor, leaf_keys, leaf_vals, no_limit)));
       }
     }
     if (r2 > 0 && m_max > 0) {
@@ -737,7 +791,7 @@ int stage_bulk_exact(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer&
       TRY(build_tiles(c, SegExtents{c->leaf_off.as<uint32_t>(), r2, nullptr, 0u}, n_l1, 1u, r2, nullptr));
       const unsigned grid2 = (unsigned)std::min<int64_t>(n_pass / kSplitTile + n_l1, (int64_t)c->n_sms * 4);
       NRP_LAUNCH((k_split_from_records<KeyT, false><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
-          leaf_keys, leaf_vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + n_l1, r1, r2, PassSel{0, 0u, 0u}, c->cursor2.as<uint32_t>(),
+          leaf_keys, leaf_vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + n_l1, r1, r2, 0, PassSel{0, 0u, 0u}, c->cursor2.as<uint32_t>(),
           free_keys, free_vals, no_limit)));
       std::swap(leaf_keys, free_keys); std::swap(leaf_vals, free_vals);
     }
@@ -745,7 +799,7 @@ int stage_bulk_exact(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer&
     KeyT* out_keys = n_passes > 1 ? c->cand_keys_buf.as<KeyT>() : free_keys;
     uint32_t* out_vals = n_passes > 1 ? c->cand_vals_buf.as<uint32_t>() : free_vals;
     if (m_max > 0)
-      TRY((launch_filter<KeyT>(c, leaf_keys, leaf_vals, LeafExtents{c->leaf_off.as<uint32_t>(), nullptr, 0u}, n_leaf, bits,
+      TRY((launch_filter<KeyT>(c, false, leaf_keys, leaf_vals, LeafExtents{c->leaf_off.as<uint32_t>(), nullptr, 0u}, n_leaf, bits,
                                (m_plan >> pass_bits) >> bits, out_keys, out_vals)));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_counters, cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, st));
@@ -1018,6 +1072,20 @@ int finish_timing(nrp_ctx* c, StageTimer& tm) {
   return NRP_OK;
 }
 
+// layout of a record of the staged parts at window length k
+void record_layout(nrp_ctx* c, int k) {
+  // carry the window index in the record value when (part, window) fits 32 bits
+  int part_bits = 1, win_bits = 1;
+  while (((int64_t)1 << part_bits) < c->n_parts) ++part_bits;
+  const int64_t max_windows = c->max_len - k + 1;
+  while (((int64_t)1 << win_bits) < max_windows) ++win_bits;
+  c->j_bits = (max_windows >= 1 && part_bits + win_bits <= 32) ? win_bits : 0;
+  if (c->opt_no_window_carry) c->j_bits = 0;
+  c->vbits = std::min(32, part_bits + c->j_bits);
+  // one 64-bit word per record on the direct path when the 2k key bits and the value bits fit
+  c->packed = c->opt_packed && !c->opt_no_bloom && 2 * k + c->vbits <= 64;
+}
+
 void begin_job(nrp_ctx* c, int k, size_t key_bytes, int want_edges) {
   memset(c->counts, 0, sizeof(c->counts));
   memset(c->timings, 0, sizeof(c->timings));
@@ -1027,13 +1095,7 @@ void begin_job(nrp_ctx* c, int k, size_t key_bytes, int want_edges) {
   c->counts[NRP_C_RUNS] = 1;
   c->k = k; c->key_bytes = (int)key_bytes;
   c->have_result = false;
-  // carry the window index in the record value when (part, window) fits 32 bits
-  int part_bits = 1, win_bits = 1;
-  while (((int64_t)1 << part_bits) < c->n_parts) ++part_bits;
-  const int64_t max_windows = c->max_len - k + 1;
-  while (((int64_t)1 << win_bits) < max_windows) ++win_bits;
-  c->j_bits = (max_windows >= 1 && part_bits + win_bits <= 32) ? win_bits : 0;
-  if (c->opt_no_window_carry) c->j_bits = 0;
+  record_layout(c, k);
 }
 
 template <typename KeyT>
@@ -1090,7 +1152,7 @@ int shard_extract_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int internal_r
   tm.begin(NRP_T_SPLIT1);
   if (c->shard_m_max > 0)
     NRP_LAUNCH((k_split_from_ascii<KeyT, 1, false><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, 8, n_owners, c->shard_tiles, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>(),
+        P, c->flags.as<uint8_t>(), k, 8, n_owners, c->shard_tiles, 0u, c->j_bits, 0, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>(),
         RegionLimit{0u, 0u, nullptr, nullptr}, PeerBuffers{}, 0)));
   CU(cudaGetLastError());
   tm.finish(c->timings);
@@ -1176,7 +1238,7 @@ int shard_scatter_impl(nrp_ctx* c, int k, const int64_t* write_offsets) {
   tm.begin(NRP_T_SPLIT1);
   if (c->shard_m_max > 0)
     NRP_LAUNCH((k_split_from_ascii<KeyT, 1, false><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, 8, c->n_owners, c->shard_tiles, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr,
+        P, c->flags.as<uint8_t>(), k, 8, c->n_owners, c->shard_tiles, 0u, c->j_bits, 0, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr,
         RegionLimit{0u, 0u, nullptr, nullptr}, c->peers, 1)));
   CU(cudaGetLastError());
   tm.finish(c->timings);
@@ -1246,10 +1308,18 @@ int shard_scatter_direct_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int int
   CU(cudaMemsetAsync(cnt + CNT_SCATTER_OVERFLOW, 0, 16, st));
   NRP_LAUNCH((k_init_owner_cursors<<<grid_for(nd, 256), 256, 0, st>>>(c->cursor1.as<uint32_t>(), c->region_ends.as<uint32_t>(), nd, c->sh_r1,
                                                                     (uint32_t)n_owners, (uint32_t)c->my_rank, c->sh_cap1s)));
-  if (c->shard_m_max > 0)
-    NRP_LAUNCH((k_split_from_ascii<KeyT, 2, false><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, c->sh_r1, n_owners, c->shard_tiles, 0u, c->j_bits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr,
-        RegionLimit{c->sh_cap1s, 0u, reinterpret_cast<uint32_t*>(cnt + CNT_SCATTER_OVERFLOW), c->region_ends.as<uint32_t>()}, c->peers_d, 1)));
+  if (c->packed != c->sh_packed) return fail(NRP_E_STATE, "receive buffers were exported for another record layout");
+  const RegionLimit lim{c->sh_cap1s, 0u, reinterpret_cast<uint32_t*>(cnt + CNT_SCATTER_OVERFLOW), c->region_ends.as<uint32_t>()};
+  if (c->shard_m_max > 0) {
+    if (c->packed)
+      NRP_LAUNCH((k_split_from_ascii<uint64_t, 2, false, true><<<split_grid(c), kTileThreads, sizeof(SplitSmem<uint64_t, true>) + sizeof(TileStage), st>>>(
+          P, c->flags.as<uint8_t>(), k, c->sh_r1, n_owners, c->shard_tiles, 0u, c->j_bits, c->vbits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(),
+          nullptr, nullptr, lim, c->peers_d, 1)));
+    else
+      NRP_LAUNCH((k_split_from_ascii<KeyT, 2, false><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+          P, c->flags.as<uint8_t>(), k, c->sh_r1, n_owners, c->shard_tiles, 0u, c->j_bits, 0, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(),
+          nullptr, nullptr, lim, c->peers_d, 1)));
+  }
   PeerEnds pe;
   for (int o = 0; o < kMaxPeers; ++o) pe.ptr[o] = c->peer_ends[o];
   NRP_LAUNCH((k_push_region_ends<<<grid_for(nd, 256), 256, 0, st>>>(c->cursor1.as<uint32_t>(), nd, c->sh_r1, (uint32_t)n_owners, (uint32_t)c->my_rank, c->sh_cap1s, pe,
@@ -1269,7 +1339,8 @@ int shard_group_direct_impl(nrp_ctx* c, int k, int internal_repeats) {
   StageTimer tm(c);
   BulkSource<KeyT> src;
   src.from_parts = false;
-  src.keys = c->recv_keys_d.as<KeyT>(); src.vals = c->recv_vals_d.as<uint32_t>();
+  src.packed = c->sh_packed;
+  src.keys = c->recv_keys_d.ptr; src.vals = c->recv_vals_d.as<uint32_t>();
   src.n_seg = (uint32_t)c->sh_world << c->sh_r1;
   src.ext = SegExtents{nullptr, 0, c->recv_ends.as<uint32_t>(), c->sh_cap1s};
   src.segs_per_bucket = (uint32_t)c->sh_world;
@@ -1492,11 +1563,13 @@ int nrp_peer_export_direct(nrp_ctx* c, int64_t windows_total, int n_owners, int 
   const int64_t n_regions = (int64_t)n_owners << r1;
   const int64_t capacity = n_regions * cap1s;
   if (capacity >= 0xffffe000ll) return fail(NRP_E_UNSUPPORTED, "receive regions exceed 32-bit record indices");
+  if (!c->have_parts) return fail(NRP_E_STATE, "nrp_load_parts has not been called");
+  record_layout(c, k);                                   // every rank stages the same parts: the same layout everywhere
   const size_t key_bytes = k <= 16 ? 4 : 8;
-  TRY(c->recv_keys_d.ensure(key_bytes * (size_t)(capacity + 16)));
+  TRY(c->recv_keys_d.ensure((c->packed ? 8 : key_bytes) * (size_t)(capacity + 16)));
   TRY(c->recv_vals_d.ensure(4 * (size_t)(capacity + 16)));
   TRY(c->recv_ends.ensure(4 * (size_t)(kLevelBuckets * kMaxPeers + 4)));
-  c->sh_world = n_owners; c->sh_r1 = r1; c->sh_cap1s = cap1s; c->sh_key_bytes = (int)key_bytes;
+  c->sh_world = n_owners; c->sh_r1 = r1; c->sh_cap1s = cap1s; c->sh_key_bytes = (int)key_bytes; c->sh_packed = c->packed;
   c->sh_windows_total = windows_total; c->sh_m_owner = m_owner;
   cudaIpcMemHandle_t h[3];
   CU(cudaIpcGetMemHandle(&h[0], c->recv_keys_d.ptr));

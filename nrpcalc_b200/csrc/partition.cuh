@@ -19,6 +19,7 @@
 // and one write by split2, one read by the filter  ->  L/W + 4*(K_b+4) bytes, against
 // L/W + (2*ceil(2k/8)+4)*(K_b+4) + K_b for the LSD formulation in SURVEY.md 8d.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace nrp {
@@ -31,10 +32,12 @@ constexpr int kLevelBuckets = 1 << kMaxLevelBits;
 constexpr int kLeafSortCap = 1024;              // candidates of one leaf that are ordered inside the filter kernel
 static_assert(kLevelBuckets <= kSplitThreads, "one thread per bucket in split_scatter");
 
-template <typename KeyT>
+// PACKED: a record is ONE 64-bit word (canonical k-mer << vbits) | value -- possible whenever 2k + vbits <= 64 (vbits = bits of
+// the part index plus bits of the window index): one load / one store per record in every pass and 8 instead of 12 bytes.
+template <typename KeyT, bool PACKED = false>
 struct alignas(16) SplitSmem {
   KeyT keys[kSplitTile];
-  uint32_t vals[kSplitTile];
+  uint32_t vals[PACKED ? 4 : kSplitTile];
   uint16_t dig[kSplitTile];          // bucket of the record at this position of the reordered tile
   uint32_t cnt[kLevelBuckets];
   uint32_t base[kLevelBuckets];
@@ -75,8 +78,8 @@ constexpr uint32_t kNoSpace = 0xffffffffu;
 // scan the bucket counts, claim global space for each non-empty bucket with one atomic per (tile, bucket),
 // reorder the tile through shared memory and write each bucket's run contiguously.
 // peer_shift >= 0 with peers: the buffers of digit d are those of owner d >> peer_shift (peer stores over NVLink).
-template <typename KeyT>
-__device__ __forceinline__ void split_reorder(SplitSmem<KeyT>& s, const KeyT (&key)[kSplitItems], const uint32_t (&val)[kSplitItems],
+template <typename KeyT, bool PACKED = false>
+__device__ __forceinline__ void split_reorder(SplitSmem<KeyT, PACKED>& s, const KeyT (&key)[kSplitItems], const uint32_t (&val)[kSplitItems],
                                               const uint32_t (&dr)[kSplitItems], int nb, uint32_t* cursor, RegionLimit lim) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   constexpr int kWarps = kSplitThreads / 32;
@@ -122,7 +125,7 @@ __device__ __forceinline__ void split_reorder(SplitSmem<KeyT>& s, const KeyT (&k
       const uint32_t d = dr[e] >> 16;
       const uint32_t pos = s.base[d] + (dr[e] & 0xffffu);
       s.keys[pos] = key[e];
-      s.vals[pos] = val[e];
+      if (!PACKED) s.vals[pos] = val[e];
       s.dig[pos] = (uint16_t)d;
     }
   }
@@ -130,8 +133,8 @@ __device__ __forceinline__ void split_reorder(SplitSmem<KeyT>& s, const KeyT (&k
 }
 
 // second half: every bucket's run of the reordered tile goes to its place in global (or peer) memory
-template <typename KeyT>
-__device__ __forceinline__ void split_flush(SplitSmem<KeyT>& s, KeyT* out_keys, uint32_t* out_vals, const PeerBuffers* peers = nullptr,
+template <typename KeyT, bool PACKED = false>
+__device__ __forceinline__ void split_flush(SplitSmem<KeyT, PACKED>& s, KeyT* out_keys, uint32_t* out_vals, const PeerBuffers* peers = nullptr,
                                             int peer_shift = 0) {
   const uint32_t total = s.total;
   for (uint32_t i = threadIdx.x; i < total; i += kSplitThreads) {
@@ -142,16 +145,16 @@ __device__ __forceinline__ void split_flush(SplitSmem<KeyT>& s, KeyT* out_keys, 
     if (peers) {                                   // digit d lives in its owner's receive buffer (peer store over NVLink)
       const uint32_t o = d >> peer_shift;
       reinterpret_cast<KeyT*>(peers->keys[o])[dst] = s.keys[i];
-      peers->vals[o][dst] = s.vals[i];
+      if (!PACKED) peers->vals[o][dst] = s.vals[i];
     } else {
       out_keys[dst] = s.keys[i];
-      out_vals[dst] = s.vals[i];
+      if (!PACKED) out_vals[dst] = s.vals[i];
     }
   }
 }
 
 template <typename KeyT>
-__device__ __forceinline__ void split_scatter(SplitSmem<KeyT>& s, const KeyT (&key)[kSplitItems], const uint32_t (&val)[kSplitItems],
+__device__ __forceinline__ void split_scatter(SplitSmem<KeyT, false>& s, const KeyT (&key)[kSplitItems], const uint32_t (&val)[kSplitItems],
                                               const uint32_t (&dr)[kSplitItems], int nb,
                                               uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals, RegionLimit lim,
                                               const PeerBuffers* peers = nullptr, int peer_shift = 0) {
@@ -218,6 +221,22 @@ __global__ void __launch_bounds__(512) k_hist_from_tiles(const KeyT* keys, const
   }
 }
 
+// packed words of a segmented record list -> (key, value) arrays at the same indices (fallback to the exact path only)
+template <typename KeyT>
+__global__ void __launch_bounds__(512) k_unpack_tiles(const uint64_t* words, const uint4* tile_desc, const uint32_t* n_tiles_ptr, int vbits,
+                                                     KeyT* out_keys, uint32_t* out_vals) {
+  const uint32_t n_tiles = *n_tiles_ptr;
+  const uint32_t vmask = (uint32_t)((1ull << vbits) - 1ull);
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint4 d4 = __ldg(tile_desc + tile);
+    for (uint32_t i = d4.x + threadIdx.x; i < d4.y; i += blockDim.x) {
+      const uint64_t w = words[i];
+      out_keys[i] = (KeyT)(w >> vbits);
+      out_vals[i] = (uint32_t)w & vmask;
+    }
+  }
+}
+
 // cursors of the direct path: cursor[i] = i * cap (region starts)
 __global__ void k_init_region_cursors(uint32_t* cursor, uint32_t n, uint32_t cap) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -251,13 +270,13 @@ __global__ void __launch_bounds__(1024) k_region_total(const uint32_t* cursor, u
 // cursor[d] must hold the start offset of bucket d and is advanced atomically.
 // Record value = part index, or (part << j_bits) | window index when both fit 32 bits (j_bits > 0): sorting by value
 // is then sorting by (part, window), and a group's first record carries the group's rank for free.
-template <typename KeyT, int MODE, bool PASSES>
+template <typename KeyT, int MODE, bool PASSES, bool PACKED = false>
 __global__ void __launch_bounds__(kTileThreads, 2) k_split_from_ascii(Parts P, const uint8_t* flags, int k, int r1, int n_owners, int64_t n_tiles,
-                                                                  uint32_t part_base, int j_bits, PassSel sel, uint32_t* cursor, KeyT* out_keys,
+                                                                  uint32_t part_base, int j_bits, int vbits, PassSel sel, uint32_t* cursor, KeyT* out_keys,
                                                                   uint32_t* out_vals, RegionLimit lim, PeerBuffers peers, int use_peers) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SplitSmem<KeyT>& s = *reinterpret_cast<SplitSmem<KeyT>*>(smem_raw);
-  TileStage& stage = *reinterpret_cast<TileStage*>(smem_raw + sizeof(SplitSmem<KeyT>));
+  SplitSmem<KeyT, PACKED>& s = *reinterpret_cast<SplitSmem<KeyT, PACKED>*>(smem_raw);
+  TileStage& stage = *reinterpret_cast<TileStage*>(smem_raw + sizeof(SplitSmem<KeyT, PACKED>));
   const int nb = MODE == 0 ? (1 << r1) : MODE == 1 ? n_owners : (n_owners << r1);
   static_assert(kLevelBuckets == kTileThreads, "one counter per thread");
   const uint32_t j_mask = j_bits ? 0xffffffffu : 0u;
@@ -287,14 +306,19 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_split_from_ascii(Parts P, c
       const uint32_t rank = atomicAdd(&s.cnt[d], 1u);
 #pragma unroll
       for (int q = 0; q < kSplitItems; ++q)
-        if (q == e) { key[q] = (KeyT)canon; val[q] = ((part_base + part) << j_bits) | (j & j_mask); dr[q] = (d << 16) | rank; }
+        if (q == e) {
+          const uint32_t v = ((part_base + part) << j_bits) | (j & j_mask);
+          if (PACKED) key[q] = (KeyT)((canon << vbits) | v);
+          else { key[q] = (KeyT)canon; val[q] = v; }
+          dr[q] = (d << 16) | rank;
+        }
     });
     __syncthreads();
-    split_reorder<KeyT>(s, key, val, dr, nb, cursor, lim);
+    split_reorder<KeyT, PACKED>(s, key, val, dr, nb, cursor, lim);
     if (t + gridDim.x < n_tiles) tile_fetch(P, tile + gridDim.x, threadIdx.x, flags, pre);
-    if (MODE == 0) split_flush<KeyT>(s, out_keys, out_vals);
-    else if (MODE == 1) split_flush<KeyT>(s, out_keys, out_vals, use_peers ? &peers : nullptr, 0);
-    else split_flush<KeyT>(s, out_keys, out_vals, &peers, r1);
+    if (MODE == 0) split_flush<KeyT, PACKED>(s, out_keys, out_vals);
+    else if (MODE == 1) split_flush<KeyT, PACKED>(s, out_keys, out_vals, use_peers ? &peers : nullptr, 0);
+    else split_flush<KeyT, PACKED>(s, out_keys, out_vals, &peers, r1);
     __syncthreads();
   }
 }
@@ -304,13 +328,13 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_split_from_ascii(Parts P, c
 // segment is cut into tiles of kSplitTile records and each tile has a descriptor {first record, end, index of the
 // first child cursor}.  Persistent CTAs walk the tile list; the next tile's descriptor is fetched one tile ahead.
 // Child bucket = hash bits [64 - r_done - r2, 64 - r_done).
-template <typename KeyT, bool PASSES>
+template <typename KeyT, bool PASSES, bool PACKED = false>
 __global__ void __launch_bounds__(kSplitThreads, 2) k_split_from_records(const KeyT* __restrict__ in_keys, const uint32_t* __restrict__ in_vals,
                                                                      const uint4* __restrict__ tile_desc, const uint32_t* n_tiles_ptr,
-                                                                     int r_done, int r2, PassSel sel, uint32_t* cursor, KeyT* out_keys,
+                                                                     int r_done, int r2, int vbits, PassSel sel, uint32_t* cursor, KeyT* out_keys,
                                                                      uint32_t* out_vals, RegionLimit lim) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SplitSmem<KeyT>& s = *reinterpret_cast<SplitSmem<KeyT>*>(smem_raw);
+  SplitSmem<KeyT, PACKED>& s = *reinterpret_cast<SplitSmem<KeyT, PACKED>*>(smem_raw);
   const uint32_t n_tiles = *n_tiles_ptr;
   const uint32_t mask = (1u << r2) - 1u;
   KeyT key[kSplitItems];
@@ -322,7 +346,7 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split_from_records(const K
       const uint32_t idx = t4.x + threadIdx.x + e * kSplitThreads;
       const bool ok = idx < t4.y;
       key[e] = ok ? __ldg(in_keys + idx) : KeyT(0);
-      val[e] = ok ? __ldg(in_vals + idx) : 0u;
+      if (!PACKED) val[e] = ok ? __ldg(in_vals + idx) : 0u;
     }
   };
   uint4 d4 = blockIdx.x < n_tiles ? __ldg(tile_desc + blockIdx.x) : make_uint4(0, 0, 0, 0);
@@ -337,7 +361,7 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split_from_records(const K
       uint32_t idx = start + threadIdx.x + e * kSplitThreads;
       dr[e] = 0xffffffffu;
       if (idx < end) {
-        const uint64_t h = key_hash((uint64_t)key[e]);
+        const uint64_t h = key_hash(PACKED ? ((uint64_t)key[e] >> vbits) : (uint64_t)key[e]);
         if (!PASSES || sel.accept(h)) {
           uint32_t d = (uint32_t)(h >> (64 - r_done - r2)) & mask;
           dr[e] = (d << 16) | atomicAdd(&s.cnt[d], 1u);
@@ -347,13 +371,13 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split_from_records(const K
     __syncthreads();
     RegionLimit tile_lim = lim;
     tile_lim.first = child0;
-    split_reorder<KeyT>(s, key, val, dr, 1 << r2, cursor + child0, tile_lim);
+    split_reorder<KeyT, PACKED>(s, key, val, dr, 1 << r2, cursor + child0, tile_lim);
     d4 = next;
     if (tile + gridDim.x < n_tiles) {
       load_tile(d4);
       if (tile + 2 * gridDim.x < n_tiles) next = __ldg(tile_desc + tile + 2 * gridDim.x);
     }
-    split_flush<KeyT>(s, out_keys, out_vals);
+    split_flush<KeyT, PACKED>(s, out_keys, out_vals);
     __syncthreads();
   }
 }
@@ -671,52 +695,63 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // capacity of a leaf = T * E records; WORDS = 32-bit words per bit map (16 bits per record or more).
-// Shared memory: exact table + suspect list + two bit maps + key staging (one leaf) + value staging (two leaves, ping-pong).
-// SORTCAP = suspects of one leaf that the exact stage and the in-leaf ordering can take (more: the global sort runs).
-template <typename KeyT, int CAP, int WORDS, int SORTCAP> constexpr size_t filter_bloom_smem() {
-  return sizeof(KeyT) * (2 * SORTCAP + SORTCAP) + 4 * (2 * WORDS + 2 * SORTCAP) + 2 * SORTCAP +
-         sizeof(KeyT) * (CAP + 8) + 2 * 4 * (CAP + 8) + 128;
+// Shared memory: exact table + suspect list + two bit maps + key staging (one leaf) + value staging (two leaves, ping-pong;
+// none for packed records).  SORTCAP = suspects of one leaf that the exact stage and the in-leaf ordering can take (more:
+// the global sort runs).  REC = bytes of a record word (8 for packed records, else the key size).
+template <int REC, bool PACKED, int CAP, int WORDS, int SORTCAP> constexpr size_t filter_bloom_smem() {
+  return (size_t)REC * (2 * SORTCAP + SORTCAP) + 4 * (2 * WORDS + 2 * SORTCAP) + 2 * SORTCAP +
+         (size_t)REC * (CAP + 8) + (PACKED ? 0 : 2 * 4 * (CAP + 8)) + 128;
 }
 
-template <typename KeyT, int T, int E, int WORDS, int MINB, int SORTCAP>
-__global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, LeafExtents leaves,
-                                                      uint32_t n_leaf, int leaf_bits, uint32_t cap, KeyT* cand_keys, uint32_t* cand_vals,
+template <typename KeyT, int T, int E, int WORDS, int MINB, int SORTCAP, bool PACKED>
+__global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict__ keys_in, const uint32_t* __restrict__ vals, LeafExtents leaves,
+                                                      uint32_t n_leaf, int leaf_bits, int vbits, uint32_t cap, KeyT* cand_keys, uint32_t* cand_vals,
                                                       unsigned long long* n_cand, uint32_t* n_oversized, uint32_t* unsorted) {
+  // RecT: what a leaf holds -- the key (values in a second array) or the packed word (key << vbits) | value
+  using RecT = typename std::conditional<PACKED, uint64_t, KeyT>::type;
+  const RecT* __restrict__ keys = reinterpret_cast<const RecT*>(keys_in);
   constexpr int kBloomWords = WORDS, kBloomCap = T * E;
   constexpr int kSuspectSlots = 2 * SORTCAP, kLeafSortCap = SORTCAP;
   static_assert(SORTCAP <= T, "one thread per suspect");
   constexpr uint32_t kBitMask = (uint32_t)WORDS * 32u - 1u;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // 16-byte aligned blocks first (they are cleared with 128-bit stores)
-  KeyT* table = reinterpret_cast<KeyT*>(smem_raw);                                  // kSuspectSlots
+  RecT* table = reinterpret_cast<RecT*>(smem_raw);                                  // kSuspectSlots (canonical k-mers)
   uint32_t* map_a = reinterpret_cast<uint32_t*>(table + kSuspectSlots);             // kBloomWords
   uint32_t* map_b = map_a + kBloomWords;                                             // kBloomWords
   unsigned char* marked = reinterpret_cast<unsigned char*>(map_b + kBloomWords);    // kSuspectSlots
-  KeyT* c_keys = reinterpret_cast<KeyT*>(marked + kSuspectSlots);                   // kLeafSortCap
+  RecT* c_keys = reinterpret_cast<RecT*>(marked + kSuspectSlots);                   // kLeafSortCap
   uint32_t* c_vals = reinterpret_cast<uint32_t*>(c_keys + kLeafSortCap);            // kLeafSortCap
   uint32_t* c_rank = c_vals + kLeafSortCap;                                          // kLeafSortCap
-  // staging, filled by TMA bulk copies (16-byte aligned source windows around the leaf): the keys of the NEXT leaf (they are
+  // staging, filled by TMA bulk copies (16-byte aligned source windows around the leaf): the records of the NEXT leaf (they are
   // copied to registers at the top of a leaf's turn) and the values of this and the next leaf (only suspects read theirs)
-  KeyT* st_keys = reinterpret_cast<KeyT*>((reinterpret_cast<uintptr_t>(c_rank + kLeafSortCap) + 15) & ~uintptr_t(15));
+  RecT* st_keys = reinterpret_cast<RecT*>((reinterpret_cast<uintptr_t>(c_rank + kLeafSortCap) + 15) & ~uintptr_t(15));
   uint32_t* st_vals0 = reinterpret_cast<uint32_t*>(st_keys + kBloomCap + 8);
   uint32_t* st_vals1 = st_vals0 + kBloomCap + 8;
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_c1, s_c2;
   __shared__ unsigned long long s_cbase;
-  const KeyT kEmpty = ~KeyT(0);
+  const RecT kEmpty = ~RecT(0);
+  const uint32_t vmask = PACKED ? (uint32_t)((1ull << vbits) - 1ull) : 0u;
+  auto canon_of = [&](RecT r) -> uint64_t { return PACKED ? ((uint64_t)r >> vbits) : (uint64_t)r; };
   const int lane = threadIdx.x & 31;
   const int bit_shift = 44 - leaf_bits, slot_shift = 33 - leaf_bits;     // 20 hash bits for the maps, the next 11 for the table
   for (int i = threadIdx.x; i < kLeafSortCap; i += T) c_rank[i] = 0;
-  constexpr uint32_t kKeysPer16 = 16 / sizeof(KeyT);
+  constexpr uint32_t kKeysPer16 = 16 / sizeof(RecT);
   // thread 0 starts the bulk copies of a leaf: the source windows are widened to 16-byte boundaries
   auto stage = [&](uint32_t slo, uint32_t sn, uint32_t* st_vals) {
     if (sn < 2 || sn > cap || sn > (uint32_t)kBloomCap) return;
     const uint32_t k0 = slo & ~(kKeysPer16 - 1), k1 = (slo + sn + kKeysPer16 - 1) & ~(kKeysPer16 - 1);
     const uint32_t v0 = slo & ~3u, v1 = (slo + sn + 3u) & ~3u;
-    const uint32_t kb = (k1 - k0) * (uint32_t)sizeof(KeyT), vb = (v1 - v0) * 4u;
+    const uint32_t kb = (k1 - k0) * (uint32_t)sizeof(RecT), vb = PACKED ? 0u : (v1 - v0) * 4u;
     mbar_expect_tx(&s_bar, kb + vb);
     tma_bulk_load(st_keys, keys + k0, kb, &s_bar);
-    tma_bulk_load(st_vals, vals + v0, vb, &s_bar);
+    if (!PACKED) tma_bulk_load(st_vals, vals + v0, vb, &s_bar);
+  };
+  // one candidate record leaves the kernel as (key, value)
+  auto emit = [&](unsigned long long dst, RecT r, uint32_t v) {
+    if (PACKED) { cand_keys[dst] = (KeyT)((uint64_t)r >> vbits); cand_vals[dst] = (uint32_t)r & vmask; }
+    else { cand_keys[dst] = (KeyT)r; cand_vals[dst] = v; }
   };
   // leaf extents are read two leaves ahead so that no global-load latency sits on the per-leaf critical path
   auto extent = [&](uint32_t lf, uint32_t& elo, uint32_t& en) { leaves.get(lf, n_leaf, elo, en); };
@@ -733,11 +768,11 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict
     const uint32_t* my_vals = (turn ? st_vals1 : st_vals0) + (lo & 3u);          // this leaf's values (valid for the whole turn)
     // records held by this thread: i = threadIdx.x + e * T < n
     const int ne = (fits && n > threadIdx.x) ? (int)((n - threadIdx.x + (uint32_t)T - 1u) / (uint32_t)T) : 0;
-    KeyT key[E];
+    RecT key[E];
     if (fits) {                                     // uniform: the copy of this leaf was issued one iteration ago
       mbar_wait(&s_bar, parity);
       parity ^= 1u;
-      const KeyT* src = st_keys + (lo & (kKeysPer16 - 1)) + threadIdx.x;
+      const RecT* src = st_keys + (lo & (kKeysPer16 - 1)) + threadIdx.x;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         if (e >= ne) break;
@@ -758,19 +793,15 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict
         unsigned long long basepos = 0;
         if (lane == 0) basepos = atomicAdd(n_cand, (unsigned long long)__popc(m));
         basepos = __shfl_sync(0xffffffffu, basepos, 0);
-        if (ok) {
-          unsigned long long dst = basepos + __popc(m & lanemask_lt());
-          cand_keys[dst] = keys[lo + i];
-          cand_vals[dst] = vals[lo + i];
-        }
+        if (ok) emit(basepos + __popc(m & lanemask_lt()), keys[lo + i], PACKED ? 0u : vals[lo + i]);
       }
       continue;
     }
     {  // clear the exact table, both maps and the marks (contiguous, 16-byte aligned) with 128-bit stores
-      constexpr int kClear16 = (int)((sizeof(KeyT) * kSuspectSlots + 8 * kBloomWords + kSuspectSlots) / 16);
+      constexpr int kClear16 = (int)((sizeof(RecT) * kSuspectSlots + 8 * kBloomWords + kSuspectSlots) / 16);
       uint4* z = reinterpret_cast<uint4*>(smem_raw);
       const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zeros = make_uint4(0u, 0u, 0u, 0u);
-      constexpr int kTable16 = (int)(sizeof(KeyT) * kSuspectSlots / 16);
+      constexpr int kTable16 = (int)(sizeof(RecT) * kSuspectSlots / 16);
 #pragma unroll
       for (int i = threadIdx.x; i < kClear16; i += T) z[i] = i < kTable16 ? ones : zeros;
     }
@@ -781,7 +812,7 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       if (e >= ne) break;
-      bits[e] = (uint32_t)(key_hash((uint64_t)key[e]) >> bit_shift) & kBitMask;
+      bits[e] = (uint32_t)(key_hash(canon_of(key[e])) >> bit_shift) & kBitMask;
       const uint32_t w = bits[e] >> 5, m = 1u << (bits[e] & 31u);
       if (atomicOr(&map_a[w], m) & m) atomicOr(&map_b[w], m);
     }
@@ -808,7 +839,7 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         if ((smask >> e) & 1u) {
-          if (pos < (uint32_t)kLeafSortCap) { c_keys[pos] = key[e]; c_vals[pos] = my_vals[threadIdx.x + e * T]; }
+          if (pos < (uint32_t)kLeafSortCap) { c_keys[pos] = key[e]; if (!PACKED) c_vals[pos] = my_vals[threadIdx.x + e * T]; }
           ++pos;
         }
       }
@@ -827,26 +858,24 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict
           unsigned long long basepos = 0;
           if (lane == 0) basepos = atomicAdd(n_cand, (unsigned long long)__popc(m));
           basepos = __shfl_sync(0xffffffffu, basepos, 0);
-          if (sus) {
-            unsigned long long dst = basepos + __popc(m & lanemask_lt());
-            cand_keys[dst] = key[e];
-            cand_vals[dst] = my_vals[threadIdx.x + e * T];
-          }
+          if (sus) emit(basepos + __popc(m & lanemask_lt()), key[e], PACKED ? 0u : my_vals[threadIdx.x + e * T]);
         }
       }
       continue;
     }
     // stage 2: exact test on the suspects (thread t owns suspect t)
     uint32_t slot = 0xffffffffu;
-    KeyT mk = kEmpty;
+    RecT mk = kEmpty;
     uint32_t mv = 0;
     if (threadIdx.x < c1) {
-      mk = c_keys[threadIdx.x]; mv = c_vals[threadIdx.x];
-      uint32_t h = (uint32_t)(key_hash((uint64_t)mk) >> slot_shift) & (kSuspectSlots - 1);
+      mk = c_keys[threadIdx.x];
+      if (!PACKED) mv = c_vals[threadIdx.x];
+      const RecT canon = (RecT)canon_of(mk);
+      uint32_t h = (uint32_t)(key_hash((uint64_t)canon) >> slot_shift) & (kSuspectSlots - 1);
       for (;;) {
-        KeyT old = atomic_cas(&table[h], kEmpty, mk);
+        RecT old = atomic_cas(&table[h], kEmpty, canon);
         if (old == kEmpty) break;
-        if (old == mk) { marked[h] = 1; break; }
+        if (old == canon) { marked[h] = 1; break; }
         h = (h + 1u) & (kSuspectSlots - 1);
       }
       slot = h;
@@ -856,21 +885,26 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict
     if (threadIdx.x < c1 && marked[slot] != 0) {
       const uint32_t pos = atomicAdd(&s_c2, 1u);
       c_keys[pos] = mk;
-      c_vals[pos] = mv;
+      if (!PACKED) c_vals[pos] = mv;
     }
     __syncthreads();
     const uint32_t c2 = s_c2;
     if (c2 == 0) continue;
-    {  // order them: rank by counting, a power-of-two group of threads per record (2^lg * c2 <= T)
+    {  // order them by (key, part, window): rank by counting, a power-of-two group of threads per record (2^lg * c2 <= T)
       const int lg = 31 - __clz((uint32_t)T / c2);
       const uint32_t cand = threadIdx.x >> lg, seg = threadIdx.x & ((1u << lg) - 1u);
       if (cand < c2) {
-        const KeyT ck = c_keys[cand];
-        const uint32_t cv = c_vals[cand];
+        const RecT ck = c_keys[cand];
+        const uint32_t cv = PACKED ? 0u : c_vals[cand];
         uint32_t partial = 0;
         for (uint32_t j = seg; j < c2; j += (1u << lg)) {
-          KeyT ok = c_keys[j]; uint32_t ov = c_vals[j];
-          partial += (ok < ck || (ok == ck && (ov < cv || (ov == cv && j < cand)))) ? 1u : 0u;
+          const RecT ok = c_keys[j];
+          if constexpr (PACKED) {                     // the packed word orders by (key, value) as it is
+            partial += (ok < ck || (ok == ck && j < cand)) ? 1u : 0u;
+          } else {
+            const uint32_t ov = c_vals[j];
+            partial += (ok < ck || (ok == ck && (ov < cv || (ov == cv && j < cand)))) ? 1u : 0u;
+          }
         }
         if (partial) atomicAdd(&c_rank[cand], partial);
       }
@@ -879,8 +913,7 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const KeyT* __restrict
     __syncthreads();
     if (threadIdx.x < c2) {
       const uint32_t rank = c_rank[threadIdx.x];
-      cand_keys[s_cbase + rank] = c_keys[threadIdx.x];
-      cand_vals[s_cbase + rank] = c_vals[threadIdx.x];
+      emit(s_cbase + rank, c_keys[threadIdx.x], PACKED ? 0u : c_vals[threadIdx.x]);
       c_rank[threadIdx.x] = 0;
     }
   }

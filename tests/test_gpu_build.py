@@ -136,13 +136,28 @@ def test_direct_and_exact_paths_agree(ctx):
         try:
             res = _run(ctx, uniq, k, internal)
             assert res.counts['direct'] == 1 and res.counts['fallbacks'] == 0
+            # one 64-bit word per record whenever 2k + value bits (13 part bits + 7 window bits here) <= 64
+            assert res.counts['packed'] == (1 if 2 * k + 20 <= 64 else 0)
             _compare(res, uniq, k, internal)
+            ctx.set_option('packed', 0)               # (key, value) arrays on the direct path
+            res = _run(ctx, uniq, k, internal)
+            assert res.counts['direct'] == 1 and res.counts['packed'] == 0
+            _compare(res, uniq, k, internal)
+            ctx.set_option('packed', -1)
             ctx.set_option('direct', 0)
             res = _run(ctx, uniq, k, internal)
             assert res.counts['direct'] == 0
             _compare(res, uniq, k, internal)
         finally:
             ctx.set_option('direct', -1)
+            ctx.set_option('packed', -1)
+
+
+def test_unpacked_when_key_and_value_exceed_64_bits(ctx):
+    uniq = _long_parts(cases.planted_parts(800, 11) + cases.random_parts(2000, 100, 6), 32)
+    res = _run(ctx, uniq, 32, False)
+    assert res.counts['direct'] == 1 and res.counts['packed'] == 0
+    _compare(res, uniq, 32, False)
 
 
 def test_direct_overflow_falls_back_to_exact(ctx):
