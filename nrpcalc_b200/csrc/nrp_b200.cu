@@ -143,6 +143,7 @@ struct nrp_ctx {
   int64_t opt_pass_records = 210000000;   // exact path: more records than this per device are processed in several hash-slice passes
   int64_t opt_persistent_split = 0;       // extraction kernel: persistent CTAs with register prefetch (1) or one CTA per byte tile (0)
   int64_t opt_r1_bias = 0;                // added to the number of level-1 bits (tuning)
+  int64_t opt_nvlink_digits = 256;        // direct exchange: most (owner, bucket) digits per tile the senders scatter over NVLink
   int64_t opt_packed = 1;                 // one 64-bit word per record on the direct path whenever key and value fit
   int64_t opt_direct = 1;                 // fixed-region partition without a histogram pass (falls back to the exact path on overflow)
 
@@ -358,6 +359,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "pass_records") c->opt_pass_records = value <= 0 ? 210000000 : value;
   else if (n == "persistent_split") c->opt_persistent_split = value > 0 ? 1 : 0;
   else if (n == "r1_bias") c->opt_r1_bias = value;
+  else if (n == "nvlink_digits") c->opt_nvlink_digits = value <= 0 ? 256 : value;
   else if (n == "packed") c->opt_packed = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "direct") c->opt_direct = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
@@ -471,7 +473,7 @@ int ensure_record_buffers(nrp_ctx* c, int64_t n_records, size_t key_bytes, int64
   TRY(c->keysB.ensure(key_bytes * rec)); TRY(c->valsB.ensure(4 * rec));
   const size_t leaf_max = (size_t)1 << kMaxDirectBits;
   TRY(c->hist.ensure(4 * (((size_t)1 << kMaxLeafBits) + 2))); TRY(c->leaf_off.ensure(4 * (((size_t)1 << kMaxLeafBits) + 2)));
-  TRY(c->cursor1.ensure(4 * (size_t)(kLevelBuckets * kMaxPeers + 4))); TRY(c->cursor2.ensure(4 * (leaf_max + 2)));
+  TRY(c->cursor1.ensure(4 * (leaf_max + 2))); TRY(c->cursor2.ensure(4 * (leaf_max + 2)));
   TRY(c->region_ends.ensure(4 * (size_t)(kLevelBuckets * kMaxPeers + 4)));
   const size_t segs = (size_t)std::max<int64_t>(n_segments, kLevelBuckets * kMaxPeers) + 4;
   TRY(c->seg_off.ensure(4 * segs)); TRY(c->tile_prefix.ensure(4 * segs));
@@ -531,23 +533,49 @@ inline uint32_t region_cap(double mean, int slack) {
   return (uint32_t)(((int64_t)v + 4) & ~3ll);
 }
 
-// Leaf bits and their division into two levels for m records.  fixed_r1 >= 0: the first level is given (pre-partitioned).
-LevelPlan plan_levels(const nrp_ctx* c, int64_t m, bool direct, int fixed_r1 = -1) {
-  const int lv = (int)c->opt_max_level_bits;
-  int max_bits = std::min(direct ? kMaxDirectBits : kMaxLeafBits, fixed_r1 >= 0 ? fixed_r1 + lv : 2 * lv);
-  int bits = fixed_r1 >= 0 ? fixed_r1 + 1 : 1;            // a pre-partitioned input always takes one more level (it merges the senders' regions)
+// number of leaf bits for m records when at most max_bits are available (and at least min_bits must be used)
+int leaf_bits_for(const nrp_ctx* c, int64_t m, int min_bits, int max_bits) {
+  int bits = std::max(min_bits, 1);
   while (bits < max_bits && (m >> bits) > c->opt_leaf_target) ++bits;
   // the small-leaf target is out of reach: take the fewest bits that still fit the large filter variant
   if (c->opt_leaf_target == kDefaultLeafTarget && (m >> bits) > kDefaultLeafTarget)
-    while (bits > (fixed_r1 >= 0 ? fixed_r1 + 1 : 1) && (m >> (bits - 1)) <= kLargeLeafTarget) --bits;
+    while (bits > std::max(min_bits, 1) && (m >> (bits - 1)) <= kLargeLeafTarget) --bits;
+  return bits;
+}
+
+// Exact path: leaf bits (<= 15, the shared-memory histogram) and their division into two levels.
+LevelPlan plan_levels(const nrp_ctx* c, int64_t m, bool /*direct*/, int /*fixed_r1*/ = -1) {
+  const int lv = (int)c->opt_max_level_bits;
+  const int bits = leaf_bits_for(c, m, 1, std::min(kMaxLeafBits, 2 * lv));
   LevelPlan p;
   p.bits = bits;
-  if (fixed_r1 >= 0) p.r1 = fixed_r1;
-  else p.r1 = bits <= std::min(lv, 8) ? bits : std::max(1, std::min(std::min(lv, bits - 1), (bits + 1) / 2 + (int)c->opt_r1_bias));
-  if (fixed_r1 < 0 && bits - p.r1 > lv) p.r1 = bits - lv;
+  p.r1 = bits <= std::min(lv, 8) ? bits : std::max(1, std::min(std::min(lv, bits - 1), (bits + 1) / 2 + (int)c->opt_r1_bias));
+  if (bits - p.r1 > lv) p.r1 = bits - lv;
   p.r2 = bits - p.r1;
-  p.cap1 = region_cap((double)m / (double)(1ll << p.r1), 1024);
-  p.cap2 = region_cap((double)m / (double)(1ll << bits), 64);
+  p.cap1 = p.cap2 = 0;
+  return p;
+}
+
+// Direct path: `pre` hash bits are already consumed by a pre-partitioned source (0 otherwise); the remaining leaf bits are
+// split over one or two levels of at most opt_max_level_bits (<= 9) bits.  cum[i] = bits consumed after level i.
+struct DirectPlan { int bits, pre, n_levels; int r[2]; int cum[2]; uint32_t cap[2]; };
+DirectPlan plan_direct(const nrp_ctx* c, int64_t m, int pre, bool must_split) {
+  const int lv = (int)c->opt_max_level_bits;
+  DirectPlan p;
+  p.pre = pre;
+  p.bits = leaf_bits_for(c, m, pre + (must_split ? 1 : 0), std::min(kMaxDirectBits, pre + 2 * lv));
+  const int rest = p.bits - pre;
+  if (rest <= std::min(lv, 8) || (pre > 0 && rest <= lv)) {
+    p.n_levels = 1; p.r[0] = rest; p.r[1] = 0;
+  } else {
+    p.n_levels = 2;
+    p.r[0] = std::max(1, std::min(std::min(lv, rest - 1), (rest + 1) / 2 + (int)c->opt_r1_bias));
+    if (rest - p.r[0] > lv) p.r[0] = rest - lv;
+    p.r[1] = rest - p.r[0];
+  }
+  p.cum[0] = pre + p.r[0]; p.cum[1] = p.cum[0] + p.r[1];
+  for (int i = 0; i < 2; ++i)
+    p.cap[i] = region_cap((double)m / (double)(1ll << p.cum[i]), i + 1 == p.n_levels ? 64 : 1024);
   return p;
 }
 
@@ -601,6 +629,8 @@ int build_tiles(nrp_ctx* c, SegExtents ext, uint32_t n_seg, uint32_t segs_per_bu
 }
 
 // Direct path: fixed regions, no histogram.  *overflowed is set when a region was too small (nothing usable was produced).
+// One or two split levels; the first reads the staged parts (extraction fused in), a flat record list, or the (bucket, sender)
+// regions of a pre-partitioned source; every level scatters into the fixed regions of the next buffer.
 template <typename KeyT>
 int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer& tm, bool* overflowed) {
   cudaStream_t st = c->stream;
@@ -610,76 +640,74 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
   const Parts P = parts_view(c);
   unsigned long long* cnt = c->counters.as<unsigned long long>();
   uint32_t* overflow = reinterpret_cast<uint32_t*>(cnt + CNT_OVERFLOW);
-  const LevelPlan lp = plan_levels(c, m_max, true, prepart ? src.r_done : -1);
-  const int bits = lp.bits, r1 = lp.r1, r2 = lp.r2;
-  const uint32_t n_leaf = 1u << bits, n_l1 = 1u << r1;
+  const DirectPlan dp = plan_direct(c, m_max, prepart ? src.r_done : 0, prepart);
+  const int bits = dp.bits;
+  const uint32_t n_leaf = 1u << bits;
   *overflowed = false;
-  const int64_t total1 = (r2 > 0 && !prepart) ? (int64_t)n_l1 * lp.cap1 : 0, total2 = (int64_t)n_leaf * lp.cap2;
-  if (std::max(total1, total2) >= 0xffffe000ll || r2 > (int)c->opt_max_level_bits) { *overflowed = true; return NRP_OK; }   // beyond 32-bit record indices: exact path
+  int64_t total_max = 0;
+  for (int i = 0; i < dp.n_levels; ++i) total_max = std::max(total_max, ((int64_t)1 << dp.cum[i]) * dp.cap[i]);
+  if (total_max >= 0xffffe000ll) { *overflowed = true; return NRP_OK; }   // beyond 32-bit record indices: exact path
   c->counts[NRP_C_BUCKETS] = (int64_t)n_leaf;
   // records as single 64-bit words when key and value fit (a packed source dictates it)
   const bool packed = from_ascii ? c->packed : src.packed;
-  TRY(ensure_record_buffers(c, std::max<int64_t>(std::max(total1, total2), m_max), packed ? 8 : sizeof(KeyT), (int64_t)n_l1 * src.segs_per_bucket));
+  const int64_t n_seg_max = std::max<int64_t>((int64_t)src.n_seg, dp.n_levels > 1 ? ((int64_t)1 << dp.cum[0]) : 0);
+  TRY(ensure_record_buffers(c, std::max<int64_t>(total_max, m_max), packed ? 8 : sizeof(KeyT), n_seg_max));
   CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * CNT_N, st));
   c->n_records = 0;
 
-  tm.begin(NRP_T_SPLIT1);
-  // level-1 output: buffer A (regions of cap1, or the leaves themselves when there is one level)
-  void* l1_keys = c->keysA.ptr; uint32_t* l1_vals = c->valsA.as<uint32_t>();
-  void* l2_keys = c->keysB.ptr; uint32_t* l2_vals = c->valsB.as<uint32_t>();
-  NRP_LAUNCH((k_init_region_cursors<<<grid_for(n_leaf, 256), 256, 0, st>>>(c->cursor2.as<uint32_t>(), n_leaf, lp.cap2)));
-  if (r2 > 0 && !prepart)
-    NRP_LAUNCH((k_init_region_cursors<<<grid_for(n_l1, 256), 256, 0, st>>>(c->cursor1.as<uint32_t>(), n_l1, lp.cap1)));
-  uint32_t* level1_cursor = r2 > 0 ? c->cursor1.as<uint32_t>() : c->cursor2.as<uint32_t>();
-  const RegionLimit lim1{r2 > 0 ? lp.cap1 : lp.cap2, 0u, overflow, nullptr};
-  const RegionLimit lim2{lp.cap2, 0u, overflow, nullptr};
-  if (m_max > 0 && !prepart) {
-    if (from_ascii) {
+  void* buf_keys[2] = {c->keysA.ptr, c->keysB.ptr};
+  uint32_t* buf_vals[2] = {c->valsA.as<uint32_t>(), c->valsB.as<uint32_t>()};
+  // the records a level reads: the source first, then the regions the previous level filled
+  const void* in_keys = src.keys; const uint32_t* in_vals = src.vals;
+  SegExtents in_ext = src.ext;
+  uint32_t in_seg = src.n_seg, in_spb = prepart ? src.segs_per_bucket : 0xffffffffu;
+  int in_done = dp.pre;
+  bool counted = false;
+  for (int lvl = 0; lvl < dp.n_levels && m_max > 0; ++lvl) {
+    tm.begin(lvl == 0 ? NRP_T_SPLIT1 : NRP_T_SPLIT2);
+    const bool last = lvl + 1 == dp.n_levels;
+    const int r = dp.r[lvl];
+    const uint32_t n_regions = 1u << dp.cum[lvl];
+    uint32_t* cursor = last ? c->cursor2.as<uint32_t>() : c->cursor1.as<uint32_t>();
+    NRP_LAUNCH((k_init_region_cursors<<<grid_for(n_regions, 256), 256, 0, st>>>(cursor, n_regions, dp.cap[lvl])));
+    const RegionLimit lim{dp.cap[lvl], 0u, overflow, nullptr};
+    void* out_k = buf_keys[lvl & 1]; uint32_t* out_v = buf_vals[lvl & 1];
+    if (lvl == 0 && from_ascii) {
       if (packed)
         NRP_LAUNCH((k_split_from_ascii<uint64_t, 0, false, true><<<split_grid(c), kTileThreads, sizeof(SplitSmem<uint64_t, true>) + sizeof(TileStage), st>>>(
-            P, c->flags.as<uint8_t>(), k, r1, 0, c->shard_tiles, c->part_base, c->j_bits, c->vbits, PassSel{0, 0u, 0u}, level1_cursor,
-            (uint64_t*)l1_keys, l1_vals, lim1, PeerBuffers{}, 0)));
+            P, c->flags.as<uint8_t>(), k, r, 0, c->shard_tiles, c->part_base, c->j_bits, c->vbits, PassSel{0, 0u, 0u}, cursor,
+            (uint64_t*)out_k, out_v, lim, PeerBuffers{}, 0)));
       else
         NRP_LAUNCH((k_split_from_ascii<KeyT, 0, false><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-            P, c->flags.as<uint8_t>(), k, r1, 0, c->shard_tiles, c->part_base, c->j_bits, 0, PassSel{0, 0u, 0u}, level1_cursor,
-            (KeyT*)l1_keys, l1_vals, lim1, PeerBuffers{}, 0)));
+            P, c->flags.as<uint8_t>(), k, r, 0, c->shard_tiles, c->part_base, c->j_bits, 0, PassSel{0, 0u, 0u}, cursor,
+            (KeyT*)out_k, out_v, lim, PeerBuffers{}, 0)));
     } else {
-      TRY(build_tiles(c, src.ext, src.n_seg, 0xffffffffu, 0, nullptr));
-      const unsigned grid = (unsigned)std::min<int64_t>(m_max / kSplitTile + src.n_seg, (int64_t)c->n_sms * 4);
+      // children of segment g: the cursors of bucket (g / in_spb), i.e. region index << r (a flat list has one bucket)
+      TRY(build_tiles(c, in_ext, in_seg, in_spb, in_spb == 0xffffffffu ? 0 : r, cnt + CNT_RECORDS));
+      counted = true;
+      const unsigned grid = (unsigned)std::min<int64_t>(m_max / kSplitTile + in_seg, (int64_t)c->n_sms * 4);
       if (packed)
         NRP_LAUNCH((k_split_from_records<uint64_t, false, true><<<grid, kSplitThreads, sizeof(SplitSmem<uint64_t, true>), st>>>(
-            (const uint64_t*)src.keys, src.vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + src.n_seg, 0, r1, c->vbits,
-            PassSel{0, 0u, 0u}, level1_cursor, (uint64_t*)l1_keys, l1_vals, lim1)));
+            (const uint64_t*)in_keys, in_vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + in_seg, in_done, r, c->vbits,
+            PassSel{0, 0u, 0u}, cursor, (uint64_t*)out_k, out_v, lim)));
       else
         NRP_LAUNCH((k_split_from_records<KeyT, false><<<grid, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
-            (const KeyT*)src.keys, src.vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + src.n_seg, 0, r1, 0, PassSel{0, 0u, 0u},
-            level1_cursor, (KeyT*)l1_keys, l1_vals, lim1)));
+            (const KeyT*)in_keys, in_vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + in_seg, in_done, r, 0, PassSel{0, 0u, 0u},
+            cursor, (KeyT*)out_k, out_v, lim)));
     }
+    in_keys = out_k; in_vals = out_v;
+    in_ext = SegExtents{nullptr, 0, cursor, dp.cap[lvl]};
+    in_seg = n_regions; in_spb = 1u; in_done = dp.cum[lvl];
   }
-  const void* leaf_keys = l1_keys; const uint32_t* leaf_vals = l1_vals;
-  void* out_keys = l2_keys; uint32_t* out_vals = l2_vals;
-  if (r2 > 0 && m_max > 0) {
-    tm.begin(NRP_T_SPLIT2);
-    const void* in_k = prepart ? src.keys : l1_keys; const uint32_t* in_v = prepart ? src.vals : l1_vals;
-    const SegExtents ext = prepart ? src.ext : SegExtents{nullptr, 0, c->cursor1.as<uint32_t>(), lp.cap1};
-    const uint32_t n_seg = prepart ? src.n_seg : n_l1;
-    TRY(build_tiles(c, ext, n_seg, prepart ? src.segs_per_bucket : 1u, r2, cnt + CNT_RECORDS));
-    const unsigned grid2 = (unsigned)std::min<int64_t>(m_max / kSplitTile + n_seg, (int64_t)c->n_sms * 4);
-    if (packed)
-      NRP_LAUNCH((k_split_from_records<uint64_t, false, true><<<grid2, kSplitThreads, sizeof(SplitSmem<uint64_t, true>), st>>>(
-          (const uint64_t*)in_k, in_v, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + n_seg, r1, r2, c->vbits, PassSel{0, 0u, 0u},
-          c->cursor2.as<uint32_t>(), (uint64_t*)l2_keys, l2_vals, lim2)));
-    else
-      NRP_LAUNCH((k_split_from_records<KeyT, false><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
-          (const KeyT*)in_k, in_v, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + n_seg, r1, r2, 0, PassSel{0, 0u, 0u},
-          c->cursor2.as<uint32_t>(), (KeyT*)l2_keys, l2_vals, lim2)));
-    leaf_keys = l2_keys; leaf_vals = l2_vals;
-    out_keys = l1_keys; out_vals = l1_vals;                  // level-1 regions are consumed: candidates go there
-  }
+  // leaves: the last level's output; candidates go to the other buffer (free, or consumed by the last level)
+  const int leaf_buf = (dp.n_levels - 1) & 1;
+  const void* leaf_keys = buf_keys[leaf_buf]; const uint32_t* leaf_vals = buf_vals[leaf_buf];
+  void* out_keys = buf_keys[leaf_buf ^ 1]; uint32_t* out_vals = buf_vals[leaf_buf ^ 1];
+  const uint32_t leaf_cap = dp.cap[dp.n_levels - 1];
   tm.begin(NRP_T_FILTER);
   if (m_max > 0) {
-    if (r2 == 0) NRP_LAUNCH((k_region_total<<<1, 1024, 0, st>>>(c->cursor2.as<uint32_t>(), n_leaf, lp.cap2, cnt + CNT_RECORDS)));
-    TRY((launch_filter<KeyT>(c, packed, leaf_keys, leaf_vals, LeafExtents{nullptr, c->cursor2.as<uint32_t>(), lp.cap2}, n_leaf, bits, m_max >> bits,
+    if (!counted) NRP_LAUNCH((k_region_total<<<1, 1024, 0, st>>>(c->cursor2.as<uint32_t>(), n_leaf, leaf_cap, cnt + CNT_RECORDS)));
+    TRY((launch_filter<KeyT>(c, packed, leaf_keys, leaf_vals, LeafExtents{nullptr, c->cursor2.as<uint32_t>(), leaf_cap}, n_leaf, bits, m_max >> bits,
                              (KeyT*)out_keys, out_vals)));
   }
   CU(cudaGetLastError());
@@ -1274,12 +1302,16 @@ __global__ void k_push_region_ends(const uint32_t* cursor, uint32_t n_digits, in
 // level-1 bits of the direct sharded path: world * 2^r1 digits must fit one split level
 int direct_shard_plan(nrp_ctx* c, int64_t windows_total, int world, int* r1_out, uint32_t* cap1s_out, int64_t* m_owner_out) {
   const int64_t m_owner = windows_total / world + (windows_total / world) / 32 + 4096;
-  int max_r1 = 0;
-  while ((world << (max_r1 + 1)) <= kLevelBuckets) ++max_r1;
-  // as few level-1 bits as the owner's second level allows: the fewer digits, the longer the runs stored over NVLink
-  const LevelPlan p = plan_levels(c, m_owner, true);
-  int r1 = std::min(std::max(p.bits - (int)c->opt_max_level_bits, 0), max_r1);
-  if ((world << r1) > kLevelBuckets) return fail(NRP_E_UNSUPPORTED, "%d owners do not fit one split level", world);
+  // Runs stored over NVLink must stay long: at most opt_nvlink_digits (owner, bucket) digits per 4096-record tile.  If the
+  // owner can finish with ONE more level of <= 9 bits the senders pre-partition by the missing bits; otherwise they scatter
+  // by owner only (or by the few bits two owner levels cannot cover) and the owner runs two levels from the received regions.
+  const int lv = (int)c->opt_max_level_bits;
+  const int need = leaf_bits_for(c, m_owner, 1, kMaxDirectBits);
+  int r1_eff = 0;
+  while (((int64_t)world << (r1_eff + 1)) <= c->opt_nvlink_digits) ++r1_eff;
+  int r1 = need - lv <= r1_eff ? std::max(need - lv, 0) : std::max(need - 2 * lv, 0);
+  while (r1 > 0 && (world << r1) > kLevelBuckets) --r1;
+  if (world > kLevelBuckets) return fail(NRP_E_UNSUPPORTED, "%d owners do not fit one split level", world);
   *r1_out = r1;
   *cap1s_out = region_cap((double)windows_total / ((double)world * world * (double)(1 << r1)), 256);
   *m_owner_out = m_owner;

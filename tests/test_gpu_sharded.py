@@ -20,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n_parts, k, internal, out_dir, mode='direct'):
+def _worker(rank, world, port, n_parts, k, internal, out_dir, mode='direct', opts=None, dups=0):
     import sys
     # exchange flavour: direct (fixed regions, no count pass), counted (count pass + peer stores), nccl (all-to-all)
     os.environ['NRPCALC_B200_DIRECT'] = '1' if mode == 'direct' else '0'
@@ -38,6 +38,9 @@ def _worker(rank, world, port, n_parts, k, internal, out_dir, mode='direct'):
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     try:
         parts = cases.planted_parts(n_parts, 1234) + cases.random_parts(n_parts, 100, 9)
+        if dups:        # one 30-mer shared by many parts: fixed regions overflow, the exchange falls back to the counted path
+            common = cases.random_parts(1, 30, 77)[0]
+            parts = [common + p if i % 4 == 0 and i < 4 * dups else p for i, p in enumerate(parts)]
         uniq = [(pid, seq) for pid, seq in ref_port.uniquify(list(parts)) if len(seq) >= k]
         seqs = [s for _, s in uniq]
         ids = np.array([pid for pid, _ in uniq], dtype=np.uint32)
@@ -45,6 +48,8 @@ def _worker(rank, world, port, n_parts, k, internal, out_dir, mode='direct'):
         np.cumsum([len(s) for s in seqs], out=offsets[1:])
         buf = np.frombuffer(''.join(seqs).encode(), dtype=np.uint8)
         ctx = _native.Context(rank)
+        for name, value in (opts or {}).items():
+            ctx.set_option(name, value)
         ops = sharded.NativeOps(ctx)
         ops.load(buf, offsets, ids)
         res = sharded.build_sharded(ops, offsets, k, internal, want_edges=True)
@@ -68,14 +73,20 @@ def _groups(res):
                   for g in range(len(res['indptr']) - 1))
 
 
-@pytest.mark.parametrize('k,internal,mode', [(13, False, 'direct'), (17, False, 'direct'), (16, True, 'direct'), (16, False, 'direct'),
-                                             (13, False, 'counted'), (17, True, 'counted'), (17, False, 'nccl')])
-def test_sharded_equals_single_gpu(tmp_path, k, internal, mode):
+@pytest.mark.parametrize('k,internal,mode,opts,dups', [
+    (13, False, 'direct', None, 0), (17, False, 'direct', None, 0), (16, True, 'direct', None, 0), (16, False, 'direct', None, 0),
+    (32, False, 'direct', None, 0),                                             # key + value exceed 64 bits: (key, value) arrays
+    (13, False, 'direct', {'leaf_target': 20}, 0),                              # senders pre-partition by 5 bits, one owner level
+    (17, False, 'direct', {'leaf_target': 20, 'nvlink_digits': 2}, 0),          # scatter by owner only, two owner levels
+    (17, True, 'direct', {'leaf_target': 20, 'nvlink_digits': 2, 'packed': 0}, 0),
+    (13, True, 'direct', None, 300),                                            # region overflow -> counted exchange
+    (13, False, 'counted', None, 0), (17, True, 'counted', None, 0), (17, False, 'nccl', None, 0)])
+def test_sharded_equals_single_gpu(tmp_path, k, internal, mode, opts, dups):
     world = min(_n_gpus(), 4)
     if world < 2:
         pytest.skip('needs at least 2 GPUs')
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(world, _free_port(), 3000, k, internal, str(tmp_path), mode), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), 3000, k, internal, str(tmp_path), mode, opts, dups), nprocs=world, join=True)
     single = np.load(str(tmp_path / 'single.npz'))
     for rank in range(world):
         res = np.load(str(tmp_path / ('rank%d.npz' % rank)))
