@@ -115,8 +115,10 @@ def background_keys(cfg):
     return np.unique(encoding.canonical_kmers(buf, off, K)), K
 
 
-def algorithmic_bytes(total_len, m, key_bytes):
-    rec = key_bytes + 4
+def algorithmic_bytes(total_len, m, key_bytes, packed):
+    """Bytes each bulk kernel has to move per launch: a record is one 8-byte word when the k-mer and
+    the value fit 64 bits (packed), else key + 4-byte value."""
+    rec = 8 if packed else key_bytes + 4
     return {'histogram': total_len, 'split1': total_len + m * rec, 'split2': 2 * m * rec, 'filter': m * rec,
             'flags': total_len}
 
@@ -273,10 +275,10 @@ def main():
 
     # ---- roofline of the dominant kernel
     peak, peak_src = measured_peak_gbs()
-    algo = algorithmic_bytes(int(off[-1]), m, counts['key_bytes'])
+    algo = algorithmic_bytes(int(off[-1]), m, counts['key_bytes'], counts['packed'])
     stage_avg = {name: stage_ms.get(name, 0.0) / args.steps for name in algo}
     dominant = max(stage_avg, key=lambda name: stage_avg[name])
-    kernel_of = {'histogram': 'k_hist_from_ascii', 'split1': 'k_split_from_ascii', 'split2': 'k_split_from_records', 'filter': 'k_filter',
+    kernel_of = {'histogram': 'k_hist_from_ascii', 'split1': 'k_split_from_ascii', 'split2': 'k_split_from_records', 'filter': 'k_filter_bloom',
                  'flags': 'k_flag_windows'}
     achieved = algo[dominant] / (stage_avg[dominant] * 1e-3) / 1e9
     traffic = None
@@ -302,8 +304,9 @@ def main():
             'dtype': 'u64' if counts['key_bytes'] == 8 else 'u32', 'data': 'synthetic',
             'config': {'workload': cfg['label'], 'n_parts': cfg['n'], 'part_len': cfg['length'], 'Lmax': cfg['Lmax'], 'k': k,
                        'internal_repeats': cfg['internal_repeats'], 'background_kmers': 0 if bg_keys is None else int(bg_keys.size),
-                       'kmers': m, 'edges': want_edges, 'l2': 'explicit 256 MiB flush between steps; per-step working set {:.2f} GB'.format(
-                           2 * m * (counts['key_bytes'] + 4) / 1e9)},
+                       'kmers': m, 'edges': want_edges, 'record_bytes': 8 if counts['packed'] else counts['key_bytes'] + 4,
+                       'l2': 'explicit 256 MiB flush between steps; per-step working set {:.2f} GB'.format(
+                           2 * m * (8 if counts['packed'] else counts['key_bytes'] + 4) / 1e9)},
             'parts_per_s': cfg['n'] / (ms_per_step * 1e-3),
             'e2e': {'value': e2e_value, 'unit': 'k-mers/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'ms_per_step': 1e3 * sum(e2e_times) / len(e2e_times),
@@ -312,7 +315,7 @@ def main():
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
             'stage_ms': {name: v / args.steps for name, v in stage_ms.items()},
             'result': {name: counts[name] for name in ('records', 'excluded', 'groups', 'members', 'edges', 'candidates', 'runs', 'buckets', 'oversized',
-                                                       'direct', 'fallbacks')},
+                                                       'direct', 'fallbacks', 'packed')},
             'wall_s_timed_region': wall}
     if not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline(cfg, buf, off, k)
