@@ -190,15 +190,19 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    cfg_name = args.config or 'c2'
-    cfg = CONFIGS[cfg_name]
+    multi = args.gpus > 1 or world > 1
+    # N = 1: BASELINE config 2 (the configuration the metric is quoted on).  N > 1: BASELINE config 4, the 10M-part batch
+    # the reference plan shards across 2/4/8 GPUs (strong scaling); --config c2w = one config-2 batch per GPU (weak scaling)
+    cfg_name = args.config or ('c4' if multi else 'c2')
+    args.weak = cfg_name == 'c2w'
+    cfg = CONFIGS['c2' if args.weak else cfg_name]
 
     if args.impl == 'reference':
         if rank == 0:
             run_reference_arm(args, cfg)
         return
 
-    if args.gpus > 1 or world > 1:
+    if multi:
         import bench_sharded
         bench_sharded.main(args, cfg, rank, world, local_rank)
         return

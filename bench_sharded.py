@@ -18,8 +18,9 @@ def main(args, cfg, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     k = cfg['Lmax'] + 1
-    # default sweep: BASELINE config 2 per GPU (weak scaling, N x 1M parts); --config c4 runs the named 10M-part batch (strong)
-    weak = args.config is None
+    # default: BASELINE config 4, the named 10M-part batch sharded across the GPUs (strong scaling);
+    # --config c2w: one BASELINE config 2 batch per GPU (weak scaling, N x 1M parts)
+    weak = bool(getattr(args, 'weak', False))
     n_parts = cfg['n'] * world if weak else cfg['n']
     buf, off = bench.make_workload(cfg, n_parts)
     ids = np.arange(n_parts, dtype=np.uint32)[::-1].copy()

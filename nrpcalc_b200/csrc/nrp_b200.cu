@@ -120,7 +120,7 @@ template <typename KeyT> constexpr size_t filter_smem_small() {
   return (sizeof(KeyT) + 1) * 2 * (size_t)(kFilterThreads * kFilterItemsSmall) + (kFilterStaged ? (sizeof(KeyT) + 4) * (size_t)kFilterCapSmall : 0);
 }
 constexpr int64_t kDefaultLeafTarget = 2750;                // records per leaf bucket aimed for (two 512-thread filter CTAs per SM, capacity 4096)
-constexpr int64_t kLargeLeafTarget = 6200;                  // when the bits run out: one 1024-thread filter CTA per SM, capacity 8192
+constexpr int64_t kLargeLeafTarget = 6400;                  // when the bits run out: one 1024-thread filter CTA per SM, capacity 8192
 constexpr int kMaxLeafBits = 15;                            // exact path: 2^15 u32 counters = 128 KB of shared memory
 constexpr int kMaxDirectBits = 2 * kMaxLevelBits;           // direct path: two levels of <= 9 bits
 
@@ -143,7 +143,7 @@ struct nrp_ctx {
   int64_t opt_pass_records = 210000000;   // exact path: more records than this per device are processed in several hash-slice passes
   int64_t opt_persistent_split = 0;       // extraction kernel: persistent CTAs with register prefetch (1) or one CTA per byte tile (0)
   int64_t opt_r1_bias = 0;                // added to the number of level-1 bits (tuning)
-  int64_t opt_nvlink_digits = 256;        // direct exchange: most (owner, bucket) digits per tile the senders scatter over NVLink
+  int64_t opt_nvlink_digits = 128;        // direct exchange: most (owner, bucket) digits per tile the senders scatter over NVLink
   int64_t opt_packed = 1;                 // one 64-bit word per record on the direct path whenever key and value fit
   int64_t opt_direct = 1;                 // fixed-region partition without a histogram pass (falls back to the exact path on overflow)
 
@@ -181,7 +181,7 @@ struct nrp_ctx {
   DevBuf recv_keys_d, recv_vals_d, recv_ends;
   PeerBuffers peers_d{};
   uint32_t* peer_ends[kMaxPeers] = {nullptr};
-  int sh_world = 0, sh_r1 = 0, sh_key_bytes = 0, n_peers_d = 0;
+  int sh_world = 0, sh_r1 = 0, sh_bits = 0, sh_key_bytes = 0, n_peers_d = 0;
   bool sh_packed = false;
   uint32_t sh_cap1s = 0;
   int64_t sh_windows_total = 0, sh_m_owner = 0, sh_sent = 0;
@@ -359,7 +359,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "pass_records") c->opt_pass_records = value <= 0 ? 210000000 : value;
   else if (n == "persistent_split") c->opt_persistent_split = value > 0 ? 1 : 0;
   else if (n == "r1_bias") c->opt_r1_bias = value;
-  else if (n == "nvlink_digits") c->opt_nvlink_digits = value <= 0 ? 256 : value;
+  else if (n == "nvlink_digits") c->opt_nvlink_digits = value <= 0 ? 128 : value;
   else if (n == "packed") c->opt_packed = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "direct") c->opt_direct = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
@@ -523,6 +523,7 @@ struct BulkSource {
   int r_done = 0;                      // pre-partitioned input: hash bits already consumed
   int64_t m_upper = 0;                 // hard upper bound of the number of records (buffer sizes)
   int64_t m_plan = 0;                  // expected number of records (level planning); 0 = m_upper
+  int bits_hint = 0;                   // pre-partitioned input: total leaf bits the senders planned for (0 = decide here)
 };
 
 struct LevelPlan { int bits, r1, r2; uint32_t cap1, cap2; };
@@ -559,11 +560,11 @@ LevelPlan plan_levels(const nrp_ctx* c, int64_t m, bool /*direct*/, int /*fixed_
 // Direct path: `pre` hash bits are already consumed by a pre-partitioned source (0 otherwise); the remaining leaf bits are
 // split over one or two levels of at most opt_max_level_bits (<= 9) bits.  cum[i] = bits consumed after level i.
 struct DirectPlan { int bits, pre, n_levels; int r[2]; int cum[2]; uint32_t cap[2]; };
-DirectPlan plan_direct(const nrp_ctx* c, int64_t m, int pre, bool must_split) {
+DirectPlan plan_direct(const nrp_ctx* c, int64_t m, int pre, bool must_split, int bits_hint = 0) {
   const int lv = (int)c->opt_max_level_bits;
   DirectPlan p;
   p.pre = pre;
-  p.bits = leaf_bits_for(c, m, pre + (must_split ? 1 : 0), std::min(kMaxDirectBits, pre + 2 * lv));
+  p.bits = bits_hint > 0 ? bits_hint : leaf_bits_for(c, m, pre + (must_split ? 1 : 0), std::min(kMaxDirectBits, pre + 2 * lv));
   const int rest = p.bits - pre;
   if (rest <= std::min(lv, 8) || (pre > 0 && rest <= lv)) {
     p.n_levels = 1; p.r[0] = rest; p.r[1] = 0;
@@ -640,7 +641,7 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
   const Parts P = parts_view(c);
   unsigned long long* cnt = c->counters.as<unsigned long long>();
   uint32_t* overflow = reinterpret_cast<uint32_t*>(cnt + CNT_OVERFLOW);
-  const DirectPlan dp = plan_direct(c, m_max, prepart ? src.r_done : 0, prepart);
+  const DirectPlan dp = plan_direct(c, m_max, prepart ? src.r_done : 0, prepart, prepart ? src.bits_hint : 0);
   const int bits = dp.bits;
   const uint32_t n_leaf = 1u << bits;
   *overflowed = false;
@@ -1300,19 +1301,27 @@ __global__ void k_push_region_ends(const uint32_t* cursor, uint32_t n_digits, in
 }
 
 // level-1 bits of the direct sharded path: world * 2^r1 digits must fit one split level
-int direct_shard_plan(nrp_ctx* c, int64_t windows_total, int world, int* r1_out, uint32_t* cap1s_out, int64_t* m_owner_out) {
+int direct_shard_plan(nrp_ctx* c, int64_t windows_total, int world, int* r1_out, int* bits_out, uint32_t* cap1s_out, int64_t* m_owner_out) {
   const int64_t m_owner = windows_total / world + (windows_total / world) / 32 + 4096;
   // Runs stored over NVLink must stay long: at most opt_nvlink_digits (owner, bucket) digits per 4096-record tile.  If the
-  // owner can finish with ONE more level of <= 9 bits the senders pre-partition by the missing bits; otherwise they scatter
-  // by owner only (or by the few bits two owner levels cannot cover) and the owner runs two levels from the received regions.
+  // owner can finish with ONE more level of <= 9 bits -- with small leaves, or else with leaves for the large filter variant
+  // -- the senders pre-partition by the missing bits; otherwise they scatter by owner only (or by the few bits two owner
+  // levels cannot cover) and the owner runs two levels from the received regions.
   const int lv = (int)c->opt_max_level_bits;
-  const int need = leaf_bits_for(c, m_owner, 1, kMaxDirectBits);
   int r1_eff = 0;
   while (((int64_t)world << (r1_eff + 1)) <= c->opt_nvlink_digits) ++r1_eff;
-  int r1 = need - lv <= r1_eff ? std::max(need - lv, 0) : std::max(need - 2 * lv, 0);
+  const int need = leaf_bits_for(c, m_owner, 1, kMaxDirectBits);
+  int need_large = need;
+  if (c->opt_leaf_target == kDefaultLeafTarget)
+    while (need_large > 1 && (m_owner >> (need_large - 1)) <= kLargeLeafTarget) --need_large;
+  int r1, bits;
+  if (need - lv <= r1_eff) { bits = need; r1 = std::max(need - lv, 0); }
+  else if (need_large - lv <= r1_eff) { bits = need_large; r1 = std::max(need_large - lv, 0); }
+  else { bits = need; r1 = std::max(need - 2 * lv, 0); }
   while (r1 > 0 && (world << r1) > kLevelBuckets) --r1;
   if (world > kLevelBuckets) return fail(NRP_E_UNSUPPORTED, "%d owners do not fit one split level", world);
   *r1_out = r1;
+  *bits_out = std::max(bits, r1 + 1);
   *cap1s_out = region_cap((double)windows_total / ((double)world * world * (double)(1 << r1)), 256);
   *m_owner_out = m_owner;
   return NRP_OK;
@@ -1380,6 +1389,7 @@ int shard_group_direct_impl(nrp_ctx* c, int k, int internal_repeats) {
   src.r_done = c->sh_r1;
   src.m_upper = (int64_t)src.n_seg * c->sh_cap1s;
   src.m_plan = c->sh_m_owner;
+  src.bits_hint = c->sh_bits;
   TRY((stage_bulk<KeyT>(c, k, src, tm)));
   TRY((stage_sort_mark<KeyT>(c, k, c->n_parts, !internal_repeats, tm)));
   tm.finish(c->timings);
@@ -1590,8 +1600,9 @@ int nrp_peer_export_direct(nrp_ctx* c, int64_t windows_total, int n_owners, int 
   if (n_owners < 1 || n_owners > kMaxPeers || windows_total < 0) return fail(NRP_E_ARG, "bad arguments");
   if (k < 1 || k > 32) return fail(NRP_E_UNSUPPORTED, "k=%d outside [1, 32]", k);
   CU(cudaSetDevice(c->device));
-  int r1 = 0; uint32_t cap1s = 0; int64_t m_owner = 0;
-  TRY(direct_shard_plan(c, windows_total, n_owners, &r1, &cap1s, &m_owner));
+  int r1 = 0, bits = 0; uint32_t cap1s = 0; int64_t m_owner = 0;
+  TRY(direct_shard_plan(c, windows_total, n_owners, &r1, &bits, &cap1s, &m_owner));
+  c->sh_bits = bits;
   const int64_t n_regions = (int64_t)n_owners << r1;
   const int64_t capacity = n_regions * cap1s;
   if (capacity >= 0xffffe000ll) return fail(NRP_E_UNSUPPORTED, "receive regions exceed 32-bit record indices");
