@@ -103,6 +103,14 @@ int nrp_ctx_set_option(nrp_ctx* ctx, const char* name, int64_t value);
 int nrp_bg_set(nrp_ctx* ctx, const uint64_t* canon_kmers, int64_t n, int K);
 int nrp_bg_clear(nrp_ctx* ctx);
 
+/* Background BUILD on the device (replaces the one-put-per-k-mer loop of kmerSetDB.add / multiadd, kmerSetDB.py:129-175, and is
+ * what the persistent store mirrors): the canonical K-mers of every K-window of n_seqs sequences over A/C/G/T (either case;
+ * sequences shorter than K contribute nothing here -- the host layer keeps their whole-string keys), sorted ascending, duplicates
+ * removed.  *n_unique receives the number of distinct keys; nrp_bg_build_fetch copies them to the host.  install != 0 also makes
+ * them this context's probe set (as nrp_bg_set would). */
+int nrp_bg_build(nrp_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t n_seqs, int K, int install, int64_t* n_unique);
+int nrp_bg_build_fetch(nrp_ctx* ctx, uint64_t* keys_out);
+
 /* Stage one batch of parts on the device (H2D copy unless ascii_on_device != 0; offsets and part_id are
  * always host arrays).
  *   ascii, offsets   concatenated parts and their n_parts+1 byte offsets, offsets[0] == 0

@@ -17,10 +17,11 @@ from . import kmerSetDB as _kmerSetDB
 __version__ = '0.1.0'
 
 
-def background(path, Lmax, verbose=True):
+def background(path, Lmax, verbose=True, device=None):
     """kmerSetDB background object storing the canonical (Lmax+1)-mers of the sequences added to it
-    (reference nrpcalc/nrpcalc.py:47-224)."""
-    return _kmerSetDB.kmerSetDB(path=path, homology=Lmax + 1, verbose=verbose)
+    (reference nrpcalc/nrpcalc.py:47-224).  device=True (additive keyword, or NRPCALC_B200_BG_DEVICE=1) builds the key
+    set of add / multiadd on the GPU instead of in the storage layer's host code."""
+    return _kmerSetDB.kmerSetDB(path=path, homology=Lmax + 1, verbose=verbose, device=device)
 
 
 def finder(seq_list, Lmax, internal_repeats=False, background=None, vercov='nrp2', output_file=None, verbose=True):

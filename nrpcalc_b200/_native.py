@@ -57,6 +57,8 @@ def _declare(lib):
         'nrp_ctx_set_option': (c_ctx, ctypes.c_char_p, i64),
         'nrp_bg_set': (c_ctx, ptr, i64, i32),
         'nrp_bg_clear': (c_ctx,),
+        'nrp_bg_build': (c_ctx, ptr, ptr, i64, i32, i32, ctypes.POINTER(i64)),
+        'nrp_bg_build_fetch': (c_ctx, ptr),
         'nrp_load_parts': (c_ctx, ptr, ptr, ptr, i64, i32),
         'nrp_build': (c_ctx, i32, i32, i32),
         'nrp_result_counts': (c_ctx, ptr),
@@ -160,6 +162,16 @@ class Context(object):
             return
         keys = np.ascontiguousarray(canon_kmers, dtype=np.uint64)
         _check(self._lib, self._lib.nrp_bg_set(self._h, _p(keys), keys.size, int(K)))
+
+    def bg_build(self, ascii_buf, offsets, K, install=False):
+        """Distinct canonical K-mers (ascending uint64) of every K-window of the sequences, built on the device."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        ascii_buf = np.ascontiguousarray(ascii_buf, dtype=np.uint8)
+        n = ctypes.c_int64(0)
+        _check(self._lib, self._lib.nrp_bg_build(self._h, _p(ascii_buf), _p(offsets), offsets.size - 1, int(K), 1 if install else 0, ctypes.byref(n)))
+        keys = np.zeros(n.value, dtype=np.uint64)
+        _check(self._lib, self._lib.nrp_bg_build_fetch(self._h, _p(keys)))
+        return keys
 
     def load_parts(self, ascii_buf, offsets, part_id=None, device_ptr=None):
         """ascii_buf: uint8 array (host) or None with device_ptr = address of the bytes in device memory."""

@@ -149,6 +149,9 @@ struct nrp_ctx {
 
   // background
   DevBuf bg_table; int bg_K = 0; int bg_log_slots = 0; int bg_key_bytes = 0; int64_t bg_n = 0;
+  // background build on the device: staged sequences, extracted / sorted / distinct keys
+  DevBuf bgb_ascii, bgb_off, bgb_tile_first, bgb_keysA, bgb_keysB, bgb_head, bgb_head_scan;
+  uint64_t* bgb_result = nullptr; int64_t bgb_n = 0;
 
   // loaded parts
   DevBuf ascii, off, part_id, tile_first;
@@ -329,7 +332,7 @@ int nrp_ctx_destroy(nrp_ctx* c) {
   if (!c) return NRP_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  DevBuf* all[] = {&c->bg_table, &c->ascii, &c->off, &c->part_id, &c->tile_first, &c->flags, &c->hist, &c->leaf_off, &c->cursor1,
+  DevBuf* all[] = {&c->bgb_ascii, &c->bgb_off, &c->bgb_tile_first, &c->bgb_keysA, &c->bgb_keysB, &c->bgb_head, &c->bgb_head_scan, &c->bg_table, &c->ascii, &c->off, &c->part_id, &c->tile_first, &c->flags, &c->hist, &c->leaf_off, &c->cursor1,
                    &c->cursor2, &c->seg_off, &c->tile_prefix, &c->tile_desc, &c->region_ends, &c->recv_ends, &c->recv_keys_d, &c->recv_vals_d, &c->fb_keys, &c->fb_vals, &c->counters, &c->scan_scratch, &c->lsd_scratch, &c->keysA, &c->valsA, &c->cand_keys_buf, &c->cand_vals_buf,
                    &c->keysB, &c->valsB, &c->head, &c->head_scan, &c->group_start, &c->valid, &c->valid_scan, &c->mem_cnt,
                    &c->mem_scan, &c->pair_cnt, &c->pair_scan, &c->g_keys, &c->g_indptr, &c->g_pair_off, &c->g_members,
@@ -372,28 +375,105 @@ int nrp_bg_clear(nrp_ctx* c) {
   return NRP_OK;
 }
 
-int nrp_bg_set(nrp_ctx* c, const uint64_t* canon_kmers, int64_t n, int K) {
-  if (!c) return fail(NRP_E_ARG, "null context");
-  if (n < 0 || (n > 0 && !canon_kmers)) return fail(NRP_E_ARG, "bad background array");
-  if (K < 1 || K > 32) return fail(NRP_E_UNSUPPORTED, "background K=%d outside [1, 32]", K);
-  CU(cudaSetDevice(c->device));
+// probe table (open addressing, >= 2n slots) from n canonical K-mers in device memory
+static int bg_install_device(nrp_ctx* c, const uint64_t* dev_keys, int64_t n, int K) {
   if (n == 0) return nrp_bg_clear(c);
   int log_slots = 6;
   while (((int64_t)1 << log_slots) < 2 * n) ++log_slots;
   const int key_bytes = K <= 16 ? 4 : 8;
   const size_t table_bytes = (size_t)key_bytes << log_slots;
   TRY(c->bg_table.ensure(table_bytes));
+  CU(cudaMemsetAsync(c->bg_table.ptr, 0xff, table_bytes, c->stream));
+  const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, c->n_sms * 8);
+  if (key_bytes == 4) NRP_LAUNCH((k_bg_insert<uint32_t><<<grid, 256, 0, c->stream>>>(dev_keys, n, c->bg_table.as<uint32_t>(), log_slots)));
+  else NRP_LAUNCH((k_bg_insert<uint64_t><<<grid, 256, 0, c->stream>>>(dev_keys, n, c->bg_table.as<uint64_t>(), log_slots)));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  c->bg_n = n; c->bg_K = K; c->bg_log_slots = log_slots; c->bg_key_bytes = key_bytes;
+  return NRP_OK;
+}
+
+int nrp_bg_set(nrp_ctx* c, const uint64_t* canon_kmers, int64_t n, int K) {
+  if (!c) return fail(NRP_E_ARG, "null context");
+  if (n < 0 || (n > 0 && !canon_kmers)) return fail(NRP_E_ARG, "bad background array");
+  if (K < 1 || K > 32) return fail(NRP_E_UNSUPPORTED, "background K=%d outside [1, 32]", K);
+  CU(cudaSetDevice(c->device));
+  if (n == 0) return nrp_bg_clear(c);
   DevBuf staging;
   TRY(staging.ensure(sizeof(uint64_t) * (size_t)n));
   CU(cudaMemcpyAsync(staging.ptr, canon_kmers, sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemsetAsync(c->bg_table.ptr, 0xff, table_bytes, c->stream));
-  const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, c->n_sms * 8);
-  if (key_bytes == 4) NRP_LAUNCH((k_bg_insert<uint32_t><<<grid, 256, 0, c->stream>>>(staging.as<uint64_t>(), n, c->bg_table.as<uint32_t>(), log_slots)));
-  else NRP_LAUNCH((k_bg_insert<uint64_t><<<grid, 256, 0, c->stream>>>(staging.as<uint64_t>(), n, c->bg_table.as<uint64_t>(), log_slots)));
-  CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(c->stream));
+  int r = bg_install_device(c, staging.as<uint64_t>(), n, K);
   staging.release();
-  c->bg_n = n; c->bg_K = K; c->bg_log_slots = log_slots; c->bg_key_bytes = key_bytes;
+  return r;
+}
+
+int nrp_bg_build(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, int64_t n_seqs, int K, int install, int64_t* n_unique) {
+  if (!c || !offsets || !n_unique) return fail(NRP_E_ARG, "null argument");
+  if (K < 1 || K > 32) return fail(NRP_E_UNSUPPORTED, "background K=%d outside [1, 32]", K);
+  if (n_seqs < 0 || offsets[0] != 0 || (n_seqs > 0 && !ascii && offsets[n_seqs] > 0)) return fail(NRP_E_ARG, "bad sequence buffers");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  c->bgb_n = 0; c->bgb_result = nullptr;
+  const int64_t total = offsets[n_seqs];
+  int64_t m = 0;
+  int uniform = n_seqs > 0 ? (int)std::min<int64_t>(offsets[1] - offsets[0], (int64_t)1 << 30) : 0;
+  for (int64_t i = 0; i < n_seqs; ++i) {
+    const int64_t len = offsets[i + 1] - offsets[i];
+    if (len < 0) return fail(NRP_E_ARG, "offsets must be non-decreasing (sequence %lld)", (long long)i);
+    if (len != uniform) uniform = 0;
+    if (len >= K) m += len - K + 1;
+  }
+  if (uniform >= (1 << 30)) uniform = 0;
+  if (m >= 0xffffe000ll) return fail(NRP_E_UNSUPPORTED, "%lld windows exceed the 32-bit index of one device", (long long)m);
+  *n_unique = 0;
+  if (m == 0) { if (install) return nrp_bg_clear(c); return NRP_OK; }
+  const int64_t n_tiles = (total + kTileBytes - 1) / kTileBytes;
+  const size_t padded = (size_t)n_tiles * kTileBytes + 256;
+  TRY(c->bgb_ascii.ensure(padded));
+  TRY(c->bgb_off.ensure(sizeof(int64_t) * (size_t)(n_seqs + 1)));
+  TRY(c->bgb_tile_first.ensure(sizeof(uint32_t) * (size_t)(n_tiles + 2)));
+  TRY(c->bgb_keysA.ensure(8 * (size_t)(m + 16))); TRY(c->bgb_keysB.ensure(8 * (size_t)(m + 16)));
+  TRY(c->bgb_head.ensure(4 * (size_t)(m + 2))); TRY(c->bgb_head_scan.ensure(4 * (size_t)(m + 2)));
+  TRY(c->scan_scratch.ensure(8 * (size_t)scan_scratch_elems(m + 2)));
+  TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(m)));
+  CU(cudaMemsetAsync(c->bgb_ascii.as<uint8_t>() + total, 0, padded - (size_t)total, st));
+  CU(cudaMemcpyAsync(c->bgb_ascii.ptr, ascii, (size_t)total, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c->bgb_off.ptr, offsets, sizeof(int64_t) * (size_t)(n_seqs + 1), cudaMemcpyHostToDevice, st));
+  if (uniform == 0)
+    NRP_LAUNCH((k_tile_first_part<<<grid_for(n_tiles + 1, 256), 256, 0, st>>>(c->bgb_off.as<int64_t>(), n_seqs, total, n_tiles, c->bgb_tile_first.as<uint32_t>())));
+  Parts P;
+  P.ascii = c->bgb_ascii.as<uint8_t>(); P.off = c->bgb_off.as<int64_t>(); P.tile_first = c->bgb_tile_first.as<uint32_t>();
+  P.n_parts = n_seqs; P.total_len = total; P.uniform_len = uniform; P.part_lo = 0; P.part_hi = n_seqs; P.tile_lo = 0;
+  unsigned long long* cnt = c->counters.as<unsigned long long>();
+  CU(cudaMemsetAsync(cnt + CNT_WORK, 0, 8, st));
+  NRP_LAUNCH((k_extract_canon<<<(unsigned)n_tiles, kTileThreads, 0, st>>>(P, K, c->bgb_keysA.as<uint64_t>(), cnt + CNT_WORK)));
+  uint64_t* sorted = nullptr;
+  LsdPlan plan; plan.n_passes = 0;
+  lsd_plan_add(plan, 0, 0, 2 * K);
+  lsd_sort<uint64_t, false>(c->bgb_keysA.as<uint64_t>(), nullptr, c->bgb_keysB.as<uint64_t>(), nullptr, m, plan, c->lsd_scratch.as<uint32_t>(), st,
+                            &sorted, nullptr);
+  uint64_t* spare = sorted == c->bgb_keysA.as<uint64_t>() ? c->bgb_keysB.as<uint64_t>() : c->bgb_keysA.as<uint64_t>();
+  NRP_LAUNCH((k_unique_heads<<<grid_for(m, 256), 256, 0, st>>>(sorted, m, c->bgb_head.as<uint32_t>())));
+  exclusive_scan<uint32_t, uint32_t>(c->bgb_head.as<uint32_t>(), c->bgb_head_scan.as<uint32_t>(), m, c->scan_scratch.as<uint32_t>(), st);
+  NRP_LAUNCH((k_unique_compact<<<grid_for(m, 256), 256, 0, st>>>(sorted, c->bgb_head.as<uint32_t>(), c->bgb_head_scan.as<uint32_t>(), m, spare)));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(c->h_counters + 48, c->bgb_head_scan.as<uint32_t>() + m, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(c->h_counters + 49, cnt + CNT_WORK, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if ((int64_t)c->h_counters[49] != m) return fail(NRP_E_CUDA, "background extraction produced %lld of %lld windows", (long long)c->h_counters[49], (long long)m);
+  c->bgb_n = (int64_t)(uint32_t)c->h_counters[48];
+  c->bgb_result = spare;
+  *n_unique = c->bgb_n;
+  if (install) return bg_install_device(c, spare, c->bgb_n, K);
+  return NRP_OK;
+}
+
+int nrp_bg_build_fetch(nrp_ctx* c, uint64_t* keys_out) {
+  if (!c || (!keys_out && c->bgb_n > 0)) return fail(NRP_E_ARG, "null argument");
+  if (c->bgb_n > 0 && !c->bgb_result) return fail(NRP_E_STATE, "no finished background build");
+  CU(cudaSetDevice(c->device));
+  if (c->bgb_n > 0) CU(cudaMemcpyAsync(keys_out, c->bgb_result, 8 * (size_t)c->bgb_n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return NRP_OK;
 }
 

@@ -22,6 +22,37 @@ __global__ void k_bg_insert(const uint64_t* keys, int64_t n, KeyT* table, int lo
   }
 }
 
+// ---- background build on the device (replaces the per-k-mer puts of reference kmerSetDB.py:129-175) --------------
+// canonical K-mers of every K-window of the staged sequences, appended in tile order (the sort that follows orders them)
+__global__ void __launch_bounds__(kTileThreads) k_extract_canon(Parts P, int K, uint64_t* out, unsigned long long* n_out) {
+  __shared__ TileStage stage;
+  __shared__ uint64_t s_keys[kTileBytes];
+  __shared__ uint32_t s_count;
+  __shared__ unsigned long long s_base;
+  const int64_t tile = P.tile_lo + blockIdx.x;
+  if (threadIdx.x == 0) s_count = 0;
+  tile_load(P, tile, stage, threadIdx.x);
+  __syncthreads();
+  tile_windows_blocked<false>(P, stage, tile, K, nullptr, threadIdx.x, [&](int, uint64_t canon, uint32_t, uint32_t, bool) {
+    s_keys[atomicAdd(&s_count, 1u)] = canon;
+  });
+  __syncthreads();
+  const uint32_t total = s_count;
+  if (threadIdx.x == 0 && total) s_base = atomicAdd(n_out, (unsigned long long)total);
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) out[s_base + i] = s_keys[i];
+}
+
+// distinct keys of a sorted array: head marks + compaction
+__global__ void k_unique_heads(const uint64_t* keys, int64_t n, uint32_t* head) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+__global__ void k_unique_compact(const uint64_t* keys, const uint32_t* head, const uint32_t* head_scan, int64_t n, uint64_t* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && head[i]) out[head_scan[i]] = keys[i];
+}
+
 template <typename KeyT>
 __device__ __forceinline__ bool bg_contains(const KeyT* table, int log_slots, uint64_t key64) {
   const KeyT kEmpty = ~KeyT(0);

@@ -14,6 +14,11 @@ What changes is the storage and who answers the hot path's membership test:
     letters) are kept verbatim in a small side set so that add/remove/len/iter behave like the reference;
     they can never match a window of an A/C/G/T part.
 The on-disk layout is NOT LMDB compatible with ShareDB stores (out of scope).
+
+Building the key set (add / multiadd, kmerSetDB.py:129-175 -- one LMDB put per k-mer in the reference): the storage
+layer's own vectorised host code by default; with device=True (or NRPCALC_B200_BG_DEVICE=1) the canonical K-mers are
+extracted, sorted and deduplicated on the GPU (nrp_bg_build in include/nrp_b200.h) and only merged into the persistent
+array here.  A requested device build raises when the CUDA library or a GPU is missing -- there is no silent fallback.
 """
 import json
 import os
@@ -38,7 +43,7 @@ def _canonical_strings(seq, K):
 
 class kmerSetDB(object):
 
-    def __init__(self, path, homology, verbose=False):
+    def __init__(self, path, homology, verbose=False, device=None):
         try:
             if not isinstance(path, str):
                 print('\n[Non-Repetitive Parts Calculator - Background]')
@@ -66,6 +71,9 @@ class kmerSetDB(object):
         self.LEN = 0
         self.K = int(homology)
         self._version = 0                              # bumped on every content change (device table refresh)
+        if device is None:
+            device = os.environ.get('NRPCALC_B200_BG_DEVICE', '0') == '1'
+        self._device = bool(device)                    # build the key set on the GPU (nrp_bg_build)
         self._open_store()
         self.VERB = bool(verbose)
         self.ALIVE = True
@@ -126,7 +134,11 @@ class kmerSetDB(object):
                 odd.extend(_canonical_strings(seq, self.K))
         if plain:
             ascii_buf, offsets = encoding.join_parts(plain)
-            ints = encoding.canonical_kmers(ascii_buf, offsets, self.K)
+            if self._device:
+                from . import hgraph                 # the process-wide device context
+                ints = hgraph._context().bg_build(ascii_buf, offsets, self.K)      # distinct, ascending
+            else:
+                ints = encoding.canonical_kmers(ascii_buf, offsets, self.K)
         else:
             ints = np.zeros(0, dtype=np.uint64)
         return ints, odd

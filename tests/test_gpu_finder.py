@@ -63,3 +63,45 @@ def test_config1_shape(scratch_cwd):
 def test_rejects_other_alphabets(scratch_cwd):
     with pytest.raises(ValueError, match='A, C, G, T'):
         nrpcalc_b200.finder(['ACGUACGUACGUACGUAA', 'ACGTNACGTACGTACGTACGT'], 12, verbose=False)
+
+
+def test_background_built_on_device_matches_host(scratch_cwd):
+    """nrp_bg_build (extract + sort + unique on the GPU) against the storage layer's host code and the reference's
+    known answer (nrpcalc.py:89-167: six 17-mers at Lmax=15 -> 12 canonical 16-mers, 10 after a remove)."""
+    import numpy as np
+    from nrpcalc_b200 import encoding
+    docs = ['ATGAGATCGTAGCAACC', 'GACGATTACGTCAGGTA', 'ACAGTAGAGACGAGTAA', 'CCAGTACGAAAAGGCCC', 'TTAGCTTGATAGTTTTA']
+    listed = ['AAAACTATCAAGCTAA', 'ACAGTAGAGACGAGTA', 'ACCTGACGTAATCGTC', 'ACGATTACGTCAGGTA', 'ATGAGATCGTAGCAAC', 'ATGCTTAGTGCCATAC',
+              'CAGTACGAAAAGGCCC', 'CAGTAGAGACGAGTAA', 'CCAGTACGAAAAGGCC', 'GGTATGGCACTAAGCA', 'GGTTGCTACGATCTCA', 'TAAAACTATCAAGCTA']
+    host = nrpcalc_b200.background(path='./bg_host/', Lmax=15, verbose=False)
+    dev = nrpcalc_b200.background(path='./bg_dev/', Lmax=15, verbose=False, device=True)
+    for bg in (host, dev):
+        bg.add('ATGCTTAGTGCCATACC')
+        bg.multiadd(docs)
+    assert len(dev) == len(host) == 12 and list(dev) == list(host) == listed
+    dev.remove('ATGCTTAGTGCCATACC'); host.remove('ATGCTTAGTGCCATACC')
+    assert len(dev) == len(host) == 10 and list(dev) == list(host)
+    assert 'ATGCTTAGTGCCATACC' not in dev and all(dev.multicheck(docs))
+    # a genome-sized batch with lower case, duplicates, short and K-long sequences
+    genome = cases.random_genome(300_000, 5)
+    seqs = [genome, genome[1000:5000].lower(), 'ACGT', genome[:16], genome[7:23]] + cases.planted_parts(300, 3, p_short=0.2)
+    seqs = [s for s in seqs if len(s) >= 16]
+    ctx = hgraph._context()
+    buf, off = encoding.join_parts(seqs)
+    got = ctx.bg_build(buf, off, 16)
+    want = np.unique(encoding.canonical_kmers(buf, off, 16))
+    assert got.dtype == np.uint64 and got.tolist() == want.tolist()
+    got25 = ctx.bg_build(buf, off, 25)
+    assert got25.tolist() == np.unique(encoding.canonical_kmers(buf, off, 25)).tolist()
+    for bg in (host, dev):
+        bg.drop()
+
+
+def test_finder_with_device_built_background(scratch_cwd):
+    case = next(c for c in GOLDEN_CASES if c['bg_seqs'] is not None)
+    bg = nrpcalc_b200.background(path='./bg_store_dev/', Lmax=case['bg_Lmax'], verbose=False, device=True)
+    bg.multiadd(case['bg_seqs'])
+    graph = hgraph.get_homology_graph(list(case['parts']), bg, case['Lmax'] + 1, case['internal_repeats'], './seq.txt', False)
+    assert list(graph.nodes()) == case['graph_nodes']
+    assert [list(graph[n]) for n in graph.nodes()] == case['graph_adj']
+    bg.drop()
