@@ -197,6 +197,7 @@ def main():
     ap.add_argument('--reference-parts', type=int, default=20_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-edges', action='store_true')
+    ap.add_argument('--h2d-chunks', type=int, default=1, help='e2e leg: pieces of the streamed host-to-device copy (1 = one blocking copy)')
     ap.add_argument('--opt', action='append', default=[], help='library tuning knob name=value (nrp_ctx_set_option), repeatable')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else max(args.warmup, 0)
@@ -277,7 +278,7 @@ def main():
         flush.fill_(1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        ctx.load_parts(host_ascii.numpy(), off, ids)
+        ctx.load_parts(host_ascii.numpy(), off, ids, chunks=args.h2d_chunks)
         t1 = time.perf_counter()
         ctx.build(k, cfg['internal_repeats'], want_edges)
         t2 = time.perf_counter()
@@ -286,7 +287,8 @@ def main():
         if step >= 2:
             e2e_times.append(dt)
             e2e_parts.append((t1 - t0, t2 - t1, t0 + dt - t2))
-        h2d = buf.nbytes + off.nbytes + ids.nbytes
+        # parts of one length: the offsets are generated on the device, only the bytes and the ids travel
+        h2d = buf.nbytes + ids.nbytes + (0 if not isinstance(cfg['length'], tuple) else off.nbytes)
         d2h = (res.flags.nbytes + res.indptr.nbytes + res.members.nbytes + res.first_window.nbytes + res.keys.nbytes +
                res.last_single.nbytes + (res.edges[0].nbytes + res.edges[1].nbytes if res.edges else 0) + 16 * 8 * 2)
     clocks = sampler.stop()
@@ -330,7 +332,8 @@ def main():
             'e2e': {'value': e2e_value, 'unit': 'k-mers/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'ms_per_step': 1e3 * sum(e2e_times) / len(e2e_times),
                     'ms_load_build_fetch': [1e3 * sum(p[i] for p in e2e_parts) / len(e2e_parts) for i in range(3)],
-                    'path': 'C ABI: nrp_load_parts(host buffers) + nrp_build + nrp_result_host (page-locked result buffers)'},
+                    'h2d_chunks': args.h2d_chunks,
+                    'path': 'C ABI: nrp_load_parts (page-locked host buffers; --h2d-chunks > 1: nrp_load_parts_streamed, measured no faster: the 49-53 GB/s copy is the floor) + nrp_build + nrp_result_host'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
             'stage_ms': {name: v / args.steps for name, v in stage_ms.items()},
             'result': {name: counts[name] for name in ('records', 'excluded', 'groups', 'members', 'edges', 'candidates', 'runs', 'buckets', 'oversized',

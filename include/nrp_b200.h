@@ -118,6 +118,12 @@ int nrp_bg_build_fetch(nrp_ctx* ctx, uint64_t* keys_out);
 int nrp_load_parts(nrp_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, const uint32_t* part_id, int64_t n_parts,
                    int ascii_on_device);
 
+/* Streamed staging for page-locked host buffers: like nrp_load_parts, but the ASCII copy is only ENQUEUED, in n_chunks pieces
+ * (contiguous part ranges) on a second stream, and the next nrp_build extracts every piece as soon as it has landed, so the
+ * host-to-device copy overlaps the extraction.  `ascii` must stay valid and unchanged until that nrp_build has returned. */
+int nrp_load_parts_streamed(nrp_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, const uint32_t* part_id, int64_t n_parts,
+                            int n_chunks);
+
 /* Build the repeat structure of the staged parts.
  *   internal_repeats 0: exclude parts with internal direct/inverted repeats or palindromic windows
  *   want_edges       != 0: also expand groups into the distinct (id_u < id_v) edges

@@ -60,6 +60,7 @@ def _declare(lib):
         'nrp_bg_build': (c_ctx, ptr, ptr, i64, i32, i32, ctypes.POINTER(i64)),
         'nrp_bg_build_fetch': (c_ctx, ptr),
         'nrp_load_parts': (c_ctx, ptr, ptr, ptr, i64, i32),
+        'nrp_load_parts_streamed': (c_ctx, ptr, ptr, ptr, i64, i32),
         'nrp_build': (c_ctx, i32, i32, i32),
         'nrp_result_counts': (c_ctx, ptr),
         'nrp_result_timings': (c_ctx, ptr),
@@ -173,8 +174,10 @@ class Context(object):
         _check(self._lib, self._lib.nrp_bg_build_fetch(self._h, _p(keys)))
         return keys
 
-    def load_parts(self, ascii_buf, offsets, part_id=None, device_ptr=None):
-        """ascii_buf: uint8 array (host) or None with device_ptr = address of the bytes in device memory."""
+    def load_parts(self, ascii_buf, offsets, part_id=None, device_ptr=None, chunks=1):
+        """ascii_buf: uint8 array (host) or None with device_ptr = address of the bytes in device memory.
+        chunks > 1 (page-locked host buffer): streamed staging -- the copy is enqueued in pieces and the next build()
+        extracts each piece as it lands; the context keeps a reference to ascii_buf until then."""
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         n_parts = offsets.size - 1
         if part_id is not None:
@@ -186,7 +189,11 @@ class Context(object):
             ascii_buf = np.ascontiguousarray(ascii_buf, dtype=np.uint8)
             assert ascii_buf.size >= int(offsets[-1])
             src, on_device = _p(ascii_buf), 0
-        _check(self._lib, self._lib.nrp_load_parts(self._h, src, _p(offsets), _p(part_id), n_parts, on_device))
+        if chunks > 1 and not on_device:
+            self._keep = ascii_buf                    # borrowed until the next build has returned
+            _check(self._lib, self._lib.nrp_load_parts_streamed(self._h, src, _p(offsets), _p(part_id), n_parts, int(chunks)))
+        else:
+            _check(self._lib, self._lib.nrp_load_parts(self._h, src, _p(offsets), _p(part_id), n_parts, on_device))
         self.n_parts = n_parts
 
     def build(self, k, internal_repeats, want_edges=True):

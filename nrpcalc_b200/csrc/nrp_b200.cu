@@ -15,6 +15,7 @@
 // If grouping finds a part with an internal repeat (and internal_repeats == 0) the part is flagged and the
 // pipeline runs once more without it -- the reference drops such parts before they touch the table
 // (hgraph.py:50-69), so their records must not be seen by any group.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -155,10 +156,16 @@ struct nrp_ctx {
 
   // loaded parts
   DevBuf ascii, off, part_id, tile_first;
-  std::vector<int64_t> h_off;
+  const int64_t* h_off = nullptr;            // host copy of the offsets (lives in h_upload until the next batch)
   int64_t n_parts = 0, total_len = 0, n_tiles = 0, max_len = 0;
   int uniform_len = 0;
   bool have_parts = false, have_ids = false;
+  // streamed staging: the ASCII copy is in flight on copy_stream in pieces (contiguous part ranges); pending_chunks > 0 until a
+  // build (or any other consumer) has waited for them
+  struct Chunk { int64_t part_lo, part_hi, tile_lo, n_tiles; cudaEvent_t landed; };
+  std::vector<Chunk> chunks;
+  cudaStream_t copy_stream = nullptr;
+  int pending_chunks = 0;
   uint32_t part_base = 0;
   int64_t max_id = 0;
 
@@ -224,6 +231,14 @@ Parts parts_view(const nrp_ctx* c) {
   P.tile_lo = c->shard_tile_lo;
   return P;
 }
+
+__global__ void k_uniform_offsets(int64_t* off, int64_t n_parts, int64_t len) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n_parts) off[i] = i * len;
+}
+
+// byte offset of part i on the host (uniform batches keep no host copy of the offsets)
+inline int64_t part_offset(const nrp_ctx* c, int64_t i) { return c->uniform_len > 0 ? i * (int64_t)c->uniform_len : c->h_off[i]; }
 
 __global__ void k_init_cursors(const uint32_t* leaf_off, int r1, int r2, uint32_t* cursor1, uint32_t* cursor2) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -341,6 +356,8 @@ int nrp_ctx_destroy(nrp_ctx* c) {
   for (void* p : c->opened_ptrs) cudaIpcCloseMemHandle(p);
   for (DevBuf* b : all) b->release();
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+  for (auto& ch : c->chunks) cudaEventDestroy(ch.landed);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->h_counters) cudaFreeHost(c->h_counters);
   c->h_upload.release(); c->h_results.release();
   if (!c->external_stream) cudaStreamDestroy(c->stream);
@@ -477,7 +494,8 @@ int nrp_bg_build_fetch(nrp_ctx* c, uint64_t* keys_out) {
   return NRP_OK;
 }
 
-int nrp_load_parts(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, const uint32_t* part_id, int64_t n_parts, int ascii_on_device) {
+static int load_parts_impl(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, const uint32_t* part_id, int64_t n_parts, int ascii_on_device,
+                           int n_chunks) {
   if (!c) return fail(NRP_E_ARG, "null context");
   if (n_parts < 0 || !offsets || (n_parts > 0 && !ascii && offsets[n_parts] > 0)) return fail(NRP_E_ARG, "bad part buffers");
   if (n_parts >= 0xfffffff0ll) return fail(NRP_E_UNSUPPORTED, "more than 2^32-16 parts");
@@ -490,35 +508,77 @@ int nrp_load_parts(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, con
   const int64_t n_tiles = (total + kTileBytes - 1) / kTileBytes;
   const size_t padded = (size_t)n_tiles * kTileBytes + 256;
   TRY(c->ascii.ensure(padded));
-  CU(cudaMemsetAsync(c->ascii.as<uint8_t>() + total, 0, padded - (size_t)total, c->stream));
-  if (total > 0)
-    CU(cudaMemcpyAsync(c->ascii.ptr, ascii, (size_t)total, ascii_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+  if (c->pending_chunks > 0) { CU(cudaStreamSynchronize(c->copy_stream)); c->pending_chunks = 0; }     // an earlier streamed batch nobody consumed
+  CU(cudaStreamSynchronize(c->stream));                     // nothing of the previous batch is still in flight (staging buffers are reused)
+  const bool streamed = n_chunks > 1 && !ascii_on_device && total > 0 && n_parts > 1;
+  if (!streamed) {
+    CU(cudaMemsetAsync(c->ascii.as<uint8_t>() + total, 0, padded - (size_t)total, c->stream));
+    if (total > 0)
+      CU(cudaMemcpyAsync(c->ascii.ptr, ascii, (size_t)total, ascii_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+  } else {
+    // pieces = contiguous part ranges of about equal bytes, copied on a second stream; each records an event when it has landed
+    if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaMemsetAsync(c->ascii.as<uint8_t>() + total, 0, padded - (size_t)total, c->copy_stream));
+    int64_t p_lo = 0;
+    int used = 0;
+    for (int i = 0; i < n_chunks && p_lo < n_parts; ++i) {
+      int64_t p_hi = n_parts;
+      if (i + 1 < n_chunks) {
+        const int64_t target = total / n_chunks * (i + 1);
+        p_hi = std::lower_bound(offsets + p_lo + 1, offsets + n_parts, target) - offsets;
+        if (p_hi <= p_lo) p_hi = p_lo + 1;
+        if (p_hi > n_parts) p_hi = n_parts;
+      }
+      const int64_t b_lo = offsets[p_lo], b_hi = offsets[p_hi];
+      if ((size_t)used >= c->chunks.size()) { nrp_ctx::Chunk ch{}; CU(cudaEventCreateWithFlags(&ch.landed, cudaEventDisableTiming)); c->chunks.push_back(ch); }
+      nrp_ctx::Chunk& ch = c->chunks[used++];
+      ch.part_lo = p_lo; ch.part_hi = p_hi;
+      ch.tile_lo = b_lo / kTileBytes;
+      ch.n_tiles = b_hi > b_lo ? (b_hi + kTileBytes - 1) / kTileBytes - ch.tile_lo : 0;
+      if (b_hi > b_lo) CU(cudaMemcpyAsync(c->ascii.as<uint8_t>() + b_lo, ascii + b_lo, (size_t)(b_hi - b_lo), cudaMemcpyHostToDevice, c->copy_stream));
+      CU(cudaEventRecord(ch.landed, c->copy_stream));
+      p_lo = p_hi;
+    }
+    c->pending_chunks = used;
+  }
   // offsets + ids travel through one page-locked staging buffer (the caller's arrays are usually pageable)
   const size_t off_bytes = sizeof(int64_t) * (size_t)(n_parts + 1), id_bytes = part_id ? sizeof(uint32_t) * (size_t)n_parts : 0;
   TRY(c->h_upload.ensure(off_bytes + id_bytes + 16));
   int64_t* st_off = c->h_upload.as<int64_t>();
   uint32_t* st_id = reinterpret_cast<uint32_t*>(c->h_upload.as<unsigned char>() + off_bytes);
-  int uniform = n_parts > 0 ? (int)std::min<int64_t>(offsets[1] - offsets[0], (int64_t)1 << 30) : 0;
-  int64_t max_len = 0;
-  st_off[0] = 0;
+  // shortest / longest part in one branch-free sweep (the compiler vectorises it), then one memcpy into the staging buffer,
+  // which also serves as the context's host copy of the offsets until the next batch
+  int64_t min_len = n_parts > 0 ? INT64_MAX : 0, max_len = n_parts > 0 ? INT64_MIN : 0;
   for (int64_t i = 0; i < n_parts; ++i) {
     const int64_t len = offsets[i + 1] - offsets[i];
-    if (len < 0) { cudaStreamSynchronize(c->stream); return fail(NRP_E_ARG, "offsets must be non-decreasing (part %lld)", (long long)i); }
-    if (len != uniform) uniform = 0;
-    if (len > max_len) max_len = len;
-    st_off[i + 1] = offsets[i + 1];
+    min_len = len < min_len ? len : min_len;
+    max_len = len > max_len ? len : max_len;
   }
-  if (uniform >= (1 << 30)) uniform = 0;
+  if (min_len < 0) {
+    cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    c->pending_chunks = 0;
+    return fail(NRP_E_ARG, "offsets must be non-decreasing");
+  }
+  int uniform = (n_parts > 0 && min_len == max_len && max_len < ((int64_t)1 << 30)) ? (int)max_len : 0;
   TRY(c->off.ensure(off_bytes));
-  CU(cudaMemcpyAsync(c->off.ptr, st_off, off_bytes, cudaMemcpyHostToDevice, c->stream));
-  c->h_off.assign(offsets, offsets + n_parts + 1);
+  if (uniform > 0) {
+    // parts of one length: the offsets are i * L -- written on the device, nothing to copy or to keep on the host
+    NRP_LAUNCH((k_uniform_offsets<<<grid_for(n_parts + 1, 256), 256, 0, c->stream>>>(c->off.as<int64_t>(), n_parts, (int64_t)uniform)));
+    c->h_off = nullptr;
+  } else {
+    memcpy(st_off, offsets, off_bytes);
+    CU(cudaMemcpyAsync(c->off.ptr, st_off, off_bytes, cudaMemcpyHostToDevice, c->stream));
+    c->h_off = st_off;
+  }
   c->n_parts = n_parts; c->total_len = total; c->uniform_len = uniform; c->max_len = max_len;
   c->n_tiles = n_tiles;
   c->have_ids = part_id != nullptr;
   c->max_id = 0;
   if (part_id && n_parts > 0) {
     uint32_t mx = 0;
-    for (int64_t i = 0; i < n_parts; ++i) { const uint32_t v = part_id[i]; st_id[i] = v; if (v > mx) mx = v; }
+    for (int64_t i = 0; i < n_parts; ++i) mx = part_id[i] > mx ? part_id[i] : mx;
+    memcpy(st_id, part_id, id_bytes);
     c->max_id = mx;
     TRY(c->part_id.ensure(id_bytes));
     CU(cudaMemcpyAsync(c->part_id.ptr, st_id, id_bytes, cudaMemcpyHostToDevice, c->stream));
@@ -528,12 +588,22 @@ int nrp_load_parts(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, con
     NRP_LAUNCH((k_tile_first_part<<<grid_for(c->n_tiles + 1, 256), 256, 0, c->stream>>>(c->off.as<int64_t>(), n_parts, total, c->n_tiles,
                                                                             c->tile_first.as<uint32_t>())));
   CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(c->stream));        // the caller's buffers are borrowed only for the duration of the call
+  // offsets and ids were staged in library memory; a blocking load also waits for the caller's ASCII buffer to be consumed
+  if (!streamed) CU(cudaStreamSynchronize(c->stream));
   c->part_base = 0;
   c->shard_lo = 0; c->shard_hi = n_parts; c->shard_tile_lo = 0; c->shard_tiles = c->n_tiles;
   c->n_owners = 0;
   c->have_parts = true;
   return NRP_OK;
+}
+
+int nrp_load_parts(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, const uint32_t* part_id, int64_t n_parts, int ascii_on_device) {
+  return load_parts_impl(c, ascii, offsets, part_id, n_parts, ascii_on_device, 1);
+}
+
+int nrp_load_parts_streamed(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, const uint32_t* part_id, int64_t n_parts, int n_chunks) {
+  if (n_chunks < 1 || n_chunks > 64) return fail(NRP_E_ARG, "n_chunks must be in [1, 64]");
+  return load_parts_impl(c, ascii, offsets, part_id, n_parts, 0, n_chunks);
 }
 
 }  // extern "C"
@@ -562,10 +632,18 @@ int ensure_record_buffers(nrp_ctx* c, int64_t n_records, size_t key_bytes, int64
   return NRP_OK;
 }
 
+// a streamed batch (nrp_load_parts_streamed): make the context's stream wait for every piece still in flight
+int wait_chunks(nrp_ctx* c) {
+  for (int i = 0; i < c->pending_chunks; ++i) CU(cudaStreamWaitEvent(c->stream, c->chunks[i].landed, 0));
+  c->pending_chunks = 0;
+  return NRP_OK;
+}
+
 // ---- stage: exclusion flags that need no grouping (palindromes, background) over the shard's tiles
 int stage_flags(nrp_ctx* c, int k, int internal_repeats, StageTimer& tm) {
   cudaStream_t st = c->stream;
   tm.begin(NRP_T_FLAGS);
+  if ((!internal_repeats && (k % 2) == 0) || c->bg_n > 0 || c->shard_lo != 0 || c->shard_hi != c->n_parts) TRY(wait_chunks(c));
   const Parts P = parts_view(c);
   TRY(c->flags.ensure((size_t)c->n_parts + 16));
   TRY(c->last_single.ensure(sizeof(int32_t) * (size_t)(c->n_parts + 1)));
@@ -754,14 +832,28 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
     const RegionLimit lim{dp.cap[lvl], 0u, overflow, nullptr};
     void* out_k = buf_keys[lvl & 1]; uint32_t* out_v = buf_vals[lvl & 1];
     if (lvl == 0 && from_ascii) {
-      if (packed)
-        NRP_LAUNCH((k_split_from_ascii<uint64_t, 0, false, true><<<split_grid(c), kTileThreads, sizeof(SplitSmem<uint64_t, true>) + sizeof(TileStage), st>>>(
-            P, c->flags.as<uint8_t>(), k, r, 0, c->shard_tiles, c->part_base, c->j_bits, c->vbits, PassSel{0, 0u, 0u}, cursor,
-            (uint64_t*)out_k, out_v, lim, PeerBuffers{}, 0)));
-      else
-        NRP_LAUNCH((k_split_from_ascii<KeyT, 0, false><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-            P, c->flags.as<uint8_t>(), k, r, 0, c->shard_tiles, c->part_base, c->j_bits, 0, PassSel{0, 0u, 0u}, cursor,
-            (KeyT*)out_k, out_v, lim, PeerBuffers{}, 0)));
+      // a streamed batch is extracted piece by piece, each as soon as its copy has landed (pieces are part ranges; the
+      // kernel only forms windows of the parts in its range, so a byte tile shared by two pieces is visited by both)
+      const int n_pieces = c->pending_chunks > 0 ? c->pending_chunks : 1;
+      for (int piece = 0; piece < n_pieces; ++piece) {
+        Parts Q = P;
+        int64_t q_tiles = c->shard_tiles;
+        if (c->pending_chunks > 0) {
+          const nrp_ctx::Chunk& ch = c->chunks[piece];
+          CU(cudaStreamWaitEvent(st, ch.landed, 0));
+          Q.part_lo = ch.part_lo; Q.part_hi = ch.part_hi; Q.tile_lo = ch.tile_lo; q_tiles = ch.n_tiles;
+          if (q_tiles == 0) continue;
+        }
+        if (packed)
+          NRP_LAUNCH((k_split_from_ascii<uint64_t, 0, false, true><<<(unsigned)q_tiles, kTileThreads, sizeof(SplitSmem<uint64_t, true>) + sizeof(TileStage), st>>>(
+              Q, c->flags.as<uint8_t>(), k, r, 0, q_tiles, c->part_base, c->j_bits, c->vbits, PassSel{0, 0u, 0u}, cursor,
+              (uint64_t*)out_k, out_v, lim, PeerBuffers{}, 0)));
+        else
+          NRP_LAUNCH((k_split_from_ascii<KeyT, 0, false><<<(unsigned)q_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
+              Q, c->flags.as<uint8_t>(), k, r, 0, q_tiles, c->part_base, c->j_bits, 0, PassSel{0, 0u, 0u}, cursor,
+              (KeyT*)out_k, out_v, lim, PeerBuffers{}, 0)));
+      }
+      c->pending_chunks = 0;
     } else {
       // children of segment g: the cursors of bucket (g / in_spb), i.e. region index << r (a flat list has one bucket)
       TRY(build_tiles(c, in_ext, in_seg, in_spb, in_spb == 0xffffffffu ? 0 : r, cnt + CNT_RECORDS));
@@ -817,6 +909,7 @@ int stage_bulk_exact(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer&
   const int64_t m_max = from_ascii ? c->shard_m_max : src.m_upper;
   const Parts P = parts_view(c);
   unsigned long long* cnt = c->counters.as<unsigned long long>();
+  TRY(wait_chunks(c));
   // passes over disjoint slices of the hash space (1 unless the batch is too large for two split levels)
   int pass_bits = 0;
   while (pass_bits < 6 && (m_max >> pass_bits) > c->opt_pass_records) ++pass_bits;
@@ -1036,13 +1129,18 @@ int stage_groups(nrp_ctx* c, bool drop_flagged, StageTimer& tm) {
   exclusive_scan<uint32_t, uint32_t>(c->head.as<uint32_t>(), c->head_scan.as<uint32_t>(), n_max, c->scan_scratch.as<uint32_t>(), st);
   const uint32_t* n_runs_dev = c->head_scan.as<uint32_t>() + n_max;
   NRP_LAUNCH((k_group_starts_n<<<grid, 256, 0, st>>>(c->head.as<uint32_t>(), c->head_scan.as<uint32_t>(), n_sorted_dev, n_max, c->group_start.as<uint32_t>())));
-  NRP_LAUNCH((k_group_sizes_n<<<grid, 256, 0, st>>>(c->group_start.as<uint32_t>(), n_runs_dev, n_max, c->valid.as<uint32_t>(),
-                                                  c->mem_cnt.as<uint32_t>(), c->pair_cnt.as<unsigned long long>())));
-  exclusive_scan<uint32_t, uint32_t>(c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), n_max, c->scan_scratch.as<uint32_t>(), st);
-  exclusive_scan<uint32_t, unsigned long long>(c->mem_cnt.as<uint32_t>(), c->mem_scan.as<unsigned long long>(), n_max,
-                                               c->scan_scratch.as<unsigned long long>(), st);
-  exclusive_scan<unsigned long long, unsigned long long>(c->pair_cnt.as<unsigned long long>(), c->pair_scan.as<unsigned long long>(),
-                                                         n_max, c->scan_scratch.as<unsigned long long>(), st);
+  {  // run sizes + the three prefix sums (validity, members, pairs) in three launches
+    const int64_t n_tiles = (n_max + kScanTile - 1) / kScanTile;
+    TRY(c->pair_cnt.ensure(sizeof(GroupTotals) * (size_t)(n_tiles + 1)));          // tile totals / offsets
+    GroupTotals* totals = c->pair_cnt.as<GroupTotals>();
+    NRP_LAUNCH((k_sizes_scan_tiles<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(c->group_start.as<uint32_t>(), n_runs_dev, n_max, c->valid.as<uint32_t>(),
+                                                                             c->valid_scan.as<uint32_t>(), c->mem_scan.as<unsigned long long>(),
+                                                                             c->pair_scan.as<unsigned long long>(), totals)));
+    NRP_LAUNCH((k_sizes_scan_top<<<1, kScanThreads, 0, st>>>(totals, n_tiles, n_max, c->valid_scan.as<uint32_t>(), c->mem_scan.as<unsigned long long>(),
+                                                            c->pair_scan.as<unsigned long long>())));
+    NRP_LAUNCH((k_sizes_scan_add<<<(unsigned)n_tiles, kScanThreads, 0, st>>>(totals, n_max, c->valid_scan.as<uint32_t>(),
+                                                                           c->mem_scan.as<unsigned long long>(), c->pair_scan.as<unsigned long long>())));
+  }
   NRP_LAUNCH((k_group_emit_n<KeyT><<<grid, 256, 0, st>>>(
       (KeyT*)c->cand_keys, c->cand_vals, c->j_bits, c->group_start.as<uint32_t>(), c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(),
       c->mem_scan.as<unsigned long long>(), c->pair_scan.as<unsigned long long>(), n_runs_dev, n_max, c->g_keys.as<uint64_t>(),
@@ -1239,7 +1337,8 @@ int shard_extract_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int internal_r
   TRY(configure_kernels<KeyT>(c));
   cudaStream_t st = c->stream;
   c->shard_lo = lo; c->shard_hi = hi; c->n_owners = n_owners;
-  const int64_t byte_lo = c->h_off[lo], byte_hi = c->h_off[hi];
+  TRY(wait_chunks(c));                                   // a streamed batch must have landed completely
+  const int64_t byte_lo = part_offset(c, lo), byte_hi = part_offset(c, hi);
   c->shard_tile_lo = byte_lo / kTileBytes;
   c->shard_tiles = hi > lo && byte_hi > byte_lo ? (byte_hi + kTileBytes - 1) / kTileBytes - c->shard_tile_lo : 0;
   c->shard_m_max = windows_in_range(c, lo, hi, k);
@@ -1306,7 +1405,8 @@ int shard_count_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int internal_rep
   TRY(configure_kernels<KeyT>(c));
   cudaStream_t st = c->stream;
   c->shard_lo = lo; c->shard_hi = hi; c->n_owners = n_owners;
-  const int64_t byte_lo = c->h_off[lo], byte_hi = c->h_off[hi];
+  TRY(wait_chunks(c));                                   // a streamed batch must have landed completely
+  const int64_t byte_lo = part_offset(c, lo), byte_hi = part_offset(c, hi);
   c->shard_tile_lo = byte_lo / kTileBytes;
   c->shard_tiles = hi > lo && byte_hi > byte_lo ? (byte_hi + kTileBytes - 1) / kTileBytes - c->shard_tile_lo : 0;
   c->shard_m_max = windows_in_range(c, lo, hi, k);
@@ -1412,7 +1512,8 @@ int shard_scatter_direct_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int int
   TRY(configure_kernels<KeyT>(c));
   cudaStream_t st = c->stream;
   c->shard_lo = lo; c->shard_hi = hi; c->n_owners = n_owners;
-  const int64_t byte_lo = c->h_off[lo], byte_hi = c->h_off[hi];
+  TRY(wait_chunks(c));                                   // a streamed batch must have landed completely
+  const int64_t byte_lo = part_offset(c, lo), byte_hi = part_offset(c, hi);
   c->shard_tile_lo = byte_lo / kTileBytes;
   c->shard_tiles = hi > lo && byte_hi > byte_lo ? (byte_hi + kTileBytes - 1) / kTileBytes - c->shard_tile_lo : 0;
   c->shard_m_max = windows_in_range(c, lo, hi, k);

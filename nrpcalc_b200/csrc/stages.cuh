@@ -2,6 +2,7 @@
 // records, group ranks / last single windows for the order-exact host replay, and part-pair edge expansion.
 #pragma once
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace nrp {
 
@@ -206,6 +207,80 @@ __global__ void k_group_sizes_n(const uint32_t* group_start, const uint32_t* n_r
   valid[g] = ok ? 1u : 0u;
   members[g] = ok ? sz : 0u;
   pairs[g] = ok ? (unsigned long long)sz * (sz - 1) / 2 : 0ull;
+}
+
+// Fused: per key run its validity (>= 2 records), member count and pair count, and the exclusive prefix sums of all three
+// over n_max run slots (zeros beyond the actual number of runs) -- three launches instead of one kernel + three scans.
+//   pass 1  per tile of kScanTile runs: local exclusive scans, tile totals
+//   pass 2  one CTA: exclusive scan of the tile totals (+ grand totals at index n_max of the outputs)
+//   pass 3  add the tile offsets
+struct GroupTotals { uint32_t valid; unsigned long long members, pairs; };
+
+__device__ __forceinline__ void run_size_values(const uint32_t* group_start, int64_t g, int64_t n_runs, uint32_t& v, unsigned long long& m,
+                                                unsigned long long& p) {
+  const uint32_t sz = g < n_runs ? group_start[g + 1] - group_start[g] : 0u;
+  const bool ok = sz >= 2;
+  v = ok ? 1u : 0u;
+  m = ok ? sz : 0ull;
+  p = ok ? (unsigned long long)sz * (sz - 1) / 2 : 0ull;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_sizes_scan_tiles(const uint32_t* group_start, const uint32_t* n_runs_ptr, int64_t n_max,
+                                                                  uint32_t* valid, uint32_t* valid_scan, unsigned long long* mem_scan,
+                                                                  unsigned long long* pair_scan, GroupTotals* tile_totals) {
+  __shared__ uint32_t ws32[33];
+  __shared__ unsigned long long ws64[33];
+  const int64_t n_runs = (int64_t)*n_runs_ptr;
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems]; unsigned long long m[kScanItems], p[kScanItems];
+  uint32_t sv = 0; unsigned long long sm = 0, sp = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    run_size_values(group_start, base + i, n_runs, v[i], m[i], p[i]);
+    if (base + i >= n_max) { v[i] = 0; m[i] = 0; p[i] = 0; }
+    sv += v[i]; sm += m[i]; sp += p[i];
+  }
+  uint32_t tv; unsigned long long tm, tp;
+  uint32_t rv = block_exclusive_scan<uint32_t>(sv, ws32, tv);
+  unsigned long long rm = block_exclusive_scan<unsigned long long>(sm, ws64, tm);
+  unsigned long long rp = block_exclusive_scan<unsigned long long>(sp, ws64, tp);
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    const int64_t g = base + i;
+    if (g < n_max) { valid[g] = v[i]; valid_scan[g] = rv; mem_scan[g] = rm; pair_scan[g] = rp; }
+    rv += v[i]; rm += m[i]; rp += p[i];
+  }
+  if (threadIdx.x == 0) tile_totals[blockIdx.x] = GroupTotals{tv, tm, tp};
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_sizes_scan_top(GroupTotals* tile_totals, int64_t n_tiles, int64_t n_max, uint32_t* valid_scan,
+                                                                unsigned long long* mem_scan, unsigned long long* pair_scan) {
+  __shared__ uint32_t ws32[33];
+  __shared__ unsigned long long ws64[33];
+  const int64_t per = (n_tiles + kScanThreads - 1) / kScanThreads;
+  const int64_t t0 = (int64_t)threadIdx.x * per, t1 = t0 + per < n_tiles ? t0 + per : n_tiles;
+  uint32_t sv = 0; unsigned long long sm = 0, sp = 0;
+  for (int64_t t = t0; t < t1; ++t) { sv += tile_totals[t].valid; sm += tile_totals[t].members; sp += tile_totals[t].pairs; }
+  uint32_t tv; unsigned long long tm, tp;
+  uint32_t rv = block_exclusive_scan<uint32_t>(sv, ws32, tv);
+  unsigned long long rm = block_exclusive_scan<unsigned long long>(sm, ws64, tm);
+  unsigned long long rp = block_exclusive_scan<unsigned long long>(sp, ws64, tp);
+  for (int64_t t = t0; t < t1; ++t) {
+    const GroupTotals cur = tile_totals[t];
+    tile_totals[t] = GroupTotals{rv, rm, rp};          // becomes the tile's offset
+    rv += cur.valid; rm += cur.members; rp += cur.pairs;
+  }
+  if (threadIdx.x == 0) { valid_scan[n_max] = tv; mem_scan[n_max] = tm; pair_scan[n_max] = tp; }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_sizes_scan_add(const GroupTotals* tile_offsets, int64_t n_max, uint32_t* valid_scan,
+                                                                unsigned long long* mem_scan, unsigned long long* pair_scan) {
+  const GroupTotals add = tile_offsets[blockIdx.x];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile;
+  for (int i = threadIdx.x; i < kScanTile; i += kScanThreads) {
+    const int64_t g = base + i;
+    if (g < n_max) { valid_scan[g] += add.valid; mem_scan[g] += add.members; pair_scan[g] += add.pairs; }
+  }
 }
 
 template <typename KeyT>

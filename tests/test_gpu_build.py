@@ -196,3 +196,31 @@ def test_empty_and_tiny(ctx):
     for parts in ([], ['ACGTACGTACGTA'], ['ACGTACGTACGTA', 'ACGTACGTACGTA'.lower(), 'TTTTTTTTTTTTTTTT']):
         uniq = _long_parts(parts, 13)
         _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
+
+
+def test_streamed_staging(ctx):
+    """nrp_load_parts_streamed: the copy is enqueued in pieces and the build extracts each piece as it lands."""
+    import torch
+    for k, internal, parts in ((13, False, cases.planted_parts(1500, 21) + cases.random_parts(3000, 100, 8)),
+                               (16, False, cases.palindrome_parts(3, n_parts=400, k=16) + cases.random_parts(2000, 100, 9)),
+                               (25, True, cases.buffer_to_list(*cases.random_varlen_buffer(4000, 50, 300, 12)))):
+        uniq = _long_parts(parts, k)
+        seqs = [s for _, s in uniq]
+        ids = np.array([pid for pid, _ in uniq], dtype=np.uint32)
+        offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum([len(s) for s in seqs], out=offsets[1:])
+        pinned = torch.from_numpy(np.frombuffer(''.join(seqs).encode(), dtype=np.uint8).copy()).pin_memory()
+        for chunks in (2, 7, 64):
+            ctx.set_background(None, 0)
+            ctx.load_parts(pinned.numpy(), offsets, ids, chunks=chunks)
+            ctx.build(k, internal, want_edges=True)
+            _compare(ctx.fetch(), uniq, k, internal)
+        ctx.load_parts(pinned.numpy(), offsets, ids, chunks=5)         # streamed, then the exact path and a second build
+        ctx.set_option('direct', 0)
+        try:
+            ctx.build(k, internal, want_edges=True)
+            _compare(ctx.fetch(), uniq, k, internal)
+        finally:
+            ctx.set_option('direct', -1)
+        ctx.build(k, internal, want_edges=True)
+        _compare(ctx.fetch(), uniq, k, internal)
