@@ -755,6 +755,21 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
   };
   // leaf extents are read two leaves ahead so that no global-load latency sits on the per-leaf critical path
   auto extent = [&](uint32_t lf, uint32_t& elo, uint32_t& en) { leaves.get(lf, n_leaf, elo, en); };
+  // The exact table, both maps and the marks are contiguous and 16-byte aligned: cleared with 128-bit stores.  They are CLEAN at
+  // the top of every leaf: each structure is cleared for the next leaf right after its last use in the current one, while the
+  // threads that still work on the leaf carry on (one barrier less per leaf, no dedicated clearing phase).
+  constexpr int kTable16 = (int)(sizeof(RecT) * kSuspectSlots / 16), kMaps16 = (int)(8 * kBloomWords / 16), kMarks16 = kSuspectSlots / 16;
+  uint4* const z16 = reinterpret_cast<uint4*>(smem_raw);
+  const uint4 ones16 = make_uint4(~0u, ~0u, ~0u, ~0u), zeros16 = make_uint4(0u, 0u, 0u, 0u);
+  auto clear_maps = [&]() {
+    for (int i = threadIdx.x; i < kMaps16; i += T) z16[kTable16 + i] = zeros16;
+  };
+  auto clear_table = [&]() {
+    for (int i = threadIdx.x; i < kTable16; i += T) z16[i] = ones16;
+    for (int i = threadIdx.x; i < kMarks16; i += T) z16[kTable16 + kMaps16 + i] = zeros16;
+  };
+  clear_maps();
+  clear_table();
   uint32_t lo, n, lo1, n1, lo2, n2;
   extent(blockIdx.x, lo, n);
   extent(blockIdx.x + gridDim.x, lo1, n1);
@@ -783,6 +798,7 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
     if (threadIdx.x == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before the async-proxy overwrite
       stage(lo1, n1, turn ? st_vals0 : st_vals1);
+      s_c1 = 0; s_c2 = 0;                           // every reader of the previous leaf's counts is past the barrier above
     }
     if (n < 2) continue;
     if (!fits) {
@@ -797,17 +813,7 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
       }
       continue;
     }
-    {  // clear the exact table, both maps and the marks (contiguous, 16-byte aligned) with 128-bit stores
-      constexpr int kClear16 = (int)((sizeof(RecT) * kSuspectSlots + 8 * kBloomWords + kSuspectSlots) / 16);
-      uint4* z = reinterpret_cast<uint4*>(smem_raw);
-      const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u), zeros = make_uint4(0u, 0u, 0u, 0u);
-      constexpr int kTable16 = (int)(sizeof(RecT) * kSuspectSlots / 16);
-#pragma unroll
-      for (int i = threadIdx.x; i < kClear16; i += T) z[i] = i < kTable16 ? ones : zeros;
-    }
-    if (threadIdx.x == 0) { s_c1 = 0; s_c2 = 0; }
-    __syncthreads();
-    // stage 1a: set bits
+    // stage 1a: set bits (the zeroing of s_c1 / s_c2 above is ordered before their first use by the barrier after this stage)
     uint32_t bits[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -846,6 +852,7 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
     }
     __syncthreads();
     const uint32_t c1 = s_c1;
+    clear_maps();                                   // last use of the maps was the suspect test: clean for the next leaf
     if (c1 == 0) continue;
     if (c1 > (uint32_t)kLeafSortCap) {
       // heavy sharing: hand all suspects (a superset of the shared records) to the global sort
@@ -889,6 +896,7 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
     }
     __syncthreads();
     const uint32_t c2 = s_c2;
+    clear_table();                                  // table and marks are done: clean for the next leaf
     if (c2 == 0) continue;
     {  // order them by (key, part, window): rank by counting, a power-of-two group of threads per record (2^lg * c2 <= T)
       const int lg = 31 - __clz((uint32_t)T / c2);
