@@ -26,6 +26,56 @@ __host__ __device__ __forceinline__ uint32_t owner_hash(uint64_t key) {
   return (uint32_t)(key >> 32);
 }
 
+// Bijective hash on the n = 2k bits of a canonical k-mer (multiply, fold, multiply -- every step invertible mod 2^n).  Packed
+// records carry this hash INSTEAD of the k-mer: every later bucket digit and filter index is a bit field of the record (no
+// re-hashing after the extraction), the bits implied by a record's level-1 region need not be stored, and the filter
+// recovers the k-mer of the few records it emits with inv().
+struct BijHash {
+  uint64_t c1inv, c2inv, mask;
+  int n, s;
+  static constexpr uint64_t kC1 = 0x9E3779B97F4A7C15ull, kC2 = 0xBF58476D1CE4E5B9ull;
+  __host__ __device__ __forceinline__ uint64_t fwd(uint64_t x) const {
+    uint64_t h = (x * kC1) & mask;
+    h ^= h >> s;                                   // s >= n/2: an involution
+    return (h * kC2) & mask;
+  }
+  __host__ __device__ __forceinline__ uint64_t inv(uint64_t h) const {
+    h = (h * c2inv) & mask;
+    h ^= h >> s;
+    return (h * c1inv) & mask;
+  }
+};
+inline uint64_t odd_inverse64(uint64_t x) {       // Newton iteration: the inverse of an odd number mod 2^64
+  uint64_t inv = x;
+  for (int i = 0; i < 6; ++i) inv *= 2 - x * inv;
+  return inv;
+}
+inline BijHash make_bijhash(int k) {
+  BijHash b;
+  b.n = 2 * k;
+  b.mask = b.n >= 64 ? ~0ull : ((1ull << b.n) - 1ull);
+  b.s = (b.n + 1) / 2;
+  b.c1inv = odd_inverse64(BijHash::kC1);
+  b.c2inv = odd_inverse64(BijHash::kC2);
+  return b;
+}
+// layout of a packed record: ((hash without its top owner_bits + drop bits) << vbits) | value
+struct PackFmt {
+  BijHash bij;
+  int vbits;        // bits of the value
+  int drop;         // hash bits implied by the record's level-1 region (not stored)
+  int owner_bits;   // sharded path with a power-of-two number of owners: the top hash bits ARE the owner (not stored either)
+  uint32_t owner;   // ... and this is the owner whose records these are (needed to recover a k-mer)
+  __host__ __device__ __forceinline__ int n_eff() const { return bij.n - owner_bits; }      // hash bits below the owner bits
+  // the full hash of a stored one: owner bits, the bits of level-1 bucket `region`, the stored bits
+  __host__ __device__ __forceinline__ uint64_t compose(uint32_t region, uint64_t stored) const {
+    uint64_t h = stored;
+    if (drop > 0) h |= (uint64_t)region << (n_eff() - drop);
+    if (owner_bits > 0) h |= (uint64_t)owner << n_eff();
+    return h;
+  }
+};
+
 // owner GPU of a key on the direct sharded path: a cheap 32-bit mix (fold, two multiplies), independent of the bit
 // fields of key_hash that select the leaf buckets; the top bits of the product are mapped onto [0, n_owners)
 __host__ __device__ __forceinline__ uint32_t owner_of(uint64_t key, uint32_t n_owners) {

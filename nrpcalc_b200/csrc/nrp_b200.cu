@@ -183,7 +183,6 @@ struct nrp_ctx {
   int n_owners = 0;
   int j_bits = 0;                // > 0: record values are (part << j_bits) | window
   int vbits = 32;                // bits of a record value
-  bool packed = false;           // direct path: records are single words (k-mer << vbits) | value
   DevBuf fb_keys, fb_vals;       // unpacked copy of a packed source for the exact-path fallback
   // receive buffers of the fused exchange (exported with CUDA IPC) and the peers' buffers opened here
   DevBuf recv_keys, recv_vals;
@@ -191,8 +190,8 @@ struct nrp_ctx {
   DevBuf recv_keys_d, recv_vals_d, recv_ends;
   PeerBuffers peers_d{};
   uint32_t* peer_ends[kMaxPeers] = {nullptr};
-  int sh_world = 0, sh_r1 = 0, sh_bits = 0, sh_key_bytes = 0, n_peers_d = 0;
-  bool sh_packed = false;
+  int sh_world = 0, sh_r1 = 0, sh_bits = 0, sh_key_bytes = 0, n_peers_d = 0, sh_owner_bits = 0;
+  bool sh_packed = false, sh_no_window = false;
   uint32_t sh_cap1s = 0;
   int64_t sh_windows_total = 0, sh_m_owner = 0, sh_sent = 0;
   int64_t recv_capacity = 0;
@@ -672,6 +671,8 @@ template <typename KeyT>
 struct BulkSource {
   bool from_parts = true;              // records are extracted from the staged parts
   bool packed = false;                 // the record list holds packed words (direct sharded path), not (key, value) arrays
+  int drop = 0;                        // packed words: top hash bits implied by the segment's level-1 bucket
+  int owner_bits = 0;                  // packed words of the sharded path: the owner is the top hash bits (this rank's records)
   const void* keys = nullptr;
   const uint32_t* vals = nullptr;
   SegExtents ext{nullptr, 0, nullptr, 0};
@@ -738,8 +739,20 @@ DirectPlan plan_direct(const nrp_ctx* c, int64_t m, int pre, bool must_split, in
   return p;
 }
 
+// Can the records of this job travel as packed words?  n = 2k hash bits, `drop` of them implied by the level-1 region,
+// `bits` leaf bits in total (the filter mixes the >= 11 hash bits below them into its bit-map and table indices).
+// (owner_bits: sharded path, the top hash bits that select the owner; `bits` then counts the owner-local leaf bits)
+bool packed_fits(const nrp_ctx* c, int k, int drop, int bits, int owner_bits = 0, int vbits = -1) {
+  const int n = 2 * k - owner_bits;
+  if (vbits < 0) vbits = c->vbits;
+  return c->opt_packed && !c->opt_no_bloom && n - drop + vbits <= 64 && n >= bits + 11 && n - drop >= 1 && 2 * k < 64;
+}
+PackFmt pack_format(const nrp_ctx* c, int k, int drop, int owner_bits = 0, uint32_t owner = 0) {
+  return PackFmt{make_bijhash(k), c->vbits, drop, owner_bits, owner};
+}
+
 template <typename KeyT>
-int launch_filter(nrp_ctx* c, bool packed, const void* leaf_keys, const uint32_t* leaf_vals, LeafExtents leaves, uint32_t n_leaf, int bits,
+int launch_filter(nrp_ctx* c, bool packed, PackFmt pf, const void* leaf_keys, const uint32_t* leaf_vals, LeafExtents leaves, uint32_t n_leaf, int bits,
                   int64_t mean_leaf, KeyT* out_keys, uint32_t* out_vals) {
   cudaStream_t st = c->stream;
   unsigned long long* cnt = c->counters.as<unsigned long long>();
@@ -752,17 +765,17 @@ int launch_filter(nrp_ctx* c, bool packed, const void* leaf_keys, const uint32_t
   if (!c->opt_no_bloom) {
     if (small && packed)           // two 512-thread CTAs per SM, leaves of up to 4096 records
       NRP_LAUNCH((k_filter_bloom<KeyT, 512, 8, 2048, 2, 512, true><<<grid_small, 512, filter_bloom_smem<8, true, 4096, 2048, 512>(), st>>>(
-          leaf_keys, leaf_vals, leaves, n_leaf, bits, c->vbits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+          leaf_keys, leaf_vals, leaves, n_leaf, bits, pf, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
     else if (small)
       NRP_LAUNCH((k_filter_bloom<KeyT, 512, 8, 2048, 2, 512, false><<<grid_small, 512, filter_bloom_smem<(int)sizeof(KeyT), false, 4096, 2048, 512>(), st>>>(
-          leaf_keys, leaf_vals, leaves, n_leaf, bits, 0, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+          leaf_keys, leaf_vals, leaves, n_leaf, bits, pf, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
     else if (packed)               // one 1024-thread CTA per SM, leaves of up to 8192 records
       NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1, 1024, true><<<grid_large, kFilterThreads, filter_bloom_smem<8, true, 8192, 4096, 1024>(), st>>>(
-          leaf_keys, leaf_vals, leaves, n_leaf, bits, c->vbits, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+          leaf_keys, leaf_vals, leaves, n_leaf, bits, pf, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
     else
       NRP_LAUNCH((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1, 1024, false><<<grid_large, kFilterThreads,
                                                                                  filter_bloom_smem<(int)sizeof(KeyT), false, 8192, 4096, 1024>(), st>>>(
-          leaf_keys, leaf_vals, leaves, n_leaf, bits, 0, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+          leaf_keys, leaf_vals, leaves, n_leaf, bits, pf, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
   } else {
     const size_t fsm = small ? filter_smem_small<KeyT>() : filter_smem_large<KeyT>();
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (220 * 1024) / (fsm + 18 * 1024)));   // + static smem of the leaf ordering
@@ -807,8 +820,9 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
   for (int i = 0; i < dp.n_levels; ++i) total_max = std::max(total_max, ((int64_t)1 << dp.cum[i]) * dp.cap[i]);
   if (total_max >= 0xffffe000ll) { *overflowed = true; return NRP_OK; }   // beyond 32-bit record indices: exact path
   c->counts[NRP_C_BUCKETS] = (int64_t)n_leaf;
-  // records as single 64-bit words when key and value fit (a packed source dictates it)
-  const bool packed = from_ascii ? c->packed : src.packed;
+  // records as single 64-bit words when hash and value fit (a packed source dictates it, with the bits its regions imply)
+  const bool packed = from_ascii ? packed_fits(c, k, dp.cum[0], bits) : src.packed;
+  const PackFmt pf = from_ascii ? pack_format(c, k, dp.cum[0]) : pack_format(c, k, src.drop, src.owner_bits, (uint32_t)c->my_rank);
   const int64_t n_seg_max = std::max<int64_t>((int64_t)src.n_seg, dp.n_levels > 1 ? ((int64_t)1 << dp.cum[0]) : 0);
   TRY(ensure_record_buffers(c, std::max<int64_t>(total_max, m_max), packed ? 8 : sizeof(KeyT), n_seg_max));
   CU(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * CNT_N, st));
@@ -846,11 +860,11 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
         }
         if (packed)
           NRP_LAUNCH((k_split_from_ascii<uint64_t, 0, false, true><<<(unsigned)q_tiles, kTileThreads, sizeof(SplitSmem<uint64_t, true>) + sizeof(TileStage), st>>>(
-              Q, c->flags.as<uint8_t>(), k, r, 0, q_tiles, c->part_base, c->j_bits, c->vbits, PassSel{0, 0u, 0u}, cursor,
+              Q, c->flags.as<uint8_t>(), k, r, 0, q_tiles, c->part_base, c->j_bits, pf, PassSel{0, 0u, 0u}, cursor,
               (uint64_t*)out_k, out_v, lim, PeerBuffers{}, 0)));
         else
           NRP_LAUNCH((k_split_from_ascii<KeyT, 0, false><<<(unsigned)q_tiles, kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-              Q, c->flags.as<uint8_t>(), k, r, 0, q_tiles, c->part_base, c->j_bits, 0, PassSel{0, 0u, 0u}, cursor,
+              Q, c->flags.as<uint8_t>(), k, r, 0, q_tiles, c->part_base, c->j_bits, pf, PassSel{0, 0u, 0u}, cursor,
               (KeyT*)out_k, out_v, lim, PeerBuffers{}, 0)));
       }
       c->pending_chunks = 0;
@@ -861,11 +875,11 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
       const unsigned grid = (unsigned)std::min<int64_t>(m_max / kSplitTile + in_seg, (int64_t)c->n_sms * 4);
       if (packed)
         NRP_LAUNCH((k_split_from_records<uint64_t, false, true><<<grid, kSplitThreads, sizeof(SplitSmem<uint64_t, true>), st>>>(
-            (const uint64_t*)in_keys, in_vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + in_seg, in_done, r, c->vbits,
+            (const uint64_t*)in_keys, in_vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + in_seg, in_done, r, pf,
             PassSel{0, 0u, 0u}, cursor, (uint64_t*)out_k, out_v, lim)));
       else
         NRP_LAUNCH((k_split_from_records<KeyT, false><<<grid, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
-            (const KeyT*)in_keys, in_vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + in_seg, in_done, r, 0, PassSel{0, 0u, 0u},
+            (const KeyT*)in_keys, in_vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + in_seg, in_done, r, pf, PassSel{0, 0u, 0u},
             cursor, (KeyT*)out_k, out_v, lim)));
     }
     in_keys = out_k; in_vals = out_v;
@@ -880,7 +894,7 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
   tm.begin(NRP_T_FILTER);
   if (m_max > 0) {
     if (!counted) NRP_LAUNCH((k_region_total<<<1, 1024, 0, st>>>(c->cursor2.as<uint32_t>(), n_leaf, leaf_cap, cnt + CNT_RECORDS)));
-    TRY((launch_filter<KeyT>(c, packed, leaf_keys, leaf_vals, LeafExtents{nullptr, c->cursor2.as<uint32_t>(), leaf_cap}, n_leaf, bits, m_max >> bits,
+    TRY((launch_filter<KeyT>(c, packed, pf, leaf_keys, leaf_vals, LeafExtents{nullptr, c->cursor2.as<uint32_t>(), leaf_cap}, n_leaf, bits, m_max >> bits,
                              (KeyT*)out_keys, out_vals)));
   }
   CU(cudaGetLastError());
@@ -928,13 +942,16 @@ int stage_bulk_exact(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer&
   KeyT* leaf_keys = nullptr; uint32_t* leaf_vals = nullptr; KeyT* free_keys = nullptr; uint32_t* free_vals = nullptr;
   int64_t cand_so_far = 0;
   const RegionLimit no_limit{0u, 0u, nullptr, nullptr};
+  const PackFmt no_pack = pack_format(c, k, 0);
   const KeyT* src_keys = (const KeyT*)src.keys; const uint32_t* src_vals = src.vals;
   if (!from_ascii && src.packed && m_max > 0) {
     // the source holds packed words (direct sharded path): the exact path works on (key, value) arrays at the same indices
     TRY(c->fb_keys.ensure(sizeof(KeyT) * (size_t)(src.m_upper + 16))); TRY(c->fb_vals.ensure(4 * (size_t)(src.m_upper + 16)));
-    TRY(build_tiles(c, src.ext, src.n_seg, 0xffffffffu, 0, nullptr));
+    TRY(build_tiles(c, src.ext, src.n_seg, src.segs_per_bucket, 0, nullptr));          // descriptor .z = level-1 bucket of the segment
     NRP_LAUNCH((k_unpack_tiles<KeyT><<<(unsigned)std::min<int64_t>(m_max / kSplitTile + src.n_seg, (int64_t)c->n_sms * 4), 512, 0, st>>>(
-        (const uint64_t*)src.keys, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + src.n_seg, c->vbits, c->fb_keys.as<KeyT>(), c->fb_vals.as<uint32_t>())));
+        (const uint64_t*)src.keys, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + src.n_seg,
+        pack_format(c, k, src.drop, src.owner_bits, (uint32_t)c->my_rank),
+        c->fb_keys.as<KeyT>(), c->fb_vals.as<uint32_t>())));
     src_keys = c->fb_keys.as<KeyT>(); src_vals = c->fb_vals.as<uint32_t>();
   }
   const uint32_t* n_src_tiles = c->tile_prefix.as<uint32_t>() + src.n_seg;
@@ -980,11 +997,11 @@ int stage_bulk_exact(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer&
     if (m_max > 0) {
       if (from_ascii) {
         NRP_LAUNCH((k_split_from_ascii<KeyT, 0, true><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-            P, c->flags.as<uint8_t>(), k, r1, 0, c->shard_tiles, c->part_base, c->j_bits, 0, sel, level1_cursor, leaf_keys, leaf_vals, no_limit, PeerBuffers{}, 0)));
+            P, c->flags.as<uint8_t>(), k, r1, 0, c->shard_tiles, c->part_base, c->j_bits, no_pack, sel, level1_cursor, leaf_keys, leaf_vals, no_limit, PeerBuffers{}, 0)));
       } else {
         const unsigned grid = (unsigned)std::min<int64_t>(src_tiles_max, (int64_t)c->n_sms * 4);
         NRP_LAUNCH((k_split_from_records<KeyT, true><<<grid, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
-            src_keys, src_vals, c->tile_desc.as<uint4>(), n_src_tiles, 0, r1, 0, sel, level1_cursor, leaf_keys, leaf_vals, no_limit)));
+            src_keys, src_vals, c->tile_desc.as<uint4>(), n_src_tiles, 0, r1, no_pack, sel, level1_cursor, leaf_keys, leaf_vals, no_limit)));
       }
     }
     if (r2 > 0 && m_max > 0) {
@@ -993,7 +1010,7 @@ int stage_bulk_exact(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer&
       TRY(build_tiles(c, SegExtents{c->leaf_off.as<uint32_t>(), r2, nullptr, 0u}, n_l1, 1u, r2, nullptr));
       const unsigned grid2 = (unsigned)std::min<int64_t>(n_pass / kSplitTile + n_l1, (int64_t)c->n_sms * 4);
       NRP_LAUNCH((k_split_from_records<KeyT, false><<<grid2, kSplitThreads, sizeof(SplitSmem<KeyT>), st>>>(
-          leaf_keys, leaf_vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + n_l1, r1, r2, 0, PassSel{0, 0u, 0u}, c->cursor2.as<uint32_t>(),
+          leaf_keys, leaf_vals, c->tile_desc.as<uint4>(), c->tile_prefix.as<uint32_t>() + n_l1, r1, r2, no_pack, PassSel{0, 0u, 0u}, c->cursor2.as<uint32_t>(),
           free_keys, free_vals, no_limit)));
       std::swap(leaf_keys, free_keys); std::swap(leaf_vals, free_vals);
     }
@@ -1001,7 +1018,7 @@ int stage_bulk_exact(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer&
     KeyT* out_keys = n_passes > 1 ? c->cand_keys_buf.as<KeyT>() : free_keys;
     uint32_t* out_vals = n_passes > 1 ? c->cand_vals_buf.as<uint32_t>() : free_vals;
     if (m_max > 0)
-      TRY((launch_filter<KeyT>(c, false, leaf_keys, leaf_vals, LeafExtents{c->leaf_off.as<uint32_t>(), nullptr, 0u}, n_leaf, bits,
+      TRY((launch_filter<KeyT>(c, false, no_pack, leaf_keys, leaf_vals, LeafExtents{c->leaf_off.as<uint32_t>(), nullptr, 0u}, n_leaf, bits,
                                (m_plan >> pass_bits) >> bits, out_keys, out_vals)));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_counters, cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, st));
@@ -1280,20 +1297,18 @@ int finish_timing(nrp_ctx* c, StageTimer& tm) {
 }
 
 // layout of a record of the staged parts at window length k
-void record_layout(nrp_ctx* c, int k) {
+void record_layout(nrp_ctx* c, int k, bool no_window = false) {
   // carry the window index in the record value when (part, window) fits 32 bits
   int part_bits = 1, win_bits = 1;
   while (((int64_t)1 << part_bits) < c->n_parts) ++part_bits;
   const int64_t max_windows = c->max_len - k + 1;
   while (((int64_t)1 << win_bits) < max_windows) ++win_bits;
   c->j_bits = (max_windows >= 1 && part_bits + win_bits <= 32) ? win_bits : 0;
-  if (c->opt_no_window_carry) c->j_bits = 0;
+  if (c->opt_no_window_carry || no_window) c->j_bits = 0;
   c->vbits = std::min(32, part_bits + c->j_bits);
-  // one 64-bit word per record on the direct path when the 2k key bits and the value bits fit
-  c->packed = c->opt_packed && !c->opt_no_bloom && 2 * k + c->vbits <= 64;
 }
 
-void begin_job(nrp_ctx* c, int k, size_t key_bytes, int want_edges) {
+void begin_job(nrp_ctx* c, int k, size_t key_bytes, int want_edges, bool no_window = false) {
   memset(c->counts, 0, sizeof(c->counts));
   memset(c->timings, 0, sizeof(c->timings));
   launch_counter() = 0;
@@ -1302,7 +1317,7 @@ void begin_job(nrp_ctx* c, int k, size_t key_bytes, int want_edges) {
   c->counts[NRP_C_RUNS] = 1;
   c->k = k; c->key_bytes = (int)key_bytes;
   c->have_result = false;
-  record_layout(c, k);
+  record_layout(c, k, no_window);
 }
 
 template <typename KeyT>
@@ -1360,7 +1375,7 @@ int shard_extract_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int internal_r
   tm.begin(NRP_T_SPLIT1);
   if (c->shard_m_max > 0)
     NRP_LAUNCH((k_split_from_ascii<KeyT, 1, false><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, 8, n_owners, c->shard_tiles, 0u, c->j_bits, 0, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>(),
+        P, c->flags.as<uint8_t>(), k, 8, n_owners, c->shard_tiles, 0u, c->j_bits, pack_format(c, k, 0), PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), c->keysA.as<KeyT>(), c->valsA.as<uint32_t>(),
         RegionLimit{0u, 0u, nullptr, nullptr}, PeerBuffers{}, 0)));
   CU(cudaGetLastError());
   tm.finish(c->timings);
@@ -1447,7 +1462,7 @@ int shard_scatter_impl(nrp_ctx* c, int k, const int64_t* write_offsets) {
   tm.begin(NRP_T_SPLIT1);
   if (c->shard_m_max > 0)
     NRP_LAUNCH((k_split_from_ascii<KeyT, 1, false><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-        P, c->flags.as<uint8_t>(), k, 8, c->n_owners, c->shard_tiles, 0u, c->j_bits, 0, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr,
+        P, c->flags.as<uint8_t>(), k, 8, c->n_owners, c->shard_tiles, 0u, c->j_bits, pack_format(c, k, 0), PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(), nullptr, nullptr,
         RegionLimit{0u, 0u, nullptr, nullptr}, c->peers, 1)));
   CU(cudaGetLastError());
   tm.finish(c->timings);
@@ -1517,7 +1532,7 @@ int shard_scatter_direct_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int int
   c->shard_tile_lo = byte_lo / kTileBytes;
   c->shard_tiles = hi > lo && byte_hi > byte_lo ? (byte_hi + kTileBytes - 1) / kTileBytes - c->shard_tile_lo : 0;
   c->shard_m_max = windows_in_range(c, lo, hi, k);
-  begin_job(c, k, sizeof(KeyT), 0);
+  begin_job(c, k, sizeof(KeyT), 0, c->sh_no_window);
   c->counts[NRP_C_WINDOWS_MAX] = c->shard_m_max;
   StageTimer tm(c);
   TRY(stage_flags(c, k, internal_repeats, tm));
@@ -1530,17 +1545,18 @@ int shard_scatter_direct_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int int
   CU(cudaMemsetAsync(cnt + CNT_SCATTER_OVERFLOW, 0, 16, st));
   NRP_LAUNCH((k_init_owner_cursors<<<grid_for(nd, 256), 256, 0, st>>>(c->cursor1.as<uint32_t>(), c->region_ends.as<uint32_t>(), nd, c->sh_r1,
                                                                     (uint32_t)n_owners, (uint32_t)c->my_rank, c->sh_cap1s)));
-  if (c->packed != c->sh_packed) return fail(NRP_E_STATE, "receive buffers were exported for another record layout");
+  if (packed_fits(c, k, c->sh_r1, c->sh_bits, c->sh_owner_bits) != c->sh_packed)
+    return fail(NRP_E_STATE, "receive buffers were exported for another record layout");
   const RegionLimit lim{c->sh_cap1s, 0u, reinterpret_cast<uint32_t*>(cnt + CNT_SCATTER_OVERFLOW), c->region_ends.as<uint32_t>()};
   if (c->shard_m_max > 0) {
-    if (c->packed)
+    if (c->sh_packed)
       NRP_LAUNCH((k_split_from_ascii<uint64_t, 2, false, true><<<split_grid(c), kTileThreads, sizeof(SplitSmem<uint64_t, true>) + sizeof(TileStage), st>>>(
-          P, c->flags.as<uint8_t>(), k, c->sh_r1, n_owners, c->shard_tiles, 0u, c->j_bits, c->vbits, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(),
-          nullptr, nullptr, lim, c->peers_d, 1)));
+          P, c->flags.as<uint8_t>(), k, c->sh_r1, n_owners, c->shard_tiles, 0u, c->j_bits, pack_format(c, k, c->sh_r1, c->sh_owner_bits, 0u), PassSel{0, 0u, 0u},
+          c->cursor1.as<uint32_t>(), nullptr, nullptr, lim, c->peers_d, 1)));
     else
       NRP_LAUNCH((k_split_from_ascii<KeyT, 2, false><<<split_grid(c), kTileThreads, sizeof(SplitSmem<KeyT>) + sizeof(TileStage), st>>>(
-          P, c->flags.as<uint8_t>(), k, c->sh_r1, n_owners, c->shard_tiles, 0u, c->j_bits, 0, PassSel{0, 0u, 0u}, c->cursor1.as<uint32_t>(),
-          nullptr, nullptr, lim, c->peers_d, 1)));
+          P, c->flags.as<uint8_t>(), k, c->sh_r1, n_owners, c->shard_tiles, 0u, c->j_bits, pack_format(c, k, 0), PassSel{0, 0u, 0u},
+          c->cursor1.as<uint32_t>(), nullptr, nullptr, lim, c->peers_d, 1)));
   }
   PeerEnds pe;
   for (int o = 0; o < kMaxPeers; ++o) pe.ptr[o] = c->peer_ends[o];
@@ -1562,6 +1578,8 @@ int shard_group_direct_impl(nrp_ctx* c, int k, int internal_repeats) {
   BulkSource<KeyT> src;
   src.from_parts = false;
   src.packed = c->sh_packed;
+  src.drop = c->sh_r1;
+  src.owner_bits = c->sh_packed ? c->sh_owner_bits : 0;
   src.keys = c->recv_keys_d.ptr; src.vals = c->recv_vals_d.as<uint32_t>();
   src.n_seg = (uint32_t)c->sh_world << c->sh_r1;
   src.ext = SegExtents{nullptr, 0, c->recv_ends.as<uint32_t>(), c->sh_cap1s};
@@ -1788,12 +1806,26 @@ int nrp_peer_export_direct(nrp_ctx* c, int64_t windows_total, int n_owners, int 
   const int64_t capacity = n_regions * cap1s;
   if (capacity >= 0xffffe000ll) return fail(NRP_E_UNSUPPORTED, "receive regions exceed 32-bit record indices");
   if (!c->have_parts) return fail(NRP_E_STATE, "nrp_load_parts has not been called");
-  record_layout(c, k);                                   // every rank stages the same parts: the same layout everywhere
+  // Record layout of the exchange (every rank stages the same parts: the same decision everywhere).  With a power-of-two number
+  // of owners the owner is the top bits of the bijective hash, which packed records then need not store; if the words still do
+  // not fit with the window index in the value, it is left out (group ranks then come from a scan of the few shared k-mers).
+  int owner_bits = 0;
+  if ((n_owners & (n_owners - 1)) == 0) while ((1 << owner_bits) < n_owners) ++owner_bits;
   const size_t key_bytes = k <= 16 ? 4 : 8;
-  TRY(c->recv_keys_d.ensure((c->packed ? 8 : key_bytes) * (size_t)(capacity + 16)));
+  record_layout(c, k, false);
+  bool no_window = false;
+  bool packed = packed_fits(c, k, r1, bits, owner_bits);
+  if (!packed && c->j_bits > 0) {
+    record_layout(c, k, true);
+    if (packed_fits(c, k, r1, bits, owner_bits)) { packed = true; no_window = true; }
+    else record_layout(c, k, false);
+  }
+  if (!packed) owner_bits = 0;
+  c->sh_owner_bits = owner_bits; c->sh_no_window = no_window;
+  TRY(c->recv_keys_d.ensure((packed ? 8 : key_bytes) * (size_t)(capacity + 16)));
   TRY(c->recv_vals_d.ensure(4 * (size_t)(capacity + 16)));
   TRY(c->recv_ends.ensure(4 * (size_t)(kLevelBuckets * kMaxPeers + 4)));
-  c->sh_world = n_owners; c->sh_r1 = r1; c->sh_cap1s = cap1s; c->sh_key_bytes = (int)key_bytes; c->sh_packed = c->packed;
+  c->sh_world = n_owners; c->sh_r1 = r1; c->sh_cap1s = cap1s; c->sh_key_bytes = (int)key_bytes; c->sh_packed = packed;
   c->sh_windows_total = windows_total; c->sh_m_owner = m_owner;
   cudaIpcMemHandle_t h[3];
   CU(cudaIpcGetMemHandle(&h[0], c->recv_keys_d.ptr));

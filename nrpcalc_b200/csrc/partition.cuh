@@ -32,8 +32,9 @@ constexpr int kLevelBuckets = 1 << kMaxLevelBits;
 constexpr int kLeafSortCap = 1024;              // candidates of one leaf that are ordered inside the filter kernel
 static_assert(kLevelBuckets <= kSplitThreads, "one thread per bucket in split_scatter");
 
-// PACKED: a record is ONE 64-bit word (canonical k-mer << vbits) | value -- possible whenever 2k + vbits <= 64 (vbits = bits of
-// the part index plus bits of the window index): one load / one store per record in every pass and 8 instead of 12 bytes.
+// PACKED: a record is ONE 64-bit word ((bijective hash of the k-mer without its top `drop` bits) << vbits) | value -- possible
+// whenever 2k - drop + vbits <= 64 (vbits = bits of the part index plus bits of the window index, drop = bits of the first
+// split level): one load / one store per record in every pass, 8 instead of 12 bytes, and no hashing after the extraction.
 template <typename KeyT, bool PACKED = false>
 struct alignas(16) SplitSmem {
   KeyT keys[kSplitTile];
@@ -222,16 +223,17 @@ __global__ void __launch_bounds__(512) k_hist_from_tiles(const KeyT* keys, const
 }
 
 // packed words of a segmented record list -> (key, value) arrays at the same indices (fallback to the exact path only)
+// (tile descriptor .z = index of the level-1 bucket the tile's segment belongs to = the hash bits the words do not store)
 template <typename KeyT>
-__global__ void __launch_bounds__(512) k_unpack_tiles(const uint64_t* words, const uint4* tile_desc, const uint32_t* n_tiles_ptr, int vbits,
+__global__ void __launch_bounds__(512) k_unpack_tiles(const uint64_t* words, const uint4* tile_desc, const uint32_t* n_tiles_ptr, PackFmt pf,
                                                      KeyT* out_keys, uint32_t* out_vals) {
   const uint32_t n_tiles = *n_tiles_ptr;
-  const uint32_t vmask = (uint32_t)((1ull << vbits) - 1ull);
+  const uint32_t vmask = (uint32_t)((1ull << pf.vbits) - 1ull);
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint4 d4 = __ldg(tile_desc + tile);
     for (uint32_t i = d4.x + threadIdx.x; i < d4.y; i += blockDim.x) {
       const uint64_t w = words[i];
-      out_keys[i] = (KeyT)(w >> vbits);
+      out_keys[i] = (KeyT)pf.bij.inv(pf.compose(d4.z, w >> pf.vbits));
       out_vals[i] = (uint32_t)w & vmask;
     }
   }
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(1024) k_region_total(const uint32_t* cursor, u
 // is then sorting by (part, window), and a group's first record carries the group's rank for free.
 template <typename KeyT, int MODE, bool PASSES, bool PACKED = false>
 __global__ void __launch_bounds__(kTileThreads, 2) k_split_from_ascii(Parts P, const uint8_t* flags, int k, int r1, int n_owners, int64_t n_tiles,
-                                                                  uint32_t part_base, int j_bits, int vbits, PassSel sel, uint32_t* cursor, KeyT* out_keys,
+                                                                  uint32_t part_base, int j_bits, PackFmt pf, PassSel sel, uint32_t* cursor, KeyT* out_keys,
                                                                   uint32_t* out_vals, RegionLimit lim, PeerBuffers peers, int use_peers) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SplitSmem<KeyT, PACKED>& s = *reinterpret_cast<SplitSmem<KeyT, PACKED>*>(smem_raw);
@@ -280,7 +282,9 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_split_from_ascii(Parts P, c
   const int nb = MODE == 0 ? (1 << r1) : MODE == 1 ? n_owners : (n_owners << r1);
   static_assert(kLevelBuckets == kTileThreads, "one counter per thread");
   const uint32_t j_mask = j_bits ? 0xffffffffu : 0u;
-  const int top_shift = 64 - r1;
+  const int top_shift = PACKED ? pf.n_eff() - r1 : 64 - r1;
+  const uint64_t low_mask = PACKED ? ((1ull << (pf.n_eff() - pf.drop)) - 1ull) : 0ull;    // hash bits a packed record stores
+  const bool hash_owner = PACKED && MODE == 2 && pf.owner_bits > 0;                       // owner = top bits of the hash itself
   // persistent CTAs: the global loads of the next tile are issued before the current tile is written out
   TileRegs pre;
   if ((int64_t)blockIdx.x < n_tiles) tile_fetch(P, P.tile_lo + blockIdx.x, threadIdx.x, flags, pre);
@@ -295,20 +299,23 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_split_from_ascii(Parts P, c
     for (int e = 0; e < kSplitItems; ++e) { dr[e] = 0xffffffffu; key[e] = 0; val[e] = 0; }
     tile_windows_blocked<true>(P, stage, tile, k, flags, threadIdx.x, [&](int e, uint64_t canon, uint32_t part, uint32_t j, bool) {
       uint32_t d;
+      uint64_t h = 0;
       if (MODE == 1) {
         d = owner_hash(canon) % (uint32_t)n_owners;
         if (PASSES && !sel.accept(key_hash(canon))) return;
       } else {
-        const uint64_t h = key_hash(canon);
+        h = PACKED ? pf.bij.fwd(canon) : key_hash(canon);
         if (PASSES && !sel.accept(h)) return;
-        d = MODE == 0 ? (uint32_t)(h >> top_shift) : ((owner_of(canon, (uint32_t)n_owners) << r1) | (r1 ? (uint32_t)(h >> top_shift) : 0u));
+        if (MODE == 0) d = (uint32_t)(h >> top_shift);
+        else if (hash_owner) d = (uint32_t)(h >> top_shift);            // (owner, bucket) = the top owner_bits + r1 bits
+        else d = (owner_of(canon, (uint32_t)n_owners) << r1) | (r1 ? (uint32_t)(h >> top_shift) : 0u);
       }
       const uint32_t rank = atomicAdd(&s.cnt[d], 1u);
 #pragma unroll
       for (int q = 0; q < kSplitItems; ++q)
         if (q == e) {
           const uint32_t v = ((part_base + part) << j_bits) | (j & j_mask);
-          if (PACKED) key[q] = (KeyT)((canon << vbits) | v);
+          if (PACKED) key[q] = (KeyT)(((h & low_mask) << pf.vbits) | v);
           else { key[q] = (KeyT)canon; val[q] = v; }
           dr[q] = (d << 16) | rank;
         }
@@ -331,12 +338,13 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_split_from_ascii(Parts P, c
 template <typename KeyT, bool PASSES, bool PACKED = false>
 __global__ void __launch_bounds__(kSplitThreads, 2) k_split_from_records(const KeyT* __restrict__ in_keys, const uint32_t* __restrict__ in_vals,
                                                                      const uint4* __restrict__ tile_desc, const uint32_t* n_tiles_ptr,
-                                                                     int r_done, int r2, int vbits, PassSel sel, uint32_t* cursor, KeyT* out_keys,
+                                                                     int r_done, int r2, PackFmt pf, PassSel sel, uint32_t* cursor, KeyT* out_keys,
                                                                      uint32_t* out_vals, RegionLimit lim) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SplitSmem<KeyT, PACKED>& s = *reinterpret_cast<SplitSmem<KeyT, PACKED>*>(smem_raw);
   const uint32_t n_tiles = *n_tiles_ptr;
   const uint32_t mask = (1u << r2) - 1u;
+  const int packed_shift = PACKED ? pf.vbits + pf.n_eff() - r_done - r2 : 0;
   KeyT key[kSplitItems];
   uint32_t val[kSplitItems], dr[kSplitItems];
   // the loads of a tile are issued while the previous tile is still being written out (its registers are free by then)
@@ -361,10 +369,15 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split_from_records(const K
       uint32_t idx = start + threadIdx.x + e * kSplitThreads;
       dr[e] = 0xffffffffu;
       if (idx < end) {
-        const uint64_t h = key_hash(PACKED ? ((uint64_t)key[e] >> vbits) : (uint64_t)key[e]);
-        if (!PASSES || sel.accept(h)) {
-          uint32_t d = (uint32_t)(h >> (64 - r_done - r2)) & mask;
+        if (PACKED) {                      // the digit is a bit field of the record: hash bits [n - r_done - r2, n - r_done)
+          const uint32_t d = (uint32_t)((uint64_t)key[e] >> packed_shift) & mask;
           dr[e] = (d << 16) | atomicAdd(&s.cnt[d], 1u);
+        } else {
+          const uint64_t h = key_hash((uint64_t)key[e]);
+          if (!PASSES || sel.accept(h)) {
+            uint32_t d = (uint32_t)(h >> (64 - r_done - r2)) & mask;
+            dr[e] = (d << 16) | atomicAdd(&s.cnt[d], 1u);
+          }
         }
       }
     }
@@ -705,7 +718,7 @@ template <int REC, bool PACKED, int CAP, int WORDS, int SORTCAP> constexpr size_
 
 template <typename KeyT, int T, int E, int WORDS, int MINB, int SORTCAP, bool PACKED>
 __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict__ keys_in, const uint32_t* __restrict__ vals, LeafExtents leaves,
-                                                      uint32_t n_leaf, int leaf_bits, int vbits, uint32_t cap, KeyT* cand_keys, uint32_t* cand_vals,
+                                                      uint32_t n_leaf, int leaf_bits, PackFmt pf, uint32_t cap, KeyT* cand_keys, uint32_t* cand_vals,
                                                       unsigned long long* n_cand, uint32_t* n_oversized, uint32_t* unsorted) {
   // RecT: what a leaf holds -- the key (values in a second array) or the packed word (key << vbits) | value
   using RecT = typename std::conditional<PACKED, uint64_t, KeyT>::type;
@@ -732,8 +745,15 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
   __shared__ uint32_t s_c1, s_c2;
   __shared__ unsigned long long s_cbase;
   const RecT kEmpty = ~RecT(0);
+  const int vbits = pf.vbits;
   const uint32_t vmask = PACKED ? (uint32_t)((1ull << vbits) - 1ull) : 0u;
-  auto canon_of = [&](RecT r) -> uint64_t { return PACKED ? ((uint64_t)r >> vbits) : (uint64_t)r; };
+  // packed: what identifies the k-mer inside a leaf is the stored hash (record >> vbits); its bits below the leaf bits feed the
+  // bit maps and the exact table through two cheap 32-bit mixes
+  const uint64_t rem_mask = PACKED ? ((1ull << (pf.n_eff() - leaf_bits)) - 1ull) : 0ull;
+  constexpr int kLogBits = WORDS == 2048 ? 16 : 17, kLogSlots = SORTCAP == 512 ? 10 : 11;
+  static_assert((WORDS == 2048 || WORDS == 4096) && (SORTCAP == 512 || SORTCAP == 1024), "index widths");
+  auto ident_of = [&](RecT r) -> uint64_t { return PACKED ? ((uint64_t)r >> vbits) : (uint64_t)r; };
+  auto fold_rem = [&](RecT r) -> uint32_t { const uint64_t rem = ((uint64_t)r >> vbits) & rem_mask; return (uint32_t)rem ^ (uint32_t)(rem >> 32); };
   const int lane = threadIdx.x & 31;
   const int bit_shift = 44 - leaf_bits, slot_shift = 33 - leaf_bits;     // 20 hash bits for the maps, the next 11 for the table
   for (int i = threadIdx.x; i < kLeafSortCap; i += T) c_rank[i] = 0;
@@ -749,9 +769,12 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
     if (!PACKED) tma_bulk_load(st_vals, vals + v0, vb, &s_bar);
   };
   // one candidate record leaves the kernel as (key, value)
-  auto emit = [&](unsigned long long dst, RecT r, uint32_t v) {
-    if (PACKED) { cand_keys[dst] = (KeyT)((uint64_t)r >> vbits); cand_vals[dst] = (uint32_t)r & vmask; }
-    else { cand_keys[dst] = (KeyT)r; cand_vals[dst] = v; }
+  // (packed: the hash bits the record does not store are the top `drop` bits of the leaf index; the k-mer is inv(hash))
+  auto emit = [&](unsigned long long dst, RecT r, uint32_t v, uint32_t lf) {
+    if (PACKED) {
+      cand_keys[dst] = (KeyT)pf.bij.inv(pf.compose(lf >> (leaf_bits - pf.drop), (uint64_t)r >> vbits));
+      cand_vals[dst] = (uint32_t)r & vmask;
+    } else { cand_keys[dst] = (KeyT)r; cand_vals[dst] = v; }
   };
   // leaf extents are read two leaves ahead so that no global-load latency sits on the per-leaf critical path
   auto extent = [&](uint32_t lf, uint32_t& elo, uint32_t& en) { leaves.get(lf, n_leaf, elo, en); };
@@ -809,7 +832,7 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
         unsigned long long basepos = 0;
         if (lane == 0) basepos = atomicAdd(n_cand, (unsigned long long)__popc(m));
         basepos = __shfl_sync(0xffffffffu, basepos, 0);
-        if (ok) emit(basepos + __popc(m & lanemask_lt()), keys[lo + i], PACKED ? 0u : vals[lo + i]);
+        if (ok) emit(basepos + __popc(m & lanemask_lt()), keys[lo + i], PACKED ? 0u : vals[lo + i], leaf);
       }
       continue;
     }
@@ -818,7 +841,7 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       if (e >= ne) break;
-      bits[e] = (uint32_t)(key_hash(canon_of(key[e])) >> bit_shift) & kBitMask;
+      bits[e] = PACKED ? (fold_rem(key[e]) * 0x9E3779B1u) >> (32 - kLogBits) : (uint32_t)(key_hash((uint64_t)key[e]) >> bit_shift) & kBitMask;
       const uint32_t w = bits[e] >> 5, m = 1u << (bits[e] & 31u);
       if (atomicOr(&map_a[w], m) & m) atomicOr(&map_b[w], m);
     }
@@ -865,7 +888,7 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
           unsigned long long basepos = 0;
           if (lane == 0) basepos = atomicAdd(n_cand, (unsigned long long)__popc(m));
           basepos = __shfl_sync(0xffffffffu, basepos, 0);
-          if (sus) emit(basepos + __popc(m & lanemask_lt()), key[e], PACKED ? 0u : my_vals[threadIdx.x + e * T]);
+          if (sus) emit(basepos + __popc(m & lanemask_lt()), key[e], PACKED ? 0u : my_vals[threadIdx.x + e * T], leaf);
         }
       }
       continue;
@@ -877,8 +900,8 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
     if (threadIdx.x < c1) {
       mk = c_keys[threadIdx.x];
       if (!PACKED) mv = c_vals[threadIdx.x];
-      const RecT canon = (RecT)canon_of(mk);
-      uint32_t h = (uint32_t)(key_hash((uint64_t)canon) >> slot_shift) & (kSuspectSlots - 1);
+      const RecT canon = (RecT)ident_of(mk);
+      uint32_t h = PACKED ? (fold_rem(mk) * 0x85EBCA6Bu) >> (32 - kLogSlots) : (uint32_t)(key_hash((uint64_t)canon) >> slot_shift) & (kSuspectSlots - 1);
       for (;;) {
         RecT old = atomic_cas(&table[h], kEmpty, canon);
         if (old == kEmpty) break;
@@ -921,7 +944,7 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
     __syncthreads();
     if (threadIdx.x < c2) {
       const uint32_t rank = c_rank[threadIdx.x];
-      emit(s_cbase + rank, c_keys[threadIdx.x], PACKED ? 0u : c_vals[threadIdx.x]);
+      emit(s_cbase + rank, c_keys[threadIdx.x], PACKED ? 0u : c_vals[threadIdx.x], leaf);
       c_rank[threadIdx.x] = 0;
     }
   }

@@ -136,8 +136,8 @@ def test_direct_and_exact_paths_agree(ctx):
         try:
             res = _run(ctx, uniq, k, internal)
             assert res.counts['direct'] == 1 and res.counts['fallbacks'] == 0
-            # one 64-bit word per record whenever 2k + value bits (13 part bits + 7 window bits here) <= 64
-            assert res.counts['packed'] == (1 if 2 * k + 20 <= 64 else 0)
+            # one 64-bit word per record whenever the 2k hash bits minus the level-1 bits, plus 20 value bits, fit 64 bits
+            assert res.counts['packed'] == 1
             _compare(res, uniq, k, internal)
             ctx.set_option('packed', 0)               # (key, value) arrays on the direct path
             res = _run(ctx, uniq, k, internal)
