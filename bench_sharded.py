@@ -78,7 +78,8 @@ def main(args, cfg, rank, world, local_rank):
     if rank == 0:
         peak, peak_src = bench.measured_peak_gbs()
         key_bytes = 8 if k > 16 else 4
-        rec = key_bytes + 4
+        packed = bool(ctx.counts().get('packed', 0))
+        rec = 8 if packed else key_bytes + 4           # bytes of a record on the wire and in HBM
         sent = res['stats']['sent']
         a2a_ms = max(sum(p.get(name, 0.0) for name in ('a2a_counts', 'a2a_alloc', 'a2a_keys', 'a2a_vals', 'all_to_all', 'scatter', 'barrier')) for p in all_phases)
         bytes_out = max(sent) * rec * (world - 1) / world
@@ -87,7 +88,7 @@ def main(args, cfg, rank, world, local_rank):
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak' if weak else 'strong',
                 'vs_baseline': None, 'dtype': 'u64' if key_bytes == 8 else 'u32', 'data': 'synthetic',
                 'config': {'workload': cfg['label'] + (' -- x{} parts (one config-2 batch per GPU)'.format(world) if weak else ''), 'n_parts': n_parts, 'part_len': cfg['length'], 'Lmax': cfg['Lmax'], 'k': k,
-                           'kmers': m, 'edges': want_edges, 'sharding': 'parts block-sharded, k-mers hash-partitioned, 1 exchange (' + os.environ.get('NRPCALC_B200_EXCHANGE', 'peer') + ')',
+                           'kmers': m, 'edges': want_edges, 'record_bytes': rec, 'sharding': 'parts block-sharded, k-mers hash-partitioned, 1 exchange (' + os.environ.get('NRPCALC_B200_EXCHANGE', 'peer') + ')',
                            'l2': 'explicit 256 MiB flush between steps', 'timing': 'wall clock between barrier+synchronize around the device phase (results resident on the devices), max over ranks'},
                 'parts_per_s': n_parts / (ms_per_step * 1e-3),
                 'e2e': {'value': m / (np.mean(e2e) * 1e-3), 'unit': 'k-mers/s', 'h2d_bytes_per_step': int(world * (buf.nbytes + off.nbytes + ids.nbytes)),
