@@ -154,15 +154,6 @@ __device__ __forceinline__ void split_flush(SplitSmem<KeyT, PACKED>& s, KeyT* ou
   }
 }
 
-template <typename KeyT>
-__device__ __forceinline__ void split_scatter(SplitSmem<KeyT, false>& s, const KeyT (&key)[kSplitItems], const uint32_t (&val)[kSplitItems],
-                                              const uint32_t (&dr)[kSplitItems], int nb,
-                                              uint32_t* cursor, KeyT* out_keys, uint32_t* out_vals, RegionLimit lim,
-                                              const PeerBuffers* peers = nullptr, int peer_shift = 0) {
-  split_reorder<KeyT>(s, key, val, dr, nb, cursor, lim);
-  split_flush<KeyT>(s, out_keys, out_vals, peers, peer_shift);
-}
-
 // ---- histogram of leaf buckets straight from the part buffer (exact path) ---------------------------------
 // hist has 2^bits entries (bits <= 15): leaf bucket = top `bits` bits of key_hash(canonical k-mer).
 // Persistent CTAs accumulate in shared memory and flush once.

@@ -129,57 +129,7 @@ __global__ void k_flagged_windows(const int64_t* off, const uint8_t* flags, int6
   if (w > 0) atomicAdd(out, (unsigned long long)w);
 }
 
-// group_start[g] for every key run (g = exclusive scan of head), plus the sentinel group_start[n_groups] = n
-__global__ void k_group_starts(const uint32_t* head, const uint32_t* head_scan, int64_t n, uint32_t* group_start) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > n) return;
-  if (i == n) { group_start[head_scan[n]] = (uint32_t)n; return; }
-  if (head[i]) group_start[head_scan[i]] = (uint32_t)i;
-}
-
-// per key run: is it a real group (>= 2 members), its member count and its pair count
-__global__ void k_group_sizes(const uint32_t* group_start, int64_t n_runs, uint32_t* valid, uint32_t* members, unsigned long long* pairs) {
-  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_runs) return;
-  uint32_t sz = group_start[g + 1] - group_start[g];
-  bool ok = sz >= 2;
-  valid[g] = ok ? 1u : 0u;
-  members[g] = ok ? sz : 0u;
-  pairs[g] = ok ? (unsigned long long)sz * (sz - 1) / 2 : 0ull;
-}
-
-// compact the real groups: keys, CSR indptr (64-bit), pair offsets, and the members
-template <typename KeyT>
-__global__ void k_group_emit(const KeyT* keys, const uint32_t* vals, int j_bits, const uint32_t* group_start, const uint32_t* valid,
-                             const uint32_t* valid_scan, const unsigned long long* member_scan, const unsigned long long* pair_scan,
-                             int64_t n_runs, uint64_t* out_keys, int64_t* out_indptr, unsigned long long* out_pair_off,
-                             uint32_t* out_first_window) {
-  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g > n_runs) return;
-  if (g == n_runs) {
-    uint32_t ng = valid_scan[n_runs];
-    out_indptr[ng] = (int64_t)member_scan[n_runs];
-    out_pair_off[ng] = pair_scan[n_runs];
-    return;
-  }
-  if (!valid[g]) return;
-  uint32_t o = valid_scan[g];
-  out_keys[o] = (uint64_t)keys[group_start[g]];
-  if (j_bits) out_first_window[o] = vals[group_start[g]] & ((1u << j_bits) - 1u);     // the first record is (first part, first window)
-  out_indptr[o] = (int64_t)member_scan[g];
-  out_pair_off[o] = pair_scan[g];
-}
-
-__global__ void k_group_members(const uint32_t* vals, const uint32_t* head_scan, const uint32_t* head, const uint32_t* group_start,
-                                const uint32_t* valid, const unsigned long long* member_scan, int64_t n, int j_bits, uint32_t* out_members) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t g = head_scan[i] + head[i] - 1u;           // run index of record i (inclusive scan - 1)
-  if (!valid[g]) return;
-  out_members[member_scan[g] + (i - group_start[g])] = vals[i] >> j_bits;
-}
-
-// ---- the same steps with the record / run counts read from device memory -------------------------------------
+// ---- key runs -> groups, with the record / run counts read from device memory ---------------------------------
 // The grouping stage is enqueued without host round trips: grids are sized by the upper bound n_max (the number of
 // candidates) and every kernel reads the actual count from a device word; slots beyond it are written as zero so that
 // the prefix sums over n_max entries give the right totals.
@@ -196,17 +146,6 @@ __global__ void k_group_starts_n(const uint32_t* head, const uint32_t* head_scan
   if (i > n) return;
   if (i == n) { group_start[head_scan[n_max]] = (uint32_t)n; return; }
   if (head[i]) group_start[head_scan[i]] = (uint32_t)i;
-}
-
-__global__ void k_group_sizes_n(const uint32_t* group_start, const uint32_t* n_runs_ptr, int64_t n_max, uint32_t* valid, uint32_t* members,
-                                unsigned long long* pairs) {
-  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_max) return;
-  uint32_t sz = g < (int64_t)*n_runs_ptr ? group_start[g + 1] - group_start[g] : 0u;
-  bool ok = sz >= 2;
-  valid[g] = ok ? 1u : 0u;
-  members[g] = ok ? sz : 0u;
-  pairs[g] = ok ? (unsigned long long)sz * (sz - 1) / 2 : 0ull;
 }
 
 // Fused: per key run its validity (>= 2 records), member count and pair count, and the exclusive prefix sums of all three
