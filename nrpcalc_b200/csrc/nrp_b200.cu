@@ -1801,10 +1801,6 @@ int nrp_peer_export_direct(nrp_ctx* c, int64_t windows_total, int n_owners, int 
   CU(cudaSetDevice(c->device));
   int r1 = 0, bits = 0; uint32_t cap1s = 0; int64_t m_owner = 0;
   TRY(direct_shard_plan(c, windows_total, n_owners, &r1, &bits, &cap1s, &m_owner));
-  c->sh_bits = bits;
-  const int64_t n_regions = (int64_t)n_owners << r1;
-  const int64_t capacity = n_regions * cap1s;
-  if (capacity >= 0xffffe000ll) return fail(NRP_E_UNSUPPORTED, "receive regions exceed 32-bit record indices");
   if (!c->have_parts) return fail(NRP_E_STATE, "nrp_load_parts has not been called");
   // Record layout of the exchange (every rank stages the same parts: the same decision everywhere).  With a power-of-two number
   // of owners the owner is the top bits of the bijective hash, which packed records then need not store; if the words still do
@@ -1820,8 +1816,26 @@ int nrp_peer_export_direct(nrp_ctx* c, int64_t windows_total, int n_owners, int 
     if (packed_fits(c, k, r1, bits, owner_bits)) { packed = true; no_window = true; }
     else record_layout(c, k, false);
   }
+  if (!packed) {
+    // a few more pre-partition bits (still long runs over NVLink) may be all that is missing: they are implied by the region
+    int r1_eff = 0;
+    while (((int64_t)n_owners << (r1_eff + 1)) <= c->opt_nvlink_digits) ++r1_eff;
+    for (int r = r1 + 1; r <= r1_eff && r < bits && !packed; ++r) {
+      for (int nw = 0; nw < 2 && !packed; ++nw) {
+        record_layout(c, k, nw != 0);
+        if (nw == 1 && c->j_bits != 0) continue;
+        if (packed_fits(c, k, r, bits, owner_bits)) { packed = true; no_window = nw != 0; r1 = r; }
+      }
+    }
+    if (packed) cap1s = region_cap((double)windows_total / ((double)n_owners * n_owners * (double)(1 << r1)), 256);
+    else record_layout(c, k, false);
+  }
   if (!packed) owner_bits = 0;
   c->sh_owner_bits = owner_bits; c->sh_no_window = no_window;
+  c->sh_bits = bits;
+  const int64_t n_regions = (int64_t)n_owners << r1;
+  const int64_t capacity = n_regions * cap1s;
+  if (capacity >= 0xffffe000ll) return fail(NRP_E_UNSUPPORTED, "receive regions exceed 32-bit record indices");
   TRY(c->recv_keys_d.ensure((packed ? 8 : key_bytes) * (size_t)(capacity + 16)));
   TRY(c->recv_vals_d.ensure(4 * (size_t)(capacity + 16)));
   TRY(c->recv_ends.ensure(4 * (size_t)(kLevelBuckets * kMaxPeers + 4)));
