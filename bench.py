@@ -60,6 +60,23 @@ class ClockSampler(object):
         self.device = device
         self.rows = []
         self.proc = None
+        self.first = 0          # rows before this index were taken before the timed region (warm-up)
+        self.extra_steps = 0
+
+    def mark(self):
+        """The timed region starts now: only later samples are reported."""
+        self.first = len(self.rows)
+
+    def need_more(self, want=2):
+        return self.proc is not None and len(self.rows) - self.first < want
+
+    def top_up(self, step, want=2, limit_s=4.0):
+        """A timed region of a few milliseconds can end before nvidia-smi has printed a row: keep the device under the SAME
+        load with extra UNTIMED steps until `want` rows exist (reported as extra_untimed_steps)."""
+        t0 = time.perf_counter()
+        while self.need_more(want) and time.perf_counter() - t0 < limit_s:
+            step()
+            self.extra_steps += 1
 
     def start(self):
         try:
@@ -84,7 +101,7 @@ class ClockSampler(object):
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for row in self.rows:
+        for row in self.rows[self.first:]:
             try:
                 sm.append(float(row[0])); mx.append(float(row[1]))
             except (ValueError, IndexError):
@@ -93,7 +110,7 @@ class ClockSampler(object):
                 if cell.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'extra_untimed_steps': self.extra_steps}
 
 
 def make_workload(cfg, n_parts=None):
@@ -245,11 +262,12 @@ def main():
 
     # ---- device-resident leg
     ctx.load_parts(None, off, ids, device_ptr=dev_ascii.data_ptr())
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                  # nvidia-smi needs a moment before its first row: started before the warm-up
     for _ in range(args.warmup):
         ctx.build(k, cfg['internal_repeats'], want_edges)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     stage_ms = {}
     total_ms = 0.0
     launches = 0
@@ -265,6 +283,7 @@ def main():
         launches += ctx.counts()['launches']
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
+    sampler.top_up(lambda: ctx.build(k, cfg['internal_repeats'], want_edges))
     clocks = sampler.stop()                          # the clocks belong to the device-timed region; no polling during the e2e leg
     counts = ctx.counts()
     m = counts['records']

@@ -36,11 +36,14 @@ def main(args, cfg, rank, world, local_rank):
         return sharded.build_sharded(ops, off, k, cfg['internal_repeats'], want_edges=want_edges, phase_ms=phase_ms,
                                      gather_host=gather_host)
 
-    for _ in range(args.warmup):
-        res = step()
     sampler = bench.ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()                                    # before the warm-up: nvidia-smi needs a moment before its first row
+    for _ in range(args.warmup):
+        res = step()
+    sampler.mark()
+    lib = _native.load_library()
+    launches0 = int(lib.nrp_launches_total())
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     phase_ms = {}
     total_ms = 0.0
@@ -56,6 +59,18 @@ def main(args, cfg, rank, world, local_rank):
         dt = torch.tensor([(time.perf_counter() - t0) * 1e3], device='cuda')
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)          # slowest rank
         total_ms += float(dt.item())
+    launches = torch.tensor([int(lib.nrp_launches_total()) - launches0], device='cuda', dtype=torch.int64)
+    dist.all_reduce(launches)                              # kernels of this library on all ranks during the timed steps
+    # a timed region of a few milliseconds can end before nvidia-smi has printed a row: extra UNTIMED steps of the same work
+    # (collective, so rank 0 decides for everyone)
+    t_top = time.perf_counter()
+    while True:
+        more = torch.tensor([1 if (rank == 0 and sampler.need_more() and time.perf_counter() - t_top < 4.0) else 0], device='cuda')
+        dist.broadcast(more, 0)
+        if int(more.item()) == 0:
+            break
+        step()
+        sampler.extra_steps += 1
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
 
@@ -94,7 +109,7 @@ def main(args, cfg, rank, world, local_rank):
                 'e2e': {'value': m / (np.mean(e2e) * 1e-3), 'unit': 'k-mers/s', 'h2d_bytes_per_step': int(world * (buf.nbytes + off.nbytes + ids.nbytes)),
                         'd2h_bytes_per_step': int(world * (res['flags'].nbytes + res['members'].nbytes + res['indptr'].nbytes + res['last_single'].nbytes)),
                         'ms_per_step': float(np.mean(e2e)), 'path': 'per rank: nrp_load_parts(host, all parts) + sharded build + merged host results'},
-                'gpu_launches': int(ctx.counts()['launches']) * args.steps * world,
+                'gpu_launches': int(launches.item()),
                 'clocks': clocks,
                 'phase_ms_per_rank': all_phases,
                 'roofline': {'bound': 'hbm', 'kernel': 'per-rank pipeline (group phase of the slowest rank)', 'unit': 'GB/s', 'peak': peak,

@@ -86,6 +86,8 @@ typedef struct nrp_ctx nrp_ctx;
 
 int         nrp_version(void);
 const char* nrp_last_error(void);
+/* Kernels this library has launched from the calling thread since it was loaded (never reset; NRP_C_LAUNCHES counts one build). */
+int64_t     nrp_launches_total(void);
 
 /* Bind a context to a CUDA device (creates a stream; device buffers grow on demand and are reused). */
 int nrp_ctx_create(int device, nrp_ctx** out);
@@ -93,8 +95,9 @@ int nrp_ctx_destroy(nrp_ctx* ctx);
 int nrp_ctx_device(nrp_ctx* ctx);
 
 /* Tuning knobs used by the tests to force rarely taken paths: name in
- * {"filter_cap", "leaf_target", "max_level_bits", "max_pairs", "no_window_carry", "no_bloom", "pass_records", "direct", "packed", "persistent_split", "r1_bias", "nvlink_digits"};
- * value <= 0 restores the default ("direct": 0 forces the exact histogram path, negative restores the default 1). */
+ * {"filter_cap", "leaf_target", "max_level_bits", "max_pairs", "no_window_carry", "no_bloom", "pass_records", "direct", "packed", "persistent_split", "r1_bias", "nvlink_digits", "coop_group"};
+ * value <= 0 restores the default ("direct": 0 forces the exact histogram path, negative restores the default 1;
+ * "coop_group": 0 = grouping as a kernel sequence, 1 = one cooperative kernel up to 2^20 candidates (default), 2 = always). */
 int nrp_ctx_set_option(nrp_ctx* ctx, const char* name, int64_t value);
 
 /* Background (replaces the kmerSetDB membership test, kmerSetDB.py:177-207): n canonical K-mers in the

@@ -50,6 +50,8 @@ def _declare(lib):
     ptr = ctypes.c_void_p
     lib.nrp_version.restype = i32
     lib.nrp_last_error.restype = ctypes.c_char_p
+    lib.nrp_launches_total.restype = i64
+    lib.nrp_launches_total.argtypes = []
     sigs = {
         'nrp_ctx_create': (i32, ctypes.POINTER(c_ctx)),
         'nrp_ctx_destroy': (c_ctx,),

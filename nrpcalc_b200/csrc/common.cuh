@@ -11,7 +11,9 @@ constexpr uint8_t kFlagRepeat = 1, kFlagPalindrome = 2, kFlagBackground = 4;
 
 // number of kernels launched by this thread (reported through NRP_C_LAUNCHES)
 inline int64_t& launch_counter() { static thread_local int64_t n = 0; return n; }
-#define NRP_LAUNCH(kernel_call) do { ++::nrp::launch_counter(); kernel_call; } while (0)
+// ... and by every library call of this thread since the library was loaded (never reset; nrp_launches_total)
+inline int64_t& launch_total() { static thread_local int64_t n = 0; return n; }
+#define NRP_LAUNCH(kernel_call) do { ++::nrp::launch_counter(); ++::nrp::launch_total(); kernel_call; } while (0)
 
 // ---------------------------------------------------------------------------------------------------
 // hashing: one multiplicative (Fibonacci) hash per key; consecutive bit fields of the product, from the top,

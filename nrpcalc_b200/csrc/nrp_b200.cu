@@ -106,7 +106,7 @@ struct HostBuf {
   template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
 };
 
-enum { CNT_SCATTER_OVERFLOW = 9, CNT_SENT = 10, CNT_NSORTED = 11 };
+enum { CNT_SCATTER_OVERFLOW = 9, CNT_SENT = 10, CNT_NSORTED = 11, CNT_GROUP = 12 /* 5 words */, CNT_WORDS = 20 };
 enum { CNT_CAND = 0, CNT_REPEAT = 1, CNT_FLAGGED = 2, CNT_WORK = 3, CNT_OVERSIZED = 4, CNT_UNSORTED = 5, CNT_OVERFLOW = 6, CNT_RECORDS = 7, CNT_N = 8, CNT_EDGES = 8, CNT_TOTAL = 12 };
 
 constexpr int kFilterThreads = 1024;
@@ -145,6 +145,8 @@ struct nrp_ctx {
   int64_t opt_persistent_split = 0;       // extraction kernel: persistent CTAs with register prefetch (1) or one CTA per byte tile (0)
   int64_t opt_r1_bias = 0;                // added to the number of level-1 bits (tuning)
   int64_t opt_nvlink_digits = 128;        // direct exchange: most (owner, bucket) digits per tile the senders scatter over NVLink
+  int64_t opt_coop_group = 1;             // grouping stage as one cooperative kernel: 1 = up to 2^20 candidates (measured: no faster than
+                                          // the kernel sequence at 8e5 candidates, slower at 2e7), 2 = always, 0 = never
   int64_t opt_packed = 1;                 // one 64-bit word per record on the direct path whenever key and value fit
   int64_t opt_direct = 1;                 // fixed-region partition without a histogram pass (falls back to the exact path on overflow)
 
@@ -160,6 +162,8 @@ struct nrp_ctx {
   int64_t n_parts = 0, total_len = 0, n_tiles = 0, max_len = 0;
   int uniform_len = 0;
   bool have_parts = false, have_ids = false;
+  int coop_blocks_per_sm[2] = {0, 0};
+  bool group_counts_coop = false;
   // streamed staging: the ASCII copy is in flight on copy_stream in pieces (contiguous part ranges); pending_chunks > 0 until a
   // build (or any other consumer) has waited for them
   struct Chunk { int64_t part_lo, part_hi, tile_lo, n_tiles; cudaEvent_t landed; };
@@ -173,6 +177,7 @@ struct nrp_ctx {
   DevBuf flags, hist, leaf_off, cursor1, cursor2, seg_off, tile_prefix, tile_desc, region_ends, counters, scan_scratch, lsd_scratch;
   DevBuf keysA, valsA, keysB, valsB, cand_keys_buf, cand_vals_buf;
   DevBuf head, head_scan, group_start, valid, valid_scan, mem_cnt, mem_scan, pair_cnt, pair_scan;
+  DevBuf g_member_end;
   DevBuf g_keys, g_indptr, g_pair_off, g_members, g_first_part, g_first_window, last_single;
   DevBuf e_codesA, e_codesB, e_head, e_head_scan, e_u, e_v, e_u_alt, e_v_alt, shared_keysA, shared_keysB;
   unsigned long long* h_counters = nullptr;   // pinned
@@ -321,6 +326,7 @@ int configure_kernels(nrp_ctx* c) {
 extern "C" {
 
 int nrp_version(void) { return 100; }
+int64_t nrp_launches_total(void) { return launch_total(); }
 const char* nrp_last_error(void) { return g_last_error.c_str(); }
 
 int nrp_ctx_create(int device, nrp_ctx** out) {
@@ -336,7 +342,7 @@ int nrp_ctx_create(int device, nrp_ctx** out) {
   c->n_sms = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaHostAlloc(&c->h_counters, sizeof(unsigned long long) * 64, cudaHostAllocDefault));
-  int r = c->counters.ensure(sizeof(unsigned long long) * CNT_TOTAL);
+  int r = c->counters.ensure(sizeof(unsigned long long) * CNT_WORDS);
   if (r != NRP_OK) return r;
   *out = c;
   return NRP_OK;
@@ -349,7 +355,7 @@ int nrp_ctx_destroy(nrp_ctx* c) {
   DevBuf* all[] = {&c->bgb_ascii, &c->bgb_off, &c->bgb_tile_first, &c->bgb_keysA, &c->bgb_keysB, &c->bgb_head, &c->bgb_head_scan, &c->bg_table, &c->ascii, &c->off, &c->part_id, &c->tile_first, &c->flags, &c->hist, &c->leaf_off, &c->cursor1,
                    &c->cursor2, &c->seg_off, &c->tile_prefix, &c->tile_desc, &c->region_ends, &c->recv_ends, &c->recv_keys_d, &c->recv_vals_d, &c->fb_keys, &c->fb_vals, &c->counters, &c->scan_scratch, &c->lsd_scratch, &c->keysA, &c->valsA, &c->cand_keys_buf, &c->cand_vals_buf,
                    &c->keysB, &c->valsB, &c->head, &c->head_scan, &c->group_start, &c->valid, &c->valid_scan, &c->mem_cnt,
-                   &c->mem_scan, &c->pair_cnt, &c->pair_scan, &c->g_keys, &c->g_indptr, &c->g_pair_off, &c->g_members,
+                   &c->mem_scan, &c->pair_cnt, &c->pair_scan, &c->g_member_end, &c->g_keys, &c->g_indptr, &c->g_pair_off, &c->g_members,
                    &c->g_first_part, &c->g_first_window, &c->last_single, &c->e_codesA, &c->e_codesB, &c->e_head, &c->e_head_scan,
                    &c->e_u, &c->e_v, &c->e_u_alt, &c->e_v_alt, &c->shared_keysA, &c->shared_keysB, &c->recv_keys, &c->recv_vals};
   for (void* p : c->opened_ptrs) cudaIpcCloseMemHandle(p);
@@ -379,6 +385,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "persistent_split") c->opt_persistent_split = value > 0 ? 1 : 0;
   else if (n == "r1_bias") c->opt_r1_bias = value;
   else if (n == "nvlink_digits") c->opt_nvlink_digits = value <= 0 ? 128 : value;
+  else if (n == "coop_group") c->opt_coop_group = value < 0 ? 1 : std::min<int64_t>(value, 2);
   else if (n == "packed") c->opt_packed = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "direct") c->opt_direct = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
@@ -1121,6 +1128,7 @@ int stage_groups(nrp_ctx* c, bool drop_flagged, StageTimer& tm) {
   const size_t ng_max = (size_t)n_max / 2 + 2;
   TRY(c->g_keys.ensure(8 * ng_max)); TRY(c->g_indptr.ensure(8 * (ng_max + 1)));
   TRY(c->g_pair_off.ensure(8 * (ng_max + 1))); TRY(c->g_members.ensure(4 * (size_t)(n_max + 1)));
+  TRY(c->g_member_end.ensure(4 * (size_t)(n_max + 1)));
   TRY(c->g_first_window.ensure(4 * ng_max)); TRY(c->g_first_part.ensure(4 * ng_max));
   if (n_max == 0) {
     CU(cudaMemsetAsync(c->g_indptr.ptr, 0, 16, st));
@@ -1128,6 +1136,38 @@ int stage_groups(nrp_ctx* c, bool drop_flagged, StageTimer& tm) {
     return NRP_OK;
   }
   unsigned long long* cnt = c->counters.as<unsigned long long>();
+  if (c->opt_coop_group == 2 || (c->opt_coop_group == 1 && n_max <= (1ll << 20))) {
+    // the whole stage as one cooperative kernel (grid-wide barriers instead of ~20 launches)
+    const int64_t n_tiles = (n_max + kScanTile - 1) / kScanTile;
+    TRY(c->pair_cnt.ensure(sizeof(GroupTotals) * (size_t)(n_tiles + 2)));
+    TRY(c->mem_cnt.ensure(4 * (size_t)(n_tiles + 2)));
+    int& per_sm = c->coop_blocks_per_sm[sizeof(KeyT) == 4 ? 0 : 1];
+    if (per_sm == 0) {
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_group_coop<KeyT>, kScanThreads, 0));
+      if (per_sm < 1) return fail(NRP_E_CUDA, "cooperative grouping kernel does not fit an SM");
+    }
+    GroupCoopArgs a;
+    a.keys = c->cand_keys; a.vals = c->cand_vals; a.keys2 = c->spare_keys; a.vals2 = c->spare_vals;
+    a.n = n_max; a.j_bits = c->j_bits; a.drop_flagged = drop_flagged ? 1 : 0; a.flags = c->flags.as<uint8_t>();
+    a.head = c->head.as<uint32_t>(); a.head_scan = c->head_scan.as<uint32_t>(); a.group_start = c->group_start.as<uint32_t>();
+    a.valid = c->valid.as<uint32_t>(); a.valid_scan = c->valid_scan.as<uint32_t>();
+    a.mem_scan = c->mem_scan.as<unsigned long long>(); a.pair_scan = c->pair_scan.as<unsigned long long>();
+    a.tile_u32 = c->mem_cnt.as<uint32_t>(); a.tile_tot = c->pair_cnt.as<GroupTotals>();
+    a.out_keys = c->g_keys.as<uint64_t>(); a.out_indptr = c->g_indptr.as<int64_t>(); a.out_pair_off = c->g_pair_off.as<unsigned long long>();
+    a.out_first_window = c->g_first_window.as<uint32_t>(); a.out_members = c->g_members.as<uint32_t>();
+    a.out_member_end = c->g_member_end.as<uint32_t>();
+    a.counts = cnt + CNT_GROUP;
+    const unsigned cgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)per_sm * c->n_sms));
+    void* args[] = {&a};
+    ++launch_counter(); ++launch_total();
+    CU(cudaLaunchCooperativeKernel((void*)k_group_coop<KeyT>, dim3(cgrid), dim3(kScanThreads), args, 0, st));
+    if (drop_flagged) { std::swap(c->cand_keys, c->spare_keys); std::swap(c->cand_vals, c->spare_vals); }
+    CU(cudaMemcpyAsync(c->h_counters + 18, cnt + CNT_REPEAT, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_counters + 50, cnt + CNT_GROUP, 5 * 8, cudaMemcpyDeviceToHost, st));
+    c->group_counts_coop = true;
+    return NRP_OK;
+  }
+  c->group_counts_coop = false;
   uint32_t* n_sorted_dev = reinterpret_cast<uint32_t*>(cnt + CNT_NSORTED);
   const unsigned grid = grid_for(n_max + 1, 256);
   if (drop_flagged) {
@@ -1164,7 +1204,8 @@ int stage_groups(nrp_ctx* c, bool drop_flagged, StageTimer& tm) {
       c->g_indptr.as<int64_t>(), c->g_pair_off.as<unsigned long long>(), c->g_first_window.as<uint32_t>())));
   NRP_LAUNCH((k_group_members_n<<<grid, 256, 0, st>>>(c->cand_vals, c->head_scan.as<uint32_t>(), c->head.as<uint32_t>(),
                                                     c->group_start.as<uint32_t>(), c->valid.as<uint32_t>(),
-                                                    c->mem_scan.as<unsigned long long>(), n_sorted_dev, c->j_bits, c->g_members.as<uint32_t>())));
+                                                    c->mem_scan.as<unsigned long long>(), n_sorted_dev, c->j_bits, c->g_members.as<uint32_t>(),
+                                                    c->g_member_end.as<uint32_t>())));
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->h_counters + 18, cnt + CNT_REPEAT, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(c->h_counters + 19, n_sorted_dev, 4, cudaMemcpyDeviceToHost, st));
@@ -1177,10 +1218,17 @@ int stage_groups(nrp_ctx* c, bool drop_flagged, StageTimer& tm) {
 // after a synchronisation that follows stage_groups
 void group_counts_ready(nrp_ctx* c) {
   c->n_repeat_records = (int64_t)c->h_counters[18];
-  c->n_sorted = c->n_cand > 0 ? (int64_t)(uint32_t)c->h_counters[19] : 0;
-  c->n_groups = (int64_t)(uint32_t)c->h_counters[20];
-  c->n_members = (int64_t)c->h_counters[21];
-  c->n_pairs = (int64_t)c->h_counters[22];
+  if (c->group_counts_coop && c->n_cand > 0) {
+    c->n_sorted = (int64_t)c->h_counters[50];
+    c->n_groups = (int64_t)c->h_counters[52];
+    c->n_members = (int64_t)c->h_counters[53];
+    c->n_pairs = (int64_t)c->h_counters[54];
+  } else {
+    c->n_sorted = c->n_cand > 0 ? (int64_t)(uint32_t)c->h_counters[19] : 0;
+    c->n_groups = (int64_t)(uint32_t)c->h_counters[20];
+    c->n_members = (int64_t)c->h_counters[21];
+    c->n_pairs = (int64_t)c->h_counters[22];
+  }
   c->counts[NRP_C_GROUPS] = c->n_groups;
   c->counts[NRP_C_MEMBERS] = c->n_members;
   c->counts[NRP_C_PAIRS] = c->n_pairs;
@@ -1253,7 +1301,7 @@ int stage_edges(nrp_ctx* c, StageTimer& tm) {
   if (c->n_pairs > 0) {
     int log_slots = 0;
     TRY(edge_set_prepare(c, c->n_pairs, &log_slots));
-    NRP_LAUNCH((k_edge_pairs<<<grid_for(c->n_members, 128), 128, 0, st>>>(c->g_indptr.as<int64_t>(), c->g_members.as<uint32_t>(), c->n_groups,
+    NRP_LAUNCH((k_edge_pairs<<<grid_for(c->n_members, 128), 128, 0, st>>>(c->g_member_end.as<uint32_t>(), c->g_members.as<uint32_t>(),
                                                                       c->n_members, c->part_id.as<uint32_t>(), c->e_codesA.as<uint64_t>(),
                                                                       log_slots, c->e_u.as<uint32_t>(), c->e_v.as<uint32_t>(),
                                                                       c->counters.as<unsigned long long>() + CNT_EDGES)));

@@ -1,6 +1,7 @@
 // Kernels around the bulk path: per-part exclusion flags, background table, grouping of the sorted candidate
 // records, group ranks / last single windows for the order-exact host replay, and part-pair edge expansion.
 #pragma once
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -246,12 +247,198 @@ __global__ void k_group_emit_n(const KeyT* keys, const uint32_t* vals, int j_bit
 
 __global__ void k_group_members_n(const uint32_t* vals, const uint32_t* head_scan, const uint32_t* head, const uint32_t* group_start,
                                   const uint32_t* valid, const unsigned long long* member_scan, const uint32_t* n_ptr, int j_bits,
-                                  uint32_t* out_members) {
+                                  uint32_t* out_members, uint32_t* out_member_end) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)*n_ptr) return;
   uint32_t g = head_scan[i] + head[i] - 1u;           // run index of record i (inclusive scan - 1)
   if (!valid[g]) return;
-  out_members[member_scan[g] + (i - group_start[g])] = vals[i] >> j_bits;
+  const unsigned long long pos = member_scan[g] + (i - group_start[g]);
+  out_members[pos] = vals[i] >> j_bits;
+  // where this member's group ends in the member list (the edge expansion needs no search for it)
+  out_member_end[pos] = (uint32_t)(member_scan[g] + (group_start[g + 1] - group_start[g]));
+}
+
+// ---- the whole grouping stage as ONE cooperative kernel ---------------------------------------------------------
+// Same results as the kernel sequence above (k_keep_unflagged .. k_group_members_n): the phases are separated by grid-wide
+// barriers instead of kernel boundaries, prefix sums are tile-local + a scan of the tile totals by CTA 0, and consumers add
+// the tile offset on the fly.  ~9 grid barriers instead of ~20 launches: the stage is latency bound, not work bound.
+struct GroupCoopArgs {
+  const void* keys; const uint32_t* vals;          // ordered candidates
+  void* keys2; uint32_t* vals2;                     // compaction target (used when drop_flagged)
+  int64_t n; int j_bits; int drop_flagged; const uint8_t* flags;
+  uint32_t* head; uint32_t* head_scan; uint32_t* group_start;
+  uint32_t* valid; uint32_t* valid_scan; unsigned long long* mem_scan; unsigned long long* pair_scan;
+  uint32_t* tile_u32; GroupTotals* tile_tot;        // per-tile totals -> offsets (n_tiles + 1 entries each)
+  uint64_t* out_keys; int64_t* out_indptr; unsigned long long* out_pair_off; uint32_t* out_first_window;
+  uint32_t* out_members; uint32_t* out_member_end;
+  unsigned long long* counts;                       // [0] records kept [1] key runs [2] groups [3] members [4] pairs
+};
+
+// exclusive scan of n_tiles per-tile totals in place by one CTA; returns the grand total to every thread
+__device__ __forceinline__ uint32_t cta_scan_tiles_u32(uint32_t* t, int64_t n_tiles, uint32_t* ws) {
+  const int64_t per = (n_tiles + blockDim.x - 1) / blockDim.x;
+  const int64_t t0 = (int64_t)threadIdx.x * per, t1 = t0 + per < n_tiles ? t0 + per : n_tiles;
+  uint32_t sum = 0;
+  for (int64_t i = t0; i < t1; ++i) sum += t[i];
+  uint32_t total;
+  uint32_t run = block_exclusive_scan<uint32_t>(sum, ws, total);
+  for (int64_t i = t0; i < t1; ++i) { const uint32_t v = t[i]; t[i] = run; run += v; }
+  return total;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kScanThreads) k_group_coop(GroupCoopArgs a) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint32_t ws32[33];
+  __shared__ unsigned long long ws64[33];
+  const int64_t n = a.n;
+  const int64_t n_tiles = (n + kScanTile - 1) / kScanTile;
+  const KeyT* K = reinterpret_cast<const KeyT*>(a.keys);
+  const uint32_t* V = a.vals;
+  int64_t n_kept = n;
+
+  if (a.drop_flagged) {
+    // A1: keep[i] = the record's part does not carry the repeat flag; tile-local scan, tile totals
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int64_t base = t * kScanTile + (int64_t)threadIdx.x * kScanItems;
+      uint32_t keep[kScanItems], sum = 0;
+#pragma unroll
+      for (int i = 0; i < kScanItems; ++i) {
+        const int64_t idx = base + i;
+        keep[i] = (idx < n && !(a.flags[V[idx] >> a.j_bits] & kFlagRepeat)) ? 1u : 0u;
+        sum += keep[i];
+      }
+      uint32_t total;
+      uint32_t run = block_exclusive_scan<uint32_t>(sum, ws32, total);
+#pragma unroll
+      for (int i = 0; i < kScanItems; ++i) {
+        const int64_t idx = base + i;
+        if (idx < n) { a.valid[idx] = keep[i]; a.valid_scan[idx] = run; }
+        run += keep[i];
+      }
+      if (threadIdx.x == 0) a.tile_u32[t] = total;
+    }
+    grid.sync();
+    if (blockIdx.x == 0) {
+      const uint32_t total = cta_scan_tiles_u32(a.tile_u32, n_tiles, ws32);
+      if (threadIdx.x == 0) { a.tile_u32[n_tiles] = total; a.counts[0] = total; }
+    }
+    grid.sync();
+    n_kept = (int64_t)a.tile_u32[n_tiles];
+    // A2: compaction (order preserved)
+    KeyT* K2 = reinterpret_cast<KeyT*>(a.keys2);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+      if (a.valid[idx]) {
+        const uint32_t dst = a.tile_u32[idx / kScanTile] + a.valid_scan[idx];
+        K2[dst] = K[idx];
+        a.vals2[dst] = V[idx];
+      }
+    }
+    grid.sync();
+    K = K2; V = a.vals2;
+  } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.counts[0] = (unsigned long long)n;
+  }
+
+  // B: key-run heads of the kept records, tile-local scan, tile totals
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t base = t * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    uint32_t h[kScanItems], sum = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+      const int64_t idx = base + i;
+      h[i] = (idx < n_kept && (idx == 0 || K[idx] != K[idx - 1])) ? 1u : 0u;
+      sum += h[i];
+    }
+    uint32_t total;
+    uint32_t run = block_exclusive_scan<uint32_t>(sum, ws32, total);
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+      const int64_t idx = base + i;
+      if (idx < n) { a.head[idx] = h[i]; a.head_scan[idx] = run; }
+      run += h[i];
+    }
+    if (threadIdx.x == 0) a.tile_u32[t] = total;
+  }
+  grid.sync();
+  if (blockIdx.x == 0) {
+    const uint32_t total = cta_scan_tiles_u32(a.tile_u32, n_tiles, ws32);
+    if (threadIdx.x == 0) { a.tile_u32[n_tiles] = total; a.counts[1] = total; }
+  }
+  grid.sync();
+  const int64_t n_runs = (int64_t)a.tile_u32[n_tiles];
+  // C: start of every key run (+ the sentinel)
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx <= n_kept; idx += (int64_t)gridDim.x * blockDim.x) {
+    if (idx == n_kept) a.group_start[n_runs] = (uint32_t)n_kept;
+    else if (a.head[idx]) a.group_start[a.tile_u32[idx / kScanTile] + a.head_scan[idx]] = (uint32_t)idx;
+  }
+  grid.sync();
+  // D: per run validity / members / pairs, tile-local scans, tile totals
+  const int64_t r_tiles = (n_runs + kScanTile - 1) / kScanTile;
+  for (int64_t t = blockIdx.x; t < r_tiles; t += gridDim.x) {
+    const int64_t base = t * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems]; unsigned long long m[kScanItems], p[kScanItems];
+    uint32_t sv = 0; unsigned long long sm = 0, sp = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+      run_size_values(a.group_start, base + i, n_runs, v[i], m[i], p[i]);
+      sv += v[i]; sm += m[i]; sp += p[i];
+    }
+    uint32_t tv; unsigned long long tm, tp;
+    uint32_t rv = block_exclusive_scan<uint32_t>(sv, ws32, tv);
+    unsigned long long rm = block_exclusive_scan<unsigned long long>(sm, ws64, tm);
+    unsigned long long rp = block_exclusive_scan<unsigned long long>(sp, ws64, tp);
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+      const int64_t g = base + i;
+      if (g < n_runs) { a.valid[g] = v[i]; a.valid_scan[g] = rv; a.mem_scan[g] = rm; a.pair_scan[g] = rp; }
+      rv += v[i]; rm += m[i]; rp += p[i];
+    }
+    if (threadIdx.x == 0) a.tile_tot[t] = GroupTotals{tv, tm, tp};
+  }
+  grid.sync();
+  if (blockIdx.x == 0) {
+    const int64_t per = (r_tiles + blockDim.x - 1) / blockDim.x;
+    const int64_t t0 = (int64_t)threadIdx.x * per, t1 = t0 + per < r_tiles ? t0 + per : r_tiles;
+    uint32_t sv = 0; unsigned long long sm = 0, sp = 0;
+    for (int64_t t = t0; t < t1; ++t) { sv += a.tile_tot[t].valid; sm += a.tile_tot[t].members; sp += a.tile_tot[t].pairs; }
+    uint32_t tv; unsigned long long tm, tp;
+    uint32_t rv = block_exclusive_scan<uint32_t>(sv, ws32, tv);
+    unsigned long long rm = block_exclusive_scan<unsigned long long>(sm, ws64, tm);
+    unsigned long long rp = block_exclusive_scan<unsigned long long>(sp, ws64, tp);
+    for (int64_t t = t0; t < t1; ++t) {
+      const GroupTotals cur = a.tile_tot[t];
+      a.tile_tot[t] = GroupTotals{rv, rm, rp};
+      rv += cur.valid; rm += cur.members; rp += cur.pairs;
+    }
+    if (threadIdx.x == 0) {
+      a.counts[2] = tv; a.counts[3] = tm; a.counts[4] = tp;
+      a.out_indptr[tv] = (int64_t)tm;
+      a.out_pair_off[tv] = tp;
+    }
+  }
+  grid.sync();
+  // E: groups (keys, CSR offsets, first windows) and their members
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_runs; g += (int64_t)gridDim.x * blockDim.x) {
+    if (!a.valid[g]) continue;
+    const GroupTotals off = a.tile_tot[g / kScanTile];
+    const uint32_t o = off.valid + a.valid_scan[g];
+    const uint32_t first = a.group_start[g];
+    a.out_keys[o] = (uint64_t)K[first];
+    if (a.j_bits) a.out_first_window[o] = V[first] & ((1u << a.j_bits) - 1u);
+    a.out_indptr[o] = (int64_t)(off.members + a.mem_scan[g]);
+    a.out_pair_off[o] = off.pairs + a.pair_scan[g];
+  }
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_kept; idx += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t g = a.tile_u32[idx / kScanTile] + a.head_scan[idx] + a.head[idx] - 1u;      // run of record idx
+    if (!a.valid[g]) continue;
+    const uint32_t first = a.group_start[g], size = a.group_start[g + 1] - first;
+    const unsigned long long gbase = a.tile_tot[g / kScanTile].members + a.mem_scan[g];
+    const unsigned long long pos = gbase + (idx - first);
+    a.out_members[pos] = V[idx] >> a.j_bits;
+    a.out_member_end[pos] = (uint32_t)(gbase + size);
+  }
 }
 
 // ---- order information for the host replay ----------------------------------------------------
@@ -337,16 +524,11 @@ __device__ __forceinline__ void edge_insert(uint32_t ida, uint32_t idb, uint64_t
 }
 
 // one thread per member a of a group: pairs (a, b > a)
-__global__ void k_edge_pairs(const int64_t* indptr, const uint32_t* members, int64_t n_groups, int64_t n_members, const uint32_t* part_id,
+__global__ void k_edge_pairs(const uint32_t* member_end, const uint32_t* members, int64_t n_members, const uint32_t* part_id,
                              uint64_t* table, int log_slots, uint32_t* out_u, uint32_t* out_v, unsigned long long* n_out) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_members) return;
-  int64_t lo = 0, hi = n_groups;                      // last group with indptr <= t
-  while (hi - lo > 1) {
-    int64_t mid = (lo + hi) >> 1;
-    if (indptr[mid] <= t) lo = mid; else hi = mid;
-  }
-  const int64_t end = indptr[lo + 1];
+  const int64_t end = (int64_t)member_end[t];
   const uint32_t ida = part_id[members[t]];
   for (int64_t b = t + 1; b < end; ++b) edge_insert(ida, part_id[members[b]], table, log_slots, out_u, out_v, n_out);
 }

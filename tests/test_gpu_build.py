@@ -112,6 +112,10 @@ def test_forced_paths(ctx):
         _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
         ctx.set_option('pass_records', 0)
         ctx.set_option('direct', -1)
+        ctx.set_option('coop_group', 0)               # grouping as a kernel sequence instead of one cooperative kernel
+        _compare(_run(ctx, uniq, 13, False), uniq, 13, False)
+        _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
+        ctx.set_option('coop_group', -1)
         ctx.set_option('no_bloom', 1)                 # exact table on every record instead of the two-stage filter
         _compare(_run(ctx, uniq, 13, False), uniq, 13, False)
         ctx.set_option('no_bloom', 0)
@@ -120,6 +124,7 @@ def test_forced_paths(ctx):
         uniq17 = _long_parts(cases.planted_parts(600, 77), 17)
         _compare(_run(ctx, uniq17, 17, True), uniq17, 17, True)
     finally:
+        ctx.set_option('coop_group', -1)
         ctx.set_option('direct', -1)
         ctx.set_option('no_window_carry', 0)
         ctx.set_option('no_bloom', 0)
