@@ -214,7 +214,9 @@ def main():
     ap.add_argument('--reference-parts', type=int, default=20_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-edges', action='store_true')
-    ap.add_argument('--h2d-chunks', type=int, default=1, help='e2e leg: pieces of the streamed host-to-device copy (1 = one blocking copy)')
+    ap.add_argument('--h2d-chunks', type=int, default=8, help='e2e leg: pieces of the streamed host-to-device copy (1 = one blocking copy)')
+    ap.add_argument('--e2e-entry', choices=('auto', 'offsets', 'uniform'), default='auto',
+                    help='e2e leg: nrp_load_parts[_streamed] with an offsets array, or nrp_load_parts_uniform (parts of one length; auto = uniform when the config has one length)')
     ap.add_argument('--opt', action='append', default=[], help='library tuning knob name=value (nrp_ctx_set_option), repeatable')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else max(args.warmup, 0)
@@ -294,11 +296,16 @@ def main():
     e2e_times = []
     e2e_parts = []
     h2d = d2h = 0
+    uniform_entry = args.e2e_entry == 'uniform' or (args.e2e_entry == 'auto' and not isinstance(cfg['length'], tuple))
+    host_ids = torch.from_numpy(ids.copy()).pin_memory()
     for step in range(2 + args.steps):
         flush.fill_(1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        ctx.load_parts(host_ascii.numpy(), off, ids, chunks=args.h2d_chunks)
+        if uniform_entry:
+            ctx.load_parts_uniform(host_ascii.numpy(), cfg['n'], cfg['length'], host_ids.numpy(), chunks=args.h2d_chunks)
+        else:
+            ctx.load_parts(host_ascii.numpy(), off, ids, chunks=args.h2d_chunks)
         t1 = time.perf_counter()
         ctx.build(k, cfg['internal_repeats'], want_edges)
         t2 = time.perf_counter()
@@ -352,7 +359,9 @@ def main():
                     'ms_per_step': 1e3 * sum(e2e_times) / len(e2e_times),
                     'ms_load_build_fetch': [1e3 * sum(p[i] for p in e2e_parts) / len(e2e_parts) for i in range(3)],
                     'h2d_chunks': args.h2d_chunks,
-                    'path': 'C ABI: nrp_load_parts (page-locked host buffers; --h2d-chunks > 1: nrp_load_parts_streamed, measured no faster: the 49-53 GB/s copy is the floor) + nrp_build + nrp_result_host'},
+                    'path': 'C ABI, page-locked host buffers: ' + ('nrp_load_parts_uniform (no offsets array; {} piece(s), copies only enqueued when > 1)'.format(args.h2d_chunks)
+                                                                  if uniform_entry else ('nrp_load_parts_streamed' if args.h2d_chunks > 1 else 'nrp_load_parts')) +
+                            ' + nrp_build + nrp_result_host'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
             'stage_ms': {name: v / args.steps for name, v in stage_ms.items()},
             'result': {name: counts[name] for name in ('records', 'excluded', 'groups', 'members', 'edges', 'candidates', 'runs', 'buckets', 'oversized',

@@ -127,6 +127,14 @@ int nrp_load_parts(nrp_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, c
 int nrp_load_parts_streamed(nrp_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, const uint32_t* part_id, int64_t n_parts,
                             int n_chunks);
 
+/* Parts that all have the same length (the BASELINE shapes; the host layer knows this from joining the strings): no offsets
+ * array -- part i is ascii[i * part_len, (i + 1) * part_len) and the offsets are generated on the device -- so nothing is swept
+ * or staged on the host and the call returns as soon as the copies are enqueued (n_chunks > 1, page-locked `ascii`; `part_id`
+ * is copied from where it lies when it is page-locked too, else through the library's staging buffer).  The next nrp_build
+ * extracts each piece as it lands: the host-to-device copy overlaps the first split.  n_chunks == 1 is a blocking load.
+ * Lifetime of `ascii` (and of a page-locked `part_id`) as for nrp_load_parts_streamed. */
+int nrp_load_parts_uniform(nrp_ctx* ctx, const uint8_t* ascii, int64_t n_parts, int part_len, const uint32_t* part_id, int n_chunks);
+
 /* Build the repeat structure of the staged parts.
  *   internal_repeats 0: exclude parts with internal direct/inverted repeats or palindromic windows
  *   want_edges       != 0: also expand groups into the distinct (id_u < id_v) edges

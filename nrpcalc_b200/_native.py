@@ -63,6 +63,7 @@ def _declare(lib):
         'nrp_bg_build_fetch': (c_ctx, ptr),
         'nrp_load_parts': (c_ctx, ptr, ptr, ptr, i64, i32),
         'nrp_load_parts_streamed': (c_ctx, ptr, ptr, ptr, i64, i32),
+        'nrp_load_parts_uniform': (c_ctx, ptr, i64, i32, ptr, i32),
         'nrp_build': (c_ctx, i32, i32, i32),
         'nrp_result_counts': (c_ctx, ptr),
         'nrp_result_timings': (c_ctx, ptr),
@@ -197,6 +198,18 @@ class Context(object):
         else:
             _check(self._lib, self._lib.nrp_load_parts(self._h, src, _p(offsets), _p(part_id), n_parts, on_device))
         self.n_parts = n_parts
+
+    def load_parts_uniform(self, ascii_buf, n_parts, part_len, part_id=None, chunks=8):
+        """Parts of one length in a page-locked uint8 host array: no offsets, copies only enqueued (nrp_load_parts_uniform);
+        the context keeps references to the arrays until the next build has returned."""
+        ascii_buf = np.ascontiguousarray(ascii_buf, dtype=np.uint8)
+        assert ascii_buf.size >= int(n_parts) * int(part_len)
+        if part_id is not None:
+            part_id = np.ascontiguousarray(part_id, dtype=np.uint32)
+            assert part_id.size == n_parts
+        self._keep = (ascii_buf, part_id)
+        _check(self._lib, self._lib.nrp_load_parts_uniform(self._h, _p(ascii_buf), int(n_parts), int(part_len), _p(part_id), int(chunks)))
+        self.n_parts = int(n_parts)
 
     def build(self, k, internal_repeats, want_edges=True):
         _check(self._lib, self._lib.nrp_build(self._h, int(k), 1 if internal_repeats else 0, 1 if want_edges else 0))

@@ -171,7 +171,6 @@ struct nrp_ctx {
   cudaStream_t copy_stream = nullptr;
   int pending_chunks = 0;
   uint32_t part_base = 0;
-  int64_t max_id = 0;
 
   // pipeline buffers
   DevBuf flags, hist, leaf_off, cursor1, cursor2, seg_off, tile_prefix, tile_desc, region_ends, counters, scan_scratch, lsd_scratch;
@@ -500,16 +499,21 @@ int nrp_bg_build_fetch(nrp_ctx* c, uint64_t* keys_out) {
   return NRP_OK;
 }
 
+// uniform_hint > 0: every part has exactly this many bytes and `offsets` is NULL (nothing to validate or to stage: part i
+// starts at i * uniform_hint)
 static int load_parts_impl(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, const uint32_t* part_id, int64_t n_parts, int ascii_on_device,
-                           int n_chunks) {
+                           int n_chunks, int64_t uniform_hint = 0) {
   if (!c) return fail(NRP_E_ARG, "null context");
-  if (n_parts < 0 || !offsets || (n_parts > 0 && !ascii && offsets[n_parts] > 0)) return fail(NRP_E_ARG, "bad part buffers");
+  const bool hinted = uniform_hint > 0;
+  if (n_parts < 0 || (!hinted && !offsets) || (hinted && uniform_hint >= ((int64_t)1 << 30))) return fail(NRP_E_ARG, "bad part buffers");
   if (n_parts >= 0xfffffff0ll) return fail(NRP_E_UNSUPPORTED, "more than 2^32-16 parts");
+  if (!hinted && offsets[0] != 0) return fail(NRP_E_ARG, "offsets[0] must be 0");
+  const int64_t total = hinted ? n_parts * uniform_hint : offsets[n_parts];
+  if (total < 0) return fail(NRP_E_ARG, "negative total length");
+  if (n_parts > 0 && !ascii && total > 0) return fail(NRP_E_ARG, "bad part buffers");
   CU(cudaSetDevice(c->device));
   c->have_parts = false; c->have_result = false;
-  if (offsets[0] != 0) return fail(NRP_E_ARG, "offsets[0] must be 0");
-  const int64_t total = offsets[n_parts];
-  if (total < 0) return fail(NRP_E_ARG, "negative total length");
+  auto first_byte = [&](int64_t part) -> int64_t { return hinted ? part * uniform_hint : offsets[part]; };
   // the big copy goes first: the DMA runs while the host validates the offsets and stages the small arrays
   const int64_t n_tiles = (total + kTileBytes - 1) / kTileBytes;
   const size_t padded = (size_t)n_tiles * kTileBytes + 256;
@@ -531,11 +535,11 @@ static int load_parts_impl(nrp_ctx* c, const uint8_t* ascii, const int64_t* offs
       int64_t p_hi = n_parts;
       if (i + 1 < n_chunks) {
         const int64_t target = total / n_chunks * (i + 1);
-        p_hi = std::lower_bound(offsets + p_lo + 1, offsets + n_parts, target) - offsets;
+        p_hi = hinted ? (target + uniform_hint - 1) / uniform_hint : std::lower_bound(offsets + p_lo + 1, offsets + n_parts, target) - offsets;
         if (p_hi <= p_lo) p_hi = p_lo + 1;
         if (p_hi > n_parts) p_hi = n_parts;
       }
-      const int64_t b_lo = offsets[p_lo], b_hi = offsets[p_hi];
+      const int64_t b_lo = first_byte(p_lo), b_hi = first_byte(p_hi);
       if ((size_t)used >= c->chunks.size()) { nrp_ctx::Chunk ch{}; CU(cudaEventCreateWithFlags(&ch.landed, cudaEventDisableTiming)); c->chunks.push_back(ch); }
       nrp_ctx::Chunk& ch = c->chunks[used++];
       ch.part_lo = p_lo; ch.part_hi = p_hi;
@@ -547,19 +551,29 @@ static int load_parts_impl(nrp_ctx* c, const uint8_t* ascii, const int64_t* offs
     }
     c->pending_chunks = used;
   }
-  // offsets + ids travel through one page-locked staging buffer (the caller's arrays are usually pageable)
+  // offsets + ids travel through one page-locked staging buffer (the caller's arrays are usually pageable; ids that already
+  // are page-locked are copied from where they lie)
+  bool ids_pinned = false;
+  if (part_id && n_parts > 0) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, part_id) == cudaSuccess) ids_pinned = attr.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+  }
   const size_t off_bytes = sizeof(int64_t) * (size_t)(n_parts + 1), id_bytes = part_id ? sizeof(uint32_t) * (size_t)n_parts : 0;
-  TRY(c->h_upload.ensure(off_bytes + id_bytes + 16));
+  const size_t off_stage = hinted ? 0 : off_bytes;
+  TRY(c->h_upload.ensure(off_stage + (ids_pinned ? 0 : id_bytes) + 16));
   int64_t* st_off = c->h_upload.as<int64_t>();
-  uint32_t* st_id = reinterpret_cast<uint32_t*>(c->h_upload.as<unsigned char>() + off_bytes);
+  uint32_t* st_id = reinterpret_cast<uint32_t*>(c->h_upload.as<unsigned char>() + off_stage);
   // shortest / longest part in one branch-free sweep (the compiler vectorises it), then one memcpy into the staging buffer,
   // which also serves as the context's host copy of the offsets until the next batch
   int64_t min_len = n_parts > 0 ? INT64_MAX : 0, max_len = n_parts > 0 ? INT64_MIN : 0;
-  for (int64_t i = 0; i < n_parts; ++i) {
-    const int64_t len = offsets[i + 1] - offsets[i];
-    min_len = len < min_len ? len : min_len;
-    max_len = len > max_len ? len : max_len;
-  }
+  if (hinted) min_len = max_len = n_parts > 0 ? uniform_hint : 0;
+  else
+    for (int64_t i = 0; i < n_parts; ++i) {
+      const int64_t len = offsets[i + 1] - offsets[i];
+      min_len = len < min_len ? len : min_len;
+      max_len = len > max_len ? len : max_len;
+    }
   if (min_len < 0) {
     cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
@@ -580,14 +594,20 @@ static int load_parts_impl(nrp_ctx* c, const uint8_t* ascii, const int64_t* offs
   c->n_parts = n_parts; c->total_len = total; c->uniform_len = uniform; c->max_len = max_len;
   c->n_tiles = n_tiles;
   c->have_ids = part_id != nullptr;
-  c->max_id = 0;
   if (part_id && n_parts > 0) {
-    uint32_t mx = 0;
-    for (int64_t i = 0; i < n_parts; ++i) mx = part_id[i] > mx ? part_id[i] : mx;
-    memcpy(st_id, part_id, id_bytes);
-    c->max_id = mx;
+    const uint32_t* src = part_id;
+    if (!ids_pinned) { memcpy(st_id, part_id, id_bytes); src = st_id; }
     TRY(c->part_id.ensure(id_bytes));
-    CU(cudaMemcpyAsync(c->part_id.ptr, st_id, id_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (streamed) {
+      // behind the pieces on the copy stream (the ids are read last, by the edge expansion); an empty piece carries the event
+      if ((size_t)c->pending_chunks >= c->chunks.size()) { nrp_ctx::Chunk ch{}; CU(cudaEventCreateWithFlags(&ch.landed, cudaEventDisableTiming)); c->chunks.push_back(ch); }
+      nrp_ctx::Chunk& ch = c->chunks[c->pending_chunks++];
+      ch.part_lo = ch.part_hi = n_parts; ch.tile_lo = 0; ch.n_tiles = 0;
+      CU(cudaMemcpyAsync(c->part_id.ptr, src, id_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+      CU(cudaEventRecord(ch.landed, c->copy_stream));
+    } else {
+      CU(cudaMemcpyAsync(c->part_id.ptr, src, id_bytes, cudaMemcpyHostToDevice, c->stream));
+    }
   }
   TRY(c->tile_first.ensure(sizeof(uint32_t) * (size_t)(c->n_tiles + 2)));
   if (uniform == 0 && n_parts > 0)
@@ -610,6 +630,12 @@ int nrp_load_parts(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, con
 int nrp_load_parts_streamed(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, const uint32_t* part_id, int64_t n_parts, int n_chunks) {
   if (n_chunks < 1 || n_chunks > 64) return fail(NRP_E_ARG, "n_chunks must be in [1, 64]");
   return load_parts_impl(c, ascii, offsets, part_id, n_parts, 0, n_chunks);
+}
+
+int nrp_load_parts_uniform(nrp_ctx* c, const uint8_t* ascii, int64_t n_parts, int part_len, const uint32_t* part_id, int n_chunks) {
+  if (n_chunks < 1 || n_chunks > 64) return fail(NRP_E_ARG, "n_chunks must be in [1, 64]");
+  if (part_len < 1) return fail(NRP_E_ARG, "part_len must be positive");
+  return load_parts_impl(c, ascii, nullptr, part_id, n_parts, 0, n_chunks, part_len);
 }
 
 }  // extern "C"

@@ -229,3 +229,28 @@ def test_streamed_staging(ctx):
             ctx.set_option('direct', -1)
         ctx.build(k, internal, want_edges=True)
         _compare(ctx.fetch(), uniq, k, internal)
+
+
+def test_uniform_streamed_staging(ctx):
+    """nrp_load_parts_uniform: parts of one length, no offsets array, ids page-locked or pageable, copies only enqueued."""
+    import torch
+    from nrpcalc_b200 import _native
+    for k, internal, parts in ((13, False, cases.planted_parts(1500, 23) + cases.random_parts(3000, 100, 18)),
+                               (16, False, cases.palindrome_parts(5, n_parts=400, k=16) + cases.random_parts(2000, 100, 19)),
+                               (17, True, cases.random_parts(5000, 100, 20))):
+        uniq = [(pid, s) for pid, s in _long_parts(parts, k) if len(s) == 100]
+        seqs = [s for _, s in uniq]
+        ids = np.array([pid for pid, _ in uniq], dtype=np.uint32)
+        pinned = torch.from_numpy(np.frombuffer(''.join(seqs).encode(), dtype=np.uint8).copy()).pin_memory()
+        pinned_ids = torch.from_numpy(ids.copy()).pin_memory()
+        for chunks, id_array in ((1, ids), (3, ids), (8, pinned_ids.numpy()), (64, pinned_ids.numpy())):
+            ctx.set_background(None, 0)
+            ctx.load_parts_uniform(pinned.numpy(), len(seqs), 100, id_array, chunks=chunks)
+            ctx.build(k, internal, want_edges=True)
+            _compare(ctx.fetch(), uniq, k, internal)
+        ctx.load_parts_uniform(pinned.numpy(), len(seqs), 100, pinned_ids.numpy(), chunks=4)     # a second build of the same batch
+        ctx.build(k, internal, want_edges=True)
+        ctx.build(k, internal, want_edges=True)
+        _compare(ctx.fetch(), uniq, k, internal)
+    with pytest.raises(_native.NativeError):
+        ctx.load_parts_uniform(np.zeros(16, dtype=np.uint8), 4, 0, None, chunks=2)
