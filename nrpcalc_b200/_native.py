@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libnrpb200.so')
+# NRPCALC_B200_LIB selects another build of the same library (A/B kernel variants, tools/build_variants.sh)
+LIB_PATH = os.environ.get('NRPCALC_B200_LIB') or os.path.join(_HERE, 'libnrpb200.so')
 
 N_COUNTS = 16
 N_TIMINGS = 16

@@ -22,6 +22,18 @@
 #include <type_traits>
 #include "common.cuh"
 
+// A/B switches of the split kernels (tools/build_variants.sh builds one library per combination; measured on config 2,
+// profiles/README.md: LATE -0.018 ms split1 / -0.013 ms split2, DUMP + EARLY another -0.011 ms split2)
+#ifndef NRP_V_DUMP
+#define NRP_V_DUMP 1         // split2: slots past the end of a tile count in per-lane dump counters instead of branching
+#endif
+#ifndef NRP_V_EARLY
+#define NRP_V_EARLY 1        // the cursor claims are issued before the scan of the bucket counts (they only need the counts)
+#endif
+#ifndef NRP_V_LATE
+#define NRP_V_LATE 1         // ... and their results are consumed after the reorder stores: the round trip to L2 overlaps both
+#endif
+
 namespace nrp {
 
 constexpr int kSplitThreads = kTileThreads;     // 512
@@ -40,7 +52,7 @@ struct alignas(16) SplitSmem {
   KeyT keys[kSplitTile];
   uint32_t vals[PACKED ? 4 : kSplitTile];
   uint16_t dig[kSplitTile];          // bucket of the record at this position of the reordered tile
-  uint32_t cnt[kLevelBuckets];
+  uint32_t cnt[kLevelBuckets + 32];  // + one dump counter per lane: register slots without a record count there (no branch)
   uint32_t base[kLevelBuckets];
   uint32_t delta[kLevelBuckets];     // global position of the bucket's run minus its position in the tile (kNoSpace: region full)
   uint32_t warp_sums[40];
@@ -86,6 +98,9 @@ __device__ __forceinline__ void split_reorder(SplitSmem<KeyT, PACKED>& s, const 
   constexpr int kWarps = kSplitThreads / 32;
   // exclusive scan of cnt[0..nb) by the first nb threads (nb <= kLevelBuckets <= blockDim)
   uint32_t c = (int)threadIdx.x < nb ? s.cnt[threadIdx.x] : 0u;
+  const bool claims = c != 0;
+  uint32_t g = 0;
+  if (NRP_V_EARLY && claims) g = atomicAdd(&cursor[threadIdx.x], c);
   uint32_t inc = c;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -106,18 +121,21 @@ __device__ __forceinline__ void split_reorder(SplitSmem<KeyT, PACKED>& s, const 
     if (lane == kWarps - 1) s.total = tin;
   }
   __syncthreads();
-  if ((int)threadIdx.x < nb) {
-    const uint32_t base = s.warp_sums[wid] + inc - c;
-    s.base[threadIdx.x] = base;
-    if (c) {
-      uint32_t g = atomicAdd(&cursor[threadIdx.x], c);
-      uint32_t dl = g - base + (uint32_t)kSplitTile;     // biased by the tile size: never wraps, never equals kNoSpace
-      if (lim.cap) {
-        const uint64_t end = lim.ends ? (uint64_t)lim.ends[threadIdx.x] : (uint64_t)(lim.first + threadIdx.x + 1u) * lim.cap;
-        if ((uint64_t)g + c > end) { dl = kNoSpace; *lim.overflow = 1u; }
-      }
-      s.delta[threadIdx.x] = dl;
+  // one atomic per (tile, bucket) claims the run's place; its result is needed by the flush only, so (NRP_V_LATE) it is
+  // consumed after the reorder stores and the round trip to L2 overlaps them
+  const uint32_t base = s.warp_sums[wid] + inc - c;
+  auto publish = [&]() {
+    uint32_t dl = g - base + (uint32_t)kSplitTile;     // biased by the tile size: never wraps, never equals kNoSpace
+    if (lim.cap) {
+      const uint64_t end = lim.ends ? (uint64_t)lim.ends[threadIdx.x] : (uint64_t)(lim.first + threadIdx.x + 1u) * lim.cap;
+      if ((uint64_t)g + c > end) { dl = kNoSpace; *lim.overflow = 1u; }
     }
+    s.delta[threadIdx.x] = dl;
+  };
+  if ((int)threadIdx.x < nb) s.base[threadIdx.x] = base;
+  if (claims) {
+    if (!NRP_V_EARLY) g = atomicAdd(&cursor[threadIdx.x], c);
+    if (!NRP_V_LATE) publish();
   }
   __syncthreads();
 #pragma unroll
@@ -130,6 +148,7 @@ __device__ __forceinline__ void split_reorder(SplitSmem<KeyT, PACKED>& s, const 
       s.dig[pos] = (uint16_t)d;
     }
   }
+  if (NRP_V_LATE && claims) publish();
   __syncthreads();
 }
 
@@ -359,11 +378,19 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split_from_records(const K
     for (int e = 0; e < kSplitItems; ++e) {
       uint32_t idx = start + threadIdx.x + e * kSplitThreads;
       dr[e] = 0xffffffffu;
-      if (idx < end) {
-        if (PACKED) {                      // the digit is a bit field of the record: hash bits [n - r_done - r2, n - r_done)
+      if (PACKED && NRP_V_DUMP) {          // the digit is a bit field of the record: hash bits [n - r_done - r2, n - r_done)
+        // branch-free: slots past the end of the tile count in the lane's dump counter
+        const bool ok = idx < end;
+        const uint32_t d = (uint32_t)((uint64_t)key[e] >> packed_shift) & mask;
+        const uint32_t rank = atomicAdd(&s.cnt[ok ? d : (uint32_t)kLevelBuckets + (threadIdx.x & 31u)], 1u);
+        dr[e] = ok ? ((d << 16) | rank) : 0xffffffffu;
+      } else if (PACKED) {
+        if (idx < end) {
           const uint32_t d = (uint32_t)((uint64_t)key[e] >> packed_shift) & mask;
           dr[e] = (d << 16) | atomicAdd(&s.cnt[d], 1u);
-        } else {
+        }
+      } else if (idx < end) {
+        {
           const uint64_t h = key_hash((uint64_t)key[e]);
           if (!PASSES || sel.accept(h)) {
             uint32_t d = (uint32_t)(h >> (64 - r_done - r2)) & mask;
