@@ -95,7 +95,7 @@ int nrp_ctx_destroy(nrp_ctx* ctx);
 int nrp_ctx_device(nrp_ctx* ctx);
 
 /* Tuning knobs used by the tests to force rarely taken paths: name in
- * {"filter_cap", "leaf_target", "max_level_bits", "max_pairs", "no_window_carry", "no_bloom", "pass_records", "direct", "packed", "persistent_split", "r1_bias", "nvlink_digits", "coop_group"};
+ * {"filter_cap", "leaf_target", "max_level_bits", "max_pairs", "no_window_carry", "no_bloom", "pass_records", "direct", "packed", "persistent_split", "r1_bias", "nvlink_digits", "coop_group", "filter_tiny"};
  * value <= 0 restores the default ("direct": 0 forces the exact histogram path, negative restores the default 1;
  * "coop_group": 0 = grouping as a kernel sequence, 1 = one cooperative kernel up to 2^20 candidates (default), 2 = always). */
 int nrp_ctx_set_option(nrp_ctx* ctx, const char* name, int64_t value);

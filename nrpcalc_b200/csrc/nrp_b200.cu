@@ -145,6 +145,7 @@ struct nrp_ctx {
   int64_t opt_persistent_split = 0;       // extraction kernel: persistent CTAs with register prefetch (1) or one CTA per byte tile (0)
   int64_t opt_r1_bias = 0;                // added to the number of level-1 bits (tuning)
   int64_t opt_nvlink_digits = 128;        // direct exchange: most (owner, bucket) digits per tile the senders scatter over NVLink
+  int64_t opt_filter_tiny = 0;            // packed leaves that average <= 1400 records: four 256-thread filter CTAs per SM (pair with leaf_target <= 1400)
   int64_t opt_coop_group = 1;             // grouping stage as one cooperative kernel: 1 = up to 2^20 candidates (measured: no faster than
                                           // the kernel sequence at 8e5 candidates, slower at 2e7), 2 = always, 0 = never
   int64_t opt_packed = 1;                 // one 64-bit word per record on the direct path whenever key and value fit
@@ -301,6 +302,8 @@ int configure_kernels(nrp_ctx* c) {
                           (int)filter_bloom_smem<(int)sizeof(KeyT), false, 8192, 4096, 1024>()));
   CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, 512, 8, 2048, 2, 512, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)filter_bloom_smem<8, true, 4096, 2048, 512>()));
+  CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, 256, 8, 1024, 4, 256, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)filter_bloom_smem<8, true, 2048, 1024, 256>()));
   CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1, 1024, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)filter_bloom_smem<8, true, 8192, 4096, 1024>()));
   const int packed_smem = (int)(sizeof(SplitSmem<uint64_t, true>) + sizeof(TileStage));
@@ -384,6 +387,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "persistent_split") c->opt_persistent_split = value > 0 ? 1 : 0;
   else if (n == "r1_bias") c->opt_r1_bias = value;
   else if (n == "nvlink_digits") c->opt_nvlink_digits = value <= 0 ? 128 : value;
+  else if (n == "filter_tiny") c->opt_filter_tiny = value > 0 ? 1 : 0;
   else if (n == "coop_group") c->opt_coop_group = value < 0 ? 1 : std::min<int64_t>(value, 2);
   else if (n == "packed") c->opt_packed = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "direct") c->opt_direct = value < 0 ? 1 : (value > 0 ? 1 : 0);
@@ -796,7 +800,11 @@ int launch_filter(nrp_ctx* c, bool packed, PackFmt pf, const void* leaf_keys, co
   uint32_t* unsorted = reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED);
   const unsigned grid_small = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * 2), grid_large = (unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms);
   if (!c->opt_no_bloom) {
-    if (small && packed)           // two 512-thread CTAs per SM, leaves of up to 4096 records
+    if (c->opt_filter_tiny && packed && mean_leaf <= 1400)    // four 256-thread CTAs per SM, leaves of up to 2048 records
+      NRP_LAUNCH((k_filter_bloom<KeyT, 256, 8, 1024, 4, 256, true><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * 4), 256,
+                                                                    filter_bloom_smem<8, true, 2048, 1024, 256>(), st>>>(
+          leaf_keys, leaf_vals, leaves, n_leaf, bits, pf, std::min<uint32_t>(cap, 2048u), out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+    else if (small && packed)      // two 512-thread CTAs per SM, leaves of up to 4096 records
       NRP_LAUNCH((k_filter_bloom<KeyT, 512, 8, 2048, 2, 512, true><<<grid_small, 512, filter_bloom_smem<8, true, 4096, 2048, 512>(), st>>>(
           leaf_keys, leaf_vals, leaves, n_leaf, bits, pf, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
     else if (small)

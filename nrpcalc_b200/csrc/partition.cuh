@@ -30,6 +30,9 @@
 #ifndef NRP_V_EARLY
 #define NRP_V_EARLY 1        // the cursor claims are issued before the scan of the bucket counts (they only need the counts)
 #endif
+#ifndef NRP_V_FPIPE
+#define NRP_V_FPIPE 1        // filter: a leaf's candidates leave the kernel during the NEXT leaf's turn (the atomic that claims their
+#endif                       // place in the output has a whole filter stage to come back)
 #ifndef NRP_V_LATE
 #define NRP_V_LATE 1         // ... and their results are consumed after the reorder stores: the round trip to L2 overlaps both
 #endif
@@ -731,6 +734,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // the global sort runs).  REC = bytes of a record word (8 for packed records, else the key size).
 template <int REC, bool PACKED, int CAP, int WORDS, int SORTCAP> constexpr size_t filter_bloom_smem() {
   return (size_t)REC * (2 * SORTCAP + SORTCAP) + 4 * (2 * WORDS + 2 * SORTCAP) + 2 * SORTCAP +
+         (size_t)(REC + 4) * SORTCAP +                    // the ordered candidates of the previous leaf (NRP_V_FPIPE)
          (size_t)REC * (CAP + 8) + (PACKED ? 0 : 2 * 4 * (CAP + 8)) + 128;
 }
 
@@ -752,11 +756,13 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
   uint32_t* map_b = map_a + kBloomWords;                                             // kBloomWords
   unsigned char* marked = reinterpret_cast<unsigned char*>(map_b + kBloomWords);    // kSuspectSlots
   RecT* c_keys = reinterpret_cast<RecT*>(marked + kSuspectSlots);                   // kLeafSortCap
-  uint32_t* c_vals = reinterpret_cast<uint32_t*>(c_keys + kLeafSortCap);            // kLeafSortCap
+  RecT* p_keys = c_keys + kLeafSortCap;                                              // kLeafSortCap: the previous leaf's candidates, ordered
+  uint32_t* c_vals = reinterpret_cast<uint32_t*>(p_keys + kLeafSortCap);            // kLeafSortCap
   uint32_t* c_rank = c_vals + kLeafSortCap;                                          // kLeafSortCap
+  uint32_t* p_vals = c_rank + kLeafSortCap;                                          // kLeafSortCap
   // staging, filled by TMA bulk copies (16-byte aligned source windows around the leaf): the records of the NEXT leaf (they are
   // copied to registers at the top of a leaf's turn) and the values of this and the next leaf (only suspects read theirs)
-  RecT* st_keys = reinterpret_cast<RecT*>((reinterpret_cast<uintptr_t>(c_rank + kLeafSortCap) + 15) & ~uintptr_t(15));
+  RecT* st_keys = reinterpret_cast<RecT*>((reinterpret_cast<uintptr_t>(p_vals + kLeafSortCap) + 15) & ~uintptr_t(15));
   uint32_t* st_vals0 = reinterpret_cast<uint32_t*>(st_keys + kBloomCap + 8);
   uint32_t* st_vals1 = st_vals0 + kBloomCap + 8;
   __shared__ __align__(8) uint64_t s_bar;
@@ -768,8 +774,8 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
   // packed: what identifies the k-mer inside a leaf is the stored hash (record >> vbits); its bits below the leaf bits feed the
   // bit maps and the exact table through two cheap 32-bit mixes
   const uint64_t rem_mask = PACKED ? ((1ull << (pf.n_eff() - leaf_bits)) - 1ull) : 0ull;
-  constexpr int kLogBits = WORDS == 2048 ? 16 : 17, kLogSlots = SORTCAP == 512 ? 10 : 11;
-  static_assert((WORDS == 2048 || WORDS == 4096) && (SORTCAP == 512 || SORTCAP == 1024), "index widths");
+  constexpr int kLogBits = WORDS == 1024 ? 15 : WORDS == 2048 ? 16 : 17, kLogSlots = SORTCAP == 256 ? 9 : SORTCAP == 512 ? 10 : 11;
+  static_assert((WORDS == 1024 || WORDS == 2048 || WORDS == 4096) && (SORTCAP == 256 || SORTCAP == 512 || SORTCAP == 1024), "index widths");
   auto ident_of = [&](RecT r) -> uint64_t { return PACKED ? ((uint64_t)r >> vbits) : (uint64_t)r; };
   auto fold_rem = [&](RecT r) -> uint32_t { const uint64_t rem = ((uint64_t)r >> vbits) & rem_mask; return (uint32_t)rem ^ (uint32_t)(rem >> 32); };
   const int lane = threadIdx.x & 31;
@@ -811,6 +817,20 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
   };
   clear_maps();
   clear_table();
+  // NRP_V_FPIPE: the ordered candidates of a leaf wait in p_keys / p_vals; thread 0 holds the (not yet consumed) result of the
+  // atomic that claimed their place and publishes it one filter stage into the next leaf's turn
+  uint32_t pend_n = 0, pend_leaf = 0;               // uniform across the CTA
+  unsigned long long pend_base = 0;                 // thread 0 only
+  auto pend_emit = [&]() {                          // after a barrier that follows `s_cbase = pend_base`
+    if (threadIdx.x < pend_n) emit(s_cbase + threadIdx.x, p_keys[threadIdx.x], PACKED ? 0u : p_vals[threadIdx.x], pend_leaf);
+    pend_n = 0;
+  };
+  auto pend_flush = [&]() {                         // on the paths that skip the filter stages (uniform)
+    if (pend_n == 0) return;
+    if (threadIdx.x == 0) s_cbase = pend_base;
+    __syncthreads();
+    pend_emit();
+  };
   uint32_t lo, n, lo1, n1, lo2, n2;
   extent(blockIdx.x, lo, n);
   extent(blockIdx.x + gridDim.x, lo1, n1);
@@ -841,8 +861,9 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
       stage(lo1, n1, turn ? st_vals0 : st_vals1);
       s_c1 = 0; s_c2 = 0;                           // every reader of the previous leaf's counts is past the barrier above
     }
-    if (n < 2) continue;
+    if (n < 2) { pend_flush(); continue; }
     if (!fits) {
+      pend_flush();
       if (threadIdx.x == 0) { atomicAdd(n_oversized, 1u); *unsorted = 1u; }
       for (uint32_t i = threadIdx.x; i < n + 31u - ((n - 1u) & 31u) ; i += T) {   // whole warps iterate together
         bool ok = i < n;
@@ -863,7 +884,9 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
       const uint32_t w = bits[e] >> 5, m = 1u << (bits[e] & 31u);
       if (atomicOr(&map_a[w], m) & m) atomicOr(&map_b[w], m);
     }
+    if (pend_n != 0 && threadIdx.x == 0) s_cbase = pend_base;      // the claim issued at the end of the previous leaf has landed by now
     __syncthreads();
+    if (pend_n != 0) pend_emit();
     // stage 1b: collect the suspects -- one shared-memory atomic per warp claims the slots of its suspects
     uint32_t smask = 0;
 #pragma unroll
@@ -957,15 +980,21 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
         }
         if (partial) atomicAdd(&c_rank[cand], partial);
       }
-      if (threadIdx.x == 0) s_cbase = atomicAdd(n_cand, (unsigned long long)c2);
+      if (threadIdx.x == 0) {
+        if (NRP_V_FPIPE) pend_base = atomicAdd(n_cand, (unsigned long long)c2);
+        else s_cbase = atomicAdd(n_cand, (unsigned long long)c2);
+      }
     }
     __syncthreads();
     if (threadIdx.x < c2) {
       const uint32_t rank = c_rank[threadIdx.x];
-      emit(s_cbase + rank, c_keys[threadIdx.x], PACKED ? 0u : c_vals[threadIdx.x], leaf);
+      if (NRP_V_FPIPE) { p_keys[rank] = c_keys[threadIdx.x]; if (!PACKED) p_vals[rank] = c_vals[threadIdx.x]; }
+      else emit(s_cbase + rank, c_keys[threadIdx.x], PACKED ? 0u : c_vals[threadIdx.x], leaf);
       c_rank[threadIdx.x] = 0;
     }
+    if (NRP_V_FPIPE) { pend_n = c2; pend_leaf = leaf; }
   }
+  pend_flush();
 }
 
 }  // namespace nrp
