@@ -120,3 +120,28 @@ def test_recovery_returns_maximal_independent_set():
         for node in graph.nodes():
             if node not in chosen:
                 assert any(nb in chosen for nb in graph[node])       # cannot be extended
+
+
+@pytest.mark.parametrize('n_parts,k,internal', [(1500, 9, True), (2500, 10, False), (800, 7, True)])
+def test_direct_graph_build_equals_public_api_and_port(n_parts, k, internal):
+    """build_homology_graph fills the graph's dicts directly; node order, adjacency order and the graph object must equal
+    what networkx's public API gives (hgraph.py:157-200 literally) and what the literal port of the reference builds,
+    on inputs dense enough that most cliques overlap."""
+    import cases
+    from collections import deque
+    from oracle import ref_port
+    parts = cases.random_parts(n_parts, 60, 100 + n_parts) + cases.planted_parts(200, n_parts)
+    uniq = hgraph.uniquify_seq_list(list(parts))
+    structure, ids = fake_device.oracle_repeat_structure(uniq, None, k, internal)
+    cliques = [tuple(c) for c in hgraph.replay_cliques(hgraph.ordered_tuples(structure, ids))]
+    fast = hgraph.build_homology_graph((deque(c) for c in cliques), False)
+    slow = hgraph._build_homology_graph_api((deque(c) for c in cliques), False)
+    expect, _ = ref_port.homology_graph(list(parts), None, k, internal)
+    assert fast.number_of_edges() > n_parts                      # dense: cliques overlap
+    for other in (slow, expect):
+        assert list(fast.nodes()) == list(other.nodes())
+        assert [list(fast[u]) for u in fast.nodes()] == [list(other[u]) for u in other.nodes()]
+        assert nx.utils.graphs_equal(fast, other)
+    assert fast.number_of_edges() == expect.number_of_edges() and fast.degree(next(iter(fast))) == expect.degree(next(iter(expect)))
+    copy = nx.Graph(fast.subgraph(list(fast.nodes())[::2]))      # the graph behaves like any nx.Graph afterwards
+    assert copy.number_of_nodes() == (fast.number_of_nodes() + 1) // 2
