@@ -4,7 +4,10 @@ reference (nrpcalc/base/recovery.py:32-96).
 The cover routines destroy the graph they are given, so the full graph is dumped once as an adjacency list
 and reloaded after every round (recovery.py:26-30,55,78).  The reload changes adjacency order (file order
 instead of insertion order), which later rounds observe; the dump/reload is therefore part of result parity
-and is kept as is.
+and is kept.  The RELOADED graph, however, is never modified -- later rounds only read it and build their
+working graph with nx.Graph(reloaded.subgraph(...)) (recovery.py:71-72,86) -- so every reload after the first
+would parse the same file into an identical object: it is parsed once and reused (a third of the recovery time
+at 100k parts).
 """
 import sys
 from time import time
@@ -36,6 +39,7 @@ def get_recovered_non_homologs(homology_graph, graph_file, vercov_func=None, ver
         sys.stdout.write(' in {} seconds\n'.format(time() - t0))
 
     iteration = -1
+    reloaded = None
     while True:
         iteration += 1
         if verbose:
@@ -49,7 +53,9 @@ def get_recovered_non_homologs(homology_graph, graph_file, vercov_func=None, ver
         if verbose:
             print('\n [+] Computed vertex cover of size: {} (in {:.4} seconds)'.format(len(cover), time() - t0))
             print(' [+] Loading graph from: {}'.format(graph_file))
-        homology_graph = nx.read_adjlist(graph_file, nodetype=int)
+        if reloaded is None:
+            reloaded = nx.read_adjlist(graph_file, nodetype=int)
+        homology_graph = reloaded
 
         fresh = candidates - cover
         independent |= fresh

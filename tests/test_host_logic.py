@@ -145,3 +145,42 @@ def test_direct_graph_build_equals_public_api_and_port(n_parts, k, internal):
     assert fast.number_of_edges() == expect.number_of_edges() and fast.degree(next(iter(fast))) == expect.degree(next(iter(expect)))
     copy = nx.Graph(fast.subgraph(list(fast.nodes())[::2]))      # the graph behaves like any nx.Graph afterwards
     assert copy.number_of_nodes() == (fast.number_of_nodes() + 1) // 2
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize('mode', ['nrp2', 'nrpG', '2apx'])
+def test_recovery_against_live_reference(mode, scratch_cwd):
+    """Independent-set recovery (reload parsed once, graph filled through its dicts) against the UNMODIFIED reference's
+    recovery on dense graphs that need several expansion rounds, same random.seed."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, 'golden'))
+    import refshim
+    if not refshim.reference_available():
+        pytest.skip('reference tree not present (GPU box)')
+    refshim.load_reference()
+    import cases
+    from nrpcalc.base import hgraph as ref_hgraph, recovery as ref_recovery
+    rounds = []
+    real_subgraph = nx.Graph.subgraph
+
+    def counting_subgraph(self, nodes):
+        rounds.append(1)
+        return real_subgraph(self, nodes)
+
+    for seed, n_parts, k in ((3, 1200, 9), (4, 2000, 10)):
+        parts = cases.random_parts(n_parts, 60, 40 + seed) + cases.planted_parts(150, seed)
+        theirs_graph = ref_hgraph.get_homology_graph(list(parts), None, k, True, './seq_ref.txt', False)
+        mine_graph = hgraph.get_homology_graph(list(parts), None, k, True, './seq_mine.txt', False)
+        assert [list(theirs_graph[n]) for n in theirs_graph.nodes()] == [list(mine_graph[n]) for n in mine_graph.nodes()]
+        random.seed(11 + seed)
+        theirs = ref_recovery.get_recovered_non_homologs(theirs_graph, './graph_ref.txt', mode, False)
+        nx.Graph.subgraph = counting_subgraph
+        try:
+            random.seed(11 + seed)
+            mine = recovery.get_recovered_non_homologs(mine_graph, './graph_mine.txt', mode, False)
+        finally:
+            nx.Graph.subgraph = real_subgraph
+        assert mine == theirs and len(mine) > 0
+        body = lambda path: [line for line in open(path).read().splitlines() if not line.startswith('#')]   # header = time stamp
+        assert body('./graph_ref.txt') == body('./graph_mine.txt')
+    assert len(rounds) >= 2                                      # at least one case went past the first reload
