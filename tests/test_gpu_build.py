@@ -116,6 +116,16 @@ def test_forced_paths(ctx):
         _compare(_run(ctx, uniq, 13, False), uniq, 13, False)
         _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
         ctx.set_option('coop_group', -1)
+        ctx.set_option('filter_tiny', 1)              # 256-thread filter CTAs (leaves that average <= 1400 records)
+        _compare(_run(ctx, uniq, 13, False), uniq, 13, False)
+        _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
+        ctx.set_option('leaf_target', 1300)
+        big = _long_parts(cases.planted_parts(800, 5) + cases.random_parts(12000, 100, 6), 17)
+        res = _run(ctx, big, 17, False)
+        assert res.counts['buckets'] >= 512 and res.counts['packed'] == 1
+        _compare(res, big, 17, False)
+        ctx.set_option('leaf_target', 0)
+        ctx.set_option('filter_tiny', 0)
         ctx.set_option('no_bloom', 1)                 # exact table on every record instead of the two-stage filter
         _compare(_run(ctx, uniq, 13, False), uniq, 13, False)
         ctx.set_option('no_bloom', 0)
@@ -124,6 +134,7 @@ def test_forced_paths(ctx):
         uniq17 = _long_parts(cases.planted_parts(600, 77), 17)
         _compare(_run(ctx, uniq17, 17, True), uniq17, 17, True)
     finally:
+        ctx.set_option('filter_tiny', 0)
         ctx.set_option('coop_group', -1)
         ctx.set_option('direct', -1)
         ctx.set_option('no_window_carry', 0)
