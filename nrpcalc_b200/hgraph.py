@@ -12,6 +12,10 @@ What runs where
           (libnrpb200.so through nrpcalc_b200._native)                    kmerSetDB.py:177-207
   host    replay of the distinct id tuples through the clique tail    <- hgraph.py:96-200
 
+The tail runs as C on real CPython containers when nrpcalc_b200/_host_tail.so is built (csrc/host_tail.c: the same
+set / dict / deque operations through the C API, identical by construction, 2-3x faster) and as the Python loops
+below otherwise; NRPCALC_B200_PYTHON_TAIL=1 forces the Python loops.
+
 The tail cannot move to the GPU without changing results: the order in which cliques reach the graph is the
 iteration order of CPython sets of tuples (hgraph.py:131-155).  It is reproduced by feeding real sets the
 same values in the same order.  Only tuples that differ from all earlier ones change a set, so the device
@@ -20,6 +24,7 @@ returns every shared k-mer group with its rank and, per part, the rank of its la
 
 There is no CPU fallback: without the CUDA library or a GPU the call raises.
 """
+import os
 import sys
 from collections import defaultdict, deque
 from time import time
@@ -29,6 +34,13 @@ import numpy as np
 
 from . import _native
 from . import encoding
+
+try:                                         # optional C extension (host only, no CUDA): the same container operations
+    from . import _host_tail
+except ImportError:                          # not built: the Python loops below
+    _host_tail = None
+if os.environ.get('NRPCALC_B200_PYTHON_TAIL'):
+    _host_tail = None
 
 _contexts = {}
 
@@ -229,6 +241,12 @@ def _maximal_cliques(clique_sets):
 def replay_cliques(tuples):
     """hgraph.py:130-155 on the compressed stream.  Re-adding a tuple that is already present never changes a
     CPython set, so adding only the (superset of) first occurrences leaves every set exactly as in the reference."""
+    if _host_tail is not None:
+        return iter(_host_tail.replay_cliques(tuples))
+    return _replay_cliques_python(tuples)
+
+
+def _replay_cliques_python(tuples):
     distinct = set()
     for members in tuples:
         distinct.add(members)
@@ -255,6 +273,15 @@ def build_homology_graph(cliques, verbose):
     adj, nodes = graph._adj, graph._node
     if not (type(adj) is dict and type(nodes) is dict):               # an unexpected networkx: the public API
         return _build_homology_graph_api(cliques, verbose)
+    if _host_tail is not None:
+        if verbose:
+            print()
+        count = _host_tail.fill_graph(adj, nodes, cliques)
+        if verbose:                                                   # what the per-clique counter leaves on the terminal
+            sys.stdout.write(' [Cliques inserted] = {}\r'.format(count))
+            sys.stdout.flush()
+            print()
+        return graph
     if verbose:
         print()
         clear_length = 0

@@ -184,3 +184,29 @@ def test_recovery_against_live_reference(mode, scratch_cwd):
         body = lambda path: [line for line in open(path).read().splitlines() if not line.startswith('#')]   # header = time stamp
         assert body('./graph_ref.txt') == body('./graph_mine.txt')
     assert len(rounds) >= 2                                      # at least one case went past the first reload
+
+
+def test_c_host_tail_equals_python_loops():
+    """csrc/host_tail.c (the tail's container operations through the C API) against the Python loops: same cliques in the
+    same order, same graph object -- on a dense case, with duplicate ids inside tuples (internal_repeats=True)."""
+    import cases
+    from collections import deque
+    if hgraph._host_tail is None:
+        pytest.skip('nrpcalc_b200/_host_tail.so not built')
+    parts = cases.random_parts(3000, 60, 77) + cases.planted_parts(300, 78)
+    uniq = hgraph.uniquify_seq_list(list(parts))
+    structure, ids = fake_device.oracle_repeat_structure(uniq, None, 10, True)
+    tuples = list(hgraph.ordered_tuples(structure, ids))
+    native = [tuple(c) for c in hgraph.replay_cliques(iter(tuples))]
+    python = [tuple(c) for c in hgraph._replay_cliques_python(iter(tuples))]
+    assert native == python and len(native) > 1000
+    g_native = hgraph.build_homology_graph((deque(c) for c in native), False)
+    saved = hgraph._host_tail
+    hgraph._host_tail = None
+    try:
+        g_python = hgraph.build_homology_graph((deque(c) for c in python), False)
+    finally:
+        hgraph._host_tail = saved
+    assert list(g_native.nodes()) == list(g_python.nodes())
+    assert [list(g_native[u]) for u in g_native.nodes()] == [list(g_python[u]) for u in g_python.nodes()]
+    assert nx.utils.graphs_equal(g_native, g_python)
