@@ -12,9 +12,10 @@ What runs where
           (libnrpb200.so through nrpcalc_b200._native)                    kmerSetDB.py:177-207
   host    replay of the distinct id tuples through the clique tail    <- hgraph.py:96-200
 
-The tail runs as C on real CPython containers when nrpcalc_b200/_host_tail.so is built (csrc/host_tail.c: the same
-set / dict / deque operations through the C API, identical by construction, 2-3x faster) and as the Python loops
-below otherwise; NRPCALC_B200_PYTHON_TAIL=1 forces the Python loops.
+The tail runs (1) on compact arrays with a layout-exact model of CPython's sets when nrpcalc_b200/libnrptail.so is built and
+its start-up self-check against the Python loops passed (csrc/host_replay.cpp, native_tail.py), else (2) as C on real CPython
+containers when nrpcalc_b200/_host_tail.so is built (csrc/host_tail.c: the same set / dict / deque operations through the C
+API, identical by construction), else (3) as the Python loops below; NRPCALC_B200_PYTHON_TAIL=1 forces (3).
 
 The tail cannot move to the GPU without changing results: the order in which cliques reach the graph is the
 iteration order of CPython sets of tuples (hgraph.py:131-155).  It is reproduced by feeding real sets the
@@ -34,6 +35,7 @@ import numpy as np
 
 from . import _native
 from . import encoding
+from . import native_tail
 
 try:                                         # optional C extension (host only, no CUDA): the same container operations
     from . import _host_tail
@@ -217,6 +219,35 @@ def ordered_tuples(structure, ids):
             yield tuple(members[s:s + z])
 
 
+def ordered_stream_arrays(structure, ids):
+    """The same stream as ordered_tuples, as arrays: tuple t = members[start[t] : start[t] + size[t]] (ids, int64)."""
+    if not structure.rank:
+        empty = np.zeros(0, dtype=np.int64)
+        return empty, empty, empty
+    rank = np.concatenate(structure.rank)
+    order = np.argsort(-rank, kind='stable')
+    start = np.concatenate(structure.start)[order].astype(np.int64)
+    size = np.concatenate(structure.size)[order].astype(np.int64)
+    members = ids[np.concatenate(structure.members)].astype(np.int64)
+    return start, size, members
+
+
+def assemble_graph(structure, ids, verbose):
+    """Ordered stream -> clique replay -> graph (hgraph.py:96-200).  On compact arrays with a layout-exact model of CPython's
+    sets when libnrptail.so is built and its self-check against the Python loops passed (native_tail.py); through real
+    CPython containers otherwise."""
+    if native_tail.usable():
+        nodes, indptr, adj, clique_off, _ = native_tail.run(*ordered_stream_arrays(structure, ids), want_cliques=True)
+        graph = native_tail.graph_from_arrays(nodes, indptr, adj)
+        if verbose:                                                   # what the per-clique counter leaves on the terminal
+            print()
+            sys.stdout.write(' [Cliques inserted] = {}\r'.format(clique_off.size - 1))
+            sys.stdout.flush()
+            print()
+        return graph
+    return build_homology_graph(replay_cliques(ordered_tuples(structure, ids)), verbose)
+
+
 def _maximal_cliques(clique_sets):
     """Keep cliques that are not contained in another one (hgraph.py:96-115), same set operations in the same order."""
     member_of = defaultdict(set)
@@ -269,19 +300,28 @@ def build_homology_graph(cliques, verbose):
     attribute-free nx.Graph: one shared empty data dict per edge), and the difference is taken against the adjacency dict
     itself -- set.difference walks the left operand's table exactly as `-` does against a set of the same keys -- which
     makes the stage ~2.6x faster with an identical graph (tests/test_host_logic.py)."""
+    if _host_tail is None:
+        return _build_homology_graph_python(cliques, verbose)
     graph = nx.Graph()
     adj, nodes = graph._adj, graph._node
     if not (type(adj) is dict and type(nodes) is dict):               # an unexpected networkx: the public API
         return _build_homology_graph_api(cliques, verbose)
-    if _host_tail is not None:
-        if verbose:
-            print()
-        count = _host_tail.fill_graph(adj, nodes, cliques)
-        if verbose:                                                   # what the per-clique counter leaves on the terminal
-            sys.stdout.write(' [Cliques inserted] = {}\r'.format(count))
-            sys.stdout.flush()
-            print()
-        return graph
+    if verbose:
+        print()
+    count = _host_tail.fill_graph(adj, nodes, cliques)
+    if verbose:                                                       # what the per-clique counter leaves on the terminal
+        sys.stdout.write(' [Cliques inserted] = {}\r'.format(count))
+        sys.stdout.flush()
+        print()
+    return graph
+
+
+def _build_homology_graph_python(cliques, verbose):
+    """build_homology_graph as Python loops over the graph's dicts."""
+    graph = nx.Graph()
+    adj, nodes = graph._adj, graph._node
+    if not (type(adj) is dict and type(nodes) is dict):               # an unexpected networkx: the public API
+        return _build_homology_graph_api(cliques, verbose)
     if verbose:
         print()
         clear_length = 0
@@ -376,7 +416,7 @@ def get_homology_graph(seq_list, background, homology, internal_repeats, seq_fil
     if verbose:
         print(' [Sequence processing remaining] = 0  (GPU: {} k-mers in {:.3f} ms on device)'.format(
             structure.records, structure.timings['total']))
-    graph = build_homology_graph(replay_cliques(ordered_tuples(structure, ids)), verbose)
+    graph = assemble_graph(structure, ids, verbose)
     last_build_info.clear()
     last_build_info.update({'records': structure.records, 'device_ms': structure.timings['total'], 'call_s': t_device,
                             'timings': dict(structure.timings), 'counts': dict(structure.counts),

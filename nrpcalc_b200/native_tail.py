@@ -1,0 +1,172 @@
+"""ctypes binding of libnrptail.so (csrc/host_replay.cpp + cpyset.hpp): the order-exact clique replay and graph assembly
+of reference nrpcalc/base/hgraph.py:96-200 on compact arrays.
+
+The C++ side models CPython's set layout (probing, resizing, dummies, the bulk operations' heuristics, the tuple hash)
+instead of creating millions of small Python objects.  That is only valid while the running interpreter follows the same
+rules, so the first use runs a self-check: a randomised stream goes through this path AND through the Python loops of
+hgraph.py (real sets); any difference disables the native path for the process (hgraph falls back to the Python loops).
+Host code only -- no CUDA, no GPU needed."""
+import ctypes
+import gc
+import os
+import random
+import sys
+
+import networkx as nx
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libnrptail.so')
+_lib = None
+_state = {'checked': False, 'usable': False, 'why': 'not loaded'}
+
+
+def _load():
+    global _lib
+    if _lib is None and os.path.exists(LIB_PATH) and not os.environ.get('NRPCALC_B200_PYTHON_TAIL'):
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.nrp_tail_run.restype = ctypes.c_void_p
+        lib.nrp_tail_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        lib.nrp_tail_sizes.restype = None
+        lib.nrp_tail_sizes.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        lib.nrp_tail_fetch.restype = None
+        lib.nrp_tail_fetch.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 5
+        lib.nrp_tail_free.restype = None
+        lib.nrp_tail_free.argtypes = [ctypes.c_void_p]
+        lib.nrp_tail_tuple_hash.restype = ctypes.c_int64
+        lib.nrp_tail_tuple_hash.argtypes = [ctypes.c_void_p, ctypes.c_int64]
+        lib.nrp_tail_set_script.restype = ctypes.c_int64
+        lib.nrp_tail_set_script.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]
+        _lib = lib
+    return _lib
+
+
+def run(start, size, members, want_cliques=False):
+    """The tail on arrays: tuple t of the ordered stream = members[start[t] : start[t] + size[t]].
+    Returns (nodes, indptr, adjacency) -- node ids in insertion order and each node's neighbours in insertion order --
+    plus (clique_off, clique_nodes) when want_cliques."""
+    lib = _load()
+    start = np.ascontiguousarray(start, dtype=np.int64)
+    size = np.ascontiguousarray(size, dtype=np.int64)
+    members = np.ascontiguousarray(members, dtype=np.int64)
+    handle = lib.nrp_tail_run(start.ctypes.data, size.ctypes.data, start.size, members.ctypes.data)
+    try:
+        sizes = np.zeros(4, dtype=np.int64)
+        lib.nrp_tail_sizes(handle, sizes.ctypes.data)
+        nodes = np.empty(int(sizes[0]), dtype=np.int64)
+        indptr = np.empty(int(sizes[0]) + 1, dtype=np.int64)
+        adj = np.empty(int(sizes[1]), dtype=np.int64)
+        c_off = np.empty(int(sizes[2]) + 1, dtype=np.int64) if want_cliques else None
+        c_nodes = np.empty(int(sizes[3]), dtype=np.int64) if want_cliques else None
+        lib.nrp_tail_fetch(handle, nodes.ctypes.data, indptr.ctypes.data, adj.ctypes.data,
+                           c_off.ctypes.data if want_cliques else None, c_nodes.ctypes.data if want_cliques else None)
+    finally:
+        lib.nrp_tail_free(handle)
+    if want_cliques:
+        return nodes, indptr, adj, c_off, c_nodes
+    return nodes, indptr, adj
+
+
+def graph_from_arrays(nodes, indptr, adj):
+    """An attribute-free nx.Graph with exactly this node order and these adjacency orders (one shared empty data dict per
+    edge, as Graph.add_edge creates)."""
+    graph = nx.Graph()
+    node_dict, adj_dict = graph._node, graph._adj
+    if not (type(node_dict) is dict and type(adj_dict) is dict):
+        raise RuntimeError('unexpected networkx Graph internals')
+    ids = nodes.tolist()
+    bounds = indptr.tolist()
+    flat = adj.tolist()
+    collecting = gc.isenabled()
+    gc.disable()               # ~a million acyclic dicts are born here: generational scans would double the time and free nothing
+    try:
+        for i, u in enumerate(ids):
+            node_dict[u] = {}
+            adj_dict[u] = dict.fromkeys(flat[bounds[i]:bounds[i + 1]])
+        for u, nbrs in adj_dict.items():
+            for v, data in nbrs.items():
+                if data is None:
+                    data = {}
+                    nbrs[v] = data
+                    adj_dict[v][u] = data
+    finally:
+        if collecting:
+            gc.enable()
+    cache = getattr(graph, '__networkx_cache__', None)
+    if cache:
+        cache.clear()
+    return graph
+
+
+def stream_arrays(tuples):
+    """(start, size, members) of an iterable of id tuples (tests and the self-check; the product passes its arrays directly)."""
+    tuples = list(tuples)
+    size = np.fromiter((len(t) for t in tuples), dtype=np.int64, count=len(tuples))
+    start = np.zeros(len(tuples), dtype=np.int64)
+    if len(tuples) > 1:
+        np.cumsum(size[:-1], out=start[1:])
+    members = np.fromiter((x for t in tuples for x in t), dtype=np.int64, count=int(size.sum()))
+    return start, size, members
+
+
+def _self_check():
+    """A randomised stream with heavy sharing through both implementations (the last case takes the set of distinct tuples
+    past 50000 entries, where CPython's growth rule changes)."""
+    from . import hgraph
+    rng = random.Random(20261020)
+    for n_nodes, n_tuples, top in ((40, 300, 4), (3000, 9000, 6), (30000, 64000, 3)):
+        tuples = [(rng.randrange(n_nodes),) for _ in range(n_tuples // 2)]
+        for _ in range(n_tuples // 2):
+            k = rng.randrange(2, top + 1)
+            base = rng.randrange(n_nodes)
+            tuples.append(tuple(min(n_nodes - 1, base + rng.randrange(0, 12)) if rng.random() < 0.7 else rng.randrange(n_nodes) for _ in range(k)))
+        rng.shuffle(tuples)
+        nodes, indptr, adj = run(*stream_arrays(tuples))
+        expect = hgraph._build_homology_graph_python(hgraph._replay_cliques_python(iter(tuples)), False)
+        if nodes.tolist() != list(expect.nodes()):
+            return False, 'node order differs'
+        bounds = indptr.tolist()
+        flat = adj.tolist()
+        for i, u in enumerate(expect.nodes()):
+            if flat[bounds[i]:bounds[i + 1]] != list(expect[u]):
+                return False, 'adjacency order differs'
+    return True, 'ok'
+
+
+def _verdict_key():
+    st = os.stat(LIB_PATH)
+    return '{}|{}|{}|{}'.format(sys.version, nx.__version__, st.st_size, int(st.st_mtime))
+
+
+def usable():
+    """True when the library is built and its set model matches this interpreter.  Checked once per process; a passed check
+    is remembered next to the library (keyed by interpreter version, networkx version and the library's size and time stamp)."""
+    if not _state['checked']:
+        _state['checked'] = True
+        if _load() is None:
+            _state['usable'], _state['why'] = False, 'libnrptail.so not built (or NRPCALC_B200_PYTHON_TAIL set)'
+            return False
+        stamp = LIB_PATH + '.ok'
+        try:
+            key = _verdict_key()
+            if os.path.exists(stamp) and open(stamp).read() == key:
+                _state['usable'], _state['why'] = True, 'ok (remembered)'
+                return True
+        except OSError:
+            key = None
+        try:
+            _state['usable'], _state['why'] = _self_check()
+        except Exception as exc:                           # never let the accelerator break the product
+            _state['usable'], _state['why'] = False, 'self-check raised {!r}'.format(exc)
+        if _state['usable'] and key is not None:
+            try:
+                with open(stamp, 'w') as fh:
+                    fh.write(key)
+            except OSError:
+                pass
+    return _state['usable']
+
+
+def status():
+    usable()
+    return dict(_state)

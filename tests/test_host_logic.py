@@ -210,3 +210,33 @@ def test_c_host_tail_equals_python_loops():
     assert list(g_native.nodes()) == list(g_python.nodes())
     assert [list(g_native[u]) for u in g_native.nodes()] == [list(g_python[u]) for u in g_python.nodes()]
     assert nx.utils.graphs_equal(g_native, g_python)
+
+
+@pytest.mark.parametrize('n_parts,k,internal', [(3000, 10, True), (2000, 9, False), (6000, 12, False)])
+def test_native_array_tail_equals_python_loops(n_parts, k, internal):
+    """csrc/host_replay.cpp (the tail on compact arrays, CPython's set layout modelled) against the Python loops on real
+    sets: the same clique stream in the same order and the same graph, on dense inputs incl. duplicate ids inside tuples."""
+    import cases
+    from nrpcalc_b200 import native_tail
+    if not native_tail.usable():
+        pytest.skip('libnrptail.so not built: ' + native_tail.status()['why'])
+    parts = cases.random_parts(n_parts, 60, 300 + n_parts) + cases.planted_parts(300, n_parts)
+    uniq = hgraph.uniquify_seq_list(list(parts))
+    structure, ids = fake_device.oracle_repeat_structure(uniq, None, k, internal)
+    tuples = list(hgraph.ordered_tuples(structure, ids))
+    start, size, members = hgraph.ordered_stream_arrays(structure, ids)
+    assert [tuple(members[s:s + z].tolist()) for s, z in zip(start.tolist(), size.tolist())] == tuples
+    nodes, indptr, adj, c_off, c_nodes = native_tail.run(start, size, members, want_cliques=True)
+    python_cliques = [tuple(c) for c in hgraph._replay_cliques_python(iter(tuples))]
+    off, flat = c_off.tolist(), c_nodes.tolist()
+    assert [tuple(flat[off[i]:off[i + 1]]) for i in range(len(off) - 1)] == python_cliques and len(python_cliques) > 1000
+    from collections import deque
+    expect = hgraph._build_homology_graph_python((deque(c) for c in python_cliques), False)
+    graph = native_tail.graph_from_arrays(nodes, indptr, adj)
+    assert list(graph.nodes()) == list(expect.nodes())
+    assert [list(graph[u]) for u in graph.nodes()] == [list(expect[u]) for u in expect.nodes()]
+    assert nx.utils.graphs_equal(graph, expect)
+    some = list(graph.nodes())[:50]
+    assert all(graph[u][v] is graph[v][u] for u in some for v in graph[u])       # one data dict per edge, as add_edge makes
+    assembled = hgraph.assemble_graph(structure, ids, False)
+    assert list(assembled.nodes()) == list(expect.nodes()) and nx.utils.graphs_equal(assembled, expect)
