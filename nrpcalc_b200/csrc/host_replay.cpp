@@ -265,6 +265,50 @@ void* nrp_tail_run(const int64_t* start, const int64_t* size, int64_t n_tuples, 
   return R;
 }
 
+// The graph that nx.read_adjlist(nx.write_adjlist(G)) gives (reference recovery.py:26-30): the dump lists every edge once,
+// under its endpoint that comes first in G's node order (networkx generate_adjlist skips neighbours already "seen"), and the
+// parser adds, line by line, the line's node and then its edges (parse_adjlist: add_node, add_edges_from) -- which fixes the
+// node order and every adjacency order of the reloaded graph.  Same simulation on arrays, no text.
+void* nrp_tail_reload(const int64_t* nodes, const int64_t* indptr, const int64_t* adj, int64_t n_nodes) {
+  TailResult* R = new TailResult();
+  int64_t max_id = 0;
+  for (int64_t i = 0; i < n_nodes; ++i) max_id = nodes[i] > max_id ? nodes[i] : max_id;
+  IdIndex old_index, new_index;
+  old_index.init(max_id, n_nodes);
+  new_index.init(max_id, n_nodes);
+  for (int64_t i = 0; i < n_nodes; ++i) old_index.set(nodes[i], (int32_t)i);
+  std::vector<char> seen((size_t)n_nodes, 0);
+  std::vector<std::vector<int64_t>> nbrs;
+  auto ensure = [&](int64_t id) -> int32_t {
+    int32_t idx = new_index.get(id);
+    if (idx >= 0) return idx;
+    idx = (int32_t)R->nodes.size();
+    new_index.set(id, idx);
+    R->nodes.push_back(id);
+    nbrs.emplace_back();
+    return idx;
+  };
+  for (int64_t i = 0; i < n_nodes; ++i) {
+    const int64_t s = nodes[i];
+    const int32_t si = ensure(s);                                   // G.add_node(u)
+    for (int64_t e = indptr[i]; e < indptr[i + 1]; ++e) {
+      const int64_t t = adj[e];
+      if (seen[(size_t)old_index.get(t)]) continue;                 // written under the earlier endpoint
+      const int32_t ti = ensure(t);                                 // add_edges_from: the target joins the graph if new
+      nbrs[(size_t)si].push_back(t);
+      nbrs[(size_t)ti].push_back(s);
+    }
+    seen[(size_t)i] = 1;
+  }
+  R->indptr.push_back(0);
+  for (const auto& list : nbrs) {
+    R->adj.insert(R->adj.end(), list.begin(), list.end());
+    R->indptr.push_back((int64_t)R->adj.size());
+  }
+  R->clique_off.push_back(0);
+  return R;
+}
+
 void nrp_tail_sizes(void* handle, int64_t out[4]) {
   const TailResult* R = static_cast<const TailResult*>(handle);
   out[0] = (int64_t)R->nodes.size(); out[1] = (int64_t)R->adj.size();

@@ -239,6 +239,7 @@ def assemble_graph(structure, ids, verbose):
     if native_tail.usable():
         nodes, indptr, adj, clique_off, _ = native_tail.run(*ordered_stream_arrays(structure, ids), want_cliques=True)
         graph = native_tail.graph_from_arrays(nodes, indptr, adj)
+        graph._nrp_arrays = (nodes, indptr, adj)                      # recovery derives the dumped-and-reloaded graph from these
         if verbose:                                                   # what the per-clique counter leaves on the terminal
             print()
             sys.stdout.write(' [Cliques inserted] = {}\r'.format(clique_off.size - 1))

@@ -27,6 +27,8 @@ def _load():
         lib = ctypes.CDLL(LIB_PATH)
         lib.nrp_tail_run.restype = ctypes.c_void_p
         lib.nrp_tail_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        lib.nrp_tail_reload.restype = ctypes.c_void_p
+        lib.nrp_tail_reload.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
         lib.nrp_tail_sizes.restype = None
         lib.nrp_tail_sizes.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         lib.nrp_tail_fetch.restype = None
@@ -50,6 +52,10 @@ def run(start, size, members, want_cliques=False):
     size = np.ascontiguousarray(size, dtype=np.int64)
     members = np.ascontiguousarray(members, dtype=np.int64)
     handle = lib.nrp_tail_run(start.ctypes.data, size.ctypes.data, start.size, members.ctypes.data)
+    return _collect(lib, handle, want_cliques)
+
+
+def _collect(lib, handle, want_cliques=False):
     try:
         sizes = np.zeros(4, dtype=np.int64)
         lib.nrp_tail_sizes(handle, sizes.ctypes.data)
@@ -62,9 +68,17 @@ def run(start, size, members, want_cliques=False):
                            c_off.ctypes.data if want_cliques else None, c_nodes.ctypes.data if want_cliques else None)
     finally:
         lib.nrp_tail_free(handle)
-    if want_cliques:
-        return nodes, indptr, adj, c_off, c_nodes
-    return nodes, indptr, adj
+    return (nodes, indptr, adj, c_off, c_nodes) if want_cliques else (nodes, indptr, adj)
+
+
+def reload_arrays(nodes, indptr, adj):
+    """Arrays of the graph nx.read_adjlist(file written by nx.write_adjlist(G)) returns, from the arrays of G
+    (reference recovery.py:26-30; the dump / reload changes node and adjacency order, which later rounds observe)."""
+    lib = _load()
+    nodes = np.ascontiguousarray(nodes, dtype=np.int64)
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    adj = np.ascontiguousarray(adj, dtype=np.int64)
+    return _collect(lib, lib.nrp_tail_reload(nodes.ctypes.data, indptr.ctypes.data, adj.ctypes.data, nodes.size))
 
 
 def graph_from_arrays(nodes, indptr, adj):

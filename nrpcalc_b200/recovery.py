@@ -7,19 +7,27 @@ instead of insertion order), which later rounds observe; the dump/reload is ther
 and is kept.  The RELOADED graph, however, is never modified -- later rounds only read it and build their
 working graph with nx.Graph(reloaded.subgraph(...)) (recovery.py:71-72,86) -- so every reload after the first
 would parse the same file into an identical object: it is parsed once and reused (a third of the recovery time
-at 100k parts).
+at 100k parts).  When the graph came from the array tail (hgraph.assemble_graph keeps its node / adjacency arrays)
+the reloaded graph is not parsed at all: what write_adjlist + read_adjlist do to the order (each edge listed once,
+under its earlier endpoint; nodes and edges added line by line) is replayed on the arrays
+(native_tail.reload_arrays, checked against networkx in tests/test_host_logic.py).  The file is still written.
 """
 import sys
 from time import time
 
 import networkx as nx
 
+from . import native_tail
 from . import vercov
 
 
 def get_recovered_non_homologs(homology_graph, graph_file, vercov_func=None, verbose=True):
     independent = set()
     candidates = set(homology_graph.nodes())
+    arrays = getattr(homology_graph, '_nrp_arrays', None)             # taken now: the cover routine empties the graph
+    if arrays is not None and not (arrays[0].size == homology_graph.number_of_nodes() and
+                                   arrays[2].size == 2 * homology_graph.number_of_edges() and native_tail.usable()):
+        arrays = None
     if verbose:
         print('\n [+] Initial independent set = {}, computing vertex cover on remaining {} nodes.'.format(
             len(independent), 0, len(candidates)))
@@ -54,7 +62,10 @@ def get_recovered_non_homologs(homology_graph, graph_file, vercov_func=None, ver
             print('\n [+] Computed vertex cover of size: {} (in {:.4} seconds)'.format(len(cover), time() - t0))
             print(' [+] Loading graph from: {}'.format(graph_file))
         if reloaded is None:
-            reloaded = nx.read_adjlist(graph_file, nodetype=int)
+            if arrays is not None:
+                reloaded = native_tail.graph_from_arrays(*native_tail.reload_arrays(*arrays))
+            else:
+                reloaded = nx.read_adjlist(graph_file, nodetype=int)
         homology_graph = reloaded
 
         fresh = candidates - cover

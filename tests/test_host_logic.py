@@ -240,3 +240,36 @@ def test_native_array_tail_equals_python_loops(n_parts, k, internal):
     assert all(graph[u][v] is graph[v][u] for u in some for v in graph[u])       # one data dict per edge, as add_edge makes
     assembled = hgraph.assemble_graph(structure, ids, False)
     assert list(assembled.nodes()) == list(expect.nodes()) and nx.utils.graphs_equal(assembled, expect)
+
+
+def test_reload_on_arrays_equals_networkx_round_trip(scratch_cwd):
+    """native_tail.reload_arrays against nx.read_adjlist(nx.write_adjlist(G)) on random graphs (isolated nodes, shuffled
+    node order, empty graph)."""
+    import numpy as np
+    from nrpcalc_b200 import native_tail
+    if not native_tail.usable():
+        pytest.skip('libnrptail.so not built')
+    rng = random.Random(5)
+    for trial in range(25):
+        n = rng.choice([0, 1, 5, 60, 800])
+        graph = nx.Graph()
+        order = list(range(n))
+        rng.shuffle(order)
+        for u in order:
+            if rng.random() < 0.7:
+                graph.add_node(u * 3)
+        for _ in range(rng.randrange(0, 3 * n + 1)):
+            a, b = rng.randrange(max(n, 1)) * 3, rng.randrange(max(n, 1)) * 3
+            if a != b:
+                graph.add_edge(a, b)
+        nodes = np.array(list(graph.nodes()), dtype=np.int64)
+        indptr, flat = [0], []
+        for u in graph.nodes():
+            flat.extend(graph[u])
+            indptr.append(len(flat))
+        nx.write_adjlist(graph, './g.txt')
+        want = nx.read_adjlist('./g.txt', nodetype=int)
+        got = native_tail.graph_from_arrays(*native_tail.reload_arrays(nodes, np.array(indptr, dtype=np.int64), np.array(flat, dtype=np.int64)))
+        assert list(want.nodes()) == list(got.nodes())
+        assert [list(want[u]) for u in want.nodes()] == [list(got[u]) for u in got.nodes()]
+        assert nx.utils.graphs_equal(want, got)
