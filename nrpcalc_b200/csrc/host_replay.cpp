@@ -8,6 +8,7 @@
 #include <unordered_map>
 #include <vector>
 #include "cpyset.hpp"
+#include "../../include/nrp_tail.h"
 
 using cpyset::IntSet;
 using cpyset::TupleSet;

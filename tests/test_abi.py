@@ -51,3 +51,18 @@ def test_no_gpu_means_loud_failure():
     import nrpcalc_b200
     with pytest.raises((RuntimeError, _native.NativeError)):
         nrpcalc_b200.finder(['ACGTTGCATGCATGCAAAGTCC', 'TTGCATGCATGCAAAGTCCAAA'], 12, verbose=False)
+
+
+def test_tail_library_exports_every_declared_symbol():
+    """libnrptail.so (host tail, plain C++) exports what include/nrp_tail.h declares."""
+    from nrpcalc_b200 import native_tail
+    if not os.path.exists(native_tail.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    text = open(os.path.join(ROOT, 'include', 'nrp_tail.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    names = sorted(set(re.findall(r'\b(nrp_tail_[a-z_0-9]+)\s*\(', text)))
+    assert len(names) == 7
+    lib = ctypes.CDLL(native_tail.LIB_PATH)
+    for name in names:
+        assert hasattr(lib, name), name
