@@ -1,13 +1,13 @@
 """Wall clock of the PUBLIC Python API (nrpcalc_b200.finder) on random 100-bp parts, next to the literal port of the reference
 (oracle/ref_port.py, graph build only) on the same list: what a user of nrpcalc.finder sees, host tail included.
-    python tools/api_timing.py [n_parts ...]"""
+    python tests/api_timing.py [n_parts ...]"""
 import os
 import random
 import sys
 import tempfile
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # test-side script: it times the oracle port next to the product
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import cases                     # noqa: E402
