@@ -273,3 +273,32 @@ def test_reload_on_arrays_equals_networkx_round_trip(scratch_cwd):
         assert list(want.nodes()) == list(got.nodes())
         assert [list(want[u]) for u in want.nodes()] == [list(got[u]) for u in got.nodes()]
         assert nx.utils.graphs_equal(want, got)
+
+
+def test_native_array_tail_on_many_small_streams():
+    """400 small random streams (tuples of 1-7 ids from a tiny universe: heavy overlap, equal tuples in different orders,
+    repeated ids inside a tuple, subset chains) through the array tail and through the Python loops."""
+    from nrpcalc_b200 import native_tail
+    if not native_tail.usable():
+        pytest.skip('libnrptail.so not built')
+    rng = random.Random(99)
+    for trial in range(400):
+        universe = rng.choice([3, 8, 20, 60, 400])
+        tuples = []
+        for _ in range(rng.randrange(1, 120)):
+            k = rng.choice([1, 1, 1, 2, 2, 3, 4, 7])
+            base = rng.randrange(universe)
+            tuples.append(tuple((base + rng.randrange(0, 4)) % universe if rng.random() < 0.6 else rng.randrange(universe)
+                                for _ in range(k)))
+            if rng.random() < 0.2 and len(tuples[-1]) > 1:                    # a sub-tuple and a permutation of it
+                tuples.append(tuples[-1][:-1])
+                tuples.append(tuples[-1][::-1])
+        nodes, indptr, adj, c_off, c_nodes = native_tail.run(*native_tail.stream_arrays(tuples), want_cliques=True)
+        cliques = [tuple(c) for c in hgraph._replay_cliques_python(iter(tuples))]
+        off, flat = c_off.tolist(), c_nodes.tolist()
+        assert [tuple(flat[off[i]:off[i + 1]]) for i in range(len(off) - 1)] == cliques, trial
+        from collections import deque
+        expect = hgraph._build_homology_graph_python((deque(c) for c in cliques), False)
+        assert nodes.tolist() == list(expect.nodes()), trial
+        bounds, nbrs = indptr.tolist(), adj.tolist()
+        assert [nbrs[bounds[i]:bounds[i + 1]] for i in range(len(bounds) - 1)] == [list(expect[u]) for u in expect.nodes()], trial
