@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <unordered_map>
 #include <vector>
 #include "cpyset.hpp"
@@ -111,8 +112,9 @@ struct TailResult {
 
 // Input: the compressed stream of id tuples in the order the reference meets them (descending first-insertion rank):
 // tuple t = members[start[t] .. start[t] + size[t]).
-void* nrp_tail_run(const int64_t* start, const int64_t* size, int64_t n_tuples, const int64_t* members) {
-  TailResult* R = new TailResult();
+static void* tail_run(const int64_t* start, const int64_t* size, int64_t n_tuples, const int64_t* members) {
+  std::unique_ptr<TailResult> owner(new TailResult());
+  TailResult* R = owner.get();
   const bool timing = std::getenv("NRP_TAIL_TIMING") != nullptr;
   auto t_last = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
@@ -263,15 +265,16 @@ void* nrp_tail_run(const int64_t* start, const int64_t* size, int64_t n_tuples, 
     }
   }
   lap("graph assembly");
-  return R;
+  return owner.release();
 }
 
 // The graph that nx.read_adjlist(nx.write_adjlist(G)) gives (reference recovery.py:26-30): the dump lists every edge once,
 // under its endpoint that comes first in G's node order (networkx generate_adjlist skips neighbours already "seen"), and the
 // parser adds, line by line, the line's node and then its edges (parse_adjlist: add_node, add_edges_from) -- which fixes the
 // node order and every adjacency order of the reloaded graph.  Same simulation on arrays, no text.
-void* nrp_tail_reload(const int64_t* nodes, const int64_t* indptr, const int64_t* adj, int64_t n_nodes) {
-  TailResult* R = new TailResult();
+static void* tail_reload(const int64_t* nodes, const int64_t* indptr, const int64_t* adj, int64_t n_nodes) {
+  std::unique_ptr<TailResult> owner(new TailResult());
+  TailResult* R = owner.get();
   int64_t max_id = 0;
   for (int64_t i = 0; i < n_nodes; ++i) max_id = nodes[i] > max_id ? nodes[i] : max_id;
   IdIndex old_index, new_index;
@@ -307,7 +310,15 @@ void* nrp_tail_reload(const int64_t* nodes, const int64_t* indptr, const int64_t
     R->indptr.push_back((int64_t)R->adj.size());
   }
   R->clique_off.push_back(0);
-  return R;
+  return owner.release();
+}
+
+// no C++ exception crosses the C ABI: NULL = out of memory (the caller falls back to the Python loops)
+void* nrp_tail_run(const int64_t* start, const int64_t* size, int64_t n_tuples, const int64_t* members) {
+  try { return tail_run(start, size, n_tuples, members); } catch (...) { return nullptr; }
+}
+void* nrp_tail_reload(const int64_t* nodes, const int64_t* indptr, const int64_t* adj, int64_t n_nodes) {
+  try { return tail_reload(nodes, indptr, adj, n_nodes); } catch (...) { return nullptr; }
 }
 
 void nrp_tail_sizes(void* handle, int64_t out[4]) {

@@ -236,8 +236,14 @@ def assemble_graph(structure, ids, verbose):
     """Ordered stream -> clique replay -> graph (hgraph.py:96-200).  On compact arrays with a layout-exact model of CPython's
     sets when libnrptail.so is built and its self-check against the Python loops passed (native_tail.py); through real
     CPython containers otherwise."""
+    arrays = None
     if native_tail.usable():
-        nodes, indptr, adj, clique_off, _ = native_tail.run(*ordered_stream_arrays(structure, ids), want_cliques=True)
+        try:
+            arrays = native_tail.run(*ordered_stream_arrays(structure, ids), want_cliques=True)
+        except MemoryError:                                           # the library ran out of memory: the Python loops
+            arrays = None
+    if arrays is not None:
+        nodes, indptr, adj, clique_off, _ = arrays
         graph = native_tail.graph_from_arrays(nodes, indptr, adj)
         graph._nrp_arrays = (nodes, indptr, adj)                      # recovery derives the dumped-and-reloaded graph from these
         if verbose:                                                   # what the per-clique counter leaves on the terminal

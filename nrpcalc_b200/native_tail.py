@@ -56,6 +56,8 @@ def run(start, size, members, want_cliques=False):
 
 
 def _collect(lib, handle, want_cliques=False):
+    if not handle:
+        raise MemoryError('libnrptail: out of memory')
     try:
         sizes = np.zeros(4, dtype=np.int64)
         lib.nrp_tail_sizes(handle, sizes.ctypes.data)

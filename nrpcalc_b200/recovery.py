@@ -63,8 +63,11 @@ def get_recovered_non_homologs(homology_graph, graph_file, vercov_func=None, ver
             print(' [+] Loading graph from: {}'.format(graph_file))
         if reloaded is None:
             if arrays is not None:
-                reloaded = native_tail.graph_from_arrays(*native_tail.reload_arrays(*arrays))
-            else:
+                try:
+                    reloaded = native_tail.graph_from_arrays(*native_tail.reload_arrays(*arrays))
+                except MemoryError:
+                    reloaded = None
+            if reloaded is None:
                 reloaded = nx.read_adjlist(graph_file, nodetype=int)
         homology_graph = reloaded
 
