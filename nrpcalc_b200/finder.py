@@ -104,8 +104,12 @@ def nrp_finder(seq_list, homology, allow_internal_repeat=False, background=None,
     seq_file = './{}/seq_list.txt'.format(current_uuid)
     graph_file = './{}/repeat_graph.txt'.format(current_uuid)
 
-    homology_graph = hgraph.get_homology_graph(seq_list, background, homology, allow_internal_repeat, seq_file, verbose)
-    indi_seqs_indx = recovery.get_recovered_non_homologs(homology_graph, graph_file, vercov_func, verbose)
+    try:
+        homology_graph = hgraph.get_homology_graph(seq_list, background, homology, allow_internal_repeat, seq_file, verbose)
+        indi_seqs_indx = recovery.get_recovered_non_homologs(homology_graph, graph_file, vercov_func, verbose)
+    except BaseException:
+        projector.remove_proj_dir()        # the reference leaves ./<uuid>/ behind when the build raises; the error itself is unchanged
+        raise
 
     parts_dict = {}
     with open(seq_file, 'r') as infile:

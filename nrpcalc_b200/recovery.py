@@ -75,8 +75,9 @@ def get_recovered_non_homologs(homology_graph, graph_file, vercov_func=None, ver
         independent |= fresh
         candidates = cover
         before = len(candidates)
-        for node in fresh:
-            candidates.difference_update(homology_graph[node])
+        neighbours = homology_graph._adj if type(getattr(homology_graph, '_adj', None)) is dict else homology_graph
+        for node in fresh:                       # the adjacency dict itself: same keys as graph[node], no view object per node
+            candidates.difference_update(neighbours[node])
         after = len(candidates)
         if verbose:
             print(' [+] Current independent set size:  {}'.format(len(independent)))

@@ -35,9 +35,14 @@ def _top_degree(degree_pairs):
 
 
 def _top_degree_nodes(graph, among=None):
+    """graph.degree() / graph.degree(nbunch) yield (node, len(adj[node])) in node order resp. nbunch order for a graph without
+    self-loops (the homology graph has none: hgraph.py:176-184 never pairs a node with itself); read off the adjacency dicts."""
+    adj = getattr(graph, '_adj', None)
+    if type(adj) is not dict:
+        return _top_degree(graph.degree() if among is None else graph.degree(among))
     if among is None:
-        return _top_degree(graph.degree())
-    return _top_degree(graph.degree(among))
+        return _top_degree((node, len(nbrs)) for node, nbrs in adj.items())
+    return _top_degree((node, len(adj[node])) for node in among if node in adj)
 
 
 def _low_degree_neighbours(graph, node):

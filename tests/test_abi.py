@@ -40,7 +40,7 @@ def test_binding_matches_header():
         assert getattr(lib, name).argtypes is not None or name in ('nrp_version', 'nrp_last_error'), name
 
 
-def test_no_gpu_means_loud_failure():
+def test_no_gpu_means_loud_failure(scratch_cwd):
     """Without a CUDA device the product must raise, never fall back to a CPU path."""
     import torch
     if torch.cuda.is_available():
