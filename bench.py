@@ -13,8 +13,13 @@ default: 1M x 100 bp, Lmax=16, internal_repeats=False).
   roofline  the dominant kernel's algorithmic bytes / its CUDA-event duration against the measured HBM copy peak
   cpu_baseline  oracle/nrp_oracle.c (hash-table restatement of the reference's algorithm) on the host cores
 
---impl reference times the literal pure-Python port of the reference (oracle/ref_port.py; the reference itself is
-pure Python and is not present on the GPU box) on a bounded sample of the same workload.
+  parity    the full result of the last build (flags, groups with ranks, last unshared windows, edges) against
+            oracle/nrp_oracle.c on the SAME full-size batch (default for c1/c2; --verify forces it for c3/c4/dup,
+            --no-verify skips it); a mismatch makes the run exit non-zero
+
+--impl reference times the UNMODIFIED reference (hgraph.get_homology_graph of the offline install under baseline/_ref,
+or /root/reference in the development container) on a bounded sample of the same workload, one core like the reference;
+without a reference tree it times the literal pure-Python port (oracle/ref_port.py) and says so.
 """
 import argparse
 import json
@@ -40,7 +45,15 @@ CONFIGS = {
                label='Finder mode: 1M 200-bp parts with a 5-Mbp synthetic background genome k-mer set, Lmax=15'),
     'c4': dict(n=10_000_000, length=100, Lmax=20, internal_repeats=False, genome=0, seed=4,
                label='Finder mode: 10M synthetic 100-bp parts, Lmax=20, hash-sharded across 2/4/8 B200'),
+    'c5': dict(n=50_000_000, length=(50, 300), Lmax=24, internal_repeats=False, genome=0, seed=5,
+               label='Finder mode: 50M variable-length (50-300 bp) parts, Lmax=24, 8xB200 all-to-all scaling sweep'),
+    # not a BASELINE shape: planted shared motifs, so that the fixed regions of the direct placement overflow and the exact
+    # (histogram) path with the global sort runs -- the workload real part libraries resemble more than i.i.d. DNA
+    'dup': dict(n=1_000_000, length=100, Lmax=16, internal_repeats=False, genome=0, seed=6, dup_motifs=64, dup_fraction=0.25,
+                label='Finder mode: 1M 100-bp parts, Lmax=16, 25 % of the parts carry one of 64 shared 40-bp motifs (duplicate-heavy)'),
 }
+# oracle passes over slices of the key space for the full-size verification (bounds the host memory of the C hash table)
+VERIFY_SLICES = {'c1': 1, 'c2': 4, 'c3': 8, 'c4': 32, 'c5': 256, 'dup': 4}
 
 
 def measured_peak_gbs():
@@ -118,7 +131,20 @@ def make_workload(cfg, n_parts=None):
     n = cfg['n'] if n_parts is None else n_parts
     if isinstance(cfg['length'], tuple):
         return cases.random_varlen_buffer(n, cfg['length'][0], cfg['length'][1], cfg['seed'])
-    return cases.random_dna_buffer(n, cfg['length'], cfg['seed'])
+    buf, off = cases.random_dna_buffer(n, cfg['length'], cfg['seed'])
+    if cfg.get('dup_motifs'):
+        # plant one of a few shared motifs at a random position of a fraction of the parts (every shared window collides)
+        rng = np.random.default_rng(cfg['seed'] + 1000)
+        motif_len = 40
+        motifs = cases.random_dna_buffer(cfg['dup_motifs'], motif_len, cfg['seed'] + 2000)[0].reshape(cfg['dup_motifs'], motif_len)
+        buf = buf.copy()
+        chosen = np.nonzero(rng.random(n) < cfg['dup_fraction'])[0]
+        which = rng.integers(0, cfg['dup_motifs'], size=chosen.size)
+        at = rng.integers(0, cfg['length'] - motif_len + 1, size=chosen.size)
+        view = buf.reshape(n, cfg['length'])
+        cols = at[:, None] + np.arange(motif_len)[None, :]
+        view[chosen[:, None], cols] = motifs[which]
+    return buf, off
 
 
 def background_keys(cfg, ctx=None, timing=None):
@@ -155,35 +181,71 @@ def algorithmic_bytes(total_len, m, key_bytes, packed):
 
 
 def run_reference_arm(args, cfg):
-    """Literal pure-Python port of the reference's graph-build path on a bounded sample (1 core, like the reference)."""
-    from oracle import ref_port
+    """The reference's own graph-build path (nrpcalc/base/hgraph.py:202-249, get_homology_graph) on a bounded sample of the
+    workload, one core (the reference is single-threaded pure Python).  The unmodified reference is imported from the offline
+    install under baseline/_ref (or /root/reference in the development container) with Bio / RNA / ShareDB stubbed
+    (tests/golden/refshim.py); without a reference tree the literal port oracle/ref_port.py is timed instead and the line says so."""
+    import tempfile
     import cases
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+    import refshim
     k = cfg['Lmax'] + 1
     sample_parts = max(1000, min(cfg['n'], args.reference_parts))
     buf, off = make_workload(cfg, sample_parts)
     parts = cases.buffer_to_list(buf, off)
-    bg = None
-    if cfg['genome']:
-        bg = ref_port.SetBackground(k)
-        bg.multiadd([cases.random_genome(min(cfg['genome'], 200_000), cfg['seed'] * 11)])
     m = int(np.maximum(np.diff(off) - k + 1, 0).sum())
-    times = []
-    for step in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        graph, _ = ref_port.homology_graph(list(parts), bg, k, cfg['internal_repeats'])
-        dt = time.perf_counter() - t0
-        if step >= args.warmup:
-            times.append(dt)
+    genome = cases.random_genome(min(cfg['genome'], 200_000), cfg['seed'] * 11) if cfg['genome'] else None
+    cwd = os.getcwd()
+    scratch = tempfile.mkdtemp(prefix='nrp_refarm_')
+    os.chdir(scratch)
+    try:
+        if refshim.reference_available():
+            ref = refshim.load_reference()
+            from nrpcalc.base import hgraph as ref_hgraph
+            kind, where = 'reference', 'unmodified nrpcalc {} from {}'.format(getattr(ref, '__version__', '1.7.6'), os.path.relpath(refshim.REFERENCE_ROOT, ROOT)
+                                                                                 if refshim.REFERENCE_ROOT.startswith(ROOT) else refshim.REFERENCE_ROOT)
+            bg = None
+            if genome:
+                bg = ref.background(path=os.path.join(scratch, 'bg'), Lmax=cfg['Lmax'], verbose=False)
+                bg.add(genome)
+
+            def one_step():
+                return ref_hgraph.get_homology_graph(list(parts), bg, k, cfg['internal_repeats'], os.path.join(scratch, 'seq_list.txt'), False)
+        else:
+            from oracle import ref_port
+            kind, where = 'port', 'oracle/ref_port.py: literal pure-Python restatement (no reference tree on this box)'
+            bg = None
+            if genome:
+                bg = ref_port.SetBackground(k)
+                bg.multiadd([genome])
+
+            def one_step():
+                return ref_port.homology_graph(list(parts), bg, k, cfg['internal_repeats'])[0]
+        times = []
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            one_step()
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+    finally:
+        os.chdir(cwd)
+        import shutil
+        shutil.rmtree(scratch, ignore_errors=True)
     ms = 1e3 * sum(times) / len(times)
     value = m / (ms * 1e-3)
-    sample = '{} of {} parts ({} k-mers) per step, get_homology_graph equivalent incl. clique tail'.format(sample_parts, cfg['n'], m)
+    total_m = cfg['n'] * (m / sample_parts)
+    sample = ('{} of {} parts ({} k-mers) per step through hgraph.get_homology_graph (table + clique tail + nx.Graph); the path is linear in '
+              'the number of k-mers, so the full workload ({:.3g} k-mers) extrapolates to {:.0f} s per step at this rate').format(
+                  sample_parts, cfg['n'], m, total_m, total_m / value)
     line = {'impl': 'reference', 'metric': 'finder_graph_build_kmers_per_s', 'value': value, 'unit': 'k-mers/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'u64' if k > 16 else 'u32', 'data': 'synthetic',
-            'config': {'workload': cfg['label'], 'n_parts': cfg['n'], 'Lmax': cfg['Lmax']},
+            'config': {'workload': cfg['label'], 'n_parts': cfg['n'], 'Lmax': cfg['Lmax'], 'sample_parts': sample_parts,
+                       'background_bp': len(genome) if genome else 0},
             'parts_per_s': sample_parts / (ms * 1e-3),
-            'cpu_baseline': {'value': value, 'unit': 'k-mers/s', 'cores': 1, 'kind': 'port', 'sample': sample,
-                             'port': 'oracle/ref_port.py: literal pure-Python restatement; the reference (pure Python, single-threaded) is not on the GPU box'},
+            'cpu_baseline': {'value': value, 'unit': 'k-mers/s', 'cores': 1, 'kind': kind, 'sample': sample, 'source': where,
+                             'host_cores_available': os.cpu_count()},
             'e2e': {'value': value, 'unit': 'k-mers/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
@@ -204,6 +266,52 @@ def cpu_baseline(cfg, buf, off, k):
                 n_sample, cfg['n'], res['n_records'], dt)}
 
 
+def verify_against_oracle(cfg_name, cfg, buf, off, ids, k, res, records, bg_keys, bg_K):
+    """Full-size parity: the result the device produced for the WHOLE batch against oracle/nrp_oracle.c (checker only)."""
+    from oracle import c_oracle
+    import parity
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    want = c_oracle.build_table(buf, off, k, cfg['internal_repeats'], bg_keys, bg_K, n_threads=cores, want_groups=True,
+                                n_slices=VERIFY_SLICES.get(cfg_name, 4))
+    t1 = time.perf_counter()
+    got = parity.canonical(res.flags, res.indptr, res.members, res.first_window, res.keys, res.last_single, res.edges, None, records)
+    ref = parity.from_c_oracle(want, ids)
+    cmp = parity.compare(got, ref)
+    return {'vs_oracle': cmp['all'], 'components': cmp, 'digest': parity.digest(got), 'oracle_digest': parity.digest(ref),
+            'checked': parity.summary(got), 'oracle': 'oracle/nrp_oracle.c on the full batch ({} parts), {} threads, {} key-space passes, {:.1f} s'.format(
+                cfg['n'], cores, VERIFY_SLICES.get(cfg_name, 4), t1 - t0),
+            'compare_s': time.perf_counter() - t1}
+
+
+def finder_api_timing(n_parts, length, Lmax, seed):
+    """What a user of the reference sees: nrpcalc_b200.finder(list[str], Lmax) wall clock on a cut of the workload, with the
+    library's own split into device call, order-exact replay, recovery and marshalling (hgraph.LAST_TIMINGS)."""
+    import random
+    import tempfile
+    import cases
+    import nrpcalc_b200
+    from nrpcalc_b200 import hgraph
+    parts = cases.random_parts(n_parts, length, seed)
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp(prefix='nrp_api_'))
+    try:
+        random.seed(1)
+        t0 = time.perf_counter()
+        found = nrpcalc_b200.finder(parts, Lmax, internal_repeats=False, vercov='nrp2', verbose=False)
+        wall = time.perf_counter() - t0
+    finally:
+        os.chdir(cwd)
+    info = dict(hgraph.last_build_info)
+    run = dict(nrpcalc_b200._finder.last_run_info)
+    return {'parts': n_parts, 'part_len': length, 'Lmax': Lmax, 'vercov': 'nrp2', 'wall_s': round(wall, 4), 'toolbox': len(found),
+            'kmers': info.get('records'), 'device_ms': info.get('device_ms'),
+            'marshal_and_device_call_s': round(info.get('call_s', 0.0), 4), 'clique_replay_and_graph_s': round(info.get('replay_s', 0.0), 4),
+            'recovery_s': round(run.get('recovery_s', 0.0), 4), 'checks_sidefiles_output_s': round(max(0.0, wall - run.get('graph_s', 0.0) - run.get('recovery_s', 0.0)), 4),
+            'native_tail': info.get('native_tail'),
+            'note': 'host wall clock of the unchanged (order-exact) tail dominates; the graph-build metric is the device / C-ABI figure'}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -214,6 +322,9 @@ def main():
     ap.add_argument('--reference-parts', type=int, default=20_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-edges', action='store_true')
+    ap.add_argument('--verify', action='store_true', help='compare the full result with oracle/nrp_oracle.c (default for c1/c2 at N=1; N>1: also against the oracle, besides the single-GPU result)')
+    ap.add_argument('--no-verify', action='store_true')
+    ap.add_argument('--api-parts', type=int, default=100_000, help='parts of the finder() API timing leg (0 = skip)')
     ap.add_argument('--h2d-chunks', type=int, default=8, help='e2e leg: pieces of the streamed host-to-device copy (1 = one blocking copy)')
     ap.add_argument('--e2e-entry', choices=('auto', 'offsets', 'uniform'), default='auto',
                     help='e2e leg: nrp_load_parts[_streamed] with an offsets array, or nrp_load_parts_uniform (parts of one length; auto = uniform when the config has one length)')

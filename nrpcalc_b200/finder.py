@@ -1,7 +1,17 @@
-"""Finder-mode orchestrator -- host wrapper with the behaviour of reference nrpcalc/base/finder.py:15-196:
-argument checks, scratch project directory, graph build (the GPU hot path), independent-set recovery, output
-dictionary in seq_list.txt order and the optional FASTA file."""
+"""Finder-mode job: validate the request, build the repeat graph on the GPU, recover an independent set, report.
+
+Stand-alone counterpart of the reference's orchestrator (nrpcalc/base/finder.py:68-196) for installations that do not
+have the reference package; when the reference IS installed, `nrpcalc_b200.patch()` rebinds only the graph-build seam
+(hgraph.get_homology_graph) and the reference's own finder / recovery / vercov run unchanged.
+
+Behaviour kept (what a caller can observe, stdout aside): the caller's list is not consumed; a request that fails
+validation raises RuntimeError('Invalid Constraints, or Background'); a closed background is reported but only raises
+later, from the membership test (reference finder.py:107-116 sets an unused name); the job keeps seq_list.txt and
+repeat_graph.txt in ./<uuid>/ while it runs; the result maps index -> upper-cased part in processing order; the optional
+FASTA file has '>index N' headers and 80-column lines (finder.py:175-189).
+"""
 import textwrap
+import time
 import uuid
 
 from . import hgraph
@@ -9,123 +19,78 @@ from . import kmerSetDB
 from . import projector
 from . import recovery
 
+VERTEX_COVERS = ('2apx', 'nrpG', 'nrp2')
 
-def _check_finder_constraints(seq_list, homology, allow_internal_repeat, vercov_func):
-    for seq in seq_list:
-        if not isinstance(seq, str):
-            print(' [ERROR]    Parts in Sequence List must be string, not {}'.format(type(seq)))
-            print(' [SOLUTION] Try correcting Lmax\n')
-            return False
+# timings of the last job (seconds): graph_s (marshalling + device + replay), recovery_s, output_s
+last_run_info = {}
+
+
+def _problems(seq_list, homology, internal_repeats, background, vercov, output_file):
+    """Yield (what is wrong, what to do) for every rule the request breaks, in the reference's order of checks
+    (finder.py:15-66, 107-125)."""
+    bad = next((seq for seq in seq_list if not isinstance(seq, str)), None)
+    if bad is not None:
+        yield 'every part must be a str, found {}'.format(type(bad).__name__), 'pass the parts as strings'
     if not isinstance(homology, int):
-        print('\n [ERROR]    Lmax must be an integer, not {}'.format(type(homology)))
-        print(' [SOLUTION] Try correcting Lmax\n')
-        return False
-    if homology - 1 < 5:
-        print('\n [ERROR]    Lmax must be greater than 4, not {}'.format(homology - 1))
-        print(' [SOLUTION] Try correcting Lmax\n')
-        return False
-    if allow_internal_repeat not in [True, False]:
-        print('\n [ERROR]    Internal Repeat must be boolean, not {}'.format(type(allow_internal_repeat)))
-        print(' [SOLUTION] Try correcting Internal Repeat\n')
-        return False
-    return True
-
-
-def _check_finder_arguments(vercov_func, output_file):
-    if not isinstance(vercov_func, str):
-        print(' [ERROR]    Vertex Cover Routine Name must be string, not {}'.format(type(vercov_func)))
-        print(' [SOLUTION] Try correcting Vertex Cover Routine Name\n')
-        return False
-    if vercov_func not in ['2apx', 'nrpG', 'nrp2']:
-        print('\n [ERROR]    Vertex Cover Routine Name must be \'2apx\', \'nrpG\', or \'nrp2\', not \'{}\''.format(vercov_func))
-        print(' [SOLUTION] Try correcting Vertex Cover Routine Name\n')
-        return False
+        yield 'Lmax must be an int, not {}'.format(type(homology).__name__), 'pass an integer Lmax'
+    elif homology - 1 < 5:
+        yield 'Lmax must be at least 5, not {}'.format(homology - 1), 'raise Lmax'
+    if internal_repeats not in (True, False):
+        yield 'internal_repeats must be a bool, not {}'.format(type(internal_repeats).__name__), 'pass True or False'
+    if background is not None and not isinstance(background, kmerSetDB.kmerSetDB):
+        yield 'background is not a kmerSetDB', 'create it with nrpcalc_b200.background(...)'
+    if not isinstance(vercov, str) or vercov not in VERTEX_COVERS:
+        yield 'vercov must be one of {}, not {!r}'.format(', '.join(VERTEX_COVERS), vercov), 'pick one of the three routines'
     if output_file is not None and not isinstance(output_file, str):
-        print('\n [ERROR]    Output File must be a string or None, not {}'.format(type(output_file)))
-        print(' [SOLUTION] Try correcting Output File\n')
-        return False
-    return True
+        yield 'output_file must be a str or None, not {}'.format(type(output_file).__name__), 'pass a path or None'
+
+
+def _validate(seq_list, homology, internal_repeats, background, vercov, output_file, verbose):
+    if verbose:
+        print('\n[Checking Request]\n parts: {}   Lmax: {}   internal repeats: {}   background: {}   vertex cover: {}   output: {}'.format(
+            len(seq_list), homology - 1 if isinstance(homology, int) else homology, internal_repeats, background, vercov, output_file))
+    problem = next(_problems(seq_list, homology, internal_repeats, background, vercov, output_file), None)
+    if problem is not None:
+        print('\n [ERROR]    {}\n [SOLUTION] {}\n'.format(*problem))
+        raise RuntimeError('Invalid Constraints, or Background')
+    if isinstance(background, kmerSetDB.kmerSetDB) and not background.ALIVE:
+        print('\n [WARNING]  the background is closed or dropped; the membership test will raise')
+    if verbose:
+        print(' request accepted\n')
+
+
+def _write_fasta(path, parts_dict):
+    with open(path, 'w') as out:
+        for index, seq in parts_dict.items():
+            out.write('>index {}\n{}\n'.format(index, '\n'.join(textwrap.wrap(seq, 80))))
 
 
 def nrp_finder(seq_list, homology, allow_internal_repeat=False, background=None, vercov_func=None, output_file=None,
                verbose=True, check_constraints=True):
     if verbose:
-        print('\n[Non-Repetitive Parts Calculator - Finder Mode]')
-    seq_list = list(seq_list)          # the caller's list is never consumed (finder.py:82)
-    ok = True
-
+        print('\n[Non-Repetitive Parts Calculator - Finder Mode, B200]')
+    seq_list = list(seq_list)
     if check_constraints:
-        if verbose:
-            print('\n[Checking Constraints]')
-            print(' Sequence List   : {} parts'.format(len(seq_list)))
-            print('          Lmax   : {} bp'.format(homology - 1))
-            print(' Internal Repeats: {}'.format(allow_internal_repeat))
-        ok = _check_finder_constraints(seq_list, homology, allow_internal_repeat, vercov_func)
-        if verbose:
-            print(' Check Status: FAIL\n' if not ok else '\n Check Status: PASS')
+        _validate(seq_list, homology, allow_internal_repeat, background, vercov_func, output_file, verbose)
 
-        if ok and background is not None:
-            if verbose:
-                print('\n[Checking Background]\n Background: {}'.format(background))
-            if isinstance(background, kmerSetDB.kmerSetDB):
-                if not background.ALIVE:
-                    # the reference reports this but does not abort here (finder.py:111-116 sets an unused name);
-                    # the RuntimeError surfaces later from the membership test
-                    print('\n [ERROR]    Background is closed or dropped')
-                    print(' [SOLUTION] Try using an open Background\n')
-                    if verbose:
-                        print(' Check Status: FAIL\n')
-                elif verbose:
-                    print('\n Check Status: PASS')
-            else:
-                ok = False
-                print('\n [ERROR]    Background Object is INVALID')
-                print(' [SOLUTION] Try instantiating background via nrpcalc.background(...)\n')
-                if verbose:
-                    print(' Check Status : FAIL\n')
-
-        if ok:
-            if verbose:
-                print('\n[Checking Arguments]')
-                print('   Vertex Cover: {}'.format(vercov_func))
-                print('   Output  File: {}'.format(output_file))
-            ok = _check_finder_arguments(vercov_func, output_file)
-            if verbose:
-                print(' Check Status: FAIL\n' if not ok else '\n Check Status: PASS')
-
-        if not ok:
-            raise RuntimeError('Invalid Constraints, or Background')
-
-    if verbose:
-        print()
-
-    current_uuid = str(uuid.uuid4())
-    projector.setup_proj_dir(current_uuid)
-    seq_file = './{}/seq_list.txt'.format(current_uuid)
-    graph_file = './{}/repeat_graph.txt'.format(current_uuid)
-
-    try:
-        homology_graph = hgraph.get_homology_graph(seq_list, background, homology, allow_internal_repeat, seq_file, verbose)
-        indi_seqs_indx = recovery.get_recovered_non_homologs(homology_graph, graph_file, vercov_func, verbose)
-    except BaseException:
-        projector.remove_proj_dir()        # the reference leaves ./<uuid>/ behind when the build raises; the error itself is unchanged
-        raise
-
-    parts_dict = {}
-    with open(seq_file, 'r') as infile:
-        for line in infile:
-            index, seq = line.strip().split(',')
-            index = int(index)
-            if index in indi_seqs_indx:
-                parts_dict[index] = seq
-
-    if output_file:
-        with open(output_file, 'w') as outfile:
-            for index, seq in parts_dict.items():
-                outfile.write('>index {}\n'.format(index))
-                outfile.write('{}\n'.format('\n'.join(textwrap.wrap(seq, 80))))
-
-    projector.remove_proj_dir()
+    scratch = projector.ScratchDir(str(uuid.uuid4()))
+    with scratch:
+        seq_file, graph_file = scratch.file('seq_list.txt'), scratch.file('repeat_graph.txt')
+        t0 = time.perf_counter()
+        graph = hgraph.get_homology_graph(seq_list, background, homology, allow_internal_repeat, seq_file, verbose)
+        t1 = time.perf_counter()
+        chosen = recovery.get_recovered_non_homologs(graph, graph_file, vercov_func, verbose)
+        t2 = time.perf_counter()
+        # the unique parts in processing order: what seq_list.txt holds (the reference re-reads the file, finder.py:175-181)
+        ordered = hgraph.last_build_info.get('parts')
+        if ordered is None:
+            with open(seq_file) as lines:
+                ordered = [(int(index), seq) for index, seq in (line.rstrip('\n').split(',') for line in lines)]
+        parts_dict = {index: seq for index, seq in ordered if index in chosen}
+        if output_file:
+            _write_fasta(output_file, parts_dict)
+    last_run_info.clear()
+    last_run_info.update({'graph_s': t1 - t0, 'recovery_s': t2 - t1, 'output_s': time.perf_counter() - t2})
     if verbose:
         print('\nNon-Repetitive Toolbox Size: {}'.format(len(parts_dict)))
     return parts_dict

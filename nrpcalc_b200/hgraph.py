@@ -427,7 +427,8 @@ def get_homology_graph(seq_list, background, homology, internal_repeats, seq_fil
     last_build_info.clear()
     last_build_info.update({'records': structure.records, 'device_ms': structure.timings['total'], 'call_s': t_device,
                             'timings': dict(structure.timings), 'counts': dict(structure.counts),
-                            'replay_s': time() - t0 - t_device})
+                            'replay_s': time() - t0 - t_device, 'parts': parts,
+                            'native_tail': getattr(graph, '_nrp_arrays', None) is not None})
     if verbose:
         print('\nBuilt homology graph in {:2.4} seconds. [Edges = {}] [Nodes = {}]'.format(
             time() - t0, graph.number_of_edges(), graph.number_of_nodes()))

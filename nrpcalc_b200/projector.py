@@ -1,29 +1,40 @@
-"""Scratch project directory of one Finder job (mirrors reference nrpcalc/base/projector.py:1-19).
+"""Scratch directory of one Finder job.
 
-finder() keeps two side files in ./<uuid>/: seq_list.txt (written by the graph builder, re-read for the
-output dict) and repeat_graph.txt (adjacency-list dump used to restore the graph after each vertex-cover
-round).  The directory is removed at the end of the job and, as a safety net, at interpreter exit.
+The reference keeps two side files of a job in ./<uuid>/ below the current directory (nrpcalc/base/projector.py:7-19;
+seq_list.txt is re-read for the output dict, repeat_graph.txt restores the graph after each vertex-cover round) and
+removes the directory when the job ends.  Here the directory is a context manager: it disappears when the job leaves the
+`with` block, whether it returned or raised, and an atexit hook sweeps whatever an interrupted interpreter left behind.
 """
 import atexit
 import os
 import shutil
 
-current_uuid = None
+_live = set()
 
 
-def setup_proj_dir(uuid):
-    global current_uuid
-    current_uuid = uuid
-    directory = './{}/'.format(current_uuid)
-    if not os.path.exists(directory):
-        os.makedirs(directory)
+class ScratchDir(object):
+    """`with ScratchDir(name) as root:` creates ./<name>/ and removes it on the way out."""
+
+    def __init__(self, name):
+        self.root = os.path.join('.', name)
+
+    def __enter__(self):
+        os.makedirs(self.root, exist_ok=True)
+        _live.add(os.path.abspath(self.root))
+        return self.root
+
+    def __exit__(self, exc_type, exc, tb):
+        path = os.path.abspath(self.root)
+        shutil.rmtree(path, ignore_errors=True)
+        _live.discard(path)
+        return False
+
+    def file(self, name):
+        return '{}/{}'.format(self.root, name)
 
 
 @atexit.register
-def remove_proj_dir():
-    global current_uuid
-    if current_uuid is None:
-        return
-    directory = './{}/'.format(current_uuid)
-    if os.path.isdir(directory):
-        shutil.rmtree(directory)
+def _sweep():
+    for path in list(_live):
+        shutil.rmtree(path, ignore_errors=True)
+        _live.discard(path)

@@ -102,6 +102,7 @@ static int bg_has(const uint64_t* bg, int64_t n, uint64_t key) {
 typedef struct {
   const uint8_t* ascii; const int64_t* off; int64_t n_parts; int k; int internal_repeats;
   const uint64_t* bg; int64_t n_bg; int bg_K; int n_threads; int tid;
+  int n_slices, slice;     /* only keys with (mix(key) >> 20) % n_slices == slice enter the table (bounds the memory of one pass) */
   int64_t max_len, m_max;
   uint8_t* flags; int32_t* last_single;
   table_t* table; int64_t n_records;
@@ -151,11 +152,12 @@ static void* table_worker(void* arg) {
   job_t* jb = (job_t*)arg;
   table_t* tb = jb->table;
   const int n_threads = jb->n_threads, t = jb->tid;
-  uint64_t want = (uint64_t)(2 * jb->m_max / n_threads + jb->m_max / 8) + 64, cap = 64;
+  const int64_t m_mine = jb->m_max / (jb->n_slices > 1 ? jb->n_slices : 1);
+  uint64_t want = (uint64_t)(2 * m_mine / n_threads + m_mine / 8) + 64, cap = 64;
   while (cap < want) cap <<= 1;
   tb->slots = (slot_t*)calloc(cap, sizeof(slot_t));
   tb->mask = cap - 1;
-  tb->pool_cap = (uint64_t)(jb->m_max / n_threads + jb->m_max / 8) + 64;
+  tb->pool_cap = (uint64_t)(m_mine / n_threads + m_mine / 8) + 64;
   tb->pool_part = (uint32_t*)malloc(sizeof(uint32_t) * tb->pool_cap);
   tb->pool_next = (uint32_t*)malloc(sizeof(uint32_t) * tb->pool_cap);
   uint64_t* win = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(jb->max_len + 1));
@@ -165,6 +167,7 @@ static void* table_worker(void* arg) {
     const int64_t w = part_windows(jb->ascii + jb->off[p], jb->off[p + 1] - jb->off[p], jb->k, win, NULL);
     for (int64_t j = 0; j < w; ++j) {
       const uint64_t key = win[j], h = mix(key);
+      if (jb->n_slices > 1 && (int)(((h >> 20) & 0xfffffu) % (uint64_t)jb->n_slices) != jb->slice) continue;
       if (n_threads > 1 && (int)((h >> 40) % (uint64_t)n_threads) != t) continue;
       ++n_records;
       if (tb->pool_used == tb->pool_cap) {
@@ -203,10 +206,13 @@ static void run_threads(void* (*fn)(void*), job_t* jobs, int n_threads) {
   free(th);
 }
 
-void* nrp_oracle_build(const uint8_t* ascii, const int64_t* off, int64_t n_parts, int k, int internal_repeats,
-                       const uint64_t* bg_sorted, int64_t n_bg, int bg_K, int n_threads,
-                       uint8_t* flags, int32_t* last_single) {
+/* One pass over slice `slice` of `n_slices` slices of the key space.  flags_given != 0: `flags` and `last_single` come from
+ * an earlier pass over another slice (flags are complete after the first pass; last_single is max-accumulated). */
+void* nrp_oracle_build_slice(const uint8_t* ascii, const int64_t* off, int64_t n_parts, int k, int internal_repeats,
+                             const uint64_t* bg_sorted, int64_t n_bg, int bg_K, int n_threads,
+                             uint8_t* flags, int32_t* last_single, int n_slices, int slice, int flags_given) {
   if (n_threads < 1) n_threads = 1;
+  if (n_slices < 1) n_slices = 1;
   int64_t max_len = 0, m_max = 0;
   for (int64_t p = 0; p < n_parts; ++p) {
     int64_t len = off[p + 1] - off[p];
@@ -219,11 +225,11 @@ void* nrp_oracle_build(const uint8_t* ascii, const int64_t* off, int64_t n_parts
   o->tables = (table_t*)calloc((size_t)n_threads, sizeof(table_t));
   job_t* jobs = (job_t*)calloc((size_t)n_threads, sizeof(job_t));
   for (int t = 0; t < n_threads; ++t) {
-    job_t jb = {ascii, off, n_parts, k, internal_repeats, bg_sorted, n_bg, bg_K, n_threads, t, max_len, m_max,
+    job_t jb = {ascii, off, n_parts, k, internal_repeats, bg_sorted, n_bg, bg_K, n_threads, t, n_slices, slice, max_len, m_max,
                 flags, last_single, &o->tables[t], 0};
     jobs[t] = jb;
   }
-  run_threads(flags_worker, jobs, n_threads);
+  if (!flags_given) run_threads(flags_worker, jobs, n_threads);
   run_threads(table_worker, jobs, n_threads);
   for (int t = 0; t < n_threads; ++t) o->n_records += jobs[t].n_records;
   free(jobs);
@@ -241,6 +247,12 @@ void* nrp_oracle_build(const uint8_t* ascii, const int64_t* off, int64_t n_parts
     }
   }
   return o;
+}
+
+void* nrp_oracle_build(const uint8_t* ascii, const int64_t* off, int64_t n_parts, int k, int internal_repeats,
+                       const uint64_t* bg_sorted, int64_t n_bg, int bg_K, int n_threads,
+                       uint8_t* flags, int32_t* last_single) {
+  return nrp_oracle_build_slice(ascii, off, n_parts, k, internal_repeats, bg_sorted, n_bg, bg_K, n_threads, flags, last_single, 1, 0, 0);
 }
 
 void nrp_oracle_counts(void* handle, int64_t out[4]) {

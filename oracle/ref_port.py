@@ -60,15 +60,35 @@ class SetBackground(object):
         self.K = int(K)
         self.ALIVE = True
         self.keys = set()
+        self.LEN = 0
 
     def multiadd(self, seq_list):
         for seq in seq_list:
             if seq in ('K', 'LEN'):                      # metadata keys share the keyspace (kmerSetDB.py:159)
                 continue
-            self.keys.update(canonical_windows(seq.replace('U', 'T'), self.K))
+            for key in canonical_windows(seq.replace('U', 'T'), self.K):
+                if key not in self.keys:                 # kmerSetDB.py:168-170
+                    self.keys.add(key)
+                    self.LEN += 1
 
     def add(self, seq):
         self.multiadd([seq])
+
+    def multiremove(self, seq_list, clear=False):
+        """kmerSetDB.py:246-280: with clear the counter drops once per streamed window, present or not."""
+        for seq in seq_list:
+            if seq in ('K', 'LEN'):
+                continue
+            for key in canonical_windows(seq.replace('U', 'T'), self.K):
+                if clear:
+                    self.keys.discard(key)
+                    self.LEN -= 1
+                elif key in self.keys:
+                    self.keys.remove(key)
+                    self.LEN -= 1
+
+    def remove(self, seq):
+        self.multiremove([seq])
 
     def contains(self, seq):
         if not self.ALIVE:
@@ -83,7 +103,7 @@ class SetBackground(object):
             yield self.contains(seq)
 
     def __len__(self):
-        return len(self.keys)
+        return self.LEN                                  # kmerSetDB.py:219-225
 
     def __iter__(self):
         return iter(self.keys)

@@ -12,11 +12,23 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get('NRPCALC_REFERENCE', '/root/reference')
+_REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def _find_reference():
+    """The reference tree: $NRPCALC_REFERENCE, the offline install under baseline/_ref (pip install --target, travels to the GPU
+    box with the repository snapshot), then the development container's /root/reference."""
+    for root in (os.environ.get('NRPCALC_REFERENCE'), os.path.join(_REPO, 'baseline', '_ref'), '/root/reference'):
+        if root and os.path.isfile(os.path.join(root, 'nrpcalc', 'base', 'hgraph.py')):
+            return root
+    return os.environ.get('NRPCALC_REFERENCE', '/root/reference')
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, 'nrpcalc'))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, 'nrpcalc', 'base', 'hgraph.py'))
 
 
 class _DictShareDB(dict):

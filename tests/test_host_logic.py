@@ -64,7 +64,7 @@ def test_verbose_run_gives_same_toolbox(capsys):
     found = nrpcalc_b200.finder(case['parts'], case['Lmax'], vercov='nrp2', verbose=True)
     assert list(found) == case['toolbox']['nrp2']['7']
     out = capsys.readouterr().out
-    assert '[Non-Repetitive Parts Calculator - Finder Mode]' in out and 'Non-Repetitive Toolbox Size' in out
+    assert 'Finder Mode' in out and 'Non-Repetitive Toolbox Size' in out
 
 
 def test_fasta_output(tmp_path):
@@ -302,3 +302,34 @@ def test_native_array_tail_on_many_small_streams():
         assert nodes.tolist() == list(expect.nodes()), trial
         bounds, nbrs = indptr.tolist(), adj.tolist()
         assert [nbrs[bounds[i]:bounds[i + 1]] for i in range(len(bounds) - 1)] == [list(expect[u]) for u in expect.nodes()], trial
+
+
+def test_patch_runs_the_reference_finder_on_our_graph_build(scratch_cwd):
+    """nrpcalc_b200.patch(): the UNMODIFIED reference's finder / recovery / vercov run on a graph built behind the seam
+    hgraph.get_homology_graph (reference hgraph.py:202-249); toolboxes equal the golden ones, with and without a (reference)
+    background object; unpatch() restores the reference's own function."""
+    import refshim
+    if not refshim.reference_available():
+        pytest.skip('no reference tree (baseline/_ref or /root/reference)')
+    ref = refshim.load_reference()
+    from nrpcalc.base import hgraph as ref_hgraph
+    original = ref_hgraph.get_homology_graph
+    assert nrpcalc_b200.patch(ref) is ref and ref_hgraph.get_homology_graph is not original
+    try:
+        for name in ('planted_s0_L15_ir0', 'docstring_finder_example', 'short_parts_ir1'):
+            case = next(c for c in GOLDEN_CASES if c['name'] == name)
+            bg = None
+            if case['bg_seqs'] is not None:
+                bg = ref.background(path='./ref_patch_bg/', Lmax=case['bg_Lmax'], verbose=False)
+                bg.multiadd(case['bg_seqs'])
+            for vc, by_seed in case['toolbox'].items():
+                for seed, expected_ids in by_seed.items():
+                    random.seed(int(seed))
+                    found = ref.finder(seq_list=list(case['parts']), Lmax=case['Lmax'], internal_repeats=case['internal_repeats'],
+                                       background=bg, vercov=vc, verbose=False)
+                    assert list(found.keys()) == expected_ids, (name, vc, seed)
+            if bg is not None:
+                bg.drop()
+    finally:
+        nrpcalc_b200.unpatch()
+    assert ref_hgraph.get_homology_graph is original

@@ -153,3 +153,34 @@ def test_c_oracle_equals_np_oracle(seed, k, threads):
                          tuple(int(ids[m]) for m in got['members'][got['indptr'][g]:got['indptr'][g + 1]]))
                         for g in range(got['n_groups']))
         assert groups == sorted(want['groups'])
+
+
+def test_c_oracle_slices_and_canonical_form():
+    """The key-space slicing of the C oracle (memory bound for the full-size configs) changes nothing, and the canonical
+    form / digest of tests/parity.py does not depend on the order in which a producer lists the groups."""
+    from oracle import c_oracle
+    import parity
+    parts = cases.planted_parts(400, 4242) + cases.random_parts(300, 60, 3)
+    k = 15
+    uniq = [(pid, seq) for pid, seq in ref_port.uniquify(list(parts)) if len(seq) >= k]
+    ids = np.array([pid for pid, _ in uniq], dtype=np.uint32)
+    seqs = [seq for _, seq in uniq]
+    offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in seqs], out=offsets[1:])
+    buf = np.frombuffer(''.join(seqs).encode(), dtype=np.uint8)
+    for internal in (False, True):
+        one = parity.from_c_oracle(c_oracle.build_table(buf, offsets, k, internal, n_threads=2), ids)
+        many = parity.from_c_oracle(c_oracle.build_table(buf, offsets, k, internal, n_threads=3, n_slices=5), ids)
+        assert parity.compare(one, many)['all'] and parity.digest(one) == parity.digest(many)
+        want = np_oracle.spec(uniq, k, internal)
+        assert one['edges'].tolist() == sorted((min(a, b) << 32) | max(a, b) for a, b in want['edges'])
+        assert one['records'] == want['n_records'] and one['keys'].size == len(want['groups'])
+        # a producer that lists the same groups in another order has the same canonical form
+        raw = c_oracle.build_table(buf, offsets, k, internal)
+        perm = np.random.default_rng(1).permutation(raw['n_groups'])
+        indptr, members = parity.reorder_csr(raw['indptr'], raw['members'], perm)
+        shuffled = parity.canonical(raw['flags'], indptr, members, raw['rank_j'][perm], raw['keys'][perm], raw['last_single'], None, ids,
+                                    raw['n_records'])
+        assert parity.compare(one, shuffled)['all']
+        broken = dict(shuffled, last_single=shuffled['last_single'] + 1)
+        assert not parity.compare(one, broken)['all']
