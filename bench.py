@@ -49,8 +49,8 @@ CONFIGS = {
                label='Finder mode: 50M variable-length (50-300 bp) parts, Lmax=24, 8xB200 all-to-all scaling sweep'),
     # not a BASELINE shape: planted shared motifs, so that the fixed regions of the direct placement overflow and the exact
     # (histogram) path with the global sort runs -- the workload real part libraries resemble more than i.i.d. DNA
-    'dup': dict(n=1_000_000, length=100, Lmax=16, internal_repeats=False, genome=0, seed=6, dup_motifs=64, dup_fraction=0.25,
-                label='Finder mode: 1M 100-bp parts, Lmax=16, 25 % of the parts carry one of 64 shared 40-bp motifs (duplicate-heavy)'),
+    'dup': dict(n=1_000_000, length=100, Lmax=16, internal_repeats=False, genome=0, seed=6, dup_motifs=4, dup_fraction=0.008,
+                label='Finder mode: 1M 100-bp parts, Lmax=16, 0.8 % of the parts carry one of 4 shared 40-bp motifs (~2000 copies of each shared k-mer: duplicate-heavy)'),
 }
 # oracle passes over slices of the key space for the full-size verification (bounds the host memory of the C hash table)
 VERIFY_SLICES = {'c1': 1, 'c2': 4, 'c3': 8, 'c4': 32, 'c5': 256, 'dup': 4}
@@ -324,6 +324,7 @@ def main():
     ap.add_argument('--no-edges', action='store_true')
     ap.add_argument('--verify', action='store_true', help='compare the full result with oracle/nrp_oracle.c (default for c1/c2 at N=1; N>1: also against the oracle, besides the single-GPU result)')
     ap.add_argument('--no-verify', action='store_true')
+    ap.add_argument('--verify-parts', type=int, default=5_000_000, help='N > 1, batches beyond one device: parts of the cut the parity check runs on')
     ap.add_argument('--api-parts', type=int, default=100_000, help='parts of the finder() API timing leg (0 = skip)')
     ap.add_argument('--h2d-chunks', type=int, default=8, help='e2e leg: pieces of the streamed host-to-device copy (1 = one blocking copy)')
     ap.add_argument('--e2e-entry', choices=('auto', 'offsets', 'uniform'), default='auto',
@@ -431,12 +432,26 @@ def main():
                res.last_single.nbytes + (res.edges[0].nbytes + res.edges[1].nbytes if res.edges else 0) + 16 * 8 * 2)
     e2e_value = m / (sum(e2e_times) / len(e2e_times))
 
+    # ---- parity of the FULL result against the C oracle (checker only; default for the configs it does in seconds)
+    parity_block = None
+    do_verify = (args.verify or cfg_name in ('c1', 'c2')) and not args.no_verify
+    if do_verify:
+        ctx.load_parts(None, off, ids, device_ptr=dev_ascii.data_ptr())
+        ctx.build(k, cfg['internal_repeats'], True)
+        full = ctx.fetch(want_keys=True, copy=True)
+        parity_block = verify_against_oracle(cfg_name, cfg, buf, off, ids, k, full, ctx.counts()['records'], bg_keys, bg_K)
+        del full
+    api_block = None
+    if args.api_parts > 0 and not isinstance(cfg['length'], tuple):
+        ctx.set_background(None, 0)
+        api_block = finder_api_timing(min(args.api_parts, cfg['n']), cfg['length'], cfg['Lmax'], cfg['seed'])
+
     # ---- roofline of the dominant kernel
     peak, peak_src = measured_peak_gbs()
     algo = algorithmic_bytes(int(off[-1]), m, counts['key_bytes'], counts['packed'])
     stage_avg = {name: stage_ms.get(name, 0.0) / args.steps for name in algo}
     dominant = max(stage_avg, key=lambda name: stage_avg[name])
-    kernel_of = {'histogram': 'k_hist_from_ascii', 'split1': 'k_split_from_ascii', 'split2': 'k_split_from_records', 'filter': 'k_filter_bloom',
+    kernel_of = {'histogram': 'k_hist_from_ascii', 'split1': 'k_split_uniform' if counts.get('uniform_kernel') else 'k_split_from_ascii', 'split2': 'k_split_from_records', 'filter': 'k_filter_bloom',
                  'flags': 'k_flag_windows'}
     achieved = algo[dominant] / (stage_avg[dominant] * 1e-3) / 1e9
     traffic = None
@@ -476,13 +491,20 @@ def main():
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
             'stage_ms': {name: v / args.steps for name, v in stage_ms.items()},
             'result': {name: counts[name] for name in ('records', 'excluded', 'groups', 'members', 'edges', 'candidates', 'runs', 'buckets', 'oversized',
-                                                       'direct', 'fallbacks', 'packed')},
+                                                       'direct', 'fallbacks', 'packed', 'uniform_kernel')},
             'wall_s_timed_region': wall}
     if bg_timing:
         line['config'].update(bg_timing)
+    if parity_block is not None:
+        line['parity'] = parity_block
+    if api_block is not None:
+        line['finder_api'] = api_block
     if not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline(cfg, buf, off, k)
     print(json.dumps(line))
+    if parity_block is not None and not parity_block['vs_oracle']:
+        sys.stderr.write('PARITY MISMATCH against oracle/nrp_oracle.c: {}\n'.format(parity_block['components']))
+        sys.exit(3)
 
 
 if __name__ == '__main__':

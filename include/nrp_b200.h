@@ -66,7 +66,8 @@ extern "C" {
 #define NRP_C_DIRECT        13  /* 1: buckets were placed in fixed regions (no histogram pass); 0: exact histogram path */
 #define NRP_C_FALLBACKS     14  /* a fixed region overflowed and the batch was repeated on the exact path */
 #define NRP_C_PACKED        15  /* 1: records travelled as single 64-bit words (k-mer << value bits) | value */
-#define NRP_N_COUNTS        16
+#define NRP_C_UNIFORM       16  /* 1: the part-aligned extraction kernel ran (parts of one length, packed records) */
+#define NRP_N_COUNTS        20
 
 /* indices into nrp_result_timings() (milliseconds, CUDA events on the context's stream) */
 #define NRP_T_TOTAL          0  /* device-resident inputs -> device-resident results (T_build) */
@@ -216,6 +217,11 @@ int nrp_shard_scatter_direct(nrp_ctx* ctx, int64_t part_lo, int64_t part_hi, int
 int nrp_shard_group_direct(nrp_ctx* ctx, int k, int internal_repeats);
 /* out[0] = records this rank sent in the last nrp_shard_scatter_direct, out[1] = records it received and partitioned */
 int nrp_shard_moved(nrp_ctx* ctx, int64_t out[2]);
+/* Close every peer mapping this context opened (cudaIpcCloseMemHandle) and forget the handles.  COLLECTIVE by contract: before
+ * any rank re-exports its receive buffers (nrp_peer_export / nrp_peer_export_direct may free and re-allocate them), ALL ranks
+ * call nrp_peer_close and synchronise (barrier) -- CUDA leaves freeing an exported allocation that an importer still maps
+ * undefined. */
+int nrp_peer_close(nrp_ctx* ctx);
 
 /* run all work of the context on a caller-owned CUDA stream (cudaStream_t), e.g. torch's current stream; NULL
  * restores a private stream */

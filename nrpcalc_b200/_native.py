@@ -11,10 +11,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # NRPCALC_B200_LIB selects another build of the same library (A/B kernel variants, tools/build_variants.sh)
 LIB_PATH = os.environ.get('NRPCALC_B200_LIB') or os.path.join(_HERE, 'libnrpb200.so')
 
-N_COUNTS = 16
+N_COUNTS = 20
 N_TIMINGS = 16
 COUNT_NAMES = ('records', 'excluded', 'groups', 'members', 'edges', 'pairs', 'candidates', 'runs', 'buckets',
-               'oversized', 'windows_max', 'key_bytes', 'launches', 'direct', 'fallbacks', 'packed')
+               'oversized', 'windows_max', 'key_bytes', 'launches', 'direct', 'fallbacks', 'packed', 'uniform_kernel')
 TIMING_NAMES = ('total', 'h2d', 'flags', 'histogram', 'split1', 'split2', 'filter', 'sort', 'group', 'edges', 'order')
 
 FLAG_REPEAT, FLAG_PALINDROME, FLAG_BACKGROUND = 1, 2, 4
@@ -93,6 +93,7 @@ def _declare(lib):
         'nrp_shard_scatter_direct': (c_ctx, i64, i64, i32, i32, i32, ctypes.POINTER(i32)),
         'nrp_shard_group_direct': (c_ctx, i32, i32),
         'nrp_shard_moved': (c_ctx, ptr),
+        'nrp_peer_close': (c_ctx,),
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -252,6 +253,10 @@ class Context(object):
     def peer_open_direct(self, handles, my_rank):
         blob = np.frombuffer(b''.join(handles), dtype=np.uint8).copy()
         _check(self._lib, self._lib.nrp_peer_open_direct(self._h, len(handles), int(my_rank), _p(blob)))
+
+    def peer_close(self):
+        """Close every peer mapping (collective by contract: all ranks, then a barrier, before anyone re-exports)."""
+        _check(self._lib, self._lib.nrp_peer_close(self._h))
 
     def shard_scatter_direct(self, part_lo, part_hi, k, internal_repeats, n_owners):
         overflow = ctypes.c_int(0)

@@ -28,14 +28,15 @@ __host__ __device__ __forceinline__ uint32_t owner_hash(uint64_t key) {
   return (uint32_t)(key >> 32);
 }
 
-// Bijective hash on the n = 2k bits of a canonical k-mer (multiply, fold, multiply -- every step invertible mod 2^n).  Packed
+// Bijective hash on the n = 2k bits of a canonical k-mer (multiply, fold, multiply -- every step invertible mod 2^n; the
+// multipliers are 32-bit odd constants, so that a 64-bit product costs two IMADs, see extract.cuh).  Packed
 // records carry this hash INSTEAD of the k-mer: every later bucket digit and filter index is a bit field of the record (no
 // re-hashing after the extraction), the bits implied by a record's level-1 region need not be stored, and the filter
 // recovers the k-mer of the few records it emits with inv().
 struct BijHash {
   uint64_t c1inv, c2inv, mask;
   int n, s;
-  static constexpr uint64_t kC1 = 0x9E3779B97F4A7C15ull, kC2 = 0xBF58476D1CE4E5B9ull;
+  static constexpr uint64_t kC1 = 0x9E3779B1ull, kC2 = 0x85EBCA6Bull;
   __host__ __device__ __forceinline__ uint64_t fwd(uint64_t x) const {
     uint64_t h = (x * kC1) & mask;
     h ^= h >> s;                                   // s >= n/2: an involution
@@ -61,10 +62,12 @@ inline BijHash make_bijhash(int k) {
   b.c2inv = odd_inverse64(BijHash::kC2);
   return b;
 }
-// layout of a packed record: ((hash without its top owner_bits + drop bits) << vbits) | value
+// layout of a packed record: ((hash without its top owner_bits + drop bits) << vbits) | value.  The stored hash bits sit at the
+// TOP of the 64-bit word (vbits = 64 - stored bits), the value at the bottom, zero bits in between: the word is a funnel
+// shift of the left-aligned hash, it orders by (hash, value), and `word & ((1 << vbits) - 1)` is the value.
 struct PackFmt {
   BijHash bij;
-  int vbits;        // bits of the value
+  int vbits;        // position of the stored hash bits = 64 - (n_eff() - drop); the value occupies the low bits below it
   int drop;         // hash bits implied by the record's level-1 region (not stored)
   int owner_bits;   // sharded path with a power-of-two number of owners: the top hash bits ARE the owner (not stored either)
   uint32_t owner;   // ... and this is the owner whose records these are (needed to recover a k-mer)
@@ -91,13 +94,18 @@ __host__ __device__ __forceinline__ uint32_t owner_of(uint64_t key, uint32_t n_o
 // ---------------------------------------------------------------------------------------------------
 // 2-bit alphabet, MSB-first.  ASCII -> code: (c>>1)&3 gives A0 C1 T2 G3 for both cases; t ^ (t>>1) swaps the
 // last two so that A<C<G<T numerically as in the reference's string comparison, and complement is x^3.
-__device__ __forceinline__ uint32_t pack4(uint32_t x) {   // 4 ASCII bytes (first char = lowest byte) -> 8 bits
+__device__ __forceinline__ uint32_t pack4_top(uint32_t x) {   // 4 ASCII bytes (first char = lowest byte) -> 8 bits in the TOP byte
   uint32_t t = (x >> 1) & 0x03030303u;
   uint32_t c = t ^ ((t >> 1) & 0x01010101u);
-  return ((c << 6) | (c >> 4) | (c >> 14) | (c >> 24)) & 0xffu;
+  // one multiply gathers the four 2-bit codes: byte i (bits 8i, 8i+1) moves to bits 30-2i.. of the product; the partial
+  // products occupy distinct bit positions (no carries) and nothing else lands in the top byte
+  return c * 0x40100401u;
 }
+__device__ __forceinline__ uint32_t pack4(uint32_t x) { return pack4_top(x) >> 24; }
 __device__ __forceinline__ uint32_t pack16(uint4 v) {     // 16 ASCII bytes -> 32 bits, first char in the top bits
-  return (pack4(v.x) << 24) | (pack4(v.y) << 16) | (pack4(v.z) << 8) | pack4(v.w);
+  const uint32_t hi = __byte_perm(pack4_top(v.y), pack4_top(v.x), 0x0073);   // byte 1 = code byte of v.x, byte 0 = of v.y
+  const uint32_t lo = __byte_perm(pack4_top(v.w), pack4_top(v.z), 0x0073);
+  return __byte_perm(lo, hi, 0x5410);
 }
 
 // reverse complement of a right-aligned 2k-bit value: complement all bits, reverse the 64 bits (BREV), swap

@@ -1,0 +1,185 @@
+// Extraction fused with the first split for parts of ONE length (every BASELINE shape but the variable-length one):
+// the part-aligned kernel.
+//
+// Replaces reference nrpcalc/base/utils.py:37-50 (stream_kmers, get_revcomp, min) + hgraph.py:82-89 (table insert) for
+// the bulk of the records, like k_split_from_ascii (partition.cuh), which stays the general kernel (variable lengths,
+// unpacked records, the exact path).  What is different here:
+//
+//   * threads are mapped to WINDOWS OF ONE PART, not to byte positions: a part with W windows is cut into
+//     Tp = ceil(W / 8) chunks of 8 consecutive windows, thread t of a tile owns chunk t % Tp of part t / Tp.  No thread
+//     ever crosses a part boundary, so the window loop has no part bookkeeping, no divergence (the byte-position kernel
+//     executes its part-change branch in almost every warp iteration: 32 lanes x 8 % crossing probability) and no
+//     positions without a window (16 % of the positions of a 100-bp part at k = 17);
+//   * forward and reverse-complement values roll LEFT-ALIGNED (the k-mer's first base in the top bits of the word): bits
+//     that leave the window fall off the top, "mod 2^2k" of the bijective hash is free, the bucket digit is one shift of
+//     the high word and the packed record is one funnel shift -- no masks;
+//   * k <= 16 runs in 32-bit arithmetic (KEY64 = false);
+//   * windows without a record (the tail of a part's last chunk, flagged parts, idle threads) take the same instructions
+//     and count in a per-lane dump counter: no branches around the shared-memory atomic.
+//
+// About 60 thread instructions per window against 163 of the byte-position kernel (profiles/ncu_full_r02*.txt).
+#pragma once
+#include "partition.cuh"
+
+namespace nrp {
+
+constexpr int kUniMaxWords = 1264;     // packed 16-base words of one tile: parts_per_tile * L <= 512 * 39 bytes, + alignment + halo
+
+// host-computed constants of the mapping
+struct UniPlan {
+  uint32_t L;        // part length
+  uint32_t W;        // windows per part = L - k + 1 (>= 1)
+  uint32_t Tp;       // threads per part = ceil(W / 8)
+  uint32_t G;        // parts per tile = 512 / Tp
+  uint32_t inv_Tp;   // ceil(2^20 / Tp): t / Tp == (t * inv_Tp) >> 20 for t < 512
+};
+inline bool uni_plan(int64_t L, int k, UniPlan* up) {
+  if (L < k || L >= (1 << 20)) return false;
+  const int64_t W = L - k + 1;
+  if (W > 4096) return false;                      // more than 512 chunks: the byte-position kernel
+  up->L = (uint32_t)L; up->W = (uint32_t)W;
+  up->Tp = (uint32_t)((W + 7) / 8);
+  up->G = 512u / up->Tp;
+  up->inv_Tp = ((1u << 20) + up->Tp - 1u) / up->Tp;
+  return (int64_t)up->G * L + 64 <= (int64_t)(kUniMaxWords - 8) * 16;
+}
+
+struct alignas(16) UniSmem {
+  SplitSmem<uint64_t, true> split;
+  uint32_t packed[kUniMaxWords];
+};
+
+// MODE 0: digit = top r1 bits of the hash (single GPU, fixed regions).  MODE 2: digit = (owner, top r1 bits), stored into the
+// owner's region of this (bucket, sender) over NVLink (direct sharded path); the owner is the top owner_bits of the hash when
+// pf.owner_bits > 0, else owner_of(k-mer).
+template <bool KEY64, int MODE>
+__global__ void __launch_bounds__(kSplitThreads, 2) k_split_uniform(const uint8_t* __restrict__ ascii, const uint8_t* __restrict__ flags, UniPlan up,
+                                                                    int64_t part_lo, int64_t part_hi, int k, int r1, int n_owners, uint32_t part_base,
+                                                                    int j_bits, PackFmt pf, uint32_t* cursor, uint64_t* out_keys, RegionLimit lim,
+                                                                    PeerBuffers peers) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  UniSmem& sm = *reinterpret_cast<UniSmem*>(smem_raw);
+  SplitSmem<uint64_t, true>& s = sm.split;
+  const int t = threadIdx.x;
+  const int64_t P0 = part_lo + (int64_t)blockIdx.x * up.G;
+  const int64_t P1 = min(P0 + (int64_t)up.G, part_hi);
+  const int64_t B0 = P0 * up.L, B1 = P1 * up.L;
+  const int64_t A0 = B0 & ~15ll;
+  const int n_chunks = (int)((B1 - A0 + 15) >> 4) + 3;          // + the words the last threads read past their windows (buffer is padded)
+  // global loads first (at most three 16-byte words per thread), the per-thread constants while they are in flight
+  uint4 raw[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int c = t + i * kSplitThreads;
+    raw[i] = make_uint4(0, 0, 0, 0);
+    if (c < n_chunks) raw[i] = __ldg(reinterpret_cast<const uint4*>(ascii + A0) + c);
+  }
+  const uint32_t pl = ((uint32_t)t * up.inv_Tp) >> 20;          // part of this thread inside the tile
+  const uint32_t j0 = ((uint32_t)t - pl * up.Tp) * (uint32_t)kSplitItems;   // its first window inside the part
+  const int64_t part = P0 + pl;
+  int n_e = 0;                                                   // windows of this thread (0: idle)
+  if (pl < up.G && part < P1) {
+    n_e = (int)min((uint32_t)kSplitItems, up.W - j0);
+    if (flags != nullptr && __ldg(flags + part) != 0) n_e = 0;  // part excluded by the flag pass (palindrome / background)
+  }
+  s.cnt[t] = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int c = t + i * kSplitThreads;
+    if (c < n_chunks) sm.packed[c] = pack16(raw[i]);
+  }
+  __syncthreads();
+
+  const int j = KEY64 ? 64 - 2 * k : 32 - 2 * k;                 // free low bits of a left-aligned k-mer
+  const uint32_t rel = n_e > 0 ? (uint32_t)(B0 - A0) + pl * up.L + j0 : 0u;     // base index of the first window in the packed tile
+  const int w = (int)(rel >> 4), sh = (int)(rel & 15u) * 2;
+  const uint32_t relT = rel + (uint32_t)k - 1u;                  // T: the 16 bases from the LAST base of window 0 on
+  const int wT = (int)(relT >> 4), shT = (int)(relT & 15u) * 2;
+  const uint32_t T = __funnelshift_l(sm.packed[wT + 1], sm.packed[wT], shT);
+  const uint32_t TF = __funnelshift_l(T, T, (j + 2) & 31);       // rotated: base e of T at bits (j+1, j) after e more 2-bit rotations
+  const uint32_t TR = ~T;                                        // complements; base e at bits (31, 30) after e 2-bit rotations
+  const uint32_t in_mask = 3u << j;
+  const uint32_t low_clear = ~((1u << j) - 1u);                  // clears the free low bits (of the low word when KEY64)
+  const int s_fold = k;                                          // BijHash::s = (2k + 1) / 2
+  const int dbits = r1 + ((MODE == 2 && pf.owner_bits > 0) ? pf.owner_bits : 0);
+  const int sdrop = pf.owner_bits + pf.drop;                     // top hash bits a record does not store
+  const bool mix_owner = MODE == 2 && pf.owner_bits == 0;        // owner from owner_of(k-mer), not from the hash
+  const uint32_t step = j_bits ? 1u : 0u;
+  const uint32_t v0 = ((part_base + (uint32_t)part) << j_bits) | (j_bits ? j0 : 0u);
+  const uint32_t lane = (uint32_t)t & 31u;
+  constexpr uint32_t C1 = (uint32_t)BijHash::kC1, C2 = (uint32_t)BijHash::kC2;
+  static_assert(BijHash::kC1 < (1ull << 32) && BijHash::kC2 < (1ull << 32), "32-bit multipliers");
+
+  uint64_t key[kSplitItems];
+  uint32_t val[kSplitItems], dr[kSplitItems];
+  if (KEY64) {
+    const uint32_t x0 = sm.packed[w], x1 = sm.packed[w + 1], x2 = sm.packed[w + 2];
+    uint32_t fh = __funnelshift_l(x1, x0, sh), fl = __funnelshift_l(x2, x1, sh) & low_clear;    // window 0, left-aligned
+    uint32_t rh, rl;
+    {
+      const uint64_t f0 = ((uint64_t)fh << 32) | fl;
+      const uint64_t r0 = revcomp2(f0 >> j, k) << j;
+      rh = (uint32_t)(r0 >> 32); rl = (uint32_t)r0;
+    }
+#pragma unroll
+    for (int e = 0; e < kSplitItems; ++e) {
+      if (e > 0) {                                               // roll both strands by one base
+        const uint32_t in_f = __funnelshift_l(TF, TF, 2 * e) & in_mask;
+        const uint32_t in_r = __funnelshift_l(TR, TR, 2 * e) & 0xC0000000u;
+        fh = __funnelshift_l(fl, fh, 2);
+        fl = (fl << 2) | in_f;
+        rl = __funnelshift_r(rl, rh, 2) & low_clear;
+        rh = (rh >> 2) | in_r;
+      }
+      const bool valid = e < n_e;
+      const bool f_less = fh < rh || (fh == rh && fl < rl);
+      const uint32_t ch_ = f_less ? fh : rh, cl = f_less ? fl : rl;     // canonical k-mer, left-aligned
+      // bijective hash (BijHash::fwd) in left-aligned arithmetic: multiply, fold, multiply -- mod 2^2k for free
+      uint64_t p1 = (uint64_t)cl * C1;
+      uint32_t hl = (uint32_t)p1, hh = ch_ * C1 + (uint32_t)(p1 >> 32);
+      hl ^= __funnelshift_rc(hl, hh, s_fold) & low_clear;
+      hh ^= __funnelshift_rc(hh, 0u, s_fold);
+      const uint64_t p2 = (uint64_t)hl * C2;
+      hl = (uint32_t)p2; hh = hh * C2 + (uint32_t)(p2 >> 32);
+      uint32_t d = __funnelshift_rc(hh, 0u, 32 - dbits);
+      if (mix_owner) {
+        const uint64_t canon = (((uint64_t)ch_ << 32) | cl) >> j;
+        d |= owner_of(canon, (uint32_t)n_owners) << r1;
+      }
+      const uint32_t rank = atomicAdd(&s.cnt[valid ? d : (uint32_t)kLevelBuckets + lane], 1u);
+      dr[e] = valid ? ((d << 16) | rank) : 0xffffffffu;
+      const uint32_t kh = __funnelshift_l(hl, hh, sdrop), kl = (hl << sdrop) | (v0 + (uint32_t)e * step);
+      key[e] = ((uint64_t)kh << 32) | kl;
+      val[e] = 0;
+    }
+  } else {
+    const uint32_t x0 = sm.packed[w], x1 = sm.packed[w + 1];
+    uint32_t f = __funnelshift_l(x1, x0, sh) & low_clear;
+    uint32_t r = (uint32_t)(revcomp2((uint64_t)(f >> j), k) << j);
+#pragma unroll
+    for (int e = 0; e < kSplitItems; ++e) {
+      if (e > 0) {
+        f = (f << 2) | (__funnelshift_l(TF, TF, 2 * e) & in_mask);
+        r = ((r >> 2) & low_clear) | (__funnelshift_l(TR, TR, 2 * e) & 0xC0000000u);
+      }
+      const bool valid = e < n_e;
+      const uint32_t c = min(f, r);
+      uint32_t h = c * C1;
+      h ^= (h >> s_fold) & low_clear;
+      h *= C2;
+      uint32_t d = __funnelshift_rc(h, 0u, 32 - dbits);
+      if (mix_owner) d |= owner_of((uint64_t)(c >> j), (uint32_t)n_owners) << r1;
+      const uint32_t rank = atomicAdd(&s.cnt[valid ? d : (uint32_t)kLevelBuckets + lane], 1u);
+      dr[e] = valid ? ((d << 16) | rank) : 0xffffffffu;
+      key[e] = ((uint64_t)(h << sdrop) << 32) | (v0 + (uint32_t)e * step);
+      val[e] = 0;
+    }
+  }
+  __syncthreads();
+  const int nb = MODE == 0 ? (1 << r1) : (n_owners << r1);
+  split_reorder<uint64_t, true>(s, key, val, dr, nb, cursor, lim);
+  if (MODE == 0) split_flush<uint64_t, true>(s, out_keys, nullptr);
+  else split_flush<uint64_t, true>(s, out_keys, nullptr, &peers, r1);
+}
+
+}  // namespace nrp

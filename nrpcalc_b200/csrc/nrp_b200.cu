@@ -27,6 +27,7 @@
 #include "scan.cuh"
 #include "lsd_sort.cuh"
 #include "partition.cuh"
+#include "extract.cuh"
 #include "stages.cuh"
 
 using namespace nrp;
@@ -150,6 +151,7 @@ struct nrp_ctx {
                                           // the kernel sequence at 8e5 candidates, slower at 2e7), 2 = always, 0 = never
   int64_t opt_packed = 1;                 // one 64-bit word per record on the direct path whenever key and value fit
   int64_t opt_direct = 1;                 // fixed-region partition without a histogram pass (falls back to the exact path on overflow)
+  int64_t opt_uniform_kernel = 1;         // parts of one length: the part-aligned extraction kernel (extract.cuh); 0 = the byte-position kernel
 
   // background
   DevBuf bg_table; int bg_K = 0; int bg_log_slots = 0; int bg_key_bytes = 0; int64_t bg_n = 0;
@@ -163,6 +165,7 @@ struct nrp_ctx {
   int64_t n_parts = 0, total_len = 0, n_tiles = 0, max_len = 0;
   int uniform_len = 0;
   bool have_parts = false, have_ids = false;
+  bool flags_set = false;                    // the flag pass of the current job ran a kernel (some flag byte may be non-zero)
   int coop_blocks_per_sm[2] = {0, 0};
   bool group_counts_coop = false;
   // streamed staging: the ASCII copy is in flight on copy_stream in pieces (contiguous part ranges); pending_chunks > 0 until a
@@ -306,6 +309,10 @@ int configure_kernels(nrp_ctx* c) {
                           (int)filter_bloom_smem<8, true, 2048, 1024, 256>()));
   CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1, 1024, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)filter_bloom_smem<8, true, 8192, 4096, 1024>()));
+  CU(cudaFuncSetAttribute((k_split_uniform<false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
+  CU(cudaFuncSetAttribute((k_split_uniform<true, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
+  CU(cudaFuncSetAttribute((k_split_uniform<false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
+  CU(cudaFuncSetAttribute((k_split_uniform<true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
   const int packed_smem = (int)(sizeof(SplitSmem<uint64_t, true>) + sizeof(TileStage));
   CU(cudaFuncSetAttribute((k_split_from_ascii<uint64_t, 0, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, packed_smem));
   CU(cudaFuncSetAttribute((k_split_from_ascii<uint64_t, 2, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, packed_smem));
@@ -391,6 +398,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "coop_group") c->opt_coop_group = value < 0 ? 1 : std::min<int64_t>(value, 2);
   else if (n == "packed") c->opt_packed = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "direct") c->opt_direct = value < 0 ? 1 : (value > 0 ? 1 : 0);
+  else if (n == "uniform_kernel") c->opt_uniform_kernel = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
   return NRP_OK;
 }
@@ -684,6 +692,7 @@ int stage_flags(nrp_ctx* c, int k, int internal_repeats, StageTimer& tm) {
   TRY(c->flags.ensure((size_t)c->n_parts + 16));
   TRY(c->last_single.ensure(sizeof(int32_t) * (size_t)(c->n_parts + 1)));
   CU(cudaMemsetAsync(c->flags.ptr, 0, (size_t)c->n_parts + 16, st));
+  c->flags_set = c->shard_tiles > 0 && ((!internal_repeats && (k % 2) == 0) || c->bg_n > 0);
   if (c->shard_tiles > 0) {
     if (!internal_repeats && (k % 2) == 0)
       NRP_LAUNCH((k_flag_windows<uint32_t><<<(unsigned)c->shard_tiles, kTileThreads, 0, st>>>(P, k, 0, nullptr, 0, c->flags.as<uint8_t>())));
@@ -785,7 +794,9 @@ bool packed_fits(const nrp_ctx* c, int k, int drop, int bits, int owner_bits = 0
   return c->opt_packed && !c->opt_no_bloom && n - drop + vbits <= 64 && n >= bits + 11 && n - drop >= 1 && 2 * k < 64;
 }
 PackFmt pack_format(const nrp_ctx* c, int k, int drop, int owner_bits = 0, uint32_t owner = 0) {
-  return PackFmt{make_bijhash(k), c->vbits, drop, owner_bits, owner};
+  // the stored hash bits go to the top of the word (see PackFmt); packed_fits has checked that the value fits below them
+  const int stored = std::max(1, 2 * k - owner_bits - drop);
+  return PackFmt{make_bijhash(k), std::max(c->vbits, 64 - stored), drop, owner_bits, owner};
 }
 
 template <typename KeyT>
@@ -899,7 +910,21 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
           Q.part_lo = ch.part_lo; Q.part_hi = ch.part_hi; Q.tile_lo = ch.tile_lo; q_tiles = ch.n_tiles;
           if (q_tiles == 0) continue;
         }
-        if (packed)
+        UniPlan up;
+        if (packed && c->opt_uniform_kernel && c->uniform_len > 0 && uni_plan(c->uniform_len, k, &up)) {
+          // parts of one length: the part-aligned kernel (threads never cross a part boundary, left-aligned rolling values)
+          const int64_t n_q = Q.part_hi - Q.part_lo;
+          const unsigned ugrid = (unsigned)((n_q + up.G - 1) / up.G);
+          const uint8_t* fl = c->flags_set ? c->flags.as<uint8_t>() : nullptr;
+          if (n_q <= 0) continue;
+          if (k > 16)
+            NRP_LAUNCH((k_split_uniform<true, 0><<<ugrid, kSplitThreads, sizeof(UniSmem), st>>>(
+                Q.ascii, fl, up, Q.part_lo, Q.part_hi, k, r, 0, c->part_base, c->j_bits, pf, cursor, (uint64_t*)out_k, lim, PeerBuffers{})));
+          else
+            NRP_LAUNCH((k_split_uniform<false, 0><<<ugrid, kSplitThreads, sizeof(UniSmem), st>>>(
+                Q.ascii, fl, up, Q.part_lo, Q.part_hi, k, r, 0, c->part_base, c->j_bits, pf, cursor, (uint64_t*)out_k, lim, PeerBuffers{})));
+          c->counts[NRP_C_UNIFORM] = 1;
+        } else if (packed)
           NRP_LAUNCH((k_split_from_ascii<uint64_t, 0, false, true><<<(unsigned)q_tiles, kTileThreads, sizeof(SplitSmem<uint64_t, true>) + sizeof(TileStage), st>>>(
               Q, c->flags.as<uint8_t>(), k, r, 0, q_tiles, c->part_base, c->j_bits, pf, PassSel{0, 0u, 0u}, cursor,
               (uint64_t*)out_k, out_v, lim, PeerBuffers{}, 0)));
@@ -1630,7 +1655,19 @@ int shard_scatter_direct_impl(nrp_ctx* c, int64_t lo, int64_t hi, int k, int int
   if (packed_fits(c, k, c->sh_r1, c->sh_bits, c->sh_owner_bits) != c->sh_packed)
     return fail(NRP_E_STATE, "receive buffers were exported for another record layout");
   const RegionLimit lim{c->sh_cap1s, 0u, reinterpret_cast<uint32_t*>(cnt + CNT_SCATTER_OVERFLOW), c->region_ends.as<uint32_t>()};
-  if (c->shard_m_max > 0) {
+  UniPlan up;
+  if (c->shard_m_max > 0 && c->sh_packed && c->opt_uniform_kernel && c->uniform_len > 0 && uni_plan(c->uniform_len, k, &up)) {
+    const unsigned ugrid = (unsigned)((hi - lo + up.G - 1) / up.G);
+    const uint8_t* fl = c->flags_set ? c->flags.as<uint8_t>() : nullptr;
+    const PackFmt pf = pack_format(c, k, c->sh_r1, c->sh_owner_bits, 0u);
+    if (k > 16)
+      NRP_LAUNCH((k_split_uniform<true, 2><<<ugrid, kSplitThreads, sizeof(UniSmem), st>>>(
+          P.ascii, fl, up, lo, hi, k, c->sh_r1, n_owners, 0u, c->j_bits, pf, c->cursor1.as<uint32_t>(), nullptr, lim, c->peers_d)));
+    else
+      NRP_LAUNCH((k_split_uniform<false, 2><<<ugrid, kSplitThreads, sizeof(UniSmem), st>>>(
+          P.ascii, fl, up, lo, hi, k, c->sh_r1, n_owners, 0u, c->j_bits, pf, c->cursor1.as<uint32_t>(), nullptr, lim, c->peers_d)));
+    c->counts[NRP_C_UNIFORM] = 1;
+  } else if (c->shard_m_max > 0) {
     if (c->sh_packed)
       NRP_LAUNCH((k_split_from_ascii<uint64_t, 2, false, true><<<split_grid(c), kTileThreads, sizeof(SplitSmem<uint64_t, true>) + sizeof(TileStage), st>>>(
           P, c->flags.as<uint8_t>(), k, c->sh_r1, n_owners, c->shard_tiles, 0u, c->j_bits, pack_format(c, k, c->sh_r1, c->sh_owner_bits, 0u), PassSel{0, 0u, 0u},
@@ -1981,6 +2018,19 @@ int nrp_shard_group_direct(nrp_ctx* c, int k, int internal_repeats) {
   if (c->n_peers_d < 1) return fail(NRP_E_STATE, "direct peers are not open");
   CU(cudaSetDevice(c->device));
   return k <= 16 ? shard_group_direct_impl<uint32_t>(c, k, internal_repeats) : shard_group_direct_impl<uint64_t>(c, k, internal_repeats);
+}
+
+int nrp_peer_close(nrp_ctx* c) {
+  if (!c) return fail(NRP_E_ARG, "null context");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  for (void* p : c->opened_ptrs) cudaIpcCloseMemHandle(p);
+  c->opened_ptrs.clear();
+  c->opened_handles.clear();
+  c->peers = PeerBuffers{}; c->peers_d = PeerBuffers{};
+  for (int o = 0; o < kMaxPeers; ++o) c->peer_ends[o] = nullptr;
+  c->n_peers = 0; c->n_peers_d = 0;
+  return NRP_OK;
 }
 
 int nrp_shard_moved(nrp_ctx* c, int64_t out[2]) {

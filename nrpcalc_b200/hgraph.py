@@ -103,7 +103,9 @@ def _device_build(ctx, structure, ascii_buf, offsets, global_p, ids, k, internal
     (nrpcalc_b200.sharded); every rank receives the same result."""
     if allow_sharding and _world_size() > 1:
         from . import sharded
-        ops = sharded.NativeOps(ctx)
+        ops = getattr(ctx, '_sharded_ops', None)           # one per context: the peer mappings of the exchange live in it
+        if ops is None:
+            ops = ctx._sharded_ops = sharded.NativeOps(ctx)
         ops.load(ascii_buf, offsets, ids if want_edges else None)
         out = sharded.build_sharded(ops, offsets, k, internal_repeats, want_edges=want_edges)
         flags, indptr, members = out['flags'], out['indptr'], out['members']

@@ -19,6 +19,7 @@ computed by the owner of a group without another exchange).
 same five calls to exercise the sharding / exchange / merge logic under gloo.
 """
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -64,6 +65,7 @@ class NativeOps(object):
     def load(self, ascii_buf, offsets, ids, device_ptr=None):
         self.ctx.load_parts(ascii_buf, offsets, ids, device_ptr=device_ptr)
         self.n_parts = len(offsets) - 1
+        self.max_len = int(np.diff(offsets).max()) if self.n_parts else 0
 
     def extract(self, lo, hi, k, internal_repeats, world):
         counts = self.ctx.shard_extract(lo, hi, k, internal_repeats, world)
@@ -83,6 +85,15 @@ class NativeOps(object):
             return False
         return True
 
+    def _close_peers(self, group):
+        """Before any rank re-exports (and possibly re-allocates) its receive buffers: every rank drops its mappings of the
+        peers' buffers, then all meet at a barrier (freeing an exported allocation a peer still maps is undefined in CUDA)."""
+        if getattr(self, '_peer_key_direct', None) is None and getattr(self, '_peer_key', None) is None:
+            return
+        self.ctx.peer_close()
+        self._peer_key_direct = self._peer_key = None
+        dist.barrier(group=group)
+
     def exchange_direct(self, lo, hi, k, internal_repeats, windows_total, group, phases):
         """Direct fused exchange: no count pass.  Every (level-1 bucket, sender) pair owns a fixed region of the owner's
         receive buffer; scatter -> all-reduce(MAX) of the overflow flags (= barrier) -> the owner's level-2 split, filter and
@@ -91,8 +102,9 @@ class NativeOps(object):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if os.environ.get('NRPCALC_B200_DIRECT', '1') == '0':
             return None
-        key = ('direct', int(windows_total), k <= 16, self.n_parts, world)
+        key = ('direct', int(windows_total), int(k), self.n_parts, world, int(getattr(self, 'max_len', 0)))
         if getattr(self, '_peer_key_direct', None) != key:
+            self._close_peers(group)
             handle = self.ctx.peer_export_direct(windows_total, world, k)
             handles = [None] * world
             dist.all_gather_object(handles, handle, group=group)
@@ -118,6 +130,7 @@ class NativeOps(object):
         capacity = int(windows_total / world * 1.15) + 65536
         key = (capacity, k <= 16, self.n_parts, world)
         if getattr(self, '_peer_key', None) != key:
+            self._close_peers(group)
             handle = self.ctx.peer_export(capacity, k)
             handles = [None] * world
             dist.all_gather_object(handles, handle, group=group)
@@ -267,10 +280,12 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
     offsets = np.asarray(offsets, dtype=np.int64)
     n = offsets.size - 1
     plan = getattr(ops, '_shard_plan', None)
-    if plan is None or plan[0] != (id(offsets), n, k, world):
+    stamp = (n, k, world, int(offsets[-1]) if n else 0, int(offsets[n // 2]) if n else 0)
+    if plan is None or plan[0] != stamp or plan[4]() is not offsets:
         windows = np.maximum(np.diff(offsets) - k + 1, 0)
-        plan = ((id(offsets), n, k, world), shard_bounds(np.diff(offsets), k, world), windows, int(windows.sum()))
-        ops._shard_plan = plan                     # host-side plan of a staged batch, reused by repeated builds
+        # host-side plan of a staged batch, reused by repeated builds over the SAME (still alive) offsets array
+        plan = (stamp, shard_bounds(np.diff(offsets), k, world), windows, int(windows.sum()), weakref.ref(offsets))
+        ops._shard_plan = plan
     bounds, windows, windows_total = plan[1], plan[2], plan[3]
     lo, hi = bounds[rank]
 

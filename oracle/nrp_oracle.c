@@ -102,7 +102,7 @@ static int bg_has(const uint64_t* bg, int64_t n, uint64_t key) {
 typedef struct {
   const uint8_t* ascii; const int64_t* off; int64_t n_parts; int k; int internal_repeats;
   const uint64_t* bg; int64_t n_bg; int bg_K; int n_threads; int tid;
-  int n_slices, slice;     /* only keys with (mix(key) >> 20) % n_slices == slice enter the table (bounds the memory of one pass) */
+  int n_slices, slice;     /* only keys with (mix(key) >> 52) % n_slices == slice enter the table (bounds the memory of one pass) */
   int64_t max_len, m_max;
   uint8_t* flags; int32_t* last_single;
   table_t* table; int64_t n_records;
@@ -167,8 +167,8 @@ static void* table_worker(void* arg) {
     const int64_t w = part_windows(jb->ascii + jb->off[p], jb->off[p + 1] - jb->off[p], jb->k, win, NULL);
     for (int64_t j = 0; j < w; ++j) {
       const uint64_t key = win[j], h = mix(key);
-      if (jb->n_slices > 1 && (int)(((h >> 20) & 0xfffffu) % (uint64_t)jb->n_slices) != jb->slice) continue;
-      if (n_threads > 1 && (int)((h >> 40) % (uint64_t)n_threads) != t) continue;
+      if (jb->n_slices > 1 && (int)((h >> 52) % (uint64_t)jb->n_slices) != jb->slice) continue;    /* top bits: the slot index uses the low ones */
+      if (n_threads > 1 && (int)(((h >> 40) & 0xfffu) % (uint64_t)n_threads) != t) continue;
       ++n_records;
       if (tb->pool_used == tb->pool_cap) {
         tb->pool_cap *= 2;

@@ -105,3 +105,75 @@ def test_finder_with_device_built_background(scratch_cwd):
     assert list(graph.nodes()) == case['graph_nodes']
     assert [list(graph[n]) for n in graph.nodes()] == case['graph_adj']
     bg.drop()
+
+
+@pytest.mark.parametrize('device_bg', [False, True])
+def test_background_with_other_characters(scratch_cwd, device_bg):
+    """A background chromosome with 'N's and a soft-masked (lower-case) stretch: only the windows that cover such a character
+    are lost to the device probe (kmerSetDB classifies windows one by one); result equals the reference port with its string
+    keys (hgraph.py:72-79, kmerSetDB.py:177-207)."""
+    parts = cases.planted_parts(800, 321)
+    rnd = random.Random(5)
+    pieces = []
+    for seq in parts:
+        if len(seq) >= 40 and rnd.random() < 0.3:
+            pieces.append(seq[5:35].upper())
+    chromosome = 'N'.join(pieces[:len(pieces) // 2]) + 'NNNNN' + ''.join(p if i % 3 else p.lower() for i, p in enumerate(pieces[len(pieces) // 2:]))
+    for K, k in ((14, 14), (12, 16), (20, 15)):
+        bg = nrpcalc_b200.background(path='./bg_n_%d_%d/' % (K, int(device_bg)), Lmax=K - 1, verbose=False, device=device_bg)
+        bg.multiadd([chromosome, cases.random_genome(5000, 3)])
+        model = ref_port.SetBackground(K)
+        model.multiadd([chromosome, cases.random_genome(5000, 3)])
+        assert len(bg) == len(model)
+        graph = hgraph.get_homology_graph(list(parts), bg, k, False, './seq.txt', False)
+        expect, _ = ref_port.homology_graph(list(parts), model, k, False)
+        assert list(graph.nodes()) == list(expect.nodes()) and len(expect.nodes()) < len(set(p.upper() for p in parts))
+        assert [list(graph[n]) for n in graph.nodes()] == [list(expect[n]) for n in expect.nodes()]
+        bg.drop()
+
+
+def test_side_files_and_fasta_on_the_device_path(scratch_cwd):
+    """Byte-exact artefacts through the CUDA path: seq_list.txt in processing order (hgraph.py:218-223), the adjacency list the
+    recovery dumps (recovery.py:26-30) and the FASTA writer (finder.py:184-189)."""
+    import networkx as nx
+    case = next(c for c in GOLDEN_CASES if c['name'] == 'planted_s0_L15_ir0')
+    graph = hgraph.get_homology_graph(list(case['parts']), None, case['Lmax'] + 1, case['internal_repeats'], './seq.txt', False)
+    assert open('./seq.txt').read().splitlines() == ['{},{}'.format(i, case['parts'][i].upper()) for i in case['seq_file_ids']]
+    expect, _ = ref_port.homology_graph(list(case['parts']), None, case['Lmax'] + 1, case['internal_repeats'])
+    nx.write_adjlist(expect, './expect_graph.txt')
+    from nrpcalc_b200 import recovery
+    random.seed(7)
+    recovery.get_recovered_non_homologs(graph, './graph.txt', 'nrp2', False)
+    body = lambda path: [line for line in open(path).read().splitlines() if not line.startswith('#')]
+    assert body('./graph.txt') == body('./expect_graph.txt')
+    random.seed(7)
+    found = nrpcalc_b200.finder(case['parts'], case['Lmax'], vercov='nrp2', output_file='./toolbox.fa', verbose=False)
+    import textwrap
+    want = ''.join('>index {}\n{}\n'.format(i, '\n'.join(textwrap.wrap(case['parts'][i].upper(), 80))) for i in case['toolbox']['nrp2']['7'])
+    assert list(found) == case['toolbox']['nrp2']['7'] and open('./toolbox.fa').read() == want
+
+
+def test_patch_on_the_device_path(scratch_cwd):
+    """nrpcalc_b200.patch(): the unmodified reference's finder runs on a graph built by libnrpb200.so behind its own seam."""
+    import refshim
+    if not refshim.reference_available():
+        pytest.skip('no reference tree (baseline/_ref or /root/reference)')
+    ref = refshim.load_reference()
+    nrpcalc_b200.patch(ref)
+    try:
+        for name in ('planted_s0_L15_ir0', 'docstring_finder_example'):
+            case = next(c for c in GOLDEN_CASES if c['name'] == name)
+            bg = None
+            if case['bg_seqs'] is not None:
+                bg = ref.background(path='./ref_bg_gpu/', Lmax=case['bg_Lmax'], verbose=False)
+                bg.multiadd(case['bg_seqs'])
+            for vc, by_seed in case['toolbox'].items():
+                for seed, expected_ids in by_seed.items():
+                    random.seed(int(seed))
+                    found = ref.finder(seq_list=list(case['parts']), Lmax=case['Lmax'], internal_repeats=case['internal_repeats'],
+                                       background=bg, vercov=vc, verbose=False)
+                    assert list(found.keys()) == expected_ids, (name, vc, seed)
+            if bg is not None:
+                bg.drop()
+    finally:
+        nrpcalc_b200.unpatch()

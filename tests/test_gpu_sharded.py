@@ -53,10 +53,30 @@ def _worker(rank, world, port, n_parts, k, internal, out_dir, mode='direct', opt
         ops = sharded.NativeOps(ctx)
         ops.load(buf, offsets, ids)
         res = sharded.build_sharded(ops, offsets, k, internal, want_edges=True)
+        if rank == 0:
+            with open(os.path.join(out_dir, 'layout.txt'), 'w') as fh:
+                fh.write(repr(ctx.counts()))
+        # a second, larger batch through the same context: the receive buffers are re-exported (collective close first)
+        if opts is None and mode == 'direct' and k == 17:
+            more = cases.random_parts(4 * n_parts, 100, 10)
+            off2 = np.arange(len(more) + 1, dtype=np.int64) * 100
+            buf2 = np.frombuffer(''.join(more).encode(), dtype=np.uint8)
+            ids2 = np.arange(len(more), dtype=np.uint32)[::-1].copy()
+            ops.load(buf2, off2, ids2)
+            big = sharded.build_sharded(ops, off2, k, internal, want_edges=True)
+            if rank == 0:
+                ctx.load_parts(buf2, off2, ids2)
+                ctx.build(k, internal, True)
+                one2 = ctx.fetch()
+                assert sorted(zip(big['edges'][0].tolist(), big['edges'][1].tolist())) == sorted(zip(one2.edges[0].tolist(), one2.edges[1].tolist()))
+                assert big['last_single'].tolist() == one2.last_single.tolist() and big['indptr'].size == one2.indptr.size
+            ops.load(buf, offsets, ids)
+            res = sharded.build_sharded(ops, offsets, k, internal, want_edges=True)
         np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), flags=res['flags'], indptr=res['indptr'], members=res['members'],
                  first_window=res['first_window'], last_single=res['last_single'], eu=res['edges'][0], ev=res['edges'][1],
                  records=res['stats']['records'])
         if rank == 0:       # single-GPU result of the same input on the same device
+            ctx.set_option('no_window_carry', 0)
             ctx.load_parts(buf, offsets, ids)
             ctx.build(k, internal, True)
             one = ctx.fetch()
@@ -79,6 +99,10 @@ def _groups(res):
     (13, False, 'direct', {'leaf_target': 20}, 0),                              # senders pre-partition by 5 bits, one owner level
     (17, False, 'direct', {'leaf_target': 20, 'nvlink_digits': 2}, 0),          # scatter by owner only, two owner levels
     (17, True, 'direct', {'leaf_target': 20, 'nvlink_digits': 2, 'packed': 0}, 0),
+    (21, False, 'direct', None, 0), (21, True, 'direct', None, 0),              # BASELINE config 4's k: packed word, owner = top hash bits
+    (21, False, 'direct', {'no_window_carry': 1}, 0),                           # ... window index NOT carried (the 4/8-GPU layout of config 4)
+    (25, False, 'direct', {'no_window_carry': 1}, 0),                           # config 5's k
+    (21, False, 'direct', {'no_window_carry': 1, 'leaf_target': 20, 'nvlink_digits': 2}, 0),   # owner-only scatter, two owner levels, no window
     (13, True, 'direct', None, 300),                                            # region overflow -> counted exchange
     (13, False, 'counted', None, 0), (17, True, 'counted', None, 0), (17, False, 'nccl', None, 0)])
 def test_sharded_equals_single_gpu(tmp_path, k, internal, mode, opts, dups):
