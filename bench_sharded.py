@@ -74,18 +74,28 @@ def main(args, cfg, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
 
-    # end to end: host buffers in (every rank stages all parts), merged host results out
-    e2e = []
-    for _ in range(max(2, args.steps // 2)):
+    # end to end: host buffers in, merged host results out.  Every rank stages only ITS shard of the parts (page-locked host
+    # buffer, chunked copy; parts of one length need no offsets array) plus the part ids; the results come back through NCCL
+    # all-gathers of the arrays and one device-to-host copy per rank.
+    uniform = not isinstance(cfg['length'], tuple)
+    host_ids = torch.from_numpy(ids.copy()).pin_memory()
+    e2e, e2e_load = [], []
+    for _ in range(2 + max(2, args.steps // 2)):
         flush.fill_(1)
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
-        ops.load(host_ascii.numpy(), off, ids)
+        if uniform:
+            ops.load_shard(host_ascii.numpy(), None, host_ids.numpy(), k, part_len=cfg['length'])
+        else:
+            ops.load_shard(host_ascii.numpy(), off, host_ids.numpy(), k)
+        t1 = time.perf_counter()
         res = step(gather_host=True)
-        dt = torch.tensor([(time.perf_counter() - t0) * 1e3], device='cuda')
+        dt = torch.tensor([(time.perf_counter() - t0) * 1e3, (t1 - t0) * 1e3], device='cuda')
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e.append(float(dt.item()))
+        e2e.append(float(dt[0].item())); e2e_load.append(float(dt[1].item()))
+    e2e, e2e_load = e2e[2:], e2e_load[2:]                    # the first two passes allocate and map the peers' buffers
+    shard_bytes = int(buf.nbytes // world) if uniform else int(off[res['stats']['bounds'][rank][1]] - off[res['stats']['bounds'][rank][0]])
     m = res['stats']['records']
     stage = ctx.timings()
     owner_levels = 2 if stage.get('split2', 0.0) > 0 else 1        # split levels the owner ran over the received regions
@@ -116,9 +126,12 @@ def main(args, cfg, rank, world, local_rank):
                            'kmers': m, 'edges': want_edges, 'record_bytes': rec, 'sharding': 'parts block-sharded, k-mers hash-partitioned, 1 exchange (' + os.environ.get('NRPCALC_B200_EXCHANGE', 'peer') + ')',
                            'l2': 'explicit 256 MiB flush between steps', 'timing': 'wall clock between barrier+synchronize around the device phase (results resident on the devices), max over ranks'},
                 'parts_per_s': n_parts / (ms_per_step * 1e-3),
-                'e2e': {'value': m / (np.mean(e2e) * 1e-3), 'unit': 'k-mers/s', 'h2d_bytes_per_step': int(world * (buf.nbytes + off.nbytes + ids.nbytes)),
-                        'd2h_bytes_per_step': int(world * (res['flags'].nbytes + res['members'].nbytes + res['indptr'].nbytes + res['last_single'].nbytes)),
-                        'ms_per_step': float(np.mean(e2e)), 'path': 'per rank: nrp_load_parts(host, all parts) + sharded build + merged host results'},
+                'e2e': {'value': m / (np.mean(e2e) * 1e-3), 'unit': 'k-mers/s',
+                        'h2d_bytes_per_step': int(buf.nbytes + world * ids.nbytes + (0 if uniform else world * off.nbytes)),
+                        'd2h_bytes_per_step': int(world * (res['flags'].nbytes + res['members'].nbytes + res['first_window'].nbytes + res['keys'].nbytes +
+                                                           res['indptr'].nbytes + res['last_single'].nbytes + (res['edges'][0].nbytes * 2 if res['edges'] else 0))),
+                        'ms_per_step': float(np.mean(e2e)), 'ms_load': float(np.mean(e2e_load)), 'h2d_bytes_this_rank': shard_bytes + int(ids.nbytes),
+                        'path': 'per rank: nrp_load_parts_shard (page-locked host buffer, ONLY the rank\'s shard of the parts travels; ids in full) + sharded build + NCCL all-gather of the result arrays + one D2H copy'},
                 'gpu_launches': int(launches.item()),
                 'clocks': clocks,
                 'phase_ms_per_rank': all_phases,

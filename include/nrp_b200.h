@@ -217,6 +217,20 @@ int nrp_shard_scatter_direct(nrp_ctx* ctx, int64_t part_lo, int64_t part_hi, int
 int nrp_shard_group_direct(nrp_ctx* ctx, int k, int internal_repeats);
 /* out[0] = records this rank sent in the last nrp_shard_scatter_direct, out[1] = records it received and partitioned */
 int nrp_shard_moved(nrp_ctx* ctx, int64_t out[2]);
+/* Shard-only staging (multi-GPU end to end): every rank copies only the bytes of ITS shard [stage_lo, stage_hi) to the device
+ * -- 1/N of the host-to-device traffic -- while the device buffer, the offsets, the ids and the record values stay GLOBAL (a
+ * part keeps its global index and byte offset on every rank).  offsets == NULL: parts of one length part_len.  The one place
+ * that needs a foreign part's bytes (the first window of a shared k-mer when records do not carry the window index) reads them
+ * from the home rank's buffer over NVLink: nrp_peer_export_parts / nrp_peer_open_parts exchange the CUDA IPC handles of the
+ * part buffers and the shard bounds (part_bounds[r] .. part_bounds[r + 1] live on rank r).  nrp_build refuses a context
+ * that holds only a shard.  Replaces nothing in the reference (it has no distributed mode); host side: sharded.py. */
+int nrp_load_parts_shard(nrp_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int part_len, const uint32_t* part_id, int64_t n_parts,
+                         int64_t stage_lo, int64_t stage_hi, int n_chunks);
+/* bytes the part buffer can hold without being re-allocated (a batch that needs more must not be loaded while peers map the
+ * buffer: nrp_peer_close on every rank first) */
+int nrp_parts_capacity(nrp_ctx* ctx, int64_t* bytes);
+int nrp_peer_export_parts(nrp_ctx* ctx, unsigned char* handle /*64*/);
+int nrp_peer_open_parts(nrp_ctx* ctx, int n_peers, int my_rank, const unsigned char* handles /* n_peers x 64 */, const int64_t* part_bounds /* n_peers + 1 */);
 /* Close every peer mapping this context opened (cudaIpcCloseMemHandle) and forget the handles.  COLLECTIVE by contract: before
  * any rank re-exports its receive buffers (nrp_peer_export / nrp_peer_export_direct may free and re-allocate them), ALL ranks
  * call nrp_peer_close and synchronise (barrier) -- CUDA leaves freeing an exported allocation that an importer still maps

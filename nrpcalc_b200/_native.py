@@ -94,6 +94,10 @@ def _declare(lib):
         'nrp_shard_group_direct': (c_ctx, i32, i32),
         'nrp_shard_moved': (c_ctx, ptr),
         'nrp_peer_close': (c_ctx,),
+        'nrp_load_parts_shard': (c_ctx, ptr, ptr, i32, ptr, i64, i64, i64, i32),
+        'nrp_parts_capacity': (c_ctx, ctypes.POINTER(i64)),
+        'nrp_peer_export_parts': (c_ctx, ptr),
+        'nrp_peer_open_parts': (c_ctx, i32, i32, ptr, ptr),
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -212,6 +216,37 @@ class Context(object):
         self._keep = (ascii_buf, part_id)
         _check(self._lib, self._lib.nrp_load_parts_uniform(self._h, _p(ascii_buf), int(n_parts), int(part_len), _p(part_id), int(chunks)))
         self.n_parts = int(n_parts)
+
+    def load_parts_shard(self, ascii_buf, offsets, part_len, part_id, n_parts, stage_lo, stage_hi, chunks=4):
+        """Shard-only staging (nrp_load_parts_shard): only the bytes of the parts [stage_lo, stage_hi) travel to the device;
+        offsets=None for parts of one length part_len.  The context keeps references to the host arrays until the next build."""
+        ascii_buf = np.ascontiguousarray(ascii_buf, dtype=np.uint8)
+        if offsets is not None:
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+            assert offsets.size == n_parts + 1
+        if part_id is not None:
+            part_id = np.ascontiguousarray(part_id, dtype=np.uint32)
+            assert part_id.size == n_parts
+        self._keep = (ascii_buf, offsets, part_id)
+        _check(self._lib, self._lib.nrp_load_parts_shard(self._h, _p(ascii_buf), _p(offsets), int(part_len or 0), _p(part_id), int(n_parts),
+                                                         int(stage_lo), int(stage_hi), int(chunks)))
+        self.n_parts = int(n_parts)
+
+    def parts_capacity(self):
+        out = ctypes.c_int64(0)
+        _check(self._lib, self._lib.nrp_parts_capacity(self._h, ctypes.byref(out)))
+        return out.value
+
+    def peer_export_parts(self):
+        handle = np.zeros(64, dtype=np.uint8)
+        _check(self._lib, self._lib.nrp_peer_export_parts(self._h, _p(handle)))
+        return handle
+
+    def peer_open_parts(self, handles, my_rank, part_bounds):
+        """handles: uint8 array of n_peers x 64 bytes; part_bounds: n_peers + 1 first part indices"""
+        blob = np.ascontiguousarray(handles, dtype=np.uint8).reshape(-1)
+        bounds = np.ascontiguousarray(part_bounds, dtype=np.int64)
+        _check(self._lib, self._lib.nrp_peer_open_parts(self._h, bounds.size - 1, int(my_rank), _p(blob), _p(bounds)))
 
     def build(self, k, internal_repeats, want_edges=True):
         _check(self._lib, self._lib.nrp_build(self._h, int(k), 1 if internal_repeats else 0, 1 if want_edges else 0))

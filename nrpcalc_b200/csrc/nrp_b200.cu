@@ -165,6 +165,8 @@ struct nrp_ctx {
   int64_t n_parts = 0, total_len = 0, n_tiles = 0, max_len = 0;
   int uniform_len = 0;
   bool have_parts = false, have_ids = false;
+  int64_t staged_lo = 0, staged_hi = 0;      // parts whose bytes are on this device (shard-only staging: a sub-range)
+  PartHomes homes{};                         // shard-only staging: the ranks' part buffers (CUDA IPC) and shard bounds
   bool flags_set = false;                    // the flag pass of the current job ran a kernel (some flag byte may be non-zero)
   int coop_blocks_per_sm[2] = {0, 0};
   bool group_counts_coop = false;
@@ -513,8 +515,10 @@ int nrp_bg_build_fetch(nrp_ctx* c, uint64_t* keys_out) {
 
 // uniform_hint > 0: every part has exactly this many bytes and `offsets` is NULL (nothing to validate or to stage: part i
 // starts at i * uniform_hint)
+// copy_lo / copy_hi: only the bytes of the parts [copy_lo, copy_hi) are copied (shard-only staging; -1 = all).  The device buffer
+// still spans ALL parts and every part keeps its global offset, so that record values, offsets and flags stay global.
 static int load_parts_impl(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, const uint32_t* part_id, int64_t n_parts, int ascii_on_device,
-                           int n_chunks, int64_t uniform_hint = 0) {
+                           int n_chunks, int64_t uniform_hint = 0, int64_t copy_lo = -1, int64_t copy_hi = -1) {
   if (!c) return fail(NRP_E_ARG, "null context");
   const bool hinted = uniform_hint > 0;
   if (n_parts < 0 || (!hinted && !offsets) || (hinted && uniform_hint >= ((int64_t)1 << 30))) return fail(NRP_E_ARG, "bad part buffers");
@@ -523,33 +527,39 @@ static int load_parts_impl(nrp_ctx* c, const uint8_t* ascii, const int64_t* offs
   const int64_t total = hinted ? n_parts * uniform_hint : offsets[n_parts];
   if (total < 0) return fail(NRP_E_ARG, "negative total length");
   if (n_parts > 0 && !ascii && total > 0) return fail(NRP_E_ARG, "bad part buffers");
+  if (copy_lo < 0) { copy_lo = 0; copy_hi = n_parts; }
+  if (copy_lo > copy_hi || copy_hi > n_parts) return fail(NRP_E_ARG, "bad staging range");
   CU(cudaSetDevice(c->device));
   c->have_parts = false; c->have_result = false;
   auto first_byte = [&](int64_t part) -> int64_t { return hinted ? part * uniform_hint : offsets[part]; };
+  const int64_t range_lo = first_byte(copy_lo), range_hi = first_byte(copy_hi);     // bytes that travel
   // the big copy goes first: the DMA runs while the host validates the offsets and stages the small arrays
   const int64_t n_tiles = (total + kTileBytes - 1) / kTileBytes;
   const size_t padded = (size_t)n_tiles * kTileBytes + 256;
+  if (padded > c->ascii.cap && c->homes.n > 0)
+    return fail(NRP_E_STATE, "the part buffer is mapped by peers and would be re-allocated: call nrp_peer_close on every rank first");
   TRY(c->ascii.ensure(padded));
   if (c->pending_chunks > 0) { CU(cudaStreamSynchronize(c->copy_stream)); c->pending_chunks = 0; }     // an earlier streamed batch nobody consumed
   CU(cudaStreamSynchronize(c->stream));                     // nothing of the previous batch is still in flight (staging buffers are reused)
-  const bool streamed = n_chunks > 1 && !ascii_on_device && total > 0 && n_parts > 1;
+  const bool streamed = n_chunks > 1 && !ascii_on_device && range_hi > range_lo && copy_hi - copy_lo > 1;
   if (!streamed) {
     CU(cudaMemsetAsync(c->ascii.as<uint8_t>() + total, 0, padded - (size_t)total, c->stream));
-    if (total > 0)
-      CU(cudaMemcpyAsync(c->ascii.ptr, ascii, (size_t)total, ascii_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    if (range_hi > range_lo)
+      CU(cudaMemcpyAsync(c->ascii.as<uint8_t>() + range_lo, ascii + range_lo, (size_t)(range_hi - range_lo),
+                         ascii_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
   } else {
     // pieces = contiguous part ranges of about equal bytes, copied on a second stream; each records an event when it has landed
     if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaMemsetAsync(c->ascii.as<uint8_t>() + total, 0, padded - (size_t)total, c->copy_stream));
-    int64_t p_lo = 0;
+    int64_t p_lo = copy_lo;
     int used = 0;
-    for (int i = 0; i < n_chunks && p_lo < n_parts; ++i) {
-      int64_t p_hi = n_parts;
+    for (int i = 0; i < n_chunks && p_lo < copy_hi; ++i) {
+      int64_t p_hi = copy_hi;
       if (i + 1 < n_chunks) {
-        const int64_t target = total / n_chunks * (i + 1);
-        p_hi = hinted ? (target + uniform_hint - 1) / uniform_hint : std::lower_bound(offsets + p_lo + 1, offsets + n_parts, target) - offsets;
+        const int64_t target = range_lo + (range_hi - range_lo) / n_chunks * (i + 1);
+        p_hi = hinted ? (target + uniform_hint - 1) / uniform_hint : std::lower_bound(offsets + p_lo + 1, offsets + copy_hi, target) - offsets;
         if (p_hi <= p_lo) p_hi = p_lo + 1;
-        if (p_hi > n_parts) p_hi = n_parts;
+        if (p_hi > copy_hi) p_hi = copy_hi;
       }
       const int64_t b_lo = first_byte(p_lo), b_hi = first_byte(p_hi);
       if ((size_t)used >= c->chunks.size()) { nrp_ctx::Chunk ch{}; CU(cudaEventCreateWithFlags(&ch.landed, cudaEventDisableTiming)); c->chunks.push_back(ch); }
@@ -614,7 +624,7 @@ static int load_parts_impl(nrp_ctx* c, const uint8_t* ascii, const int64_t* offs
       // behind the pieces on the copy stream (the ids are read last, by the edge expansion); an empty piece carries the event
       if ((size_t)c->pending_chunks >= c->chunks.size()) { nrp_ctx::Chunk ch{}; CU(cudaEventCreateWithFlags(&ch.landed, cudaEventDisableTiming)); c->chunks.push_back(ch); }
       nrp_ctx::Chunk& ch = c->chunks[c->pending_chunks++];
-      ch.part_lo = ch.part_hi = n_parts; ch.tile_lo = 0; ch.n_tiles = 0;
+      ch.part_lo = ch.part_hi = copy_hi; ch.tile_lo = 0; ch.n_tiles = 0;
       CU(cudaMemcpyAsync(c->part_id.ptr, src, id_bytes, cudaMemcpyHostToDevice, c->copy_stream));
       CU(cudaEventRecord(ch.landed, c->copy_stream));
     } else {
@@ -630,6 +640,7 @@ static int load_parts_impl(nrp_ctx* c, const uint8_t* ascii, const int64_t* offs
   if (!streamed) CU(cudaStreamSynchronize(c->stream));
   c->part_base = 0;
   c->shard_lo = 0; c->shard_hi = n_parts; c->shard_tile_lo = 0; c->shard_tiles = c->n_tiles;
+  c->staged_lo = copy_lo; c->staged_hi = copy_hi;
   c->n_owners = 0;
   c->have_parts = true;
   return NRP_OK;
@@ -648,6 +659,14 @@ int nrp_load_parts_uniform(nrp_ctx* c, const uint8_t* ascii, int64_t n_parts, in
   if (n_chunks < 1 || n_chunks > 64) return fail(NRP_E_ARG, "n_chunks must be in [1, 64]");
   if (part_len < 1) return fail(NRP_E_ARG, "part_len must be positive");
   return load_parts_impl(c, ascii, nullptr, part_id, n_parts, 0, n_chunks, part_len);
+}
+
+int nrp_load_parts_shard(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, int part_len, const uint32_t* part_id, int64_t n_parts,
+                         int64_t stage_lo, int64_t stage_hi, int n_chunks) {
+  if (n_chunks < 1 || n_chunks > 64) return fail(NRP_E_ARG, "n_chunks must be in [1, 64]");
+  if (!offsets && part_len < 1) return fail(NRP_E_ARG, "offsets or a positive part_len is required");
+  if (stage_lo < 0 || stage_hi < stage_lo || stage_hi > n_parts) return fail(NRP_E_ARG, "bad staging range");
+  return load_parts_impl(c, ascii, offsets, part_id, n_parts, 0, n_chunks, offsets ? 0 : part_len, stage_lo, stage_hi);
 }
 
 }  // extern "C"
@@ -1298,12 +1317,18 @@ int stage_first_window(nrp_ctx* c, int k, StageTimer& tm) {
   cudaStream_t st = c->stream;
   tm.begin(NRP_T_ORDER);
   TRY(c->g_first_part.ensure(4 * (size_t)(c->n_groups + 1))); TRY(c->g_first_window.ensure(4 * (size_t)(c->n_groups + 1)));
+  PartHomes homes{};
+  if (c->staged_lo != 0 || c->staged_hi != c->n_parts) {
+    if (c->homes.n == 0 && c->n_groups > 0 && c->j_bits == 0)
+      return fail(NRP_E_STATE, "shard-only staging needs the peers' part buffers (nrp_peer_open_parts) to rank groups without a carried window");
+    homes = c->homes;
+  }
   if (c->n_groups > 0 && c->j_bits == 0) {
     NRP_LAUNCH((k_gather_first_part<<<grid_for(c->n_groups, 256), 256, 0, st>>>(c->g_indptr.as<int64_t>(), c->g_members.as<uint32_t>(),
                                                                             c->n_groups, c->g_first_part.as<uint32_t>())));
     NRP_LAUNCH((k_group_first_window<<<grid_for(c->n_groups, 128), 128, 0, st>>>(c->ascii.as<uint8_t>(), c->off.as<int64_t>(),
                                                                              c->g_keys.as<uint64_t>(), c->g_first_part.as<uint32_t>(),
-                                                                             c->n_parts, c->n_groups, k, c->g_first_window.as<uint32_t>())));
+                                                                             c->n_parts, c->n_groups, k, c->g_first_window.as<uint32_t>(), homes)));
   }
   CU(cudaGetLastError());
   return NRP_OK;
@@ -1722,6 +1747,8 @@ int nrp_build(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   if (!c) return fail(NRP_E_ARG, "null context");
   if (!c->have_parts) return fail(NRP_E_STATE, "nrp_load_parts has not been called");
   if (k < 1 || k > 32) return fail(NRP_E_UNSUPPORTED, "k=%d outside [1, 32]", k);
+  if (c->staged_lo != 0 || c->staged_hi != c->n_parts) return fail(NRP_E_STATE, "only the parts [%lld, %lld) are staged (nrp_load_parts_shard): nrp_build needs all of them",
+                                                                    (long long)c->staged_lo, (long long)c->staged_hi);
   CU(cudaSetDevice(c->device));
   c->have_result = false;
   return k <= 16 ? build_impl<uint32_t>(c, k, internal_repeats, want_edges) : build_impl<uint64_t>(c, k, internal_repeats, want_edges);
@@ -1743,6 +1770,7 @@ int nrp_shard_extract(nrp_ctx* c, int64_t part_lo, int64_t part_hi, int k, int i
   if (k < 1 || k > 32) return fail(NRP_E_UNSUPPORTED, "k=%d outside [1, 32]", k);
   if (part_lo < 0 || part_hi < part_lo || part_hi > c->n_parts) return fail(NRP_E_ARG, "bad shard range");
   if (n_owners < 1 || n_owners > 256) return fail(NRP_E_ARG, "n_owners must be in [1, 256]");
+  if (part_lo < c->staged_lo || part_hi > c->staged_hi) return fail(NRP_E_STATE, "shard [%lld, %lld) is not staged on this device", (long long)part_lo, (long long)part_hi);
   CU(cudaSetDevice(c->device));
   return k <= 16 ? shard_extract_impl<uint32_t>(c, part_lo, part_hi, k, internal_repeats, n_owners, owner_counts)
                  : shard_extract_impl<uint64_t>(c, part_lo, part_hi, k, internal_repeats, n_owners, owner_counts);
@@ -1895,6 +1923,7 @@ int nrp_shard_count(nrp_ctx* c, int64_t part_lo, int64_t part_hi, int k, int int
   if (k < 1 || k > 32) return fail(NRP_E_UNSUPPORTED, "k=%d outside [1, 32]", k);
   if (part_lo < 0 || part_hi < part_lo || part_hi > c->n_parts) return fail(NRP_E_ARG, "bad shard range");
   if (n_owners < 1 || n_owners > kMaxPeers) return fail(NRP_E_ARG, "n_owners must be in [1, %d]", kMaxPeers);
+  if (part_lo < c->staged_lo || part_hi > c->staged_hi) return fail(NRP_E_STATE, "shard [%lld, %lld) is not staged on this device", (long long)part_lo, (long long)part_hi);
   CU(cudaSetDevice(c->device));
   return k <= 16 ? shard_count_impl<uint32_t>(c, part_lo, part_hi, k, internal_repeats, n_owners, owner_counts)
                  : shard_count_impl<uint64_t>(c, part_lo, part_hi, k, internal_repeats, n_owners, owner_counts);
@@ -2007,6 +2036,7 @@ int nrp_shard_scatter_direct(nrp_ctx* c, int64_t part_lo, int64_t part_hi, int k
   if (part_lo < 0 || part_hi < part_lo || part_hi > c->n_parts) return fail(NRP_E_ARG, "bad shard range");
   if (c->n_peers_d != n_owners || c->sh_world != n_owners) return fail(NRP_E_STATE, "direct peers are not open for %d owners", n_owners);
   if (c->sh_key_bytes != (k <= 16 ? 4 : 8)) return fail(NRP_E_STATE, "receive buffers were exported for another key width");
+  if (part_lo < c->staged_lo || part_hi > c->staged_hi) return fail(NRP_E_STATE, "shard [%lld, %lld) is not staged on this device", (long long)part_lo, (long long)part_hi);
   CU(cudaSetDevice(c->device));
   return k <= 16 ? shard_scatter_direct_impl<uint32_t>(c, part_lo, part_hi, k, internal_repeats, n_owners, overflow)
                  : shard_scatter_direct_impl<uint64_t>(c, part_lo, part_hi, k, internal_repeats, n_owners, overflow);
@@ -2020,10 +2050,55 @@ int nrp_shard_group_direct(nrp_ctx* c, int k, int internal_repeats) {
   return k <= 16 ? shard_group_direct_impl<uint32_t>(c, k, internal_repeats) : shard_group_direct_impl<uint64_t>(c, k, internal_repeats);
 }
 
+int nrp_parts_capacity(nrp_ctx* c, int64_t* bytes) {
+  if (!c || !bytes) return fail(NRP_E_ARG, "null argument");
+  *bytes = (int64_t)c->ascii.cap;
+  return NRP_OK;
+}
+
+int nrp_peer_export_parts(nrp_ctx* c, unsigned char* handle) {
+  if (!c || !handle) return fail(NRP_E_ARG, "null argument");
+  if (!c->have_parts || !c->ascii.ptr) return fail(NRP_E_STATE, "no parts are staged");
+  CU(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, c->ascii.ptr));
+  memcpy(handle, &h, 64);
+  return NRP_OK;
+}
+
+int nrp_peer_open_parts(nrp_ctx* c, int n_peers, int my_rank, const unsigned char* handles, const int64_t* part_bounds) {
+  if (!c || !handles || !part_bounds) return fail(NRP_E_ARG, "null argument");
+  if (n_peers < 1 || n_peers > kMaxPeers || my_rank < 0 || my_rank >= n_peers) return fail(NRP_E_ARG, "bad peer count");
+  CU(cudaSetDevice(c->device));
+  PartHomes homes{};
+  for (int p = 0; p < n_peers; ++p) {
+    homes.first[p] = part_bounds[p];
+    if (p == my_rank) { homes.base[p] = c->ascii.as<uint8_t>(); continue; }
+    const unsigned char* h = handles + (size_t)p * 64;
+    void* ptr = nullptr;
+    for (size_t i = 0; i < c->opened_handles.size(); ++i)
+      if (memcmp(c->opened_handles[i].data(), h, 64) == 0) ptr = c->opened_ptrs[i];
+    if (!ptr) {
+      cudaIpcMemHandle_t handle;
+      memcpy(&handle, h, 64);
+      CU(cudaIpcOpenMemHandle(&ptr, handle, cudaIpcMemLazyEnablePeerAccess));
+      c->opened_handles.emplace_back(h, h + 64);
+      c->opened_ptrs.push_back(ptr);
+    }
+    homes.base[p] = reinterpret_cast<const uint8_t*>(ptr);
+  }
+  homes.first[n_peers] = part_bounds[n_peers];
+  homes.n = n_peers;
+  c->homes = homes;
+  c->my_rank = my_rank;
+  return NRP_OK;
+}
+
 int nrp_peer_close(nrp_ctx* c) {
   if (!c) return fail(NRP_E_ARG, "null context");
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
+  c->homes = PartHomes{};
   for (void* p : c->opened_ptrs) cudaIpcCloseMemHandle(p);
   c->opened_ptrs.clear();
   c->opened_handles.clear();

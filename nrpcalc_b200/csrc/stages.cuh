@@ -455,12 +455,21 @@ __device__ __forceinline__ uint64_t window_from_ascii(const uint8_t* seq, int k)
 
 // first window of part `first_part[g]` whose canonical k-mer equals the group's key: the rank of the group
 // (reference: position of the key's first insertion into repeat_dict, hgraph.py:82-89)
+// (shard-only staging: the bytes of part p live on the rank whose shard holds p -- every rank keeps them at the same global
+// offset of its own part buffer, mapped here through CUDA IPC, so a foreign part is read over NVLink)
+struct PartHomes {
+  const uint8_t* base[kMaxPeers];    // part buffer of rank r (the own rank: local memory)
+  int64_t first[kMaxPeers + 1];      // rank r holds the parts [first[r], first[r + 1])
+  int n;                             // 0: everything is staged locally
+};
 __global__ void k_group_first_window(const uint8_t* ascii, const int64_t* off, const uint64_t* group_keys, const uint32_t* first_part,
-                                     int64_t n_parts, int64_t n_groups, int k, uint32_t* first_window) {
+                                     int64_t n_parts, int64_t n_groups, int k, uint32_t* first_window, PartHomes homes) {
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_groups) return;
   int64_t p = (int64_t)first_part[g];
   if (p >= n_parts) return;
+  for (int r = 0; r < homes.n; ++r)
+    if (p >= homes.first[r] && p < homes.first[r + 1]) ascii = homes.base[r];
   const uint8_t* seq = ascii + off[p];
   const int64_t len = off[p + 1] - off[p];
   const uint64_t key = group_keys[g];

@@ -106,7 +106,7 @@ def _device_build(ctx, structure, ascii_buf, offsets, global_p, ids, k, internal
         ops = getattr(ctx, '_sharded_ops', None)           # one per context: the peer mappings of the exchange live in it
         if ops is None:
             ops = ctx._sharded_ops = sharded.NativeOps(ctx)
-        ops.load(ascii_buf, offsets, ids if want_edges else None)
+        ops.load_shard(ascii_buf, offsets, ids if want_edges else None, k)      # every rank stages its own shard only
         out = sharded.build_sharded(ops, offsets, k, internal_repeats, want_edges=want_edges)
         flags, indptr, members = out['flags'], out['indptr'], out['members']
         first_window, last_single = out['first_window'], out['last_single']

@@ -63,9 +63,42 @@ class NativeOps(object):
             self.stage_ms[name] = value           # cumulative inside the library for the current job
 
     def load(self, ascii_buf, offsets, ids, device_ptr=None):
+        """Stage ALL parts on this rank's device."""
         self.ctx.load_parts(ascii_buf, offsets, ids, device_ptr=device_ptr)
         self.n_parts = len(offsets) - 1
         self.max_len = int(np.diff(offsets).max()) if self.n_parts else 0
+        self.staged_bounds = None
+
+    def load_shard(self, ascii_buf, offsets, ids, k, group=None, part_len=None, chunks=4):
+        """COLLECTIVE.  Stage only this rank's shard (the part range build_sharded will give it): 1/world of the host-to-device
+        traffic.  The device buffer, offsets, ids and record values stay global; the part buffers of all ranks are mapped
+        through CUDA IPC so that the first window of a shared k-mer can be read from its home rank over NVLink.
+        offsets=None with part_len: parts of one length (no offsets array is built or copied)."""
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if offsets is None:
+            n = int(len(ids)) if ids is not None else int(len(ascii_buf) // part_len)
+            cuts = [(n * r) // world for r in range(world + 1)]
+            bounds = [(cuts[r], cuts[r + 1]) for r in range(world)]
+            total, self.max_len = n * int(part_len), int(part_len)
+        else:
+            offsets = np.asarray(offsets, dtype=np.int64)
+            n = offsets.size - 1
+            lengths = np.diff(offsets)
+            bounds = shard_bounds(lengths, k, world)
+            total, self.max_len = int(offsets[-1]), (int(lengths.max()) if n else 0)
+        needed = ((total + 4095) // 4096) * 4096 + 256
+        if needed > self.ctx.parts_capacity():
+            self._close_peers(group, force=True)           # the part buffer will be re-allocated: nobody may still map it
+        lo, hi = bounds[rank]
+        self.ctx.load_parts_shard(ascii_buf, offsets, part_len, ids, n, lo, hi, chunks=chunks)
+        self.n_parts = n
+        self.staged_bounds = bounds
+        # exchange the IPC handles of the part buffers (64 bytes per rank) and open the peers'
+        mine = torch.from_numpy(self.ctx.peer_export_parts()).to(self.device)
+        everyone = torch.empty(64 * world, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(everyone, mine, group=group)
+        self.ctx.peer_open_parts(everyone.cpu().numpy(), rank, [b[0] for b in bounds] + [n])
+        self._parts_open = True
 
     def extract(self, lo, hi, k, internal_repeats, world):
         counts = self.ctx.shard_extract(lo, hi, k, internal_repeats, world)
@@ -85,13 +118,15 @@ class NativeOps(object):
             return False
         return True
 
-    def _close_peers(self, group):
-        """Before any rank re-exports (and possibly re-allocates) its receive buffers: every rank drops its mappings of the
+    def _close_peers(self, group, force=False):
+        """Before any rank re-exports (and possibly re-allocates) a buffer its peers map: every rank drops its mappings of the
         peers' buffers, then all meet at a barrier (freeing an exported allocation a peer still maps is undefined in CUDA)."""
-        if getattr(self, '_peer_key_direct', None) is None and getattr(self, '_peer_key', None) is None:
+        if (getattr(self, '_peer_key_direct', None) is None and getattr(self, '_peer_key', None) is None
+                and not getattr(self, '_parts_open', False) and not force):
             return
         self.ctx.peer_close()
         self._peer_key_direct = self._peer_key = None
+        self._parts_open = False
         dist.barrier(group=group)
 
     def exchange_direct(self, lo, hi, k, internal_repeats, windows_total, group, phases):
@@ -192,6 +227,48 @@ class NativeOps(object):
         torch.cuda.current_stream(self.device).synchronize()
         self.ctx.edges_merge(codes.data_ptr() if codes.numel() else 0, 0, codes.numel())
 
+    def gather_results(self, group, lo, hi, n, want_edges):
+        """Every rank's groups and last single windows on every host, through NCCL all-gathers of the arrays themselves (device
+        views of the library's result buffers, one small size exchange, one padded all-gather, one device-to-host copy)."""
+        world = dist.get_world_size(group)
+        counts = self.ctx.counts()
+        indptr = self._view(5, torch.int64, '<i8')
+        members = self._view(6, torch.int32, '<i4')
+        first_window = self._view(7, torch.int32, '<i4')
+        keys = self._view(0, torch.int64, '<i8')
+        last_single = self._view(4, torch.int32, '<i4')[lo:hi] if n else torch.empty(0, dtype=torch.int32, device=self.device)
+        ng, nm = int(keys.numel()), int(members.numel())
+        sizes = torch.tensor([ng, nm, hi - lo, counts['candidates'], counts['oversized']], dtype=torch.int64, device=self.device)
+        all_sizes = torch.empty(5 * world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(all_sizes, sizes, group=group)
+        all_sizes = all_sizes.cpu().view(world, 5).tolist()
+        # one int32 payload per rank: group sizes | members | first windows | keys (two words each) | last single windows
+        group_sizes = (indptr[1:] - indptr[:-1]).to(torch.int32) if ng else torch.empty(0, dtype=torch.int32, device=self.device)
+        payload = torch.cat([group_sizes, members, first_window, keys.view(torch.int32), last_single])
+        longest = max(2 * s[0] + s[1] + 2 * s[0] + s[2] for s in all_sizes)
+        padded = torch.empty(max(longest, 1), dtype=torch.int32, device=self.device)
+        padded[:payload.numel()] = payload
+        everything = torch.empty(world * padded.numel(), dtype=torch.int32, device=self.device)
+        dist.all_gather_into_tensor(everything, padded, group=group)
+        host = everything.cpu().numpy().reshape(world, -1)
+        parts = {'sizes': [], 'members': [], 'first_window': [], 'keys': [], 'last_single': []}
+        for r, (g, m, span, _, _) in enumerate(all_sizes):
+            row, at = host[r], 0
+            for name, count in (('sizes', g), ('members', m), ('first_window', g), ('keys', 2 * g), ('last_single', span)):
+                parts[name].append(row[at:at + count])
+                at += count
+        indptr_all = np.zeros(sum(s[0] for s in all_sizes) + 1, dtype=np.int64)
+        np.cumsum(np.concatenate(parts['sizes']).astype(np.int64), out=indptr_all[1:])
+        edges = None
+        if want_edges:
+            eu, ev = self._view(1, torch.int32, '<i4'), self._view(2, torch.int32, '<i4')
+            edges = (eu.cpu().numpy().view(np.uint32), ev.cpu().numpy().view(np.uint32))
+        return {'indptr': indptr_all, 'members': np.concatenate(parts['members']).view(np.uint32),
+                'first_window': np.concatenate(parts['first_window']).view(np.uint32),
+                'keys': np.ascontiguousarray(np.concatenate(parts['keys'])).view(np.uint64),
+                'last_single': np.concatenate(parts['last_single']) if n else np.zeros(0, dtype=np.int32),
+                'edges': edges, 'candidates': [s[3] for s in all_sizes], 'oversized': [s[4] for s in all_sizes]}
+
     def fetch_host(self, want_edges):
         """Host copies of this rank's groups, the flags, this shard's last single windows and the merged edges."""
         counts = self.ctx.counts()
@@ -287,6 +364,9 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
         plan = (stamp, shard_bounds(np.diff(offsets), k, world), windows, int(windows.sum()), weakref.ref(offsets))
         ops._shard_plan = plan
     bounds, windows, windows_total = plan[1], plan[2], plan[3]
+    staged = getattr(ops, 'staged_bounds', None)
+    if staged is not None:                      # shard-only staging: the shards ARE what each rank holds
+        bounds = staged
     lo, hi = bounds[rank]
 
     phases = _Phases(phase_ms, ops.device)
@@ -342,28 +422,33 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
     # records of parts flagged for an internal repeat were exchanged before the flag was known (single path: same)
     stats['records'] = int(per_rank[:, 1].sum()) - int(windows[(flags_host & 1) != 0].sum())
 
-    local = ops.fetch_host(want_edges)
-    gathered = [None] * world
-    dist.all_gather_object(gathered, {'indptr': local['indptr'], 'members': local['members'], 'first_window': local['first_window'],
-                                      'keys': local['keys'], 'last_single': local['last_single'][lo:hi],
-                                      'candidates': local['candidates'], 'oversized': local['oversized']}, group=group)
-    indptr = [np.zeros(1, dtype=np.int64)]
-    base = 0
-    for g in gathered:
-        indptr.append(g['indptr'][1:] + base)
-        base += int(g['indptr'][-1])
-    stats['candidates'] = [g['candidates'] for g in gathered]
-    stats['oversized'] = [g['oversized'] for g in gathered]
-    result = {
-        'flags': flags_host,
-        'indptr': np.concatenate(indptr),
-        'members': np.concatenate([g['members'] for g in gathered]),
-        'first_window': np.concatenate([g['first_window'] for g in gathered]),
-        'keys': np.concatenate([g['keys'] for g in gathered]),
-        'last_single': np.concatenate([g['last_single'] for g in gathered]) if n else np.zeros(0, dtype=np.int32),
-        'edges': local['edges'],
-        'stats': stats,
-    }
+    if hasattr(ops, 'gather_results'):
+        result = ops.gather_results(group, lo, hi, n, want_edges)
+        stats['candidates'], stats['oversized'] = result.pop('candidates'), result.pop('oversized')
+        result.update({'flags': flags_host, 'stats': stats})
+    else:
+        local = ops.fetch_host(want_edges)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {'indptr': local['indptr'], 'members': local['members'], 'first_window': local['first_window'],
+                                          'keys': local['keys'], 'last_single': local['last_single'][lo:hi],
+                                          'candidates': local['candidates'], 'oversized': local['oversized']}, group=group)
+        indptr = [np.zeros(1, dtype=np.int64)]
+        base = 0
+        for g in gathered:
+            indptr.append(g['indptr'][1:] + base)
+            base += int(g['indptr'][-1])
+        stats['candidates'] = [g['candidates'] for g in gathered]
+        stats['oversized'] = [g['oversized'] for g in gathered]
+        result = {
+            'flags': flags_host,
+            'indptr': np.concatenate(indptr),
+            'members': np.concatenate([g['members'] for g in gathered]),
+            'first_window': np.concatenate([g['first_window'] for g in gathered]),
+            'keys': np.concatenate([g['keys'] for g in gathered]),
+            'last_single': np.concatenate([g['last_single'] for g in gathered]) if n else np.zeros(0, dtype=np.int32),
+            'edges': local['edges'],
+            'stats': stats,
+        }
     phases.mark('host_gather')
     return result
 
