@@ -320,6 +320,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', default=None)
     ap.add_argument('--reference-parts', type=int, default=20_000)
+    ap.add_argument('--n-parts', type=int, default=0, help='run a SCALED copy of the configuration with this many parts (labelled as such; development runs)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-edges', action='store_true')
     ap.add_argument('--verify', action='store_true', help='compare the full result with oracle/nrp_oracle.c (default for c1/c2 at N=1; N>1: also against the oracle, besides the single-GPU result)')
@@ -341,7 +342,10 @@ def main():
     # the reference plan shards across 2/4/8 GPUs (strong scaling); --config c2w = one config-2 batch per GPU (weak scaling)
     cfg_name = args.config or ('c4' if multi else 'c2')
     args.weak = cfg_name == 'c2w'
-    cfg = CONFIGS['c2' if args.weak else cfg_name]
+    cfg = dict(CONFIGS['c2' if args.weak else cfg_name])
+    if args.n_parts > 0 and args.n_parts != cfg['n']:
+        cfg['label'] += ' -- SCALED to {} of {} parts'.format(args.n_parts, cfg['n'])
+        cfg['n'] = args.n_parts
 
     if args.impl == 'reference':
         if rank == 0:
