@@ -151,6 +151,8 @@ struct nrp_ctx {
                                           // the kernel sequence at 8e5 candidates, slower at 2e7), 2 = always, 0 = never
   int64_t opt_packed = 1;                 // one 64-bit word per record on the direct path whenever key and value fit
   int64_t opt_direct = 1;                 // fixed-region partition without a histogram pass (falls back to the exact path on overflow)
+  int64_t opt_filter_wide = 0;            // packed leaves of <= 4096 records: three 256-thread CTAs per SM with 16 records per thread (half the
+                                          // per-leaf fixed work per record) when few suspects are expected; 0 = two 512-thread CTAs
   int64_t opt_uniform_kernel = 1;         // parts of one length: the part-aligned extraction kernel (extract.cuh); 0 = the byte-position kernel
 
   // background
@@ -309,6 +311,8 @@ int configure_kernels(nrp_ctx* c) {
                           (int)filter_bloom_smem<8, true, 4096, 2048, 512>()));
   CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, 256, 8, 1024, 4, 256, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)filter_bloom_smem<8, true, 2048, 1024, 256>()));
+  CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, 256, 16, 2048, 3, 256, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)filter_bloom_smem<8, true, 4096, 2048, 256>()));
   CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1, 1024, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)filter_bloom_smem<8, true, 8192, 4096, 1024>()));
   CU(cudaFuncSetAttribute((k_split_uniform<false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
@@ -400,6 +404,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "coop_group") c->opt_coop_group = value < 0 ? 1 : std::min<int64_t>(value, 2);
   else if (n == "packed") c->opt_packed = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "direct") c->opt_direct = value < 0 ? 1 : (value > 0 ? 1 : 0);
+  else if (n == "filter_wide") c->opt_filter_wide = value > 0 ? 1 : 0;
   else if (n == "uniform_kernel") c->opt_uniform_kernel = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
   return NRP_OK;
@@ -820,7 +825,7 @@ PackFmt pack_format(const nrp_ctx* c, int k, int drop, int owner_bits = 0, uint3
 
 template <typename KeyT>
 int launch_filter(nrp_ctx* c, bool packed, PackFmt pf, const void* leaf_keys, const uint32_t* leaf_vals, LeafExtents leaves, uint32_t n_leaf, int bits,
-                  int64_t mean_leaf, KeyT* out_keys, uint32_t* out_vals) {
+                  int64_t mean_leaf, KeyT* out_keys, uint32_t* out_vals, double shared_fraction = 1.0) {
   cudaStream_t st = c->stream;
   unsigned long long* cnt = c->counters.as<unsigned long long>();
   // leaves that average <= 2750 records use the half-size variant (two CTAs per SM); larger ones the full one
@@ -834,6 +839,11 @@ int launch_filter(nrp_ctx* c, bool packed, PackFmt pf, const void* leaf_keys, co
       NRP_LAUNCH((k_filter_bloom<KeyT, 256, 8, 1024, 4, 256, true><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * 4), 256,
                                                                     filter_bloom_smem<8, true, 2048, 1024, 256>(), st>>>(
           leaf_keys, leaf_vals, leaves, n_leaf, bits, pf, std::min<uint32_t>(cap, 2048u), out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
+    else if (small && packed && c->opt_filter_wide && (double)mean_leaf * (shared_fraction + (double)mean_leaf / 65536.0) <= 160.0)
+      // few suspects expected per leaf (shared records + bit-map collisions): three 256-thread CTAs per SM, 16 records per thread
+      NRP_LAUNCH((k_filter_bloom<KeyT, 256, 16, 2048, 3, 256, true><<<(unsigned)std::min<int64_t>(n_leaf, (int64_t)c->n_sms * 3), 256,
+                                                                     filter_bloom_smem<8, true, 4096, 2048, 256>(), st>>>(
+          leaf_keys, leaf_vals, leaves, n_leaf, bits, pf, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
     else if (small && packed)      // two 512-thread CTAs per SM, leaves of up to 4096 records
       NRP_LAUNCH((k_filter_bloom<KeyT, 512, 8, 2048, 2, 512, true><<<grid_small, 512, filter_bloom_smem<8, true, 4096, 2048, 512>(), st>>>(
           leaf_keys, leaf_vals, leaves, n_leaf, bits, pf, cap, out_keys, out_vals, cnt + CNT_CAND, n_over, unsorted)));
@@ -979,8 +989,11 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
   tm.begin(NRP_T_FILTER);
   if (m_max > 0) {
     if (!counted) NRP_LAUNCH((k_region_total<<<1, 1024, 0, st>>>(c->cursor2.as<uint32_t>(), n_leaf, leaf_cap, cnt + CNT_RECORDS)));
+    // expected fraction of records whose k-mer occurs again: all records of the job over the canonical k-mer space (random DNA)
+    const double all_records = c->n_owners > 1 ? (double)m_max * c->n_owners : (double)m_max;
+    const double shared_fraction = k >= 31 ? 0.0 : std::min(1.0, 2.0 * all_records / std::ldexp(1.0, 2 * k));
     TRY((launch_filter<KeyT>(c, packed, pf, leaf_keys, leaf_vals, LeafExtents{nullptr, c->cursor2.as<uint32_t>(), leaf_cap}, n_leaf, bits, m_max >> bits,
-                             (KeyT*)out_keys, out_vals)));
+                             (KeyT*)out_keys, out_vals, shared_fraction)));
   }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->h_counters, cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, st));

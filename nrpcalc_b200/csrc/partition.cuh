@@ -963,7 +963,9 @@ __global__ void __launch_bounds__(T, MINB) k_filter_bloom(const void* __restrict
     clear_table();                                  // table and marks are done: clean for the next leaf
     if (c2 == 0) continue;
     {  // order them by (key, part, window): rank by counting, a power-of-two group of threads per record (2^lg * c2 <= T)
-      const int lg = 31 - __clz((uint32_t)T / c2);
+      // largest power of two 2^lg with 2^lg * c2 <= T (no integer division: T is a power of two, c2 <= T)
+      static_assert((T & (T - 1)) == 0, "T must be a power of two");
+      const int lg = max(0, (31 - __clz((uint32_t)T)) - (32 - __clz(c2 - 1u)));       // log2(T) - ceil(log2(c2))
       const uint32_t cand = threadIdx.x >> lg, seg = threadIdx.x & ((1u << lg) - 1u);
       if (cand < c2) {
         const RecT ck = c_keys[cand];
