@@ -27,7 +27,8 @@ def main(args, cfg, rank, world, local_rank):
     want_edges = not args.no_edges
     ctx = _native.Context(local_rank)
     ops = sharded.NativeOps(ctx)
-    host_ascii = torch.from_numpy(buf.copy()).pin_memory()
+    host_ascii = torch.from_numpy(buf).pin_memory()       # one page-locked copy; the pageable original is dropped
+    buf = host_ascii.numpy()
     dev_ascii = host_ascii.cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     ops.load(None, off, ids, device_ptr=dev_ascii.data_ptr())

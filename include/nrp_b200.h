@@ -249,7 +249,17 @@ int nrp_shard_group(nrp_ctx* ctx, const void* keys_dev, const uint32_t* vals_dev
 /* copy the n_parts per-part flag bytes to / from caller-owned device memory (for the all-reduce) */
 int nrp_flags_export(nrp_ctx* ctx, uint8_t* dst_dev);
 int nrp_flags_import(nrp_ctx* ctx, const uint8_t* src_dev);
+/* Returns NRP_RETRY_DENSE_FLAGS (> 0) when a list handed to nrp_flags_repeat_apply was truncated: the caller combines the flag
+ * bytes densely (nrp_flags_export / all-reduce / nrp_flags_import) and calls nrp_shard_finish again. */
 int nrp_shard_finish(nrp_ctx* ctx, int k, int internal_repeats, int want_edges);
+#define NRP_RETRY_DENSE_FLAGS 1
+/* Sparse form of the flag exchange.  Only the repeat bit has to travel between ranks during the device phase (it is set by the
+ * OWNER of a repeated k-mer, every rank must drop the part's records; palindrome / background bits are set and used by the
+ * part's home rank).  nrp_flags_repeat_list writes {count, part indices...} of the parts this rank flagged into list_dev
+ * (1 + cap words, device memory); after an all-gather, nrp_flags_repeat_apply ORs the lists of all ranks (world rows of
+ * 1 + cap words) into this rank's flags. */
+int nrp_flags_repeat_list(nrp_ctx* ctx, uint32_t* list_dev, int cap);
+int nrp_flags_repeat_apply(nrp_ctx* ctx, const uint32_t* lists_dev, int world, int cap);
 /* shared_keys: canonical k-mers of ALL ranks' groups, any order (host memory, or device memory when keys_on_device != 0);
  * afterwards nrp_result_last_single holds valid entries for the parts of this rank's shard */
 int nrp_shard_last_single(nrp_ctx* ctx, const uint64_t* shared_keys, int64_t n_shared, int k, int keys_on_device);

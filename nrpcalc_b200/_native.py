@@ -94,6 +94,8 @@ def _declare(lib):
         'nrp_shard_group_direct': (c_ctx, i32, i32),
         'nrp_shard_moved': (c_ctx, ptr),
         'nrp_peer_close': (c_ctx,),
+        'nrp_flags_repeat_list': (c_ctx, ptr, i32),
+        'nrp_flags_repeat_apply': (c_ctx, ptr, i32, i32),
         'nrp_load_parts_shard': (c_ctx, ptr, ptr, i32, ptr, i64, i64, i64, i32),
         'nrp_parts_capacity': (c_ctx, ctypes.POINTER(i64)),
         'nrp_peer_export_parts': (c_ctx, ptr),
@@ -327,7 +329,18 @@ class Context(object):
         _check(self._lib, self._lib.nrp_flags_import(self._h, ctypes.c_void_p(int(src_ptr))))
 
     def shard_finish(self, k, internal_repeats, want_edges):
-        _check(self._lib, self._lib.nrp_shard_finish(self._h, int(k), 1 if internal_repeats else 0, 1 if want_edges else 0))
+        """True when the stage finished; False when a sparse flag list was truncated (combine the flags densely and call again)."""
+        code = self._lib.nrp_shard_finish(self._h, int(k), 1 if internal_repeats else 0, 1 if want_edges else 0)
+        if code == 1:                               # NRP_RETRY_DENSE_FLAGS
+            return False
+        _check(self._lib, code)
+        return True
+
+    def flags_repeat_list(self, list_ptr, cap):
+        _check(self._lib, self._lib.nrp_flags_repeat_list(self._h, ctypes.c_void_p(int(list_ptr)), int(cap)))
+
+    def flags_repeat_apply(self, lists_ptr, world, cap):
+        _check(self._lib, self._lib.nrp_flags_repeat_apply(self._h, ctypes.c_void_p(int(lists_ptr)), int(world), int(cap)))
 
     def shard_last_single(self, shared_keys, k, device_ptr=None, n=0):
         """shared keys as a host uint64 array, or (device_ptr, n) for keys already in device memory"""

@@ -107,7 +107,7 @@ struct HostBuf {
   template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
 };
 
-enum { CNT_SCATTER_OVERFLOW = 9, CNT_SENT = 10, CNT_NSORTED = 11, CNT_GROUP = 12 /* 5 words */, CNT_WORDS = 20 };
+enum { CNT_SCATTER_OVERFLOW = 9, CNT_SENT = 10, CNT_NSORTED = 11, CNT_GROUP = 12 /* 5 words */, CNT_FLAG_OVERFLOW = 18, CNT_WORDS = 20 };
 enum { CNT_CAND = 0, CNT_REPEAT = 1, CNT_FLAGGED = 2, CNT_WORK = 3, CNT_OVERSIZED = 4, CNT_UNSORTED = 5, CNT_OVERFLOW = 6, CNT_RECORDS = 7, CNT_N = 8, CNT_EDGES = 8, CNT_TOTAL = 12 };
 
 constexpr int kFilterThreads = 1024;
@@ -151,8 +151,9 @@ struct nrp_ctx {
                                           // the kernel sequence at 8e5 candidates, slower at 2e7), 2 = always, 0 = never
   int64_t opt_packed = 1;                 // one 64-bit word per record on the direct path whenever key and value fit
   int64_t opt_direct = 1;                 // fixed-region partition without a histogram pass (falls back to the exact path on overflow)
-  int64_t opt_filter_wide = 0;            // packed leaves of <= 4096 records: three 256-thread CTAs per SM with 16 records per thread (half the
-                                          // per-leaf fixed work per record) when few suspects are expected; 0 = two 512-thread CTAs
+  int64_t opt_filter_wide = 1;            // packed leaves of <= 4096 records: three 256-thread CTAs per SM with 16 records per thread (half the
+                                          // per-leaf fixed work per record: config 2 filter 0.437 -> 0.381 ms) when few suspects are expected;
+                                          // 0 = two 512-thread CTAs
   int64_t opt_uniform_kernel = 1;         // parts of one length: the part-aligned extraction kernel (extract.cuh); 0 = the byte-position kernel
 
   // background
@@ -169,6 +170,7 @@ struct nrp_ctx {
   bool have_parts = false, have_ids = false;
   int64_t staged_lo = 0, staged_hi = 0;      // parts whose bytes are on this device (shard-only staging: a sub-range)
   PartHomes homes{};                         // shard-only staging: the ranks' part buffers (CUDA IPC) and shard bounds
+  bool flag_lists_applied = false;           // nrp_flags_repeat_apply ran since the last nrp_shard_finish
   bool flags_set = false;                    // the flag pass of the current job ran a kernel (some flag byte may be non-zero)
   int coop_blocks_per_sm[2] = {0, 0};
   bool group_counts_coop = false;
@@ -404,7 +406,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "coop_group") c->opt_coop_group = value < 0 ? 1 : std::min<int64_t>(value, 2);
   else if (n == "packed") c->opt_packed = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "direct") c->opt_direct = value < 0 ? 1 : (value > 0 ? 1 : 0);
-  else if (n == "filter_wide") c->opt_filter_wide = value > 0 ? 1 : 0;
+  else if (n == "filter_wide") c->opt_filter_wide = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "uniform_kernel") c->opt_uniform_kernel = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
   return NRP_OK;
@@ -1555,6 +1557,7 @@ int shard_finish_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   TRY(stage_first_window(c, k, tm));
   if (want_edges) { c->counts[NRP_C_EDGES] = 0; TRY(stage_edges(c, tm)); }
   tm.finish(c->timings);
+  c->n_cand = c->n_sorted;          // the candidate list now holds the kept records only (a repeated finish starts from them)
   c->have_result = true;
   return NRP_OK;
 }
@@ -1820,10 +1823,38 @@ int nrp_flags_import(nrp_ctx* c, const uint8_t* src_dev) {
   return NRP_OK;
 }
 
+int nrp_flags_repeat_list(nrp_ctx* c, uint32_t* list_dev, int cap) {
+  if (!c || !list_dev || cap < 1) return fail(NRP_E_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemsetAsync(list_dev, 0, 4, c->stream));
+  if (c->n_parts > 0)
+    NRP_LAUNCH((k_repeat_list<<<grid_for((c->n_parts + 15) / 16, 256), 256, 0, c->stream>>>(c->flags.as<uint8_t>(), c->n_parts, list_dev, (uint32_t)cap)));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  return NRP_OK;
+}
+
+int nrp_flags_repeat_apply(nrp_ctx* c, const uint32_t* lists_dev, int world, int cap) {
+  if (!c || !lists_dev || cap < 1 || world < 1) return fail(NRP_E_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  uint32_t* overflow = reinterpret_cast<uint32_t*>(c->counters.as<unsigned long long>() + CNT_FLAG_OVERFLOW);
+  CU(cudaMemsetAsync(overflow, 0, 8, c->stream));
+  NRP_LAUNCH((k_repeat_apply<<<32, 256, 0, c->stream>>>(lists_dev, world, (uint32_t)cap, c->flags.as<uint8_t>(), c->n_parts, overflow)));
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(c->h_counters + 56, overflow, 8, cudaMemcpyDeviceToHost, c->stream));
+  c->flag_lists_applied = true;
+  return NRP_OK;          // asynchronous: nrp_shard_finish reports a truncated list (NRP_RETRY_DENSE_FLAGS)
+}
+
 int nrp_shard_finish(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   if (!c) return fail(NRP_E_ARG, "null context");
   CU(cudaSetDevice(c->device));
-  return k <= 16 ? shard_finish_impl<uint32_t>(c, k, internal_repeats, want_edges) : shard_finish_impl<uint64_t>(c, k, internal_repeats, want_edges);
+  const int r = k <= 16 ? shard_finish_impl<uint32_t>(c, k, internal_repeats, want_edges) : shard_finish_impl<uint64_t>(c, k, internal_repeats, want_edges);
+  if (r == NRP_OK && c->flag_lists_applied) {
+    c->flag_lists_applied = false;
+    if ((uint32_t)c->h_counters[56] != 0) return NRP_RETRY_DENSE_FLAGS;     // (the stream was synchronised by the stage)
+  }
+  return r;
 }
 
 int nrp_shard_last_single(nrp_ctx* c, const uint64_t* shared_keys, int64_t n_shared, int k, int keys_on_device) {

@@ -556,6 +556,38 @@ __global__ void k_edge_merge(const uint32_t* u, const uint32_t* v, int64_t n, ui
   if (i < n) edge_insert(u[i], v[i], table, log_slots, out_u, out_v, n_out);
 }
 
+// sharded path: the parts this rank flagged for an internal repeat (it owns the repeated k-mer) as a compact list
+// list[0] = count (may exceed cap: the list then holds the first cap entries), list[1..] = part indices.  16 flag bytes per thread.
+__global__ void k_repeat_list(const uint8_t* flags, int64_t n, uint32_t* list, uint32_t cap) {
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (i0 >= n) return;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (i0 + 16 <= n) v = *reinterpret_cast<const uint4*>(flags + i0);                  // the flag buffer is 16-byte aligned and padded
+  else for (int b = 0; b < 16 && i0 + b < n; ++b) reinterpret_cast<uint8_t*>(&v)[b] = flags[i0 + b];
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  if (((w[0] | w[1] | w[2] | w[3]) & 0x01010101u) == 0) return;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    for (int b = 0; b < 4; ++b)
+      if ((w[q] >> (8 * b)) & kFlagRepeat) {
+        const uint32_t pos = atomicAdd(list, 1u);
+        if (pos < cap) list[1 + pos] = (uint32_t)(i0 + 4 * q + b);
+      }
+}
+// ... and the lists of all ranks (world rows of 1 + cap words) applied to this rank's flags; *overflow is set when some rank's
+// list was truncated (the caller then falls back to the dense all-reduce)
+__global__ void k_repeat_apply(const uint32_t* lists, int world, uint32_t cap, uint8_t* flags, int64_t n, uint32_t* overflow) {
+  for (int r = 0; r < world; ++r) {
+    const uint32_t* row = lists + (size_t)r * (cap + 1);
+    const uint32_t count = row[0];
+    if (count > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1u; continue; }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+      const uint32_t p = row[1 + i];
+      if ((int64_t)p < n) flags[p] |= kFlagRepeat;          // several ranks may flag one part: same value, benign
+    }
+  }
+}
+
 __global__ void k_count_flagged(const uint8_t* flags, int64_t n, unsigned long long* out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool f = i < n && flags[i] != 0;

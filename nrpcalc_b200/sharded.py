@@ -194,6 +194,20 @@ class NativeOps(object):
         torch.cuda.current_stream(self.device).synchronize()
         self.ctx.shard_group(keys.data_ptr() if keys.numel() else 0, vals.data_ptr() if vals.numel() else 0, keys.numel(), k, internal_repeats)
 
+    def exchange_repeat_flags(self, group):
+        """Sparse form of the flag exchange: the parts this rank flagged for an internal repeat travel as a short list (one small
+        all-gather instead of an all-reduce over n_parts bytes); finish() reports a truncated list."""
+        world = dist.get_world_size(group)
+        cap = int(os.environ.get('NRPCALC_B200_FLAG_CAP', '16384'))
+        if getattr(self, '_flag_lists', None) is None or self._flag_lists[0].numel() != cap + 1 or self._flag_lists[1].numel() != world * (cap + 1):
+            self._flag_lists = (torch.empty(cap + 1, dtype=torch.int32, device=self.device),
+                                torch.empty(world * (cap + 1), dtype=torch.int32, device=self.device))
+        mine, everyone = self._flag_lists
+        self.ctx.flags_repeat_list(mine.data_ptr(), cap)
+        dist.all_gather_into_tensor(everyone, mine, group=group)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.ctx.flags_repeat_apply(everyone.data_ptr(), world, cap)
+
     def flags(self):
         out = torch.empty(max(self.n_parts, 1), dtype=torch.uint8, device=self.device)
         self.ctx.flags_export(out.data_ptr())
@@ -212,7 +226,8 @@ class NativeOps(object):
 
     def finish(self, k, internal_repeats, want_edges):
         """Groups of this rank stay on the device; returns zero-copy views of (group keys, edge u, edge v)."""
-        self.ctx.shard_finish(k, internal_repeats, want_edges)
+        if not self.ctx.shard_finish(k, internal_repeats, want_edges):
+            return None                                   # truncated flag list (see exchange_repeat_flags)
         keys = self._view(0, torch.int64, '<i8')
         if want_edges:
             return keys, self._view(1, torch.int32, '<i4'), self._view(2, torch.int32, '<i4')
@@ -226,6 +241,19 @@ class NativeOps(object):
         """codes: int64 tensor of (u << 32) | v gathered from all ranks"""
         torch.cuda.current_stream(self.device).synchronize()
         self.ctx.edges_merge(codes.data_ptr() if codes.numel() else 0, 0, codes.numel())
+
+    def to_host(self, tensor):
+        """Device tensor -> numpy through a cached page-locked staging buffer (a pageable .cpu() runs at a fraction of PCIe speed)."""
+        nbytes = tensor.numel() * tensor.element_size()
+        if nbytes == 0:
+            return np.zeros(0, dtype=torch.empty(0, dtype=tensor.dtype).numpy().dtype)
+        pool = getattr(self, '_pinned', None)
+        if pool is None or pool.numel() < nbytes:
+            pool = self._pinned = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+        view = pool[:nbytes].view(tensor.dtype)
+        view.copy_(tensor.reshape(-1), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return view.numpy().copy()
 
     def gather_results(self, group, lo, hi, n, want_edges):
         """Every rank's groups and last single windows on every host, through NCCL all-gathers of the arrays themselves (device
@@ -250,7 +278,7 @@ class NativeOps(object):
         padded[:payload.numel()] = payload
         everything = torch.empty(world * padded.numel(), dtype=torch.int32, device=self.device)
         dist.all_gather_into_tensor(everything, padded, group=group)
-        host = everything.cpu().numpy().reshape(world, -1)
+        host = self.to_host(everything).reshape(world, -1)
         parts = {'sizes': [], 'members': [], 'first_window': [], 'keys': [], 'last_single': []}
         for r, (g, m, span, _, _) in enumerate(all_sizes):
             row, at = host[r], 0
@@ -262,7 +290,7 @@ class NativeOps(object):
         edges = None
         if want_edges:
             eu, ev = self._view(1, torch.int32, '<i4'), self._view(2, torch.int32, '<i4')
-            edges = (eu.cpu().numpy().view(np.uint32), ev.cpu().numpy().view(np.uint32))
+            edges = (self.to_host(eu).view(np.uint32), self.to_host(ev).view(np.uint32))
         return {'indptr': indptr_all, 'members': np.concatenate(parts['members']).view(np.uint32),
                 'first_window': np.concatenate(parts['first_window']).view(np.uint32),
                 'keys': np.ascontiguousarray(np.concatenate(parts['keys'])).view(np.uint64),
@@ -383,10 +411,19 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
         ops.group(recv_keys, recv_vals, k, internal_repeats)
         moved = (int(np.sum(send_counts)), int(np.sum(recv_counts)))
     phases.mark('group')
-    flags_all = _or_reduce_flags(ops, ops.flags(), group)
-    ops.set_flags(flags_all)
+    flags_all = None
+    if hasattr(ops, 'exchange_repeat_flags') and os.environ.get('NRPCALC_B200_DENSE_FLAGS', '0') != '1':
+        ops.exchange_repeat_flags(group)                # only the repeat bit has to reach the other ranks during the device phase
+    else:
+        flags_all = _or_reduce_flags(ops, ops.flags(), group)
+        ops.set_flags(flags_all)
     phases.mark('flag_reduce')
-    group_keys, edge_u, edge_v = ops.finish(k, internal_repeats, want_edges)
+    finished = ops.finish(k, internal_repeats, want_edges)
+    if finished is None:                                # a rank's list of flagged parts was truncated: the dense all-reduce
+        flags_all = _or_reduce_flags(ops, ops.flags(), group)
+        ops.set_flags(flags_all)
+        finished = ops.finish(k, internal_repeats, want_edges)
+    group_keys, edge_u, edge_v = finished
     phases.mark('finish')
     # one variable-length all-gather carries both small results: the shared k-mers and the edge codes
     n_keys = group_keys.numel()
@@ -418,7 +455,10 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
     per_rank = per_rank.cpu().numpy().reshape(world, 2)
     stats['sent'] = per_rank[:, 0].tolist()
     stats['received'] = per_rank[:, 1].tolist()
-    flags_host = flags_all.cpu().numpy() if n else np.zeros(0, dtype=np.uint8)
+    if flags_all is None:                                # sparse exchange: the other ranks' palindrome / background bits are still missing
+        flags_all = _or_reduce_flags(ops, ops.flags(), group)
+        ops.set_flags(flags_all)
+    flags_host = (ops.to_host(flags_all) if hasattr(ops, 'to_host') else flags_all.cpu().numpy()) if n else np.zeros(0, dtype=np.uint8)
     # records of parts flagged for an internal repeat were exchanged before the flag was known (single path: same)
     stats['records'] = int(per_rank[:, 1].sum()) - int(windows[(flags_host & 1) != 0].sum())
 

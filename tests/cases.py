@@ -18,8 +18,9 @@ def rc(seq):
 def random_dna_buffer(n_parts, length, seed):
     """(ascii uint8[n*L], offsets int64[n+1]) of i.i.d. uniform ACGT parts -- the BASELINE shapes."""
     rng = np.random.default_rng(seed)
-    codes = rng.integers(0, 4, size=n_parts * length, dtype=np.uint8)
-    ascii_buf = _BASES[codes]
+    ascii_buf = rng.integers(0, 4, size=n_parts * length, dtype=np.uint8)
+    for a in range(0, ascii_buf.size, 1 << 26):    # codes -> letters in place, piece by piece
+        ascii_buf[a:a + (1 << 26)] = _BASES[ascii_buf[a:a + (1 << 26)]]
     offsets = np.arange(n_parts + 1, dtype=np.int64) * length
     return ascii_buf, offsets
 
@@ -30,8 +31,10 @@ def random_varlen_buffer(n_parts, lo, hi, seed):
     lengths = rng.integers(lo, hi + 1, size=n_parts, dtype=np.int64)
     offsets = np.zeros(n_parts + 1, dtype=np.int64)
     np.cumsum(lengths, out=offsets[1:])
-    codes = rng.integers(0, 4, size=int(offsets[-1]), dtype=np.uint8)
-    return _BASES[codes], offsets
+    buf = rng.integers(0, 4, size=int(offsets[-1]), dtype=np.uint8)
+    for a in range(0, buf.size, 1 << 26):          # codes -> letters in place, piece by piece (config 5 is 8.75 GB)
+        buf[a:a + (1 << 26)] = _BASES[buf[a:a + (1 << 26)]]
+    return buf, offsets
 
 
 def buffer_to_list(ascii_buf, offsets):

@@ -116,6 +116,20 @@ def test_forced_paths(ctx):
         _compare(_run(ctx, uniq, 13, False), uniq, 13, False)
         _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
         ctx.set_option('coop_group', -1)
+        ctx.set_option('filter_wide', 0)              # two 512-thread filter CTAs per SM instead of three 256-thread ones
+        _compare(_run(ctx, uniq, 13, False), uniq, 13, False)
+        big = _long_parts(cases.planted_parts(800, 5) + cases.random_parts(12000, 100, 6), 17)
+        _compare(_run(ctx, big, 17, False), big, 17, False)
+        ctx.set_option('filter_wide', -1)
+        ctx.set_option('uniform_kernel', 0)           # byte-position extraction kernel on a batch of one length
+        uni = _long_parts(cases.random_parts(6000, 90, 12) + [p[:90] for p in cases.planted_parts(900, 8, lo=90, hi=120, p_short=0, p_dup=0)], 17)
+        res = _run(ctx, uni, 17, False)
+        assert res.counts['uniform_kernel'] == 0
+        _compare(res, uni, 17, False)
+        ctx.set_option('uniform_kernel', -1)
+        res = _run(ctx, uni, 17, False)
+        assert res.counts['uniform_kernel'] == 1
+        _compare(res, uni, 17, False)
         ctx.set_option('filter_tiny', 1)              # 256-thread filter CTAs (leaves that average <= 1400 records)
         _compare(_run(ctx, uniq, 13, False), uniq, 13, False)
         _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
@@ -134,6 +148,8 @@ def test_forced_paths(ctx):
         uniq17 = _long_parts(cases.planted_parts(600, 77), 17)
         _compare(_run(ctx, uniq17, 17, True), uniq17, 17, True)
     finally:
+        ctx.set_option('filter_wide', -1)
+        ctx.set_option('uniform_kernel', -1)
         ctx.set_option('filter_tiny', 0)
         ctx.set_option('coop_group', -1)
         ctx.set_option('direct', -1)
@@ -265,3 +281,44 @@ def test_uniform_streamed_staging(ctx):
         _compare(ctx.fetch(), uniq, k, internal)
     with pytest.raises(_native.NativeError):
         ctx.load_parts_uniform(np.zeros(16, dtype=np.uint8), 4, 0, None, chunks=2)
+
+
+def _uniform_with_repeats(n, length, seed, k):
+    """n parts of ONE length with planted shared / internal / reverse-complement stretches (all stay `length` long)."""
+    import random
+    rnd = random.Random(seed)
+    parts = cases.random_parts(n, length, seed)
+    span = min(length, k + rnd.randint(0, 6))
+    for i in range(0, n, 3):
+        src = parts[rnd.randrange(n)]
+        a, b = rnd.randint(0, length - span), rnd.randint(0, length - span)
+        piece = src[a:a + span]
+        if rnd.random() < 0.4:
+            piece = cases.rc(piece)
+        parts[i] = parts[i][:b] + piece + parts[i][b + span:]
+    return parts
+
+
+@pytest.mark.parametrize('length,k', [(13, 13), (14, 13), (20, 13), (21, 13), (29, 13), (100, 16), (40, 6), (64, 32), (33, 32), (100, 32),
+                                      (300, 25), (57, 17), (2000, 17), (4111, 16), (4200, 17)])
+@pytest.mark.parametrize('internal', [False, True])
+def test_uniform_kernel_shapes(ctx, length, k, internal):
+    """The part-aligned extraction kernel (extract.cuh) at its corners: one window per part, chunks that end inside the last
+    thread of a part, 32-bit and 64-bit keys with no free low bits (k = 16, 32), even k with palindromes (flag pass feeds the
+    kernel), 4096 windows per part (the largest it takes) and beyond (byte-position kernel)."""
+    n = 3000 if length <= 300 else 60
+    uniq = _long_parts(_uniform_with_repeats(n, length, 100 + length + k, k), k)
+    res = _run(ctx, uniq, k, internal)
+    windows = length - k + 1
+    assert res.counts['uniform_kernel'] == (1 if windows <= 4096 and res.counts['packed'] else 0)
+    _compare(res, uniq, k, internal)
+
+
+def test_uniform_kernel_with_background(ctx):
+    parts = _uniform_with_repeats(4000, 80, 5, 16)
+    bg_keys = np_oracle.canonical_key_set(cases.background_seqs_for(parts, 3), 14)
+    uniq = _long_parts(parts, 16)
+    res = _run(ctx, uniq, 16, False, bg_keys, 14)
+    assert res.counts['uniform_kernel'] == 1 and (res.flags & 4).any()
+    _compare(res, uniq, 16, False, bg_keys, 14)
+    ctx.set_background(None, 0)

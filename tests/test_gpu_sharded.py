@@ -48,8 +48,12 @@ def _worker(rank, world, port, n_parts, k, internal, out_dir, mode='direct', opt
         np.cumsum([len(s) for s in seqs], out=offsets[1:])
         buf = np.frombuffer(''.join(seqs).encode(), dtype=np.uint8)
         ctx = _native.Context(rank)
-        for name, value in (opts or {}).items():
+        opts = dict(opts or {})
+        for name, value in opts.pop('_env', {}).items():      # switches of the host layer (sharded.py)
+            os.environ[name] = value
+        for name, value in opts.items():
             ctx.set_option(name, value)
+        opts = opts or None
         ops = sharded.NativeOps(ctx)
         ops.load(buf, offsets, ids)
         res = sharded.build_sharded(ops, offsets, k, internal, want_edges=True)
@@ -103,6 +107,8 @@ def _groups(res):
     (21, False, 'direct', {'no_window_carry': 1}, 0),                           # ... window index NOT carried (the 4/8-GPU layout of config 4)
     (25, False, 'direct', {'no_window_carry': 1}, 0),                           # config 5's k
     (21, False, 'direct', {'no_window_carry': 1, 'leaf_target': 20, 'nvlink_digits': 2}, 0),   # owner-only scatter, two owner levels, no window
+    (16, False, 'direct', {'_env': {'NRPCALC_B200_FLAG_CAP': '2'}}, 0),         # sparse flag lists truncated -> dense all-reduce, finish repeated
+    (17, False, 'direct', {'_env': {'NRPCALC_B200_DENSE_FLAGS': '1'}}, 0),      # dense flag all-reduce
     (13, True, 'direct', None, 300),                                            # region overflow -> counted exchange
     (13, False, 'counted', None, 0), (17, True, 'counted', None, 0), (17, False, 'nccl', None, 0)])
 def test_sharded_equals_single_gpu(tmp_path, k, internal, mode, opts, dups):
