@@ -28,6 +28,17 @@ void nrp_tail_sizes(void* handle, int64_t out[4]);
 void nrp_tail_fetch(void* handle, int64_t* nodes, int64_t* indptr, int64_t* adj, int64_t* clique_off, int64_t* clique_nodes);
 void nrp_tail_free(void* handle);
 
+/* Vertex cover 'nrp2' (mode 0, reference vercov.py:119-138) or 'nrpG' (mode 1, vercov.py:140-154) with the pendant elimination
+ * of vercov.py:47-89, on the CSR of a graph restricted to the nodes with keep[i] != 0 (n_nodes nodes in iteration order,
+ * adj_index = neighbour INDICES in adjacency order).  mt_state = the 624 words + index of the interpreter's Mersenne Twister
+ * (random.getstate()[1]); random.shuffle is replayed on it and the state is updated in place.  cover_out[i] = 1 for cover nodes.
+ * Returns 0; -1 out of memory; -2 the adjacency is not symmetric. */
+int nrp_tail_cover(const int64_t* indptr, const int32_t* adj_index, int64_t n_nodes, const uint8_t* keep, int mode, uint32_t* mt_state,
+                   uint8_t* cover_out);
+/* The lines networkx.write_adjlist emits for a graph (recovery.py:26-30), without the comment header.  Returns the bytes written,
+ * or -(bytes needed) when cap is too small. */
+int64_t nrp_tail_adjlist(const int64_t* nodes, const int64_t* indptr, const int32_t* adj_index, int64_t n_nodes, char* out, int64_t cap);
+
 /* Test hooks (tests/test_cpyset.py): hash(tuple of small ints) as CPython computes it, and a small interpreter over a pool of
  * modelled sets (rows of opcode, a, b, c -- see csrc/host_replay.cpp) whose iteration orders are compared with real sets. */
 int64_t nrp_tail_tuple_hash(const int64_t* items, int64_t len);
