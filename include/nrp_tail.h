@@ -35,6 +35,12 @@ void nrp_tail_free(void* handle);
  * Returns 0; -1 out of memory; -2 the adjacency is not symmetric. */
 int nrp_tail_cover(const int64_t* indptr, const int32_t* adj_index, int64_t n_nodes, const uint8_t* keep, int mode, uint32_t* mt_state,
                    uint8_t* cover_out);
+/* The whole independent-set recovery of reference recovery.py:32-96 around 'nrp2' / 'nrpG' (verbose off): graph 0 = the homology
+ * graph as assembled (ids0, CSR over indices into ids0), graph 1 = its dump-and-reload (nrp_tail_reload; ids1, CSR over indices
+ * into ids1).  independent_out[i] = 1 when ids1[i] is in the recovered independent set.  Returns the number of rounds (>= 1 for a
+ * non-empty graph); -1 out of memory; -2 malformed adjacency.  mt_state as in nrp_tail_cover. */
+int64_t nrp_tail_recover(const int64_t* ids0, const int64_t* indptr0, const int32_t* adj0, const int64_t* ids1, const int64_t* indptr1,
+                         const int32_t* adj1, int64_t n_nodes, int mode, uint32_t* mt_state, uint8_t* independent_out);
 /* The lines networkx.write_adjlist emits for a graph (recovery.py:26-30), without the comment header.  Returns the bytes written,
  * or -(bytes needed) when cap is too small. */
 int64_t nrp_tail_adjlist(const int64_t* nodes, const int64_t* indptr, const int32_t* adj_index, int64_t n_nodes, char* out, int64_t cap);

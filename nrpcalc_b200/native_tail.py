@@ -39,6 +39,13 @@ def _load():
         lib.nrp_tail_tuple_hash.argtypes = [ctypes.c_void_p, ctypes.c_int64]
         lib.nrp_tail_set_script.restype = ctypes.c_int64
         lib.nrp_tail_set_script.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]
+        if hasattr(lib, 'nrp_tail_cover'):
+            lib.nrp_tail_cover.restype = ctypes.c_int
+            lib.nrp_tail_cover.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+            lib.nrp_tail_recover.restype = ctypes.c_int64
+            lib.nrp_tail_recover.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+            lib.nrp_tail_adjlist.restype = ctypes.c_int64
+            lib.nrp_tail_adjlist.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]
         _lib = lib
     return _lib
 
@@ -81,6 +88,172 @@ def reload_arrays(nodes, indptr, adj):
     indptr = np.ascontiguousarray(indptr, dtype=np.int64)
     adj = np.ascontiguousarray(adj, dtype=np.int64)
     return _collect(lib, lib.nrp_tail_reload(nodes.ctypes.data, indptr.ctypes.data, adj.ctypes.data, nodes.size))
+
+
+def adjacency_indices(nodes, adj):
+    """Neighbour ids -> node indices (int32) for a graph given as (node ids in iteration order, flat adjacency of ids)."""
+    nodes = np.asarray(nodes, dtype=np.int64)
+    order = np.argsort(nodes, kind='stable')
+    return order[np.searchsorted(nodes[order], adj)].astype(np.int32)
+
+
+COVER_MODES = {'nrp2': 0, 'nrpG': 1}
+
+
+def cover_arrays(indptr, adj_index, keep, mode):
+    """'nrp2' / 'nrpG' vertex cover (reference vercov.py:119-154) of the graph restricted to the nodes with keep != 0, on arrays.
+    Consumes the module-global `random` generator exactly as the Python routines' random.shuffle calls would.
+    Returns a uint8 mask of the cover."""
+    lib = _load()
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    adj_index = np.ascontiguousarray(adj_index, dtype=np.int32)
+    keep = np.ascontiguousarray(keep, dtype=np.uint8)
+    version, words, gauss = random.getstate()
+    state = np.array(words, dtype=np.uint32)
+    cover = np.zeros(keep.size, dtype=np.uint8)
+    code = lib.nrp_tail_cover(indptr.ctypes.data, adj_index.ctypes.data, keep.size, keep.ctypes.data, COVER_MODES[mode], state.ctypes.data,
+                              cover.ctypes.data)
+    if code == -1:
+        raise MemoryError('libnrptail: out of memory')
+    if code != 0:
+        raise RuntimeError('libnrptail: cover failed ({})'.format(code))
+    random.setstate((version, tuple(int(w) for w in state), gauss))
+    return cover
+
+
+def recover_arrays(nodes, indptr, adj, mode):
+    """Independent-set recovery (reference recovery.py:32-96 around 'nrp2' / 'nrpG') of the graph given by its arrays (node ids in
+    insertion order, CSR adjacency of ids in insertion order), entirely on arrays.  Consumes the global `random` generator like the
+    Python routines.  Returns (set of independent node ids, rounds, reloaded arrays)."""
+    lib = _load()
+    nodes = np.ascontiguousarray(nodes, dtype=np.int64)
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    adj0 = adjacency_indices(nodes, adj)
+    nodes1, indptr1, adj1_ids = reload_arrays(nodes, indptr, adj)
+    adj1 = adjacency_indices(nodes1, adj1_ids)
+    version, words, gauss = random.getstate()
+    state = np.array(words, dtype=np.uint32)
+    chosen = np.zeros(nodes.size, dtype=np.uint8)
+    rounds = lib.nrp_tail_recover(nodes.ctypes.data, indptr.ctypes.data, adj0.ctypes.data, nodes1.ctypes.data, indptr1.ctypes.data,
+                                  adj1.ctypes.data, nodes.size, COVER_MODES[mode], state.ctypes.data, chosen.ctypes.data)
+    if rounds == -1:
+        raise MemoryError('libnrptail: out of memory')
+    if rounds < 0:
+        raise RuntimeError('libnrptail: recovery failed ({})'.format(rounds))
+    random.setstate((version, tuple(int(w) for w in state), gauss))
+    return set(nodes1[chosen != 0].tolist()), int(rounds), (nodes1, indptr1, adj1_ids)
+
+
+def adjlist_body(nodes, indptr, adj_index):
+    """The lines nx.write_adjlist writes for this graph (without the comment header), as bytes."""
+    lib = _load()
+    nodes = np.ascontiguousarray(nodes, dtype=np.int64)
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    adj_index = np.ascontiguousarray(adj_index, dtype=np.int32)
+    cap = int(indptr[-1]) * 12 + nodes.size * 14 + 64
+    out = np.empty(cap, dtype=np.uint8)
+    n = lib.nrp_tail_adjlist(nodes.ctypes.data, indptr.ctypes.data, adj_index.ctypes.data, nodes.size, out.ctypes.data, cap)
+    if n < 0:
+        raise MemoryError('libnrptail: adjacency list does not fit')
+    return out[:n].tobytes()
+
+
+_cover_state = {'checked': False, 'usable': False, 'why': 'not checked'}
+
+
+def _cover_self_check():
+    """Random graphs through the native routines and through vercov.py (real networkx graphs, the real random module): the
+    covers and the generator's state afterwards must be equal."""
+    from . import vercov
+    rng = random.Random(77)
+    for n, m, mode in ((60, 90, 'nrp2'), (400, 700, 'nrpG'), (3000, 4200, 'nrp2'), (3000, 2500, 'nrpG')):
+        graph = nx.Graph()
+        order = list(range(n))
+        rng.shuffle(order)
+        for u in order:
+            if rng.random() < 0.9:
+                graph.add_node(u)
+        for _ in range(m):
+            u, v = rng.randrange(n), rng.randrange(n)
+            if u != v:
+                graph.add_edge(u, v)
+        if mode == 'nrpG':                                 # a re-derived working graph, as recovery builds for later rounds
+            graph = nx.Graph(graph.subgraph([u for i, u in enumerate(graph.nodes()) if i % 7]))
+        nodes = np.fromiter(graph.nodes(), dtype=np.int64)
+        indptr = np.zeros(nodes.size + 1, dtype=np.int64)
+        np.cumsum([len(graph[u]) for u in graph.nodes()], out=indptr[1:])
+        adj = np.fromiter((v for u in graph.nodes() for v in graph[u]), dtype=np.int64, count=int(indptr[-1]))
+        keep = np.ones(nodes.size, dtype=np.uint8)
+        if n == 400:
+            keep[::5] = 0                                   # the cover of an induced subgraph
+        saved = random.getstate()
+        try:
+            random.seed(1234 + n)
+            mask = cover_arrays(indptr, adjacency_indices(nodes, adj), keep, mode)
+            state_native = random.getstate()
+            random.seed(1234 + n)
+            graph.remove_nodes_from(nodes[keep == 0].tolist())     # (Graph.copy() would re-derive the adjacency order)
+            expect = vercov.ROUTINES[mode][0](graph, False)
+            state_python = random.getstate()
+        finally:
+            random.setstate(saved)
+        if set(nodes[mask != 0].tolist()) != set(expect):
+            return False, 'cover differs ({} nodes, {})'.format(n, mode)
+        if state_native != state_python:
+            return False, 'random state differs ({} nodes, {})'.format(n, mode)
+    # the whole recovery (several rounds; working graphs re-derived from the candidate SET) against the graph-based loop
+    from . import recovery
+    import tempfile
+    scratch = tempfile.mkdtemp(prefix='nrp_tail_check_')
+    try:
+        for n, m, mode in ((300, 420, 'nrp2'), (2500, 6000, 'nrp2'), (2500, 2600, 'nrpG'), (9000, 5200, 'nrp2')):
+            graph = nx.Graph()
+            ids = rng.sample(range(4 * n), n)
+            for u in ids:
+                graph.add_node(u)
+            for _ in range(m):
+                u, v = rng.choice(ids), rng.choice(ids)
+                if u != v:
+                    graph.add_edge(u, v)
+            nodes = np.fromiter(graph.nodes(), dtype=np.int64)
+            indptr = np.zeros(nodes.size + 1, dtype=np.int64)
+            np.cumsum([len(graph[u]) for u in graph.nodes()], out=indptr[1:])
+            adj = np.fromiter((v for u in graph.nodes() for v in graph[u]), dtype=np.int64, count=int(indptr[-1]))
+            saved = random.getstate()
+            try:
+                random.seed(99 + n)
+                got, _, _ = recover_arrays(nodes, indptr, adj, mode)
+                state_native = random.getstate()
+                random.seed(99 + n)
+                expect = recovery._recover_on_graphs(graph, os.path.join(scratch, 'graph.txt'), mode, False)
+                state_python = random.getstate()
+            finally:
+                random.setstate(saved)
+            if got != expect:
+                return False, 'recovery differs ({} nodes, {})'.format(n, mode)
+            if state_native != state_python:
+                return False, 'random state after recovery differs ({} nodes, {})'.format(n, mode)
+    finally:
+        import shutil
+        shutil.rmtree(scratch, ignore_errors=True)
+    return True, 'ok'
+
+
+def cover_usable():
+    """True when libnrptail.so has the cover routines and they agree with vercov.py on this interpreter (checked once)."""
+    if not _cover_state['checked']:
+        _cover_state['checked'] = True
+        lib = _load()
+        if lib is None or not hasattr(lib, 'nrp_tail_cover'):
+            _cover_state['usable'], _cover_state['why'] = False, 'libnrptail.so without cover routines'
+        else:
+            try:
+                _cover_state['usable'], _cover_state['why'] = _cover_self_check()
+            except Exception as exc:
+                _cover_state['usable'], _cover_state['why'] = False, 'self-check raised {!r}'.format(exc)
+            if not _cover_state['usable']:
+                sys.stderr.write('nrpcalc_b200: native cover routines disabled ({}); the Python routines run\n'.format(_cover_state['why']))
+    return _cover_state['usable']
 
 
 def graph_from_arrays(nodes, indptr, adj):
@@ -174,6 +347,9 @@ def usable():
             _state['usable'], _state['why'] = _self_check()
         except Exception as exc:                           # never let the accelerator break the product
             _state['usable'], _state['why'] = False, 'self-check raised {!r}'.format(exc)
+        if not _state['usable']:                           # said once: the results stay identical, the tail is just ~3.6x slower
+            sys.stderr.write('nrpcalc_b200: the array tail (libnrptail.so) does not match this interpreter ({}); '
+                             'the Python loops run instead\n'.format(_state['why']))
         if _state['usable'] and key is not None:
             try:
                 with open(stamp, 'w') as fh:

@@ -12,6 +12,7 @@ the reloaded graph is not parsed at all: what write_adjlist + read_adjlist do to
 under its earlier endpoint; nodes and edges added line by line) is replayed on the arrays
 (native_tail.reload_arrays, checked against networkx in tests/test_host_logic.py).  The file is still written.
 """
+import os
 import sys
 from time import time
 
@@ -21,7 +22,43 @@ from . import native_tail
 from . import vercov
 
 
+def _write_adjlist_from_arrays(arrays, graph_file):
+    """What nx.write_adjlist(graph, graph_file) writes (header of three comment lines, then one line per node), from the arrays."""
+    import time as _time
+    nodes, indptr, adj = arrays
+    header = '#' + ' '.join(sys.argv) + '\n' + '# GMT {}\n'.format(_time.asctime(_time.gmtime())) + '# \n'
+    body = native_tail.adjlist_body(nodes, indptr, native_tail.adjacency_indices(nodes, adj))
+    with open(graph_file, 'wb') as out:
+        out.write(header.encode('utf-8'))
+        out.write(body)
+
+
+def recover_from_arrays(arrays, graph_file, vercov_func):
+    """The whole recovery on the arrays of the assembled graph (libnrptail.so: cover routines, candidate sets and working graphs of
+    every round modelled exactly -- host_cover.cpp); the adjacency-list side file is still written.  'nrp2' / 'nrpG' only."""
+    nodes = arrays[0]
+    if nodes.size == 0:
+        return set()
+    _write_adjlist_from_arrays(arrays, graph_file)
+    mode = vercov_func if vercov_func in native_tail.COVER_MODES else 'nrp2'       # unknown names fall through to 'nrp2' (recovery.py:18-24)
+    chosen, _, _ = native_tail.recover_arrays(arrays[0], arrays[1], arrays[2], mode)
+    return chosen
+
+
+def native_recovery_applies(arrays, vercov_func, verbose):
+    return (arrays is not None and not verbose and vercov_func != '2apx' and not os.environ.get('NRPCALC_B200_PYTHON_RECOVERY')
+            and native_tail.usable() and native_tail.cover_usable())
+
+
 def get_recovered_non_homologs(homology_graph, graph_file, vercov_func=None, verbose=True):
+    arrays = getattr(homology_graph, '_nrp_arrays', None)
+    if (arrays is not None and arrays[0].size == homology_graph.number_of_nodes() and arrays[2].size == 2 * homology_graph.number_of_edges()
+            and native_recovery_applies(arrays, vercov_func, verbose)):
+        return recover_from_arrays(arrays, graph_file, vercov_func)
+    return _recover_on_graphs(homology_graph, graph_file, vercov_func, verbose)
+
+
+def _recover_on_graphs(homology_graph, graph_file, vercov_func=None, verbose=True):
     independent = set()
     candidates = set(homology_graph.nodes())
     arrays = getattr(homology_graph, '_nrp_arrays', None)             # taken now: the cover routine empties the graph

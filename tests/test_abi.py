@@ -62,7 +62,7 @@ def test_tail_library_exports_every_declared_symbol():
     text = open(os.path.join(ROOT, 'include', 'nrp_tail.h')).read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
     names = sorted(set(re.findall(r'\b(nrp_tail_[a-z_0-9]+)\s*\(', text)))
-    assert len(names) == 7
+    assert len(names) == 10
     lib = ctypes.CDLL(native_tail.LIB_PATH)
     for name in names:
         assert hasattr(lib, name), name

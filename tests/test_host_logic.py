@@ -6,6 +6,7 @@ import os
 import random
 
 import networkx as nx
+import numpy as np
 import pytest
 
 import fake_device
@@ -172,15 +173,17 @@ def test_recovery_against_live_reference(mode, scratch_cwd):
         theirs_graph = ref_hgraph.get_homology_graph(list(parts), None, k, True, './seq_ref.txt', False)
         mine_graph = hgraph.get_homology_graph(list(parts), None, k, True, './seq_mine.txt', False)
         assert [list(theirs_graph[n]) for n in theirs_graph.nodes()] == [list(mine_graph[n]) for n in mine_graph.nodes()]
-        random.seed(11 + seed)
-        theirs = ref_recovery.get_recovered_non_homologs(theirs_graph, './graph_ref.txt', mode, False)
-        nx.Graph.subgraph = counting_subgraph
+        nx.Graph.subgraph = counting_subgraph                   # rounds past the first one, counted on the reference's side
         try:
             random.seed(11 + seed)
-            mine = recovery.get_recovered_non_homologs(mine_graph, './graph_mine.txt', mode, False)
+            theirs = ref_recovery.get_recovered_non_homologs(theirs_graph, './graph_ref.txt', mode, False)
         finally:
             nx.Graph.subgraph = real_subgraph
+        state_theirs = random.getstate()
+        random.seed(11 + seed)
+        mine = recovery.get_recovered_non_homologs(mine_graph, './graph_mine.txt', mode, False)      # on arrays for nrp2 / nrpG
         assert mine == theirs and len(mine) > 0
+        assert random.getstate() == state_theirs                # the generator was consumed exactly as by the reference
         body = lambda path: [line for line in open(path).read().splitlines() if not line.startswith('#')]   # header = time stamp
         assert body('./graph_ref.txt') == body('./graph_mine.txt')
     assert len(rounds) >= 2                                      # at least one case went past the first reload
@@ -333,3 +336,73 @@ def test_patch_runs_the_reference_finder_on_our_graph_build(scratch_cwd):
     finally:
         nrpcalc_b200.unpatch()
     assert ref_hgraph.get_homology_graph is original
+
+
+def test_native_recovery_equals_graph_based_recovery(tmp_path):
+    """libnrptail's recovery on arrays (cover routines with the interpreter's Mersenne Twister state, candidate sets and working
+    graphs of every round modelled slot for slot) against the graph-based loop on random graphs of several densities: same
+    independent set, same random state afterwards; some cases take several rounds, with the working graph ordered by the candidate
+    set (2 * |candidates| < |graph|) and by the graph."""
+    from nrpcalc_b200 import native_tail
+    if not (native_tail.usable() and native_tail.cover_usable()):
+        pytest.skip('libnrptail.so not built')
+    rng = random.Random(5)
+    rounds_seen, shapes = [], set()
+    for case in range(80):
+        n = rng.choice((40, 300, 2000, 6000))
+        m = int(n * rng.choice((0.3, 0.6, 1.0, 1.5, 3.0, 6.0, 12.0)))
+        mode = rng.choice(('nrp2', 'nrpG'))
+        graph = nx.Graph()
+        ids = rng.sample(range(3 * n), n)
+        for u in ids:
+            if rng.random() < 0.95:
+                graph.add_node(u)
+        for _ in range(m):
+            u, v = rng.choice(ids), rng.choice(ids)
+            if u != v:
+                graph.add_edge(u, v)
+        for _ in range(n // 50):                                    # a few hubs: long tie lists for the shuffles
+            hub = rng.choice(ids)
+            for v in rng.sample(ids, min(12, n)):
+                if v != hub:
+                    graph.add_edge(hub, v)
+        nodes = np.fromiter(graph.nodes(), dtype=np.int64)
+        indptr = np.zeros(nodes.size + 1, dtype=np.int64)
+        np.cumsum([len(graph[u]) for u in graph.nodes()], out=indptr[1:])
+        adj = np.fromiter((v for u in graph.nodes() for v in graph[u]), dtype=np.int64, count=int(indptr[-1]))
+        random.seed(case)
+        got, rounds, _ = native_tail.recover_arrays(nodes, indptr, adj, mode)
+        state_native = random.getstate()
+        random.seed(case)
+        expect = recovery._recover_on_graphs(graph, str(tmp_path / 'g.txt'), mode, False)
+        assert got == expect, (case, n, m, mode)
+        assert random.getstate() == state_native, (case, n, m, mode)
+        rounds_seen.append(rounds)
+        shapes.add((n, mode))
+    assert sum(1 for r in rounds_seen if r >= 2) >= 10 and len(shapes) >= 6, rounds_seen      # rounds >= 2: a re-derived working graph
+
+
+def test_adjlist_file_from_arrays_equals_networkx(tmp_path):
+    from nrpcalc_b200 import native_tail
+    if not native_tail.usable():
+        pytest.skip('libnrptail.so not built')
+    rng = random.Random(9)
+    graph = nx.Graph()
+    for u in rng.sample(range(5000), 1500):
+        graph.add_node(u)
+    ids = list(graph.nodes())
+    for _ in range(2600):
+        u, v = rng.choice(ids), rng.choice(ids)
+        if u != v:
+            graph.add_edge(u, v)
+    nodes = np.fromiter(graph.nodes(), dtype=np.int64)
+    indptr = np.zeros(nodes.size + 1, dtype=np.int64)
+    np.cumsum([len(graph[u]) for u in graph.nodes()], out=indptr[1:])
+    adj = np.fromiter((v for u in graph.nodes() for v in graph[u]), dtype=np.int64, count=int(indptr[-1]))
+    nx.write_adjlist(graph, str(tmp_path / 'nx.txt'))
+    recovery._write_adjlist_from_arrays((nodes, indptr, adj), str(tmp_path / 'mine.txt'))
+    body = lambda path: [line for line in open(path).read().splitlines() if not line.startswith('#')]
+    assert body(str(tmp_path / 'mine.txt')) == body(str(tmp_path / 'nx.txt'))
+    assert len(open(str(tmp_path / 'mine.txt')).read().splitlines()) == len(open(str(tmp_path / 'nx.txt')).read().splitlines())
+    reread = nx.read_adjlist(str(tmp_path / 'mine.txt'), nodetype=int)
+    assert sorted(reread.edges()) == sorted(tuple(sorted(e)) for e in graph.edges()) or set(map(frozenset, reread.edges())) == set(map(frozenset, graph.edges()))
