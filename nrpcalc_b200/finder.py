@@ -77,9 +77,18 @@ def nrp_finder(seq_list, homology, allow_internal_repeat=False, background=None,
     with scratch:
         seq_file, graph_file = scratch.file('seq_list.txt'), scratch.file('repeat_graph.txt')
         t0 = time.perf_counter()
-        graph = hgraph.get_homology_graph(seq_list, background, homology, allow_internal_repeat, seq_file, verbose)
-        t1 = time.perf_counter()
-        chosen = recovery.get_recovered_non_homologs(graph, graph_file, vercov_func, verbose)
+        graph = None
+        if recovery.native_recovery_applies((), vercov_func, verbose):
+            # quiet run with 'nrp2' / 'nrpG': graph and recovery stay on arrays (same result; no nx.Graph object is built)
+            graph = hgraph.get_homology_arrays(seq_list, background, homology, allow_internal_repeat, seq_file)
+        if isinstance(graph, tuple):
+            t1 = time.perf_counter()
+            chosen = recovery.recover_from_arrays(graph, graph_file, vercov_func)
+        else:
+            if graph is None:
+                graph = hgraph.get_homology_graph(seq_list, background, homology, allow_internal_repeat, seq_file, verbose)
+            t1 = time.perf_counter()
+            chosen = recovery.get_recovered_non_homologs(graph, graph_file, vercov_func, verbose)
         t2 = time.perf_counter()
         # the unique parts in processing order: what seq_list.txt holds (the reference re-reads the file, finder.py:175-181)
         ordered = hgraph.last_build_info.get('parts')

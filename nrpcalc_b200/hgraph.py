@@ -405,7 +405,8 @@ def _build_homology_graph_api(cliques, verbose):
 last_build_info = {}
 
 
-def get_homology_graph(seq_list, background, homology, internal_repeats, seq_file, verbose):
+def _build_structure(seq_list, background, homology, internal_repeats, seq_file, verbose):
+    """hgraph.py:209-233 up to the table: uniquify, side file, device build.  Returns (parts, structure, ids, seconds of the call)."""
     t0 = time()
     num_seqs = len(seq_list)
     parts = uniquify_seq_list(seq_list)
@@ -425,15 +426,41 @@ def get_homology_graph(seq_list, background, homology, internal_repeats, seq_fil
     if verbose:
         print(' [Sequence processing remaining] = 0  (GPU: {} k-mers in {:.3f} ms on device)'.format(
             structure.records, structure.timings['total']))
-    graph = assemble_graph(structure, ids, verbose)
+    return parts, structure, ids, t_device
+
+
+def _record_build(parts, structure, t_device, t_replay, native):
     last_build_info.clear()
     last_build_info.update({'records': structure.records, 'device_ms': structure.timings['total'], 'call_s': t_device,
                             'timings': dict(structure.timings), 'counts': dict(structure.counts),
-                            'replay_s': time() - t0 - t_device, 'parts': parts,
-                            'native_tail': getattr(graph, '_nrp_arrays', None) is not None})
+                            'replay_s': t_replay, 'parts': parts, 'native_tail': native})
+
+
+def get_homology_graph(seq_list, background, homology, internal_repeats, seq_file, verbose):
+    parts, structure, ids, t_device = _build_structure(seq_list, background, homology, internal_repeats, seq_file, verbose)
+    t0 = time()
+    graph = assemble_graph(structure, ids, verbose)
+    _record_build(parts, structure, t_device, time() - t0, getattr(graph, '_nrp_arrays', None) is not None)
     if verbose:
         print('\nBuilt homology graph in {:2.4} seconds. [Edges = {}] [Nodes = {}]'.format(
-            time() - t0, graph.number_of_edges(), graph.number_of_nodes()))
+            time() - t0 + t_device, graph.number_of_edges(), graph.number_of_nodes()))
         print(' [Intital Nodes = {}] - [Repetitive Nodes = {}] = [Final Nodes = {}]'.format(
-            unq_seqs, unq_seqs - graph.number_of_nodes(), graph.number_of_nodes()))
+            len(parts), len(parts) - graph.number_of_nodes(), graph.number_of_nodes()))
     return graph
+
+
+def get_homology_arrays(seq_list, background, homology, internal_repeats, seq_file):
+    """The same graph as get_homology_graph, as arrays only: (node ids in insertion order, CSR offsets, neighbour ids in insertion
+    order) -- for callers that go on with the array recovery (recovery.recover_from_arrays) and never need the nx.Graph object,
+    whose millions of small dicts cost more than the whole tail.  None when the array tail is not usable."""
+    if not native_tail.usable():
+        return None
+    parts, structure, ids, t_device = _build_structure(seq_list, background, homology, internal_repeats, seq_file, False)
+    t0 = time()
+    try:
+        nodes, indptr, adj = native_tail.run(*ordered_stream_arrays(structure, ids))
+    except MemoryError:
+        _record_build(parts, structure, t_device, time() - t0, False)
+        return assemble_graph(structure, ids, False)               # the caller checks the type
+    _record_build(parts, structure, t_device, time() - t0, True)
+    return nodes, indptr, adj

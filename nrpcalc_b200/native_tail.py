@@ -93,6 +93,10 @@ def reload_arrays(nodes, indptr, adj):
 def adjacency_indices(nodes, adj):
     """Neighbour ids -> node indices (int32) for a graph given as (node ids in iteration order, flat adjacency of ids)."""
     nodes = np.asarray(nodes, dtype=np.int64)
+    if nodes.size and int(nodes.max()) <= 16 * nodes.size + (1 << 20):      # ids are first indices in the caller's list: a flat table
+        table = np.zeros(int(nodes.max()) + 1, dtype=np.int32)
+        table[nodes] = np.arange(nodes.size, dtype=np.int32)
+        return table[adj]
     order = np.argsort(nodes, kind='stable')
     return order[np.searchsorted(nodes[order], adj)].astype(np.int32)
 
@@ -121,14 +125,16 @@ def cover_arrays(indptr, adj_index, keep, mode):
     return cover
 
 
-def recover_arrays(nodes, indptr, adj, mode):
+def recover_arrays(nodes, indptr, adj, mode, adj0=None):
     """Independent-set recovery (reference recovery.py:32-96 around 'nrp2' / 'nrpG') of the graph given by its arrays (node ids in
     insertion order, CSR adjacency of ids in insertion order), entirely on arrays.  Consumes the global `random` generator like the
     Python routines.  Returns (set of independent node ids, rounds, reloaded arrays)."""
     lib = _load()
     nodes = np.ascontiguousarray(nodes, dtype=np.int64)
     indptr = np.ascontiguousarray(indptr, dtype=np.int64)
-    adj0 = adjacency_indices(nodes, adj)
+    if adj0 is None:
+        adj0 = adjacency_indices(nodes, adj)
+    adj0 = np.ascontiguousarray(adj0, dtype=np.int32)
     nodes1, indptr1, adj1_ids = reload_arrays(nodes, indptr, adj)
     adj1 = adjacency_indices(nodes1, adj1_ids)
     version, words, gauss = random.getstate()

@@ -22,12 +22,12 @@ from . import native_tail
 from . import vercov
 
 
-def _write_adjlist_from_arrays(arrays, graph_file):
+def _write_adjlist_from_arrays(arrays, graph_file, adj_index=None):
     """What nx.write_adjlist(graph, graph_file) writes (header of three comment lines, then one line per node), from the arrays."""
     import time as _time
     nodes, indptr, adj = arrays
     header = '#' + ' '.join(sys.argv) + '\n' + '# GMT {}\n'.format(_time.asctime(_time.gmtime())) + '# \n'
-    body = native_tail.adjlist_body(nodes, indptr, native_tail.adjacency_indices(nodes, adj))
+    body = native_tail.adjlist_body(nodes, indptr, native_tail.adjacency_indices(nodes, adj) if adj_index is None else adj_index)
     with open(graph_file, 'wb') as out:
         out.write(header.encode('utf-8'))
         out.write(body)
@@ -39,9 +39,10 @@ def recover_from_arrays(arrays, graph_file, vercov_func):
     nodes = arrays[0]
     if nodes.size == 0:
         return set()
-    _write_adjlist_from_arrays(arrays, graph_file)
+    adj0 = native_tail.adjacency_indices(arrays[0], arrays[2])
+    _write_adjlist_from_arrays(arrays, graph_file, adj0)
     mode = vercov_func if vercov_func in native_tail.COVER_MODES else 'nrp2'       # unknown names fall through to 'nrp2' (recovery.py:18-24)
-    chosen, _, _ = native_tail.recover_arrays(arrays[0], arrays[1], arrays[2], mode)
+    chosen, _, _ = native_tail.recover_arrays(arrays[0], arrays[1], arrays[2], mode, adj0=adj0)
     return chosen
 
 

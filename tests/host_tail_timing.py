@@ -49,7 +49,8 @@ def main():
     hgraph.repeat_structure = device_stand_in
     for module, name in ((hgraph, 'repeat_structure'), (hgraph, 'uniquify_seq_list'), (hgraph, 'assemble_graph'),
                          (recovery, 'get_recovered_non_homologs'), (nx, 'write_adjlist'), (native_tail, 'graph_from_arrays'),
-                         (native_tail, 'run'), (native_tail, 'reload_arrays')):
+                         (native_tail, 'run'), (native_tail, 'reload_arrays'), (native_tail, 'recover_arrays'),
+                         (recovery, 'recover_from_arrays'), (recovery, '_write_adjlist_from_arrays'), (native_tail, 'adjacency_indices')):
         timed(module, name)
     routine, label = vercov.ROUTINES['nrp2']
 
