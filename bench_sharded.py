@@ -81,7 +81,8 @@ def main(args, cfg, rank, world, local_rank):
     uniform = not isinstance(cfg['length'], tuple)
     host_ids = torch.from_numpy(ids.copy()).pin_memory()
     e2e, e2e_load = [], []
-    for _ in range(2 + max(2, args.steps // 2)):
+    e2e_phase = {}
+    for it in range(2 + max(2, args.steps // 2)):
         flush.fill_(1)
         torch.cuda.synchronize()
         dist.barrier()
@@ -91,7 +92,7 @@ def main(args, cfg, rank, world, local_rank):
         else:
             ops.load_shard(host_ascii.numpy(), off, host_ids.numpy(), k)
         t1 = time.perf_counter()
-        res = step(gather_host=True)
+        res = step(e2e_phase if it >= 2 else None, gather_host=True)
         dt = torch.tensor([(time.perf_counter() - t0) * 1e3, (t1 - t0) * 1e3], device='cuda')
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e.append(float(dt[0].item())); e2e_load.append(float(dt[1].item()))
@@ -132,6 +133,7 @@ def main(args, cfg, rank, world, local_rank):
                         'd2h_bytes_per_step': int(world * (res['flags'].nbytes + res['members'].nbytes + res['first_window'].nbytes + res['keys'].nbytes +
                                                            res['indptr'].nbytes + res['last_single'].nbytes + (res['edges'][0].nbytes * 2 if res['edges'] else 0))),
                         'ms_per_step': float(np.mean(e2e)), 'ms_load': float(np.mean(e2e_load)), 'h2d_bytes_this_rank': shard_bytes + int(ids.nbytes),
+                        'phase_ms_rank0': {name: v / max(1, len(e2e)) for name, v in e2e_phase.items()},
                         'path': 'per rank: nrp_load_parts_shard (page-locked host buffer, ONLY the rank\'s shard of the parts travels; ids in full) + sharded build + NCCL all-gather of the result arrays + one D2H copy'},
                 'gpu_launches': int(launches.item()),
                 'clocks': clocks,

@@ -459,8 +459,11 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
         flags_all = _or_reduce_flags(ops, ops.flags(), group)
         ops.set_flags(flags_all)
     flags_host = (ops.to_host(flags_all) if hasattr(ops, 'to_host') else flags_all.cpu().numpy()) if n else np.zeros(0, dtype=np.uint8)
-    # records of parts flagged for an internal repeat were exchanged before the flag was known (single path: same)
-    stats['records'] = int(per_rank[:, 1].sum()) - int(windows[(flags_host & 1) != 0].sum())
+    # records of parts flagged for an internal repeat were exchanged before the flag was known (single path: same); the few
+    # flagged parts are picked out on the device
+    repeated = torch.nonzero(flags_all & 1).reshape(-1).cpu().numpy() if n else np.zeros(0, dtype=np.int64)
+    stats['records'] = int(per_rank[:, 1].sum()) - int(windows[repeated].sum())
+    phases.mark('host_flags')
 
     if hasattr(ops, 'gather_results'):
         result = ops.gather_results(group, lo, hi, n, want_edges)
