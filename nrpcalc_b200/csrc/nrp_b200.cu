@@ -149,6 +149,7 @@ struct nrp_ctx {
   int64_t opt_filter_tiny = 0;            // packed leaves that average <= 1400 records: four 256-thread filter CTAs per SM (pair with leaf_target <= 1400)
   int64_t opt_coop_group = 1;             // grouping stage as one cooperative kernel: 1 = up to 2^20 candidates (measured: no faster than
                                           // the kernel sequence at 8e5 candidates, slower at 2e7), 2 = always, 0 = never
+  int64_t opt_group_walk = 1;             // grouping with two grid barriers (run heads walk their runs) instead of nine; falls back on long runs
   int64_t opt_packed = 1;                 // one 64-bit word per record on the direct path whenever key and value fit
   int64_t opt_direct = 1;                 // fixed-region partition without a histogram pass (falls back to the exact path on overflow)
   int64_t opt_filter_wide = 1;            // packed leaves of <= 4096 records: three 256-thread CTAs per SM with 16 records per thread (half the
@@ -174,6 +175,8 @@ struct nrp_ctx {
   bool flags_set = false;                    // the flag pass of the current job ran a kernel (some flag byte may be non-zero)
   int coop_blocks_per_sm[2] = {0, 0};
   bool group_counts_coop = false;
+  bool group_walk_gave_up = false;           // the walk variant met a run longer than kGroupWalkMax: this job repeats the stage without it
+  bool cand_compacted = false;               // the grouping stage left the candidate list without the records of flagged parts
   // streamed staging: the ASCII copy is in flight on copy_stream in pieces (contiguous part ranges); pending_chunks > 0 until a
   // build (or any other consumer) has waited for them
   struct Chunk { int64_t part_lo, part_hi, tile_lo, n_tiles; cudaEvent_t landed; };
@@ -404,6 +407,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "nvlink_digits") c->opt_nvlink_digits = value <= 0 ? 128 : value;
   else if (n == "filter_tiny") c->opt_filter_tiny = value > 0 ? 1 : 0;
   else if (n == "coop_group") c->opt_coop_group = value < 0 ? 1 : std::min<int64_t>(value, 2);
+  else if (n == "group_walk") c->opt_group_walk = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "packed") c->opt_packed = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "direct") c->opt_direct = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "filter_wide") c->opt_filter_wide = value < 0 ? 1 : (value > 0 ? 1 : 0);
@@ -1236,7 +1240,10 @@ int stage_groups(nrp_ctx* c, bool drop_flagged, StageTimer& tm) {
     TRY(c->mem_cnt.ensure(4 * (size_t)(n_tiles + 2)));
     int& per_sm = c->coop_blocks_per_sm[sizeof(KeyT) == 4 ? 0 : 1];
     if (per_sm == 0) {
+      int per_sm_walk = 0;
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_group_coop<KeyT>, kScanThreads, 0));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_walk, k_group_walk<KeyT>, kScanThreads, 0));
+      per_sm = std::min(per_sm, per_sm_walk);          // one grid size for both cooperative variants
       if (per_sm < 1) return fail(NRP_E_CUDA, "cooperative grouping kernel does not fit an SM");
     }
     GroupCoopArgs a;
@@ -1253,14 +1260,27 @@ int stage_groups(nrp_ctx* c, bool drop_flagged, StageTimer& tm) {
     const unsigned cgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)per_sm * c->n_sms));
     void* args[] = {&a};
     ++launch_counter(); ++launch_total();
-    CU(cudaLaunchCooperativeKernel((void*)k_group_coop<KeyT>, dim3(cgrid), dim3(kScanThreads), args, 0, st));
-    if (drop_flagged) { std::swap(c->cand_keys, c->spare_keys); std::swap(c->cand_vals, c->spare_vals); }
+    c->h_counters[55] = 0;
+    if (c->opt_group_walk && !c->group_walk_gave_up) {
+      // two grid barriers: the run heads walk their runs on the uncompacted list (nothing is swapped); a run longer than
+      // kGroupWalkMax raises counts[5] and the caller repeats the stage with the nine-barrier kernel (group_stage_retry)
+      CU(cudaMemsetAsync(cnt + CNT_GROUP, 0, 6 * 8, st));
+      CU(cudaLaunchCooperativeKernel((void*)k_group_walk<KeyT>, dim3(cgrid), dim3(kScanThreads), args, 0, st));
+      CU(cudaMemcpyAsync(c->h_counters + 55, cnt + CNT_GROUP + 5, 8, cudaMemcpyDeviceToHost, st));
+      c->cand_compacted = false;
+    } else {
+      CU(cudaLaunchCooperativeKernel((void*)k_group_coop<KeyT>, dim3(cgrid), dim3(kScanThreads), args, 0, st));
+      if (drop_flagged) { std::swap(c->cand_keys, c->spare_keys); std::swap(c->cand_vals, c->spare_vals); }
+      c->cand_compacted = drop_flagged;
+    }
     CU(cudaMemcpyAsync(c->h_counters + 18, cnt + CNT_REPEAT, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(c->h_counters + 50, cnt + CNT_GROUP, 5 * 8, cudaMemcpyDeviceToHost, st));
     c->group_counts_coop = true;
     return NRP_OK;
   }
   c->group_counts_coop = false;
+  c->h_counters[55] = 0;
+  c->cand_compacted = drop_flagged;
   uint32_t* n_sorted_dev = reinterpret_cast<uint32_t*>(cnt + CNT_NSORTED);
   const unsigned grid = grid_for(n_max + 1, 256);
   if (drop_flagged) {
@@ -1306,6 +1326,12 @@ int stage_groups(nrp_ctx* c, bool drop_flagged, StageTimer& tm) {
   CU(cudaMemcpyAsync(c->h_counters + 21, c->mem_scan.as<unsigned long long>() + n_max, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(c->h_counters + 22, c->pair_scan.as<unsigned long long>() + n_max, 8, cudaMemcpyDeviceToHost, st));
   return NRP_OK;
+}
+
+// after a synchronisation that follows stage_groups: true when the walk variant gave up and the stage has to be repeated
+bool group_stage_retry(nrp_ctx* c) {
+  if (c->group_counts_coop && c->n_cand > 0 && c->h_counters[55] != 0) { c->group_walk_gave_up = true; return true; }
+  return false;
 }
 
 // after a synchronisation that follows stage_groups
@@ -1483,6 +1509,11 @@ int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   TRY((stage_groups<KeyT>(c, !internal_repeats, tm)));
   TRY(finish_counts_enqueue(c, tm));
   CU(cudaStreamSynchronize(c->stream));               // the one host round trip of the grouping: all counts at once
+  if (group_stage_retry(c)) {                         // a very long key run: the nine-barrier kernel
+    TRY((stage_groups<KeyT>(c, !internal_repeats, tm)));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  c->group_walk_gave_up = false;
   group_counts_ready(c);
   finish_counts_ready(c);
   TRY(stage_first_window(c, k, tm));
@@ -1553,11 +1584,16 @@ int shard_finish_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   StageTimer tm(c);
   TRY((stage_groups<KeyT>(c, !internal_repeats, tm)));     // flags may come from other ranks: always filter
   CU(cudaStreamSynchronize(c->stream));
+  if (group_stage_retry(c)) {
+    TRY((stage_groups<KeyT>(c, !internal_repeats, tm)));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  c->group_walk_gave_up = false;
   group_counts_ready(c);
   TRY(stage_first_window(c, k, tm));
   if (want_edges) { c->counts[NRP_C_EDGES] = 0; TRY(stage_edges(c, tm)); }
   tm.finish(c->timings);
-  c->n_cand = c->n_sorted;          // the candidate list now holds the kept records only (a repeated finish starts from them)
+  if (c->cand_compacted) c->n_cand = c->n_sorted;   // the list now holds the kept records only (a repeated finish starts from them)
   c->have_result = true;
   return NRP_OK;
 }

@@ -441,6 +441,121 @@ __global__ void __launch_bounds__(kScanThreads) k_group_coop(GroupCoopArgs a) {
   }
 }
 
+// ---- the grouping stage with TWO grid barriers ("walk" variant) ---------------------------------------------------
+// Same results as k_group_coop.  The records of flagged parts are not compacted away: a key run of the ordered candidate list is
+// contiguous with or without them, so the thread that holds a run's first record WALKS the run (two records on average),
+// counts the records that stay, and contributes (group?, members, pairs) to ONE set of prefix sums over the record slots; after
+// the scan of the tile totals the same threads walk their runs again and write groups and members.  A walk longer than
+// kGroupWalkMax gives up and raises a flag: the host then runs k_group_coop (pathological inputs: one k-mer shared by
+// thousands of records).  counts: [0] records kept [1] key runs with a kept record [2] groups [3] members [4] pairs [5] gave up.
+constexpr int kGroupWalkMax = 256;
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kScanThreads) k_group_walk(GroupCoopArgs a) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint32_t ws32[33];
+  __shared__ unsigned long long ws64[33];
+  const int64_t n = a.n;
+  const int64_t n_tiles = (n + kScanTile - 1) / kScanTile;
+  const KeyT* K = reinterpret_cast<const KeyT*>(a.keys);
+  const uint32_t* V = a.vals;
+  const bool drop = a.drop_flagged != 0;
+  auto kept = [&](int64_t idx) -> bool { return !drop || !(a.flags[V[idx] >> a.j_bits] & kFlagRepeat); };
+  unsigned long long my_kept = 0, my_runs = 0;
+  // pass 1: per run head its kept size; tile-local exclusive scans of (group?, members, pairs) over the record slots
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t base = t * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems]; unsigned long long m[kScanItems], p[kScanItems];
+    uint32_t sv = 0; unsigned long long sm = 0, sp = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+      const int64_t idx = base + i;
+      v[i] = 0; m[i] = 0; p[i] = 0;
+      if (idx < n && (idx == 0 || K[idx] != K[idx - 1])) {
+        const KeyT key = K[idx];
+        uint32_t size = 0;
+        int64_t j = idx;
+        for (; j < n && K[j] == key; ++j) {
+          if (j - idx >= kGroupWalkMax) { a.counts[5] = 1ull; break; }
+          size += kept(j) ? 1u : 0u;
+        }
+        my_kept += size;
+        my_runs += size ? 1u : 0u;
+        if (size >= 2) { v[i] = 1u; m[i] = size; p[i] = (unsigned long long)size * (size - 1) / 2; }
+      }
+      sv += v[i]; sm += m[i]; sp += p[i];
+    }
+    uint32_t tv; unsigned long long tm, tp;
+    uint32_t rv = block_exclusive_scan<uint32_t>(sv, ws32, tv);
+    unsigned long long rm = block_exclusive_scan<unsigned long long>(sm, ws64, tm);
+    unsigned long long rp = block_exclusive_scan<unsigned long long>(sp, ws64, tp);
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+      const int64_t idx = base + i;
+      if (idx < n && v[i]) { a.valid_scan[idx] = rv; a.mem_scan[idx] = rm; a.pair_scan[idx] = rp; }
+      if (idx < n) a.valid[idx] = v[i];
+      rv += v[i]; rm += m[i]; rp += p[i];
+    }
+    if (threadIdx.x == 0) a.tile_tot[t] = GroupTotals{tv, tm, tp};
+  }
+  // the two plain totals: one atomic per warp
+  for (int d = 16; d > 0; d >>= 1) { my_kept += __shfl_down_sync(0xffffffffu, my_kept, d); my_runs += __shfl_down_sync(0xffffffffu, my_runs, d); }
+  if ((threadIdx.x & 31) == 0) { if (my_kept) atomicAdd(&a.counts[0], my_kept); if (my_runs) atomicAdd(&a.counts[1], my_runs); }
+  grid.sync();
+  if (blockIdx.x == 0) {
+    const int64_t per = (n_tiles + blockDim.x - 1) / blockDim.x;
+    const int64_t t0 = (int64_t)threadIdx.x * per, t1 = t0 + per < n_tiles ? t0 + per : n_tiles;
+    uint32_t sv = 0; unsigned long long sm = 0, sp = 0;
+    for (int64_t t = t0; t < t1; ++t) { sv += a.tile_tot[t].valid; sm += a.tile_tot[t].members; sp += a.tile_tot[t].pairs; }
+    uint32_t tv; unsigned long long tm, tp;
+    uint32_t rv = block_exclusive_scan<uint32_t>(sv, ws32, tv);
+    unsigned long long rm = block_exclusive_scan<unsigned long long>(sm, ws64, tm);
+    unsigned long long rp = block_exclusive_scan<unsigned long long>(sp, ws64, tp);
+    for (int64_t t = t0; t < t1; ++t) {
+      const GroupTotals cur = a.tile_tot[t];
+      a.tile_tot[t] = GroupTotals{rv, rm, rp};
+      rv += cur.valid; rm += cur.members; rp += cur.pairs;
+    }
+    if (threadIdx.x == 0) {
+      a.counts[2] = tv; a.counts[3] = tm; a.counts[4] = tp;
+      a.out_indptr[tv] = (int64_t)tm;
+      a.out_pair_off[tv] = tp;
+    }
+  }
+  grid.sync();
+  // pass 2: the run heads write their groups and members
+  const uint32_t j_mask = a.j_bits ? ((1u << a.j_bits) - 1u) : 0u;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const GroupTotals off = a.tile_tot[t];
+    const int64_t base = t * kScanTile + (int64_t)threadIdx.x * kScanItems;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+      const int64_t idx = base + i;
+      if (idx >= n || !a.valid[idx]) continue;
+      const uint32_t o = off.valid + a.valid_scan[idx];
+      const unsigned long long gbase = off.members + a.mem_scan[idx];
+      const KeyT key = K[idx];
+      unsigned long long pos = gbase;
+      bool first = true;
+      int64_t j = idx;
+      for (; j < n && K[j] == key; ++j) {
+        if (!kept(j)) continue;
+        if (first) {                                   // the first kept record is (first part, first window)
+          a.out_keys[o] = (uint64_t)key;
+          if (a.j_bits) a.out_first_window[o] = V[j] & j_mask;
+          first = false;
+        }
+        a.out_members[pos++] = V[j] >> a.j_bits;
+      }
+      const uint32_t end = (uint32_t)pos;
+      for (unsigned long long q = gbase; q < pos; ++q) a.out_member_end[q] = end;
+      a.out_indptr[o] = (int64_t)gbase;
+      a.out_pair_off[o] = off.pairs + a.pair_scan[idx];
+    }
+  }
+}
+
 // ---- order information for the host replay ----------------------------------------------------
 // canonical k-mer of window j of a part, straight from the ASCII buffer (only used on the few shared keys)
 __device__ __forceinline__ uint64_t window_from_ascii(const uint8_t* seq, int k) {

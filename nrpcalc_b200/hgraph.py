@@ -114,7 +114,7 @@ def _device_build(ctx, structure, ascii_buf, offsets, global_p, ids, k, internal
         structure.counts['groups'] += indptr.size - 1
         structure.counts['members'] += members.size
         structure.counts['runs'] = max(structure.counts['runs'], 1)
-        structure.edges = out['edges']
+        structure.edges = None if out['edges'] is None else tuple(e.copy() for e in out['edges'])     # views of staging buffers
     else:
         ctx.load_parts(ascii_buf, offsets, ids if want_edges else None)
         ctx.build(k, internal_repeats, want_edges=want_edges)

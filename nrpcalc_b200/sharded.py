@@ -242,22 +242,30 @@ class NativeOps(object):
         torch.cuda.current_stream(self.device).synchronize()
         self.ctx.edges_merge(codes.data_ptr() if codes.numel() else 0, 0, codes.numel())
 
-    def to_host(self, tensor):
-        """Device tensor -> numpy through a cached page-locked staging buffer (a pageable .cpu() runs at a fraction of PCIe speed)."""
+    def to_host(self, tensor, pool='default'):
+        """Device tensor -> numpy VIEW of a cached page-locked staging buffer (a pageable .cpu() runs at a fraction of PCIe speed;
+        a second copy out of the staging buffer would cost as much again).  One buffer per `pool` name; the view is valid until the
+        next call with the same name."""
         nbytes = tensor.numel() * tensor.element_size()
         if nbytes == 0:
             return np.zeros(0, dtype=torch.empty(0, dtype=tensor.dtype).numpy().dtype)
-        pool = getattr(self, '_pinned', None)
-        if pool is None or pool.numel() < nbytes:
-            pool = self._pinned = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
-        view = pool[:nbytes].view(tensor.dtype)
+        view = self._pinned(pool, nbytes)[:nbytes].view(tensor.dtype)
         view.copy_(tensor.reshape(-1), non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return view.numpy().copy()
+        return view.numpy()
+
+    def _pinned(self, pool, nbytes):
+        pools = self.__dict__.setdefault('_pinned_pools', {})
+        buf = pools.get(pool)
+        if buf is None or buf.numel() < nbytes:
+            buf = pools[pool] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+        return buf
 
     def gather_results(self, group, lo, hi, n, want_edges):
         """Every rank's groups and last single windows on every host, through NCCL all-gathers of the arrays themselves (device
-        views of the library's result buffers, one small size exchange, one padded all-gather, one device-to-host copy)."""
+        views of the library's result buffers): one small size exchange, one padded all-gather of the group arrays, one of the
+        last-single slices whose rows are copied straight to their place in a page-locked result array.  The returned arrays are
+        views of page-locked buffers owned by this object (valid until the next call)."""
         world = dist.get_world_size(group)
         counts = self.ctx.counts()
         indptr = self._view(5, torch.int64, '<i8')
@@ -266,36 +274,49 @@ class NativeOps(object):
         keys = self._view(0, torch.int64, '<i8')
         last_single = self._view(4, torch.int32, '<i4')[lo:hi] if n else torch.empty(0, dtype=torch.int32, device=self.device)
         ng, nm = int(keys.numel()), int(members.numel())
-        sizes = torch.tensor([ng, nm, hi - lo, counts['candidates'], counts['oversized']], dtype=torch.int64, device=self.device)
-        all_sizes = torch.empty(5 * world, dtype=torch.int64, device=self.device)
+        sizes = torch.tensor([ng, nm, hi - lo, lo, counts['candidates'], counts['oversized']], dtype=torch.int64, device=self.device)
+        all_sizes = torch.empty(6 * world, dtype=torch.int64, device=self.device)
         dist.all_gather_into_tensor(all_sizes, sizes, group=group)
-        all_sizes = all_sizes.cpu().view(world, 5).tolist()
-        # one int32 payload per rank: group sizes | members | first windows | keys (two words each) | last single windows
+        all_sizes = all_sizes.cpu().view(world, 6).tolist()
+        # group arrays (small): one int32 payload per rank = group sizes | members | first windows | keys (two words each)
         group_sizes = (indptr[1:] - indptr[:-1]).to(torch.int32) if ng else torch.empty(0, dtype=torch.int32, device=self.device)
-        payload = torch.cat([group_sizes, members, first_window, keys.view(torch.int32), last_single])
-        longest = max(2 * s[0] + s[1] + 2 * s[0] + s[2] for s in all_sizes)
+        payload = torch.cat([group_sizes, members, first_window, keys.view(torch.int32)])
+        longest = max(4 * s[0] + s[1] for s in all_sizes)
         padded = torch.empty(max(longest, 1), dtype=torch.int32, device=self.device)
         padded[:payload.numel()] = payload
         everything = torch.empty(world * padded.numel(), dtype=torch.int32, device=self.device)
         dist.all_gather_into_tensor(everything, padded, group=group)
-        host = self.to_host(everything).reshape(world, -1)
-        parts = {'sizes': [], 'members': [], 'first_window': [], 'keys': [], 'last_single': []}
-        for r, (g, m, span, _, _) in enumerate(all_sizes):
+        host = self.to_host(everything, 'groups').reshape(world, -1)
+        parts = {'sizes': [], 'members': [], 'first_window': [], 'keys': []}
+        for r, (g, m, _, _, _, _) in enumerate(all_sizes):
             row, at = host[r], 0
-            for name, count in (('sizes', g), ('members', m), ('first_window', g), ('keys', 2 * g), ('last_single', span)):
+            for name, count in (('sizes', g), ('members', m), ('first_window', g), ('keys', 2 * g)):
                 parts[name].append(row[at:at + count])
                 at += count
         indptr_all = np.zeros(sum(s[0] for s in all_sizes) + 1, dtype=np.int64)
         np.cumsum(np.concatenate(parts['sizes']).astype(np.int64), out=indptr_all[1:])
+        # last single windows (n entries in all): padded rows on the device, each row copied to its place on the host
+        last_all = np.zeros(0, dtype=np.int32)
+        if n:
+            widest = max(s[2] for s in all_sizes)
+            row = torch.empty(max(widest, 1), dtype=torch.int32, device=self.device)
+            row[:last_single.numel()] = last_single
+            rows = torch.empty(world * row.numel(), dtype=torch.int32, device=self.device)
+            dist.all_gather_into_tensor(rows, row, group=group)
+            target = self._pinned('last_single', 4 * n)[:4 * n].view(torch.int32)
+            for r, (_, _, span, first, _, _) in enumerate(all_sizes):
+                if span:
+                    target[first:first + span].copy_(rows[r * row.numel():r * row.numel() + span], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            last_all = target.numpy()
         edges = None
         if want_edges:
             eu, ev = self._view(1, torch.int32, '<i4'), self._view(2, torch.int32, '<i4')
-            edges = (self.to_host(eu).view(np.uint32), self.to_host(ev).view(np.uint32))
+            edges = (self.to_host(eu, 'edge_u').view(np.uint32), self.to_host(ev, 'edge_v').view(np.uint32))
         return {'indptr': indptr_all, 'members': np.concatenate(parts['members']).view(np.uint32),
                 'first_window': np.concatenate(parts['first_window']).view(np.uint32),
                 'keys': np.ascontiguousarray(np.concatenate(parts['keys'])).view(np.uint64),
-                'last_single': np.concatenate(parts['last_single']) if n else np.zeros(0, dtype=np.int32),
-                'edges': edges, 'candidates': [s[3] for s in all_sizes], 'oversized': [s[4] for s in all_sizes]}
+                'last_single': last_all, 'edges': edges, 'candidates': [s[4] for s in all_sizes], 'oversized': [s[5] for s in all_sizes]}
 
     def fetch_host(self, want_edges):
         """Host copies of this rank's groups, the flags, this shard's last single windows and the merged edges."""
@@ -458,7 +479,7 @@ def build_sharded(ops, offsets, k, internal_repeats, want_edges=False, group=Non
     if flags_all is None:                                # sparse exchange: the other ranks' palindrome / background bits are still missing
         flags_all = _or_reduce_flags(ops, ops.flags(), group)
         ops.set_flags(flags_all)
-    flags_host = (ops.to_host(flags_all) if hasattr(ops, 'to_host') else flags_all.cpu().numpy()) if n else np.zeros(0, dtype=np.uint8)
+    flags_host = (ops.to_host(flags_all, 'flags') if hasattr(ops, 'to_host') else flags_all.cpu().numpy()) if n else np.zeros(0, dtype=np.uint8)
     # records of parts flagged for an internal repeat were exchanged before the flag was known (single path: same); the few
     # flagged parts are picked out on the device
     repeated = torch.nonzero(flags_all & 1).reshape(-1).cpu().numpy() if n else np.zeros(0, dtype=np.int64)

@@ -116,6 +116,10 @@ def test_forced_paths(ctx):
         _compare(_run(ctx, uniq, 13, False), uniq, 13, False)
         _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
         ctx.set_option('coop_group', -1)
+        ctx.set_option('group_walk', 0)               # grouping with nine grid barriers (compaction) instead of the walk variant
+        _compare(_run(ctx, uniq, 13, False), uniq, 13, False)
+        _compare(_run(ctx, uniq, 13, True), uniq, 13, True)
+        ctx.set_option('group_walk', -1)
         ctx.set_option('filter_wide', 0)              # two 512-thread filter CTAs per SM instead of three 256-thread ones
         _compare(_run(ctx, uniq, 13, False), uniq, 13, False)
         big = _long_parts(cases.planted_parts(800, 5) + cases.random_parts(12000, 100, 6), 17)
@@ -148,6 +152,7 @@ def test_forced_paths(ctx):
         uniq17 = _long_parts(cases.planted_parts(600, 77), 17)
         _compare(_run(ctx, uniq17, 17, True), uniq17, 17, True)
     finally:
+        ctx.set_option('group_walk', -1)
         ctx.set_option('filter_wide', -1)
         ctx.set_option('uniform_kernel', -1)
         ctx.set_option('filter_tiny', 0)
@@ -322,3 +327,21 @@ def test_uniform_kernel_with_background(ctx):
     assert res.counts['uniform_kernel'] == 1 and (res.flags & 4).any()
     _compare(res, uniq, 16, False, bg_keys, 14)
     ctx.set_background(None, 0)
+
+
+@pytest.mark.parametrize('internal', [False, True])
+def test_long_key_runs_fall_back_from_the_walk_grouping(ctx, internal):
+    """One k-mer shared by ~1500 records (more than the walk variant of the grouping stage follows): the stage is repeated with
+    the nine-barrier kernel; a second shared stretch of ~200 records stays inside the walk limit."""
+    import random
+    rnd = random.Random(4)
+    parts = cases.random_parts(4000, 60, 31)
+    motif, short_motif = cases.random_parts(1, 20, 32)[0], cases.random_parts(1, 18, 33)[0]
+    for i in range(0, 1500):
+        at = rnd.randint(0, 40)
+        parts[i] = parts[i][:at] + motif + parts[i][at + 20:]
+    for i in range(2000, 2200):
+        parts[i] = parts[i][:5] + short_motif + parts[i][23:]
+    uniq = _long_parts(parts, 17)
+    res = _run(ctx, uniq, 17, internal)
+    _compare(res, uniq, 17, internal)
