@@ -66,7 +66,7 @@ extern "C" {
 #define NRP_C_DIRECT        13  /* 1: buckets were placed in fixed regions (no histogram pass); 0: exact histogram path */
 #define NRP_C_FALLBACKS     14  /* a fixed region overflowed and the batch was repeated on the exact path */
 #define NRP_C_PACKED        15  /* 1: records travelled as single 64-bit words (k-mer << value bits) | value */
-#define NRP_C_UNIFORM       16  /* 1: the part-aligned extraction kernel ran (parts of one length, packed records) */
+#define NRP_C_UNIFORM       16  /* 1: the part-aligned extraction kernel ran (parts of one length, packed records); 2: it also computed the palindrome / background flags */
 #define NRP_N_COUNTS        20
 
 /* indices into nrp_result_timings() (milliseconds, CUDA events on the context's stream) */
@@ -114,6 +114,18 @@ int nrp_bg_clear(nrp_ctx* ctx);
  * them this context's probe set (as nrp_bg_set would). */
 int nrp_bg_build(nrp_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int64_t n_seqs, int K, int install, int64_t* n_unique);
 int nrp_bg_build_fetch(nrp_ctx* ctx, uint64_t* keys_out);
+
+/* Device-side uniquify of a packed part list (replaces uniquify_seq_list, hgraph.py:11-21, and the processing order of
+ * hgraph.py:218-223): n_parts parts as one ASCII buffer (host) + int64 offsets[n_parts+1], or offsets == NULL and every part
+ * part_len bytes long.  The parts are upper-cased, exact duplicates are dropped, the survivors are ordered by DESCENDING index of
+ * their last occurrence and gathered into a device buffer.  out[0] = number of unique parts, out[1] = their total bytes,
+ * out[2] = status bits (1: a character outside A/C/G/T occurs; 2: two different parts collided in the 64-bit hash -- the result
+ * must not be used, take the host path), out[3] = longest part.  nrp_uniquify_fetch copies, for processing rank q,
+ * ids[q] = index of the FIRST occurrence (the part's id), source[q] = index of the last occurrence, offsets[0..n_unique] of the
+ * gathered buffer (any of them may be NULL), and returns the gathered buffer's device address (valid until the next nrp_uniquify /
+ * nrp_ctx_destroy) -- pass it to nrp_load_parts with ascii_on_device = 1. */
+int nrp_uniquify(nrp_ctx* ctx, const uint8_t* ascii, const int64_t* offsets, int part_len, int64_t n_parts, int64_t out[4]);
+int nrp_uniquify_fetch(nrp_ctx* ctx, uint32_t* ids, uint32_t* source, int64_t* offsets, void** dev_ascii);
 
 /* Stage one batch of parts on the device (H2D copy unless ascii_on_device != 0; offsets and part_id are
  * always host arrays).

@@ -15,6 +15,7 @@ import sys
 
 from . import finder as _finder
 from . import kmerSetDB as _kmerSetDB
+from .packed import finder_packed          # additive entry: packed part buffer in, uniquify on the GPU (packed.py)
 
 __version__ = '0.1.0'
 

@@ -100,6 +100,8 @@ def _declare(lib):
         'nrp_parts_capacity': (c_ctx, ctypes.POINTER(i64)),
         'nrp_peer_export_parts': (c_ctx, ptr),
         'nrp_peer_open_parts': (c_ctx, i32, i32, ptr, ptr),
+        'nrp_uniquify': (c_ctx, ptr, ptr, i32, i64, ptr),
+        'nrp_uniquify_fetch': (c_ctx, ptr, ptr, ptr, ctypes.POINTER(ptr)),
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -184,6 +186,27 @@ class Context(object):
         keys = np.zeros(n.value, dtype=np.uint64)
         _check(self._lib, self._lib.nrp_bg_build_fetch(self._h, _p(keys)))
         return keys
+
+    def uniquify(self, ascii_buf, offsets=None, part_len=0):
+        """Device-side uniquify of a packed part list (nrp_uniquify): returns (ids, source, offsets, device address of the gathered
+        upper-cased unique parts in processing order, status bits, longest part).  status & 1: some character is outside A/C/G/T;
+        status & 2: a hash collision between different parts -- the result is unusable, take the host path."""
+        ascii_buf = np.ascontiguousarray(ascii_buf, dtype=np.uint8)
+        if offsets is not None:
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+            n_parts = offsets.size - 1
+            assert ascii_buf.size >= int(offsets[-1])
+        else:
+            n_parts = ascii_buf.size // int(part_len) if part_len else 0
+        out = np.zeros(4, dtype=np.int64)
+        _check(self._lib, self._lib.nrp_uniquify(self._h, _p(ascii_buf) if ascii_buf.size else None, _p(offsets), int(part_len or 0), int(n_parts), _p(out)))
+        n_unique, status, max_len = int(out[0]), int(out[2]), int(out[3])
+        ids = np.zeros(n_unique, dtype=np.uint32)
+        source = np.zeros(n_unique, dtype=np.uint32)
+        new_off = np.zeros(n_unique + 1, dtype=np.int64)
+        dev = ctypes.c_void_p()
+        _check(self._lib, self._lib.nrp_uniquify_fetch(self._h, _p(ids), _p(source), _p(new_off), ctypes.byref(dev)))
+        return ids, source, new_off, dev.value or 0, status, max_len
 
     def load_parts(self, ascii_buf, offsets, part_id=None, device_ptr=None, chunks=1):
         """ascii_buf: uint8 array (host) or None with device_ptr = address of the bytes in device memory.

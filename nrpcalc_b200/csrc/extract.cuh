@@ -20,6 +20,7 @@
 // About 60 thread instructions per window against 163 of the byte-position kernel (profiles/ncu_full_r02*.txt).
 #pragma once
 #include "partition.cuh"
+#include "stages.cuh"
 
 namespace nrp {
 
@@ -44,19 +45,42 @@ inline bool uni_plan(int64_t L, int k, UniPlan* up) {
   return (int64_t)up->G * L + 64 <= (int64_t)(kUniMaxWords - 8) * 16;
 }
 
+// bit map in front of the background table for the folded probe: bit (top log_bits of the bijective hash of the k-mer)
+__global__ void k_bg_bitmap(const uint64_t* keys, int64_t n, BijHash bij, int log_bits, uint32_t* bits) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t bi = (uint32_t)(bij.fwd(keys[i]) >> (bij.n - log_bits));
+    atomicOr(bits + (bi >> 5), 1u << (bi & 31u));
+  }
+}
+
 struct alignas(16) UniSmem {
   SplitSmem<uint64_t, true> split;
   uint32_t packed[kUniMaxWords];
+  uint32_t pflag[kSplitThreads];       // FOLD: flag bits found by the threads of one part (a tile holds at most 512 parts)
+};
+
+// FOLD: the exclusion flags that need no grouping are computed HERE instead of in a pass of their own over the parts
+// (k_flag_windows; reference hgraph.py:59-79): a window equal to its own reverse complement (even k, internal_repeats off) and --
+// when the background's K equals k -- background membership of the canonical k-mer (kmerSetDB.py:177-207).  The probe is a bit map
+// indexed by the top bits of the SAME bijective hash the split uses (one load per window; a set bit -- a few percent of the windows --
+// is confirmed in the exact open-addressing table), loaded two windows ahead of its test.  The threads of a part OR their findings
+// in shared memory; after one more CTA barrier a flagged part emits no record and its first thread writes the flag byte.
+struct FoldArgs {
+  uint8_t* flags;              // per-part flag bytes (read-modify-write by the part's first thread only)
+  const uint32_t* bg_bits;     // nullptr: no background probe
+  const void* bg_table;        // canonical k-mers, open addressing (k_bg_insert)
+  int bg_log_bits, bg_log_slots, bg_key_bytes;
+  int check_pal;
 };
 
 // MODE 0: digit = top r1 bits of the hash (single GPU, fixed regions).  MODE 2: digit = (owner, top r1 bits), stored into the
 // owner's region of this (bucket, sender) over NVLink (direct sharded path); the owner is the top owner_bits of the hash when
 // pf.owner_bits > 0, else owner_of(k-mer).
-template <bool KEY64, int MODE>
-__global__ void __launch_bounds__(kSplitThreads, 2) k_split_uniform(const uint8_t* __restrict__ ascii, const uint8_t* __restrict__ flags, UniPlan up,
+template <bool KEY64, int MODE, bool FOLD = false>
+__global__ void __launch_bounds__(kSplitThreads, 2) k_split_uniform(const uint8_t* __restrict__ ascii, const uint8_t* flags, UniPlan up,
                                                                     int64_t part_lo, int64_t part_hi, int k, int r1, int n_owners, uint32_t part_base,
                                                                     int j_bits, PackFmt pf, uint32_t* cursor, uint64_t* out_keys, RegionLimit lim,
-                                                                    PeerBuffers peers) {
+                                                                    PeerBuffers peers, FoldArgs fold = FoldArgs{}) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   UniSmem& sm = *reinterpret_cast<UniSmem*>(smem_raw);
   SplitSmem<uint64_t, true>& s = sm.split;
@@ -80,9 +104,10 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split_uniform(const uint8_
   int n_e = 0;                                                   // windows of this thread (0: idle)
   if (pl < up.G && part < P1) {
     n_e = (int)min((uint32_t)kSplitItems, up.W - j0);
-    if (flags != nullptr && __ldg(flags + part) != 0) n_e = 0;  // part excluded by the flag pass (palindrome / background)
+    if (flags != nullptr && flags[part] != 0) n_e = 0;          // part excluded by the flag pass (palindrome / background)
   }
   s.cnt[t] = 0;
+  if (FOLD) sm.pflag[t] = 0;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int c = t + i * kSplitThreads;
@@ -112,6 +137,31 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split_uniform(const uint8_
 
   uint64_t key[kSplitItems];
   uint32_t val[kSplitItems], dr[kSplitItems];
+  // FOLD: flag bits this thread found; the bit-map word of window e is tested while window e + 2 is computed
+  uint32_t fbits = 0, bw0 = 0, bw1 = 0, bp0 = 0, bp1 = 0;
+  const bool probe = FOLD && fold.bg_bits != nullptr;
+  auto canon_at = [&](int e) -> uint64_t {                       // canonical k-mer of window e, right-aligned (rare path)
+    const uint32_t c = rel + (uint32_t)e;
+    const int cw = (int)(c >> 4), csh = (int)(c & 15u) * 2;
+    const uint32_t y0 = sm.packed[cw], y1 = sm.packed[cw + 1], y2 = sm.packed[cw + 2];
+    const uint64_t v = ((((uint64_t)__funnelshift_l(y1, y0, csh)) << 32) | __funnelshift_l(y2, y1, csh)) >> (64 - 2 * k);
+    const uint64_t rc = revcomp2(v, k);
+    return v < rc ? v : rc;
+  };
+  auto confirm = [&](int e) {                                     // the bit of window e was set: exact test
+    const uint64_t canon = canon_at(e);
+    const bool hit = fold.bg_key_bytes == 4 ? bg_contains<uint32_t>(reinterpret_cast<const uint32_t*>(fold.bg_table), fold.bg_log_slots, canon)
+                                            : bg_contains<uint64_t>(reinterpret_cast<const uint64_t*>(fold.bg_table), fold.bg_log_slots, canon);
+    if (hit) fbits |= kFlagBackground;
+  };
+  // one step of the two-deep probe pipeline: test the word loaded two windows ago, then issue this window's load
+  auto probe_step = [&](int e, uint32_t top_hash, bool valid) {    // top_hash: the hash left-aligned in 32 bits
+    if (e >= 2 && ((bw0 >> bp0) & 1u)) confirm(e - 2);
+    bw0 = bw1; bp0 = bp1;
+    const uint32_t bi = __funnelshift_rc(top_hash, 0u, 32 - fold.bg_log_bits);
+    bp1 = bi & 31u;
+    bw1 = valid ? __ldg(fold.bg_bits + (bi >> 5)) : 0u;
+  };
   if (KEY64) {
     const uint32_t x0 = sm.packed[w], x1 = sm.packed[w + 1], x2 = sm.packed[w + 2];
     uint32_t fh = __funnelshift_l(x1, x0, sh), fl = __funnelshift_l(x2, x1, sh) & low_clear;    // window 0, left-aligned
@@ -134,6 +184,7 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split_uniform(const uint8_
       const bool valid = e < n_e;
       const bool f_less = fh < rh || (fh == rh && fl < rl);
       const uint32_t ch_ = f_less ? fh : rh, cl = f_less ? fl : rl;     // canonical k-mer, left-aligned
+      if (FOLD && fold.check_pal && valid && fh == rh && fl == rl) fbits |= kFlagPalindrome;
       // bijective hash (BijHash::fwd) in left-aligned arithmetic: multiply, fold, multiply -- mod 2^2k for free
       uint64_t p1 = (uint64_t)cl * C1;
       uint32_t hl = (uint32_t)p1, hh = ch_ * C1 + (uint32_t)(p1 >> 32);
@@ -146,8 +197,13 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split_uniform(const uint8_
         const uint64_t canon = (((uint64_t)ch_ << 32) | cl) >> j;
         d |= owner_of(canon, (uint32_t)n_owners) << r1;
       }
-      const uint32_t rank = atomicAdd(&s.cnt[valid ? d : (uint32_t)kLevelBuckets + lane], 1u);
-      dr[e] = valid ? ((d << 16) | rank) : 0xffffffffu;
+      if (FOLD) {
+        if (probe) probe_step(e, hh, valid);
+        dr[e] = d;                                               // ranked after the part's flags are known
+      } else {
+        const uint32_t rank = atomicAdd(&s.cnt[valid ? d : (uint32_t)kLevelBuckets + lane], 1u);
+        dr[e] = valid ? ((d << 16) | rank) : 0xffffffffu;
+      }
       const uint32_t kh = __funnelshift_l(hl, hh, sdrop), kl = (hl << sdrop) | (v0 + (uint32_t)e * step);
       key[e] = ((uint64_t)kh << 32) | kl;
       val[e] = 0;
@@ -164,15 +220,43 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split_uniform(const uint8_
       }
       const bool valid = e < n_e;
       const uint32_t c = min(f, r);
+      if (FOLD && fold.check_pal && valid && f == r) fbits |= kFlagPalindrome;
       uint32_t h = c * C1;
       h ^= (h >> s_fold) & low_clear;
       h *= C2;
       uint32_t d = __funnelshift_rc(h, 0u, 32 - dbits);
       if (mix_owner) d |= owner_of((uint64_t)(c >> j), (uint32_t)n_owners) << r1;
-      const uint32_t rank = atomicAdd(&s.cnt[valid ? d : (uint32_t)kLevelBuckets + lane], 1u);
-      dr[e] = valid ? ((d << 16) | rank) : 0xffffffffu;
+      if (FOLD) {
+        if (probe) probe_step(e, h, valid);
+        dr[e] = d;
+      } else {
+        const uint32_t rank = atomicAdd(&s.cnt[valid ? d : (uint32_t)kLevelBuckets + lane], 1u);
+        dr[e] = valid ? ((d << 16) | rank) : 0xffffffffu;
+      }
       key[e] = ((uint64_t)(h << sdrop) << 32) | (v0 + (uint32_t)e * step);
       val[e] = 0;
+    }
+  }
+  if (FOLD) {
+    if (probe) {                                                 // drain the probe pipeline: windows 6 and 7
+      if ((bw0 >> bp0) & 1u) confirm(kSplitItems - 2);
+      if ((bw1 >> bp1) & 1u) confirm(kSplitItems - 1);
+    }
+    if (fbits != 0) atomicOr(&sm.pflag[pl], fbits);
+    __syncthreads();
+    if (n_e > 0) {
+      const uint32_t found = sm.pflag[pl];
+      if (found != 0) {
+        if (j0 == 0) fold.flags[part] |= (uint8_t)found;          // the part's first thread (always one of its active threads)
+        n_e = 0;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < kSplitItems; ++e) {
+      const bool valid = e < n_e;
+      const uint32_t d = dr[e];
+      const uint32_t rank = atomicAdd(&s.cnt[valid ? d : (uint32_t)kLevelBuckets + lane], 1u);
+      dr[e] = valid ? ((d << 16) | rank) : 0xffffffffu;
     }
   }
   __syncthreads();

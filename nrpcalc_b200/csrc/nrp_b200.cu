@@ -29,6 +29,7 @@
 #include "partition.cuh"
 #include "extract.cuh"
 #include "stages.cuh"
+#include "uniquify.cuh"
 
 using namespace nrp;
 
@@ -155,13 +156,21 @@ struct nrp_ctx {
   int64_t opt_filter_wide = 1;            // packed leaves of <= 4096 records: three 256-thread CTAs per SM with 16 records per thread (half the
                                           // per-leaf fixed work per record: config 2 filter 0.437 -> 0.381 ms) when few suspects are expected;
                                           // 0 = two 512-thread CTAs
+  int64_t opt_fold_flags = 1;             // part-aligned kernel: palindrome test and (K == k) background probe inside the extraction instead
+                                          // of a pass of their own over the parts
   int64_t opt_uniform_kernel = 1;         // parts of one length: the part-aligned extraction kernel (extract.cuh); 0 = the byte-position kernel
 
   // background
   DevBuf bg_table; int bg_K = 0; int bg_log_slots = 0; int bg_key_bytes = 0; int64_t bg_n = 0;
+  DevBuf bg_bits; int bg_log_bits = 0;      // bit map by the top bits of the bijective hash (folded probe, extract.cuh)
+  bool fold_pal = false, fold_bg = false;   // this job's extraction kernel computes these flags itself
   // background build on the device: staged sequences, extracted / sorted / distinct keys
   DevBuf bgb_ascii, bgb_off, bgb_tile_first, bgb_keysA, bgb_keysB, bgb_head, bgb_head_scan;
   uint64_t* bgb_result = nullptr; int64_t bgb_n = 0;
+
+  // device-side uniquify (nrp_uniquify): the caller's parts, the surviving parts in processing order, their ids / sources / offsets
+  DevBuf uq_in, uq_off, uq_out, uq_rep, uq_run_first, uq_source, uq_ids, uq_lens, uq_newoff, uq_status;
+  int64_t uq_n = 0, uq_unique = -1, uq_total = 0, uq_uniform = 0;
 
   // loaded parts
   DevBuf ascii, off, part_id, tile_first;
@@ -324,6 +333,8 @@ int configure_kernels(nrp_ctx* c) {
   CU(cudaFuncSetAttribute((k_split_uniform<true, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
   CU(cudaFuncSetAttribute((k_split_uniform<false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
   CU(cudaFuncSetAttribute((k_split_uniform<true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
+  CU(cudaFuncSetAttribute((k_split_uniform<false, 0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
+  CU(cudaFuncSetAttribute((k_split_uniform<true, 0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
   const int packed_smem = (int)(sizeof(SplitSmem<uint64_t, true>) + sizeof(TileStage));
   CU(cudaFuncSetAttribute((k_split_from_ascii<uint64_t, 0, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, packed_smem));
   CU(cudaFuncSetAttribute((k_split_from_ascii<uint64_t, 2, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, packed_smem));
@@ -412,6 +423,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "direct") c->opt_direct = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "filter_wide") c->opt_filter_wide = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "uniform_kernel") c->opt_uniform_kernel = value < 0 ? 1 : (value > 0 ? 1 : 0);
+  else if (n == "fold_flags") c->opt_fold_flags = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
   return NRP_OK;
 }
@@ -434,9 +446,17 @@ static int bg_install_device(nrp_ctx* c, const uint64_t* dev_keys, int64_t n, in
   const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, c->n_sms * 8);
   if (key_bytes == 4) NRP_LAUNCH((k_bg_insert<uint32_t><<<grid, 256, 0, c->stream>>>(dev_keys, n, c->bg_table.as<uint32_t>(), log_slots)));
   else NRP_LAUNCH((k_bg_insert<uint64_t><<<grid, 256, 0, c->stream>>>(dev_keys, n, c->bg_table.as<uint64_t>(), log_slots)));
+  // bit map for the folded probe: >= 16 bits per key, at most 2K (all the hash has) and 2^30 bits
+  int log_bits = 10;
+  while (log_bits < 30 && ((int64_t)1 << log_bits) < 16 * n) ++log_bits;
+  log_bits = std::min(log_bits, 2 * K);
+  const size_t bit_bytes = ((((size_t)1 << log_bits) + 31) / 32) * 4;
+  TRY(c->bg_bits.ensure(bit_bytes));
+  CU(cudaMemsetAsync(c->bg_bits.ptr, 0, bit_bytes, c->stream));
+  NRP_LAUNCH((k_bg_bitmap<<<grid, 256, 0, c->stream>>>(dev_keys, n, make_bijhash(K), log_bits, c->bg_bits.as<uint32_t>())));
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
-  c->bg_n = n; c->bg_K = K; c->bg_log_slots = log_slots; c->bg_key_bytes = key_bytes;
+  c->bg_n = n; c->bg_K = K; c->bg_log_slots = log_slots; c->bg_key_bytes = key_bytes; c->bg_log_bits = log_bits;
   return NRP_OK;
 }
 
@@ -521,6 +541,107 @@ int nrp_bg_build_fetch(nrp_ctx* c, uint64_t* keys_out) {
   CU(cudaSetDevice(c->device));
   if (c->bgb_n > 0) CU(cudaMemcpyAsync(keys_out, c->bgb_result, 8 * (size_t)c->bgb_n, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  return NRP_OK;
+}
+
+// ---- device-side uniquify (uniquify.cuh) ----------------------------------------------------------------------------------------
+int nrp_uniquify(nrp_ctx* c, const uint8_t* ascii, const int64_t* offsets, int part_len, int64_t n_parts, int64_t out[4]) {
+  if (!c || !out) return fail(NRP_E_ARG, "null argument");
+  if (n_parts < 0 || (!offsets && part_len < 1 && n_parts > 0)) return fail(NRP_E_ARG, "offsets or a positive part_len is required");
+  if (n_parts >= 0xfffffff0ll) return fail(NRP_E_UNSUPPORTED, "%lld parts exceed the 32-bit part index", (long long)n_parts);
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  c->uq_unique = -1;
+  int64_t total = 0, min_len = 0, max_len = 0;
+  if (offsets) {
+    if (offsets[0] != 0) return fail(NRP_E_ARG, "offsets[0] must be 0");
+    min_len = n_parts > 0 ? INT64_MAX : 0;
+    for (int64_t i = 0; i < n_parts; ++i) {
+      const int64_t len = offsets[i + 1] - offsets[i];
+      min_len = std::min(min_len, len); max_len = std::max(max_len, len);
+    }
+    if (min_len < 0) return fail(NRP_E_ARG, "offsets must be non-decreasing");
+    total = offsets[n_parts];
+  } else {
+    total = n_parts * (int64_t)part_len; min_len = max_len = n_parts > 0 ? part_len : 0;
+  }
+  if (total > 0 && !ascii) return fail(NRP_E_ARG, "null part buffer");
+  if (max_len >= ((int64_t)1 << 31)) return fail(NRP_E_UNSUPPORTED, "parts of 2^31 bytes or more");
+  const int64_t uniform = (n_parts > 0 && min_len == max_len) ? max_len : 0;
+  out[0] = 0; out[1] = 0; out[2] = 0; out[3] = max_len;
+  c->uq_n = n_parts; c->uq_uniform = uniform; c->uq_total = 0;
+  if (n_parts == 0) { c->uq_unique = 0; return NRP_OK; }
+  const size_t n1 = (size_t)n_parts + 2;
+  TRY(c->uq_in.ensure((size_t)total + 64)); TRY(c->uq_out.ensure((size_t)total + 64));
+  TRY(c->uq_off.ensure(8 * n1)); TRY(c->uq_newoff.ensure(8 * n1));
+  TRY(c->uq_rep.ensure(4 * n1)); TRY(c->uq_run_first.ensure(4 * n1)); TRY(c->uq_source.ensure(4 * n1));
+  TRY(c->uq_ids.ensure(4 * n1)); TRY(c->uq_lens.ensure(4 * n1)); TRY(c->uq_status.ensure(16));
+  TRY(c->keysA.ensure(8 * n1)); TRY(c->keysB.ensure(8 * n1)); TRY(c->valsA.ensure(4 * n1)); TRY(c->valsB.ensure(4 * n1));
+  TRY(c->head.ensure(4 * n1)); TRY(c->head_scan.ensure(4 * n1)); TRY(c->valid.ensure(4 * n1)); TRY(c->valid_scan.ensure(4 * n1));
+  TRY(c->scan_scratch.ensure(8 * (size_t)scan_scratch_elems((int64_t)n1 + 1)));
+  TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n_parts)));
+  CU(cudaStreamSynchronize(st));
+  if (total > 0) CU(cudaMemcpyAsync(c->uq_in.ptr, ascii, (size_t)total, cudaMemcpyHostToDevice, st));
+  if (offsets && uniform == 0) CU(cudaMemcpyAsync(c->uq_off.ptr, offsets, 8 * (size_t)(n_parts + 1), cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(c->uq_status.ptr, 0, 16, st));
+  CU(cudaMemsetAsync(c->uq_rep.ptr, 0, 4 * n1, st));
+  const PartSpan S{c->uq_in.as<uint8_t>(), c->uq_off.as<int64_t>(), uniform};
+  uint32_t* status = c->uq_status.as<uint32_t>();
+  const unsigned warp_grid = (unsigned)std::min<int64_t>((n_parts + 7) / 8, (int64_t)c->n_sms * 16);
+  NRP_LAUNCH((k_part_hash<<<warp_grid, 256, 0, st>>>(S, n_parts, c->keysA.as<uint64_t>(), c->valsA.as<uint32_t>(), status)));
+  LsdPlan plan; plan.n_passes = 0;
+  lsd_plan_add(plan, 0, 0, 64);
+  uint64_t* sk = nullptr; uint32_t* sv = nullptr;
+  lsd_sort<uint64_t, true>(c->keysA.as<uint64_t>(), c->valsA.as<uint32_t>(), c->keysB.as<uint64_t>(), c->valsB.as<uint32_t>(), n_parts, plan,
+                           c->lsd_scratch.as<uint32_t>(), st, &sk, &sv);
+  const unsigned grid = grid_for(n_parts, 256);
+  NRP_LAUNCH((k_uniq_heads<<<grid, 256, 0, st>>>(S, sk, sv, n_parts, c->head.as<uint32_t>(), status)));
+  exclusive_scan<uint32_t, uint32_t>(c->head.as<uint32_t>(), c->head_scan.as<uint32_t>(), n_parts, c->scan_scratch.as<uint32_t>(), st);
+  NRP_LAUNCH((k_uniq_runs<<<grid, 256, 0, st>>>(sk, sv, c->head.as<uint32_t>(), c->head_scan.as<uint32_t>(), n_parts, c->uq_run_first.as<uint32_t>(),
+                                                c->uq_rep.as<uint32_t>())));
+  NRP_LAUNCH((k_uniq_keep<<<grid, 256, 0, st>>>(c->uq_rep.as<uint32_t>(), n_parts, c->valid.as<uint32_t>())));
+  exclusive_scan<uint32_t, uint32_t>(c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(), n_parts, c->scan_scratch.as<uint32_t>(), st);
+  NRP_LAUNCH((k_uniq_emit<<<grid, 256, 0, st>>>(S, c->uq_rep.as<uint32_t>(), c->valid.as<uint32_t>(), c->valid_scan.as<uint32_t>(),
+                                                c->uq_run_first.as<uint32_t>(), n_parts, c->uq_source.as<uint32_t>(), c->uq_ids.as<uint32_t>(),
+                                                c->uq_lens.as<uint32_t>())));
+  CU(cudaMemcpyAsync(c->h_counters + 58, c->valid_scan.as<uint32_t>() + n_parts, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(c->h_counters + 59, status, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));
+  const int64_t n_unique = (int64_t)(uint32_t)c->h_counters[58];
+  const uint32_t bits = (uint32_t)c->h_counters[59];
+  int64_t total_unique = n_unique * uniform;
+  if (uniform == 0) {
+    exclusive_scan<uint32_t, unsigned long long>(c->uq_lens.as<uint32_t>(), c->uq_newoff.as<unsigned long long>(), n_unique,
+                                                 c->scan_scratch.as<unsigned long long>(), st);
+    CU(cudaMemcpyAsync(c->h_counters + 58, c->uq_newoff.as<unsigned long long>() + n_unique, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    total_unique = (int64_t)c->h_counters[58];
+  }
+  if (n_unique > 0)
+    NRP_LAUNCH((k_uniq_gather<<<(unsigned)std::min<int64_t>((n_unique + 7) / 8, (int64_t)c->n_sms * 16), 256, 0, st>>>(
+        S, c->uq_source.as<uint32_t>(), c->uq_newoff.as<unsigned long long>(), uniform, n_unique, c->uq_out.as<uint8_t>())));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));
+  c->uq_unique = n_unique; c->uq_total = total_unique;
+  out[0] = n_unique; out[1] = total_unique; out[2] = (int64_t)bits; out[3] = max_len;
+  return NRP_OK;
+}
+
+int nrp_uniquify_fetch(nrp_ctx* c, uint32_t* ids, uint32_t* source, int64_t* offsets, void** dev_ascii) {
+  if (!c) return fail(NRP_E_ARG, "null context");
+  if (c->uq_unique < 0) return fail(NRP_E_STATE, "no finished nrp_uniquify");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int64_t n = c->uq_unique;
+  if (n > 0 && ids) CU(cudaMemcpyAsync(ids, c->uq_ids.ptr, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (n > 0 && source) CU(cudaMemcpyAsync(source, c->uq_source.ptr, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (offsets) {
+    if (c->uq_uniform > 0 || n == 0) { for (int64_t i = 0; i <= n; ++i) offsets[i] = i * c->uq_uniform; }
+    else CU(cudaMemcpyAsync(offsets, c->uq_newoff.ptr, 8 * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  if (dev_ascii) *dev_ascii = c->uq_out.ptr;
   return NRP_OK;
 }
 
@@ -713,20 +834,29 @@ int wait_chunks(nrp_ctx* c) {
   return NRP_OK;
 }
 
-// ---- stage: exclusion flags that need no grouping (palindromes, background) over the shard's tiles
-int stage_flags(nrp_ctx* c, int k, int internal_repeats, StageTimer& tm) {
+bool uniform_kernel_runs(const nrp_ctx* c, int k);
+
+// ---- stage: exclusion flags that need no grouping (palindromes, background) over the shard's tiles.
+// allow_fold (single-GPU build): when the part-aligned extraction kernel is going to run, the palindrome test and -- for a
+// background with K == k -- the background probe are left to it (FOLD in extract.cuh): no pass of their own over the parts.
+int stage_flags(nrp_ctx* c, int k, int internal_repeats, StageTimer& tm, bool allow_fold = false) {
   cudaStream_t st = c->stream;
   tm.begin(NRP_T_FLAGS);
-  if ((!internal_repeats && (k % 2) == 0) || c->bg_n > 0 || c->shard_lo != 0 || c->shard_hi != c->n_parts) TRY(wait_chunks(c));
+  const bool want_pal = !internal_repeats && (k % 2) == 0, want_bg = c->bg_n > 0;
+  const bool fold = allow_fold && c->opt_fold_flags && (want_pal || want_bg) && uniform_kernel_runs(c, k);
+  c->fold_pal = fold && want_pal;
+  c->fold_bg = fold && want_bg && c->bg_K == k;
+  const bool pass_pal = want_pal && !c->fold_pal, pass_bg = want_bg && !c->fold_bg;
+  if (pass_pal || pass_bg || c->shard_lo != 0 || c->shard_hi != c->n_parts) TRY(wait_chunks(c));
   const Parts P = parts_view(c);
   TRY(c->flags.ensure((size_t)c->n_parts + 16));
   TRY(c->last_single.ensure(sizeof(int32_t) * (size_t)(c->n_parts + 1)));
   CU(cudaMemsetAsync(c->flags.ptr, 0, (size_t)c->n_parts + 16, st));
-  c->flags_set = c->shard_tiles > 0 && ((!internal_repeats && (k % 2) == 0) || c->bg_n > 0);
+  c->flags_set = c->shard_tiles > 0 && (pass_pal || pass_bg);
   if (c->shard_tiles > 0) {
-    if (!internal_repeats && (k % 2) == 0)
+    if (pass_pal)
       NRP_LAUNCH((k_flag_windows<uint32_t><<<(unsigned)c->shard_tiles, kTileThreads, 0, st>>>(P, k, 0, nullptr, 0, c->flags.as<uint8_t>())));
-    if (c->bg_n > 0) {
+    if (pass_bg) {
       if (c->bg_key_bytes == 4)
         NRP_LAUNCH((k_flag_windows<uint32_t><<<(unsigned)c->shard_tiles, kTileThreads, 0, st>>>(P, c->bg_K, 1, c->bg_table.as<uint32_t>(),
                                                                                               c->bg_log_slots, c->flags.as<uint8_t>())));
@@ -827,6 +957,19 @@ PackFmt pack_format(const nrp_ctx* c, int k, int drop, int owner_bits = 0, uint3
   // the stored hash bits go to the top of the word (see PackFmt); packed_fits has checked that the value fits below them
   const int stored = std::max(1, 2 * k - owner_bits - drop);
   return PackFmt{make_bijhash(k), std::max(c->vbits, 64 - stored), drop, owner_bits, owner};
+}
+
+// Will the first split of a single-GPU build of the staged parts be the part-aligned kernel?  (The same decisions as
+// stage_bulk_direct takes; the extraction kernel then also computes the flags stage_flags left to it.)
+bool uniform_kernel_runs(const nrp_ctx* c, int k) {
+  UniPlan up;
+  if (!c->opt_direct || !c->opt_uniform_kernel || c->uniform_len <= 0 || c->n_owners > 0 || !uni_plan(c->uniform_len, k, &up)) return false;
+  if (c->shard_m_max <= 0) return false;
+  const DirectPlan dp = plan_direct(c, c->shard_m_max, 0, false, 0);
+  int64_t total_max = 0;
+  for (int i = 0; i < dp.n_levels; ++i) total_max = std::max(total_max, ((int64_t)1 << dp.cum[i]) * dp.cap[i]);
+  if (total_max >= 0xffffe000ll) return false;
+  return packed_fits(c, k, dp.cum[0], dp.bits);
 }
 
 template <typename KeyT>
@@ -952,6 +1095,19 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
           const unsigned ugrid = (unsigned)((n_q + up.G - 1) / up.G);
           const uint8_t* fl = c->flags_set ? c->flags.as<uint8_t>() : nullptr;
           if (n_q <= 0) continue;
+          if (c->fold_pal || c->fold_bg) {
+            // the flags stage_flags left to this kernel: palindromic windows and / or the background probe (K == k)
+            FoldArgs fa{c->flags.as<uint8_t>(), c->fold_bg ? c->bg_bits.as<uint32_t>() : nullptr, c->bg_table.ptr, c->bg_log_bits, c->bg_log_slots,
+                        c->bg_key_bytes, c->fold_pal ? 1 : 0};
+            if (k > 16)
+              NRP_LAUNCH((k_split_uniform<true, 0, true><<<ugrid, kSplitThreads, sizeof(UniSmem), st>>>(
+                  Q.ascii, fl, up, Q.part_lo, Q.part_hi, k, r, 0, c->part_base, c->j_bits, pf, cursor, (uint64_t*)out_k, lim, PeerBuffers{}, fa)));
+            else
+              NRP_LAUNCH((k_split_uniform<false, 0, true><<<ugrid, kSplitThreads, sizeof(UniSmem), st>>>(
+                  Q.ascii, fl, up, Q.part_lo, Q.part_hi, k, r, 0, c->part_base, c->j_bits, pf, cursor, (uint64_t*)out_k, lim, PeerBuffers{}, fa)));
+            c->counts[NRP_C_UNIFORM] = 2;
+            continue;
+          }
           if (k > 16)
             NRP_LAUNCH((k_split_uniform<true, 0><<<ugrid, kSplitThreads, sizeof(UniSmem), st>>>(
                 Q.ascii, fl, up, Q.part_lo, Q.part_hi, k, r, 0, c->part_base, c->j_bits, pf, cursor, (uint64_t*)out_k, lim, PeerBuffers{})));
@@ -1503,7 +1659,7 @@ int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   begin_job(c, k, sizeof(KeyT), want_edges);
   c->counts[NRP_C_WINDOWS_MAX] = c->shard_m_max;
   StageTimer tm(c);
-  TRY(stage_flags(c, k, internal_repeats, tm));
+  TRY(stage_flags(c, k, internal_repeats, tm, true));
   TRY((stage_bulk<KeyT>(c, k, BulkSource<KeyT>{}, tm)));
   TRY((stage_sort_mark<KeyT>(c, k, c->n_parts, !internal_repeats, tm)));
   TRY((stage_groups<KeyT>(c, !internal_repeats, tm)));

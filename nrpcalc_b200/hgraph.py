@@ -97,7 +97,8 @@ def _world_size():
         return 1
 
 
-def _device_build(ctx, structure, ascii_buf, offsets, global_p, ids, k, internal_repeats, want_edges=False, allow_sharding=False):
+def _device_build(ctx, structure, ascii_buf, offsets, global_p, ids, k, internal_repeats, want_edges=False, allow_sharding=False,
+                  device_ptr=None):
     """One build over parts that all have length >= k; global_p maps local index -> processing rank.
     With an initialised torch.distributed group of more than one rank the build is hash-sharded across the ranks
     (nrpcalc_b200.sharded); every rank receives the same result."""
@@ -116,7 +117,7 @@ def _device_build(ctx, structure, ascii_buf, offsets, global_p, ids, k, internal
         structure.counts['runs'] = max(structure.counts['runs'], 1)
         structure.edges = None if out['edges'] is None else tuple(e.copy() for e in out['edges'])     # views of staging buffers
     else:
-        ctx.load_parts(ascii_buf, offsets, ids if want_edges else None)
+        ctx.load_parts(ascii_buf, offsets, ids if want_edges else None, device_ptr=device_ptr)
         ctx.build(k, internal_repeats, want_edges=want_edges)
         res = ctx.fetch(want_keys=False)
         flags, indptr, members, first_window, last_single = res.flags, res.indptr, res.members, res.first_window, res.last_single
@@ -140,6 +141,38 @@ def _device_build(ctx, structure, ascii_buf, offsets, global_p, ids, k, internal
                               global_p[own])
 
 
+def _install_background(ctx, background, longest_part):
+    """Make the background's canonical K-mers the context's probe set (kmerSetDB.py:177-207 on the device)."""
+    if background is None:
+        ctx.set_background(None, 0)
+        return
+    if background.K <= longest_part and not background.ALIVE:
+        raise RuntimeError('kmerSetDB was closed or dropped')      # surfaces from multicheck, kmerSetDB.py:97-102
+    keys, _ = background.device_keys()
+    if background.K > 32:
+        if keys.size or len(background):
+            raise ValueError('backgrounds with Lmax > 31 are not supported by the device path')
+        ctx.set_background(None, 0)
+    else:
+        ctx.set_background(keys, background.K)
+
+
+def repeat_structure_device(ctx, device_ptr, offsets, ids, longest_part, background, homology, internal_repeats, want_edges=False):
+    """The device path over parts that already lie in device memory in processing order (the gathered buffer of
+    Context.uniquify): every part at least `homology` long, A/C/G/T only.  Returns the RepeatStructure."""
+    n = int(offsets.size - 1)
+    structure = RepeatStructure(n)
+    if homology > 32 and n:
+        raise ValueError('Lmax > 31 needs keys wider than 64 bits, which the device path does not support')
+    _install_background(ctx, background, longest_part)
+    try:
+        _device_build(ctx, structure, None, offsets, np.arange(n, dtype=np.int64), ids, homology, internal_repeats, want_edges,
+                      allow_sharding=False, device_ptr=device_ptr)
+    finally:
+        ctx.set_background(None, 0)
+    return structure
+
+
 def repeat_structure(parts, background, homology, internal_repeats, ctx=None, want_edges=False):
     """Run the device path over the processing-ordered [(id, SEQ)] list.  Returns (RepeatStructure, ids)."""
     ctx = ctx or _context()
@@ -152,18 +185,7 @@ def repeat_structure(parts, background, homology, internal_repeats, ctx=None, wa
     lengths = np.diff(offsets)
     structure = RepeatStructure(n)
 
-    if background is not None:
-        if background.K <= (int(lengths.max()) if n else 0) and not background.ALIVE:
-            raise RuntimeError('kmerSetDB was closed or dropped')      # surfaces from multicheck, kmerSetDB.py:97-102
-        keys, _ = background.device_keys()
-        if background.K > 32:
-            if keys.size or len(background):
-                raise ValueError('backgrounds with Lmax > 31 are not supported by the device path')
-            ctx.set_background(None, 0)
-        else:
-            ctx.set_background(keys, background.K)
-    else:
-        ctx.set_background(None, 0)
+    _install_background(ctx, background, int(lengths.max()) if n else 0)
 
     if homology > 32 and n and int(lengths.max()) > 32:
         raise ValueError('Lmax > 31 needs keys wider than 64 bits, which the device path does not support')

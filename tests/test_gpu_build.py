@@ -217,6 +217,33 @@ def test_direct_overflow_falls_back_to_exact(ctx):
         ctx.set_option('max_pairs', 0)
 
 
+def test_direct_overflow_after_folded_flags(ctx):
+    """The same overflow when the extraction kernel also computed the palindrome / background flags (even k, K == k): the exact
+    path that repeats the batch must find those flags complete."""
+    import random
+    rnd = random.Random(4)
+    common = ''.join(rnd.choice('ACGT') for _ in range(15))
+    parts = [common + ''.join(rnd.choice('ACGT') for _ in range(35)) for _ in range(1200)]
+    for i in range(3, 1200, 50):
+        half = ''.join(rnd.choice('ACGT') for _ in range(7))
+        parts[i] = parts[i][:20] + half + cases.rc(half) + parts[i][34:]
+    bg_keys = np_oracle.canonical_key_set([p[30:50] for p in parts[::40]], 14)
+    uniq = _long_parts(parts, 14)
+    try:
+        ctx.set_option('max_pairs', 1 << 40)
+        res = _run(ctx, uniq, 14, False, bg_keys, 14)
+        assert res.counts['fallbacks'] == 1 and res.counts['direct'] == 0 and res.counts['uniform_kernel'] == 2
+        want = np_oracle.spec(uniq, 14, False, bg_keys, 14)
+        assert (res.flags != 0).tolist() == (want['flags'] != 0).tolist() and (res.flags & 4).any() and (res.flags & 2).any()
+        assert res.counts['records'] == want['n_records']
+        assert res.counts['groups'] == len(want['groups'])
+        assert sorted(zip(res.edges[0].tolist(), res.edges[1].tolist())) == sorted(want['edges'])
+        assert res.last_single.tolist() == want['last_single'].tolist()
+    finally:
+        ctx.set_option('max_pairs', 0)
+        ctx.set_background(None, 0)
+
+
 def test_deep_direct_levels(ctx):
     """Tiny leaf target: two 9-bit levels on the direct path."""
     uniq = _long_parts(cases.planted_parts(800, 9) + cases.random_parts(4000, 100, 4), 17)
@@ -315,7 +342,8 @@ def test_uniform_kernel_shapes(ctx, length, k, internal):
     uniq = _long_parts(_uniform_with_repeats(n, length, 100 + length + k, k), k)
     res = _run(ctx, uniq, k, internal)
     windows = length - k + 1
-    assert res.counts['uniform_kernel'] == (1 if windows <= 4096 and res.counts['packed'] else 0)
+    folded = 2 if (k % 2 == 0 and not internal) else 1          # 2: the kernel also tested its windows for palindromes
+    assert res.counts['uniform_kernel'] == (folded if windows <= 4096 and res.counts['packed'] else 0)
     _compare(res, uniq, k, internal)
 
 
@@ -327,6 +355,41 @@ def test_uniform_kernel_with_background(ctx):
     assert res.counts['uniform_kernel'] == 1 and (res.flags & 4).any()
     _compare(res, uniq, 16, False, bg_keys, 14)
     ctx.set_background(None, 0)
+
+
+@pytest.mark.parametrize('k,K', [(16, 16), (6, 6), (17, 17), (20, 20), (32, 32), (12, 12), (16, 14), (14, 16)])
+@pytest.mark.parametrize('fold', [1, 0])
+def test_uniform_kernel_folded_flags(ctx, k, K, fold):
+    """Palindrome test and background probe (K == k) inside the part-aligned extraction kernel (FOLD, extract.cuh) against the
+    separate flag pass and the oracle: planted palindromic windows (even k), a background cut from the parts themselves (hits at
+    the first / last window of a part and in the middle), background lengths that differ from k (probe stays a pass of its own)."""
+    import random
+    rnd = random.Random(1000 * k + K)
+    length = max(k, K) + 37
+    parts = _uniform_with_repeats(3000, length, 7 * k + K, k)
+    if k % 2 == 0:
+        for i in range(5, len(parts), 41):                         # a palindromic k-window at a random position
+            half = cases.random_parts(1, k // 2, i)[0]
+            at = rnd.choice([0, length - k, rnd.randint(0, length - k)])
+            parts[i] = parts[i][:at] + half + cases.rc(half) + parts[i][at + k:]
+    bg_seqs = cases.background_seqs_for(parts, 3)
+    bg_seqs += [parts[i][:K] for i in range(0, len(parts), 97)] + [parts[i][-K:] for i in range(1, len(parts), 89)]
+    bg_keys = np_oracle.canonical_key_set(bg_seqs, K)
+    uniq = _long_parts(parts, k)
+    try:
+        ctx.set_option('fold_flags', fold)
+        for internal in (False, True):
+            res = _run(ctx, uniq, k, internal, bg_keys, K)
+            expect_fold = fold and (K == k or (k % 2 == 0 and not internal))
+            assert res.counts['uniform_kernel'] == (2 if expect_fold else 1)
+            assert (res.flags & 4).any()
+            _compare(res, uniq, k, internal, bg_keys, K)
+        res = _run(ctx, uniq, k, False)                                # no background at all
+        assert res.counts['uniform_kernel'] == (2 if fold and k % 2 == 0 else 1)
+        _compare(res, uniq, k, False)
+    finally:
+        ctx.set_option('fold_flags', -1)
+        ctx.set_background(None, 0)
 
 
 @pytest.mark.parametrize('internal', [False, True])

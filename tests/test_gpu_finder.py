@@ -177,3 +177,88 @@ def test_patch_on_the_device_path(scratch_cwd):
                 bg.drop()
     finally:
         nrpcalc_b200.unpatch()
+
+
+def _py_uniquify(parts):
+    """hgraph.py:11-21 + the processing order of 218-223 on strings: (ids, sources) by descending last occurrence"""
+    first, last = {}, {}
+    for i, s in enumerate(parts):
+        s = s.upper()
+        first.setdefault(s, i)
+        last[s] = i
+    order = sorted(last.values(), reverse=True)
+    return [first[parts[i].upper()] for i in order], order
+
+
+@pytest.mark.parametrize('uniform', [True, False])
+def test_device_uniquify_against_python(uniform):
+    """nrp_uniquify: ids, sources, offsets and the gathered (upper-cased) bytes against the dict-based host version on lists with
+    many duplicates, lower-case copies, parts that differ in their last byte only and empty parts."""
+    import ctypes
+    import numpy as np
+    rnd = random.Random(11)
+    ctx = hgraph._context()
+    for n, dup in ((1, 0.0), (5000, 0.0), (20000, 0.4), (3000, 0.95)):
+        base = cases.random_parts(n, 60, n) if uniform else cases.buffer_to_list(*cases.random_varlen_buffer(n, 0 if n > 1 else 5, 90, n))
+        parts = []
+        for i in range(n):
+            r = rnd.random()
+            if parts and r < dup:
+                s = parts[rnd.randrange(len(parts))]
+                s = s.lower() if rnd.random() < 0.3 else s
+            elif parts and r < dup + 0.02 and len(parts[-1]) > 1:
+                s = parts[-1][:-1] + ('A' if parts[-1][-1].upper() != 'A' else 'C')      # equal but for the last byte
+            else:
+                s = base[i]
+            parts.append(s)
+        blob = np.frombuffer(''.join(parts).encode(), dtype=np.uint8)
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum([len(s) for s in parts], out=offsets[1:])
+        if uniform:
+            ids, source, new_off, dev, status, longest = ctx.uniquify(blob, None, 60)
+        else:
+            ids, source, new_off, dev, status, longest = ctx.uniquify(blob, offsets, 0)
+        want_ids, want_src = _py_uniquify(parts)
+        assert status == 0 and longest == max(len(s) for s in parts)
+        assert ids.tolist() == want_ids and source.tolist() == want_src
+        assert np.diff(new_off).tolist() == [len(parts[i]) for i in want_src]
+        import torch
+        gathered = torch.empty(int(new_off[-1]), dtype=torch.uint8, device='cuda:{}'.format(ctx.device))
+        if gathered.numel():
+            ctypes.CDLL('libcudart.so.12').cudaMemcpy(ctypes.c_void_p(gathered.data_ptr()), ctypes.c_void_p(dev), ctypes.c_size_t(gathered.numel()), 3)
+        assert gathered.cpu().numpy().tobytes().decode() == ''.join(parts[i].upper() for i in want_src)
+    ids, source, new_off, dev, status, longest = ctx.uniquify(np.frombuffer(b'ACGTNNACGTAC', dtype=np.uint8), None, 6)
+    assert status == 1 and ids.tolist() == [1, 0]
+
+
+@pytest.mark.parametrize('case', [c for c in GOLDEN_CASES if c['parts']], ids=[c['name'] for c in GOLDEN_CASES if c['parts']])
+def test_finder_packed_matches_golden(case, scratch_cwd):
+    """The packed entry (device uniquify -> build on the gathered buffer -> array tail) against the reference's toolboxes."""
+    import numpy as np
+    from nrpcalc_b200 import packed
+    bg = _background(case)
+    blob = ''.join(case['parts']).encode()
+    offsets = np.zeros(len(case['parts']) + 1, dtype=np.int64)
+    np.cumsum([len(s) for s in case['parts']], out=offsets[1:])
+    short = any(len(s) <= case['Lmax'] for s in case['parts'])
+    for vc, by_seed in case['toolbox'].items():
+        for seed, expected_ids in by_seed.items():
+            random.seed(int(seed))
+            found = nrpcalc_b200.finder_packed(blob, case['Lmax'], offsets=offsets, internal_repeats=case['internal_repeats'], background=bg, vercov=vc)
+            assert list(found.keys()) == expected_ids, (vc, seed)
+            assert all(found[i] == case['parts'][i].upper() for i in expected_ids)
+            assert packed.last_run_info['path'] == ('strings' if short else 'device')
+    if bg is not None:
+        bg.drop()
+
+
+def test_finder_packed_uniform_batch_equals_finder(scratch_cwd):
+    from nrpcalc_b200 import packed
+    parts = cases.random_parts(30000, 100, 77) + cases.random_parts(2000, 100, 77)       # 2000 exact duplicates
+    parts[5] = parts[5].lower()
+    random.seed(3)
+    want = nrpcalc_b200.finder(list(parts), 12, verbose=False)
+    random.seed(3)
+    got = nrpcalc_b200.finder_packed(''.join(parts).encode(), 12, part_len=100)
+    assert packed.last_run_info['path'] == 'device' and packed.last_run_info['unique'] == 30000
+    assert got == want and list(got) == list(want)
