@@ -16,6 +16,11 @@ length = int(os.environ.get('NRP_PROFILE_LEN', '100'))
 buf, off = cases.random_dna_buffer(n, length, 2)
 ids = np.arange(n, dtype=np.uint32)[::-1].copy()
 ctx = _native.Context(0)
+bg = int(os.environ.get('NRP_PROFILE_BG', '0'))          # bp of a random background genome (K = k)
+if bg:
+    from nrpcalc_b200 import encoding
+    gbuf, goff = encoding.join_parts([cases.random_genome(bg, 33)])
+    ctx.bg_build(gbuf, goff, k, install=True)
 ctx.load_parts(buf, off, ids)
 for _ in range(int(os.environ.get('NRP_PROFILE_BUILDS', '2'))):
     ctx.build(k, False, True)
