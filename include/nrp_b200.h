@@ -154,6 +154,19 @@ int nrp_load_parts_uniform(nrp_ctx* ctx, const uint8_t* ascii, int64_t n_parts, 
  * Synchronous: returns when the results are resident on the device.  May be called repeatedly. */
 int nrp_build(nrp_ctx* ctx, int k, int internal_repeats, int want_edges);
 
+/* The same build for parts over ANY byte alphabet and for ANY k >= 1 (the reference has neither limit: utils.py:10 maps 'ATGCU'
+ * to 'TACGA' and leaves every other character alone -- U's complement is A but A's is T --, keys are compared as strings,
+ * hgraph.py:23-94).  Windows are keyed by a seeded 64-bit hash of the canonical string min(w, rc(w)); every equality that changes
+ * a result is verified on the bytes, so the result is exact: *status != 0 reports a hash collision between different strings
+ * (no result was produced -- call again with another seed).  Internal repeats follow hgraph.py:50-69 literally (two equal forward
+ * windows, or the reverse complement of a window among the forward windows).  The background probe applies U -> T first
+ * (kmerSetDB.py:183-184) and takes windows over A/C/G/T; preset_flags (host, n_parts bytes, or NULL) carries exclusions the
+ * host layer decided itself (background keys it holds as strings, K > 32) -- parts with a non-zero preset flag produce no record.
+ * The parts must be upper-case already.  Limits: at most 4096 windows per part, (part, window) must fit 32 bits.  seed: the low
+ * 58 bits seed the hash; the top 6 bits must be 0 (a non-zero value b keeps only b hash bits -- for tests of the collision path).
+ * Results: the same getters as after nrp_build; group keys are hashes (meaningful only for equality). */
+int nrp_build_generic(nrp_ctx* ctx, int k, int internal_repeats, int want_edges, uint64_t seed, const uint8_t* preset_flags, int* status);
+
 int nrp_result_counts(nrp_ctx* ctx, int64_t out[NRP_N_COUNTS]);
 int nrp_result_timings(nrp_ctx* ctx, double out[NRP_N_TIMINGS]);
 /* flags[n_parts]: NRP_FLAG_* bits per part */

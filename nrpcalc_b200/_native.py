@@ -66,6 +66,7 @@ def _declare(lib):
         'nrp_load_parts_streamed': (c_ctx, ptr, ptr, ptr, i64, i32),
         'nrp_load_parts_uniform': (c_ctx, ptr, i64, i32, ptr, i32),
         'nrp_build': (c_ctx, i32, i32, i32),
+        'nrp_build_generic': (c_ctx, i32, i32, i32, ctypes.c_uint64, ptr, ctypes.POINTER(i32)),
         'nrp_result_counts': (c_ctx, ptr),
         'nrp_result_timings': (c_ctx, ptr),
         'nrp_result_flags': (c_ctx, ptr),
@@ -275,6 +276,23 @@ class Context(object):
 
     def build(self, k, internal_repeats, want_edges=True):
         _check(self._lib, self._lib.nrp_build(self._h, int(k), 1 if internal_repeats else 0, 1 if want_edges else 0))
+
+    def build_generic(self, k, internal_repeats, want_edges=True, preset_flags=None, seed=0x9E3779B97F4A7C15, attempts=6, hash_bits=0):
+        """nrp_build_generic: any byte alphabet, any k; windows keyed by a seeded hash, equalities verified on the bytes.  A
+        reported collision between different strings repeats the build with the next seed.  Returns the number of retries.
+        hash_bits > 0 keeps only that many bits of the hash (tests of the collision path)."""
+        if preset_flags is not None:
+            preset_flags = np.ascontiguousarray(preset_flags, dtype=np.uint8)
+            assert preset_flags.size == self.n_parts
+        status = ctypes.c_int(0)
+        for attempt in range(attempts):
+            _check(self._lib, self._lib.nrp_build_generic(self._h, int(k), 1 if internal_repeats else 0, 1 if want_edges else 0,
+                                                          ctypes.c_uint64((seed & ((1 << 58) - 1)) | (int(hash_bits) << 58)), _p(preset_flags),
+                                                          ctypes.byref(status)))
+            if status.value == 0:
+                return attempt
+            seed = (seed * 0xD1342543DE82EF95 + 0x2545F4914F6CDD1D) & 0xFFFFFFFFFFFFFFFF
+        raise NativeError(E_STATE, 'hash collisions under {} different seeds (status {})'.format(attempts, status.value))
 
     # ---- sharded path (device pointers are plain ints, e.g. torch.Tensor.data_ptr()) --------------------
     def set_stream(self, cuda_stream):

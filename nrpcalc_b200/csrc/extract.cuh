@@ -45,11 +45,19 @@ inline bool uni_plan(int64_t L, int k, UniPlan* up) {
   return (int64_t)up->G * L + 64 <= (int64_t)(kUniMaxWords - 8) * 16;
 }
 
-// bit map in front of the background table for the folded probe: bit (top log_bits of the bijective hash of the k-mer)
+// Bit map in front of the background table for the folded probe: a blocked Bloom filter with ONE 32-bit word per probe.  The word
+// is selected by the top (log_bits - 5) bits of the bijective hash of the k-mer, three bit positions inside it by a 32-bit mix of
+// the top 32 hash bits: at >= 16 bits per key a window that is not in the set passes all three with probability ~1e-3.
+__host__ __device__ __forceinline__ uint32_t bg_bit_mask(uint32_t top_hash) {
+  const uint32_t m = top_hash * 0x9E3779B1u;
+  return (1u << (m >> 27)) | (1u << ((m >> 22) & 31u)) | (1u << ((m >> 17) & 31u));
+}
 __global__ void k_bg_bitmap(const uint64_t* keys, int64_t n, BijHash bij, int log_bits, uint32_t* bits) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t bi = (uint32_t)(bij.fwd(keys[i]) >> (bij.n - log_bits));
-    atomicOr(bits + (bi >> 5), 1u << (bi & 31u));
+    const uint64_t h = bij.fwd(keys[i]);
+    const uint32_t top = bij.n >= 32 ? (uint32_t)(h >> (bij.n - 32)) : (uint32_t)(h << (32 - bij.n));     // the hash left-aligned in 32 bits
+    const uint32_t word = log_bits > 5 ? top >> (37 - log_bits) : 0u;
+    atomicOr(bits + word, bg_bit_mask(top));
   }
 }
 
@@ -61,10 +69,11 @@ struct alignas(16) UniSmem {
 
 // FOLD: the exclusion flags that need no grouping are computed HERE instead of in a pass of their own over the parts
 // (k_flag_windows; reference hgraph.py:59-79): a window equal to its own reverse complement (even k, internal_repeats off) and --
-// when the background's K equals k -- background membership of the canonical k-mer (kmerSetDB.py:177-207).  The probe is a bit map
-// indexed by the top bits of the SAME bijective hash the split uses (one load per window; a set bit -- a few percent of the windows --
-// is confirmed in the exact open-addressing table), loaded two windows ahead of its test.  The threads of a part OR their findings
-// in shared memory; after one more CTA barrier a flagged part emits no record and its first thread writes the flag byte.
+// when the background's K equals k -- background membership of the canonical k-mer (kmerSetDB.py:177-207).  The probe is one
+// word of a blocked Bloom filter indexed by the SAME bijective hash the split uses (k_bg_bitmap), loaded three windows ahead of
+// its test; the few windows that pass (~0.1 % + the true hits) are confirmed in the exact open-addressing table after the window
+// loop.  The threads of a part OR their findings in shared memory; after one more CTA barrier a flagged part emits no record and
+// its first thread writes the flag byte.
 struct FoldArgs {
   uint8_t* flags;              // per-part flag bytes (read-modify-write by the part's first thread only)
   const uint32_t* bg_bits;     // nullptr: no background probe
@@ -137,8 +146,11 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split_uniform(const uint8_
 
   uint64_t key[kSplitItems];
   uint32_t val[kSplitItems], dr[kSplitItems];
-  // FOLD: flag bits this thread found; the bit-map word of window e is tested while window e + 2 is computed
-  uint32_t fbits = 0, bw0 = 0, bw1 = 0, bp0 = 0, bp1 = 0;
+  // FOLD: flag bits this thread found.  The bit-map word of window e is tested while window e + 3 is computed (three loads in
+  // flight per thread); a window whose bits are all set becomes a SUSPECT and is confirmed in the exact table after the loop --
+  // inside the loop the confirmation would run for whole warps although a fraction of a percent of the windows need it.
+  uint32_t fbits = 0, suspects = 0;
+  uint32_t bw0 = 0, bw1 = 0, bw2 = 0, bm0 = 1, bm1 = 1, bm2 = 1;     // (word, mask) of the three windows in flight
   const bool probe = FOLD && fold.bg_bits != nullptr;
   auto canon_at = [&](int e) -> uint64_t {                       // canonical k-mer of window e, right-aligned (rare path)
     const uint32_t c = rel + (uint32_t)e;
@@ -148,19 +160,12 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split_uniform(const uint8_
     const uint64_t rc = revcomp2(v, k);
     return v < rc ? v : rc;
   };
-  auto confirm = [&](int e) {                                     // the bit of window e was set: exact test
-    const uint64_t canon = canon_at(e);
-    const bool hit = fold.bg_key_bytes == 4 ? bg_contains<uint32_t>(reinterpret_cast<const uint32_t*>(fold.bg_table), fold.bg_log_slots, canon)
-                                            : bg_contains<uint64_t>(reinterpret_cast<const uint64_t*>(fold.bg_table), fold.bg_log_slots, canon);
-    if (hit) fbits |= kFlagBackground;
-  };
-  // one step of the two-deep probe pipeline: test the word loaded two windows ago, then issue this window's load
+  // one step of the three-deep probe pipeline: test the word loaded three windows ago, then issue this window's load
   auto probe_step = [&](int e, uint32_t top_hash, bool valid) {    // top_hash: the hash left-aligned in 32 bits
-    if (e >= 2 && ((bw0 >> bp0) & 1u)) confirm(e - 2);
-    bw0 = bw1; bp0 = bp1;
-    const uint32_t bi = __funnelshift_rc(top_hash, 0u, 32 - fold.bg_log_bits);
-    bp1 = bi & 31u;
-    bw1 = valid ? __ldg(fold.bg_bits + (bi >> 5)) : 0u;
+    if (e >= 3) suspects |= ((bw0 & bm0) == bm0 ? 1u : 0u) << (e - 3);
+    bw0 = bw1; bm0 = bm1; bw1 = bw2; bm1 = bm2;
+    bm2 = bg_bit_mask(top_hash);
+    bw2 = valid ? __ldg(fold.bg_bits + __funnelshift_rc(top_hash, 0u, 37 - fold.bg_log_bits)) : 0u;
   };
   if (KEY64) {
     const uint32_t x0 = sm.packed[w], x1 = sm.packed[w + 1], x2 = sm.packed[w + 2];
@@ -238,9 +243,18 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split_uniform(const uint8_
     }
   }
   if (FOLD) {
-    if (probe) {                                                 // drain the probe pipeline: windows 6 and 7
-      if ((bw0 >> bp0) & 1u) confirm(kSplitItems - 2);
-      if ((bw1 >> bp1) & 1u) confirm(kSplitItems - 1);
+    if (probe) {                                                 // drain the probe pipeline (windows 5, 6, 7), then confirm the suspects
+      suspects |= ((bw0 & bm0) == bm0 ? 1u : 0u) << (kSplitItems - 3);
+      suspects |= ((bw1 & bm1) == bm1 ? 1u : 0u) << (kSplitItems - 2);
+      suspects |= ((bw2 & bm2) == bm2 ? 1u : 0u) << (kSplitItems - 1);
+      while (suspects != 0) {
+        const int e = __ffs(suspects) - 1;
+        suspects &= suspects - 1u;
+        const uint64_t canon = canon_at(e);
+        const bool hit = fold.bg_key_bytes == 4 ? bg_contains<uint32_t>(reinterpret_cast<const uint32_t*>(fold.bg_table), fold.bg_log_slots, canon)
+                                                : bg_contains<uint64_t>(reinterpret_cast<const uint64_t*>(fold.bg_table), fold.bg_log_slots, canon);
+        if (hit) { fbits |= kFlagBackground; break; }
+      }
     }
     if (fbits != 0) atomicOr(&sm.pflag[pl], fbits);
     __syncthreads();

@@ -30,6 +30,7 @@
 #include "extract.cuh"
 #include "stages.cuh"
 #include "uniquify.cuh"
+#include "generic.cuh"
 
 using namespace nrp;
 
@@ -171,6 +172,10 @@ struct nrp_ctx {
   // device-side uniquify (nrp_uniquify): the caller's parts, the surviving parts in processing order, their ids / sources / offsets
   DevBuf uq_in, uq_off, uq_out, uq_rep, uq_run_first, uq_source, uq_ids, uq_lens, uq_newoff, uq_status;
   int64_t uq_n = 0, uq_unique = -1, uq_total = 0, uq_uniform = 0;
+
+  // general path (generic.cuh): records keyed by a seeded 64-bit hash of the canonical window string
+  bool generic = false; uint64_t gen_seed = 0;
+  DevBuf gen_keys, gen_vals, gen_status;
 
   // loaded parts
   DevBuf ascii, off, part_id, tile_first;
@@ -1350,7 +1355,7 @@ int stage_sort_mark(nrp_ctx* c, int k, int64_t n_parts_total, bool mark_repeats,
   if (c->cand_unsorted) {
     // rare: a leaf bucket over the filter capacity or with more suspects than the in-leaf ordering takes (heavy duplicate keys)
     TRY(c->lsd_scratch.ensure(sizeof(uint32_t) * (size_t)lsd_scratch_elems(n)));
-    LsdPlan plan = lsd_plan(2 * k, part_bits + c->j_bits);
+    LsdPlan plan = lsd_plan(c->generic ? 64 : 2 * k, part_bits + c->j_bits);
     KeyT* sk; uint32_t* sv;
     lsd_sort<KeyT, true>((KeyT*)c->cand_keys, c->cand_vals, (KeyT*)c->spare_keys, c->spare_vals, n, plan, c->lsd_scratch.as<uint32_t>(), st, &sk, &sv);
     if (sk != (KeyT*)c->cand_keys) { std::swap(c->cand_keys, c->spare_keys); std::swap(c->cand_vals, c->spare_vals); }
@@ -1545,7 +1550,11 @@ int stage_last_single(nrp_ctx* c, int k, const uint64_t* shared_keys, int64_t n_
     NRP_LAUNCH((k_bg_insert<uint64_t><<<grid, 256, 0, st>>>(shared_keys, n_shared, c->shared_keysB.as<uint64_t>(), log_slots)));
   }
   if (c->n_parts > 0) CU(cudaMemsetAsync(c->last_single.ptr, 0xff, sizeof(int32_t) * (size_t)c->n_parts, st));
-  if (hi > lo)
+  if (hi > lo && c->generic)
+    NRP_LAUNCH((k_generic_last_single<<<grid_for(c->n_parts, 128), 128, 0, st>>>(c->ascii.as<uint8_t>(), c->off.as<int64_t>(), c->flags.as<uint8_t>(),
+                                                                             c->n_parts, k, c->gen_seed, c->shared_keysB.as<uint64_t>(), log_slots,
+                                                                             c->last_single.as<int32_t>())));
+  else if (hi > lo)
     NRP_LAUNCH((k_last_single<<<grid_for(hi - lo, 128), 128, 0, st>>>(c->ascii.as<uint8_t>(), c->off.as<int64_t>(), c->flags.as<uint8_t>(), lo, hi,
                                                                   k, c->shared_keysB.as<uint64_t>(), log_slots, c->last_single.as<int32_t>())));
   CU(cudaGetLastError());
@@ -1601,8 +1610,9 @@ int finish_counts_enqueue(nrp_ctx* c, StageTimer& tm) {
   CU(cudaMemsetAsync(cnt + CNT_FLAGGED, 0, 16, st));
   if (c->n_parts > 0) {
     NRP_LAUNCH((k_count_flagged<<<grid_for(c->n_parts, 256), 256, 0, st>>>(c->flags.as<uint8_t>(), c->n_parts, cnt + CNT_FLAGGED)));
-    NRP_LAUNCH((k_flagged_windows<<<grid_for(c->shard_hi - c->shard_lo, 256), 256, 0, st>>>(c->off.as<int64_t>(), c->flags.as<uint8_t>(),
-                                                                                        c->shard_lo, c->shard_hi, c->k, cnt + CNT_WORK)));
+    if (!c->generic)   // (the general path never emits the records of a part with an internal repeat: nothing to subtract)
+      NRP_LAUNCH((k_flagged_windows<<<grid_for(c->shard_hi - c->shard_lo, 256), 256, 0, st>>>(c->off.as<int64_t>(), c->flags.as<uint8_t>(),
+                                                                                          c->shard_lo, c->shard_hi, c->k, cnt + CNT_WORK)));
   }
   CU(cudaMemcpyAsync(c->h_counters + 26, cnt + CNT_FLAGGED, 16, cudaMemcpyDeviceToHost, st));
   CU(cudaGetLastError());
@@ -1652,6 +1662,7 @@ void begin_job(nrp_ctx* c, int k, size_t key_bytes, int want_edges, bool no_wind
 template <typename KeyT>
 int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   TRY(configure_kernels<KeyT>(c));
+  c->generic = false;
   c->shard_lo = 0; c->shard_hi = c->n_parts; c->shard_tile_lo = 0; c->shard_tiles = c->n_tiles; c->n_owners = 0;
   c->shard_m_max = windows_in_range(c, 0, c->n_parts, k);
   if (c->shard_m_max >= 0xffffe000ll)
@@ -1672,6 +1683,91 @@ int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   c->group_walk_gave_up = false;
   group_counts_ready(c);
   finish_counts_ready(c);
+  TRY(stage_first_window(c, k, tm));
+  TRY(stage_last_single(c, k, c->g_keys.as<uint64_t>(), c->n_groups, 0, c->n_parts, tm));
+  if (want_edges) TRY(stage_edges(c, tm));
+  TRY(finish_timing(c, tm));
+  c->have_result = true;
+  return NRP_OK;
+}
+
+// ---- general path (generic.cuh): any byte alphabet, any k.  *status receives the collision bits (non-zero: repeat with another seed).
+int build_generic_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges, uint64_t seed, const uint8_t* preset_flags, int* status) {
+  TRY(configure_kernels<uint64_t>(c));
+  cudaStream_t st = c->stream;
+  *status = 0;
+  c->generic = true; c->gen_seed = seed;
+  c->shard_lo = 0; c->shard_hi = c->n_parts; c->shard_tile_lo = 0; c->shard_tiles = c->n_tiles; c->n_owners = 0;
+  c->shard_m_max = windows_in_range(c, 0, c->n_parts, k);
+  if (c->shard_m_max >= 0xffffe000ll)
+    return fail(NRP_E_UNSUPPORTED, "%lld records exceed the 32-bit record index of one device", (long long)c->shard_m_max);
+  begin_job(c, k, 8, want_edges);
+  c->fold_pal = c->fold_bg = false;
+  const int64_t max_windows = std::max<int64_t>(1, c->max_len - k + 1);
+  if (max_windows > kGenMaxWindows)
+    return fail(NRP_E_UNSUPPORTED, "the general path takes parts of at most %d windows (longest part: %lld)", kGenMaxWindows, (long long)max_windows);
+  if (c->j_bits == 0 && c->shard_m_max > 0)
+    return fail(NRP_E_UNSUPPORTED, "the general path needs (part, window) to fit 32 bits");
+  c->counts[NRP_C_WINDOWS_MAX] = c->shard_m_max;
+  StageTimer tm(c);
+  tm.begin(NRP_T_FLAGS);
+  TRY(wait_chunks(c));
+  TRY(c->flags.ensure((size_t)c->n_parts + 16));
+  TRY(c->last_single.ensure(sizeof(int32_t) * (size_t)(c->n_parts + 1)));
+  CU(cudaMemsetAsync(c->flags.ptr, 0, (size_t)c->n_parts + 16, st));
+  if (preset_flags && c->n_parts > 0) CU(cudaMemcpyAsync(c->flags.ptr, preset_flags, (size_t)c->n_parts, cudaMemcpyHostToDevice, st));
+  c->flags_set = true;
+  TRY(c->gen_keys.ensure(8 * (size_t)(c->shard_m_max + 16))); TRY(c->gen_vals.ensure(4 * (size_t)(c->shard_m_max + 16)));
+  TRY(c->gen_status.ensure(16));
+  CU(cudaMemsetAsync(c->gen_status.ptr, 0, 16, st));
+  unsigned long long* cnt = c->counters.as<unsigned long long>();
+  CU(cudaMemsetAsync(cnt + CNT_WORK, 0, 8, st));
+  tm.begin(NRP_T_SPLIT1);
+  int64_t n_records = 0;
+  if (c->shard_m_max > 0) {
+    int slots = 64;
+    while (slots < 2 * max_windows) slots <<= 1;
+    GenArgs a;
+    a.ascii = c->ascii.as<uint8_t>(); a.off = c->off.as<int64_t>(); a.n_parts = c->n_parts;
+    a.k = k; a.seed = seed; a.internal_repeats = internal_repeats; a.j_bits = c->j_bits; a.part_base = c->part_base;
+    const bool bg_on = c->bg_n > 0;
+    a.bg_table = c->bg_table.ptr; a.bg_log_slots = c->bg_log_slots; a.bg_key_bytes = c->bg_key_bytes; a.bg_K = bg_on ? c->bg_K : 0;
+    a.flags = c->flags.as<uint8_t>();
+    a.out_keys = c->gen_keys.as<uint64_t>(); a.out_vals = c->gen_vals.as<uint32_t>(); a.n_out = cnt + CNT_WORK;
+    a.status = c->gen_status.as<uint32_t>();
+    a.max_windows = (int)max_windows; a.table_slots = slots;
+    const size_t smem = 16 * (size_t)max_windows + 4 * (size_t)slots + (size_t)max_windows + 16;
+    CU(cudaFuncSetAttribute(k_generic_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::min<int64_t>(c->n_parts, (int64_t)c->n_sms * 16);
+    NRP_LAUNCH((k_generic_extract<<<grid, kGenThreads, smem, st>>>(a)));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_counters + 60, cnt + CNT_WORK, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_counters + 61, c->gen_status.ptr, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    n_records = (int64_t)c->h_counters[60];
+    if ((uint32_t)c->h_counters[61] != 0) { *status = (int)(uint32_t)c->h_counters[61]; tm.finish(c->timings); return NRP_OK; }
+  }
+  BulkSource<uint64_t> src;
+  TRY((flat_source<uint64_t>(c, c->gen_keys.as<uint64_t>(), c->gen_vals.as<uint32_t>(), n_records, &src)));
+  TRY((stage_bulk<uint64_t>(c, std::min(k, 32), src, tm)));
+  TRY((stage_sort_mark<uint64_t>(c, std::min(k, 32), c->n_parts, false, tm)));
+  if (c->n_cand > 1) {
+    NRP_LAUNCH((k_generic_verify<<<grid_for(c->n_cand, 256), 256, 0, st>>>(c->ascii.as<uint8_t>(), c->off.as<int64_t>(), (const uint64_t*)c->cand_keys,
+                                                                      c->cand_vals, c->n_cand, k, c->j_bits, c->part_base, c->gen_status.as<uint32_t>())));
+    CU(cudaMemcpyAsync(c->h_counters + 61, c->gen_status.ptr, 4, cudaMemcpyDeviceToHost, st));
+  }
+  TRY((stage_groups<uint64_t>(c, false, tm)));
+  TRY(finish_counts_enqueue(c, tm));
+  CU(cudaStreamSynchronize(st));
+  if (c->n_cand > 1 && (uint32_t)c->h_counters[61] != 0) { *status = (int)(uint32_t)c->h_counters[61]; tm.finish(c->timings); return NRP_OK; }
+  if (group_stage_retry(c)) {
+    TRY((stage_groups<uint64_t>(c, false, tm)));
+    CU(cudaStreamSynchronize(st));
+  }
+  c->group_walk_gave_up = false;
+  group_counts_ready(c);
+  finish_counts_ready(c);
+  c->counts[NRP_C_RECORDS] = n_records;
   TRY(stage_first_window(c, k, tm));
   TRY(stage_last_single(c, k, c->g_keys.as<uint64_t>(), c->n_groups, 0, c->n_parts, tm));
   if (want_edges) TRY(stage_edges(c, tm));
@@ -1960,6 +2056,18 @@ int nrp_build(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   CU(cudaSetDevice(c->device));
   c->have_result = false;
   return k <= 16 ? build_impl<uint32_t>(c, k, internal_repeats, want_edges) : build_impl<uint64_t>(c, k, internal_repeats, want_edges);
+}
+
+int nrp_build_generic(nrp_ctx* c, int k, int internal_repeats, int want_edges, uint64_t seed, const uint8_t* preset_flags, int* status) {
+  if (!c || !status) return fail(NRP_E_ARG, "null argument");
+  if (!c->have_parts) return fail(NRP_E_STATE, "nrp_load_parts has not been called");
+  if (k < 1) return fail(NRP_E_ARG, "k=%d must be positive", k);
+  if (c->staged_lo != 0 || c->staged_hi != c->n_parts) return fail(NRP_E_STATE, "nrp_build_generic needs all parts staged");
+  CU(cudaSetDevice(c->device));
+  c->have_result = false;
+  const int r = build_generic_impl(c, k, internal_repeats, want_edges, seed, preset_flags, status);
+  if (r != NRP_OK || *status != 0) c->generic = false;
+  return r;
 }
 
 int nrp_ctx_set_stream(nrp_ctx* c, void* cuda_stream) {

@@ -26,7 +26,7 @@ def join_parts(seqs):
     try:
         blob = ''.join(seqs).encode('ascii')
     except UnicodeEncodeError:
-        raise ValueError('parts must be ASCII strings over A, C, G, T')
+        raise ValueError('parts must be ASCII strings (the reference compares parts character by character; text outside ASCII has no byte form here)')
     return np.frombuffer(blob, dtype=np.uint8), offsets
 
 

@@ -98,11 +98,11 @@ def _world_size():
 
 
 def _device_build(ctx, structure, ascii_buf, offsets, global_p, ids, k, internal_repeats, want_edges=False, allow_sharding=False,
-                  device_ptr=None):
+                  device_ptr=None, generic=False, preset=None):
     """One build over parts that all have length >= k; global_p maps local index -> processing rank.
     With an initialised torch.distributed group of more than one rank the build is hash-sharded across the ranks
     (nrpcalc_b200.sharded); every rank receives the same result."""
-    if allow_sharding and _world_size() > 1:
+    if allow_sharding and not generic and _world_size() > 1:
         from . import sharded
         ops = getattr(ctx, '_sharded_ops', None)           # one per context: the peer mappings of the exchange live in it
         if ops is None:
@@ -118,7 +118,11 @@ def _device_build(ctx, structure, ascii_buf, offsets, global_p, ids, k, internal
         structure.edges = None if out['edges'] is None else tuple(e.copy() for e in out['edges'])     # views of staging buffers
     else:
         ctx.load_parts(ascii_buf, offsets, ids if want_edges else None, device_ptr=device_ptr)
-        ctx.build(k, internal_repeats, want_edges=want_edges)
+        if generic:          # any alphabet / k > 32: hashed window strings, equalities verified on the bytes (nrp_build_generic)
+            structure.counts['generic_retries'] += ctx.build_generic(k, internal_repeats, want_edges=want_edges, preset_flags=preset)
+            structure.counts['generic_builds'] += 1
+        else:
+            ctx.build(k, internal_repeats, want_edges=want_edges)
         res = ctx.fetch(want_keys=False)
         flags, indptr, members, first_window, last_single = res.flags, res.indptr, res.members, res.first_window, res.last_single
         structure.records += res.counts['records']
@@ -149,12 +153,35 @@ def _install_background(ctx, background, longest_part):
     if background.K <= longest_part and not background.ALIVE:
         raise RuntimeError('kmerSetDB was closed or dropped')      # surfaces from multicheck, kmerSetDB.py:97-102
     keys, _ = background.device_keys()
-    if background.K > 32:
-        if keys.size or len(background):
-            raise ValueError('backgrounds with Lmax > 31 are not supported by the device path')
+    if background.K > 32:                                          # keys wider than 64 bits: the host answers (preset flags)
         ctx.set_background(None, 0)
     else:
         ctx.set_background(keys, background.K)
+
+
+_ACGTU = np.zeros(256, dtype=bool)
+_ACGTU[np.frombuffer(b'ACGTU', dtype=np.uint8)] = True
+
+
+def _host_background_flags(background, seqs, ascii_buf, offsets):
+    """Background exclusions only the host can decide (kmerSetDB.py:177-207 on strings): every part when the background's keys
+    are wider than 64 bits (K > 32), else the parts with characters other than A/C/G/T/U when the store holds such keys.  None
+    when there is nothing to decide."""
+    if background is None or not background.ALIVE or len(background) == 0:
+        return None
+    everything = background.K > 32
+    if not everything and not background.has_verbatim_keys():
+        return None
+    lengths = np.diff(offsets)
+    todo = lengths >= background.K
+    if not everything:
+        other = np.concatenate(([0], np.cumsum(~_ACGTU[ascii_buf])))
+        todo &= (other[offsets[1:]] - other[offsets[:-1]]) > 0
+    flags = np.zeros(len(seqs), dtype=np.uint8)
+    for p in np.nonzero(todo)[0].tolist():
+        if seqs[p] in background:
+            flags[p] = _native.FLAG_BACKGROUND
+    return flags
 
 
 def repeat_structure_device(ctx, device_ptr, offsets, ids, longest_part, background, homology, internal_repeats, want_edges=False):
@@ -180,15 +207,17 @@ def repeat_structure(parts, background, homology, internal_repeats, ctx=None, wa
     ids = np.fromiter((pid for pid, _ in parts), dtype=np.uint32, count=n)
     seqs = [seq for _, seq in parts]
     ascii_buf, offsets = encoding.join_parts(seqs)
-    if not encoding.all_acgt(ascii_buf):
-        raise ValueError('nrpcalc_b200 supports parts over A, C, G, T only (see DESIGN.md, documented deviation)')
     lengths = np.diff(offsets)
     structure = RepeatStructure(n)
-
     _install_background(ctx, background, int(lengths.max()) if n else 0)
+    # The 2-bit kernels take A/C/G/T and k <= 32.  Everything else the reference accepts -- RNA (U's complement is A, utils.py:10),
+    # other symbols, longer windows, backgrounds with K > 32 -- goes through the general path (csrc/generic.cuh): same results.
+    wide_background = background is not None and background.ALIVE and background.K > 32 and len(background) > 0
+    other_alphabet = not encoding.all_acgt(ascii_buf)
+    preset = _host_background_flags(background, seqs, ascii_buf, offsets) if (other_alphabet or wide_background) else None
 
-    if homology > 32 and n and int(lengths.max()) > 32:
-        raise ValueError('Lmax > 31 needs keys wider than 64 bits, which the device path does not support')
+    def is_generic(k_class):
+        return other_alphabet or wide_background or k_class > 32
 
     # parts with len >= k: ordinary k-windows.  Shorter parts are keyed by their whole string (utils.py:37-40):
     # one build per distinct length l < k with k' = l (a string of length l can only equal another of length l).
@@ -196,7 +225,8 @@ def repeat_structure(parts, background, homology, internal_repeats, ctx=None, wa
     long_mask = lengths >= homology
     try:
         if long_mask.all():
-            _device_build(ctx, structure, ascii_buf, offsets, all_p, ids, homology, internal_repeats, want_edges, allow_sharding=True)
+            _device_build(ctx, structure, ascii_buf, offsets, all_p, ids, homology, internal_repeats, want_edges, allow_sharding=True,
+                          generic=is_generic(homology), preset=preset)
         else:
             classes = [(homology, np.nonzero(long_mask)[0])]
             for short_len in np.unique(lengths[~long_mask]).tolist():
@@ -211,14 +241,13 @@ def repeat_structure(parts, background, homology, internal_repeats, ctx=None, wa
                     else:
                         structure.flags[idx] |= _native.FLAG_PALINDROME
                     continue
-                if k_class > 32:
-                    raise ValueError('parts longer than 32 nt that are shorter than Lmax+1 are not supported')
                 sub_off = np.zeros(idx.size + 1, dtype=np.int64)
                 np.cumsum(lengths[idx], out=sub_off[1:])
                 pieces = [ascii_buf[offsets[i]:offsets[i + 1]] for i in idx.tolist()]
                 sub_ascii = np.concatenate(pieces) if pieces else np.zeros(0, dtype=np.uint8)
                 _device_build(ctx, structure, sub_ascii, sub_off, idx, ids[idx], k_class, internal_repeats, False,
-                              allow_sharding=k_class == homology)
+                              allow_sharding=k_class == homology, generic=is_generic(k_class),
+                              preset=None if preset is None else preset[idx])
     finally:
         ctx.set_background(None, 0)
     return structure, ids

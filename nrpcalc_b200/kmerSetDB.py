@@ -131,6 +131,11 @@ class kmerSetDB(object):
         self._dirty = False
         self._version = 0                              # bumped on every content change (device table refresh)
 
+    def has_verbatim_keys(self):
+        """True when the store holds keys outside the 2-bit form (windows with other characters, whole strings shorter than K,
+        every key when K > 32): only the host can answer membership for them."""
+        return bool(self._extra)
+
     def _merged(self):
         """The sorted key array with every buffered insert merged in."""
         if self._pending:

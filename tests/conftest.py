@@ -16,8 +16,8 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'needs_reference: needs /root/reference (dev container only)')
 
 
-def _load_golden():
-    with open(os.path.join(HERE, 'golden', 'finder_golden.json')) as fh:
+def _load_golden(name='finder_golden.json'):
+    with open(os.path.join(HERE, 'golden', name)) as fh:
         blob = json.load(fh)
     for case in blob['cases']:
         case['parts'] = blob['partsets'][case['partset']]
@@ -25,6 +25,8 @@ def _load_golden():
 
 
 GOLDEN_CASES = _load_golden()
+# inputs outside the 2-bit domain (RNA, other symbols, windows longer than 32 bases): tests/golden/make_golden_general.py
+GOLDEN_GENERAL = _load_golden('finder_golden_general.json')
 
 
 @pytest.fixture(scope='session')

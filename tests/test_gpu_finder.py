@@ -60,9 +60,18 @@ def test_config1_shape(scratch_cwd):
     assert hgraph.last_build_info['counts']['runs'] == 1
 
 
-def test_rejects_other_alphabets(scratch_cwd):
-    with pytest.raises(ValueError, match='A, C, G, T'):
-        nrpcalc_b200.finder(['ACGUACGUACGUACGUAA', 'ACGTNACGTACGTACGTACGT'], 12, verbose=False)
+def test_other_alphabets_take_the_general_path(scratch_cwd):
+    """RNA and other symbols are keyed as the reference keys them (utils.py:10: U's complement is A, an N is its own); text that
+    is not ASCII has no byte form and is refused."""
+    parts = ['ACGUACGUACGUACGUAA', 'ACGTNACGTACGTACGTACGT', 'UUACGUACGUACGUACGU', 'ACGTNACGTACGTACGAAAAA']
+    random.seed(1)
+    found = nrpcalc_b200.finder(list(parts), 12, verbose=False)
+    expect, _ = ref_port.homology_graph(list(parts), None, 13, False)
+    assert set(found) <= set(expect.nodes()) and hgraph.last_build_info['counts']['generic_builds'] == 1
+    graph = hgraph.get_homology_graph(list(parts), None, 13, False, './seq.txt', False)
+    assert list(graph.nodes()) == list(expect.nodes()) and [list(graph[n]) for n in graph.nodes()] == [list(expect[n]) for n in expect.nodes()]
+    with pytest.raises(ValueError, match='ASCII'):
+        nrpcalc_b200.finder(['ACGTACGTACGTACGT\u00e9ACGT', 'ACGTACGTACGTACGTTTTT'], 12, verbose=False)
 
 
 def test_background_built_on_device_matches_host(scratch_cwd):
