@@ -304,7 +304,24 @@ def finder_api_timing(n_parts, length, Lmax, seed):
         os.chdir(cwd)
     info = dict(hgraph.last_build_info)
     run = dict(nrpcalc_b200._finder.last_run_info)
+    # the same job through the packed entry (bytes in, uniquify on the device, no side file): same toolbox, less host work
+    packed_block = None
+    try:
+        from nrpcalc_b200 import packed
+        blob = ''.join(parts).encode('ascii')
+        os.chdir(tempfile.mkdtemp(prefix='nrp_api_'))
+        random.seed(1)
+        t0 = time.perf_counter()
+        found_packed = nrpcalc_b200.finder_packed(blob, Lmax, part_len=length, internal_repeats=False, vercov='nrp2')
+        wall_packed = time.perf_counter() - t0
+        packed_block = {'wall_s': round(wall_packed, 4), 'same_toolbox': found_packed == found and list(found_packed) == list(found)}
+        packed_block.update({k: (round(v, 4) if isinstance(v, float) else v) for k, v in packed.last_run_info.items()})
+    except Exception as exc:                                   # reported, never fatal for the bench line
+        packed_block = {'error': repr(exc)}
+    finally:
+        os.chdir(cwd)
     return {'parts': n_parts, 'part_len': length, 'Lmax': Lmax, 'vercov': 'nrp2', 'wall_s': round(wall, 4), 'toolbox': len(found),
+            'finder_packed': packed_block,
             'kmers': info.get('records'), 'device_ms': info.get('device_ms'),
             'marshal_and_device_call_s': round(info.get('call_s', 0.0), 4), 'clique_replay_and_graph_s': round(info.get('replay_s', 0.0), 4),
             'recovery_s': round(run.get('recovery_s', 0.0), 4), 'checks_sidefiles_output_s': round(max(0.0, wall - run.get('graph_s', 0.0) - run.get('recovery_s', 0.0)), 4),

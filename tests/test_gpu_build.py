@@ -381,11 +381,12 @@ def test_uniform_kernel_folded_flags(ctx, k, K, fold):
         for internal in (False, True):
             res = _run(ctx, uniq, k, internal, bg_keys, K)
             expect_fold = fold and (K == k or (k % 2 == 0 and not internal))
-            assert res.counts['uniform_kernel'] == (2 if expect_fold else 1)
+            # (records of a k-mer too short for the packed word -- k = 6 -- take the byte-position kernel and the separate flag passes)
+            assert res.counts['uniform_kernel'] == ((2 if expect_fold else 1) if res.counts['packed'] else 0)
             assert (res.flags & 4).any()
             _compare(res, uniq, k, internal, bg_keys, K)
         res = _run(ctx, uniq, k, False)                                # no background at all
-        assert res.counts['uniform_kernel'] == (2 if fold and k % 2 == 0 else 1)
+        assert res.counts['uniform_kernel'] == ((2 if fold and k % 2 == 0 else 1) if res.counts['packed'] else 0)
         _compare(res, uniq, k, False)
     finally:
         ctx.set_option('fold_flags', -1)
