@@ -67,6 +67,7 @@ extern "C" {
 #define NRP_C_FALLBACKS     14  /* a fixed region overflowed and the batch was repeated on the exact path */
 #define NRP_C_PACKED        15  /* 1: records travelled as single 64-bit words (k-mer << value bits) | value */
 #define NRP_C_UNIFORM       16  /* 1: the part-aligned extraction kernel ran (parts of one length, packed records); 2: it also computed the palindrome / background flags */
+#define NRP_C_FILTER_WARP   17  /* 1 / 2: the warp-private duplicate filter ran (leaves of <= 800 / <= 400 records on average) */
 #define NRP_N_COUNTS        20
 
 /* indices into nrp_result_timings() (milliseconds, CUDA events on the context's stream) */

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get('NRPCALC_B200_LIB') or os.path.join(_HERE, 'libnrpb200
 N_COUNTS = 20
 N_TIMINGS = 16
 COUNT_NAMES = ('records', 'excluded', 'groups', 'members', 'edges', 'pairs', 'candidates', 'runs', 'buckets',
-               'oversized', 'windows_max', 'key_bytes', 'launches', 'direct', 'fallbacks', 'packed', 'uniform_kernel')
+               'oversized', 'windows_max', 'key_bytes', 'launches', 'direct', 'fallbacks', 'packed', 'uniform_kernel', 'filter_warp')
 TIMING_NAMES = ('total', 'h2d', 'flags', 'histogram', 'split1', 'split2', 'filter', 'sort', 'group', 'edges', 'order')
 
 FLAG_REPEAT, FLAG_PALINDROME, FLAG_BACKGROUND = 1, 2, 4

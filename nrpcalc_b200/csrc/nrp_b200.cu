@@ -28,6 +28,7 @@
 #include "lsd_sort.cuh"
 #include "partition.cuh"
 #include "extract.cuh"
+#include "filter_warp.cuh"
 #include "stages.cuh"
 #include "uniquify.cuh"
 #include "generic.cuh"
@@ -157,6 +158,8 @@ struct nrp_ctx {
   int64_t opt_filter_wide = 1;            // packed leaves of <= 4096 records: three 256-thread CTAs per SM with 16 records per thread (half the
                                           // per-leaf fixed work per record: config 2 filter 0.437 -> 0.381 ms) when few suspects are expected;
                                           // 0 = two 512-thread CTAs
+  int64_t opt_filter_warp = 1;            // packed leaves that average <= 800 records: the warp-private filter (filter_warp.cuh); the level planner
+                                          // then aims at such leaves
   int64_t opt_overlap_tail = 1;           // single-GPU build: the last-unshared-window pass runs on a second stream beside the edge expansion
   int64_t opt_fold_flags = 1;             // part-aligned kernel: palindrome test and (K == k) background probe inside the extraction instead
                                           // of a pass of their own over the parts
@@ -337,6 +340,8 @@ int configure_kernels(nrp_ctx* c) {
                           (int)filter_bloom_smem<8, true, 4096, 2048, 256>()));
   CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1, 1024, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)filter_bloom_smem<8, true, 8192, 4096, 1024>()));
+  CU(cudaFuncSetAttribute((k_filter_warp<KeyT, 512, 96>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 96>))));
+  CU(cudaFuncSetAttribute((k_filter_warp<KeyT, 256, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<256, 64>))));
   CU(cudaFuncSetAttribute((k_split_uniform<false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
   CU(cudaFuncSetAttribute((k_split_uniform<true, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
   CU(cudaFuncSetAttribute((k_split_uniform<false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
@@ -434,6 +439,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "uniform_kernel") c->opt_uniform_kernel = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "fold_flags") c->opt_fold_flags = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "overlap_tail") c->opt_overlap_tail = value < 0 ? 1 : (value > 0 ? 1 : 0);
+  else if (n == "filter_warp") c->opt_filter_warp = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
   return NRP_OK;
 }
@@ -910,11 +916,12 @@ inline uint32_t region_cap(double mean, int slack) {
 }
 
 // number of leaf bits for m records when at most max_bits are available (and at least min_bits must be used)
-int leaf_bits_for(const nrp_ctx* c, int64_t m, int min_bits, int max_bits) {
+int leaf_bits_for(const nrp_ctx* c, int64_t m, int min_bits, int max_bits, int64_t target = 0) {
+  if (target <= 0) target = c->opt_leaf_target;
   int bits = std::max(min_bits, 1);
-  while (bits < max_bits && (m >> bits) > c->opt_leaf_target) ++bits;
+  while (bits < max_bits && (m >> bits) > target) ++bits;
   // the small-leaf target is out of reach: take the fewest bits that still fit the large filter variant
-  if (c->opt_leaf_target == kDefaultLeafTarget && (m >> bits) > kDefaultLeafTarget)
+  if (target == kDefaultLeafTarget && (m >> bits) > kDefaultLeafTarget)
     while (bits > std::max(min_bits, 1) && (m >> (bits - 1)) <= kLargeLeafTarget) --bits;
   return bits;
 }
@@ -935,11 +942,11 @@ LevelPlan plan_levels(const nrp_ctx* c, int64_t m, bool /*direct*/, int /*fixed_
 // Direct path: `pre` hash bits are already consumed by a pre-partitioned source (0 otherwise); the remaining leaf bits are
 // split over one or two levels of at most opt_max_level_bits (<= 9) bits.  cum[i] = bits consumed after level i.
 struct DirectPlan { int bits, pre, n_levels; int r[2]; int cum[2]; uint32_t cap[2]; };
-DirectPlan plan_direct(const nrp_ctx* c, int64_t m, int pre, bool must_split, int bits_hint = 0) {
+DirectPlan plan_direct(const nrp_ctx* c, int64_t m, int pre, bool must_split, int bits_hint = 0, int64_t leaf_target = 0) {
   const int lv = (int)c->opt_max_level_bits;
   DirectPlan p;
   p.pre = pre;
-  p.bits = bits_hint > 0 ? bits_hint : leaf_bits_for(c, m, pre + (must_split ? 1 : 0), std::min(kMaxDirectBits, pre + 2 * lv));
+  p.bits = bits_hint > 0 ? bits_hint : leaf_bits_for(c, m, pre + (must_split ? 1 : 0), std::min(kMaxDirectBits, pre + 2 * lv), leaf_target);
   const int rest = p.bits - pre;
   if (rest <= std::min(lv, 8) || (pre > 0 && rest <= lv)) {
     p.n_levels = 1; p.r[0] = rest; p.r[1] = 0;
@@ -969,24 +976,78 @@ PackFmt pack_format(const nrp_ctx* c, int k, int drop, int owner_bits = 0, uint3
   return PackFmt{make_bijhash(k), std::max(c->vbits, 64 - stored), drop, owner_bits, owner};
 }
 
+// expected fraction of records whose k-mer occurs again: all records of the job over the canonical k-mer space (random DNA)
+inline double shared_fraction_of(const nrp_ctx* c, int k, int64_t m) {
+  const double all_records = c->n_owners > 1 ? (double)m * c->n_owners : (double)m;
+  return k >= 31 ? 0.0 : std::min(1.0, 2.0 * all_records / std::ldexp(1.0, 2 * k));
+}
+
+constexpr int64_t kWarpLeafTarget = 800;     // records per leaf the warp-private filter is planned for (filter_warp.cuh)
+// suspects per leaf the warp-private filter may expect: shared records + bit-map collisions (mean^2 / bits)
+inline double warp_filter_suspects(double mean_leaf, double shared_fraction, int map_bits) {
+  return mean_leaf * shared_fraction * 1.5 + mean_leaf * mean_leaf / (double)map_bits;
+}
+
+// Level plan of a direct build whose records come from the staged parts.  *warp_filter: the leaves are planned small (<= 800
+// records on average) and filtered warp-privately -- when the records pack, the leaf bits allow it and few suspects are expected.
+DirectPlan choose_direct_plan(const nrp_ctx* c, int k, int64_t m_max, bool* packed_out, bool* warp_filter) {
+  *warp_filter = false;
+  if (c->opt_filter_warp && !c->opt_no_bloom && c->opt_leaf_target == kDefaultLeafTarget && c->opt_filter_cap == kFilterCap && m_max > 0) {
+    const double shared = shared_fraction_of(c, k, m_max);
+    for (int64_t target = kWarpLeafTarget; target >= kWarpLeafTarget / 4; target /= 2) {      // smaller leaves when many suspects are expected
+      const DirectPlan small = plan_direct(c, m_max, 0, false, 0, target);
+      const double mean = (double)m_max / (double)((int64_t)1 << small.bits);
+      int64_t total_max = 0;
+      for (int i = 0; i < small.n_levels; ++i) total_max = std::max(total_max, ((int64_t)1 << small.cum[i]) * small.cap[i]);
+      if (mean > (double)target || total_max >= 0xffffe000ll || !packed_fits(c, k, small.cum[0], small.bits)) break;
+      if (warp_filter_suspects(mean, shared, 512 * 32) <= 56.0) {
+        *warp_filter = true; *packed_out = true;
+        return small;
+      }
+    }
+  }
+  const DirectPlan dp = plan_direct(c, m_max, 0, false, 0);
+  *packed_out = packed_fits(c, k, dp.cum[0], dp.bits);
+  return dp;
+}
+
 // Will the first split of a single-GPU build of the staged parts be the part-aligned kernel?  (The same decisions as
 // stage_bulk_direct takes; the extraction kernel then also computes the flags stage_flags left to it.)
 bool uniform_kernel_runs(const nrp_ctx* c, int k) {
   UniPlan up;
   if (!c->opt_direct || !c->opt_uniform_kernel || c->uniform_len <= 0 || c->n_owners > 0 || !uni_plan(c->uniform_len, k, &up)) return false;
   if (c->shard_m_max <= 0) return false;
-  const DirectPlan dp = plan_direct(c, c->shard_m_max, 0, false, 0);
+  bool packed = false, warp_filter = false;
+  const DirectPlan dp = choose_direct_plan(c, k, c->shard_m_max, &packed, &warp_filter);
   int64_t total_max = 0;
   for (int i = 0; i < dp.n_levels; ++i) total_max = std::max(total_max, ((int64_t)1 << dp.cum[i]) * dp.cap[i]);
   if (total_max >= 0xffffe000ll) return false;
-  return packed_fits(c, k, dp.cum[0], dp.bits);
+  return packed;
 }
 
 template <typename KeyT>
 int launch_filter(nrp_ctx* c, bool packed, PackFmt pf, const void* leaf_keys, const uint32_t* leaf_vals, LeafExtents leaves, uint32_t n_leaf, int bits,
-                  int64_t mean_leaf, KeyT* out_keys, uint32_t* out_vals, double shared_fraction = 1.0) {
+                  int64_t mean_leaf, KeyT* out_keys, uint32_t* out_vals, double shared_fraction = 1.0, bool warp_filter = false) {
   cudaStream_t st = c->stream;
   unsigned long long* cnt = c->counters.as<unsigned long long>();
+  if (warp_filter && packed) {
+    // small leaves, one warp each (filter_warp.cuh): as many 8-warp CTAs per SM as shared memory allows
+    uint32_t* over = reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED);
+    uint32_t* unsrt = reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED);
+    const bool tiny = mean_leaf <= 400 && warp_filter_suspects((double)mean_leaf, shared_fraction, 256 * 32) <= 36.0;
+    const size_t smem = tiny ? kFwWarps * sizeof(FwWarp<256, 64>) : kFwWarps * sizeof(FwWarp<512, 96>);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(tiny ? 6 : 4, (216 * 1024) / (smem + 1024)));
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(((int64_t)n_leaf + kFwWarps - 1) / kFwWarps, (int64_t)c->n_sms * per_sm));
+    if (tiny)
+      NRP_LAUNCH((k_filter_warp<KeyT, 256, 64><<<grid, kFwThreads, smem, st>>>((const uint64_t*)leaf_keys, leaves, n_leaf, bits, pf, out_keys, out_vals,
+                                                                          cnt + CNT_CAND, over, unsrt)));
+    else
+      NRP_LAUNCH((k_filter_warp<KeyT, 512, 96><<<grid, kFwThreads, smem, st>>>((const uint64_t*)leaf_keys, leaves, n_leaf, bits, pf, out_keys, out_vals,
+                                                                          cnt + CNT_CAND, over, unsrt)));
+    CU(cudaGetLastError());
+    c->counts[NRP_C_FILTER_WARP] = tiny ? 2 : 1;
+    return NRP_OK;
+  }
   // leaves that average <= 2750 records use the half-size variant (two CTAs per SM); larger ones the full one
   const bool small = mean_leaf <= 2750;
   const uint32_t cap = (uint32_t)std::min<int64_t>(c->opt_filter_cap, small ? kFilterCapSmall : kFilterCap);
@@ -1052,7 +1113,9 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
   const Parts P = parts_view(c);
   unsigned long long* cnt = c->counters.as<unsigned long long>();
   uint32_t* overflow = reinterpret_cast<uint32_t*>(cnt + CNT_OVERFLOW);
-  const DirectPlan dp = plan_direct(c, m_max, prepart ? src.r_done : 0, prepart, prepart ? src.bits_hint : 0);
+  bool chosen_packed = false, warp_filter = false;
+  const DirectPlan dp = from_ascii ? choose_direct_plan(c, k, m_max, &chosen_packed, &warp_filter)
+                                   : plan_direct(c, m_max, prepart ? src.r_done : 0, prepart, prepart ? src.bits_hint : 0);
   const int bits = dp.bits;
   const uint32_t n_leaf = 1u << bits;
   *overflowed = false;
@@ -1061,7 +1124,7 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
   if (total_max >= 0xffffe000ll) { *overflowed = true; return NRP_OK; }   // beyond 32-bit record indices: exact path
   c->counts[NRP_C_BUCKETS] = (int64_t)n_leaf;
   // records as single 64-bit words when hash and value fit (a packed source dictates it, with the bits its regions imply)
-  const bool packed = from_ascii ? packed_fits(c, k, dp.cum[0], bits) : src.packed;
+  const bool packed = from_ascii ? chosen_packed : src.packed;
   const PackFmt pf = from_ascii ? pack_format(c, k, dp.cum[0]) : pack_format(c, k, src.drop, src.owner_bits, (uint32_t)c->my_rank);
   const int64_t n_seg_max = std::max<int64_t>((int64_t)src.n_seg, dp.n_levels > 1 ? ((int64_t)1 << dp.cum[0]) : 0);
   TRY(ensure_record_buffers(c, std::max<int64_t>(total_max, m_max), packed ? 8 : sizeof(KeyT), n_seg_max));
@@ -1161,11 +1224,9 @@ int stage_bulk_direct(nrp_ctx* c, int k, const BulkSource<KeyT>& src, StageTimer
   tm.begin(NRP_T_FILTER);
   if (m_max > 0) {
     if (!counted) NRP_LAUNCH((k_region_total<<<1, 1024, 0, st>>>(c->cursor2.as<uint32_t>(), n_leaf, leaf_cap, cnt + CNT_RECORDS)));
-    // expected fraction of records whose k-mer occurs again: all records of the job over the canonical k-mer space (random DNA)
-    const double all_records = c->n_owners > 1 ? (double)m_max * c->n_owners : (double)m_max;
-    const double shared_fraction = k >= 31 ? 0.0 : std::min(1.0, 2.0 * all_records / std::ldexp(1.0, 2 * k));
+    const double shared_fraction = shared_fraction_of(c, k, m_max);
     TRY((launch_filter<KeyT>(c, packed, pf, leaf_keys, leaf_vals, LeafExtents{nullptr, c->cursor2.as<uint32_t>(), leaf_cap}, n_leaf, bits, m_max >> bits,
-                             (KeyT*)out_keys, out_vals, shared_fraction)));
+                             (KeyT*)out_keys, out_vals, shared_fraction, warp_filter)));
   }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->h_counters, cnt, sizeof(unsigned long long) * CNT_N, cudaMemcpyDeviceToHost, st));

@@ -197,6 +197,35 @@ def test_unpacked_when_key_and_value_exceed_64_bits(ctx):
     _compare(res, uniq, 32, False)
 
 
+@pytest.mark.parametrize('warp', [1, 0])
+def test_warp_private_filter(ctx, warp):
+    """The warp-private duplicate filter (filter_warp.cuh: leaves of a few hundred records, one warp each) against the CTA-per-leaf
+    variants and the oracle: random parts (both map sizes), planted repeats (leaves with more suspects than a warp takes are passed
+    on whole and the global sort runs), 32-bit and 64-bit keys, internal repeats on and off, a background."""
+    try:
+        ctx.set_option('filter_warp', warp)
+        seen = set()
+        for n, length, k, internal in ((20000, 100, 17, False), (60000, 100, 17, False), (9000, 100, 13, False), (30000, 60, 16, True)):
+            uniq = ref_port.uniquify(cases.random_parts(n, length, n + k))
+            res = _run(ctx, uniq, k, internal)
+            seen.add(res.counts['filter_warp'])
+            assert (res.counts['filter_warp'] != 0) == bool(warp)
+            _compare(res, uniq, k, internal)
+        if warp:
+            assert seen <= {1, 2} and seen
+        planted = _long_parts(cases.planted_parts(3000, 12) + cases.random_parts(12000, 100, 13), 17)
+        res = _run(ctx, planted, 17, False)
+        _compare(res, planted, 17, False)
+        res = _run(ctx, planted, 17, True)
+        _compare(res, planted, 17, True)
+        bg_keys = np_oracle.canonical_key_set(cases.background_seqs_for([s for _, s in planted[:400]], 3), 17)
+        res = _run(ctx, planted, 17, False, bg_keys, 17)
+        _compare(res, planted, 17, False, bg_keys, 17)
+    finally:
+        ctx.set_option('filter_warp', -1)
+        ctx.set_background(None, 0)
+
+
 def test_direct_overflow_falls_back_to_exact(ctx):
     """A k-mer shared by thousands of parts overflows its fixed region: the batch is repeated on the exact path."""
     import random
