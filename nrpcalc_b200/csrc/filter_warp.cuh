@@ -19,8 +19,8 @@
 
 namespace nrp {
 
-constexpr int kFwThreads = 256;
-constexpr int kFwWarps = kFwThreads / 32;
+constexpr int kFwWarps = 10;               // warps per CTA: three CTAs of ten warps fit an SM with the 7.2 KB slices (30 leaves in flight)
+constexpr int kFwThreads = kFwWarps * 32;
 
 template <int MAPW, int SUSP>
 struct alignas(16) FwWarp {
@@ -61,52 +61,67 @@ __global__ void __launch_bounds__(kFwThreads) k_filter_warp(const uint64_t* __re
   for (int i = lane; i < kSlots; i += 32) { S.table[i] = ~0ull; S.marked[i] = 0; }
   __syncwarp();
   const uint32_t n_warps = gridDim.x * kFwWarps;
-  for (uint32_t leaf = blockIdx.x * kFwWarps + wib; leaf < n_leaf; leaf += n_warps) {
-    uint32_t lo, n;
-    leaves.get(leaf, n_leaf, lo, n);
+  // the bits that tell the k-mers of a leaf apart usually fit 32 bits and lie in one word of the record: one shift, one mask
+  const int rem_bits = pf.n_eff() - leaf_bits;
+  const bool rem32 = rem_bits <= 32 && (vbits >= 32 || vbits + rem_bits <= 32);
+  const int rem_shift = vbits >= 32 ? vbits - 32 : vbits;
+  const uint32_t rem_mask32 = rem_bits >= 32 ? 0xffffffffu : ((1u << rem_bits) - 1u);
+  auto map_bit = [&](uint64_t r) -> uint32_t {
+    const uint32_t x = rem32 ? (((vbits >= 32 ? (uint32_t)(r >> 32) : (uint32_t)r) >> rem_shift) & rem_mask32) : fold_rem(r);
+    return (x * 0x9E3779B1u) >> (32 - kLogBits);
+  };
+  uint32_t lo, n, lo_next, n_next;
+  leaves.get(blockIdx.x * kFwWarps + wib, n_leaf, lo, n);
+  for (uint32_t leaf = blockIdx.x * kFwWarps + wib; leaf < n_leaf; leaf += n_warps, lo = lo_next, n = n_next) {
+    leaves.get(leaf + n_warps, n_leaf, lo_next, n_next);         // the next leaf's extent: its load latency hides behind this leaf
     if (n < 2) continue;                                         // uniform across the warp
     const uint64_t* src = recs + lo;
-    // pass 1: every record sets its bit in map A; a record that finds it set also sets it in map B
-    for (uint32_t i0 = 0; i0 < n; i0 += 128) {
-      uint64_t r[4];
+    auto load4 = [&](uint32_t i0, uint64_t (&r)[4]) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const uint32_t i = i0 + q * 32 + lane;
         r[q] = i < n ? __ldg(src + i) : 0ull;
       }
+    };
+    // pass 1: every record sets its bit in map A; a record that finds it set also sets it in map B.  The loads of the next 128
+    // records are issued before the current ones are used (eight 8-byte loads per lane in flight).
+    uint64_t cur[4], nxt[4];
+    load4(0, cur);
+    for (uint32_t i0 = 0; i0 < n; i0 += 128) {
+      load4(i0 + 128, nxt);                                      // past the end: no load is issued
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (i0 + q * 32 + lane < n) {
-          const uint32_t bit = (fold_rem(r[q]) * 0x9E3779B1u) >> (32 - kLogBits);
+          const uint32_t bit = map_bit(cur[q]);
           const uint32_t w = bit >> 5, m = 1u << (bit & 31u);
           if (atomicOr(&S.map_a[w], m) & m) atomicOr(&S.map_b[w], m);
         }
       }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
     }
+    load4(0, cur);                                               // pass 2 reads the leaf again (L1 / L2): issued before the warp meets
     __syncwarp();
     // pass 2: suspects = records whose bit is set in map B (both records of every shared k-mer, plus the few that share a bit)
     uint32_t c1 = 0;                                             // uniform
     for (uint32_t i0 = 0; i0 < n; i0 += 128) {
-      uint64_t r[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t i = i0 + q * 32 + lane;
-        r[q] = i < n ? __ldg(src + i) : 0ull;
-      }
+      load4(i0 + 128, nxt);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         bool sus = false;
         if (i0 + q * 32 + lane < n) {
-          const uint32_t bit = (fold_rem(r[q]) * 0x9E3779B1u) >> (32 - kLogBits);
+          const uint32_t bit = map_bit(cur[q]);
           sus = (S.map_b[bit >> 5] >> (bit & 31u)) & 1u;
         }
         const uint32_t ballot = __ballot_sync(0xffffffffu, sus);
         if (ballot != 0) {
           const uint32_t pos = c1 + __popc(ballot & lt);
-          if (sus && pos < (uint32_t)SUSP) S.c_recs[pos] = r[q];
+          if (sus && pos < (uint32_t)SUSP) S.c_recs[pos] = cur[q];
           c1 += __popc(ballot);
         }
       }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
     }
     __syncwarp();
     clear_maps();                                                // last use of the maps: clean for the next leaf

@@ -1036,7 +1036,7 @@ int launch_filter(nrp_ctx* c, bool packed, PackFmt pf, const void* leaf_keys, co
     uint32_t* unsrt = reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED);
     const bool tiny = mean_leaf <= 400 && warp_filter_suspects((double)mean_leaf, shared_fraction, 256 * 32) <= 36.0;
     const size_t smem = tiny ? kFwWarps * sizeof(FwWarp<256, 64>) : kFwWarps * sizeof(FwWarp<512, 96>);
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(tiny ? 6 : 4, (216 * 1024) / (smem + 1024)));
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (228 * 1024) / (smem + 1024)));      // 1 KB per CTA is reserved by the system
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(((int64_t)n_leaf + kFwWarps - 1) / kFwWarps, (int64_t)c->n_sms * per_sm));
     if (tiny)
       NRP_LAUNCH((k_filter_warp<KeyT, 256, 64><<<grid, kFwThreads, smem, st>>>((const uint64_t*)leaf_keys, leaves, n_leaf, bits, pf, out_keys, out_vals,
