@@ -131,6 +131,7 @@ constexpr int kMaxDirectBits = 2 * kMaxLevelBits;           // direct path: two 
 
 }  // namespace
 
+constexpr int64_t kWarpLeafTarget = 800;     // records per leaf the warp-private filter is planned for (filter_warp.cuh)
 struct nrp_ctx {
   int device = 0;
   int n_sms = 148;
@@ -158,8 +159,10 @@ struct nrp_ctx {
   int64_t opt_filter_wide = 1;            // packed leaves of <= 4096 records: three 256-thread CTAs per SM with 16 records per thread (half the
                                           // per-leaf fixed work per record: config 2 filter 0.437 -> 0.381 ms) when few suspects are expected;
                                           // 0 = two 512-thread CTAs
-  int64_t opt_filter_warp = 1;            // packed leaves that average <= 800 records: the warp-private filter (filter_warp.cuh); the level planner
+  int64_t opt_filter_warp = 2;            // (2 = k_filter_warp2, 1 = the first version, 0 = off) packed leaves that average <= 800 records: the warp-private filter (filter_warp.cuh); the level planner
                                           // then aims at such leaves
+  int64_t opt_warp_leaf_target = kWarpLeafTarget;     // mean records per leaf the planner aims at for the warp-private filter (halved while too many suspects
+                                          // are expected); <= 400 selects its small-map variant (4.2 KB per warp: 50 warps per SM instead of 30)
   int64_t opt_overlap_tail = 1;           // single-GPU build: the last-unshared-window pass runs on a second stream beside the edge expansion
   int64_t opt_fold_flags = 1;             // part-aligned kernel: palindrome test and (K == k) background probe inside the extraction instead
                                           // of a pass of their own over the parts
@@ -342,6 +345,10 @@ int configure_kernels(nrp_ctx* c) {
                           (int)filter_bloom_smem<8, true, 8192, 4096, 1024>()));
   CU(cudaFuncSetAttribute((k_filter_warp<KeyT, 512, 96>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 96>))));
   CU(cudaFuncSetAttribute((k_filter_warp<KeyT, 256, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<256, 64>))));
+  CU(cudaFuncSetAttribute((k_filter_warp2<KeyT, 512, 96, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 96>))));
+  CU(cudaFuncSetAttribute((k_filter_warp2<KeyT, 512, 96, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 96>))));
+  CU(cudaFuncSetAttribute((k_filter_warp2<KeyT, 256, 64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<256, 64>))));
+  CU(cudaFuncSetAttribute((k_filter_warp2<KeyT, 256, 64, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<256, 64>))));
   CU(cudaFuncSetAttribute((k_split_uniform<false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
   CU(cudaFuncSetAttribute((k_split_uniform<true, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
   CU(cudaFuncSetAttribute((k_split_uniform<false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
@@ -439,7 +446,8 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "uniform_kernel") c->opt_uniform_kernel = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "fold_flags") c->opt_fold_flags = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "overlap_tail") c->opt_overlap_tail = value < 0 ? 1 : (value > 0 ? 1 : 0);
-  else if (n == "filter_warp") c->opt_filter_warp = value < 0 ? 1 : (value > 0 ? 1 : 0);
+  else if (n == "filter_warp") c->opt_filter_warp = value < 0 ? 2 : std::min<int64_t>(value, 2);
+  else if (n == "warp_leaf_target") c->opt_warp_leaf_target = value <= 0 ? kWarpLeafTarget : std::min<int64_t>(value, kWarpLeafTarget);
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
   return NRP_OK;
 }
@@ -982,7 +990,6 @@ inline double shared_fraction_of(const nrp_ctx* c, int k, int64_t m) {
   return k >= 31 ? 0.0 : std::min(1.0, 2.0 * all_records / std::ldexp(1.0, 2 * k));
 }
 
-constexpr int64_t kWarpLeafTarget = 800;     // records per leaf the warp-private filter is planned for (filter_warp.cuh)
 // suspects per leaf the warp-private filter may expect: shared records + bit-map collisions (mean^2 / bits)
 inline double warp_filter_suspects(double mean_leaf, double shared_fraction, int map_bits) {
   return mean_leaf * shared_fraction * 1.5 + mean_leaf * mean_leaf / (double)map_bits;
@@ -994,7 +1001,7 @@ DirectPlan choose_direct_plan(const nrp_ctx* c, int k, int64_t m_max, bool* pack
   *warp_filter = false;
   if (c->opt_filter_warp && !c->opt_no_bloom && c->opt_leaf_target == kDefaultLeafTarget && c->opt_filter_cap == kFilterCap && m_max > 0) {
     const double shared = shared_fraction_of(c, k, m_max);
-    for (int64_t target = kWarpLeafTarget; target >= kWarpLeafTarget / 4; target /= 2) {      // smaller leaves when many suspects are expected
+    for (int64_t target = c->opt_warp_leaf_target; target >= 100; target /= 2) {      // smaller leaves when many suspects are expected
       const DirectPlan small = plan_direct(c, m_max, 0, false, 0, target);
       const double mean = (double)m_max / (double)((int64_t)1 << small.bits);
       int64_t total_max = 0;
@@ -1038,12 +1045,20 @@ int launch_filter(nrp_ctx* c, bool packed, PackFmt pf, const void* leaf_keys, co
     const size_t smem = tiny ? kFwWarps * sizeof(FwWarp<256, 64>) : kFwWarps * sizeof(FwWarp<512, 96>);
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (228 * 1024) / (smem + 1024)));      // 1 KB per CTA is reserved by the system
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(((int64_t)n_leaf + kFwWarps - 1) / kFwWarps, (int64_t)c->n_sms * per_sm));
-    if (tiny)
+#define NRP_FW2(MAPW_, SUSP_, VHI_)                                                                                                              \
+  NRP_LAUNCH((k_filter_warp2<KeyT, MAPW_, SUSP_, VHI_><<<grid, kFwThreads, smem, st>>>((const uint64_t*)leaf_keys, leaves, n_leaf, bits, pf, out_keys, \
+                                                                                      out_vals, cnt + CNT_CAND, over, unsrt)))
+    const bool vhi = pf.vbits >= 32;
+    if (c->opt_filter_warp >= 2) {       // record pairs, check-free batches, per-lane suspect masks
+      if (tiny) { if (vhi) NRP_FW2(256, 64, true); else NRP_FW2(256, 64, false); }
+      else { if (vhi) NRP_FW2(512, 96, true); else NRP_FW2(512, 96, false); }
+    } else if (tiny)
       NRP_LAUNCH((k_filter_warp<KeyT, 256, 64><<<grid, kFwThreads, smem, st>>>((const uint64_t*)leaf_keys, leaves, n_leaf, bits, pf, out_keys, out_vals,
                                                                           cnt + CNT_CAND, over, unsrt)));
     else
       NRP_LAUNCH((k_filter_warp<KeyT, 512, 96><<<grid, kFwThreads, smem, st>>>((const uint64_t*)leaf_keys, leaves, n_leaf, bits, pf, out_keys, out_vals,
                                                                           cnt + CNT_CAND, over, unsrt)));
+#undef NRP_FW2
     CU(cudaGetLastError());
     c->counts[NRP_C_FILTER_WARP] = tiny ? 2 : 1;
     return NRP_OK;

@@ -37,6 +37,10 @@
 #define NRP_V_LATE 1         // ... and their results are consumed after the reorder stores: the round trip to L2 overlaps both
 #endif
 
+#ifndef NRP_V_FLUSH_ILP
+#define NRP_V_FLUSH_ILP 1    // split_flush: eight records per thread with their shared-memory loads issued together
+#endif
+
 namespace nrp {
 
 constexpr int kSplitThreads = kTileThreads;     // 512
@@ -160,6 +164,42 @@ template <typename KeyT, bool PACKED = false>
 __device__ __forceinline__ void split_flush(SplitSmem<KeyT, PACKED>& s, KeyT* out_keys, uint32_t* out_vals, const PeerBuffers* peers = nullptr,
                                             int peer_shift = 0) {
   const uint32_t total = s.total;
+#if NRP_V_FLUSH_ILP
+  // eight records per thread with their shared-memory loads issued together: digit, then the digit's displacement, then the record
+  // (as a loop over i += blockDim the three dependent loads of ONE record were all a thread had in flight)
+  uint32_t dl[kSplitItems];
+#pragma unroll
+  for (int e = 0; e < kSplitItems; ++e) {
+    const uint32_t i = threadIdx.x + (uint32_t)e * kSplitThreads;
+    dl[e] = i < total ? (uint32_t)s.dig[i] : 0u;
+  }
+#pragma unroll
+  for (int e = 0; e < kSplitItems; ++e) {
+    const uint32_t i = threadIdx.x + (uint32_t)e * kSplitThreads;
+    const uint32_t d = dl[e];
+    dl[e] = i < total ? s.delta[d] : kNoSpace;
+  }
+  if (peers) {                                     // digit d lives in its owner's receive buffer (peer store over NVLink)
+#pragma unroll
+    for (int e = 0; e < kSplitItems; ++e) {
+      const uint32_t i = threadIdx.x + (uint32_t)e * kSplitThreads;
+      if (dl[e] == kNoSpace) continue;
+      const uint32_t o = (uint32_t)s.dig[i] >> peer_shift;
+      const uint32_t dst = i + dl[e] - (uint32_t)kSplitTile;
+      reinterpret_cast<KeyT*>(peers->keys[o])[dst] = s.keys[i];
+      if (!PACKED) peers->vals[o][dst] = s.vals[i];
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < kSplitItems; ++e) {
+      const uint32_t i = threadIdx.x + (uint32_t)e * kSplitThreads;
+      if (dl[e] == kNoSpace) continue;
+      const uint32_t dst = i + dl[e] - (uint32_t)kSplitTile;
+      out_keys[dst] = s.keys[i];
+      if (!PACKED) out_vals[dst] = s.vals[i];
+    }
+  }
+#else
   for (uint32_t i = threadIdx.x; i < total; i += kSplitThreads) {
     const uint32_t d = s.dig[i];
     const uint32_t dl = s.delta[d];
@@ -174,6 +214,7 @@ __device__ __forceinline__ void split_flush(SplitSmem<KeyT, PACKED>& s, KeyT* ou
       if (!PACKED) out_vals[dst] = s.vals[i];
     }
   }
+#endif
 }
 
 // ---- histogram of leaf buckets straight from the part buffer (exact path) ---------------------------------
