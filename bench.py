@@ -440,7 +440,7 @@ def main():
         else:
             ctx.load_parts(host_ascii.numpy(), off, ids, chunks=args.h2d_chunks)
         t1 = time.perf_counter()
-        ctx.build(k, cfg['internal_repeats'], want_edges)
+        ctx.build(k, cfg['internal_repeats'], want_edges, early_fetch=True)       # as nrpcalc_b200.hgraph calls it: the result is fetched next
         t2 = time.perf_counter()
         res = ctx.fetch(want_keys=True)
         dt = time.perf_counter() - t0
@@ -472,7 +472,7 @@ def main():
     algo = algorithmic_bytes(int(off[-1]), m, counts['key_bytes'], counts['packed'])
     stage_avg = {name: stage_ms.get(name, 0.0) / args.steps for name in algo}
     dominant = max(stage_avg, key=lambda name: stage_avg[name])
-    kernel_of = {'histogram': 'k_hist_from_ascii', 'split1': 'k_split_uniform' if counts.get('uniform_kernel') else 'k_split_from_ascii', 'split2': 'k_split_from_records', 'filter': 'k_filter_bloom',
+    kernel_of = {'histogram': 'k_hist_from_ascii', 'split1': 'k_split_uniform' if counts.get('uniform_kernel') else 'k_split_from_ascii', 'split2': 'k_split_from_records', 'filter': {0: 'k_filter_bloom', 1: 'k_filter_warp', 2: 'k_filter_warp', 3: 'k_filter_warp'}.get(counts.get('filter_warp', 0), 'k_filter_bloom'),
                  'flags': 'k_flag_windows'}
     achieved = algo[dominant] / (stage_avg[dominant] * 1e-3) / 1e9
     traffic = None
@@ -508,7 +508,7 @@ def main():
                     'h2d_chunks': args.h2d_chunks,
                     'path': 'C ABI, page-locked host buffers: ' + ('nrp_load_parts_uniform (no offsets array; {} piece(s), copies only enqueued when > 1)'.format(args.h2d_chunks)
                                                                   if uniform_entry else ('nrp_load_parts_streamed' if args.h2d_chunks > 1 else 'nrp_load_parts')) +
-                            ' + nrp_build + nrp_result_host'},
+                            ' + nrp_build (early_fetch: results that are final after the grouping stage travel beside the rest of the build) + nrp_result_host'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
             'stage_ms': {name: v / args.steps for name, v in stage_ms.items()},
             'result': {name: counts[name] for name in ('records', 'excluded', 'groups', 'members', 'edges', 'candidates', 'runs', 'buckets', 'oversized',

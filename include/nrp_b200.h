@@ -67,7 +67,7 @@ extern "C" {
 #define NRP_C_FALLBACKS     14  /* a fixed region overflowed and the batch was repeated on the exact path */
 #define NRP_C_PACKED        15  /* 1: records travelled as single 64-bit words (k-mer << value bits) | value */
 #define NRP_C_UNIFORM       16  /* 1: the part-aligned extraction kernel ran (parts of one length, packed records); 2: it also computed the palindrome / background flags */
-#define NRP_C_FILTER_WARP   17  /* 1 / 2: the warp-private duplicate filter ran (leaves of <= 800 / <= 400 records on average) */
+#define NRP_C_FILTER_WARP   17  /* 1 / 2 / 3: the warp-private duplicate filter ran (leaves of <= 800 / <= 400 records on average / room for 192 suspects) */
 #define NRP_N_COUNTS        20
 
 /* indices into nrp_result_timings() (milliseconds, CUDA events on the context's stream) */
@@ -185,7 +185,10 @@ int nrp_result_edges(nrp_ctx* ctx, uint32_t* u, uint32_t* v);
 
 /* All results of the last build in ONE call: the library copies them into its own page-locked host buffers (full-speed DMA,
  * one synchronisation) and returns pointers that stay valid until the next nrp_load_parts / nrp_build / nrp_ctx_destroy on this
- * context.  keys is NULL unless want_keys != 0; edge_u / edge_v are NULL when edges were not requested. */
+ * context.  keys is NULL unless want_keys != 0; edge_u / edge_v are NULL when edges were not requested.
+ * With the option early_fetch set (nrp_ctx_set_option; for callers that go on to fetch), a single-GPU nrp_build already starts
+ * the copies of everything that is final after its grouping stage (members, group offsets, first windows, keys, flags) beside the
+ * edge expansion; this call then moves only the rest. */
 typedef struct nrp_host_result {
   const uint8_t*  flags;         /* n_parts */
   const int64_t*  indptr;        /* n_groups + 1 */

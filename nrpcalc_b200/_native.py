@@ -274,7 +274,12 @@ class Context(object):
         bounds = np.ascontiguousarray(part_bounds, dtype=np.int64)
         _check(self._lib, self._lib.nrp_peer_open_parts(self._h, bounds.size - 1, int(my_rank), _p(blob), _p(bounds)))
 
-    def build(self, k, internal_repeats, want_edges=True):
+    def build(self, k, internal_repeats, want_edges=True, early_fetch=False):
+        """nrp_build.  early_fetch=True (callers that go on to fetch() the result): whatever is final after the grouping stage
+        starts its way to the page-locked result buffer beside the rest of the build (library option early_fetch)."""
+        if bool(early_fetch) != getattr(self, '_early_fetch', False):
+            self.set_option('early_fetch', 1 if early_fetch else 0)
+            self._early_fetch = bool(early_fetch)
         _check(self._lib, self._lib.nrp_build(self._h, int(k), 1 if internal_repeats else 0, 1 if want_edges else 0))
 
     def build_generic(self, k, internal_repeats, want_edges=True, preset_flags=None, seed=0x9E3779B97F4A7C15, attempts=6, hash_bits=0):

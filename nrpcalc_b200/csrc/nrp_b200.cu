@@ -131,6 +131,7 @@ constexpr int kMaxDirectBits = 2 * kMaxLevelBits;           // direct path: two 
 
 }  // namespace
 
+constexpr double kWarpSuspects = 56.0, kWarpSuspectsWide = 150.0;     // expected suspects per leaf the warp-private filter takes (capacity 96 / 192)
 constexpr int64_t kWarpLeafTarget = 800;     // records per leaf the warp-private filter is planned for (filter_warp.cuh)
 struct nrp_ctx {
   int device = 0;
@@ -159,10 +160,14 @@ struct nrp_ctx {
   int64_t opt_filter_wide = 1;            // packed leaves of <= 4096 records: three 256-thread CTAs per SM with 16 records per thread (half the
                                           // per-leaf fixed work per record: config 2 filter 0.437 -> 0.381 ms) when few suspects are expected;
                                           // 0 = two 512-thread CTAs
-  int64_t opt_filter_warp = 2;            // (2 = k_filter_warp2, 1 = the first version, 0 = off) packed leaves that average <= 800 records: the warp-private filter (filter_warp.cuh); the level planner
+  int64_t opt_filter_warp = 3;            // (3 = k_filter_warp3, 2 = k_filter_warp2, 1 = the first version, 0 = off) packed leaves that average <= 800 records: the warp-private filter (filter_warp.cuh); the level planner
                                           // then aims at such leaves
   int64_t opt_warp_leaf_target = kWarpLeafTarget;     // mean records per leaf the planner aims at for the warp-private filter (halved while too many suspects
                                           // are expected); <= 400 selects its small-map variant (4.2 KB per warp: 50 warps per SM instead of 30)
+  int64_t opt_early_fetch = 0;            // single-GPU build: results that are final after the grouping stage are copied to the page-locked
+                                          // result buffer beside the rest of the build (nrp_result_host finds them there).  For callers
+                                          // that fetch: config 2 end to end 3.35 -> 3.28 ms, config 3 10.1 -> 8.8 ms; the build itself
+                                          // ends later (its last count read-back queues behind the copy on PCIe), hence off by default
   int64_t opt_overlap_tail = 1;           // single-GPU build: the last-unshared-window pass runs on a second stream beside the edge expansion
   int64_t opt_fold_flags = 1;             // part-aligned kernel: palindrome test and (K == k) background probe inside the extraction instead
                                           // of a pass of their own over the parts
@@ -217,6 +222,13 @@ struct nrp_ctx {
   DevBuf e_codesA, e_codesB, e_head, e_head_scan, e_u, e_v, e_u_alt, e_v_alt, shared_keysA, shared_keysB;
   unsigned long long* h_counters = nullptr;   // pinned
   HostBuf h_upload, h_results;                // pinned staging: offsets + ids on the way in, all results on the way out
+  // early fetch (single-GPU build): everything that is final after the grouping stage (members, group offsets, first windows, keys,
+  // flags) starts its way to h_results on fetch_stream while the edge expansion and the last-unshared-window pass still run;
+  // nrp_result_host then copies only what came later.  early_* describe what is (being) copied and for which sizes.
+  cudaStream_t fetch_stream = nullptr;
+  cudaEvent_t fetch_ready = nullptr, fetch_done = nullptr;
+  bool early_valid = false;
+  int64_t early_n = 0, early_ng = 0, early_nm = 0;
 
   // shard window (whole batch unless nrp_shard_extract narrowed it)
   int64_t shard_lo = 0, shard_hi = 0, shard_tile_lo = 0, shard_tiles = 0, shard_m_max = 0;
@@ -345,6 +357,12 @@ int configure_kernels(nrp_ctx* c) {
                           (int)filter_bloom_smem<8, true, 8192, 4096, 1024>()));
   CU(cudaFuncSetAttribute((k_filter_warp<KeyT, 512, 96>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 96>))));
   CU(cudaFuncSetAttribute((k_filter_warp<KeyT, 256, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<256, 64>))));
+  CU(cudaFuncSetAttribute((k_filter_warp3<KeyT, 512, 192, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 192>))));
+  CU(cudaFuncSetAttribute((k_filter_warp3<KeyT, 512, 192, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 192>))));
+  CU(cudaFuncSetAttribute((k_filter_warp3<KeyT, 512, 96, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 96>))));
+  CU(cudaFuncSetAttribute((k_filter_warp3<KeyT, 512, 96, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 96>))));
+  CU(cudaFuncSetAttribute((k_filter_warp3<KeyT, 256, 64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<256, 64>))));
+  CU(cudaFuncSetAttribute((k_filter_warp3<KeyT, 256, 64, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<256, 64>))));
   CU(cudaFuncSetAttribute((k_filter_warp2<KeyT, 512, 96, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 96>))));
   CU(cudaFuncSetAttribute((k_filter_warp2<KeyT, 512, 96, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 96>))));
   CU(cudaFuncSetAttribute((k_filter_warp2<KeyT, 256, 64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<256, 64>))));
@@ -414,6 +432,7 @@ int nrp_ctx_destroy(nrp_ctx* c) {
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   for (auto& ch : c->chunks) cudaEventDestroy(ch.landed);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->fetch_stream) { cudaStreamSynchronize(c->fetch_stream); cudaStreamDestroy(c->fetch_stream); cudaEventDestroy(c->fetch_ready); cudaEventDestroy(c->fetch_done); }
   if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaStreamDestroy(c->aux_stream); cudaEventDestroy(c->aux_begin); cudaEventDestroy(c->aux_end); }
   if (c->h_counters) cudaFreeHost(c->h_counters);
   c->h_upload.release(); c->h_results.release();
@@ -446,7 +465,8 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "uniform_kernel") c->opt_uniform_kernel = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "fold_flags") c->opt_fold_flags = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "overlap_tail") c->opt_overlap_tail = value < 0 ? 1 : (value > 0 ? 1 : 0);
-  else if (n == "filter_warp") c->opt_filter_warp = value < 0 ? 2 : std::min<int64_t>(value, 2);
+  else if (n == "early_fetch") c->opt_early_fetch = value > 0 ? 1 : 0;
+  else if (n == "filter_warp") c->opt_filter_warp = value < 0 ? 3 : std::min<int64_t>(value, 3);
   else if (n == "warp_leaf_target") c->opt_warp_leaf_target = value <= 0 ? kWarpLeafTarget : std::min<int64_t>(value, kWarpLeafTarget);
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
   return NRP_OK;
@@ -1007,7 +1027,9 @@ DirectPlan choose_direct_plan(const nrp_ctx* c, int k, int64_t m_max, bool* pack
       int64_t total_max = 0;
       for (int i = 0; i < small.n_levels; ++i) total_max = std::max(total_max, ((int64_t)1 << small.cum[i]) * small.cap[i]);
       if (mean > (double)target || total_max >= 0xffffe000ll || !packed_fits(c, k, small.cum[0], small.bits)) break;
-      if (warp_filter_suspects(mean, shared, 512 * 32) <= 56.0) {
+      // (up to 56 expected suspects per leaf: room for 96; the third version also comes with room for 192 -- config 3, where 6 %
+      // of the records share their k-mer and two 9-bit levels cannot make the leaves smaller than ~700 records)
+      if (warp_filter_suspects(mean, shared, 512 * 32) <= (c->opt_filter_warp >= 3 ? kWarpSuspectsWide : kWarpSuspects)) {
         *warp_filter = true; *packed_out = true;
         return small;
       }
@@ -1042,14 +1064,22 @@ int launch_filter(nrp_ctx* c, bool packed, PackFmt pf, const void* leaf_keys, co
     uint32_t* over = reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED);
     uint32_t* unsrt = reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED);
     const bool tiny = mean_leaf <= 400 && warp_filter_suspects((double)mean_leaf, shared_fraction, 256 * 32) <= 36.0;
-    const size_t smem = tiny ? kFwWarps * sizeof(FwWarp<256, 64>) : kFwWarps * sizeof(FwWarp<512, 96>);
+    const bool wide = !tiny && c->opt_filter_warp >= 3 && warp_filter_suspects((double)mean_leaf, shared_fraction, 512 * 32) > kWarpSuspects;
+    const size_t smem = tiny ? kFwWarps * sizeof(FwWarp<256, 64>) : wide ? kFwWarps * sizeof(FwWarp<512, 192>) : kFwWarps * sizeof(FwWarp<512, 96>);
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (228 * 1024) / (smem + 1024)));      // 1 KB per CTA is reserved by the system
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(((int64_t)n_leaf + kFwWarps - 1) / kFwWarps, (int64_t)c->n_sms * per_sm));
 #define NRP_FW2(MAPW_, SUSP_, VHI_)                                                                                                              \
   NRP_LAUNCH((k_filter_warp2<KeyT, MAPW_, SUSP_, VHI_><<<grid, kFwThreads, smem, st>>>((const uint64_t*)leaf_keys, leaves, n_leaf, bits, pf, out_keys, \
                                                                                       out_vals, cnt + CNT_CAND, over, unsrt)))
+#define NRP_FW3(MAPW_, SUSP_, VHI_)                                                                                                              \
+  NRP_LAUNCH((k_filter_warp3<KeyT, MAPW_, SUSP_, VHI_><<<grid, kFwThreads, smem, st>>>((const uint64_t*)leaf_keys, leaves, n_leaf, bits, pf, out_keys, \
+                                                                                      out_vals, cnt + CNT_CAND, over, unsrt)))
     const bool vhi = pf.vbits >= 32;
-    if (c->opt_filter_warp >= 2) {       // record pairs, check-free batches, per-lane suspect masks
+    if (c->opt_filter_warp >= 3) {       // the leaf's k-mer bits in registers: every load issued at once, nothing read twice
+      if (tiny) { if (vhi) NRP_FW3(256, 64, true); else NRP_FW3(256, 64, false); }
+      else if (wide) { if (vhi) NRP_FW3(512, 192, true); else NRP_FW3(512, 192, false); }
+      else { if (vhi) NRP_FW3(512, 96, true); else NRP_FW3(512, 96, false); }
+    } else if (c->opt_filter_warp == 2) {       // record pairs, check-free batches, per-lane suspect masks
       if (tiny) { if (vhi) NRP_FW2(256, 64, true); else NRP_FW2(256, 64, false); }
       else { if (vhi) NRP_FW2(512, 96, true); else NRP_FW2(512, 96, false); }
     } else if (tiny)
@@ -1059,8 +1089,9 @@ int launch_filter(nrp_ctx* c, bool packed, PackFmt pf, const void* leaf_keys, co
       NRP_LAUNCH((k_filter_warp<KeyT, 512, 96><<<grid, kFwThreads, smem, st>>>((const uint64_t*)leaf_keys, leaves, n_leaf, bits, pf, out_keys, out_vals,
                                                                           cnt + CNT_CAND, over, unsrt)));
 #undef NRP_FW2
+#undef NRP_FW3
     CU(cudaGetLastError());
-    c->counts[NRP_C_FILTER_WARP] = tiny ? 2 : 1;
+    c->counts[NRP_C_FILTER_WARP] = tiny ? 2 : wide ? 3 : 1;
     return NRP_OK;
   }
   // leaves that average <= 2750 records use the half-size variant (two CTAs per SM); larger ones the full one
@@ -1646,7 +1677,7 @@ int stage_last_single(nrp_ctx* c, int k, const uint64_t* shared_keys, int64_t n_
 // hash set for at most n_codes edge codes in e_codesA, cleared; output lists e_u / e_v sized for n_codes
 int edge_set_prepare(nrp_ctx* c, int64_t n_codes, int* log_slots) {
   int ls = 6;
-  while (((int64_t)1 << ls) < 2 * n_codes) ++ls;
+  while (((int64_t)1 << ls) < n_codes + n_codes / 2) ++ls;      // load <= 2/3 (config 3: 4.2e6 pairs in 64 MB, which the L2 holds, not 128)
   TRY(c->e_codesA.ensure((size_t)8 << ls));
   TRY(c->e_u.ensure(4 * (size_t)(n_codes + 1))); TRY(c->e_v.ensure(4 * (size_t)(n_codes + 1)));
   CU(cudaMemsetAsync(c->e_codesA.ptr, 0xff, (size_t)8 << ls, c->stream));
@@ -1730,6 +1761,7 @@ void record_layout(nrp_ctx* c, int k, bool no_window = false) {
 }
 
 void begin_job(nrp_ctx* c, int k, size_t key_bytes, int want_edges, bool no_window = false) {
+  if (c->early_valid) { cudaStreamSynchronize(c->fetch_stream); c->early_valid = false; }     // an early fetch nobody collected: its sources are about to change
   memset(c->counts, 0, sizeof(c->counts));
   memset(c->timings, 0, sizeof(c->timings));
   launch_counter() = 0;
@@ -1739,6 +1771,76 @@ void begin_job(nrp_ctx* c, int k, size_t key_bytes, int want_edges, bool no_wind
   c->k = k; c->key_bytes = (int)key_bytes;
   c->have_result = false;
   record_layout(c, k, no_window);
+}
+
+// Layout of the page-locked result buffer (nrp_result_host).  The edge arrays come last, so that every other offset is known as
+// soon as the grouping stage has reported its sizes.
+struct ResultLayout {
+  size_t indptr, keys, members, fw, last, flags, eu, ev, total;
+  ResultLayout(int64_t n, int64_t ng, int64_t nm, int64_t ne) {
+    auto up = [](size_t b) { return (b + 63) & ~(size_t)63; };
+    indptr = 0; keys = indptr + up(8 * (size_t)(ng + 1)); members = keys + up(8 * (size_t)ng); fw = members + up(4 * (size_t)nm);
+    last = fw + up(4 * (size_t)ng); flags = last + up(4 * (size_t)n); eu = flags + up((size_t)n); ev = eu + up(4 * (size_t)ne);
+    total = ev + up(4 * (size_t)ne) + 64;
+  }
+};
+
+// Device-to-host copy by a few CTAs storing straight into the page-locked result buffer (mapped into the device's address space).
+// Not cudaMemcpyAsync: the copy engine that would move these 12 MB is also the one the rest of the build needs for its memsets and
+// its small count read-backs, and they queue behind the bulk copies (measured, run R: the build grew by the copies' 0.23 ms).
+struct FetchSegments {
+  const unsigned char* src[5];
+  unsigned char* dst[5];
+  size_t bytes[5];
+};
+__global__ void __launch_bounds__(256) k_fetch_to_host(FetchSegments f) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+#pragma unroll 1
+  for (int sgm = 0; sgm < 5; ++sgm) {
+    const uint4* src = reinterpret_cast<const uint4*>(f.src[sgm]);            // device buffers and result offsets are 16-byte aligned
+    uint4* dst = reinterpret_cast<uint4*>(f.dst[sgm]);
+    const size_t n16 = f.bytes[sgm] >> 4;
+    size_t i = tid;
+    for (; i + 3 * nth < n16; i += 4 * nth) {                                 // four loads in flight per thread
+      const uint4 a = src[i], b = src[i + nth], c4 = src[i + 2 * nth], d = src[i + 3 * nth];
+      dst[i] = a; dst[i + nth] = b; dst[i + 2 * nth] = c4; dst[i + 3 * nth] = d;
+    }
+    for (; i < n16; i += nth) dst[i] = src[i];
+    if (tid == 0)
+      for (size_t b = n16 << 4; b < f.bytes[sgm]; ++b) f.dst[sgm][b] = f.src[sgm][b];
+  }
+}
+
+// Start copying what the grouping stage has finished (the host knows the sizes: it has just synchronised).  The copy waits for the
+// kernels already enqueued on the build's stream (the first-window pass, when the records do not carry the window) and runs on a
+// stream of its own beside everything enqueued afterwards.
+int early_fetch_enqueue(nrp_ctx* c) {
+  c->early_valid = false;
+  if (!c->opt_early_fetch || c->external_stream || c->n_parts <= 0) return NRP_OK;
+  const int64_t n = c->n_parts, ng = c->n_groups, nm = c->n_members;
+  const int64_t ne_bound = std::min<int64_t>(std::max<int64_t>(c->n_pairs, 0), (int64_t)1 << 24);     // more edges than this: nrp_result_host re-allocates and copies everything
+  const ResultLayout L(n, ng, nm, ne_bound);
+  TRY(c->h_results.ensure(L.total));
+  unsigned char* hd = nullptr;                     // the result buffer as the device sees it
+  if (cudaHostGetDevicePointer((void**)&hd, c->h_results.ptr, 0) != cudaSuccess || hd == nullptr) { cudaGetLastError(); return NRP_OK; }
+  if (!c->fetch_stream) {
+    CU(cudaStreamCreateWithFlags(&c->fetch_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->fetch_ready, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->fetch_done, cudaEventDisableTiming));
+  }
+  FetchSegments f;
+  f.src[0] = c->g_members.as<unsigned char>(); f.dst[0] = hd + L.members; f.bytes[0] = 4 * (size_t)nm;
+  f.src[1] = c->g_indptr.as<unsigned char>(); f.dst[1] = hd + L.indptr; f.bytes[1] = 8 * (size_t)(ng + 1);
+  f.src[2] = c->g_first_window.as<unsigned char>(); f.dst[2] = hd + L.fw; f.bytes[2] = 4 * (size_t)ng;
+  f.src[3] = c->flags.as<unsigned char>(); f.dst[3] = hd + L.flags; f.bytes[3] = (size_t)n;
+  f.src[4] = c->g_keys.as<unsigned char>(); f.dst[4] = hd + L.keys; f.bytes[4] = 8 * (size_t)ng;
+  cudaStream_t fs = c->fetch_stream;
+  CU(cudaEventRecord(c->fetch_ready, c->stream));
+  CU(cudaStreamWaitEvent(fs, c->fetch_ready, 0));
+  NRP_LAUNCH((k_fetch_to_host<<<32, 256, 0, fs>>>(f)));
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->fetch_done, fs));
+  c->early_valid = true; c->early_n = n; c->early_ng = ng; c->early_nm = nm;
+  return NRP_OK;
 }
 
 template <typename KeyT>
@@ -1766,6 +1868,7 @@ int build_impl(nrp_ctx* c, int k, int internal_repeats, int want_edges) {
   group_counts_ready(c);
   finish_counts_ready(c);
   TRY(stage_first_window(c, k, tm));
+  TRY(early_fetch_enqueue(c));
   if (c->opt_overlap_tail && want_edges && c->n_pairs > 0 && !c->external_stream) {
     // The host has just synchronised: the device is idle.  The last-unshared-window pass (reads the parts, probes the shared
     // k-mers) and the edge expansion (walks the member lists) touch different buffers and neither fills the device: two streams.
@@ -2601,34 +2704,36 @@ int nrp_result_host(nrp_ctx* c, int want_keys, nrp_host_result* out) {
   if (!out) return fail(NRP_E_ARG, "null argument");
   const int64_t n = c->n_parts, ng = c->counts[NRP_C_GROUPS], nm = c->counts[NRP_C_MEMBERS];
   const int64_t ne = c->counts[NRP_C_EDGES] < 0 ? 0 : c->counts[NRP_C_EDGES];
-  auto up = [](size_t b) { return (b + 63) & ~(size_t)63; };
-  const size_t o_indptr = 0, o_keys = o_indptr + up(8 * (size_t)(ng + 1)), o_members = o_keys + up(8 * (size_t)ng),
-               o_fw = o_members + up(4 * (size_t)nm), o_last = o_fw + up(4 * (size_t)ng), o_eu = o_last + up(4 * (size_t)n),
-               o_ev = o_eu + up(4 * (size_t)ne), o_flags = o_ev + up(4 * (size_t)ne), total = o_flags + up((size_t)n) + 64;
-  TRY(c->h_results.ensure(total));
+  const ResultLayout L(n, ng, nm, ne);
+  // what the build already sent on its way (early_fetch_enqueue) is not copied again -- unless the buffer has to grow for the edges
+  bool early = c->early_valid && c->early_n == n && c->early_ng == ng && c->early_nm == nm;
+  if (early && L.total > c->h_results.cap) { CU(cudaStreamSynchronize(c->fetch_stream)); early = false; }
+  c->early_valid = false;
+  TRY(c->h_results.ensure(L.total));
   unsigned char* h = c->h_results.as<unsigned char>();
   cudaStream_t st = c->stream;
-  CU(cudaMemcpyAsync(h + o_indptr, c->g_indptr.ptr, 8 * (size_t)(ng + 1), cudaMemcpyDeviceToHost, st));
-  if (want_keys && ng > 0) CU(cudaMemcpyAsync(h + o_keys, c->g_keys.ptr, 8 * (size_t)ng, cudaMemcpyDeviceToHost, st));
-  if (nm > 0) CU(cudaMemcpyAsync(h + o_members, c->g_members.ptr, 4 * (size_t)nm, cudaMemcpyDeviceToHost, st));
-  if (ng > 0) CU(cudaMemcpyAsync(h + o_fw, c->g_first_window.ptr, 4 * (size_t)ng, cudaMemcpyDeviceToHost, st));
-  if (n > 0) {
-    CU(cudaMemcpyAsync(h + o_last, c->last_single.ptr, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h + o_flags, c->flags.ptr, (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (!early) {
+    CU(cudaMemcpyAsync(h + L.indptr, c->g_indptr.ptr, 8 * (size_t)(ng + 1), cudaMemcpyDeviceToHost, st));
+    if (want_keys && ng > 0) CU(cudaMemcpyAsync(h + L.keys, c->g_keys.ptr, 8 * (size_t)ng, cudaMemcpyDeviceToHost, st));
+    if (nm > 0) CU(cudaMemcpyAsync(h + L.members, c->g_members.ptr, 4 * (size_t)nm, cudaMemcpyDeviceToHost, st));
+    if (ng > 0) CU(cudaMemcpyAsync(h + L.fw, c->g_first_window.ptr, 4 * (size_t)ng, cudaMemcpyDeviceToHost, st));
+    if (n > 0) CU(cudaMemcpyAsync(h + L.flags, c->flags.ptr, (size_t)n, cudaMemcpyDeviceToHost, st));
   }
+  if (n > 0) CU(cudaMemcpyAsync(h + L.last, c->last_single.ptr, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
   if (ne > 0) {
-    CU(cudaMemcpyAsync(h + o_eu, c->e_u.ptr, 4 * (size_t)ne, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h + o_ev, c->e_v.ptr, 4 * (size_t)ne, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h + L.eu, c->e_u.ptr, 4 * (size_t)ne, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h + L.ev, c->e_v.ptr, 4 * (size_t)ne, cudaMemcpyDeviceToHost, st));
   }
   CU(cudaStreamSynchronize(st));
-  out->flags = h + o_flags;
-  out->indptr = reinterpret_cast<const int64_t*>(h + o_indptr);
-  out->members = reinterpret_cast<const uint32_t*>(h + o_members);
-  out->first_window = reinterpret_cast<const uint32_t*>(h + o_fw);
-  out->keys = want_keys ? reinterpret_cast<const uint64_t*>(h + o_keys) : nullptr;
-  out->last_single = reinterpret_cast<const int32_t*>(h + o_last);
-  out->edge_u = c->counts[NRP_C_EDGES] < 0 ? nullptr : reinterpret_cast<const uint32_t*>(h + o_eu);
-  out->edge_v = c->counts[NRP_C_EDGES] < 0 ? nullptr : reinterpret_cast<const uint32_t*>(h + o_ev);
+  if (early) CU(cudaEventSynchronize(c->fetch_done));
+  out->flags = h + L.flags;
+  out->indptr = reinterpret_cast<const int64_t*>(h + L.indptr);
+  out->members = reinterpret_cast<const uint32_t*>(h + L.members);
+  out->first_window = reinterpret_cast<const uint32_t*>(h + L.fw);
+  out->keys = want_keys ? reinterpret_cast<const uint64_t*>(h + L.keys) : nullptr;
+  out->last_single = reinterpret_cast<const int32_t*>(h + L.last);
+  out->edge_u = c->counts[NRP_C_EDGES] < 0 ? nullptr : reinterpret_cast<const uint32_t*>(h + L.eu);
+  out->edge_v = c->counts[NRP_C_EDGES] < 0 ? nullptr : reinterpret_cast<const uint32_t*>(h + L.ev);
   out->n_parts = n; out->n_groups = ng; out->n_members = nm; out->n_edges = ne;
   return NRP_OK;
 }

@@ -37,8 +37,8 @@
 #define NRP_V_LATE 1         // ... and their results are consumed after the reorder stores: the round trip to L2 overlaps both
 #endif
 
-#ifndef NRP_V_FLUSH_ILP
-#define NRP_V_FLUSH_ILP 1    // split_flush: eight records per thread with their shared-memory loads issued together
+#ifndef NRP_V_KEYDIG
+#define NRP_V_KEYDIG 1       // k_split_from_records on packed records: the flush takes the digit from the record, no digit array
 #endif
 
 namespace nrp {
@@ -98,7 +98,7 @@ constexpr uint32_t kNoSpace = 0xffffffffu;
 // scan the bucket counts, claim global space for each non-empty bucket with one atomic per (tile, bucket),
 // reorder the tile through shared memory and write each bucket's run contiguously.
 // peer_shift >= 0 with peers: the buffers of digit d are those of owner d >> peer_shift (peer stores over NVLink).
-template <typename KeyT, bool PACKED = false>
+template <typename KeyT, bool PACKED = false, bool KEYDIG = false>
 __device__ __forceinline__ void split_reorder(SplitSmem<KeyT, PACKED>& s, const KeyT (&key)[kSplitItems], const uint32_t (&val)[kSplitItems],
                                               const uint32_t (&dr)[kSplitItems], int nb, uint32_t* cursor, RegionLimit lim) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -128,9 +128,9 @@ __device__ __forceinline__ void split_reorder(SplitSmem<KeyT, PACKED>& s, const 
     if (lane == kWarps - 1) s.total = tin;
   }
   __syncthreads();
+  const uint32_t base = s.warp_sums[wid] + inc - c;
   // one atomic per (tile, bucket) claims the run's place; its result is needed by the flush only, so (NRP_V_LATE) it is
   // consumed after the reorder stores and the round trip to L2 overlaps them
-  const uint32_t base = s.warp_sums[wid] + inc - c;
   auto publish = [&]() {
     uint32_t dl = g - base + (uint32_t)kSplitTile;     // biased by the tile size: never wraps, never equals kNoSpace
     if (lim.cap) {
@@ -152,7 +152,7 @@ __device__ __forceinline__ void split_reorder(SplitSmem<KeyT, PACKED>& s, const 
       const uint32_t pos = s.base[d] + (dr[e] & 0xffffu);
       s.keys[pos] = key[e];
       if (!PACKED) s.vals[pos] = val[e];
-      s.dig[pos] = (uint16_t)d;
+      if (!KEYDIG) s.dig[pos] = (uint16_t)d;      // (KEYDIG: the flush reads the digit off the record itself)
     }
   }
   if (NRP_V_LATE && claims) publish();
@@ -164,42 +164,6 @@ template <typename KeyT, bool PACKED = false>
 __device__ __forceinline__ void split_flush(SplitSmem<KeyT, PACKED>& s, KeyT* out_keys, uint32_t* out_vals, const PeerBuffers* peers = nullptr,
                                             int peer_shift = 0) {
   const uint32_t total = s.total;
-#if NRP_V_FLUSH_ILP
-  // eight records per thread with their shared-memory loads issued together: digit, then the digit's displacement, then the record
-  // (as a loop over i += blockDim the three dependent loads of ONE record were all a thread had in flight)
-  uint32_t dl[kSplitItems];
-#pragma unroll
-  for (int e = 0; e < kSplitItems; ++e) {
-    const uint32_t i = threadIdx.x + (uint32_t)e * kSplitThreads;
-    dl[e] = i < total ? (uint32_t)s.dig[i] : 0u;
-  }
-#pragma unroll
-  for (int e = 0; e < kSplitItems; ++e) {
-    const uint32_t i = threadIdx.x + (uint32_t)e * kSplitThreads;
-    const uint32_t d = dl[e];
-    dl[e] = i < total ? s.delta[d] : kNoSpace;
-  }
-  if (peers) {                                     // digit d lives in its owner's receive buffer (peer store over NVLink)
-#pragma unroll
-    for (int e = 0; e < kSplitItems; ++e) {
-      const uint32_t i = threadIdx.x + (uint32_t)e * kSplitThreads;
-      if (dl[e] == kNoSpace) continue;
-      const uint32_t o = (uint32_t)s.dig[i] >> peer_shift;
-      const uint32_t dst = i + dl[e] - (uint32_t)kSplitTile;
-      reinterpret_cast<KeyT*>(peers->keys[o])[dst] = s.keys[i];
-      if (!PACKED) peers->vals[o][dst] = s.vals[i];
-    }
-  } else {
-#pragma unroll
-    for (int e = 0; e < kSplitItems; ++e) {
-      const uint32_t i = threadIdx.x + (uint32_t)e * kSplitThreads;
-      if (dl[e] == kNoSpace) continue;
-      const uint32_t dst = i + dl[e] - (uint32_t)kSplitTile;
-      out_keys[dst] = s.keys[i];
-      if (!PACKED) out_vals[dst] = s.vals[i];
-    }
-  }
-#else
   for (uint32_t i = threadIdx.x; i < total; i += kSplitThreads) {
     const uint32_t d = s.dig[i];
     const uint32_t dl = s.delta[d];
@@ -214,7 +178,20 @@ __device__ __forceinline__ void split_flush(SplitSmem<KeyT, PACKED>& s, KeyT* ou
       if (!PACKED) out_vals[dst] = s.vals[i];
     }
   }
-#endif
+}
+
+// The flush for packed records whose word still holds the digit of this level (every level but the first): the digit is the bit
+// field (key >> key_shift) & key_mask of the record the flush loads anyway -- no digit array, one scattered 16-bit store and one
+// load less per record in shared memory, whose pipe these kernels keep busy (~20 wavefronts per 32 records).
+template <typename KeyT, bool PACKED>
+__device__ __forceinline__ void split_flush_keydigit(SplitSmem<KeyT, PACKED>& s, KeyT* out_keys, int key_shift, uint32_t key_mask) {
+  const uint32_t total = s.total;
+  for (uint32_t i = threadIdx.x; i < total; i += kSplitThreads) {
+    const KeyT kv = s.keys[i];
+    const uint32_t dl = s.delta[(uint32_t)((uint64_t)kv >> key_shift) & key_mask];
+    if (dl == kNoSpace) continue;
+    out_keys[i + dl - (uint32_t)kSplitTile] = kv;
+  }
 }
 
 // ---- histogram of leaf buckets straight from the part buffer (exact path) ---------------------------------
@@ -446,13 +423,14 @@ __global__ void __launch_bounds__(kSplitThreads, 2) k_split_from_records(const K
     __syncthreads();
     RegionLimit tile_lim = lim;
     tile_lim.first = child0;
-    split_reorder<KeyT, PACKED>(s, key, val, dr, 1 << r2, cursor + child0, tile_lim);
+    split_reorder<KeyT, PACKED, PACKED && NRP_V_KEYDIG>(s, key, val, dr, 1 << r2, cursor + child0, tile_lim);
     d4 = next;
     if (tile + gridDim.x < n_tiles) {
       load_tile(d4);
       if (tile + 2 * gridDim.x < n_tiles) next = __ldg(tile_desc + tile + 2 * gridDim.x);
     }
-    split_flush<KeyT, PACKED>(s, out_keys, out_vals);
+    if (PACKED && NRP_V_KEYDIG) split_flush_keydigit<KeyT, PACKED>(s, out_keys, packed_shift, mask);
+    else split_flush<KeyT, PACKED>(s, out_keys, out_vals);
     __syncthreads();
   }
 }

@@ -122,7 +122,7 @@ def _device_build(ctx, structure, ascii_buf, offsets, global_p, ids, k, internal
             structure.counts['generic_retries'] += ctx.build_generic(k, internal_repeats, want_edges=want_edges, preset_flags=preset)
             structure.counts['generic_builds'] += 1
         else:
-            ctx.build(k, internal_repeats, want_edges=want_edges)
+            ctx.build(k, internal_repeats, want_edges=want_edges, early_fetch=True)      # fetched right below
         res = ctx.fetch(want_keys=False)
         flags, indptr, members, first_window, last_single = res.flags, res.indptr, res.members, res.first_window, res.last_single
         structure.records += res.counts['records']

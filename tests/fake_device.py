@@ -121,7 +121,7 @@ class ModelContext(object):
         self.result = _native.BuildResult(counts, {name: 0.0 for name in _native.TIMING_NAMES}, spec['flags'], indptr, members, first_window, None,
                                           spec['last_single'], edges)
 
-    def build(self, k, internal_repeats, want_edges=True):
+    def build(self, k, internal_repeats, want_edges=True, early_fetch=False):
         assert 1 <= k <= 32, 'nrp_build: k outside [1, 32]'
         assert all(set(s) <= set('ACGT') for _, s in self.uniq), 'nrp_build: characters outside A/C/G/T'
         self.calls.append(('build', k))

@@ -16,6 +16,9 @@ length = int(os.environ.get('NRP_PROFILE_LEN', '100'))
 buf, off = cases.random_dna_buffer(n, length, 2)
 ids = np.arange(n, dtype=np.uint32)[::-1].copy()
 ctx = _native.Context(0)
+for item in os.environ.get('NRP_PROFILE_OPTS', '').split(','):       # library knobs name=value,...
+    if item:
+        ctx.set_option(item.split('=')[0], int(item.split('=')[1]))
 bg = int(os.environ.get('NRP_PROFILE_BG', '0'))          # bp of a random background genome (K = k)
 if bg:
     from nrpcalc_b200 import encoding

@@ -82,7 +82,9 @@ def main():
     traffic = {}
     for name, d in agg.items():
         short = name.split('::')[-1].split('<')[0]
-        if short in ('k_hist_from_ascii', 'k_split_uniform', 'k_split_from_ascii', 'k_split_from_records', 'k_filter', 'k_filter_bloom', 'k_flag_windows') and d['n']:
+        if short.startswith('k_filter_warp'):
+            short = 'k_filter_warp'                  # every version of the warp-private filter under one name (bench.py looks it up)
+        if short in ('k_hist_from_ascii', 'k_split_uniform', 'k_split_from_ascii', 'k_split_from_records', 'k_filter', 'k_filter_bloom', 'k_filter_warp', 'k_flag_windows') and d['n']:
             traffic[short] = int((d['rd'] + d['wr']) / d['n'])
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     blob = json.load(open(tpath)) if os.path.exists(tpath) else {}
