@@ -160,7 +160,7 @@ struct nrp_ctx {
   int64_t opt_filter_wide = 1;            // packed leaves of <= 4096 records: three 256-thread CTAs per SM with 16 records per thread (half the
                                           // per-leaf fixed work per record: config 2 filter 0.437 -> 0.381 ms) when few suspects are expected;
                                           // 0 = two 512-thread CTAs
-  int64_t opt_filter_warp = 3;            // (3 = k_filter_warp3, 2 = k_filter_warp2, 1 = the first version, 0 = off) packed leaves that average <= 800 records: the warp-private filter (filter_warp.cuh); the level planner
+  int64_t opt_filter_warp = 1;            // packed leaves that average <= 800 records: the warp-private filter (filter_warp.cuh); the level planner
                                           // then aims at such leaves
   int64_t opt_warp_leaf_target = kWarpLeafTarget;     // mean records per leaf the planner aims at for the warp-private filter (halved while too many suspects
                                           // are expected); <= 400 selects its small-map variant (4.2 KB per warp: 50 warps per SM instead of 30)
@@ -355,18 +355,12 @@ int configure_kernels(nrp_ctx* c) {
                           (int)filter_bloom_smem<8, true, 4096, 2048, 256>()));
   CU(cudaFuncSetAttribute((k_filter_bloom<KeyT, kFilterThreads, 8, 4096, 1, 1024, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)filter_bloom_smem<8, true, 8192, 4096, 1024>()));
-  CU(cudaFuncSetAttribute((k_filter_warp<KeyT, 512, 96>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 96>))));
-  CU(cudaFuncSetAttribute((k_filter_warp<KeyT, 256, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<256, 64>))));
-  CU(cudaFuncSetAttribute((k_filter_warp3<KeyT, 512, 192, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 192>))));
-  CU(cudaFuncSetAttribute((k_filter_warp3<KeyT, 512, 192, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 192>))));
-  CU(cudaFuncSetAttribute((k_filter_warp3<KeyT, 512, 96, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 96>))));
-  CU(cudaFuncSetAttribute((k_filter_warp3<KeyT, 512, 96, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 96>))));
-  CU(cudaFuncSetAttribute((k_filter_warp3<KeyT, 256, 64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<256, 64>))));
-  CU(cudaFuncSetAttribute((k_filter_warp3<KeyT, 256, 64, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<256, 64>))));
-  CU(cudaFuncSetAttribute((k_filter_warp2<KeyT, 512, 96, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 96>))));
-  CU(cudaFuncSetAttribute((k_filter_warp2<KeyT, 512, 96, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 96>))));
-  CU(cudaFuncSetAttribute((k_filter_warp2<KeyT, 256, 64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<256, 64>))));
-  CU(cudaFuncSetAttribute((k_filter_warp2<KeyT, 256, 64, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<256, 64>))));
+  CU(cudaFuncSetAttribute((k_filter_warp<KeyT, 512, 192, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 192>))));
+  CU(cudaFuncSetAttribute((k_filter_warp<KeyT, 512, 192, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 192>))));
+  CU(cudaFuncSetAttribute((k_filter_warp<KeyT, 512, 96, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 96>))));
+  CU(cudaFuncSetAttribute((k_filter_warp<KeyT, 512, 96, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<512, 96>))));
+  CU(cudaFuncSetAttribute((k_filter_warp<KeyT, 256, 64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<256, 64>))));
+  CU(cudaFuncSetAttribute((k_filter_warp<KeyT, 256, 64, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFwWarps * sizeof(FwWarp<256, 64>))));
   CU(cudaFuncSetAttribute((k_split_uniform<false, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
   CU(cudaFuncSetAttribute((k_split_uniform<true, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
   CU(cudaFuncSetAttribute((k_split_uniform<false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
@@ -466,7 +460,7 @@ int nrp_ctx_set_option(nrp_ctx* c, const char* name, int64_t value) {
   else if (n == "fold_flags") c->opt_fold_flags = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "overlap_tail") c->opt_overlap_tail = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "early_fetch") c->opt_early_fetch = value > 0 ? 1 : 0;
-  else if (n == "filter_warp") c->opt_filter_warp = value < 0 ? 3 : std::min<int64_t>(value, 3);
+  else if (n == "filter_warp") c->opt_filter_warp = value < 0 ? 1 : (value > 0 ? 1 : 0);
   else if (n == "warp_leaf_target") c->opt_warp_leaf_target = value <= 0 ? kWarpLeafTarget : std::min<int64_t>(value, kWarpLeafTarget);
   else return fail(NRP_E_ARG, "unknown option '%s'", name);
   return NRP_OK;
@@ -1027,9 +1021,9 @@ DirectPlan choose_direct_plan(const nrp_ctx* c, int k, int64_t m_max, bool* pack
       int64_t total_max = 0;
       for (int i = 0; i < small.n_levels; ++i) total_max = std::max(total_max, ((int64_t)1 << small.cum[i]) * small.cap[i]);
       if (mean > (double)target || total_max >= 0xffffe000ll || !packed_fits(c, k, small.cum[0], small.bits)) break;
-      // (up to 56 expected suspects per leaf: room for 96; the third version also comes with room for 192 -- config 3, where 6 %
-      // of the records share their k-mer and two 9-bit levels cannot make the leaves smaller than ~700 records)
-      if (warp_filter_suspects(mean, shared, 512 * 32) <= (c->opt_filter_warp >= 3 ? kWarpSuspectsWide : kWarpSuspects)) {
+      // (up to 56 expected suspects per leaf: room for 96; up to 150: the variant with room for 192 -- config 3, where 6 % of the
+      // records share their k-mer and two 9-bit levels cannot make the leaves smaller than ~700 records)
+      if (warp_filter_suspects(mean, shared, 512 * 32) <= kWarpSuspectsWide) {
         *warp_filter = true; *packed_out = true;
         return small;
       }
@@ -1064,32 +1058,18 @@ int launch_filter(nrp_ctx* c, bool packed, PackFmt pf, const void* leaf_keys, co
     uint32_t* over = reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED);
     uint32_t* unsrt = reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED);
     const bool tiny = mean_leaf <= 400 && warp_filter_suspects((double)mean_leaf, shared_fraction, 256 * 32) <= 36.0;
-    const bool wide = !tiny && c->opt_filter_warp >= 3 && warp_filter_suspects((double)mean_leaf, shared_fraction, 512 * 32) > kWarpSuspects;
+    const bool wide = !tiny && warp_filter_suspects((double)mean_leaf, shared_fraction, 512 * 32) > kWarpSuspects;
     const size_t smem = tiny ? kFwWarps * sizeof(FwWarp<256, 64>) : wide ? kFwWarps * sizeof(FwWarp<512, 192>) : kFwWarps * sizeof(FwWarp<512, 96>);
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (228 * 1024) / (smem + 1024)));      // 1 KB per CTA is reserved by the system
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(((int64_t)n_leaf + kFwWarps - 1) / kFwWarps, (int64_t)c->n_sms * per_sm));
-#define NRP_FW2(MAPW_, SUSP_, VHI_)                                                                                                              \
-  NRP_LAUNCH((k_filter_warp2<KeyT, MAPW_, SUSP_, VHI_><<<grid, kFwThreads, smem, st>>>((const uint64_t*)leaf_keys, leaves, n_leaf, bits, pf, out_keys, \
-                                                                                      out_vals, cnt + CNT_CAND, over, unsrt)))
-#define NRP_FW3(MAPW_, SUSP_, VHI_)                                                                                                              \
-  NRP_LAUNCH((k_filter_warp3<KeyT, MAPW_, SUSP_, VHI_><<<grid, kFwThreads, smem, st>>>((const uint64_t*)leaf_keys, leaves, n_leaf, bits, pf, out_keys, \
-                                                                                      out_vals, cnt + CNT_CAND, over, unsrt)))
-    const bool vhi = pf.vbits >= 32;
-    if (c->opt_filter_warp >= 3) {       // the leaf's k-mer bits in registers: every load issued at once, nothing read twice
-      if (tiny) { if (vhi) NRP_FW3(256, 64, true); else NRP_FW3(256, 64, false); }
-      else if (wide) { if (vhi) NRP_FW3(512, 192, true); else NRP_FW3(512, 192, false); }
-      else { if (vhi) NRP_FW3(512, 96, true); else NRP_FW3(512, 96, false); }
-    } else if (c->opt_filter_warp == 2) {       // record pairs, check-free batches, per-lane suspect masks
-      if (tiny) { if (vhi) NRP_FW2(256, 64, true); else NRP_FW2(256, 64, false); }
-      else { if (vhi) NRP_FW2(512, 96, true); else NRP_FW2(512, 96, false); }
-    } else if (tiny)
-      NRP_LAUNCH((k_filter_warp<KeyT, 256, 64><<<grid, kFwThreads, smem, st>>>((const uint64_t*)leaf_keys, leaves, n_leaf, bits, pf, out_keys, out_vals,
-                                                                          cnt + CNT_CAND, over, unsrt)));
-    else
-      NRP_LAUNCH((k_filter_warp<KeyT, 512, 96><<<grid, kFwThreads, smem, st>>>((const uint64_t*)leaf_keys, leaves, n_leaf, bits, pf, out_keys, out_vals,
-                                                                          cnt + CNT_CAND, over, unsrt)));
-#undef NRP_FW2
-#undef NRP_FW3
+#define NRP_FW(MAPW_, SUSP_, VHI_)                                                                                                              \
+  NRP_LAUNCH((k_filter_warp<KeyT, MAPW_, SUSP_, VHI_><<<grid, kFwThreads, smem, st>>>((const uint64_t*)leaf_keys, leaves, n_leaf, bits, pf, out_keys, \
+                                                                                     out_vals, cnt + CNT_CAND, over, unsrt)))
+    const bool vhi = pf.vbits >= 32;       // where the stored k-mer bits begin: in the high word of the record, or below it
+    if (tiny) { if (vhi) NRP_FW(256, 64, true); else NRP_FW(256, 64, false); }
+    else if (wide) { if (vhi) NRP_FW(512, 192, true); else NRP_FW(512, 192, false); }
+    else { if (vhi) NRP_FW(512, 96, true); else NRP_FW(512, 96, false); }
+#undef NRP_FW
     CU(cudaGetLastError());
     c->counts[NRP_C_FILTER_WARP] = tiny ? 2 : wide ? 3 : 1;
     return NRP_OK;

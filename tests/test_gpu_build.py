@@ -197,7 +197,7 @@ def test_unpacked_when_key_and_value_exceed_64_bits(ctx):
     _compare(res, uniq, 32, False)
 
 
-@pytest.mark.parametrize('warp', [3, 2, 1, 0])
+@pytest.mark.parametrize('warp', [1, 0])
 def test_warp_private_filter(ctx, warp):
     """The warp-private duplicate filter (filter_warp.cuh: leaves of a few hundred records, one warp each) against the CTA-per-leaf
     variants and the oracle: random parts (both map sizes), planted repeats (leaves with more suspects than a warp takes are passed
@@ -205,7 +205,7 @@ def test_warp_private_filter(ctx, warp):
     try:
         ctx.set_option('filter_warp', warp)
         seen = set()
-        # (k = 21 / 23: the k-mer bits of a record start below bit 32 of the word -- the other addressing of the second version)
+        # (k = 21 / 23: the k-mer bits of a record start below bit 32 of the word -- the kernel's other addressing)
         for n, length, k, internal, target in ((20000, 100, 17, False, 0), (60000, 100, 17, False, 0), (9000, 100, 13, False, 0),
                                                (30000, 60, 16, True, 0), (20000, 100, 21, False, 0), (40000, 100, 17, False, 300),
                                                (15000, 90, 23, True, 250), (2500, 33, 17, False, 100),
@@ -218,7 +218,7 @@ def test_warp_private_filter(ctx, warp):
             _compare(res, uniq, k, internal)
         ctx.set_option('warp_leaf_target', 0)
         if warp:
-            assert seen <= {1, 2, 3} and seen and (warp < 3 or 3 in seen)
+            assert seen == {1, 2, 3}              # standard, small-map and many-suspect variants all ran
         planted = _long_parts(cases.planted_parts(3000, 12) + cases.random_parts(12000, 100, 13), 17)
         res = _run(ctx, planted, 17, False)
         _compare(res, planted, 17, False)
