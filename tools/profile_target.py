@@ -25,7 +25,7 @@ if bg:
     gbuf, goff = encoding.join_parts([cases.random_genome(bg, 33)])
     ctx.bg_build(gbuf, goff, k, install=True)
 ctx.load_parts(buf, off, ids)
-for _ in range(int(os.environ.get('NRP_PROFILE_BUILDS', '2'))):
+for _ in range(int(os.environ.get("NRP_PROFILE_BUILDS", "2"))):
     ctx.build(k, False, True)
 print(ctx.counts())
 print(ctx.timings())
