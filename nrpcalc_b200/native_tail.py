@@ -246,19 +246,36 @@ def _cover_self_check():
 
 
 def cover_usable():
-    """True when libnrptail.so has the cover routines and they agree with vercov.py on this interpreter (checked once)."""
+    """True when libnrptail.so has the cover routines and they agree with vercov.py on this interpreter.  Checked once per process;
+    a passed check is remembered as a second line of the stamp file next to the library (same key as usable(): interpreter
+    version, networkx version, a digest of the library) -- the check costs 0.6 s, more than a 100k-part job."""
     if not _cover_state['checked']:
         _cover_state['checked'] = True
         lib = _load()
         if lib is None or not hasattr(lib, 'nrp_tail_cover'):
             _cover_state['usable'], _cover_state['why'] = False, 'libnrptail.so without cover routines'
         else:
+            stamp = LIB_PATH + '.ok'
+            key = None
+            try:
+                key = _verdict_key()
+                if os.path.exists(stamp) and open(stamp).read().split('\n')[:2] == [key, 'cover ok']:
+                    _cover_state['usable'], _cover_state['why'] = True, 'ok (remembered)'
+                    return True
+            except OSError:
+                key = None
             try:
                 _cover_state['usable'], _cover_state['why'] = _cover_self_check()
             except Exception as exc:
                 _cover_state['usable'], _cover_state['why'] = False, 'self-check raised {!r}'.format(exc)
             if not _cover_state['usable']:
                 sys.stderr.write('nrpcalc_b200: native cover routines disabled ({}); the Python routines run\n'.format(_cover_state['why']))
+            elif key is not None and usable():             # (the first line of the stamp is the array tail's own verdict)
+                try:
+                    with open(stamp, 'w') as fh:
+                        fh.write(key + '\ncover ok')
+                except OSError:
+                    pass
     return _cover_state['usable']
 
 
@@ -329,13 +346,17 @@ def _self_check():
 
 
 def _verdict_key():
-    st = os.stat(LIB_PATH)
-    return '{}|{}|{}|{}'.format(sys.version, nx.__version__, st.st_size, int(st.st_mtime))
+    """What a remembered verdict is valid for: this interpreter, this networkx, this library (by content: a copy of the tree to
+    another machine with the same image keeps the verdict; size and time stamp would not)."""
+    import hashlib
+    with open(LIB_PATH, 'rb') as fh:
+        digest = hashlib.sha1(fh.read()).hexdigest()
+    return '{}|{}|{}'.format(sys.version, nx.__version__, digest)
 
 
 def usable():
     """True when the library is built and its set model matches this interpreter.  Checked once per process; a passed check
-    is remembered next to the library (keyed by interpreter version, networkx version and the library's size and time stamp)."""
+    is remembered next to the library (keyed by interpreter version, networkx version and a digest of the library)."""
     if not _state['checked']:
         _state['checked'] = True
         if _load() is None:
@@ -344,7 +365,7 @@ def usable():
         stamp = LIB_PATH + '.ok'
         try:
             key = _verdict_key()
-            if os.path.exists(stamp) and open(stamp).read() == key:
+            if os.path.exists(stamp) and open(stamp).read().split('\n')[0] == key:
                 _state['usable'], _state['why'] = True, 'ok (remembered)'
                 return True
         except OSError:

@@ -406,3 +406,51 @@ def test_adjlist_file_from_arrays_equals_networkx(tmp_path):
     assert len(open(str(tmp_path / 'mine.txt')).read().splitlines()) == len(open(str(tmp_path / 'nx.txt')).read().splitlines())
     reread = nx.read_adjlist(str(tmp_path / 'mine.txt'), nodetype=int)
     assert sorted(reread.edges()) == sorted(tuple(sorted(e)) for e in graph.edges()) or set(map(frozenset, reread.edges())) == set(map(frozenset, graph.edges()))
+
+
+def test_self_check_verdicts_are_remembered_by_library_content(tmp_path, monkeypatch):
+    """The first-use self-checks of libnrptail.so (array tail, cover routines) cost more than a 100k-part job; a passed check is
+    remembered next to the library under a key of interpreter, networkx and the library's CONTENT -- a copied tree keeps it, another
+    library (or a stale stamp) is checked again."""
+    import shutil
+    from nrpcalc_b200 import native_tail
+    if not native_tail.usable():
+        pytest.skip('libnrptail.so not built')
+    lib_copy = tmp_path / 'libnrptail.so'
+    shutil.copy(native_tail.LIB_PATH, lib_copy)
+    os.utime(lib_copy, (1, 1))                                   # another time stamp: the key must not care
+    key_here = native_tail._verdict_key()
+    monkeypatch.setattr(native_tail, 'LIB_PATH', str(lib_copy))
+    assert native_tail._verdict_key() == key_here
+    calls = {'tail': 0, 'cover': 0}
+    real_tail, real_cover = native_tail._self_check, native_tail._cover_self_check
+
+    def counted_tail():
+        calls['tail'] += 1
+        return real_tail()
+
+    def counted_cover():
+        calls['cover'] += 1
+        return real_cover()
+
+    monkeypatch.setattr(native_tail, '_self_check', counted_tail)
+    monkeypatch.setattr(native_tail, '_cover_self_check', counted_cover)
+
+    def fresh_process():
+        monkeypatch.setattr(native_tail, '_state', {'checked': False, 'usable': False, 'why': ''})
+        monkeypatch.setattr(native_tail, '_cover_state', {'checked': False, 'usable': False, 'why': ''})
+
+    stamp = str(lib_copy) + '.ok'
+    fresh_process()                                              # no stamp: both checks run, both verdicts are written
+    assert native_tail.usable() and native_tail.cover_usable() and calls == {'tail': 1, 'cover': 1}
+    assert open(stamp).read().split('\n') == [key_here, 'cover ok']
+    fresh_process()                                              # stamp present: nothing runs
+    assert native_tail.usable() and native_tail.cover_usable() and calls == {'tail': 1, 'cover': 1}
+    with open(stamp, 'w') as fh:                                 # a round-1 stamp (tail only): the cover check runs once more
+        fh.write(key_here)
+    fresh_process()
+    assert native_tail.usable() and native_tail.cover_usable() and calls == {'tail': 1, 'cover': 2}
+    with open(stamp, 'w') as fh:                                 # a stamp of another library: everything is checked again
+        fh.write('something else\ncover ok')
+    fresh_process()
+    assert native_tail.usable() and native_tail.cover_usable() and calls == {'tail': 2, 'cover': 3}
