@@ -701,6 +701,7 @@ static int load_parts_impl(nrp_ctx* c, const uint8_t* ascii, const int64_t* offs
   if (copy_lo > copy_hi || copy_hi > n_parts) return fail(NRP_E_ARG, "bad staging range");
   CU(cudaSetDevice(c->device));
   c->have_parts = false; c->have_result = false;
+  if (c->early_valid) { CU(cudaStreamSynchronize(c->fetch_stream)); c->early_valid = false; }     // an early fetch nobody collected still reads the old result
   auto first_byte = [&](int64_t part) -> int64_t { return hinted ? part * uniform_hint : offsets[part]; };
   const int64_t range_lo = first_byte(copy_lo), range_hi = first_byte(copy_hi);     // bytes that travel
   // the big copy goes first: the DMA runs while the host validates the offsets and stages the small arrays
@@ -1054,7 +1055,7 @@ int launch_filter(nrp_ctx* c, bool packed, PackFmt pf, const void* leaf_keys, co
   cudaStream_t st = c->stream;
   unsigned long long* cnt = c->counters.as<unsigned long long>();
   if (warp_filter && packed) {
-    // small leaves, one warp each (filter_warp.cuh): as many 8-warp CTAs per SM as shared memory allows
+    // small leaves, one warp each (filter_warp.cuh): as many ten-warp CTAs per SM as shared memory allows
     uint32_t* over = reinterpret_cast<uint32_t*>(cnt + CNT_OVERSIZED);
     uint32_t* unsrt = reinterpret_cast<uint32_t*>(cnt + CNT_UNSORTED);
     const bool tiny = mean_leaf <= 400 && warp_filter_suspects((double)mean_leaf, shared_fraction, 256 * 32) <= 36.0;

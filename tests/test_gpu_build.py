@@ -445,3 +445,46 @@ def test_long_key_runs_fall_back_from_the_walk_grouping(ctx, internal):
     uniq = _long_parts(parts, 17)
     res = _run(ctx, uniq, 17, internal)
     _compare(res, uniq, 17, internal)
+
+
+@pytest.mark.parametrize('k,internal', [(13, False), (17, True), (25, False)])
+def test_early_fetch_gives_the_same_host_result(ctx, k, internal):
+    """Option early_fetch (nrp_build starts copying what is final after the grouping stage into the page-locked result buffer,
+    nrp_result_host moves only the rest): the same arrays as the plain fetch -- also when a build's early fetch is never collected
+    (the next load / build waits for it) and when the buffer has to grow for the next batch."""
+    def fetched(uniq, early):
+        seqs = [s for _, s in uniq]
+        ids = np.array([pid for pid, _ in uniq], dtype=np.uint32)
+        offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum([len(s) for s in seqs], out=offsets[1:])
+        ctx.load_parts(np.frombuffer(''.join(seqs).encode(), dtype=np.uint8), offsets, ids)
+        ctx.build(k, internal, want_edges=True, early_fetch=early)
+        return ctx.fetch(want_keys=True, copy=True)
+
+    def groups_of(r):          # (the order of the groups differs from build to build: leaves finish in any order)
+        return sorted((int(r.keys[g]), int(r.first_window[g]), tuple(r.members[r.indptr[g]:r.indptr[g + 1]].tolist()))
+                      for g in range(r.counts['groups']))
+
+    def same(a, b):
+        assert a.counts['groups'] == b.counts['groups'] and a.counts['members'] == b.counts['members']
+        assert np.array_equal(a.flags, b.flags) and np.array_equal(a.last_single, b.last_single)
+        assert a.indptr[0] == 0 and a.indptr[-1] == a.counts['members'] and a.indptr.size == a.counts['groups'] + 1
+        assert groups_of(a) == groups_of(b)
+        assert sorted(zip(a.edges[0].tolist(), a.edges[1].tolist())) == sorted(zip(b.edges[0].tolist(), b.edges[1].tolist()))
+
+    try:
+        small = _long_parts(cases.planted_parts(900, 5) + cases.random_parts(2000, 100, 6), k)
+        large = _long_parts(cases.planted_parts(4000, 7) + cases.random_parts(30000, 100, 8), k)
+        plain_small, plain_large = fetched(small, False), fetched(large, False)
+        same(fetched(small, True), plain_small)
+        _compare(fetched(small, True), small, k, internal)
+        same(fetched(large, True), plain_large)                  # larger batch: the result buffer grows
+        ctx.build(k, internal, want_edges=True, early_fetch=True)    # an early fetch nobody collects ...
+        ctx.build(k, internal, want_edges=True, early_fetch=True)    # ... the next build waits for it
+        same(ctx.fetch(want_keys=True, copy=True), plain_large)
+        ctx.build(k, internal, want_edges=True, early_fetch=True)    # ... and so does the next load
+        same(fetched(small, True), plain_small)
+        same(fetched(small, False), plain_small)
+    finally:
+        ctx.set_option('early_fetch', 0)
+        ctx._early_fetch = False
