@@ -163,7 +163,8 @@ struct nrp_ctx {
   int64_t opt_filter_warp = 1;            // packed leaves that average <= 800 records: the warp-private filter (filter_warp.cuh); the level planner
                                           // then aims at such leaves
   int64_t opt_warp_leaf_target = kWarpLeafTarget;     // mean records per leaf the planner aims at for the warp-private filter (halved while too many suspects
-                                          // are expected); <= 400 selects its small-map variant (4.2 KB per warp: 50 warps per SM instead of 30)
+                                          // are expected); <= 400 selects its small-map variant (4.2 KB per warp).  Smaller is not faster:
+                                          // config 2 with 2^18 leaves of 320 records, filter 0.30 -> 0.39 ms (r02p)
   int64_t opt_early_fetch = 0;            // single-GPU build: results that are final after the grouping stage are copied to the page-locked
                                           // result buffer beside the rest of the build (nrp_result_host finds them there).  For callers
                                           // that fetch: config 2 end to end 3.35 -> 3.28 ms, config 3 10.1 -> 8.8 ms; the build itself
