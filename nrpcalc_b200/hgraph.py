@@ -28,6 +28,7 @@ There is no CPU fallback: without the CUDA library or a GPU the call raises.
 import os
 import sys
 from collections import defaultdict, deque
+from operator import itemgetter
 from time import time
 
 import networkx as nx
@@ -204,8 +205,8 @@ def repeat_structure(parts, background, homology, internal_repeats, ctx=None, wa
     """Run the device path over the processing-ordered [(id, SEQ)] list.  Returns (RepeatStructure, ids)."""
     ctx = ctx or _context()
     n = len(parts)
-    ids = np.fromiter((pid for pid, _ in parts), dtype=np.uint32, count=n)
-    seqs = [seq for _, seq in parts]
+    ids = np.fromiter(map(itemgetter(0), parts), dtype=np.uint32, count=n)
+    seqs = list(map(itemgetter(1), parts))
     ascii_buf, offsets = encoding.join_parts(seqs)
     lengths = np.diff(offsets)
     structure = RepeatStructure(n)
@@ -467,7 +468,7 @@ def _build_structure(seq_list, background, homology, internal_repeats, seq_file,
 
     t0 = time()
     with open(seq_file, 'w') as outfile:
-        outfile.write(''.join('{},{}\n'.format(pid, seq) for pid, seq in parts))
+        outfile.write(''.join(['%d,%s\n' % part for part in parts]))
     if verbose:
         print('\nWritten {} unique sequences out to {} in {:2.4} seconds'.format(unq_seqs, seq_file, time() - t0))
 
