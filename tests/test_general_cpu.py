@@ -76,3 +76,20 @@ def test_host_background_flags_cover_only_what_the_device_cannot_decide(model):
     structure, _ = hgraph.repeat_structure(uniq, bg, 9, True)
     assert (structure.flags != 0).tolist() == [True, True, False, True]
     bg.drop()
+
+
+def test_join_parts_and_alphabet_check():
+    """encoding.join_parts / all_acgt (the routing decision between the 2-bit kernels and the general path): the answer by
+    bytes.translate on the joined bytes equals the table look-up on a copy, for both cases, other symbols, empty parts, no parts;
+    text outside ASCII is refused."""
+    from nrpcalc_b200 import encoding
+    for seqs, want in ((['ACGT', 'acgt', 'AAAA'], True), (['ACGT', 'ACNT'], False), (['ACGU'], False), (['AC-T'], False),
+                       ([], True), ([''], True), (['', 'ACGT', ''], True), (['ACGT' * 1000, 'T' * 33], True), (['ACGT' * 1000 + 'R'], False)):
+        buf, off = encoding.join_parts(seqs)
+        assert off.tolist() == np.concatenate(([0], np.cumsum([len(s) for s in seqs]))).astype(int).tolist()
+        assert bytes(buf) == ''.join(seqs).encode()
+        assert encoding.all_acgt(buf) is want                        # a view of the joined bytes: translate
+        assert encoding.all_acgt(buf.copy()) is want                 # any other array: the table
+        assert encoding.all_acgt(buf[:max(0, buf.size - 1)]) in (True, False)
+    with pytest.raises(ValueError):
+        encoding.join_parts(['ACGÄ'])
